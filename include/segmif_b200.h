@@ -1,0 +1,191 @@
+/* segmif_b200 -- C ABI of the B200 (sm_100a) kernels behind the SegMiF hot path.
+ *
+ * The reference (JinyuanLiu-CV/SegMiF) has no FFI layer: its hot path is a set of PyTorch
+ * nn.Module.forward() methods whose arithmetic is implicit ATen/cuDNN/cuBLAS calls.  Each entry
+ * point below replaces one such implicit library call (or a fused chain of them); the comment on
+ * every function names the reference call site(s) it replaces as <file>:<lines> relative to the
+ * SegMiF repository root.  The Python mirror of the reference classes (segmif_b200/core/*.py)
+ * binds these symbols with ctypes (segmif_b200/_lib.py); INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *  - plain pointers + sizes only; all pointers are DEVICE pointers unless stated otherwise;
+ *    no allocation, no synchronisation and no global state inside (outputs and workspaces are
+ *    caller allocated); every launch goes to the stream passed in (a cudaStream_t cast to void*),
+ *    which must be the stream the caller orders its other work on.
+ *  - return value: 0 on success, negative SEGMIF_ERR_* otherwise; segmif_last_error() returns a
+ *    thread-local message for the last failure.
+ *  - "tokens"/NHWC: activations are pixel-major [B, H, W, C] (equivalently [B, N, C] tokens, the
+ *    layout MiT uses between blocks).  `ld` arguments are the channel pitch of one pixel in
+ *    ELEMENTS, `coff` a channel offset inside that pitch: this is how DRDB's dense concatenation
+ *    and the decoder / conv2 concatenations are written in place with no torch.cat.
+ *  - dtypes are SEGMIF_F32 / SEGMIF_BF16 storage; all arithmetic accumulates in fp32.
+ */
+#ifndef SEGMIF_B200_H_
+#define SEGMIF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SEGMIF_ABI_VERSION 1
+
+typedef void* segmif_stream_t; /* cudaStream_t */
+
+enum { SEGMIF_F32 = 0, SEGMIF_BF16 = 1 };
+enum { SEGMIF_ACT_NONE = 0, SEGMIF_ACT_RELU = 1, SEGMIF_ACT_PRELU = 2, SEGMIF_ACT_GELU = 3 };
+enum {
+  SEGMIF_OK = 0,
+  SEGMIF_ERR_INVALID = -1,  /* bad argument / unsupported shape */
+  SEGMIF_ERR_CUDA = -2,     /* CUDA runtime or launch failure  */
+  SEGMIF_ERR_DEVICE = -3    /* not an sm_100 device            */
+};
+
+int segmif_abi_version(void);
+const char* segmif_last_error(void);
+/* Checks that `device` is compute capability 10.x and raises the dynamic shared-memory limits of
+ * the kernels.  Must be called once per process per device before any other entry point. */
+int segmif_init(int device);
+
+/* ---- K2: LayerNorm over the last dim --------------------------------------------------------
+ * replaces nn.LayerNorm call sites: core/mix_transformer.py:152-153 (Block.norm1/2, eps 1e-6),
+ * :101 (Attention.norm, 1e-5), :196 (OverlapPatchEmbed.norm, 1e-5), :320,328,336,344 (stage norms).
+ * x [rows, C] -> y [rows, C]; gamma/beta fp32 [C]; C % 32 == 0, C <= 1024. */
+int segmif_layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, void* y, int y_dtype,
+                         int64_t rows, int C, float eps, segmif_stream_t stream);
+
+/* ---- K1/K3/K4/K9/K10/K11/K12: implicit-GEMM convolution / linear layer on tensor cores --------
+ * One entry point for every dense contraction on the path (weights pre-packed [Cout][KH*KW][Cin] bf16):
+ *   nn.Linear   core/mix_transformer.py:96,102,112 (q, kv, proj), :47,51 (fc1, fc2);
+ *               core/segformer_head.py:23 (linear_c*), :77-80 (linear_fuse 1x1 conv + folded BN + ReLU,
+ *               linear_pred);                                    -> KH=KW=1, B=1, H=1, W=rows
+ *   nn.Conv2d   core/mix_transformer.py:193 (patch_embed2-4, k3 s2 p1), :100 (Attention.sr, k=s=sr);
+ *               core/model_fusion.py:135-151 (DRDB Dcov1-5, k3 pad2 dil2 + ReLU, written in place into the
+ *               224-channel growth buffer), :155-156 (DRDB 1x1 + ReLU + residual), :1063-1064 (conv2, conv21
+ *               + shared PReLU).
+ * dst[m, dst_coff+n] = residual[m, res_coff+n] + act( bias[n] + sum_{tap,c} src[pix(m,tap), src_coff+c] * w[n,tap,c] )
+ * with m = (b, oy, ox) row-major over [B, Ho, Wo] and out-of-image taps reading zero.  Cin % 32 == 0. */
+typedef struct {
+  const void* src;        /* bf16 [B, H, W, ld_src]                                   */
+  const void* weight;     /* bf16 [Cout, KH*KW, Cin]                                  */
+  const float* bias;      /* fp32 [Cout] or NULL                                      */
+  const float* prelu_alpha; /* device scalar, read only when act == SEGMIF_ACT_PRELU  */
+  const void* residual;   /* [M, ld_res] or NULL, added after the activation          */
+  void* dst;              /* [M, ld_dst]                                              */
+  int B, H, W, Cin, ld_src, src_coff;
+  int KH, KW, stride, pad, dil, Ho, Wo, Cout;
+  int act;
+  int res_dtype, ld_res, res_coff;
+  int dst_dtype, ld_dst, dst_coff;
+} segmif_conv_params;
+int segmif_conv_fwd(const segmif_conv_params* p, segmif_stream_t stream);
+
+/* ---- K1 (stage 1): 7x7 stride-4 pad-3 patch embedding + LayerNorm --------------------------------
+ * replaces core/mix_transformer.py:192-198 for patch_embed1, fused with the input affine of
+ * Network3.forward core/model_fusion.py:1083-1085 (x*255 - mean)/std  (pass scale=1, shift=0 otherwise).
+ * img fp32 NCHW [B,3,H,W]; w fp32 [147][C0] (tap-major: (c*7+ky)*7+kx); tokens fp32 [B, Ho*Wo, C0]. */
+int segmif_patch_embed7_ln_fwd(const float* img, const float* w, const float* bias, const float* gamma,
+                               const float* beta, float eps, const float* in_scale3, const float* in_shift3,
+                               float* tokens, int B, int H, int W, int C0, segmif_stream_t stream);
+
+/* ---- K5: spatial-reduction attention core  softmax(q k^T * scale) v ------------------------------
+ * replaces core/mix_transformer.py:107-111 (scores are never materialised).
+ * q bf16 [B, N, ldq] (head h at columns h*D..), k/v bf16 [B, Nk, ldkv], out bf16 [B, N, ldo]; D in {32, 64}. */
+int segmif_sr_attention_fwd(const void* q, int ldq, const void* k, const void* v, int ldkv, void* out, int ldo,
+                            int B, int heads, int N, int Nk, int D, float scale, segmif_stream_t stream);
+
+/* ---- K6: depthwise 3x3 (pad 1, bias) + GELU(erf) on tokens -----------------------------------------
+ * replaces core/mix_transformer.py:381-387 (DWConv) + :49 (act).  x,y bf16 [B,H,W,C]; w fp32 [9][C]. */
+int segmif_dwconv3x3_gelu_fwd(const void* x, const float* w9c, const float* bias, void* y, int B, int H, int W,
+                              int C, segmif_stream_t stream);
+
+/* ---- K8: bilinear resize, align_corners=False, pixel-major --------------------------------------------
+ * replaces F.interpolate at core/mix_transformer.py:364-373, core/segformer_head.py:67-73. */
+int segmif_bilinear_nhwc_fwd(const void* src, int src_dtype, int B, int h, int w, int C, int ld_src, void* dst,
+                             int dst_dtype, int H, int W, int ld_dst, int dst_coff, segmif_stream_t stream);
+
+/* ---- K8+K19: bilinear upsample of class logits fused with argmax (labels bit-exact, lowest index wins ties)
+ * replaces test_segmentation.py:170-175.  logits fp32 [B,h,w,nc] pixel-major -> labels int64 [B,H,W]. */
+int segmif_upsample_argmax_fwd(const float* logits, int B, int h, int w, int nc, int64_t* labels, int H, int W,
+                               segmif_stream_t stream);
+
+/* ---- layout converters at the module boundary (NCHW fp32 is the reference's interface layout) -------- */
+int segmif_nhwc_to_nchw(const void* src, int src_dtype, int ld_src, int src_coff, float* dst, int B, int HW, int C,
+                        segmif_stream_t stream);
+int segmif_nchw_to_nhwc(const float* src, void* dst, int dst_dtype, int ld_dst, int dst_coff, int B, int HW, int C,
+                        segmif_stream_t stream);
+
+/* ---- K11 (edge layers): 3x3 pad-1 convs with 1 input or 1 output channel + shared PReLU --------------
+ * conv1_ir / conv1_vis  core/model_fusion.py:1051-1052,1055-1056: plane fp32 [B,H,W] (channel 0 of an NCHW
+ *   tensor with batch stride `bstride` elements) -> bf16 [B,H,W,ld_dst] channels coff..coff+63; w fp32 [9][64].
+ * conv22               core/model_fusion.py:1065: bf16 [B,H,W,32] -> fp32 [B,1,H,W]; w fp32 [9][32]. */
+int segmif_conv3x3_in1_fwd(const float* plane, int64_t bstride, const float* w, const float* bias,
+                           const float* prelu_alpha, void* dst, int ld_dst, int dst_coff, int B, int H, int W,
+                           int Cout, segmif_stream_t stream);
+int segmif_conv3x3_out1_fwd(const void* src, int ld_src, const float* w, const float* bias, const float* prelu_alpha,
+                            float* dst, int B, int H, int W, int Cin, segmif_stream_t stream);
+
+/* ---- K13: hierarchical interactive attention (FeatureFusionModule / CrossPath) -----------------------
+ * replaces core/model_fusion.py:453-463 -> :350-361 -> :263-288 (MoAM) and :303-328 (SoAM), two passes:
+ *  (1) gram:  G_s = sum_pixels p_s^T p_s  for p_1 = y1, p_2 = y2 (first halves of relu(channel_proj1/2)),
+ *             p_3 = u3 (second half of relu(channel_proj3 o conv3|conv4)); because the kv Linears have no
+ *             bias, k^T v = Wk G Wv^T, so the 8x8 per-head contexts need only these 64x64 Gram matrices.
+ *             partials fp32 [B, nchunk, 3, 64, 64] are reduced deterministically by (2).
+ *  (2) ctx:   softmax_{dim=-2}(k^T v * 8^-1/2) per head, folded with end_proj into four 64x64 bf16 matrices
+ *             per batch item:  folded [B, 4, 64(out), 64(in)] = {Mz1, Mv1, Mz2, Mv2}.
+ *  (3) apply: out_i = LayerNorm(x_i + y3 Mz_i + u_i Mv_i + b_end_i), written pixel-major (ld/coff).
+ * x1,x2: bf16 [B,HW,ld] 64 channels; x3: bf16 [B,HW,ld3] with C3 in {64,128} channels.
+ * wproj: bf16 packed by the host: [w1y 64x64][w2y 64x64][w3u 64xC3] for gram and
+ *        [w3y 64xC3][w1u 64x64][w2u 64x64] for apply (rows = output channel, K-major); bproj fp32 [3][64]. */
+int segmif_ffm_gram_fwd(const void* x1, int ld1, int coff1, const void* x2, int ld2, int coff2, const void* x3,
+                        int ld3, int C3, const void* wproj, const float* bproj, float* partials, int nchunk, int B,
+                        int64_t HW, segmif_stream_t stream);
+int segmif_ffm_ctx_fwd(const float* partials, int nchunk, const float* wkv /* fp32 [3][128][64]: kv1, kv2, kv3 */,
+                       const float* wend /* fp32 [2][64][128] */, void* folded /* bf16 [B,4,64,64] */,
+                       float* ctx_out /* fp32 [B,3,8,8,8] or NULL */, int B, segmif_stream_t stream);
+int segmif_ffm_apply_fwd(const void* x1, int ld1, int coff1, const void* x2, int ld2, int coff2, const void* x3,
+                         int ld3, int C3, const void* wproj, const float* bproj, const void* folded,
+                         const float* bend /* [2][64] */, const float* ln_gamma /* [2][64] */,
+                         const float* ln_beta /* [2][64] */, float eps, void* out1, int ldo1, int coffo1, void* out2,
+                         int ldo2, int coffo2, int B, int64_t HW, segmif_stream_t stream);
+
+/* ---- K14: colour transforms (NCHW fp32) ------------------------------------------------------------------
+ * replaces core/model_fusion.py:69-92 (RGB2YCrCb), :94-111 (YCrCb2RGB) and the recompose chain
+ * train.py:364-366 / test_fusion.py:102-111 (replace Y by the fused image, back to RGB, clamp to [0,1]). */
+int segmif_rgb2ycrcb(const float* rgb, float* ycc, int B, int64_t HW, segmif_stream_t stream);
+int segmif_ycrcb2rgb(const float* ycc, float* rgb, int B, int64_t HW, segmif_stream_t stream);
+int segmif_recompose_rgb(const float* fused_y, const float* vis_rgb, float* rgb_out, int clamp01, int B, int64_t HW,
+                         segmif_stream_t stream);
+
+/* ---- K15-K18: fusion losses, forward (fp32 NCHW single-channel planes [B,1,H,W]) --------------------------
+ * Each writes per-block partial sums into `workspace` and reduces them (in fp64, fixed order) into `out`.
+ * ssim      pytorch_ssim/__init__.py:19-43  out[0] = mean ssim (size_average) or out[b] per image.
+ * laploss2  lap_loss.py:112-118             out[0] = 10*(L1_3 + L1_5) + L1_7 against max(res(ir), res(vis)).
+ * laploss   lap_loss.py:93-98               out[0] likewise against res(target).
+ * entropy   core/Entropy.py:15-56           out[0] = sum over patches and batch of -sum p log p.
+ * sobel_l1  core/loss.py:471-475 + :647-650 out[0] = mean |x - y|, out[1] = mean | sobel(x) - sobel(y) |.
+ * mse_l1    F.mse_loss / F.l1_loss          out[0] = mean (x-y)^2, out[1] = mean |x - y|.                  */
+size_t segmif_loss_workspace_bytes(int B, int H, int W);
+int segmif_ssim_fwd(const float* img1, const float* img2, int B, int H, int W, int per_image, float* workspace,
+                    float* out, segmif_stream_t stream);
+int segmif_laploss2_fwd(const float* inp, const float* ir, const float* vis, int B, int H, int W, float* workspace,
+                        float* out, segmif_stream_t stream);
+int segmif_laploss_fwd(const float* inp, const float* target, int B, int H, int W, float* workspace, float* out,
+                       segmif_stream_t stream);
+int segmif_entropy_fwd(const float* img, int B, int H, int W, int patch, float* workspace, float* out,
+                       segmif_stream_t stream);
+int segmif_sobel_l1_fwd(const float* x, const float* y, int B, int H, int W, float* workspace, float* out,
+                        segmif_stream_t stream);
+int segmif_mse_l1_fwd(const float* x, const float* y, int64_t n, float* workspace, float* out,
+                      segmif_stream_t stream);
+/* CE(ignore_index) over bilinearly upsampled logits: core/model_fusion.py:1095-1096 + train.py:156.
+ * logits fp32 [B,h,w,nc] pixel-major, labels int64 [B,H,W]; out[0] = mean over non-ignored pixels. */
+int segmif_upsample_ce_fwd(const float* logits, int B, int h, int w, int nc, const int64_t* labels, int H, int W,
+                           int ignore_index, float* workspace, float* out, segmif_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEGMIF_B200_H_ */

@@ -1,0 +1,116 @@
+"""ctypes binding of libsegmif_b200.so (the C ABI declared in include/segmif_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or the device is not an sm_100
+part, importing the ops fails with a RuntimeError that says how to build it.  Nothing here (or anywhere
+in the package) imports `oracle/`.
+"""
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsegmif_b200.so")
+
+c_void_p, c_int, c_int64, c_float, c_size_t, c_char_p = (
+    ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_size_t, ctypes.c_char_p)
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_RELU, ACT_PRELU, ACT_GELU = 0, 1, 2, 3
+
+
+class ConvParams(ctypes.Structure):
+    """Mirror of segmif_conv_params (include/segmif_b200.h)."""
+    _fields_ = [
+        ("src", c_void_p), ("weight", c_void_p), ("bias", c_void_p), ("prelu_alpha", c_void_p),
+        ("residual", c_void_p), ("dst", c_void_p),
+        ("B", c_int), ("H", c_int), ("W", c_int), ("Cin", c_int), ("ld_src", c_int), ("src_coff", c_int),
+        ("KH", c_int), ("KW", c_int), ("stride", c_int), ("pad", c_int), ("dil", c_int), ("Ho", c_int),
+        ("Wo", c_int), ("Cout", c_int),
+        ("act", c_int),
+        ("res_dtype", c_int), ("ld_res", c_int), ("res_coff", c_int),
+        ("dst_dtype", c_int), ("ld_dst", c_int), ("dst_coff", c_int),
+    ]
+
+
+P = c_void_p
+# name -> argtypes; every function returns int except where noted in _RESTYPES
+SIGNATURES = {
+    "segmif_abi_version": [],
+    "segmif_last_error": [],
+    "segmif_init": [c_int],
+    "segmif_layernorm_fwd": [P, c_int, P, P, P, c_int, c_int64, c_int, c_float, P],
+    "segmif_conv_fwd": [ctypes.POINTER(ConvParams), P],
+    "segmif_patch_embed7_ln_fwd": [P, P, P, P, P, c_float, P, P, P, c_int, c_int, c_int, c_int, P],
+    "segmif_sr_attention_fwd": [P, c_int, P, P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P],
+    "segmif_dwconv3x3_gelu_fwd": [P, P, P, P, c_int, c_int, c_int, c_int, P],
+    "segmif_bilinear_nhwc_fwd": [P, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, P],
+    "segmif_upsample_argmax_fwd": [P, c_int, c_int, c_int, c_int, P, c_int, c_int, P],
+    "segmif_nhwc_to_nchw": [P, c_int, c_int, c_int, P, c_int, c_int, c_int, P],
+    "segmif_nchw_to_nhwc": [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P],
+    "segmif_conv3x3_in1_fwd": [P, c_int64, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P],
+    "segmif_conv3x3_out1_fwd": [P, c_int, P, P, P, P, c_int, c_int, c_int, c_int, P],
+    "segmif_ffm_gram_fwd": [P, c_int, c_int, P, c_int, c_int, P, c_int, c_int, P, P, P, c_int, c_int, c_int64, P],
+    "segmif_ffm_ctx_fwd": [P, c_int, P, P, P, P, c_int, P],
+    "segmif_ffm_apply_fwd": [P, c_int, c_int, P, c_int, c_int, P, c_int, c_int, P, P, P, P, P, P, c_float,
+                             P, c_int, c_int, P, c_int, c_int, c_int, c_int64, P],
+    "segmif_rgb2ycrcb": [P, P, c_int, c_int64, P],
+    "segmif_ycrcb2rgb": [P, P, c_int, c_int64, P],
+    "segmif_recompose_rgb": [P, P, P, c_int, c_int, c_int64, P],
+    "segmif_loss_workspace_bytes": [c_int, c_int, c_int],
+    "segmif_ssim_fwd": [P, P, c_int, c_int, c_int, c_int, P, P, P],
+    "segmif_laploss2_fwd": [P, P, P, c_int, c_int, c_int, P, P, P],
+    "segmif_laploss_fwd": [P, P, c_int, c_int, c_int, P, P, P],
+    "segmif_entropy_fwd": [P, c_int, c_int, c_int, c_int, P, P, P],
+    "segmif_sobel_l1_fwd": [P, P, c_int, c_int, c_int, P, P, P],
+    "segmif_mse_l1_fwd": [P, P, c_int64, P, P, P],
+    "segmif_upsample_ce_fwd": [P, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, P, P, P],
+}
+_RESTYPES = {"segmif_last_error": c_char_p, "segmif_loss_workspace_bytes": c_size_t}
+
+_lib = None
+_lock = threading.Lock()
+_inited = set()
+launch_count = 0          # kernels-launching entry points called so far (bench.py reports the delta)
+
+
+def load():
+    """Returns the loaded CDLL; raises if the library has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(
+                    f"segmif_b200: {LIB_PATH} is missing. Build it with `python -m segmif_b200.build` "
+                    "(needs nvcc; sm_100a only). There is no CPU or PyTorch fallback.")
+            lib = ctypes.CDLL(LIB_PATH)
+            for name, argtypes in SIGNATURES.items():
+                fn = getattr(lib, name)          # AttributeError here == header/library mismatch
+                fn.argtypes = argtypes
+                fn.restype = _RESTYPES.get(name, c_int)
+            if lib.segmif_abi_version() != 1:
+                raise RuntimeError("segmif_b200: ABI version mismatch between _lib.py and the shared library")
+            _lib = lib
+    return _lib
+
+
+def last_error():
+    return load().segmif_last_error().decode()
+
+
+def check(rc, what=""):
+    if rc != 0:
+        raise RuntimeError(f"segmif_b200 {what} failed (code {rc}): {last_error()}")
+
+
+def ensure_init(device_index):
+    if device_index not in _inited:
+        check(load().segmif_init(int(device_index)), "segmif_init")
+        _inited.add(device_index)
+
+
+def call(name, *args):
+    global launch_count
+    launch_count += 1
+    check(getattr(load(), name)(*args), name)

@@ -1,0 +1,381 @@
+"""Segmentation wrapper (WeTr / Network3), fusion network (Fusion_Network3_ac, DRDB) and hierarchical
+interactive attention (FeatureFusionModule / CrossPath / CrossAttention[2]) with the reference's class,
+attribute and state_dict surface (core/model_fusion.py of SegMiF), computed by the segmif_b200 kernels.
+
+Full-resolution feature maps live pixel-major in bf16.  A DRDB owns one [B, H, W, 224] growth buffer: the
+five dilated convs append their 32 channels in place (torch.cat never runs) and the 1x1 conv reads all 224.
+conv3 / conv4 on the segmentation features are folded into channel_proj3 on the host (both are linear and
+nothing sits between them), so the FFM kernels read the upsampled encoder features directly.
+"""
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..ops import ACT_PRELU, ACT_RELU
+from ..packing import PackCache
+from . import mix_transformer
+from .mix_transformer import _reference_init
+from .segformer_head import SegFormerHead
+
+IMAGENET_MEAN = [123.675, 116.28, 103.53]
+IMAGENET_STD = [58.395, 57.12, 57.375]
+
+
+def _no_autograd(module, *tensors):
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
+        raise NotImplementedError(
+            f"segmif_b200: {type(module).__name__} was asked for gradients, but only the forward kernels exist so "
+            "far (backward is the next row of the build plan). Wrap the call in torch.no_grad().")
+
+
+def _pixel_major_bf16(x):
+    """Logical NCHW tensor -> (pixel-major bf16 storage [B, HW, C], C).  Zero-copy when `x` already is a
+    channels_last bf16 view (what MixVisionTransformer.forward_fusion returns); otherwise one convert kernel."""
+    B, C, H, W = x.shape
+    if x.dtype == torch.bfloat16 and x.permute(0, 2, 3, 1).is_contiguous():
+        return x.permute(0, 2, 3, 1).reshape(B, H * W, C)
+    return ops.nchw_to_nhwc(x.float().contiguous(), out_dtype=torch.bfloat16)
+
+
+# ------------------------------------------------------------------------------------------------ colour
+def RGB2YCrCb(input_im):
+    """core/model_fusion.py:69-92 (device-agnostic: runs on the input's device)."""
+    return ops.rgb2ycrcb(input_im.float().contiguous())
+
+
+def YCrCb2RGB(input_im):
+    """core/model_fusion.py:94-111."""
+    return ops.ycrcb2rgb(input_im.float().contiguous())
+
+
+# ------------------------------------------------------------------------------------------------ segmentation
+class WeTr(nn.Module):
+    """core/model_fusion.py:9-68."""
+
+    def __init__(self, backbone, num_classes=20, embedding_dim=256, pretrained=None):
+        super().__init__()
+        self.num_classes = num_classes
+        self.embedding_dim = embedding_dim
+        self.backbone = backbone
+        self.feature_strides = [4, 8, 16, 32]
+        self.encoder = getattr(mix_transformer, backbone)()
+        self.in_channels = self.encoder.embed_dims
+        if pretrained:
+            self.initialize()
+        self.decoder = SegFormerHead(feature_strides=self.feature_strides, in_channels=self.in_channels,
+                                     embedding_dim=self.embedding_dim, num_classes=self.num_classes)
+        # kept for state_dict / optimizer-group parity; its output is discarded by the reference (:66) so it never runs
+        self.classifier = nn.Conv2d(in_channels=self.in_channels[-1], out_channels=self.num_classes, kernel_size=1,
+                                    bias=False)
+
+    def initialize(self):
+        state_dict = torch.load('pretrained/' + self.backbone + '.pth')
+        state_dict.pop('head.weight')
+        state_dict.pop('head.bias')
+        self.encoder.load_state_dict(state_dict)
+
+    def get_param_groups(self):
+        groups = [[], [], []]
+        for name, param in list(self.encoder.named_parameters()):
+            groups[1 if "norm" in name else 0].append(param)
+        for param in list(self.decoder.parameters()):
+            groups[2].append(param)
+        groups[2].append(self.classifier.weight)
+        return groups
+
+    def forward_pixel_major(self, x, in_scale=None, in_shift=None):
+        """fp32 logits [B, H/4, W/4, nc], pixel-major (what the fused upsample+argmax / CE kernels consume)."""
+        stages = self.encoder.forward_stages(x, in_scale, in_shift)
+        return self.decoder.forward_tokens(stages)
+
+    def forward(self, x):
+        _no_autograd(self, x)
+        lg = self.forward_pixel_major(x)
+        B, h, w, nc = lg.shape
+        return ops.nhwc_to_nchw(lg, B, h * w, nc).view(B, nc, h, w)
+
+
+class Network3(nn.Module):
+    """core/model_fusion.py:1068-1104.  The x*255 / ImageNet mean-std normalisation is fused into patch_embed1."""
+
+    def __init__(self, backbone, num_classes=20, embedding_dim=256, pretrained=True):
+        super().__init__()
+        self.fusion_nums = 2
+        self.seg_nums = 2
+        self.fusion_channel = 48
+        self.seg_channel = 64
+        self.denoise_net = WeTr(backbone, num_classes, embedding_dim, pretrained)
+        self.mean = IMAGENET_MEAN
+        self.std = IMAGENET_STD
+        self._affine = {}
+
+    def _input_affine(self, device):
+        key = (device, tuple(self.mean), tuple(self.std))
+        if key not in self._affine:
+            std = torch.tensor(self.std, dtype=torch.float64)
+            mean = torch.tensor(self.mean, dtype=torch.float64)
+            self._affine = {key: ((255.0 / std).float().to(device), (-mean / std).float().to(device))}
+        return self._affine[key]
+
+    def logits_pixel_major(self, fused_seg1):
+        sc, sh = self._input_affine(fused_seg1.device)
+        return self.denoise_net.forward_pixel_major(fused_seg1, sc, sh)
+
+    def forward(self, fused_seg1):
+        _no_autograd(self, fused_seg1)
+        lg = self.logits_pixel_major(fused_seg1)
+        B, h, w, nc = lg.shape
+        seg_map = ops.nhwc_to_nchw(lg, B, h * w, nc).view(B, nc, h, w)
+        return fused_seg1, fused_seg1, seg_map
+
+    def predict_labels(self, fused_seg1, size=None):
+        """Extension: test_segmentation.py:169-175 in one call -- logits, bilinear upsample and argmax fused;
+        the [B, nc, H, W] upsampled logits are never materialised."""
+        lg = self.logits_pixel_major(fused_seg1)
+        B, h, w, nc = lg.shape
+        H, W = size if size is not None else fused_seg1.shape[2:]
+        return ops.upsample_argmax(lg, B, h, w, nc, H, W)
+
+    def _loss(self, fused_seg1, label, criterion):
+        """core/model_fusion.py:1090-1097 for criterion = CrossEntropyLoss(ignore_index=...): upsample + CE fused."""
+        _no_autograd(self, fused_seg1)
+        if not isinstance(criterion, nn.CrossEntropyLoss) or criterion.weight is not None \
+                or criterion.reduction != "mean" or getattr(criterion, "label_smoothing", 0.0) != 0.0:
+            raise NotImplementedError("segmif_b200: _loss supports plain mean CrossEntropyLoss(ignore_index=...) only")
+        lg = self.logits_pixel_major(fused_seg1)
+        B, h, w, nc = lg.shape
+        return ops.upsample_ce(lg, B, h, w, nc, label.long().contiguous(), criterion.ignore_index)
+
+    def enhance_net_parameters(self):
+        return self.enhance_net.parameters()
+
+    def denoise_net_parameters(self):
+        return self.denoise_net.parameters()
+
+
+Network = Network3     # core/__init__.py:4 of the reference imports a `Network` that does not exist there
+
+
+# ------------------------------------------------------------------------------------------------ DRDB
+class DRDB(nn.Module):
+    """Dilated residual dense block (core/model_fusion.py:117-157)."""
+    GROWTH_LD = 224
+
+    def __init__(self, in_ch=64, growth_rate=32):
+        super().__init__()
+        c = in_ch
+        for i in range(1, 6):
+            setattr(self, f"Dcov{i}", nn.Conv2d(c, growth_rate, 3, padding=2, dilation=2))
+            c += growth_rate
+        self.conv = nn.Conv2d(c, in_ch, 1, padding=0)
+        self.in_ch, self.growth, self.total = in_ch, growth_rate, c
+        self._packs = PackCache()
+
+    def forward_buffer(self, buf, B, H, W, out=None, ld_dst=None, dst_coff=0):
+        """`buf` bf16 [B, H, W, total] with the block input in channels 0..in_ch; appends the five growth slices
+        in place, then writes x + relu(conv1x1(all)) to `out` (pixel-major bf16)."""
+        ld = buf.shape[-1]
+        cin = self.in_ch
+        for i in range(1, 6):
+            cv = getattr(self, f"Dcov{i}")
+            ops.conv(buf, self._packs.conv(cv.weight), cv.bias.detach(), B=B, H=H, W=W, Cin=cin, ld_src=ld, KH=3, KW=3,
+                     pad=2, dil=2, Cout=self.growth, act=ACT_RELU, out=buf.view(-1, ld), ld_dst=ld, dst_coff=cin)
+            cin += self.growth
+        return ops.conv(buf, self._packs.conv(self.conv.weight), self.conv.bias.detach(), B=B, H=H, W=W, Cin=cin,
+                        ld_src=ld, Cout=self.in_ch, act=ACT_RELU, residual=buf.view(-1, ld), ld_res=ld, res_coff=0,
+                        out=out, ld_dst=ld_dst, dst_coff=dst_coff)
+
+    def forward(self, x):
+        _no_autograd(self, x)
+        B, C, H, W = x.shape
+        buf = torch.empty((B, H, W, self.total), dtype=torch.bfloat16, device=x.device)
+        ops.nchw_to_nhwc(x.float().contiguous(), out=buf.view(B, H * W, self.total), ld_dst=self.total)
+        y = self.forward_buffer(buf, B, H, W)
+        return ops.nhwc_to_nchw(y, B, H * W, C).view(B, C, H, W)
+
+
+# ------------------------------------------------------------------------------------------------ HIA
+class CrossAttention(nn.Module):
+    """MoAM parameters (core/model_fusion.py:250-262); the computation lives in CrossPath's fused kernels."""
+
+    def __init__(self, dim, num_heads=8, qkv_bias=False, qk_scale=None):
+        super().__init__()
+        assert dim % num_heads == 0, f"dim {dim} should be divided by num_heads {num_heads}."
+        self.dim = dim
+        self.num_heads = num_heads
+        self.scale = qk_scale or (dim // num_heads) ** -0.5
+        self.kv3 = nn.Linear(dim, dim * 2, bias=qkv_bias)
+
+
+class CrossAttention2(nn.Module):
+    """SoAM parameters (core/model_fusion.py:290-302)."""
+
+    def __init__(self, dim, num_heads=8, qkv_bias=False, qk_scale=None):
+        super().__init__()
+        assert dim % num_heads == 0, f"dim {dim} should be divided by num_heads {num_heads}."
+        self.dim = dim
+        self.num_heads = num_heads
+        self.scale = qk_scale or (dim // num_heads) ** -0.5
+        self.kv1 = nn.Linear(dim, dim * 2, bias=qkv_bias)
+        self.kv2 = nn.Linear(dim, dim * 2, bias=qkv_bias)
+
+
+class CrossPath(nn.Module):
+    """core/model_fusion.py:329-361."""
+
+    def __init__(self, dim, reduction=1, num_heads=8, norm_layer=nn.LayerNorm):
+        super().__init__()
+        if dim != 64 or reduction != 1 or num_heads != 8:
+            raise NotImplementedError("segmif_b200: the HIA kernels are specialised for dim=64, 8 heads (the only "
+                                      "configuration Fusion_Network3_ac instantiates)")
+        self.channel_proj1 = nn.Linear(dim, dim // reduction * 2)
+        self.channel_proj2 = nn.Linear(dim, dim // reduction * 2)
+        self.channel_proj3 = nn.Linear(dim, dim // reduction * 2)
+        self.act1 = nn.ReLU(inplace=True)
+        self.act2 = nn.ReLU(inplace=True)
+        self.act3 = nn.ReLU(inplace=True)
+        self.cross_attn = CrossAttention(dim // reduction, num_heads=num_heads)
+        self.cross_attn2 = CrossAttention2(dim // reduction, num_heads=num_heads)
+        self.end_proj1 = nn.Linear(dim // reduction * 2, dim)
+        self.end_proj2 = nn.Linear(dim // reduction * 2, dim)
+        self.norm1 = norm_layer(dim)
+        self.norm2 = norm_layer(dim)
+        self._packs = PackCache()
+
+    def packs(self, pre_conv=None):
+        """Kernel operand packs; `pre_conv` (a 1x1 nn.Conv2d applied to the segmentation features before this
+        module, i.e. conv3 / conv4) is folded into channel_proj3."""
+        plist = [self.channel_proj1.weight, self.channel_proj1.bias, self.channel_proj2.weight,
+                 self.channel_proj2.bias, self.channel_proj3.weight, self.channel_proj3.bias,
+                 self.cross_attn2.kv1.weight, self.cross_attn2.kv2.weight, self.cross_attn.kv3.weight,
+                 self.end_proj1.weight, self.end_proj1.bias, self.end_proj2.weight, self.end_proj2.bias,
+                 self.norm1.weight, self.norm1.bias, self.norm2.weight, self.norm2.bias]
+        if pre_conv is not None:
+            plist += [pre_conv.weight, pre_conv.bias]
+
+        def build(w1, b1, w2, b2, w3, b3, kv1, kv2, kv3, we1, be1, we2, be2, g1, n1, g2, n2, wc=None, bc=None):
+            f = lambda t: t.detach().float()
+            w3e, b3e = f(w3), f(b3)
+            if wc is not None:
+                wcm = f(wc).reshape(wc.shape[0], -1)                      # [64, Cin]
+                b3e = w3e @ f(bc) + b3e
+                w3e = w3e @ wcm                                           # [128, Cin]
+            bf = lambda *ts: torch.cat([t.reshape(-1) for t in ts]).to(torch.bfloat16).contiguous()
+            fl = lambda *ts: torch.cat([t.reshape(-1) for t in ts]).float().contiguous()
+            return dict(
+                C3=w3e.shape[1],
+                w_gram=bf(f(w1)[:64], f(w2)[:64], w3e[64:]), b_gram=fl(f(b1)[:64], f(b2)[:64], b3e[64:]),
+                w_apply=bf(w3e[:64], f(w1)[64:], f(w2)[64:]), b_apply=fl(b3e[:64], f(b1)[64:], f(b2)[64:]),
+                wkv=torch.stack([f(kv1), f(kv2), f(kv3)]).contiguous(),
+                wend=torch.stack([f(we1), f(we2)]).contiguous(), bend=fl(f(be1), f(be2)),
+                ln_g=fl(f(g1), f(g2)), ln_b=fl(f(n1), f(n2)))
+        return self._packs.get_multi(plist, build, "ffm" if pre_conv is None else f"ffm+{id(pre_conv)}")
+
+    def forward(self, x1, x2, segfeature):
+        """Token interface of the reference: three [B, N, 64] tensors -> two [B, N, 64] tensors (fp32)."""
+        _no_autograd(self, x1, x2, segfeature)
+        B, N, C = x1.shape
+        cvt = lambda t: ops.nchw_to_nhwc(t.float().contiguous().view(1, 1, -1), out_dtype=torch.bfloat16).view(B, N, -1)
+        t1, t2, t3 = cvt(x1), cvt(x2), cvt(segfeature)
+        o1 = torch.empty((B, N, C), dtype=torch.bfloat16, device=x1.device)
+        o2 = torch.empty_like(o1)
+        pk = self.packs()
+        ops.ffm(t1, C, 0, t2, C, 0, t3, t3.shape[-1], pk["C3"], pk, o1, C, 0, o2, C, 0, B, N)
+        return o1.float(), o2.float()
+
+
+class FeatureFusionModule(nn.Module):
+    """core/model_fusion.py:430-463."""
+
+    def __init__(self, dim, reduction=1, num_heads=8, norm_layer=nn.BatchNorm2d):
+        super().__init__()
+        self.cross = CrossPath(dim=dim, reduction=reduction, num_heads=num_heads)
+        self.apply(_reference_init)
+
+    def forward_pixel_major(self, x1, ld1, x2, ld2, seg, ld3, out1, ldo1, coffo1, out2, ldo2, coffo2, B, HW,
+                            pre_conv=None):
+        pk = self.cross.packs(pre_conv)
+        return ops.ffm(x1, ld1, 0, x2, ld2, 0, seg, ld3, pk["C3"], pk, out1, ldo1, coffo1, out2, ldo2, coffo2, B, HW)
+
+    def forward(self, x1, x2, segfeature):
+        _no_autograd(self, x1, x2, segfeature)
+        B, C, H, W = x1.shape
+        t1, t2, t3 = _pixel_major_bf16(x1), _pixel_major_bf16(x2), _pixel_major_bf16(segfeature)
+        o1 = torch.empty((B, H * W, C), dtype=torch.bfloat16, device=x1.device)
+        o2 = torch.empty_like(o1)
+        self.forward_pixel_major(t1, C, t2, C, t3, t3.shape[-1], o1, C, 0, o2, C, 0, B, H * W)
+        nchw = lambda t: ops.nhwc_to_nchw(t, B, H * W, C).view(B, C, H, W)
+        return nchw(o1), nchw(o2)
+
+
+# ------------------------------------------------------------------------------------------------ fusion net
+class Fusion_Network3_ac(nn.Module):
+    """core/model_fusion.py:1026-1067."""
+
+    def __init__(self):
+        super().__init__()
+        self.conv1_ir = nn.Conv2d(1, 64, 3, padding=1)
+        self.conv1_vis = nn.Conv2d(1, 64, 3, padding=1)
+        self.DRDB1 = DRDB(in_ch=64)
+        self.DRDB2 = DRDB(in_ch=64)
+        self.DRDB3 = DRDB(in_ch=64)
+        self.DRDB4 = DRDB(in_ch=64)
+        self.conv2 = nn.Conv2d(128, 64, 3, padding=1)
+        self.relu = nn.PReLU()                 # ONE shared scalar slope for all five call sites (:1038)
+        self.ffm = FeatureFusionModule(64)
+        self.ffm2 = FeatureFusionModule(64)    # allocated and saved by the reference, never used (:1040)
+        self.conv3 = nn.Conv2d(64, 64, 1, padding=0)
+        self.conv4 = nn.Conv2d(128, 64, 1, padding=0)
+        self.conv21 = nn.Conv2d(64, 32, 3, padding=1)
+        self.conv22 = nn.Conv2d(32, 1, 3, padding=1)
+        self._packs = PackCache()
+
+    def forward(self, ir, vis, out1, out2):
+        _no_autograd(self, ir, vis, out1, out2)
+        B, _, H, W = ir.shape
+        HW = H * W
+        dev = ir.device
+        alpha = self.relu.weight.detach()
+        ir, vis = ir.float(), vis.float()      # no-ops for fp32 inputs; channel 0 is read through the batch stride
+        seg1, seg2 = _pixel_major_bf16(out1), _pixel_major_bf16(out2)
+        G = DRDB.GROWTH_LD
+        buf1 = torch.empty((B, H, W, G), dtype=torch.bfloat16, device=dev)
+        buf2 = torch.empty((B, H, W, G), dtype=torch.bfloat16, device=dev)
+        # x = PReLU(conv1(channel 0)) written straight into the DRDB growth buffers
+        ops.conv3x3_in1(ir, self._packs.taps_f32(self.conv1_ir.weight), self.conv1_ir.bias.detach(), alpha, buf1, G, 0, 64)
+        ops.conv3x3_in1(vis, self._packs.taps_f32(self.conv1_vis.weight), self.conv1_vis.bias.detach(), alpha, buf2, G, 0, 64)
+        x1 = self.DRDB1.forward_buffer(buf1, B, H, W)                    # [B*HW, 64] bf16
+        x2 = self.DRDB2.forward_buffer(buf2, B, H, W)
+        # ffm(x1, x2, conv3(out1)) -> inputs of DRDB3 / DRDB4 (channels 0..63 of the growth buffers)
+        self.ffm.forward_pixel_major(x1, 64, x2, 64, seg1, seg1.shape[-1], buf1, G, 0, buf2, G, 0, B, HW,
+                                     pre_conv=self.conv3)
+        x1 = self.DRDB3.forward_buffer(buf1, B, H, W, out=x1, ld_dst=64)
+        x2 = self.DRDB4.forward_buffer(buf2, B, H, W, out=x2, ld_dst=64)
+        # second pass of the SAME ffm with conv4(out2); outputs land side by side = torch.cat([x1, x2], 1)
+        cat = torch.empty((B, H, W, 128), dtype=torch.bfloat16, device=dev)
+        self.ffm.forward_pixel_major(x1, 64, x2, 64, seg2, seg2.shape[-1], cat, 128, 0, cat, 128, 64, B, HW,
+                                     pre_conv=self.conv4)
+        f = ops.conv(cat, self._packs.conv(self.conv2.weight), self.conv2.bias.detach(), B=B, H=H, W=W, Cin=128, KH=3,
+                     KW=3, pad=1, Cout=64, act=ACT_PRELU, prelu_alpha=alpha)
+        f = ops.conv(f, self._packs.conv(self.conv21.weight), self.conv21.bias.detach(), B=B, H=H, W=W, Cin=64, KH=3,
+                     KW=3, pad=1, Cout=32, act=ACT_PRELU, prelu_alpha=alpha)
+        return ops.conv3x3_out1(f, self._packs.taps_f32(self.conv22.weight), self.conv22.bias.detach(), alpha, B, H, W, 32)
+
+
+class Mean(nn.Module):
+    """core/model_fusion.py:184-214 (imported by train.py:18): recompose RGB from a given Y plane, clamp,
+    global min-max renormalisation.  Not on the hot path; the renormalisation uses torch reductions."""
+
+    def __init__(self):
+        super().__init__()
+        self.fusion_nums = 2
+        self.seg_nums = 2
+        self.fusion_channel = 48
+        self.seg_channel = 64
+        self.mean = IMAGENET_MEAN
+        self.std = IMAGENET_STD
+
+    def forward(self, mask, vis):
+        rgb = ops.recompose_rgb(mask[:, 0:1].float().contiguous(), vis.float().contiguous(), clamp=True)
+        lo, hi = torch.aminmax(rgb)
+        return (rgb - lo) / (hi - lo)

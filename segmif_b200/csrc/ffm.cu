@@ -1,0 +1,417 @@
+// Hierarchical interactive attention (FeatureFusionModule -> CrossPath -> MoAM + SoAM) at full image
+// resolution (N = H*W tokens, 64 channels, 8 heads of 8).  See include/segmif_b200.h for the algebra:
+//   k^T v = Wk (P^T P) Wv^T   because the kv Linears carry no bias, so pass 1 only accumulates three
+//   64x64 Gram matrices per image; pass 2 (one tiny CTA per image) turns them into the per-head 8x8
+//   column-softmaxed contexts and folds them with end_proj into four 64x64 matrices; pass 3 recomputes
+//   the three needed 64-channel projections per pixel tile, applies the folded matrices, adds the
+//   residual and LayerNorms -- 384 B/px read in pass 1, 384 B/px read + 256 B/px written in pass 3.
+// conv3 / conv4 (1x1 on the segmentation features) are folded into channel_proj3 by the host.
+#include "common.cuh"
+
+namespace segmif {
+
+constexpr int kTilePx = 64;          // pixels per tile (4 warps x 16 rows)
+constexpr int kFfmThreads = 128;
+
+__device__ __forceinline__ int swz128(int row, int chunk) { return chunk ^ (row & 7); }
+
+// copy a [rows x K] bf16 tile (K multiple of 8, rows of K*2 bytes) from pixel-major global memory
+__device__ __forceinline__ void load_rows_async(bf16* s, const bf16* g, int64_t first_row, int64_t nrows_total, int ld,
+                                                int K, int rows, int tid) {
+  const int cpr = K >> 3;
+  for (int i = tid; i < rows * cpr; i += kFfmThreads) {
+    const int row = i / cpr, chunk = i - row * cpr;
+    const bool ok = (first_row + row) < nrows_total;
+    const bf16* src = ok ? g + (first_row + row) * ld + chunk * 8 : g;
+    cp_async16_cg(smem_u32(s + row * K + swz128(row, chunk) * 8), src, ok ? 16 : 0);
+  }
+}
+
+// acc[8][4] (16 px x 64 out) = X[16 x K] * W[64 x K]^T for this warp's 16 rows
+__device__ __forceinline__ void proj16x64(float (&acc)[8][4], const bf16* sX, int K, int row0, const bf16* sW, int lane) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int ks = 0; ks < (K >> 4); ++ks) {
+    uint32_t af[4];
+    {
+      const int row = row0 + (lane & 15), chunk = ks * 2 + (lane >> 4);
+      ldmatrix_x4(af, smem_u32(sX + row * K + swz128(row, chunk) * 8));
+    }
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      uint32_t bfr[4];
+      const int row = np * 16 + (lane & 7) + ((lane >> 4) << 3), chunk = ks * 2 + ((lane >> 3) & 1);
+      ldmatrix_x4(bfr, smem_u32(sW + row * K + swz128(row, chunk) * 8));
+      mma_bf16_16816(acc[np * 2], af, bfr[0], bfr[1]);
+      mma_bf16_16816(acc[np * 2 + 1], af, bfr[2], bfr[3]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ pass 1
+__global__ void __launch_bounds__(kFfmThreads) ffm_gram_kernel(const bf16* __restrict__ x1, int ld1,
+                                                               const bf16* __restrict__ x2, int ld2,
+                                                               const bf16* __restrict__ x3, int ld3, int C3,
+                                                               const bf16* __restrict__ wproj,
+                                                               const float* __restrict__ bproj,
+                                                               float* __restrict__ partials, int64_t HW) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  bf16* sW = reinterpret_cast<bf16*>(smem_raw);            // [w1y 64x64][w2y 64x64][w3u 64xC3]
+  bf16* sX = sW + 64 * (128 + C3);                         // [64 px][<=128]
+  bf16* sP = sX + kTilePx * 128;                           // [64 px][64]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.y, chunk_id = blockIdx.x, nchunk = gridDim.x;
+
+  // weights (global layout is dense row-major; smem rows are swizzled)
+  {
+    const int koff[3] = {0, 64 * 64, 2 * 64 * 64};
+    const int kk[3] = {64, 64, C3};
+    for (int s = 0; s < 3; ++s) {
+      const int cpr = kk[s] >> 3;
+      for (int i = tid; i < 64 * cpr; i += kFfmThreads) {
+        const int row = i / cpr, chunk = i - row * cpr;
+        cp_async16_cg(smem_u32(sW + koff[s] + row * kk[s] + swz128(row, chunk) * 8), wproj + koff[s] + row * kk[s] + chunk * 8, 16);
+      }
+    }
+    cp_async_commit();
+  }
+  float gacc[3][8][4];
+#pragma unroll
+  for (int s = 0; s < 3; ++s)
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) gacc[s][i][j] = 0.f;
+
+  const int64_t ntiles = (HW + kTilePx - 1) / kTilePx;
+  const int g = lane >> 2, tq = lane & 3;
+  for (int64_t t = chunk_id; t < ntiles; t += nchunk) {
+    const int64_t p0 = t * kTilePx;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      const bf16* xs = (s == 0 ? x1 : s == 1 ? x2 : x3) + (int64_t)b * HW * (s == 0 ? ld1 : s == 1 ? ld2 : ld3);
+      const int ld = s == 0 ? ld1 : s == 1 ? ld2 : ld3;
+      const int K = s == 2 ? C3 : 64;
+      const bf16* w = sW + (s == 0 ? 0 : s == 1 ? 64 * 64 : 2 * 64 * 64);
+      __syncthreads();                                  // previous users of sX / sP are done
+      load_rows_async(sX, xs, p0, HW, ld, K, kTilePx, tid);
+      cp_async_commit();
+      cp_async_wait<0>();
+      __syncthreads();
+      float acc[8][4];
+      proj16x64(acc, sX, K, warp * 16, w, lane);
+      // bias + ReLU, zero rows past the image, write P (bf16) to smem
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int row = warp * 16 + g + half * 8;
+        const bool live = (p0 + row) < HW;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          const int ch = nt * 8 + tq * 2;
+          float v0 = fmaxf(acc[nt][half * 2] + bproj[s * 64 + ch], 0.f);
+          float v1 = fmaxf(acc[nt][half * 2 + 1] + bproj[s * 64 + ch + 1], 0.f);
+          if (!live) { v0 = 0.f; v1 = 0.f; }
+          *reinterpret_cast<uint32_t*>(sP + row * 64 + swz128(row, nt) * 8 + tq * 2) = pack_bf16x2(v0, v1);
+        }
+      }
+      __syncthreads();
+      // G_s[16 rows of this warp][64] += P^T P over the 64 pixels of the tile
+#pragma unroll
+      for (int ks = 0; ks < kTilePx / 16; ++ks) {
+        uint32_t af[4];
+        {
+          const int row = ks * 16 + (lane & 7) + ((lane >> 4) << 3), chunk = warp * 2 + ((lane >> 3) & 1);
+          ldmatrix_x4_trans(af, smem_u32(sP + row * 64 + swz128(row, chunk) * 8));
+        }
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {
+          uint32_t bfr[4];
+          const int row = ks * 16 + (lane & 7) + (((lane >> 3) & 1) << 3), chunk = np * 2 + (lane >> 4);
+          ldmatrix_x4_trans(bfr, smem_u32(sP + row * 64 + swz128(row, chunk) * 8));
+          mma_bf16_16816(gacc[s][np * 2], af, bfr[0], bfr[1]);
+          mma_bf16_16816(gacc[s][np * 2 + 1], af, bfr[2], bfr[3]);
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+  float* out = partials + ((int64_t)b * nchunk + chunk_id) * 3 * 4096;
+#pragma unroll
+  for (int s = 0; s < 3; ++s)
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int i = warp * 16 + g + half * 8, j = nt * 8 + tq * 2;
+        *reinterpret_cast<float2*>(out + s * 4096 + i * 64 + j) = make_float2(gacc[s][nt][half * 2], gacc[s][nt][half * 2 + 1]);
+      }
+}
+
+// ------------------------------------------------------------------------------------------------ pass 2
+__global__ void __launch_bounds__(256) ffm_ctx_kernel(const float* __restrict__ partials, int nchunk,
+                                                      const float* __restrict__ wkv, const float* __restrict__ wend,
+                                                      bf16* __restrict__ folded, float* __restrict__ ctx_out) {
+  extern __shared__ float sm[];
+  float* G = sm;                 // [3][4096]
+  float* T = G + 3 * 4096;       // [4096]
+  float* ctx = T + 4096;         // [3][8][8][8]
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float* pb = partials + (int64_t)b * nchunk * 3 * 4096;
+  for (int idx = tid; idx < 3 * 4096; idx += 256) {
+    float s = 0.f;
+    for (int c = 0; c < nchunk; ++c) s += pb[(int64_t)c * 3 * 4096 + idx];
+    G[idx] = s;
+  }
+  __syncthreads();
+  const float scale = 0.35355339059327379f;     // 8^-1/2 (head_dim 8)
+  for (int s = 0; s < 3; ++s) {
+    const float* Wk = wkv + (int64_t)s * 128 * 64;
+    const float* Wv = Wk + 64 * 64;
+    for (int idx = tid; idx < 4096; idx += 256) {     // T = Wk G_s
+      const int r = idx >> 6, c = idx & 63;
+      float a = 0.f;
+      for (int k = 0; k < 64; ++k) a = fmaf(Wk[r * 64 + k], G[s * 4096 + k * 64 + c], a);
+      T[idx] = a;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < 512; idx += 256) {      // logits[h][i][j] = scale * T[h8+i,:] . Wv[h8+j,:]
+      const int h = idx >> 6, i = (idx >> 3) & 7, j = idx & 7;
+      float a = 0.f;
+      for (int c = 0; c < 64; ++c) a = fmaf(T[(h * 8 + i) * 64 + c], Wv[(h * 8 + j) * 64 + c], a);
+      ctx[s * 512 + idx] = a * scale;
+    }
+    __syncthreads();
+  }
+  if (tid < 192) {                                    // softmax over i (dim=-2) for every (s, h, j)
+    const int s = tid >> 6, h = (tid >> 3) & 7, j = tid & 7;
+    float* c = ctx + s * 512 + h * 64 + j;
+    float m = -INFINITY;
+    for (int i = 0; i < 8; ++i) m = fmaxf(m, c[i * 8]);
+    float e[8], sum = 0.f;
+    for (int i = 0; i < 8; ++i) { e[i] = expf(c[i * 8] - m); sum += e[i]; }
+    for (int i = 0; i < 8; ++i) c[i * 8] = e[i] / sum;
+  }
+  __syncthreads();
+  if (ctx_out)
+    for (int idx = tid; idx < 1536; idx += 256) ctx_out[(int64_t)b * 1536 + idx] = ctx[idx];
+  // folded[m][o][c]: m=0 Mz1 (ctx1, We1[:, :64]); 1 Mv1 (ctx3, We1[:, 64:]); 2 Mz2 (ctx2, We2[:, :64]); 3 Mv2 (ctx3, We2[:, 64:])
+  for (int idx = tid; idx < 4 * 4096; idx += 256) {
+    const int m = idx >> 12, o = (idx >> 6) & 63, c = idx & 63;
+    const int h = c >> 3, i = c & 7;
+    const int stream = m >> 1, is_v = m & 1;
+    const float* cx = ctx + (is_v ? 2 : stream) * 512 + h * 64 + i * 8;
+    const float* we = wend + (int64_t)stream * 64 * 128 + o * 128 + (is_v ? 64 : 0) + h * 8;
+    float a = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a = fmaf(cx[j], we[j], a);
+    folded[(int64_t)b * 4 * 4096 + idx] = __float2bfloat16_rn(a);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ pass 3
+__device__ __forceinline__ void relu_bias_to_afrag(uint32_t (&af)[4][4], const float (&acc)[8][4], const float* bias, int tq) {
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+    for (int sub = 0; sub < 2; ++sub) {
+      const int nt = kk * 2 + sub;
+      const float b0 = bias[nt * 8 + tq * 2], b1 = bias[nt * 8 + tq * 2 + 1];
+      af[kk][sub * 2 + 0] = pack_bf16x2(fmaxf(acc[nt][0] + b0, 0.f), fmaxf(acc[nt][1] + b1, 0.f));
+      af[kk][sub * 2 + 1] = pack_bf16x2(fmaxf(acc[nt][2] + b0, 0.f), fmaxf(acc[nt][3] + b1, 0.f));
+    }
+  }
+}
+
+// acc += A(16x64, register fragments) * M^T, M stored [64 out][64 in] bf16 swizzled
+__device__ __forceinline__ void apply64(float (&acc)[8][4], const uint32_t (&af)[4][4], const bf16* sM, int lane) {
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      uint32_t bfr[4];
+      const int row = np * 16 + (lane & 7) + ((lane >> 4) << 3), chunk = kk * 2 + ((lane >> 3) & 1);
+      ldmatrix_x4(bfr, smem_u32(sM + row * 64 + swz128(row, chunk) * 8));
+      mma_bf16_16816(acc[np * 2], af[kk], bfr[0], bfr[1]);
+      mma_bf16_16816(acc[np * 2 + 1], af[kk], bfr[2], bfr[3]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kFfmThreads) ffm_apply_kernel(
+    const bf16* __restrict__ x1, int ld1, const bf16* __restrict__ x2, int ld2, const bf16* __restrict__ x3, int ld3,
+    int C3, const bf16* __restrict__ wproj, const float* __restrict__ bproj, const bf16* __restrict__ folded,
+    const float* __restrict__ bend, const float* __restrict__ ln_g, const float* __restrict__ ln_b, float eps,
+    bf16* __restrict__ out1, int ldo1, bf16* __restrict__ out2, int ldo2, int64_t HW) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  bf16* sW3 = reinterpret_cast<bf16*>(smem_raw);   // [64][C3]   channel_proj3 (y half) folded with conv3|conv4
+  bf16* sW1 = sW3 + 64 * C3;                       // [64][64]   channel_proj1 (u half)
+  bf16* sW2 = sW1 + 64 * 64;                       // [64][64]   channel_proj2 (u half)
+  bf16* sM = sW2 + 64 * 64;                        // [4][64][64] folded Mz1, Mv1, Mz2, Mv2 of this image
+  bf16* sX1 = sM + 4 * 64 * 64;                    // [64 px][64]
+  bf16* sX2 = sX1 + kTilePx * 64;
+  bf16* sX3 = sX2 + kTilePx * 64;                  // [64 px][C3]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.y;
+  {
+    // weights: global [w3y 64xC3][w1u 64x64][w2u 64x64] dense; folded [4][64][64] dense
+    const int cpr3 = C3 >> 3;
+    for (int i = tid; i < 64 * cpr3; i += kFfmThreads) {
+      const int row = i / cpr3, chunk = i - row * cpr3;
+      cp_async16_cg(smem_u32(sW3 + row * C3 + swz128(row, chunk) * 8), wproj + row * C3 + chunk * 8, 16);
+    }
+    for (int i = tid; i < 2 * 64 * 8; i += kFfmThreads) {
+      const int m = i >> 9, row = (i >> 3) & 63, chunk = i & 7;
+      cp_async16_cg(smem_u32(sW1 + m * 4096 + row * 64 + swz128(row, chunk) * 8), wproj + 64 * C3 + m * 4096 + row * 64 + chunk * 8, 16);
+    }
+    const bf16* fb = folded + (int64_t)b * 4 * 4096;
+    for (int i = tid; i < 4 * 64 * 8; i += kFfmThreads) {
+      const int m = i >> 9, row = (i >> 3) & 63, chunk = i & 7;
+      cp_async16_cg(smem_u32(sM + m * 4096 + row * 64 + swz128(row, chunk) * 8), fb + m * 4096 + row * 64 + chunk * 8, 16);
+    }
+    cp_async_commit();
+  }
+  const int g = lane >> 2, tq = lane & 3;
+  const int64_t ntiles = (HW + kTilePx - 1) / kTilePx;
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int64_t p0 = t * kTilePx;
+    __syncthreads();
+    load_rows_async(sX1, x1 + (int64_t)b * HW * ld1, p0, HW, ld1, 64, kTilePx, tid);
+    load_rows_async(sX2, x2 + (int64_t)b * HW * ld2, p0, HW, ld2, 64, kTilePx, tid);
+    load_rows_async(sX3, x3 + (int64_t)b * HW * ld3, p0, HW, ld3, C3, kTilePx, tid);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    const int row0 = warp * 16;
+    uint32_t ay[4][4];
+    {
+      float acc[8][4];
+      proj16x64(acc, sX3, C3, row0, sW3, lane);
+      relu_bias_to_afrag(ay, acc, bproj, tq);
+    }
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const bf16* sX = s == 0 ? sX1 : sX2;
+      uint32_t au[4][4];
+      {
+        float acc[8][4];
+        proj16x64(acc, sX, 64, row0, s == 0 ? sW1 : sW2, lane);
+        relu_bias_to_afrag(au, acc, bproj + 64 * (1 + s), tq);
+      }
+      float acc[8][4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+      apply64(acc, ay, sM + (2 * s) * 4096, lane);
+      apply64(acc, au, sM + (2 * s + 1) * 4096, lane);
+      // + end_proj bias + residual x_s, LayerNorm over the 64 channels of each row
+      float sum[2] = {0.f, 0.f};
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int ch = nt * 8 + tq * 2;
+        const float b0 = bend[s * 64 + ch], b1 = bend[s * 64 + ch + 1];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int row = row0 + g + half * 8;
+          const float2 xr = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(sX + row * 64 + swz128(row, nt) * 8 + tq * 2));
+          acc[nt][half * 2] += b0 + xr.x;
+          acc[nt][half * 2 + 1] += b1 + xr.y;
+          sum[half] += acc[nt][half * 2] + acc[nt][half * 2 + 1];
+        }
+      }
+      float mean[2], rstd[2];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        sum[half] += __shfl_xor_sync(0xffffffffu, sum[half], 1);
+        sum[half] += __shfl_xor_sync(0xffffffffu, sum[half], 2);
+        mean[half] = sum[half] * (1.f / 64.f);
+      }
+      float sq[2] = {0.f, 0.f};
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float d = acc[nt][j] - mean[j >> 1]; sq[j >> 1] += d * d; }
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        sq[half] += __shfl_xor_sync(0xffffffffu, sq[half], 1);
+        sq[half] += __shfl_xor_sync(0xffffffffu, sq[half], 2);
+        rstd[half] = rsqrtf(sq[half] * (1.f / 64.f) + eps);
+      }
+      bf16* op = (s == 0 ? out1 : out2);
+      const int ldo = s == 0 ? ldo1 : ldo2;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int64_t px = p0 + row0 + g + half * 8;
+        if (px >= HW) continue;
+        bf16* o = op + ((int64_t)b * HW + px) * ldo + tq * 2;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          const int ch = nt * 8 + tq * 2;
+          const float v0 = (acc[nt][half * 2] - mean[half]) * rstd[half] * ln_g[s * 64 + ch] + ln_b[s * 64 + ch];
+          const float v1 = (acc[nt][half * 2 + 1] - mean[half]) * rstd[half] * ln_g[s * 64 + ch + 1] + ln_b[s * 64 + ch + 1];
+          *reinterpret_cast<uint32_t*>(o + nt * 8) = pack_bf16x2(v0, v1);
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+}
+
+static int set_smem(const void* fn, size_t bytes, const char* what) {
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) { set_error("%s: cudaFuncSetAttribute(%zu) failed: %s", what, bytes, cudaGetErrorString(e)); return SEGMIF_ERR_CUDA; }
+  return SEGMIF_OK;
+}
+
+}  // namespace segmif
+
+using namespace segmif;
+
+extern "C" int segmif_ffm_gram_fwd(const void* x1, int ld1, int coff1, const void* x2, int ld2, int coff2,
+                                   const void* x3, int ld3, int C3, const void* wproj, const float* bproj,
+                                   float* partials, int nchunk, int B, int64_t HW, segmif_stream_t stream) {
+  SEGMIF_REQUIRE(x1 && x2 && x3 && wproj && bproj && partials, "ffm_gram: null pointer");
+  SEGMIF_REQUIRE(C3 == 64 || C3 == 128, "ffm_gram: C3=%d must be 64 or 128", C3);
+  SEGMIF_REQUIRE(ld1 % 8 == 0 && ld2 % 8 == 0 && ld3 % 8 == 0 && coff1 % 8 == 0 && coff2 % 8 == 0, "ffm_gram: pitches/offsets must be multiples of 8");
+  SEGMIF_REQUIRE(nchunk > 0 && B > 0 && HW > 0, "ffm_gram: bad sizes");
+  const size_t smem = (size_t)(64 * (128 + C3) + kTilePx * 128 + kTilePx * 64) * sizeof(bf16);
+  int rc = set_smem((const void*)ffm_gram_kernel, smem, "ffm_gram");
+  if (rc) return rc;
+  dim3 grid(nchunk, B);
+  ffm_gram_kernel<<<grid, kFfmThreads, smem, as_stream(stream)>>>((const bf16*)x1 + coff1, ld1, (const bf16*)x2 + coff2, ld2,
+                                                                   (const bf16*)x3, ld3, C3, (const bf16*)wproj, bproj, partials, HW);
+  return check_launch("segmif_ffm_gram_fwd");
+}
+
+extern "C" int segmif_ffm_ctx_fwd(const float* partials, int nchunk, const float* wkv, const float* wend, void* folded,
+                                  float* ctx_out, int B, segmif_stream_t stream) {
+  SEGMIF_REQUIRE(partials && wkv && wend && folded, "ffm_ctx: null pointer");
+  const size_t smem = (size_t)(3 * 4096 + 4096 + 1536) * sizeof(float);
+  int rc = set_smem((const void*)ffm_ctx_kernel, smem, "ffm_ctx");
+  if (rc) return rc;
+  ffm_ctx_kernel<<<B, 256, smem, as_stream(stream)>>>(partials, nchunk, wkv, wend, (bf16*)folded, ctx_out);
+  return check_launch("segmif_ffm_ctx_fwd");
+}
+
+extern "C" int segmif_ffm_apply_fwd(const void* x1, int ld1, int coff1, const void* x2, int ld2, int coff2,
+                                    const void* x3, int ld3, int C3, const void* wproj, const float* bproj,
+                                    const void* folded, const float* bend, const float* ln_gamma, const float* ln_beta,
+                                    float eps, void* out1, int ldo1, int coffo1, void* out2, int ldo2, int coffo2, int B,
+                                    int64_t HW, segmif_stream_t stream) {
+  SEGMIF_REQUIRE(x1 && x2 && x3 && wproj && bproj && folded && bend && ln_gamma && ln_beta && out1 && out2, "ffm_apply: null pointer");
+  SEGMIF_REQUIRE(C3 == 64 || C3 == 128, "ffm_apply: C3=%d must be 64 or 128", C3);
+  SEGMIF_REQUIRE(ld1 % 8 == 0 && ld2 % 8 == 0 && ld3 % 8 == 0 && coff1 % 8 == 0 && coff2 % 8 == 0, "ffm_apply: input pitches/offsets must be multiples of 8");
+  SEGMIF_REQUIRE(ldo1 % 2 == 0 && ldo2 % 2 == 0 && coffo1 % 2 == 0 && coffo2 % 2 == 0, "ffm_apply: output pitches/offsets must be even");
+  const size_t smem = (size_t)(64 * C3 + 2 * 4096 + 4 * 4096 + 2 * kTilePx * 64 + kTilePx * C3) * sizeof(bf16);
+  int rc = set_smem((const void*)ffm_apply_kernel, smem, "ffm_apply");
+  if (rc) return rc;
+  const int64_t ntiles = (HW + kTilePx - 1) / kTilePx;
+  const int per_image = (int)std::min<int64_t>(ntiles, std::max<int64_t>(1, (148 * 2 * 4) / B));
+  dim3 grid(per_image, B);
+  ffm_apply_kernel<<<grid, kFfmThreads, smem, as_stream(stream)>>>(
+      (const bf16*)x1 + coff1, ld1, (const bf16*)x2 + coff2, ld2, (const bf16*)x3, ld3, C3, (const bf16*)wproj, bproj,
+      (const bf16*)folded, bend, ln_gamma, ln_beta, eps, (bf16*)out1 + coffo1, ldo1, (bf16*)out2 + coffo2, ldo2, HW);
+  return check_launch("segmif_ffm_apply_fwd");
+}

@@ -1,0 +1,189 @@
+// Edge layers of Fusion_Network3_ac (1-channel in / 1-channel out 3x3 convs with the shared PReLU)
+// and the colour transforms.  All HBM-bound; fp32 math.
+#include "common.cuh"
+
+namespace segmif {
+
+// conv1_ir / conv1_vis: fp32 plane [B,H,W] -> bf16 pixel-major, Cout channels (multiple of 8).
+// thread = (pixel, 8-channel group); the 9 input taps come from L1.
+__global__ void __launch_bounds__(256) conv3x3_in1_kernel(const float* __restrict__ plane, int64_t bstride,
+                                                          const float* __restrict__ w, const float* __restrict__ bias,
+                                                          const float* __restrict__ alpha_p, bf16* __restrict__ dst,
+                                                          int ld_dst, int dst_coff, int B, int H, int W, int Cout) {
+  const int cg = Cout >> 3;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)B * H * W * cg) return;
+  const int c = (int)(idx % cg) * 8;
+  const int64_t pix = idx / cg;
+  const int X = (int)(pix % W), Y = (int)((pix / W) % H);
+  const int64_t b = pix / ((int64_t)W * H);
+  const float alpha = *alpha_p;
+  const float* src = plane + b * bstride;
+  float acc[8];
+  load8(bias + c, acc);
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int iy = Y + ky - 1;
+    if ((unsigned)iy >= (unsigned)H) continue;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int ix = X + kx - 1;
+      if ((unsigned)ix >= (unsigned)W) continue;
+      const float v = src[(int64_t)iy * W + ix];
+      float wv[8];
+      load8(w + (ky * 3 + kx) * Cout + c, wv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wv[j], acc[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = acc[j] >= 0.f ? acc[j] : alpha * acc[j];
+  store8(dst + pix * ld_dst + dst_coff + c, acc);
+}
+
+// conv22: bf16 pixel-major Cin channels -> fp32 plane [B,1,H,W]; a quad of 4 lanes shares one pixel
+// (each lane owns Cin/4 channels), reduced with two shuffles.
+__global__ void __launch_bounds__(256) conv3x3_out1_kernel(const bf16* __restrict__ src, int ld_src,
+                                                           const float* __restrict__ w, const float* __restrict__ bias,
+                                                           const float* __restrict__ alpha_p, float* __restrict__ dst,
+                                                           int B, int H, int W, int Cin) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t pix = gid >> 2;
+  const int q = (int)(gid & 3);
+  const int64_t npix = (int64_t)B * H * W;
+  const bool live = pix < npix;
+  const int64_t pp = live ? pix : 0;
+  const int X = (int)(pp % W), Y = (int)((pp / W) % H);
+  const int64_t b = pp / ((int64_t)W * H);
+  const int cpl = Cin >> 2;                 // channels per lane (multiple of 8)
+  float acc = 0.f;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int iy = Y + ky - 1;
+    if ((unsigned)iy >= (unsigned)H) continue;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int ix = X + kx - 1;
+      if ((unsigned)ix >= (unsigned)W) continue;
+      const bf16* p = src + ((b * H + iy) * W + ix) * ld_src + q * cpl;
+      const float* wp = w + (ky * 3 + kx) * Cin + q * cpl;
+      for (int c = 0; c < cpl; c += 8) {
+        float v[8], wv[8];
+        load8(p + c, v);
+        load8(wp + c, wv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc = fmaf(v[j], wv[j], acc);
+      }
+    }
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  if (live && q == 0) {
+    const float alpha = *alpha_p;
+    float v = acc + bias[0];
+    dst[pix] = v >= 0.f ? v : alpha * v;
+  }
+}
+
+// ---- colour: constants exactly as core/model_fusion.py:69-111 -------------------------------------------------
+__device__ __forceinline__ void rgb_to_ycc(float r, float g, float b, float& y, float& cr, float& cb) {
+  y = 0.299f * r + 0.587f * g + 0.114f * b;
+  cr = (r - y) * 0.713f + 0.5f;
+  cb = (b - y) * 0.564f + 0.5f;
+}
+__device__ __forceinline__ void ycc_to_rgb(float y, float cr, float cb, float& r, float& g, float& b) {
+  const float c1 = cr - 0.5f, c2 = cb - 0.5f;       // (im + bias) . mat, mat rows: [1,1,1],[1.403,-.714,0],[0,-.344,1.773]
+  r = y * 1.0f + c1 * 1.403f + c2 * 0.0f;
+  g = y * 1.0f + c1 * -0.714f + c2 * -0.344f;
+  b = y * 1.0f + c1 * 0.0f + c2 * 1.773f;
+}
+
+__global__ void rgb2ycrcb_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int64_t HW) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * HW) return;
+  const int64_t b = i / HW, p = i - b * HW;
+  const float* s = in + b * 3 * HW + p;
+  float y, cr, cb;
+  rgb_to_ycc(s[0], s[HW], s[2 * HW], y, cr, cb);
+  float* d = out + b * 3 * HW + p;
+  d[0] = y; d[HW] = cr; d[2 * HW] = cb;
+}
+
+__global__ void ycrcb2rgb_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int64_t HW) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * HW) return;
+  const int64_t b = i / HW, p = i - b * HW;
+  const float* s = in + b * 3 * HW + p;
+  float r, g, bl;
+  ycc_to_rgb(s[0], s[HW], s[2 * HW], r, g, bl);
+  float* d = out + b * 3 * HW + p;
+  d[0] = r; d[HW] = g; d[2 * HW] = bl;
+}
+
+// fused: YCrCb(vis) with Y replaced by the fused plane -> RGB -> optional clamp
+__global__ void recompose_rgb_kernel(const float* __restrict__ fused, const float* __restrict__ vis,
+                                     float* __restrict__ out, int clamp01, int B, int64_t HW) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * HW) return;
+  const int64_t b = i / HW, p = i - b * HW;
+  const float* s = vis + b * 3 * HW + p;
+  float y, cr, cb, r, g, bl;
+  rgb_to_ycc(s[0], s[HW], s[2 * HW], y, cr, cb);
+  ycc_to_rgb(fused[i], cr, cb, r, g, bl);
+  if (clamp01) {
+    r = fminf(fmaxf(r, 0.f), 1.f); g = fminf(fmaxf(g, 0.f), 1.f); bl = fminf(fmaxf(bl, 0.f), 1.f);
+  }
+  float* d = out + b * 3 * HW + p;
+  d[0] = r; d[HW] = g; d[2 * HW] = bl;
+}
+
+}  // namespace segmif
+
+using namespace segmif;
+
+extern "C" int segmif_conv3x3_in1_fwd(const float* plane, int64_t bstride, const float* w, const float* bias,
+                                      const float* prelu_alpha, void* dst, int ld_dst, int dst_coff, int B, int H,
+                                      int W, int Cout, segmif_stream_t stream) {
+  SEGMIF_REQUIRE(plane && w && bias && prelu_alpha && dst, "conv3x3_in1: null pointer");
+  SEGMIF_REQUIRE(Cout % 8 == 0 && ld_dst % 8 == 0 && dst_coff % 8 == 0, "conv3x3_in1: channel counts must be multiples of 8");
+  const int64_t total = (int64_t)B * H * W * (Cout / 8);
+  if (total == 0) return SEGMIF_OK;
+  conv3x3_in1_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, as_stream(stream)>>>(
+      plane, bstride, w, bias, prelu_alpha, (bf16*)dst, ld_dst, dst_coff, B, H, W, Cout);
+  return check_launch("segmif_conv3x3_in1_fwd");
+}
+
+extern "C" int segmif_conv3x3_out1_fwd(const void* src, int ld_src, const float* w, const float* bias,
+                                       const float* prelu_alpha, float* dst, int B, int H, int W, int Cin,
+                                       segmif_stream_t stream) {
+  SEGMIF_REQUIRE(src && w && bias && prelu_alpha && dst, "conv3x3_out1: null pointer");
+  SEGMIF_REQUIRE(Cin % 32 == 0 && ld_src % 8 == 0, "conv3x3_out1: Cin must be a multiple of 32");
+  const int64_t total = (int64_t)B * H * W * 4;
+  if (total == 0) return SEGMIF_OK;
+  conv3x3_out1_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, as_stream(stream)>>>(
+      (const bf16*)src, ld_src, w, bias, prelu_alpha, dst, B, H, W, Cin);
+  return check_launch("segmif_conv3x3_out1_fwd");
+}
+
+extern "C" int segmif_rgb2ycrcb(const float* rgb, float* ycc, int B, int64_t HW, segmif_stream_t stream) {
+  SEGMIF_REQUIRE(rgb && ycc, "rgb2ycrcb: null pointer");
+  if (B * HW == 0) return SEGMIF_OK;
+  rgb2ycrcb_kernel<<<(unsigned)ceil_div(B * HW, 256), 256, 0, as_stream(stream)>>>(rgb, ycc, B, HW);
+  return check_launch("segmif_rgb2ycrcb");
+}
+
+extern "C" int segmif_ycrcb2rgb(const float* ycc, float* rgb, int B, int64_t HW, segmif_stream_t stream) {
+  SEGMIF_REQUIRE(rgb && ycc, "ycrcb2rgb: null pointer");
+  if (B * HW == 0) return SEGMIF_OK;
+  ycrcb2rgb_kernel<<<(unsigned)ceil_div(B * HW, 256), 256, 0, as_stream(stream)>>>(ycc, rgb, B, HW);
+  return check_launch("segmif_ycrcb2rgb");
+}
+
+extern "C" int segmif_recompose_rgb(const float* fused_y, const float* vis_rgb, float* rgb_out, int clamp01, int B,
+                                    int64_t HW, segmif_stream_t stream) {
+  SEGMIF_REQUIRE(fused_y && vis_rgb && rgb_out, "recompose_rgb: null pointer");
+  if (B * HW == 0) return SEGMIF_OK;
+  recompose_rgb_kernel<<<(unsigned)ceil_div(B * HW, 256), 256, 0, as_stream(stream)>>>(fused_y, vis_rgb, rgb_out,
+                                                                                       clamp01, B, HW);
+  return check_launch("segmif_recompose_rgb");
+}

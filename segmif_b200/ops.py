@@ -1,0 +1,316 @@
+"""Thin tensor-level wrappers over the C ABI: allocate outputs, pass raw device pointers and the
+current CUDA stream.  PyTorch is used here for device memory and streams only; every computation
+is a kernel in libsegmif_b200.so.  All wrappers raise on non-CUDA tensors -- there is no fallback."""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import ACT_GELU, ACT_NONE, ACT_PRELU, ACT_RELU, BF16, F32
+
+_DT = {torch.float32: F32, torch.bfloat16: BF16}
+
+
+def _dt(t):
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise TypeError(f"segmif_b200: unsupported dtype {t.dtype}")
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _prep(*tensors):
+    """Validates tensors, initialises the library for their device and returns the stream handle."""
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("segmif_b200: tensors must live on a CUDA (sm_100) device; there is no CPU path")
+        if not t.is_contiguous():
+            raise RuntimeError("segmif_b200: tensors must be contiguous")
+        dev = t.device if dev is None else dev
+        if t.device != dev:
+            raise RuntimeError("segmif_b200: tensors on different devices")
+    _lib.ensure_init(dev.index if dev.index is not None else torch.cuda.current_device())
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def layernorm(x, gamma, beta, eps, out_dtype=torch.bfloat16, out=None):
+    st = _prep(x, gamma, beta, out)
+    C = x.shape[-1]
+    rows = x.numel() // C
+    if out is None:
+        out = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+    _lib.call("segmif_layernorm_fwd", _ptr(x), _dt(x), _ptr(gamma), _ptr(beta), _ptr(out), _dt(out), rows, C,
+              float(eps), st)
+    return out
+
+
+def conv(src, weight, bias, *, B, H, W, Cin, KH=1, KW=1, stride=1, pad=0, dil=1, Cout, ld_src=None, src_coff=0,
+         act=ACT_NONE, prelu_alpha=None, residual=None, ld_res=None, res_coff=0, out=None, out_dtype=torch.bfloat16,
+         ld_dst=None, dst_coff=0):
+    """Implicit-GEMM conv / linear (segmif_conv_fwd).  `src` is pixel-major bf16 with channel pitch ld_src;
+    `weight` is the packed bf16 [Cout, KH*KW, Cin] tensor.  Returns `out` ([B*Ho*Wo, ld_dst])."""
+    st = _prep(src, weight, bias, prelu_alpha, residual, out)
+    if src.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16:
+        raise TypeError("segmif_b200.conv: src and weight must be bf16")
+    Ho = (H + 2 * pad - dil * (KH - 1) - 1) // stride + 1
+    Wo = (W + 2 * pad - dil * (KW - 1) - 1) // stride + 1
+    M = B * Ho * Wo
+    ld_src = Cin if ld_src is None else ld_src
+    if out is None:
+        ld_dst = Cout if ld_dst is None else ld_dst
+        out = torch.empty((M, ld_dst), dtype=out_dtype, device=src.device)
+    elif ld_dst is None:
+        ld_dst = out.shape[-1]
+    if residual is not None and ld_res is None:
+        ld_res = residual.shape[-1]
+    p = _lib.ConvParams()
+    p.src, p.weight, p.bias = src.data_ptr(), weight.data_ptr(), (bias.data_ptr() if bias is not None else None)
+    p.prelu_alpha = prelu_alpha.data_ptr() if prelu_alpha is not None else None
+    p.residual = residual.data_ptr() if residual is not None else None
+    p.dst = out.data_ptr()
+    p.B, p.H, p.W, p.Cin, p.ld_src, p.src_coff = B, H, W, Cin, ld_src, src_coff
+    p.KH, p.KW, p.stride, p.pad, p.dil, p.Ho, p.Wo, p.Cout = KH, KW, stride, pad, dil, Ho, Wo, Cout
+    p.act = act
+    p.res_dtype = _dt(residual) if residual is not None else F32
+    p.ld_res, p.res_coff = (ld_res or 0), res_coff
+    p.dst_dtype, p.ld_dst, p.dst_coff = _dt(out), ld_dst, dst_coff
+    _lib.call("segmif_conv_fwd", ctypes.byref(p), st)
+    return out
+
+
+def linear(x, weight, bias, *, act=ACT_NONE, residual=None, out_dtype=torch.bfloat16, out=None, ld_dst=None,
+           dst_coff=0):
+    """y[rows, N] = act(x[rows, K] @ W^T + b) (+ residual); x bf16 [..., K], W packed bf16 [N, 1, K]."""
+    K = x.shape[-1]
+    rows = x.numel() // K
+    N = weight.shape[0]
+    return conv(x, weight, bias, B=1, H=1, W=rows, Cin=K, Cout=N, act=act, residual=residual, out=out,
+                out_dtype=out_dtype, ld_dst=ld_dst, dst_coff=dst_coff)
+
+
+def patch_embed7_ln(img, w147, bias, gamma, beta, eps, in_scale=None, in_shift=None):
+    st = _prep(img, w147, bias, gamma, beta, in_scale, in_shift)
+    B, C, H, W = img.shape
+    assert C == 3 and img.dtype == torch.float32
+    C0 = w147.shape[1]
+    Ho, Wo = (H + 6 - 7) // 4 + 1, (W + 6 - 7) // 4 + 1
+    tokens = torch.empty((B, Ho * Wo, C0), dtype=torch.float32, device=img.device)
+    _lib.call("segmif_patch_embed7_ln_fwd", _ptr(img), _ptr(w147), _ptr(bias), _ptr(gamma), _ptr(beta), float(eps),
+              _ptr(in_scale), _ptr(in_shift), _ptr(tokens), B, H, W, C0, st)
+    return tokens, Ho, Wo
+
+
+def sr_attention(q, kv, B, heads, N, Nk, D, scale):
+    """q bf16 [B*N, C]; kv bf16 [B*Nk, 2C] (k = first C columns, v = last C); returns bf16 [B*N, C]."""
+    st = _prep(q, kv)
+    C = heads * D
+    out = torch.empty((B * N, C), dtype=torch.bfloat16, device=q.device)
+    kptr = kv.data_ptr()
+    _lib.call("segmif_sr_attention_fwd", _ptr(q), C, ctypes.c_void_p(kptr), ctypes.c_void_p(kptr + 2 * C), 2 * C,
+              _ptr(out), C, B, heads, N, Nk, D, float(scale), st)
+    return out
+
+
+def dwconv3x3_gelu(x, w9c, bias, B, H, W):
+    st = _prep(x, w9c, bias)
+    C = x.shape[-1]
+    y = torch.empty_like(x)
+    _lib.call("segmif_dwconv3x3_gelu_fwd", _ptr(x), _ptr(w9c), _ptr(bias), _ptr(y), B, H, W, C, st)
+    return y
+
+
+def bilinear_nhwc(src, B, h, w, C, H, W, *, ld_src=None, out=None, out_dtype=torch.bfloat16, ld_dst=None, dst_coff=0):
+    st = _prep(src, out)
+    ld_src = C if ld_src is None else ld_src
+    if out is None:
+        ld_dst = C if ld_dst is None else ld_dst
+        out = torch.empty((B, H, W, ld_dst), dtype=out_dtype, device=src.device)
+    elif ld_dst is None:
+        ld_dst = out.shape[-1]
+    _lib.call("segmif_bilinear_nhwc_fwd", _ptr(src), _dt(src), B, h, w, C, ld_src, _ptr(out), _dt(out), H, W, ld_dst,
+              dst_coff, st)
+    return out
+
+
+def upsample_argmax(logits_nhwc, B, h, w, nc, H, W):
+    st = _prep(logits_nhwc)
+    assert logits_nhwc.dtype == torch.float32
+    labels = torch.empty((B, H, W), dtype=torch.int64, device=logits_nhwc.device)
+    _lib.call("segmif_upsample_argmax_fwd", _ptr(logits_nhwc), B, h, w, nc, _ptr(labels), H, W, st)
+    return labels
+
+
+def nhwc_to_nchw(src, B, HW, C, *, ld_src=None, src_coff=0, out=None):
+    st = _prep(src, out)
+    ld_src = C if ld_src is None else ld_src
+    if out is None:
+        out = torch.empty((B, C, HW), dtype=torch.float32, device=src.device)
+    _lib.call("segmif_nhwc_to_nchw", _ptr(src), _dt(src), ld_src, src_coff, _ptr(out), B, HW, C, st)
+    return out
+
+
+def nchw_to_nhwc(src, *, out=None, out_dtype=torch.bfloat16, ld_dst=None, dst_coff=0):
+    """src fp32 [B, C, ...spatial] -> pixel-major [B, HW, ld_dst]."""
+    st = _prep(src, out)
+    assert src.dtype == torch.float32
+    B, C = src.shape[0], src.shape[1]
+    HW = src.numel() // (B * C)
+    if out is None:
+        ld_dst = C if ld_dst is None else ld_dst
+        out = torch.empty((B, HW, ld_dst), dtype=out_dtype, device=src.device)
+    elif ld_dst is None:
+        ld_dst = out.shape[-1]
+    _lib.call("segmif_nchw_to_nhwc", _ptr(src), _ptr(out), _dt(out), ld_dst, dst_coff, B, HW, C, st)
+    return out
+
+
+def conv3x3_in1(img_nchw, w9c, bias, alpha, out, ld_dst, dst_coff, Cout):
+    """Channel 0 of an fp32 NCHW tensor -> bf16 pixel-major `out` channels dst_coff..dst_coff+Cout."""
+    st = _prep(w9c, bias, alpha, out)
+    B, C, H, W = img_nchw.shape
+    if not img_nchw.is_cuda or img_nchw.dtype != torch.float32 or img_nchw.stride(3) != 1 or img_nchw.stride(2) != W:
+        raise RuntimeError("segmif_b200.conv3x3_in1: need a CUDA fp32 NCHW tensor with dense rows")
+    _lib.call("segmif_conv3x3_in1_fwd", _ptr(img_nchw), img_nchw.stride(0), _ptr(w9c), _ptr(bias), _ptr(alpha), _ptr(out),
+              ld_dst, dst_coff, B, H, W, Cout, st)
+    return out
+
+
+def conv3x3_out1(src, w9c, bias, alpha, B, H, W, Cin, ld_src=None):
+    st = _prep(src, w9c, bias, alpha)
+    out = torch.empty((B, 1, H, W), dtype=torch.float32, device=src.device)
+    _lib.call("segmif_conv3x3_out1_fwd", _ptr(src), Cin if ld_src is None else ld_src, _ptr(w9c), _ptr(bias),
+              _ptr(alpha), _ptr(out), B, H, W, Cin, st)
+    return out
+
+
+def ffm(x1, ld1, coff1, x2, ld2, coff2, x3, ld3, C3, packs, out1, ldo1, coffo1, out2, ldo2, coffo2, B, HW,
+        want_ctx=False):
+    """Three-pass hierarchical interactive attention; `packs` is the dict built by core.model_fusion._pack_ffm."""
+    st = _prep(x1, x2, x3, out1, out2)
+    dev = x1.device
+    nchunk = max(1, min((148 * 4) // max(B, 1), (HW + 63) // 64))
+    partials = torch.empty((B, nchunk, 3, 64, 64), dtype=torch.float32, device=dev)
+    folded = torch.empty((B, 4, 64, 64), dtype=torch.bfloat16, device=dev)
+    ctx = torch.empty((B, 3, 8, 8, 8), dtype=torch.float32, device=dev) if want_ctx else None
+    _lib.call("segmif_ffm_gram_fwd", _ptr(x1), ld1, coff1, _ptr(x2), ld2, coff2, _ptr(x3), ld3, C3,
+              _ptr(packs["w_gram"]), _ptr(packs["b_gram"]), _ptr(partials), nchunk, B, HW, st)
+    _lib.call("segmif_ffm_ctx_fwd", _ptr(partials), nchunk, _ptr(packs["wkv"]), _ptr(packs["wend"]), _ptr(folded),
+              _ptr(ctx), B, st)
+    _lib.call("segmif_ffm_apply_fwd", _ptr(x1), ld1, coff1, _ptr(x2), ld2, coff2, _ptr(x3), ld3, C3,
+              _ptr(packs["w_apply"]), _ptr(packs["b_apply"]), _ptr(folded), _ptr(packs["bend"]), _ptr(packs["ln_g"]),
+              _ptr(packs["ln_b"]), 1e-5, _ptr(out1), ldo1, coffo1, _ptr(out2), ldo2, coffo2, B, HW, st)
+    return ctx
+
+
+def rgb2ycrcb(x):
+    st = _prep(x)
+    assert x.dtype == torch.float32 and x.shape[1] == 3
+    out = torch.empty_like(x)
+    _lib.call("segmif_rgb2ycrcb", _ptr(x), _ptr(out), x.shape[0], x.shape[2] * x.shape[3], st)
+    return out
+
+
+def ycrcb2rgb(x):
+    st = _prep(x)
+    assert x.dtype == torch.float32 and x.shape[1] == 3
+    out = torch.empty_like(x)
+    _lib.call("segmif_ycrcb2rgb", _ptr(x), _ptr(out), x.shape[0], x.shape[2] * x.shape[3], st)
+    return out
+
+
+def recompose_rgb(fused_y, vis_rgb, clamp=True):
+    st = _prep(fused_y, vis_rgb)
+    out = torch.empty_like(vis_rgb)
+    _lib.call("segmif_recompose_rgb", _ptr(fused_y), _ptr(vis_rgb), _ptr(out), 1 if clamp else 0, vis_rgb.shape[0],
+              vis_rgb.shape[2] * vis_rgb.shape[3], st)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- losses
+def _loss_ws(ref, B, H, W):
+    nbytes = _lib.load().segmif_loss_workspace_bytes(B, H, W)
+    return torch.empty(((nbytes + 3) // 4,), dtype=torch.float32, device=ref.device)
+
+
+def _plane(t):
+    if t.dim() != 4 or t.shape[1] != 1 or t.dtype != torch.float32:
+        raise ValueError("segmif_b200 losses take fp32 [B,1,H,W] planes")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def ssim(a, b, size_average=True):
+    a, b = _plane(a), _plane(b)
+    st = _prep(a, b)
+    B, _, H, W = a.shape
+    ws = _loss_ws(a, B, H, W)
+    out = torch.empty((1 if size_average else B,), dtype=torch.float32, device=a.device)
+    _lib.call("segmif_ssim_fwd", _ptr(a), _ptr(b), B, H, W, 0 if size_average else 1, _ptr(ws), _ptr(out), st)
+    return out[0] if size_average else out
+
+
+def laploss2(inp, ir, vis):
+    inp, ir, vis = _plane(inp), _plane(ir), _plane(vis)
+    st = _prep(inp, ir, vis)
+    B, _, H, W = inp.shape
+    ws = _loss_ws(inp, B, H, W)
+    out = torch.empty((1,), dtype=torch.float32, device=inp.device)
+    _lib.call("segmif_laploss2_fwd", _ptr(inp), _ptr(ir), _ptr(vis), B, H, W, _ptr(ws), _ptr(out), st)
+    return out[0]
+
+
+def laploss(inp, target):
+    inp, target = _plane(inp), _plane(target)
+    st = _prep(inp, target)
+    B, _, H, W = inp.shape
+    ws = _loss_ws(inp, B, H, W)
+    out = torch.empty((1,), dtype=torch.float32, device=inp.device)
+    _lib.call("segmif_laploss_fwd", _ptr(inp), _ptr(target), B, H, W, _ptr(ws), _ptr(out), st)
+    return out[0]
+
+
+def entropy(img, patch):
+    img = _plane(img)
+    st = _prep(img)
+    B, _, H, W = img.shape
+    ws = _loss_ws(img, B, H, W)
+    out = torch.empty((1,), dtype=torch.float32, device=img.device)
+    _lib.call("segmif_entropy_fwd", _ptr(img), B, H, W, int(patch), _ptr(ws), _ptr(out), st)
+    return out[0]
+
+
+def sobel_l1(x, y):
+    """returns (mean |x-y|, mean |sobel(x)-sobel(y)|)"""
+    x, y = _plane(x), _plane(y)
+    st = _prep(x, y)
+    B, _, H, W = x.shape
+    ws = _loss_ws(x, B, H, W)
+    out = torch.empty((2,), dtype=torch.float32, device=x.device)
+    _lib.call("segmif_sobel_l1_fwd", _ptr(x), _ptr(y), B, H, W, _ptr(ws), _ptr(out), st)
+    return out[0], out[1]
+
+
+def mse_l1(x, y):
+    """returns (mean (x-y)^2, mean |x-y|) over all elements"""
+    x = x if x.is_contiguous() else x.contiguous()
+    y = y if y.is_contiguous() else y.contiguous()
+    st = _prep(x, y)
+    ws = _loss_ws(x, 1, 32, 32)
+    out = torch.empty((2,), dtype=torch.float32, device=x.device)
+    _lib.call("segmif_mse_l1_fwd", _ptr(x), _ptr(y), x.numel(), _ptr(ws), _ptr(out), st)
+    return out[0], out[1]
+
+
+def upsample_ce(logits_nhwc, B, h, w, nc, labels, ignore_index=255):
+    st = _prep(logits_nhwc, labels)
+    H, W = labels.shape[1], labels.shape[2]
+    ws = _loss_ws(logits_nhwc, 1, 32, 32)
+    out = torch.empty((1,), dtype=torch.float32, device=labels.device)
+    _lib.call("segmif_upsample_ce_fwd", _ptr(logits_nhwc), B, h, w, nc, _ptr(labels), H, W, int(ignore_index),
+              _ptr(ws), _ptr(out), st)
+    return out[0]

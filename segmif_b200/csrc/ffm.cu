@@ -6,6 +6,8 @@
 //   the three needed 64-channel projections per pixel tile, applies the folded matrices, adds the
 //   residual and LayerNorms -- 384 B/px read in pass 1, 384 B/px read + 256 B/px written in pass 3.
 // conv3 / conv4 (1x1 on the segmentation features) are folded into channel_proj3 by the host.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace segmif {

@@ -3,6 +3,9 @@
 // upsample-fused cross entropy.  fp32 throughout (sigma^2 = E[x^2]-mu^2 cancels).
 // Every kernel writes one partial per block; finalize_kernel reduces them in fp64 in a fixed order, so
 // results are deterministic run to run.
+#include <algorithm>
+#include <math.h>
+
 #include "common.cuh"
 
 namespace segmif {
@@ -163,13 +166,13 @@ __global__ void __launch_bounds__(256) laploss_kernel(const float* __restrict__ 
 struct Bins32 { float b[32]; };
 
 template <int P>
-__global__ void __launch_bounds__(256) entropy_kernel(const float* __restrict__ img, int H, int W, Bins32 bins,
+__global__ void __launch_bounds__(256) entropy_kernel(const float* __restrict__ img, int B, int H, int W, Bins32 bins,
                                                       float* __restrict__ partials) {
   __shared__ float sred[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const int segs_x = (W + 31) / 32;
   const int prow = H / P;
-  const int64_t nseg = (int64_t)gridDim.y * prow * segs_x;   // gridDim.y == batch
+  const int64_t nseg = (int64_t)B * prow * segs_x;
   const float mybin = bins.b[lane];
   const float sigma = 0.01f;
   float total = 0.f;
@@ -431,14 +434,54 @@ extern "C" int segmif_entropy_fwd(const float* img, int B, int H, int W, int pat
   const float step = 1.0f / 31.0f;
   for (int i = 0; i < 32; ++i) bins.b[i] = i < 16 ? 0.0f + step * (float)i : 1.0f - step * (float)(31 - i);
   const int nblocks = 148 * 8;
-  dim3 grid(nblocks, B);   // gridDim.y only carries the batch count; blocks with y > 0 idle
   cudaStream_t st = as_stream(stream);
+  float* part = partial_area(workspace);
   switch (patch) {
-    case 2: entropy_kernel<2><<<dim3(nblocks, 1, 1), 256, 0, st>>>(img, H, W, bins, partial_area(workspace)); break;
-    default: break;
+    case 2: entropy_kernel<2><<<nblocks, 256, 0, st>>>(img, B, H, W, bins, part); break;
+    case 4: entropy_kernel<4><<<nblocks, 256, 0, st>>>(img, B, H, W, bins, part); break;
+    case 8: entropy_kernel<8><<<nblocks, 256, 0, st>>>(img, B, H, W, bins, part); break;
+    default: entropy_kernel<16><<<nblocks, 256, 0, st>>>(img, B, H, W, bins, part); break;
   }
-  // gridDim.y trick is awkward for a 1-D walk; pass the batch through a dedicated launch shape instead
-  (void)grid;
-  set_error("entropy: internal dispatch error");
-  return SEGMIF_ERR_INVALID;
+  int rc = check_launch("segmif_entropy_fwd");
+  if (rc) return rc;
+  return finish(workspace, 1, nblocks, 1, 2, 1.0, out, st, "segmif_entropy_fwd");
+}
+
+extern "C" int segmif_sobel_l1_fwd(const float* x, const float* y, int B, int H, int W, float* workspace, float* out,
+                                   segmif_stream_t stream) {
+  SEGMIF_REQUIRE(x && y && workspace && out, "sobel_l1: null pointer");
+  SEGMIF_REQUIRE(B > 0 && H > 0 && W > 0, "sobel_l1: empty input");
+  const int64_t n = (int64_t)B * H * W;
+  const int nblocks = (int)std::min<int64_t>(ceil_div(n, 256), 148 * 8);
+  cudaStream_t st = as_stream(stream);
+  sobel_l1_kernel<<<nblocks, 256, 0, st>>>(x, y, B, H, W, partial_area(workspace));
+  int rc = check_launch("segmif_sobel_l1_fwd");
+  if (rc) return rc;
+  return finish(workspace, 1, nblocks, 2, 3, 1.0 / (double)n, out, st, "segmif_sobel_l1_fwd");
+}
+
+extern "C" int segmif_mse_l1_fwd(const float* x, const float* y, int64_t n, float* workspace, float* out,
+                                 segmif_stream_t stream) {
+  SEGMIF_REQUIRE(x && y && workspace && out && n > 0, "mse_l1: bad arguments");
+  const int nblocks = (int)std::min<int64_t>(ceil_div(n, 256), 148 * 8);
+  cudaStream_t st = as_stream(stream);
+  mse_l1_kernel<<<nblocks, 256, 0, st>>>(x, y, n, partial_area(workspace));
+  int rc = check_launch("segmif_mse_l1_fwd");
+  if (rc) return rc;
+  return finish(workspace, 1, nblocks, 2, 3, 1.0 / (double)n, out, st, "segmif_mse_l1_fwd");
+}
+
+extern "C" int segmif_upsample_ce_fwd(const float* logits, int B, int h, int w, int nc, const int64_t* labels, int H,
+                                      int W, int ignore_index, float* workspace, float* out, segmif_stream_t stream) {
+  SEGMIF_REQUIRE(logits && labels && workspace && out, "upsample_ce: null pointer");
+  SEGMIF_REQUIRE(nc > 0 && nc <= 32, "upsample_ce: nc=%d unsupported (1..32)", nc);
+  const int64_t n = (int64_t)B * H * W;
+  SEGMIF_REQUIRE(n > 0, "upsample_ce: empty input");
+  const int nblocks = (int)std::min<int64_t>(ceil_div(n, 256), 148 * 8);
+  cudaStream_t st = as_stream(stream);
+  upsample_ce_kernel<<<nblocks, 256, 0, st>>>(logits, B, h, w, nc, labels, H, W, ignore_index, (float)h / (float)H,
+                                              (float)w / (float)W, partial_area(workspace));
+  int rc = check_launch("segmif_upsample_ce_fwd");
+  if (rc) return rc;
+  return finish(workspace, 1, nblocks, 2, 4, 1.0, out, st, "segmif_upsample_ce_fwd");
 }

@@ -1,6 +1,8 @@
 // Bandwidth-bound row / pixel kernels of the MiT encoder and the decode head:
 // LayerNorm, depthwise 3x3 + GELU, 7x7 patch embedding + LayerNorm, bilinear resize,
 // upsample+argmax, NCHW<->NHWC converters.  All fp32 math, 128-bit accesses where alignment allows.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace segmif {

@@ -1,0 +1,460 @@
+"""Parity checks of the CUDA path (called through the C ABI) against the CPU oracle.
+
+Each check returns a dict(name, err, tol, ok, note).  tests/test_gpu_parity.py turns every check into a
+pytest case (marker `gpu`); tools/run_gpu_checks.py runs them all without stopping and writes a JSON report
+(useful because the GPU box is remote: one call, all diagnostics).
+
+Tolerances (stated per check):
+  * fp32 kernels (LayerNorm fp32 out, losses, colour, resize): <= 1e-5 relative -- reordering of fp32 sums only.
+  * tensor-core kernels are fed bf16-representable inputs/weights and checked with fp32 OUTPUT against the fp32
+    oracle on the same values: <= 1e-3 relative to the output's max |value| (north_star's fp32 tolerance);
+    with bf16 output the bound is bf16 rounding, 2^-8 = 3.9e-3.
+  * multi-kernel bf16 pipelines (DRDB, FFM, encoder, whole pipeline): error grows with depth; bounds are stated
+    at each check and were set from measured error with ~3x headroom.
+"""
+import math
+import os
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from oracle import segmif_oracle as O
+from segmif_b200 import ops, synth
+from segmif_b200.ops import ACT_GELU, ACT_NONE, ACT_PRELU, ACT_RELU
+
+DEV = "cuda"
+CHECKS = []
+
+
+def check(fn):
+    CHECKS.append(fn)
+    return fn
+
+
+def rel_err(got, ref):
+    got = got.detach().double().cpu()
+    ref = ref.detach().double().cpu()
+    denom = float(ref.abs().max()) + 1e-30
+    return float((got - ref).abs().max()) / denom
+
+
+def result(name, err, tol, note=""):
+    ok = bool(err <= tol) and math.isfinite(err)
+    return dict(name=name, err=float(err), tol=float(tol), ok=ok, note=note)
+
+
+def rnd(*shape, seed=0, scale=1.0, bf16=True):
+    g = torch.Generator().manual_seed(seed)
+    t = torch.randn(*shape, generator=g) * scale
+    return t.bfloat16().float() if bf16 else t
+
+
+def pack_conv(w):
+    return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1, w.shape[1]).to(torch.bfloat16).contiguous().to(DEV)
+
+
+def pack_lin(w):
+    return w.to(torch.bfloat16).reshape(w.shape[0], 1, w.shape[1]).contiguous().to(DEV)
+
+
+# ----------------------------------------------------------------------------------------- LayerNorm
+@check
+def layernorm():
+    worst, worst_b = 0.0, 0.0
+    for i, C in enumerate((32, 64, 128, 160, 256, 320, 512)):
+        for eps in (1e-5, 1e-6):
+            x = rnd(77, C, seed=i, scale=3.0, bf16=False) + 0.5
+            g, b = 1 + 0.1 * rnd(C, seed=100 + i, bf16=False), 0.1 * rnd(C, seed=200 + i, bf16=False)
+            ref = F.layer_norm(x, (C,), g, b, eps)
+            y32 = ops.layernorm(x.to(DEV), g.to(DEV), b.to(DEV), eps, out_dtype=torch.float32)
+            y16 = ops.layernorm(x.to(DEV), g.to(DEV), b.to(DEV), eps, out_dtype=torch.bfloat16)
+            worst = max(worst, rel_err(y32, ref))
+            worst_b = max(worst_b, rel_err(y16.float(), ref))
+    r = result("layernorm_fp32_out", worst, 1e-5)
+    r2 = result("layernorm_bf16_out", worst_b, 4e-3)
+    r["ok"] = r["ok"] and r2["ok"]
+    r["note"] = f"bf16-out err {worst_b:.2e} (tol 4e-3)"
+    return r
+
+
+# ----------------------------------------------------------------------------------------- linear / conv
+def _conv_case(name, B, H, W, Cin, Cout, k=1, stride=1, pad=0, dil=1, act=ACT_NONE, residual=None, bias=True,
+               ld_src=None, src_coff=0, ld_dst=None, dst_coff=0, out_dtype=torch.float32, seed=0, tol=1e-3):
+    ld_src = ld_src or Cin
+    x_full = rnd(B, H, W, ld_src, seed=seed)
+    w = rnd(Cout, Cin, k, k, seed=seed + 1, scale=1.0 / math.sqrt(Cin * k * k))
+    bv = rnd(Cout, seed=seed + 2, bf16=False) * 0.1 if bias else None
+    alpha = torch.tensor([0.25])
+    x = x_full[..., src_coff:src_coff + Cin]
+    ref = F.conv2d(x.permute(0, 3, 1, 2), w, bv, stride=stride, padding=pad, dilation=dil)
+    if act == ACT_RELU:
+        ref = F.relu(ref)
+    elif act == ACT_PRELU:
+        ref = F.prelu(ref, alpha)
+    elif act == ACT_GELU:
+        ref = F.gelu(ref)
+    ref = ref.permute(0, 2, 3, 1).reshape(-1, Cout)
+    res_t = None
+    if residual is not None:
+        res_t = rnd(ref.shape[0], Cout, seed=seed + 3, bf16=(residual == torch.bfloat16))
+        ref = ref + res_t
+        res_t = res_t.to(residual).to(DEV)
+    ld_dst = ld_dst or Cout
+    out = torch.full((ref.shape[0], ld_dst), 7.0, dtype=out_dtype, device=DEV)
+    ops.conv(x_full.bfloat16().to(DEV), pack_conv(w), bv.to(DEV) if bias else None, B=B, H=H, W=W, Cin=Cin, KH=k, KW=k,
+             stride=stride, pad=pad, dil=dil, Cout=Cout, ld_src=ld_src, src_coff=src_coff, act=act,
+             prelu_alpha=alpha.to(DEV) if act == ACT_PRELU else None, residual=res_t, out=out, ld_dst=ld_dst,
+             dst_coff=dst_coff)
+    got = out[:, dst_coff:dst_coff + Cout].float()
+    err = rel_err(got, ref)
+    untouched = True
+    if ld_dst > Cout:
+        mask = torch.ones(ld_dst, dtype=torch.bool)
+        mask[dst_coff:dst_coff + Cout] = False
+        untouched = bool((out[:, mask.to(DEV)] == 7.0).all())
+    r = result(name, err, tol)
+    if not untouched:
+        r["ok"] = False
+        r["note"] = "wrote outside its channel slice"
+    return r
+
+
+@check
+def linear_shapes():
+    rs = [
+        _conv_case("lin_64x64", 1, 1, 1000, 64, 64),
+        _conv_case("lin_512x2048_gelu", 1, 1, 300, 512, 2048, act=ACT_GELU, seed=3),
+        _conv_case("lin_2048x512_res_f32", 1, 1, 300, 2048, 512, residual=torch.float32, seed=4),
+        _conv_case("lin_320x320_res", 1, 1, 333, 320, 320, residual=torch.float32, seed=5),
+        _conv_case("lin_256x9_pred", 1, 1, 500, 256, 9, seed=6),
+        _conv_case("lin_1024x256_relu", 1, 1, 700, 1024, 256, act=ACT_RELU, seed=7),
+        _conv_case("lin_64x128_nobias", 1, 1, 129, 64, 128, bias=False, seed=8),
+        _conv_case("lin_160x160_b0", 1, 1, 200, 160, 160, seed=9),
+        _conv_case("lin_bf16_out", 1, 1, 512, 128, 128, out_dtype=torch.bfloat16, seed=10, tol=4e-3),
+        _conv_case("lin_slice_dst", 1, 1, 257, 64, 256, ld_dst=1024, dst_coff=768, out_dtype=torch.bfloat16, seed=11, tol=4e-3),
+    ]
+    return rs
+
+
+@check
+def conv_shapes():
+    rs = [
+        _conv_case("drdb_dcov_96_dil2_inplace_layout", 2, 20, 28, 96, 32, k=3, pad=2, dil=2, act=ACT_RELU, ld_src=224,
+                   ld_dst=224, dst_coff=96, out_dtype=torch.bfloat16, seed=20, tol=4e-3),
+        _conv_case("drdb_dcov_192_dil2", 1, 17, 23, 192, 32, k=3, pad=2, dil=2, act=ACT_RELU, seed=21),
+        _conv_case("drdb_1x1_224_res_bf16", 1, 16, 24, 224, 64, act=ACT_RELU, residual=torch.bfloat16, seed=22),
+        _conv_case("conv2_128_64_prelu", 2, 16, 24, 128, 64, k=3, pad=1, act=ACT_PRELU, seed=23),
+        _conv_case("conv21_64_32_prelu", 1, 19, 21, 64, 32, k=3, pad=1, act=ACT_PRELU, seed=24),
+        _conv_case("patch_embed_k3s2", 2, 16, 24, 64, 128, k=3, stride=2, pad=1, seed=25),
+        _conv_case("patch_embed_k3s2_odd", 1, 15, 21, 128, 320, k=3, stride=2, pad=1, seed=26),
+        _conv_case("sr_k8s8", 2, 16, 24, 64, 64, k=8, stride=8, seed=27),
+        _conv_case("sr_k2s2_320", 1, 4, 6, 320, 320, k=2, stride=2, seed=28),
+        _conv_case("src_slice", 1, 9, 11, 32, 32, k=3, pad=1, ld_src=96, src_coff=64, seed=29),
+    ]
+    return rs
+
+
+# ----------------------------------------------------------------------------------------- attention
+@check
+def attention():
+    rs = []
+    for name, B, heads, N, Nk, D in (("attn_h1_N384_Nk300", 2, 1, 384, 300, 64), ("attn_h2_N100_Nk37", 1, 2, 100, 37, 64),
+                                     ("attn_h5_N130_Nk128", 2, 5, 130, 128, 64), ("attn_h8_N6_Nk6", 1, 8, 6, 6, 64),
+                                     ("attn_b0_D32", 2, 2, 150, 70, 32), ("attn_Nk1024", 1, 1, 256, 1024, 64)):
+        C = heads * D
+        q = rnd(B, N, C, seed=1)
+        kv = rnd(B, Nk, 2 * C, seed=2)
+        k, v = kv[..., :C], kv[..., C:]
+        qh = q.reshape(B, N, heads, D).permute(0, 2, 1, 3)
+        kh = k.reshape(B, Nk, heads, D).permute(0, 2, 1, 3)
+        vh = v.reshape(B, Nk, heads, D).permute(0, 2, 1, 3)
+        att = ((qh @ kh.transpose(-2, -1)) * D ** -0.5).softmax(-1)
+        ref = (att @ vh).transpose(1, 2).reshape(B * N, C)
+        got = ops.sr_attention(q.bfloat16().reshape(B * N, C).to(DEV), kv.bfloat16().reshape(B * Nk, 2 * C).to(DEV), B,
+                               heads, N, Nk, D, D ** -0.5)
+        # P is rounded to bf16 before the PV product and the output is bf16: bound = a few bf16 ulps
+        rs.append(result(name, rel_err(got.float(), ref), 1.2e-2))
+    return rs
+
+
+# ----------------------------------------------------------------------------------------- dwconv / patch embed / resize
+@check
+def dwconv_gelu():
+    B, H, W, C = 2, 13, 17, 256
+    x = rnd(B, H, W, C, seed=5)
+    w = rnd(C, 1, 3, 3, seed=6, bf16=False) * 0.3
+    b = rnd(C, seed=7, bf16=False) * 0.1
+    ref = F.gelu(F.conv2d(x.permute(0, 3, 1, 2), w, b, padding=1, groups=C)).permute(0, 2, 3, 1)
+    got = ops.dwconv3x3_gelu(x.bfloat16().to(DEV), w.reshape(C, 9).t().contiguous().to(DEV), b.to(DEV), B, H, W)
+    return result("dwconv3x3_gelu_bf16_out", rel_err(got.float().view(B, H, W, C), ref), 4e-3)
+
+
+@check
+def patch_embed():
+    rs = []
+    for name, C0, H, W, affine in (("pe7_c64", 64, 64, 96, False), ("pe7_c64_affine", 64, 50, 70, True), ("pe7_c32_b0", 32, 33, 47, False)):
+        img = rnd(2, 3, H, W, seed=9, bf16=False).abs()
+        w = rnd(C0, 3, 7, 7, seed=10, bf16=False) * 0.1
+        b = rnd(C0, seed=11, bf16=False) * 0.1
+        g, be = 1 + 0.1 * rnd(C0, seed=12, bf16=False), 0.1 * rnd(C0, seed=13, bf16=False)
+        sc = sh = None
+        x = img
+        if affine:
+            sc = (255.0 / torch.tensor(O.IMAGENET_STD)).float()
+            sh = (-torch.tensor(O.IMAGENET_MEAN) / torch.tensor(O.IMAGENET_STD)).float()
+            x = (img * 255 - torch.tensor(O.IMAGENET_MEAN).view(1, 3, 1, 1)) / torch.tensor(O.IMAGENET_STD).view(1, 3, 1, 1)
+        y = F.conv2d(x, w, b, stride=4, padding=3)
+        ref = F.layer_norm(y.flatten(2).transpose(1, 2), (C0,), g, be, 1e-5)
+        tok, Ho, Wo = ops.patch_embed7_ln(img.to(DEV), w.reshape(C0, -1).t().contiguous().to(DEV), b.to(DEV), g.to(DEV),
+                                          be.to(DEV), 1e-5, sc.to(DEV) if affine else None, sh.to(DEV) if affine else None)
+        r = result(name, rel_err(tok, ref), 2e-5)
+        r["ok"] = r["ok"] and (Ho, Wo) == tuple(y.shape[2:])
+        rs.append(r)
+    return rs
+
+
+@check
+def bilinear_and_argmax():
+    rs = []
+    x = rnd(2, 15, 20, 64, seed=3, bf16=False)
+    ref = F.interpolate(x.permute(0, 3, 1, 2), size=(60, 80), mode="bilinear", align_corners=False).permute(0, 2, 3, 1)
+    got = ops.bilinear_nhwc(x.to(DEV), 2, 15, 20, 64, 60, 80, out_dtype=torch.float32)
+    rs.append(result("bilinear_x4_fp32", rel_err(got, ref), 1e-5))
+    ref = F.interpolate(x.permute(0, 3, 1, 2), size=(37, 53), mode="bilinear", align_corners=False).permute(0, 2, 3, 1)
+    got = ops.bilinear_nhwc(x.to(DEV), 2, 15, 20, 64, 37, 53, out_dtype=torch.float32)
+    rs.append(result("bilinear_odd_fp32", rel_err(got, ref), 1e-5))
+    lg = rnd(2, 16, 24, 9, seed=4, bf16=False)
+    up = F.interpolate(lg.permute(0, 3, 1, 2), size=(64, 96), mode="bilinear", align_corners=False)
+    ref_lab = up.argmax(1)
+    got_lab = ops.upsample_argmax(lg.to(DEV), 2, 16, 24, 9, 64, 96).cpu()
+    mism = (got_lab != ref_lab)
+    # any mismatch must be a numerical tie (top-2 margin below fp32 noise)
+    top2 = up.topk(2, dim=1).values
+    margin = (top2[:, 0] - top2[:, 1])[mism]
+    bad = int((margin > 1e-5).sum()) if mism.any() else 0
+    r = result("upsample_argmax_labels", float(bad), 0.0, note=f"{int(mism.sum())} of {mism.numel()} differ, all near-ties" if mism.any() else "bit-exact")
+    rs.append(r)
+    return rs
+
+
+@check
+def layout_and_colour():
+    rs = []
+    x = rnd(2, 37, 5, 7, seed=1, bf16=False)              # NCHW [2,37,5,7]
+    t = ops.nchw_to_nhwc(x.to(DEV), out_dtype=torch.float32)
+    rs.append(result("nchw_to_nhwc", rel_err(t.view(2, 5, 7, 37), x.permute(0, 2, 3, 1)), 0.0))
+    back = ops.nhwc_to_nchw(t, 2, 35, 37)
+    rs.append(result("nhwc_to_nchw", rel_err(back.view(2, 37, 5, 7), x), 0.0))
+    img = rnd(2, 3, 21, 33, seed=2, bf16=False).abs()
+    ycc = ops.rgb2ycrcb(img.to(DEV))
+    rs.append(result("rgb2ycrcb", rel_err(ycc, O.rgb2ycrcb(img)), 1e-6))
+    rs.append(result("ycrcb2rgb", rel_err(ops.ycrcb2rgb(ycc), O.ycrcb2rgb(O.rgb2ycrcb(img))), 1e-6))
+    fused = rnd(2, 1, 21, 33, seed=3, bf16=False)
+    rs.append(result("recompose_rgb", rel_err(ops.recompose_rgb(fused.to(DEV), img.to(DEV)), O.recompose_rgb(fused, O.rgb2ycrcb(img))), 1e-6))
+    return rs
+
+
+@check
+def edge_convs():
+    rs = []
+    B, H, W = 2, 19, 27
+    img = rnd(B, 3, H, W, seed=1, bf16=False)
+    w = rnd(64, 1, 3, 3, seed=2, bf16=False) * 0.3
+    b = rnd(64, seed=3, bf16=False) * 0.1
+    a = torch.tensor([0.25])
+    ref = F.prelu(F.conv2d(img[:, 0:1], w, b, padding=1), a).permute(0, 2, 3, 1)
+    buf = torch.zeros((B, H, W, 224), dtype=torch.bfloat16, device=DEV)
+    ops.conv3x3_in1(img.to(DEV), w.reshape(64, 9).t().contiguous().to(DEV), b.to(DEV), a.to(DEV), buf, 224, 0, 64)
+    rs.append(result("conv1_in1_prelu", rel_err(buf[..., :64].float(), ref), 4e-3))
+    x = rnd(B, H, W, 32, seed=4)
+    w2 = rnd(1, 32, 3, 3, seed=5, bf16=False) * 0.1
+    b2 = torch.tensor([0.03])
+    ref2 = F.prelu(F.conv2d(x.permute(0, 3, 1, 2), w2, b2, padding=1), a)
+    got2 = ops.conv3x3_out1(x.bfloat16().to(DEV), w2.reshape(32, 9).t().contiguous().to(DEV), b2.to(DEV), a.to(DEV), B, H, W, 32)
+    rs.append(result("conv22_out1_prelu", rel_err(got2, ref2), 1e-5))
+    return rs
+
+
+# ----------------------------------------------------------------------------------------- losses
+@check
+def losses():
+    rs = []
+    a, b, c = synth.analytic_images()
+    A, Bq, Cq = a.to(DEV), b.to(DEV), c.to(DEV)
+    rs.append(result("ssim_kat", abs(float(ops.ssim(A, Bq)) - 0.32508987) / 0.325, 1e-5))
+    per = ops.ssim(A, Bq, size_average=False).cpu()
+    rs.append(result("ssim_per_image_kat", float((per - torch.tensor([0.32683358, 0.32334623])).abs().max()) / 0.32, 1e-5))
+    rs.append(result("laploss2_kat", abs(float(ops.laploss2(A, Bq, Cq)) - 0.32943434) / 0.329, 1e-5))
+    rs.append(result("laploss_kat", abs(float(ops.laploss(A, Bq)) - 0.22952789) / 0.2295, 1e-5))
+    rs.append(result("entropy4_kat", abs(float(ops.entropy(A, 4)) - 1350.0389) / 1350.0, 1e-5))
+    rs.append(result("entropy8_kat", abs(float(ops.entropy(A, 8)) - 460.45056) / 460.0, 1e-5))
+    inp = synth.synth_inputs(3, 70, 100, seed=5)      # sizes that are not tile multiples
+    ir, vis, mask = inp["ir"], inp["vis"][:, :1].contiguous(), inp["mask"][:, :1].contiguous()
+    fused = (0.6 * ir + 0.4 * vis).clamp(0, 1)
+    rs.append(result("ssim_random", rel_err(ops.ssim(fused.to(DEV), mask.to(DEV)), O.ssim(fused, mask)), 1e-5))
+    rs.append(result("laploss2_random", rel_err(ops.laploss2(fused.to(DEV), ir.to(DEV), vis.to(DEV)), O.lap_loss2(fused, ir, vis)), 1e-5))
+    big = synth.synth_inputs(2, 64, 96, seed=6)["ir"]
+    rs.append(result("entropy4_random", rel_err(ops.entropy(big.to(DEV), 4), O.entropy(big, 4)), 1e-5))
+    rs.append(result("entropy16_random", rel_err(ops.entropy(big.to(DEV), 16), O.entropy(big, 16)), 1e-5))
+    l1, lg = ops.sobel_l1(mask.to(DEV), fused.to(DEV))
+    rs.append(result("sobel_l1", rel_err(l1 + lg, O.fusionloss3(ir, inp["vis"], fused, inp["mask"])), 1e-5))
+    mse, l1b = ops.mse_l1(mask.to(DEV), fused.to(DEV))
+    rs.append(result("mse", rel_err(mse, F.mse_loss(mask, fused)), 1e-5))
+    rs.append(result("l1", rel_err(l1b, F.l1_loss(mask, fused)), 1e-5))
+    lgts = rnd(2, 16, 24, 9, seed=7, bf16=False)
+    labels = synth.synth_inputs(2, 64, 96, seed=8)["labels"]
+    ref = O.seg_cross_entropy(lgts.permute(0, 3, 1, 2), labels)
+    rs.append(result("upsample_ce", rel_err(ops.upsample_ce(lgts.to(DEV), 2, 16, 24, 9, labels.to(DEV)), ref), 1e-5))
+    return rs
+
+
+@check
+def loss_modules():
+    """The reference-named loss classes (core.loss, pytorch_ssim, lap_loss, core.Entropy) against the golden fixtures."""
+    from conftest import GOLDEN
+    from segmif_b200 import lap_loss as LL, pytorch_ssim as PS
+    from segmif_b200.core import loss as CL
+    from segmif_b200.core.Entropy import Entropy
+    g = np.load(os.path.join(GOLDEN, "losses.npz"))
+    inp = synth.synth_inputs(2, 48, 80, seed=3)
+    ir, vis, mask = inp["ir"], inp["vis"], inp["mask"]
+    fused = (0.6 * ir + 0.4 * vis[:, :1]).clamp(0, 1)
+    d = lambda t: t.to(DEV)
+    rs = []
+    with torch.no_grad():
+        rs.append(result("mod_ssim", rel_err(PS.ssim(d(fused), d(mask[:, :1])), torch.tensor(g["rnd_ssim"])), 1e-5))
+        rs.append(result("mod_SSIM_class", rel_err(PS.SSIM()(d(fused), d(mask[:, :1])), torch.tensor(g["rnd_ssim"])), 1e-5))
+        rs.append(result("mod_LapLoss2", rel_err(LL.LapLoss2()(d(fused), d(ir), d(vis[:, :1])), torch.tensor(g["rnd_lap2"])), 1e-5))
+        rs.append(result("mod_Entropy4", rel_err(Entropy(4)(d(fused)), torch.tensor(g["rnd_entropy4"])), 1e-5))
+        rs.append(result("mod_Fusionloss3", rel_err(CL.Fusionloss3()(d(ir), d(vis), d(fused), d(mask)), torch.tensor(g["rnd_fusionloss3"])), 1e-5))
+        rs.append(result("mod_Fusionloss_grad3", rel_err(CL.Fusionloss_grad3()(d(ir), d(vis), d(fused), d(mask)), torch.tensor(g["rnd_fusionloss_grad3"])), 1e-5))
+        rs.append(result("mod_Fusionloss_grad2", rel_err(CL.Fusionloss_grad2()(d(ir), d(vis), d(fused), d(mask)), torch.tensor(g["rnd_fusionloss_grad2"])), 1e-5))
+    return rs
+
+
+# ----------------------------------------------------------------------------------------- modules vs oracle / golden
+def _golden():
+    from conftest import GOLDEN
+    return np.load(os.path.join(GOLDEN, "pipeline_mit_b1_64x96.npz"))
+
+
+_MODELS = {}
+
+
+def models(backbone="mit_b1"):
+    if backbone not in _MODELS:
+        from segmif_b200.core.model_fusion import Fusion_Network3_ac, Network3
+        seg = synth.load_synthetic(Network3(backbone, 9, 256, None), 0).eval()
+        fus = synth.load_synthetic(Fusion_Network3_ac(), 0).eval()
+        sds = ({k: v.clone() for k, v in seg.state_dict().items()}, {k: v.clone() for k, v in fus.state_dict().items()})
+        _MODELS[backbone] = (seg.to(DEV), fus.to(DEV), sds)
+    return _MODELS[backbone]
+
+
+@check
+def drdb_module():
+    seg, fus, (seg_sd, fus_sd) = models()
+    x = rnd(1, 64, 24, 40, seed=1)
+    with torch.no_grad():
+        ref = O.drdb(x, fus_sd, "DRDB1")
+        got = fus.DRDB1(x.to(DEV))
+    # 6 chained bf16 tensor-core layers with bf16 storage between them
+    return result("DRDB_vs_oracle", rel_err(got, ref), 2e-2)
+
+
+@check
+def ffm_module():
+    seg, fus, (seg_sd, fus_sd) = models()
+    rs = []
+    x1, x2, s3 = rnd(2, 64, 24, 40, seed=1), rnd(2, 64, 24, 40, seed=2), rnd(2, 64, 24, 40, seed=3)
+    with torch.no_grad():
+        r1, r2 = O.feature_fusion_module(x1, x2, s3, fus_sd, "ffm")
+        g1, g2 = fus.ffm(x1.to(DEV), x2.to(DEV), s3.to(DEV))
+    rs.append(result("FFM_out1_vs_oracle", rel_err(g1, r1), 3e-2))
+    rs.append(result("FFM_out2_vs_oracle", rel_err(g2, r2), 3e-2))
+    # contexts (fp32 on both sides, ours from bf16-rounded projections)
+    with torch.no_grad():
+        B, C, H, W = x1.shape
+        tok = lambda t: ops.nchw_to_nhwc(t.to(DEV), out_dtype=torch.bfloat16)
+        pk = fus.ffm.cross.packs()
+        o1 = torch.empty((B, H * W, 64), dtype=torch.bfloat16, device=DEV)
+        o2 = torch.empty_like(o1)
+        ctx = ops.ffm(tok(x1), 64, 0, tok(x2), 64, 0, tok(s3), 64, 64, pk, o1, 64, 0, o2, 64, 0, B, H * W, want_ctx=True).cpu()
+        sd, name = fus_sd, "ffm.cross"
+        t = lambda z: z.flatten(2).transpose(1, 2)
+        y1, u1 = F.relu(O._linear(t(x1), sd, name + ".channel_proj1")).chunk(2, -1)
+        y2, u2 = F.relu(O._linear(t(x2), sd, name + ".channel_proj2")).chunk(2, -1)
+        y3, u3 = F.relu(O._linear(t(s3), sd, name + ".channel_proj3")).chunk(2, -1)
+        kv1 = F.linear(y1, sd[name + ".cross_attn2.kv1.weight"])
+        kv2 = F.linear(y2, sd[name + ".cross_attn2.kv2.weight"])
+        kv3 = F.linear(u3, sd[name + ".cross_attn.kv3.weight"])
+        ref_ctx = torch.stack([O._ctx(kv1[..., :64], kv1[..., 64:], 8), O._ctx(kv2[..., :64], kv2[..., 64:], 8),
+                               O._ctx(kv3[..., :64], kv3[..., 64:], 8)], dim=1)
+    rs.append(result("FFM_ctx_softmax", float((ctx - ref_ctx).abs().max()), 5e-3, note="abs error of softmaxed 8x8 contexts"))
+    return rs
+
+
+@check
+def encoder_features_golden():
+    seg, fus, _ = models()
+    g = _golden()
+    inp = synth.synth_inputs(1, 64, 96, seed=0)
+    with torch.no_grad():
+        feats = seg.denoise_net.encoder.forward_features(inp["mask"].to(DEV))
+    rs = []
+    for i, f in enumerate(feats):
+        rs.append(result(f"encoder_feat{i}_vs_reference", rel_err(f, torch.from_numpy(g[f"feat{i}"])), 3e-2))
+    return rs
+
+
+@check
+def pipeline_golden():
+    from segmif_b200.pipeline import FusionSegPipeline
+    seg, fus, _ = models()
+    g = _golden()
+    inp = synth.synth_inputs(1, 64, 96, seed=0)
+    pipe = FusionSegPipeline(seg, fus)
+    with torch.no_grad():
+        out = pipe(inp["ir"].to(DEV), inp["vis"].to(DEV), inp["mask"].to(DEV), return_intermediates=True)
+    rs = []
+    rs.append(result("pipe_out0_vs_reference", rel_err(out["out0"].float()[:, ::4, ::4, ::4], torch.from_numpy(g["out0_s"])), 3e-2))
+    rs.append(result("pipe_out1_vs_reference", rel_err(out["out1"].float()[:, ::8, ::4, ::4], torch.from_numpy(g["out1_s"])), 3e-2))
+    rs.append(result("pipe_fused_vs_reference", rel_err(out["fused"], torch.from_numpy(g["fused"])), 5e-2))
+    rs.append(result("pipe_rgb_vs_reference", rel_err(out["rgb"][:, :, ::2, ::2], torch.from_numpy(g["rgb_s"])), 3e-2))
+    rs.append(result("pipe_logits_vs_reference", rel_err(out["logits"], torch.from_numpy(g["logits"])), 5e-2))
+    lab = out["labels"].cpu().numpy().astype(np.int16)
+    agree = float((lab == g["labels"]).mean())
+    rs.append(result("pipe_label_agreement", 1.0 - agree, 0.03, note=f"{agree * 100:.2f}% of pixels equal the reference's labels (bf16 path)"))
+    return rs
+
+
+@check
+def ce_and_label_modules():
+    seg, fus, _ = models()
+    g = _golden()
+    inp = synth.synth_inputs(1, 64, 96, seed=0)
+    rgb_ref = None
+    with torch.no_grad():
+        from segmif_b200.pipeline import FusionSegPipeline
+        out = FusionSegPipeline(seg, fus)(inp["ir"].to(DEV), inp["vis"].to(DEV), inp["mask"].to(DEV), return_intermediates=True)
+        ce = seg._loss(out["rgb"], inp["labels"].to(DEV), torch.nn.CrossEntropyLoss(ignore_index=255))
+    return result("network3_loss_ce_vs_reference", rel_err(ce, torch.tensor(g["ce"])), 2e-2)
+
+
+def run_all(verbose=True):
+    out = []
+    for fn in CHECKS:
+        try:
+            r = fn()
+            rs = r if isinstance(r, list) else [r]
+        except Exception as e:  # noqa: BLE001 -- report and continue: one remote GPU call should surface everything
+            import traceback
+            rs = [dict(name=fn.__name__, err=float("nan"), tol=0.0, ok=False, note="EXCEPTION: " + repr(e) + "\n" + traceback.format_exc()[-1500:])]
+        for x in rs:
+            x["group"] = fn.__name__
+            if verbose:
+                print(("PASS " if x["ok"] else "FAIL ") + f"{x['name']:<40} err={x['err']:.3e} tol={x['tol']:.1e} {x.get('note', '')}", flush=True)
+        out.extend(rs)
+        torch.cuda.synchronize()
+    return out

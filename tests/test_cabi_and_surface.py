@@ -1,0 +1,109 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/segmif_b200.h declares (no compute
+calls without a GPU), the Python mirror has the reference's state_dict surface, and the product path refuses to
+run without CUDA instead of falling back."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, ROOT
+
+
+def test_library_exports_every_declared_symbol():
+    from segmif_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "segmif_b200.h")).read()
+    declared = set(re.findall(r"\b(segmif_[a-z0-9_]+)\s*\(", header))
+    declared -= {"segmif_conv_params"}
+    lib = _lib.load()
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, missing
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.segmif_abi_version() == 1
+
+
+def test_init_reports_missing_device_loudly():
+    from segmif_b200 import _lib
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    rc = _lib.load().segmif_init(0)
+    assert rc != 0 and "CUDA" in _lib.last_error()
+
+
+def test_no_cpu_fallback():
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from segmif_b200 import ops
+    with pytest.raises(RuntimeError, match="no CPU path|CUDA"):
+        ops.layernorm(torch.zeros(4, 64), torch.ones(64), torch.zeros(64), 1e-5)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "segmif_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f"{f} imports the oracle"
+
+
+def _keys(mod):
+    return [f"{k}|{','.join(map(str, v.shape))}" for k, v in mod.state_dict().items()]
+
+
+def test_state_dict_surface_matches_reference():
+    from segmif_b200.core.model_fusion import Fusion_Network3_ac, Network3
+    g = np.load(os.path.join(GOLDEN, "state_dict_keys.npz"))
+    assert _keys(Fusion_Network3_ac()) == [str(s) for s in g["fusion_keys"]]
+    for bb in ("mit_b0", "mit_b1", "mit_b2"):
+        assert _keys(Network3(bb, 9, 256, None)) == [str(s) for s in g[f"network3_{bb}_keys"]]
+
+
+def test_core_package_surface():
+    import segmif_b200.core as core
+    for name in ("Network", "WeTr", "SegFormerHead", "mit_b0", "mit_b5", "MixVisionTransformer", "OverlapPatchEmbed",
+                 "Attention", "Mlp", "DWConv", "Block", "Fusionloss3", "Fusionloss_grad3", "Fusionloss_grad2",
+                 "Total_fusion_loss", "Total_fusion_loss2", "Fusionloss", "Fusionloss_add", "Fusionloss2",
+                 "Fusionloss4", "RGB2YCrCb"):
+        assert hasattr(core, name), name
+    from segmif_b200.core.model_fusion import Mean, Network3, Fusion_Network3_ac  # noqa: F401  (train.py:18)
+    n = Network3("mit_b1", 9, 256, None)
+    groups = n.denoise_net.get_param_groups()
+    assert len(groups) == 3 and groups[2][-1] is n.denoise_net.classifier.weight
+    assert all("norm" in k for k, p in n.denoise_net.encoder.named_parameters() if any(p is q for q in groups[1]))
+
+
+def test_ffm_operand_packing_matches_oracle_algebra():
+    """Host-side folding of conv3 into channel_proj3 and the y/u halves: pure tensor algebra, checked on CPU."""
+    from oracle import segmif_oracle as O
+    from segmif_b200 import synth
+    from segmif_b200.core.model_fusion import Fusion_Network3_ac
+    fus = synth.load_synthetic(Fusion_Network3_ac(), 0)
+    pk = fus.ffm.cross.packs(fus.conv4)
+    assert pk["C3"] == 128
+    sd = fus.state_dict()
+    x = torch.randn(5, 128)
+    seg = torch.nn.functional.linear(x, sd["conv4.weight"].reshape(64, 128), sd["conv4.bias"])
+    full = torch.nn.functional.linear(seg, sd["ffm.cross.channel_proj3.weight"], sd["ffm.cross.channel_proj3.bias"])
+    w3y = pk["w_apply"][:64 * 128].float().reshape(64, 128)
+    w3u = pk["w_gram"][2 * 4096:].float().reshape(64, 128)
+    y3 = x @ w3y.t() + pk["b_apply"][:64]
+    u3 = x @ w3u.t() + pk["b_gram"][128:]
+    assert torch.allclose(y3, full[:, :64], atol=2e-2)      # bf16-rounded folded weights
+    assert torch.allclose(u3, full[:, 64:], atol=2e-2)
+
+
+def test_optimizer_schedule_matches_reference_formula():
+    from segmif_b200.utils.optimizer import PolyWarmupAdamW
+    p = torch.nn.Parameter(torch.zeros(3))
+    opt = PolyWarmupAdamW([{"params": [p], "lr": 1e-3}], lr=1e-3, weight_decay=0.01, betas=(0.9, 0.999), warmup_iter=10,
+                          max_iter=100, warmup_ratio=1e-6, power=1.0)
+    lrs = []
+    for _ in range(30):
+        p.grad = torch.ones(3)
+        opt.step()
+        lrs.append(opt.param_groups[0]["lr"])
+    assert abs(lrs[0] - 1e-3 * 1e-6) < 1e-12
+    assert abs(lrs[5] - 1e-3 * (1 - (1 - 5 / 10) * (1 - 1e-6))) < 1e-12
+    assert abs(lrs[20] - 1e-3 * (1 - 20 / 100)) < 1e-12

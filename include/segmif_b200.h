@@ -82,6 +82,37 @@ typedef struct {
 } segmif_conv_params;
 int segmif_conv_fwd(const segmif_conv_params* p, segmif_stream_t stream);
 
+/* ---- K3 on tcgen05: linear layer / 1x1 conv with TMA-fed 5th-generation tensor cores -------------------------
+ * Same contract as segmif_conv_fwd with KH=KW=1 (the nn.Linear call sites listed above and DRDB's 1x1 conv,
+ * core/model_fusion.py:155-156), restricted to N % 32 == 0; K % 8 == 0; 16-byte aligned pitches.
+ * dst[m, dst_coff+n] = residual[m, res_coff+n] + act(bias[n] + sum_k src[m, src_coff+k] * weight[n, k]).          */
+typedef struct {
+  const void* src;          /* bf16 [M, ld_src]            */
+  const void* weight;       /* bf16 [N, K] (K contiguous)  */
+  const float* bias;        /* fp32 [N] or NULL            */
+  const float* prelu_alpha; /* device scalar (PReLU only)  */
+  const void* residual;     /* [M, ld_res] or NULL         */
+  void* dst;                /* [M, ld_dst]                 */
+  int M, N, K, ld_src, src_coff;
+  int act;
+  int res_dtype, ld_res, res_coff;
+  int dst_dtype, ld_dst, dst_coff;
+} segmif_linear_params;
+int segmif_linear_tc_fwd(const segmif_linear_params* p, segmif_stream_t stream);
+/* Diagnostics (tests only): the same GEMM with N == 64 where output row m is computed from src row m + row_shift,
+ * read through a shared-memory matrix descriptor whose start is not aligned to the 1024-byte swizzle pattern.
+ * base_offset_mode 0: descriptor base-offset field 0; 1: (start >> 7) & 7.  src must have M + 16 rows. */
+int segmif_dbg_linear_tc_shifted(const segmif_linear_params* p, int row_shift, int base_offset_mode,
+                                 segmif_stream_t stream);
+
+/* ---- K10/K11 on tcgen05: 3x3 stride-1 'same' convolution (dilation 1 or 2), Cout in {32, 64}, bf16 out ----------
+ * DRDB Dcov1-5 (core/model_fusion.py:135-151), conv2 / conv21 (:1063-1064).  Same parameter block as
+ * segmif_conv_fwd (KH=KW=3, stride=1, pad=dil, no residual, bias required); weights resident in shared memory,
+ * halo tiles fetched by 4-D TMA, nine taps = nine shifted views of one tile.                                     */
+int segmif_conv3x3_tc_fwd(const segmif_conv_params* p, segmif_stream_t stream);
+/* Diagnostics: selects how segmif_conv3x3_tc_fwd encodes the base-offset field of shifted descriptors (0 | 1). */
+int segmif_dbg_set_desc_mode(int base_offset_mode);
+
 /* ---- K1 (stage 1): 7x7 stride-4 pad-3 patch embedding + LayerNorm --------------------------------
  * replaces core/mix_transformer.py:192-198 for patch_embed1, fused with the input affine of
  * Network3.forward core/model_fusion.py:1083-1085 (x*255 - mean)/std  (pass scale=1, shift=0 otherwise).

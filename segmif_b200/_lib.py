@@ -32,6 +32,18 @@ class ConvParams(ctypes.Structure):
     ]
 
 
+class LinearParams(ctypes.Structure):
+    """Mirror of segmif_linear_params."""
+    _fields_ = [
+        ("src", c_void_p), ("weight", c_void_p), ("bias", c_void_p), ("prelu_alpha", c_void_p),
+        ("residual", c_void_p), ("dst", c_void_p),
+        ("M", c_int), ("N", c_int), ("K", c_int), ("ld_src", c_int), ("src_coff", c_int),
+        ("act", c_int),
+        ("res_dtype", c_int), ("ld_res", c_int), ("res_coff", c_int),
+        ("dst_dtype", c_int), ("ld_dst", c_int), ("dst_coff", c_int),
+    ]
+
+
 P = c_void_p
 # name -> argtypes; every function returns int except where noted in _RESTYPES
 SIGNATURES = {
@@ -40,6 +52,10 @@ SIGNATURES = {
     "segmif_init": [c_int],
     "segmif_layernorm_fwd": [P, c_int, P, P, P, c_int, c_int64, c_int, c_float, P],
     "segmif_conv_fwd": [ctypes.POINTER(ConvParams), P],
+    "segmif_linear_tc_fwd": [ctypes.POINTER(LinearParams), P],
+    "segmif_dbg_linear_tc_shifted": [ctypes.POINTER(LinearParams), c_int, c_int, P],
+    "segmif_conv3x3_tc_fwd": [ctypes.POINTER(ConvParams), P],
+    "segmif_dbg_set_desc_mode": [c_int],
     "segmif_patch_embed7_ln_fwd": [P, P, P, P, P, c_float, P, P, P, c_int, c_int, c_int, c_int, P],
     "segmif_sr_attention_fwd": [P, c_int, P, P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P],
     "segmif_dwconv3x3_gelu_fwd": [P, P, P, P, c_int, c_int, c_int, c_int, P],

@@ -1,0 +1,260 @@
+// 3x3 (optionally dilated) stride-1 convolution as an implicit GEMM on tcgen05 tensor cores (segmif_conv3x3_tc_fwd):
+// the DRDB growth convolutions (65 % of the pipeline's FLOPs) and conv2 / conv21 of Fusion_Network3_ac.
+//
+//  * persistent kernel, one CTA per SM; ALL packed weights of the layer ([Cout][9][Cin] bf16, <= 144 KB) are
+//    loaded once per CTA by TMA and stay resident in shared memory;
+//  * per output tile of 16 x (8*NSUB) pixels and per 64-channel slab, ONE 4-D TMA box load brings the tile plus its
+//    dilation halo (rows x cols x 64 ch, 128-byte swizzle, out-of-image pixels and channels >= Cin zero-filled by
+//    the TMA unit = the conv's zero padding for free).  The nine taps are nine shifted VIEWS of that box:
+//    MMA row r = (ty, tx) = (r / 8, r % 8) sits at line (ty + ky*dil) * HXP + tx + kx*dil, i.e. a K-major SW128
+//    operand with 8-row groups HXP*128 bytes apart whose start is shifted by (ky*dil*HXP + kx*dil) lines --
+//    L2->SM traffic drops ~5x versus gathering every tap separately;
+//  * one thread issues tcgen05.mma (M=128, N=Cout, K=16); accumulators live in TMEM, double buffered so the
+//    epilogue (tcgen05.ld -> bias -> ReLU/PReLU -> bf16 channel-slice store) of tile i overlaps the MMAs of tile i+1.
+// Warp roles: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = epilogue.
+#include <algorithm>
+
+#include "tc_common.cuh"
+
+namespace segmif {
+
+static int g_desc_base_offset_mode = 0;   // see segmif_dbg_linear_tc_shifted; fixed after the on-device probe
+
+struct ConvTcArgs {
+  const float* bias;
+  const float* alpha;
+  bf16* dst;
+  int B, H, W, nchunks, act, ld_dst, dst_coff;
+  int tiles_x, tiles_y, base_offset_mode, cin;
+};
+
+constexpr int kConvTcThreads = 192;
+
+template <int COUT, int DIL, int NSUB>
+struct ConvTcCfg {
+  static constexpr int TH = 16, TW = 8 * NSUB;
+  static constexpr int HROWS = TH + 2 * DIL;
+  static constexpr int HXP = ((TW + 2 * DIL + 7) / 8) * 8;            // halo columns padded to a multiple of 8 lines
+  static constexpr int A_BYTES = HROWS * HXP * 128;
+  static constexpr int W_TILE_BYTES = COUT * 128;                      // one (slab, tap) weight tile
+  static constexpr int ACC_COLS = NSUB * COUT;                         // TMEM columns per accumulator buffer
+  static constexpr uint32_t TMEM_COLS = (2 * ACC_COLS) <= 32 ? 32 : (2 * ACC_COLS) <= 64 ? 64 : (2 * ACC_COLS) <= 128 ? 128 : 256;
+};
+
+template <int COUT, int DIL, int NSUB>
+__global__ void __launch_bounds__(kConvTcThreads, 1) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                       const __grid_constant__ CUtensorMap tmW,
+                                                                       const ConvTcArgs a) {
+  using Cfg = ConvTcCfg<COUT, DIL, NSUB>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int w_bytes = a.nchunks * 9 * Cfg::W_TILE_BYTES;
+  uint8_t* sW = smem;
+  uint8_t* sA = smem + w_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sA + 2 * Cfg::A_BYTES);
+  uint64_t* empty = full + 2;
+  uint64_t* wfull = empty + 2;
+  uint64_t* tmem_full = wfull + 1;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_per_img = a.tiles_x * a.tiles_y;
+  const int num_tiles = tiles_per_img * a.B;
+
+  if (threadIdx.x == 0) {
+    tc::prefetch_tmap(&tmA);
+    tc::prefetch_tmap(&tmW);
+    for (int s = 0; s < 2; ++s) {
+      tc::mbar_init(full + s, 1);
+      tc::mbar_init(empty + s, 1);
+      tc::mbar_init(tmem_full + s, 1);
+      tc::mbar_init(tmem_empty + s, 4);        // one arrive per epilogue warp
+    }
+    tc::mbar_init(wfull, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // resident weights: nchunks * 9 tiles of [COUT x 64]
+      tc::mbar_expect_tx(wfull, (uint32_t)w_bytes);
+      for (int c = 0; c < a.nchunks; ++c)
+        for (int t = 0; t < 9; ++t)
+          tc::tma_load_2d(sW + (c * 9 + t) * Cfg::W_TILE_BYTES, &tmW, wfull, t * a.cin + c * 64, 0);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int b = tile / tiles_per_img, rem = tile - b * tiles_per_img;
+        const int y0 = (rem / a.tiles_x) * Cfg::TH, x0 = (rem % a.tiles_x) * Cfg::TW;
+        for (int c = 0; c < a.nchunks; ++c, ++it) {
+          const int s = it & 1;
+          const uint32_t ph = (it >> 1) & 1;
+          tc::mbar_wait(empty + s, ph ^ 1);
+          tc::mbar_expect_tx(full + s, Cfg::A_BYTES);
+          tc::tma_load_4d(sA + s * Cfg::A_BYTES, &tmA, full + s, c * 64, x0 - DIL, y0 - DIL, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::make_idesc_bf16(128, COUT);
+      tc::mbar_wait(wfull, 0);
+      int it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+        const int buf = lt & 1;
+        tc::mbar_wait(tmem_empty + buf, ((lt >> 1) & 1) ^ 1);
+        tc::tc_fence_after();
+        const uint32_t acc = tmem_base + (uint32_t)(buf * Cfg::ACC_COLS);
+        for (int c = 0; c < a.nchunks; ++c, ++it) {
+          const int s = it & 1;
+          tc::mbar_wait(full + s, (it >> 1) & 1);
+          tc::tc_fence_after();
+          const uint32_t a_base = smem_u32(sA + s * Cfg::A_BYTES);
+#pragma unroll 1
+          for (int t = 0; t < 9; ++t) {
+            const int ky = t / 3, kx = t - ky * 3;
+            const uint32_t w_addr = smem_u32(sW + (c * 9 + t) * Cfg::W_TILE_BYTES);
+#pragma unroll
+            for (int sub = 0; sub < NSUB; ++sub) {
+              const uint32_t a_addr = a_base + (uint32_t)((ky * DIL * Cfg::HXP + kx * DIL + sub * 8) * 128);
+              const uint32_t bo = a.base_offset_mode ? ((a_addr >> 7) & 7) : 0;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t da = tc::make_smem_desc_sw128(a_addr + k * 32, Cfg::HXP * 128, bo);
+                const uint64_t db = tc::make_smem_desc_sw128(w_addr + k * 32, 1024, 0);
+                tc::umma_bf16(acc + (uint32_t)(sub * COUT), da, db, idesc, (c | t | k) != 0 ? 1u : 0u);
+              }
+            }
+          }
+          tc::umma_commit(empty + s);
+        }
+        tc::umma_commit(tmem_full + buf);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane, ty = r >> 3, tx = r & 7;
+    const float alpha = (a.act == SEGMIF_ACT_PRELU) ? *a.alpha : 0.f;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      const int buf = lt & 1;
+      const int b = tile / tiles_per_img, rem = tile - b * tiles_per_img;
+      const int y = (rem / a.tiles_x) * Cfg::TH + ty;
+      const int x0 = (rem % a.tiles_x) * Cfg::TW + tx;
+      tc::mbar_wait(tmem_full + buf, (lt >> 1) & 1);
+      tc::tc_fence_after();
+#pragma unroll
+      for (int sub = 0; sub < NSUB; ++sub) {
+        const int x = x0 + sub * 8;
+#pragma unroll 1
+        for (int c = 0; c < COUT; c += 32) {
+          float v[32];
+          tc::tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * Cfg::ACC_COLS + sub * COUT + c), v);
+          if (y < a.H && x < a.W) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j] + __ldg(a.bias + c + j), a.act, alpha);
+            uint4* d = reinterpret_cast<uint4*>(a.dst + (((int64_t)b * a.H + y) * a.W + x) * a.ld_dst + a.dst_coff + c);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              d[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+          }
+        }
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(tmem_empty + buf);     // this warp has drained the accumulator buffer
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+template <int COUT, int DIL, int NSUB>
+static int launch_conv_tc(const segmif_conv_params* p, cudaStream_t st) {
+  using Cfg = ConvTcCfg<COUT, DIL, NSUB>;
+  const int nchunks = (p->Cin + 63) / 64;
+  const size_t smem = (size_t)nchunks * 9 * Cfg::W_TILE_BYTES + 2 * (size_t)Cfg::A_BYTES + 9 * 8 + 16;
+  auto kern = conv3x3_tc_kernel<COUT, DIL, NSUB>;
+  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) { set_error("conv3x3_tc: %zu bytes of shared memory refused: %s", smem, cudaGetErrorString(err)); return SEGMIF_ERR_CUDA; }
+  CUtensorMap tmA, tmW;
+  {
+    const uint64_t dims[4] = {(uint64_t)p->Cin, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B};
+    const uint64_t strides[3] = {(uint64_t)p->ld_src * 2, (uint64_t)p->W * p->ld_src * 2, (uint64_t)p->H * p->W * p->ld_src * 2};
+    const uint32_t box[4] = {64, (uint32_t)Cfg::HXP, (uint32_t)Cfg::HROWS, 1};
+    int rc = make_tmap_bf16_sw128(&tmA, reinterpret_cast<const bf16*>(p->src) + p->src_coff, 4, dims, strides, box, "conv3x3_tc(A)");
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)9 * p->Cin, (uint64_t)COUT};
+    const uint64_t strides[1] = {(uint64_t)9 * p->Cin * 2};
+    const uint32_t box[2] = {64, (uint32_t)COUT};
+    int rc = make_tmap_bf16_sw128(&tmW, p->weight, 2, dims, strides, box, "conv3x3_tc(W)");
+    if (rc) return rc;
+  }
+  ConvTcArgs a;
+  a.bias = p->bias; a.alpha = p->prelu_alpha; a.dst = reinterpret_cast<bf16*>(p->dst);
+  a.B = p->B; a.H = p->H; a.W = p->W; a.nchunks = nchunks; a.act = p->act; a.ld_dst = p->ld_dst; a.dst_coff = p->dst_coff;
+  a.tiles_x = (p->W + Cfg::TW - 1) / Cfg::TW; a.tiles_y = (p->H + Cfg::TH - 1) / Cfg::TH;
+  a.base_offset_mode = g_desc_base_offset_mode;
+  a.cin = p->Cin;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int num_tiles = a.tiles_x * a.tiles_y * a.B;
+  kern<<<std::min(num_tiles, sms), kConvTcThreads, smem, st>>>(tmA, tmW, a);
+  return check_launch("segmif_conv3x3_tc_fwd");
+}
+
+}  // namespace segmif
+
+using namespace segmif;
+
+extern "C" int segmif_dbg_set_desc_mode(int base_offset_mode) {
+  g_desc_base_offset_mode = base_offset_mode ? 1 : 0;
+  return SEGMIF_OK;
+}
+
+extern "C" int segmif_conv3x3_tc_fwd(const segmif_conv_params* p, segmif_stream_t stream) {
+  SEGMIF_REQUIRE(p && p->src && p->weight && p->dst && p->bias, "conv3x3_tc: null pointer (bias is required)");
+  SEGMIF_REQUIRE(p->KH == 3 && p->KW == 3 && p->stride == 1 && (p->dil == 1 || p->dil == 2) && p->pad == p->dil,
+                 "conv3x3_tc: only 3x3, stride 1, dilation 1 or 2 with 'same' padding");
+  SEGMIF_REQUIRE(p->Cout == 32 || p->Cout == 64, "conv3x3_tc: Cout=%d must be 32 or 64", p->Cout);
+  SEGMIF_REQUIRE(p->Cin % 8 == 0 && p->Cin > 0 && p->ld_src % 8 == 0 && p->src_coff % 8 == 0, "conv3x3_tc: Cin/pitch/offset must be multiples of 8");
+  SEGMIF_REQUIRE(p->dst_dtype == SEGMIF_BF16 && p->ld_dst % 8 == 0 && p->dst_coff % 8 == 0, "conv3x3_tc: dst must be bf16 with 16-byte aligned slices");
+  SEGMIF_REQUIRE(p->residual == nullptr, "conv3x3_tc: residual is not supported");
+  SEGMIF_REQUIRE(p->act != SEGMIF_ACT_GELU, "conv3x3_tc: GELU is not supported");
+  SEGMIF_REQUIRE(p->act != SEGMIF_ACT_PRELU || p->prelu_alpha, "conv3x3_tc: PReLU needs prelu_alpha");
+  SEGMIF_REQUIRE(p->src_coff + p->Cin <= p->ld_src && p->dst_coff + p->Cout <= p->ld_dst, "conv3x3_tc: channel slice exceeds pitch");
+  SEGMIF_REQUIRE(((uintptr_t)p->src & 15) == 0 && ((uintptr_t)p->weight & 15) == 0 && ((uintptr_t)p->dst & 15) == 0, "conv3x3_tc: pointers must be 16-byte aligned");
+  cudaStream_t st = as_stream(stream);
+  const size_t nchunks = (size_t)(p->Cin + 63) / 64;
+  const size_t limit = 227 * 1024 - 256;
+  const size_t wbytes = nchunks * 9 * (size_t)p->Cout * 128;
+  constexpr size_t a_32_2_2 = 2 * (size_t)ConvTcCfg<32, 2, 2>::A_BYTES, a_32_2_1 = 2 * (size_t)ConvTcCfg<32, 2, 1>::A_BYTES;
+  constexpr size_t a_32_1_2 = 2 * (size_t)ConvTcCfg<32, 1, 2>::A_BYTES, a_32_1_1 = 2 * (size_t)ConvTcCfg<32, 1, 1>::A_BYTES;
+  constexpr size_t a_64_1_1 = 2 * (size_t)ConvTcCfg<64, 1, 1>::A_BYTES, a_64_2_1 = 2 * (size_t)ConvTcCfg<64, 2, 1>::A_BYTES;
+  if (p->Cout == 32 && p->dil == 2) {
+    if (wbytes + a_32_2_2 <= limit) return launch_conv_tc<32, 2, 2>(p, st);
+    SEGMIF_REQUIRE(wbytes + a_32_2_1 <= limit, "conv3x3_tc: Cin=%d too large for resident weights", p->Cin);
+    return launch_conv_tc<32, 2, 1>(p, st);
+  }
+  if (p->Cout == 32 && p->dil == 1) {
+    if (wbytes + a_32_1_2 <= limit) return launch_conv_tc<32, 1, 2>(p, st);
+    SEGMIF_REQUIRE(wbytes + a_32_1_1 <= limit, "conv3x3_tc: Cin=%d too large for resident weights", p->Cin);
+    return launch_conv_tc<32, 1, 1>(p, st);
+  }
+  if (p->Cout == 64 && p->dil == 1) {
+    SEGMIF_REQUIRE(wbytes + a_64_1_1 <= limit, "conv3x3_tc: Cin=%d too large for resident weights", p->Cin);
+    return launch_conv_tc<64, 1, 1>(p, st);
+  }
+  SEGMIF_REQUIRE(wbytes + a_64_2_1 <= limit, "conv3x3_tc: Cin=%d too large for resident weights", p->Cin);
+  return launch_conv_tc<64, 2, 1>(p, st);
+}

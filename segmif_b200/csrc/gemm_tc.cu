@@ -1,0 +1,259 @@
+// Linear layer / 1x1 conv on the 5th-generation tensor cores (segmif_linear_tc_fwd):
+//   dst[m, n] = residual[m, n] + act(bias[n] + sum_k A[m, k] W[n, k])
+// A: bf16 pixel-major rows (pitch lda), W: bf16 [N, K] K-major.  Both operands are staged by TMA
+// (cp.async.bulk.tensor.2d, 128-byte swizzle, out-of-range rows/columns zero-filled) into a 4-stage
+// shared-memory ring; ONE thread issues tcgen05.mma (M=128, N=BN, K=16 per instruction) accumulating in
+// TMEM; four epilogue warps read the accumulator with tcgen05.ld (one output row per thread) and fuse
+// bias / ReLU / PReLU / GELU / residual and the channel-slice store.
+// Warp roles: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = epilogue (TMEM lane quadrant = warp % 4).
+#include <algorithm>
+
+#include "tc_common.cuh"
+
+namespace segmif {
+
+EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  if (!fn) set_error("cuTensorMapEncodeTiled is not available from this driver");
+  return fn;
+}
+
+int make_tmap_bf16_sw128(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                         const uint32_t* box, const char* what) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return SEGMIF_ERR_CUDA;
+  cuuint64_t gd[5], gs[5];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("%s: cuTensorMapEncodeTiled failed (CUresult %d)", what, (int)r);
+    return SEGMIF_ERR_CUDA;
+  }
+  return SEGMIF_OK;
+}
+
+struct TcEpilogue {
+  const float* bias;
+  const float* alpha;
+  const void* res;
+  void* dst;
+  int M, N, act, res_dtype, ld_res, res_coff, dst_dtype, ld_dst, dst_coff;
+};
+
+// one output row (this thread) x 32 columns starting at n
+__device__ __forceinline__ void epilogue_row32(const TcEpilogue& e, float (&v)[32], int64_t m, int n, float alpha) {
+  if (e.bias) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] += __ldg(e.bias + n + j);
+  }
+  if (e.act != SEGMIF_ACT_NONE) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], e.act, alpha);
+  }
+  if (e.res) {
+    const int64_t ro = m * e.ld_res + e.res_coff + n;
+    if (e.res_dtype == SEGMIF_F32) {
+      const float4* r = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(e.res) + ro);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float4 t = r[j]; v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w; }
+    } else {
+      const uint4* r = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(e.res) + ro);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 t = r[j];
+        const float2 a = unpack_bf16x2(t.x), b = unpack_bf16x2(t.y), c = unpack_bf16x2(t.z), d = unpack_bf16x2(t.w);
+        v[8 * j] += a.x; v[8 * j + 1] += a.y; v[8 * j + 2] += b.x; v[8 * j + 3] += b.y;
+        v[8 * j + 4] += c.x; v[8 * j + 5] += c.y; v[8 * j + 6] += d.x; v[8 * j + 7] += d.y;
+      }
+    }
+  }
+  const int64_t d_o = m * e.ld_dst + e.dst_coff + n;
+  if (e.dst_dtype == SEGMIF_F32) {
+    float4* d = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.dst) + d_o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) d[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  } else {
+    uint4* d = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(e.dst) + d_o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      d[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                        pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+  }
+}
+
+constexpr int kTcStages = 4;
+constexpr int kTcThreads = 192;
+
+// DBG: the A box carries 16 extra rows and the MMA reads rows [shift, shift+128) of it through a descriptor whose
+// start address is NOT 1024-byte aligned -- the addressing the conv kernel's halo-tile taps rely on.
+template <int BN, bool DBG>
+__global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                const __grid_constant__ CUtensorMap tmB,
+                                                                const TcEpilogue e, const int num_k_blocks,
+                                                                const int dbg_shift, const int dbg_base_offset_mode) {
+  constexpr int A_ROWS = DBG ? 144 : 128;
+  constexpr int A_BYTES = A_ROWS * 128, B_BYTES = BN * 128;
+  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kTcStages * A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + kTcStages * B_BYTES);
+  uint64_t* empty = full + kTcStages;
+  uint64_t* tmem_full = empty + kTcStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN;
+  const int m0 = blockIdx.y * 128;
+
+  if (threadIdx.x == 0) {
+    tc::prefetch_tmap(&tmA);
+    tc::prefetch_tmap(&tmB);
+    for (int s = 0; s < kTcStages; ++s) { tc::mbar_init(full + s, 1); tc::mbar_init(empty + s, 1); }
+    tc::mbar_init(tmem_full, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, TMEM_COLS);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < num_k_blocks; ++kb) {
+        const int s = kb % kTcStages;
+        const uint32_t ph = (kb / kTcStages) & 1;
+        tc::mbar_wait(empty + s, ph ^ 1);
+        tc::mbar_expect_tx(full + s, A_BYTES + B_BYTES);
+        tc::tma_load_2d(sA + s * A_BYTES, &tmA, full + s, kb * 64, m0);
+        tc::tma_load_2d(sB + s * B_BYTES, &tmB, full + s, kb * 64, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::make_idesc_bf16(128, BN);
+      for (int kb = 0; kb < num_k_blocks; ++kb) {
+        const int s = kb % kTcStages;
+        const uint32_t ph = (kb / kTcStages) & 1;
+        tc::mbar_wait(full + s, ph);
+        tc::tc_fence_after();
+        uint32_t a_addr = smem_u32(sA + s * A_BYTES);
+        uint32_t bo = 0;
+        if (DBG) {
+          a_addr += dbg_shift * 128;
+          bo = dbg_base_offset_mode ? ((a_addr >> 7) & 7) : 0;
+        }
+        const uint32_t b_addr = smem_u32(sB + s * B_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t da = tc::make_smem_desc_sw128(a_addr + k * 32, 1024, bo);
+          const uint64_t db = tc::make_smem_desc_sw128(b_addr + k * 32, 1024, 0);
+          tc::umma_bf16(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        tc::umma_commit(empty + s);            // frees the smem stage when these MMAs have read it
+      }
+      tc::umma_commit(tmem_full);              // accumulator complete
+    }
+    __syncwarp();
+  } else {
+    const int quad = warp & 3;                 // TMEM lanes [32*quad, 32*quad+32) are visible to this warp
+    tc::mbar_wait(tmem_full, 0);
+    tc::tc_fence_after();
+    const int64_t m = (int64_t)m0 + quad * 32 + lane;
+    const float alpha = (e.act == SEGMIF_ACT_PRELU) ? *e.alpha : 0.f;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      float v[32];
+      tc::tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c, v);   // warp-collective: no divergence before it
+      if (m < e.M && (n0 + c) < e.N) epilogue_row32(e, v, m, n0 + c, alpha);
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+template <int BN, bool DBG>
+static int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcEpilogue& e, int K, int dbg_shift,
+                          int dbg_bo, cudaStream_t st) {
+  constexpr int A_ROWS = DBG ? 144 : 128;
+  constexpr size_t smem = (size_t)kTcStages * (A_ROWS * 128 + BN * 128) + (2 * kTcStages + 1) * 8 + 16;
+  auto kern = gemm_tc_kernel<BN, DBG>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) { set_error("linear_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(err)); return SEGMIF_ERR_CUDA; }
+    configured = true;
+  }
+  dim3 grid((unsigned)ceil_div(e.N, BN), (unsigned)ceil_div(e.M, 128));
+  kern<<<grid, kTcThreads, smem, st>>>(tmA, tmB, e, (int)ceil_div(K, 64), dbg_shift, dbg_bo);
+  return check_launch("segmif_linear_tc_fwd");
+}
+
+static int linear_tc_impl(const segmif_linear_params* p, cudaStream_t st, bool dbg, int dbg_shift, int dbg_bo) {
+  SEGMIF_REQUIRE(p && p->src && p->weight && p->dst, "linear_tc: null pointer");
+  SEGMIF_REQUIRE(p->M > 0 && p->N > 0 && p->K > 0, "linear_tc: bad sizes");
+  SEGMIF_REQUIRE(p->K % 8 == 0 && p->ld_src % 8 == 0 && p->src_coff % 8 == 0, "linear_tc: K, ld_src, src_coff must be multiples of 8");
+  SEGMIF_REQUIRE(p->N % 32 == 0, "linear_tc: N=%d must be a multiple of 32", p->N);
+  SEGMIF_REQUIRE(p->src_coff + p->K <= p->ld_src && p->dst_coff + p->N <= p->ld_dst, "linear_tc: channel slice exceeds pitch");
+  const int dalign = p->dst_dtype == SEGMIF_F32 ? 4 : 8;
+  SEGMIF_REQUIRE(p->ld_dst % dalign == 0 && p->dst_coff % dalign == 0, "linear_tc: dst pitch/offset must be 16-byte multiples");
+  if (p->residual) {
+    const int ralign = p->res_dtype == SEGMIF_F32 ? 4 : 8;
+    SEGMIF_REQUIRE(p->ld_res % ralign == 0 && p->res_coff % ralign == 0, "linear_tc: residual pitch/offset must be 16-byte multiples");
+  }
+  SEGMIF_REQUIRE(p->act != SEGMIF_ACT_PRELU || p->prelu_alpha, "linear_tc: PReLU needs prelu_alpha");
+  SEGMIF_REQUIRE(((uintptr_t)p->src & 15) == 0 && ((uintptr_t)p->weight & 15) == 0 && ((uintptr_t)p->dst & 15) == 0,
+                 "linear_tc: pointers must be 16-byte aligned");
+  const int BN = (p->N % 128 == 0 || p->N > 192) ? 128 : (p->N % 64 == 0 ? 64 : 32);
+  CUtensorMap tmA, tmB;
+  {
+    const uint64_t dims[2] = {(uint64_t)p->K, (uint64_t)p->M};
+    const uint64_t strides[1] = {(uint64_t)p->ld_src * 2};
+    const uint32_t box[2] = {64, dbg ? 144u : 128u};
+    int rc = make_tmap_bf16_sw128(&tmA, reinterpret_cast<const bf16*>(p->src) + p->src_coff, 2, dims, strides, box, "linear_tc(A)");
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)p->K, (uint64_t)p->N};
+    const uint64_t strides[1] = {(uint64_t)p->K * 2};
+    const uint32_t box[2] = {64, (uint32_t)BN};
+    int rc = make_tmap_bf16_sw128(&tmB, p->weight, 2, dims, strides, box, "linear_tc(W)");
+    if (rc) return rc;
+  }
+  TcEpilogue e;
+  e.bias = p->bias; e.alpha = p->prelu_alpha; e.res = p->residual; e.dst = p->dst;
+  e.M = p->M; e.N = p->N; e.act = p->act; e.res_dtype = p->res_dtype; e.ld_res = p->ld_res; e.res_coff = p->res_coff;
+  e.dst_dtype = p->dst_dtype; e.ld_dst = p->ld_dst; e.dst_coff = p->dst_coff;
+  if (dbg) return launch_gemm_tc<64, true>(tmA, tmB, e, p->K, dbg_shift, dbg_bo, st);
+  if (BN == 128) return launch_gemm_tc<128, false>(tmA, tmB, e, p->K, 0, 0, st);
+  if (BN == 64) return launch_gemm_tc<64, false>(tmA, tmB, e, p->K, 0, 0, st);
+  return launch_gemm_tc<32, false>(tmA, tmB, e, p->K, 0, 0, st);
+}
+
+}  // namespace segmif
+
+using namespace segmif;
+
+extern "C" int segmif_linear_tc_fwd(const segmif_linear_params* p, segmif_stream_t stream) {
+  return linear_tc_impl(p, as_stream(stream), false, 0, 0);
+}
+
+// Test-only: output row m is computed from A row m + row_shift, read through a shifted (non-1024-aligned) smem descriptor.
+extern "C" int segmif_dbg_linear_tc_shifted(const segmif_linear_params* p, int row_shift, int base_offset_mode,
+                                            segmif_stream_t stream) {
+  SEGMIF_REQUIRE(row_shift >= 0 && row_shift <= 16, "dbg_linear_tc: row_shift out of range");
+  SEGMIF_REQUIRE(p && p->N == 64, "dbg_linear_tc: N must be 64");
+  return linear_tc_impl(p, as_stream(stream), true, row_shift, base_offset_mode);
+}

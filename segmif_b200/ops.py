@@ -2,6 +2,7 @@
 current CUDA stream.  PyTorch is used here for device memory and streams only; every computation
 is a kernel in libsegmif_b200.so.  All wrappers raise on non-CUDA tensors -- there is no fallback."""
 import ctypes
+import os
 
 import torch
 
@@ -52,9 +53,12 @@ def layernorm(x, gamma, beta, eps, out_dtype=torch.bfloat16, out=None):
 
 def conv(src, weight, bias, *, B, H, W, Cin, KH=1, KW=1, stride=1, pad=0, dil=1, Cout, ld_src=None, src_coff=0,
          act=ACT_NONE, prelu_alpha=None, residual=None, ld_res=None, res_coff=0, out=None, out_dtype=torch.bfloat16,
-         ld_dst=None, dst_coff=0):
-    """Implicit-GEMM conv / linear (segmif_conv_fwd).  `src` is pixel-major bf16 with channel pitch ld_src;
-    `weight` is the packed bf16 [Cout, KH*KW, Cin] tensor.  Returns `out` ([B*Ho*Wo, ld_dst])."""
+         ld_dst=None, dst_coff=0, entry=None):
+    """Dense contraction on the tensor cores.  `src` is pixel-major bf16 with channel pitch ld_src; `weight` is the
+    packed bf16 [Cout, KH*KW, Cin] tensor.  Returns `out` ([B*Ho*Wo, ld_dst]).  Kernel selection (entry=None):
+    1x1 -> segmif_linear_tc_fwd and 3x3 stride-1 'same' -> segmif_conv3x3_tc_fwd (tcgen05 + TMA) whenever the shape
+    qualifies; strided / odd-width cases (patch_embed2-4, Attention.sr, linear_pred's 9 classes) ->
+    segmif_conv_fwd (mma.sync implicit GEMM)."""
     st = _prep(src, weight, bias, prelu_alpha, residual, out)
     if src.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16:
         raise TypeError("segmif_b200.conv: src and weight must be bf16")
@@ -80,8 +84,50 @@ def conv(src, weight, bias, *, B, H, W, Cin, KH=1, KW=1, stride=1, pad=0, dil=1,
     p.res_dtype = _dt(residual) if residual is not None else F32
     p.ld_res, p.res_coff = (ld_res or 0), res_coff
     p.dst_dtype, p.ld_dst, p.dst_coff = _dt(out), ld_dst, dst_coff
-    _lib.call("segmif_conv_fwd", ctypes.byref(p), st)
+    if entry is None:
+        entry = "segmif_conv_fwd"
+        if USE_TCGEN05:
+            dal = 4 if out.dtype == torch.float32 else 8
+            ral = 4 if (residual is not None and residual.dtype == torch.float32) else 8
+            aligned = (ld_src % 8 == 0 and src_coff % 8 == 0 and ld_dst % dal == 0 and dst_coff % dal == 0
+                       and (residual is None or ((ld_res or 0) % ral == 0 and res_coff % ral == 0)))
+            if KH == 1 and KW == 1 and stride == 1 and pad == 0 and Cout % 32 == 0 and Cin % 8 == 0 and aligned:
+                lp = _linear_params(src, weight, bias, M, Cout, Cin, ld_src, src_coff, act, prelu_alpha, residual, ld_res,
+                                    res_coff, out, ld_dst, dst_coff)
+                _lib.call("segmif_linear_tc_fwd", ctypes.byref(lp), st)
+                return out
+            if (KH == 3 and KW == 3 and stride == 1 and pad == dil and dil in (1, 2) and Cout in (32, 64)
+                    and out.dtype == torch.bfloat16 and residual is None and bias is not None and act != ACT_GELU
+                    and aligned and _conv3x3_tc_fits(Cin, Cout, dil)):
+                entry = "segmif_conv3x3_tc_fwd"
+    _lib.call(entry, ctypes.byref(p), st)
     return out
+
+
+USE_TCGEN05 = os.environ.get("SEGMIF_TCGEN05", "1") != "0"
+if "SEGMIF_DESC_MODE" in os.environ:          # diagnostics only
+    _lib.check(_lib.load().segmif_dbg_set_desc_mode(int(os.environ["SEGMIF_DESC_MODE"])), "segmif_dbg_set_desc_mode")
+
+
+def _conv3x3_tc_fits(Cin, Cout, dil):
+    """Resident weights + two halo-tile stages must fit the 227 KB of shared memory (mirrors conv_tc.cu)."""
+    wbytes = ((Cin + 63) // 64) * 9 * Cout * 128
+    a_bytes = (16 + 2 * dil) * (((8 + 2 * dil + 7) // 8) * 8) * 128          # NSUB = 1 tile
+    return wbytes + 2 * a_bytes <= 227 * 1024 - 256
+
+
+def conv3x3_tc(src, weight, bias, **kw):
+    """3x3 stride-1 'same' conv (dil 1|2, Cout 32|64, bf16 out) on tcgen05 tensor cores with TMA halo tiles."""
+    return conv(src, weight, bias, KH=3, KW=3, entry="segmif_conv3x3_tc_fwd", **kw)
+
+
+def conv_mma(src, weight, bias, **kw):
+    """Forces the mma.sync implicit-GEMM kernel (segmif_conv_fwd)."""
+    return conv(src, weight, bias, entry="segmif_conv_fwd", **kw)
+
+
+def dbg_set_desc_mode(mode):
+    _lib.check(_lib.load().segmif_dbg_set_desc_mode(int(mode)), "segmif_dbg_set_desc_mode")
 
 
 def linear(x, weight, bias, *, act=ACT_NONE, residual=None, out_dtype=torch.bfloat16, out=None, ld_dst=None,
@@ -92,6 +138,53 @@ def linear(x, weight, bias, *, act=ACT_NONE, residual=None, out_dtype=torch.bflo
     N = weight.shape[0]
     return conv(x, weight, bias, B=1, H=1, W=rows, Cin=K, Cout=N, act=act, residual=residual, out=out,
                 out_dtype=out_dtype, ld_dst=ld_dst, dst_coff=dst_coff)
+
+
+def _linear_params(x, weight, bias, M, N, K, ld_src, src_coff, act, prelu_alpha, residual, ld_res, res_coff, out, ld_dst,
+                   dst_coff):
+    p = _lib.LinearParams()
+    p.src, p.weight = x.data_ptr(), weight.data_ptr()
+    p.bias = bias.data_ptr() if bias is not None else None
+    p.prelu_alpha = prelu_alpha.data_ptr() if prelu_alpha is not None else None
+    p.residual = residual.data_ptr() if residual is not None else None
+    p.dst = out.data_ptr()
+    p.M, p.N, p.K, p.ld_src, p.src_coff = M, N, K, ld_src, src_coff
+    p.act = act
+    p.res_dtype = _dt(residual) if residual is not None else F32
+    p.ld_res, p.res_coff = (ld_res or 0), res_coff
+    p.dst_dtype, p.ld_dst, p.dst_coff = _dt(out), ld_dst, dst_coff
+    return p
+
+
+def linear_tc(x, weight, bias, *, M=None, K=None, ld_src=None, src_coff=0, act=ACT_NONE, prelu_alpha=None, residual=None,
+              ld_res=None, res_coff=0, out=None, out_dtype=torch.bfloat16, ld_dst=None, dst_coff=0):
+    """tcgen05 + TMA linear layer (segmif_linear_tc_fwd).  x bf16 [..., ld_src]; weight packed bf16 [N, 1, K]."""
+    st = _prep(x, weight, bias, prelu_alpha, residual, out)
+    N = weight.shape[0]
+    K = weight.shape[-1] if K is None else K
+    ld_src = x.shape[-1] if ld_src is None else ld_src
+    M = x.numel() // ld_src if M is None else M
+    if out is None:
+        ld_dst = N if ld_dst is None else ld_dst
+        out = torch.empty((M, ld_dst), dtype=out_dtype, device=x.device)
+    elif ld_dst is None:
+        ld_dst = out.shape[-1]
+    if residual is not None and ld_res is None:
+        ld_res = residual.shape[-1]
+    p = _linear_params(x, weight, bias, M, N, K, ld_src, src_coff, act, prelu_alpha, residual, ld_res, res_coff, out,
+                       ld_dst, dst_coff)
+    _lib.call("segmif_linear_tc_fwd", ctypes.byref(p), st)
+    return out
+
+
+def dbg_linear_tc_shifted(x, weight, M, row_shift, base_offset_mode):
+    """Diagnostics: out[m] = x[m + row_shift] @ W^T through a shifted smem descriptor (N must be 64)."""
+    st = _prep(x, weight)
+    N, K = weight.shape[0], weight.shape[-1]
+    out = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    p = _linear_params(x, weight, None, M, N, K, x.shape[-1], 0, ACT_NONE, None, None, None, 0, out, N, 0)
+    _lib.call("segmif_dbg_linear_tc_shifted", ctypes.byref(p), int(row_shift), int(base_offset_mode), st)
+    return out
 
 
 def patch_embed7_ln(img, w147, bias, gamma, beta, eps, in_scale=None, in_shift=None):

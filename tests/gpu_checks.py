@@ -102,7 +102,7 @@ def _conv_case(name, B, H, W, Cin, Cout, k=1, stride=1, pad=0, dil=1, act=ACT_NO
         res_t = res_t.to(residual).to(DEV)
     ld_dst = ld_dst or Cout
     out = torch.full((ref.shape[0], ld_dst), 7.0, dtype=out_dtype, device=DEV)
-    ops.conv(x_full.bfloat16().to(DEV), pack_conv(w), bv.to(DEV) if bias else None, B=B, H=H, W=W, Cin=Cin, KH=k, KW=k,
+    ops.conv_mma(x_full.bfloat16().to(DEV), pack_conv(w), bv.to(DEV) if bias else None, B=B, H=H, W=W, Cin=Cin, KH=k, KW=k,
              stride=stride, pad=pad, dil=dil, Cout=Cout, ld_src=ld_src, src_coff=src_coff, act=act,
              prelu_alpha=alpha.to(DEV) if act == ACT_PRELU else None, residual=res_t, out=out, ld_dst=ld_dst,
              dst_coff=dst_coff)
@@ -152,6 +152,136 @@ def conv_shapes():
         _conv_case("sr_k2s2_320", 1, 4, 6, 320, 320, k=2, stride=2, seed=28),
         _conv_case("src_slice", 1, 9, 11, 32, 32, k=3, pad=1, ld_src=96, src_coff=64, seed=29),
     ]
+    return rs
+
+
+# ----------------------------------------------------------------------------------------- tcgen05 GEMM
+def _tc_case(name, M, K, N, act=ACT_NONE, residual=None, bias=True, ld_src=None, src_coff=0, ld_dst=None, dst_coff=0,
+             out_dtype=torch.float32, seed=0, tol=1e-3):
+    ld_src = ld_src or K
+    x_full = rnd(M, ld_src, seed=seed)
+    w = rnd(N, K, seed=seed + 1, scale=1.0 / math.sqrt(K))
+    bv = rnd(N, seed=seed + 2, bf16=False) * 0.1 if bias else None
+    alpha = torch.tensor([0.25])
+    ref = F.linear(x_full[:, src_coff:src_coff + K], w, bv)
+    if act == ACT_RELU:
+        ref = F.relu(ref)
+    elif act == ACT_PRELU:
+        ref = F.prelu(ref, alpha)
+    elif act == ACT_GELU:
+        ref = F.gelu(ref)
+    res_t = None
+    if residual is not None:
+        res_t = rnd(M, N, seed=seed + 3, bf16=(residual == torch.bfloat16))
+        ref = ref + res_t
+        res_t = res_t.to(residual).to(DEV)
+    ld_dst = ld_dst or N
+    out = torch.full((M, ld_dst), 7.0, dtype=out_dtype, device=DEV)
+    ops.linear_tc(x_full.bfloat16().to(DEV), pack_lin(w), bv.to(DEV) if bias else None, M=M, K=K, ld_src=ld_src,
+                  src_coff=src_coff, act=act, prelu_alpha=alpha.to(DEV) if act == ACT_PRELU else None, residual=res_t,
+                  out=out, ld_dst=ld_dst, dst_coff=dst_coff)
+    r = result(name, rel_err(out[:, dst_coff:dst_coff + N].float(), ref), tol)
+    if ld_dst > N:
+        mask = torch.ones(ld_dst, dtype=torch.bool)
+        mask[dst_coff:dst_coff + N] = False
+        if not bool((out[:, mask.to(DEV)] == 7.0).all()):
+            r["ok"], r["note"] = False, "wrote outside its channel slice"
+    return r
+
+
+@check
+def linear_tcgen05():
+    return [
+        _tc_case("tc_lin_64x64", 1000, 64, 64),
+        _tc_case("tc_lin_128x128_bf16out", 515, 128, 128, out_dtype=torch.bfloat16, seed=2, tol=4e-3),
+        _tc_case("tc_lin_512x2048_gelu", 300, 512, 2048, act=ACT_GELU, seed=3),
+        _tc_case("tc_lin_2048x512_res_f32", 300, 2048, 512, residual=torch.float32, seed=4),
+        _tc_case("tc_lin_320x320_res", 333, 320, 320, residual=torch.float32, seed=5),
+        _tc_case("tc_lin_1024x256_relu", 700, 1024, 256, act=ACT_RELU, seed=7),
+        _tc_case("tc_lin_160x160_b0", 200, 160, 160, seed=9),
+        _tc_case("tc_drdb_1x1_K224_res_bf16", 2 * 384, 224, 64, act=ACT_RELU, residual=torch.bfloat16, seed=22),
+        _tc_case("tc_lin_slice_dst", 257, 64, 256, ld_dst=1024, dst_coff=768, out_dtype=torch.bfloat16, seed=11, tol=4e-3),
+        _tc_case("tc_lin_src_slice_prelu", 400, 96, 32, ld_src=224, src_coff=64, act=ACT_PRELU, seed=12),
+        _tc_case("tc_lin_big_M", 20000, 64, 128, seed=13),
+    ]
+
+
+@check
+def tcgen05_shifted_descriptor():
+    """Which descriptor convention addresses a K-major SW128 tile whose start is not 1024-byte aligned?
+    (decides how the conv kernel's halo-tile taps are encoded; informational -- both variants reported)."""
+    M, K = 256, 128
+    x = rnd(M + 16, K, seed=31)
+    w = rnd(64, K, seed=32, scale=1.0 / math.sqrt(K))
+    rs = []
+    for mode in (0, 1):
+        worst = 0.0
+        for shift in (0, 2, 4, 8, 10):
+            ref = F.linear(x[shift:shift + M], w)
+            got = ops.dbg_linear_tc_shifted(x.bfloat16().to(DEV), pack_lin(w), M, shift, mode)
+            worst = max(worst, rel_err(got, ref))
+        r = result(f"tc_shifted_desc_base_offset_mode{mode}", worst, 1e-3)
+        r["note"] = "informational"
+        rs.append(r)
+    if any(r["ok"] for r in rs):          # at least one convention must work
+        for r in rs:
+            r["ok"] = True
+    return rs
+
+
+def _conv_tc_case(name, B, H, W, Cin, Cout, dil, act=ACT_RELU, ld_src=None, src_coff=0, ld_dst=None, dst_coff=0, seed=0,
+                  tol=4e-3):
+    ld_src = ld_src or Cin
+    x_full = rnd(B, H, W, ld_src, seed=seed)
+    w = rnd(Cout, Cin, 3, 3, seed=seed + 1, scale=1.0 / math.sqrt(Cin * 9))
+    bv = rnd(Cout, seed=seed + 2, bf16=False) * 0.1
+    alpha = torch.tensor([0.25])
+    ref = F.conv2d(x_full[..., src_coff:src_coff + Cin].permute(0, 3, 1, 2), w, bv, padding=dil, dilation=dil)
+    ref = F.relu(ref) if act == ACT_RELU else F.prelu(ref, alpha) if act == ACT_PRELU else ref
+    ref = ref.permute(0, 2, 3, 1).reshape(-1, Cout)
+    ld_dst = ld_dst or Cout
+    out = torch.full((ref.shape[0], ld_dst), 7.0, dtype=torch.bfloat16, device=DEV)
+    ops.conv3x3_tc(x_full.bfloat16().to(DEV), pack_conv(w), bv.to(DEV), B=B, H=H, W=W, Cin=Cin, pad=dil, dil=dil, Cout=Cout,
+                   ld_src=ld_src, src_coff=src_coff, act=act, prelu_alpha=alpha.to(DEV) if act == ACT_PRELU else None,
+                   out=out, ld_dst=ld_dst, dst_coff=dst_coff)
+    got = out[:, dst_coff:dst_coff + Cout].float()
+    r = result(name, rel_err(got, ref), tol)
+    if ld_dst > Cout:
+        mask = torch.ones(ld_dst, dtype=torch.bool)
+        mask[dst_coff:dst_coff + Cout] = False
+        if not bool((out[:, mask.to(DEV)] == 7.0).all()):
+            r["ok"], r["note"] = False, "wrote outside its channel slice"
+    return r
+
+
+def _conv_tc_cases(tag):
+    return [
+        _conv_tc_case(f"tc_dcov1_64_dil2{tag}", 2, 48, 80, 64, 32, 2, ld_src=224, ld_dst=224, dst_coff=64, seed=40),
+        _conv_tc_case(f"tc_dcov2_96_dil2{tag}", 1, 33, 45, 96, 32, 2, ld_src=224, ld_dst=224, dst_coff=96, seed=41),
+        _conv_tc_case(f"tc_dcov4_160_dil2_nsub1{tag}", 1, 40, 24, 160, 32, 2, ld_src=224, ld_dst=224, dst_coff=160, seed=42),
+        _conv_tc_case(f"tc_dcov5_192_dil2_nsub1{tag}", 2, 16, 16, 192, 32, 2, seed=43),
+        _conv_tc_case(f"tc_conv2_128_64_prelu{tag}", 1, 32, 40, 128, 64, 1, act=ACT_PRELU, seed=44),
+        _conv_tc_case(f"tc_conv21_64_32_prelu{tag}", 2, 19, 21, 64, 32, 1, act=ACT_PRELU, seed=45),
+    ]
+
+
+@check
+def conv3x3_tcgen05():
+    """The tcgen05 halo-tile conv under both encodings of the shifted descriptors' base-offset field; the product
+    uses the convention that segmif_dbg_linear_tc_shifted / this check show to be right (informational per mode)."""
+    rs = []
+    for mode in (0, 1):
+        ops.dbg_set_desc_mode(mode)
+        try:
+            rs += _conv_tc_cases(f"_mode{mode}")
+        finally:
+            ops.dbg_set_desc_mode(0)
+    ok0 = all(r["ok"] for r in rs if r["name"].endswith("_mode0"))
+    ok1 = all(r["ok"] for r in rs if r["name"].endswith("_mode1"))
+    for r in rs:
+        r["note"] = (r.get("note", "") + f" [mode0 {'ok' if ok0 else 'BAD'}, mode1 {'ok' if ok1 else 'BAD'}]").strip()
+        if ok0 or ok1:
+            r["ok"] = True
     return rs
 
 

@@ -99,20 +99,11 @@ typedef struct {
   int dst_dtype, ld_dst, dst_coff;
 } segmif_linear_params;
 int segmif_linear_tc_fwd(const segmif_linear_params* p, segmif_stream_t stream);
-/* Diagnostics (tests only): the same GEMM with N == 64 where output row m is computed from src row m + row_shift,
- * read through a shared-memory matrix descriptor whose start is not aligned to the 1024-byte swizzle pattern.
- * base_offset_mode 0: descriptor base-offset field 0; 1: (start >> 7) & 7.  src must have M + 16 rows. */
-int segmif_dbg_linear_tc_shifted(const segmif_linear_params* p, int row_shift, int base_offset_mode,
-                                 segmif_stream_t stream);
-
 /* ---- K10/K11 on tcgen05: 3x3 stride-1 'same' convolution (dilation 1 or 2), Cout in {32, 64}, bf16 out ----------
  * DRDB Dcov1-5 (core/model_fusion.py:135-151), conv2 / conv21 (:1063-1064).  Same parameter block as
  * segmif_conv_fwd (KH=KW=3, stride=1, pad=dil, no residual, bias required); weights resident in shared memory,
  * halo tiles fetched by 4-D TMA, nine taps = nine shifted views of one tile.                                     */
 int segmif_conv3x3_tc_fwd(const segmif_conv_params* p, segmif_stream_t stream);
-/* Diagnostics: selects how segmif_conv3x3_tc_fwd encodes the base-offset field of shifted descriptors (0 | 1). */
-int segmif_dbg_set_desc_mode(int base_offset_mode);
-
 /* ---- K1 (stage 1): 7x7 stride-4 pad-3 patch embedding + LayerNorm --------------------------------
  * replaces core/mix_transformer.py:192-198 for patch_embed1, fused with the input affine of
  * Network3.forward core/model_fusion.py:1083-1085 (x*255 - mean)/std  (pass scale=1, shift=0 otherwise).

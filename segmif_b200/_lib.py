@@ -53,9 +53,7 @@ SIGNATURES = {
     "segmif_layernorm_fwd": [P, c_int, P, P, P, c_int, c_int64, c_int, c_float, P],
     "segmif_conv_fwd": [ctypes.POINTER(ConvParams), P],
     "segmif_linear_tc_fwd": [ctypes.POINTER(LinearParams), P],
-    "segmif_dbg_linear_tc_shifted": [ctypes.POINTER(LinearParams), c_int, c_int, P],
     "segmif_conv3x3_tc_fwd": [ctypes.POINTER(ConvParams), P],
-    "segmif_dbg_set_desc_mode": [c_int],
     "segmif_patch_embed7_ln_fwd": [P, P, P, P, P, c_float, P, P, P, c_int, c_int, c_int, c_int, P],
     "segmif_sr_attention_fwd": [P, c_int, P, P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P],
     "segmif_dwconv3x3_gelu_fwd": [P, P, P, P, c_int, c_int, c_int, c_int, P],

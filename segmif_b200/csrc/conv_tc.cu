@@ -18,14 +18,12 @@
 
 namespace segmif {
 
-static int g_desc_base_offset_mode = 0;   // see segmif_dbg_linear_tc_shifted; fixed after the on-device probe
-
 struct ConvTcArgs {
   const float* bias;
   const float* alpha;
   bf16* dst;
   int B, H, W, nchunks, act, ld_dst, dst_coff;
-  int tiles_x, tiles_y, base_offset_mode, cin;
+  int tiles_x, tiles_y, cin;
 };
 
 constexpr int kConvTcThreads = 192;
@@ -121,11 +119,10 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv3x3_tc_kernel(const __g
 #pragma unroll
             for (int sub = 0; sub < NSUB; ++sub) {
               const uint32_t a_addr = a_base + (uint32_t)((ky * DIL * Cfg::HXP + kx * DIL + sub * 8) * 128);
-              const uint32_t bo = a.base_offset_mode ? ((a_addr >> 7) & 7) : 0;
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                const uint64_t da = tc::make_smem_desc_sw128(a_addr + k * 32, Cfg::HXP * 128, bo);
-                const uint64_t db = tc::make_smem_desc_sw128(w_addr + k * 32, 1024, 0);
+                const uint64_t da = tc::make_smem_desc_sw128(a_addr + k * 32, Cfg::HXP * 128);
+                const uint64_t db = tc::make_smem_desc_sw128(w_addr + k * 32, 1024);
                 tc::umma_bf16(acc + (uint32_t)(sub * COUT), da, db, idesc, (c | t | k) != 0 ? 1u : 0u);
               }
             }
@@ -203,7 +200,6 @@ static int launch_conv_tc(const segmif_conv_params* p, cudaStream_t st) {
   a.bias = p->bias; a.alpha = p->prelu_alpha; a.dst = reinterpret_cast<bf16*>(p->dst);
   a.B = p->B; a.H = p->H; a.W = p->W; a.nchunks = nchunks; a.act = p->act; a.ld_dst = p->ld_dst; a.dst_coff = p->dst_coff;
   a.tiles_x = (p->W + Cfg::TW - 1) / Cfg::TW; a.tiles_y = (p->H + Cfg::TH - 1) / Cfg::TH;
-  a.base_offset_mode = g_desc_base_offset_mode;
   a.cin = p->Cin;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -216,11 +212,6 @@ static int launch_conv_tc(const segmif_conv_params* p, cudaStream_t st) {
 }  // namespace segmif
 
 using namespace segmif;
-
-extern "C" int segmif_dbg_set_desc_mode(int base_offset_mode) {
-  g_desc_base_offset_mode = base_offset_mode ? 1 : 0;
-  return SEGMIF_OK;
-}
 
 extern "C" int segmif_conv3x3_tc_fwd(const segmif_conv_params* p, segmif_stream_t stream) {
   SEGMIF_REQUIRE(p && p->src && p->weight && p->dst && p->bias, "conv3x3_tc: null pointer (bias is required)");

@@ -94,15 +94,11 @@ __device__ __forceinline__ void epilogue_row32(const TcEpilogue& e, float (&v)[3
 constexpr int kTcStages = 4;
 constexpr int kTcThreads = 192;
 
-// DBG: the A box carries 16 extra rows and the MMA reads rows [shift, shift+128) of it through a descriptor whose
-// start address is NOT 1024-byte aligned -- the addressing the conv kernel's halo-tile taps rely on.
-template <int BN, bool DBG>
+template <int BN>
 __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB,
-                                                                const TcEpilogue e, const int num_k_blocks,
-                                                                const int dbg_shift, const int dbg_base_offset_mode) {
-  constexpr int A_ROWS = DBG ? 144 : 128;
-  constexpr int A_BYTES = A_ROWS * 128, B_BYTES = BN * 128;
+                                                                const TcEpilogue e, const int num_k_blocks) {
+  constexpr int A_BYTES = 128 * 128, B_BYTES = BN * 128;
   constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
@@ -148,17 +144,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         const uint32_t ph = (kb / kTcStages) & 1;
         tc::mbar_wait(full + s, ph);
         tc::tc_fence_after();
-        uint32_t a_addr = smem_u32(sA + s * A_BYTES);
-        uint32_t bo = 0;
-        if (DBG) {
-          a_addr += dbg_shift * 128;
-          bo = dbg_base_offset_mode ? ((a_addr >> 7) & 7) : 0;
-        }
+        const uint32_t a_addr = smem_u32(sA + s * A_BYTES);
         const uint32_t b_addr = smem_u32(sB + s * B_BYTES);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const uint64_t da = tc::make_smem_desc_sw128(a_addr + k * 32, 1024, bo);
-          const uint64_t db = tc::make_smem_desc_sw128(b_addr + k * 32, 1024, 0);
+          const uint64_t da = tc::make_smem_desc_sw128(a_addr + k * 32, 1024);
+          const uint64_t db = tc::make_smem_desc_sw128(b_addr + k * 32, 1024);
           tc::umma_bf16(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
         }
         tc::umma_commit(empty + s);            // frees the smem stage when these MMAs have read it
@@ -184,12 +175,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
   if (warp == 1) tc::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-template <int BN, bool DBG>
-static int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcEpilogue& e, int K, int dbg_shift,
-                          int dbg_bo, cudaStream_t st) {
-  constexpr int A_ROWS = DBG ? 144 : 128;
-  constexpr size_t smem = (size_t)kTcStages * (A_ROWS * 128 + BN * 128) + (2 * kTcStages + 1) * 8 + 16;
-  auto kern = gemm_tc_kernel<BN, DBG>;
+template <int BN>
+static int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcEpilogue& e, int K, cudaStream_t st) {
+  constexpr size_t smem = (size_t)kTcStages * (128 * 128 + BN * 128) + (2 * kTcStages + 1) * 8 + 16;
+  auto kern = gemm_tc_kernel<BN>;
   static bool configured = false;
   if (!configured) {
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -197,11 +186,11 @@ static int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
     configured = true;
   }
   dim3 grid((unsigned)ceil_div(e.N, BN), (unsigned)ceil_div(e.M, 128));
-  kern<<<grid, kTcThreads, smem, st>>>(tmA, tmB, e, (int)ceil_div(K, 64), dbg_shift, dbg_bo);
+  kern<<<grid, kTcThreads, smem, st>>>(tmA, tmB, e, (int)ceil_div(K, 64));
   return check_launch("segmif_linear_tc_fwd");
 }
 
-static int linear_tc_impl(const segmif_linear_params* p, cudaStream_t st, bool dbg, int dbg_shift, int dbg_bo) {
+static int linear_tc_impl(const segmif_linear_params* p, cudaStream_t st) {
   SEGMIF_REQUIRE(p && p->src && p->weight && p->dst, "linear_tc: null pointer");
   SEGMIF_REQUIRE(p->M > 0 && p->N > 0 && p->K > 0, "linear_tc: bad sizes");
   SEGMIF_REQUIRE(p->K % 8 == 0 && p->ld_src % 8 == 0 && p->src_coff % 8 == 0, "linear_tc: K, ld_src, src_coff must be multiples of 8");
@@ -221,7 +210,7 @@ static int linear_tc_impl(const segmif_linear_params* p, cudaStream_t st, bool d
   {
     const uint64_t dims[2] = {(uint64_t)p->K, (uint64_t)p->M};
     const uint64_t strides[1] = {(uint64_t)p->ld_src * 2};
-    const uint32_t box[2] = {64, dbg ? 144u : 128u};
+    const uint32_t box[2] = {64, 128};
     int rc = make_tmap_bf16_sw128(&tmA, reinterpret_cast<const bf16*>(p->src) + p->src_coff, 2, dims, strides, box, "linear_tc(A)");
     if (rc) return rc;
   }
@@ -236,10 +225,9 @@ static int linear_tc_impl(const segmif_linear_params* p, cudaStream_t st, bool d
   e.bias = p->bias; e.alpha = p->prelu_alpha; e.res = p->residual; e.dst = p->dst;
   e.M = p->M; e.N = p->N; e.act = p->act; e.res_dtype = p->res_dtype; e.ld_res = p->ld_res; e.res_coff = p->res_coff;
   e.dst_dtype = p->dst_dtype; e.ld_dst = p->ld_dst; e.dst_coff = p->dst_coff;
-  if (dbg) return launch_gemm_tc<64, true>(tmA, tmB, e, p->K, dbg_shift, dbg_bo, st);
-  if (BN == 128) return launch_gemm_tc<128, false>(tmA, tmB, e, p->K, 0, 0, st);
-  if (BN == 64) return launch_gemm_tc<64, false>(tmA, tmB, e, p->K, 0, 0, st);
-  return launch_gemm_tc<32, false>(tmA, tmB, e, p->K, 0, 0, st);
+  if (BN == 128) return launch_gemm_tc<128>(tmA, tmB, e, p->K, st);
+  if (BN == 64) return launch_gemm_tc<64>(tmA, tmB, e, p->K, st);
+  return launch_gemm_tc<32>(tmA, tmB, e, p->K, st);
 }
 
 }  // namespace segmif
@@ -247,13 +235,5 @@ static int linear_tc_impl(const segmif_linear_params* p, cudaStream_t st, bool d
 using namespace segmif;
 
 extern "C" int segmif_linear_tc_fwd(const segmif_linear_params* p, segmif_stream_t stream) {
-  return linear_tc_impl(p, as_stream(stream), false, 0, 0);
-}
-
-// Test-only: output row m is computed from A row m + row_shift, read through a shifted (non-1024-aligned) smem descriptor.
-extern "C" int segmif_dbg_linear_tc_shifted(const segmif_linear_params* p, int row_shift, int base_offset_mode,
-                                            segmif_stream_t stream) {
-  SEGMIF_REQUIRE(row_shift >= 0 && row_shift <= 16, "dbg_linear_tc: row_shift out of range");
-  SEGMIF_REQUIRE(p && p->N == 64, "dbg_linear_tc: N must be 64");
-  return linear_tc_impl(p, as_stream(stream), true, row_shift, base_offset_mode);
+  return linear_tc_impl(p, as_stream(stream));
 }

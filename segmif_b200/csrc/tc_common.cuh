@@ -98,13 +98,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 // Shared-memory matrix descriptor for a K-major operand tile stored as 128-byte rows with the 128B swizzle
 // (what TMA writes with CU_TENSOR_MAP_SWIZZLE_128B): rows of one 8-row group are 128 B apart, groups are
 // `sbo_bytes` apart.  bits: [0,14) addr>>4 | [16,30) LBO>>4 (unused here) | [32,46) SBO>>4 | [46,48) version=1 |
-// [49,52) base offset | [61,64) layout (2 = SWIZZLE_128B).
-__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_t sbo_bytes, uint32_t base_offset) {
+// [49,52) base offset = 0 | [61,64) layout (2 = SWIZZLE_128B).
+// Measured on B200 (round 1): the swizzle XOR is taken from the ABSOLUTE shared-memory address bits [7,10), so a
+// descriptor may start at any 128-byte line of a 1024-byte-aligned TMA tile (and the 8-row groups may be any
+// multiple of 1024 bytes apart) with the base-offset field left 0; setting it to (addr >> 7) & 7 gives wrong data.
+// conv_tc.cu's nine tap views of one halo tile rely on exactly this.
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)(base_offset & 7) << 49;
   d |= (uint64_t)2 << 61;
   return d;
 }

@@ -105,8 +105,6 @@ def conv(src, weight, bias, *, B, H, W, Cin, KH=1, KW=1, stride=1, pad=0, dil=1,
 
 
 USE_TCGEN05 = os.environ.get("SEGMIF_TCGEN05", "1") != "0"
-if "SEGMIF_DESC_MODE" in os.environ:          # diagnostics only
-    _lib.check(_lib.load().segmif_dbg_set_desc_mode(int(os.environ["SEGMIF_DESC_MODE"])), "segmif_dbg_set_desc_mode")
 
 
 def _conv3x3_tc_fits(Cin, Cout, dil):
@@ -124,10 +122,6 @@ def conv3x3_tc(src, weight, bias, **kw):
 def conv_mma(src, weight, bias, **kw):
     """Forces the mma.sync implicit-GEMM kernel (segmif_conv_fwd)."""
     return conv(src, weight, bias, entry="segmif_conv_fwd", **kw)
-
-
-def dbg_set_desc_mode(mode):
-    _lib.check(_lib.load().segmif_dbg_set_desc_mode(int(mode)), "segmif_dbg_set_desc_mode")
 
 
 def linear(x, weight, bias, *, act=ACT_NONE, residual=None, out_dtype=torch.bfloat16, out=None, ld_dst=None,
@@ -174,16 +168,6 @@ def linear_tc(x, weight, bias, *, M=None, K=None, ld_src=None, src_coff=0, act=A
     p = _linear_params(x, weight, bias, M, N, K, ld_src, src_coff, act, prelu_alpha, residual, ld_res, res_coff, out,
                        ld_dst, dst_coff)
     _lib.call("segmif_linear_tc_fwd", ctypes.byref(p), st)
-    return out
-
-
-def dbg_linear_tc_shifted(x, weight, M, row_shift, base_offset_mode):
-    """Diagnostics: out[m] = x[m + row_shift] @ W^T through a shifted smem descriptor (N must be 64)."""
-    st = _prep(x, weight)
-    N, K = weight.shape[0], weight.shape[-1]
-    out = torch.empty((M, N), dtype=torch.float32, device=x.device)
-    p = _linear_params(x, weight, None, M, N, K, x.shape[-1], 0, ACT_NONE, None, None, None, 0, out, N, 0)
-    _lib.call("segmif_dbg_linear_tc_shifted", ctypes.byref(p), int(row_shift), int(base_offset_mode), st)
     return out
 
 

@@ -206,29 +206,6 @@ def linear_tcgen05():
     ]
 
 
-@check
-def tcgen05_shifted_descriptor():
-    """Which descriptor convention addresses a K-major SW128 tile whose start is not 1024-byte aligned?
-    (decides how the conv kernel's halo-tile taps are encoded; informational -- both variants reported)."""
-    M, K = 256, 128
-    x = rnd(M + 16, K, seed=31)
-    w = rnd(64, K, seed=32, scale=1.0 / math.sqrt(K))
-    rs = []
-    for mode in (0, 1):
-        worst = 0.0
-        for shift in (0, 2, 4, 8, 10):
-            ref = F.linear(x[shift:shift + M], w)
-            got = ops.dbg_linear_tc_shifted(x.bfloat16().to(DEV), pack_lin(w), M, shift, mode)
-            worst = max(worst, rel_err(got, ref))
-        r = result(f"tc_shifted_desc_base_offset_mode{mode}", worst, 1e-3)
-        r["note"] = "informational"
-        rs.append(r)
-    if any(r["ok"] for r in rs):          # at least one convention must work
-        for r in rs:
-            r["ok"] = True
-    return rs
-
-
 def _conv_tc_case(name, B, H, W, Cin, Cout, dil, act=ACT_RELU, ld_src=None, src_coff=0, ld_dst=None, dst_coff=0, seed=0,
                   tol=4e-3):
     ld_src = ld_src or Cin
@@ -267,22 +244,8 @@ def _conv_tc_cases(tag):
 
 @check
 def conv3x3_tcgen05():
-    """The tcgen05 halo-tile conv under both encodings of the shifted descriptors' base-offset field; the product
-    uses the convention that segmif_dbg_linear_tc_shifted / this check show to be right (informational per mode)."""
-    rs = []
-    for mode in (0, 1):
-        ops.dbg_set_desc_mode(mode)
-        try:
-            rs += _conv_tc_cases(f"_mode{mode}")
-        finally:
-            ops.dbg_set_desc_mode(0)
-    ok0 = all(r["ok"] for r in rs if r["name"].endswith("_mode0"))
-    ok1 = all(r["ok"] for r in rs if r["name"].endswith("_mode1"))
-    for r in rs:
-        r["note"] = (r.get("note", "") + f" [mode0 {'ok' if ok0 else 'BAD'}, mode1 {'ok' if ok1 else 'BAD'}]").strip()
-        if ok0 or ok1:
-            r["ok"] = True
-    return rs
+    """tcgen05 halo-tile conv: all four instantiations (NSUB 1/2, dilation 1/2, Cout 32/64), odd image sizes."""
+    return _conv_tc_cases("")
 
 
 # ----------------------------------------------------------------------------------------- attention

@@ -166,7 +166,7 @@ int segmif_ffm_gram_fwd(const void* x1, int ld1, int coff1, const void* x2, int 
                         int64_t HW, segmif_stream_t stream);
 int segmif_ffm_ctx_fwd(const float* partials, int nchunk, const float* wkv /* fp32 [3][128][64]: kv1, kv2, kv3 */,
                        const float* wend /* fp32 [2][64][128] */, void* folded /* bf16 [B,4,64,64] */,
-                       float* ctx_out /* fp32 [B,3,8,8,8] or NULL */, int B, segmif_stream_t stream);
+                       float* ctx_out /* fp32 [B,3,8,8,8], required */, int B, segmif_stream_t stream);
 int segmif_ffm_apply_fwd(const void* x1, int ld1, int coff1, const void* x2, int ld2, int coff2, const void* x3,
                          int ld3, int C3, const void* wproj, const float* bproj, const void* folded,
                          const float* bend /* [2][64] */, const float* ln_gamma /* [2][64] */,

@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv3x3_tc_kernel(const __g
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (tc::elect_one()) {
       // resident weights: nchunks * 9 tiles of [COUT x 64]
       tc::mbar_expect_tx(wfull, (uint32_t)w_bytes);
       for (int c = 0; c < a.nchunks; ++c)
@@ -97,42 +97,49 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv3x3_tc_kernel(const __g
         }
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = tc::make_idesc_bf16(128, COUT);
-      tc::mbar_wait(wfull, 0);
-      int it = 0, lt = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
-        const int buf = lt & 1;
-        tc::mbar_wait(tmem_empty + buf, ((lt >> 1) & 1) ^ 1);
+    // Whole warp walks the loop (uniform control flow -> descriptors live in uniform registers); the elected lane issues.
+    constexpr uint32_t idesc = tc::make_idesc_bf16(128, COUT);
+    constexpr uint32_t A_HI = tc::desc_hi_sw128(Cfg::HXP * 128), B_HI = tc::desc_hi_sw128(1024);
+    const bool leader = tc::elect_one();
+    tc::mbar_wait(wfull, 0);
+    const uint32_t w_lo0 = smem_u32(sW) >> 4;
+    int it = 0, lt = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      const int buf = lt & 1;
+      tc::mbar_wait(tmem_empty + buf, ((lt >> 1) & 1) ^ 1);
+      tc::tc_fence_after();
+      const uint32_t acc = tmem_base + (uint32_t)(buf * Cfg::ACC_COLS);
+      for (int c = 0; c < a.nchunks; ++c, ++it) {
+        const int s = it & 1;
+        tc::mbar_wait(full + s, (it >> 1) & 1);
         tc::tc_fence_after();
-        const uint32_t acc = tmem_base + (uint32_t)(buf * Cfg::ACC_COLS);
-        for (int c = 0; c < a.nchunks; ++c, ++it) {
-          const int s = it & 1;
-          tc::mbar_wait(full + s, (it >> 1) & 1);
-          tc::tc_fence_after();
-          const uint32_t a_base = smem_u32(sA + s * Cfg::A_BYTES);
-#pragma unroll 1
+        if (leader) {
+          const uint32_t a_lo0 = smem_u32(sA + s * Cfg::A_BYTES) >> 4;
+          const uint32_t w_lo = w_lo0 + (uint32_t)(c * 9 * (Cfg::W_TILE_BYTES >> 4));
+          const uint32_t first = c != 0 ? 1u : 0u;
+#pragma unroll
           for (int t = 0; t < 9; ++t) {
-            const int ky = t / 3, kx = t - ky * 3;
-            const uint32_t w_addr = smem_u32(sW + (c * 9 + t) * Cfg::W_TILE_BYTES);
+            const int ky = t / 3, kx = t % 3;
 #pragma unroll
             for (int sub = 0; sub < NSUB; ++sub) {
-              const uint32_t a_addr = a_base + (uint32_t)((ky * DIL * Cfg::HXP + kx * DIL + sub * 8) * 128);
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                const uint64_t da = tc::make_smem_desc_sw128(a_addr + k * 32, Cfg::HXP * 128);
-                const uint64_t db = tc::make_smem_desc_sw128(w_addr + k * 32, 1024);
-                tc::umma_bf16(acc + (uint32_t)(sub * COUT), da, db, idesc, (c | t | k) != 0 ? 1u : 0u);
+                const uint32_t a_off = (uint32_t)(((ky * DIL * Cfg::HXP + kx * DIL + sub * 8) * 128 + k * 32) >> 4);
+                const uint32_t w_off = (uint32_t)((t * Cfg::W_TILE_BYTES + k * 32) >> 4);
+                tc::umma_bf16_lohi(acc + (uint32_t)(sub * COUT), a_lo0 + a_off, A_HI, w_lo + w_off, B_HI, idesc,
+                                   (t == 0 && k == 0) ? first : 1u);
               }
             }
           }
           tc::umma_commit(empty + s);
         }
-        tc::umma_commit(tmem_full + buf);
+        __syncwarp();
       }
+      if (leader) tc::umma_commit(tmem_full + buf);
+      __syncwarp();
     }
-    __syncwarp();
   } else {
     const int quad = warp & 3;
     const int r = quad * 32 + lane, ty = r >> 3, tx = r & 7;

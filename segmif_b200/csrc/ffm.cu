@@ -152,43 +152,50 @@ __global__ void __launch_bounds__(kFfmThreads) ffm_gram_kernel(const bf16* __res
 }
 
 // ------------------------------------------------------------------------------------------------ pass 2
+// (a) one CTA per (stream, image): deterministic reduction of the Gram partials, T = Wk G, logits = T Wv^T per
+//     head, column softmax (dim=-2)  ->  ctx[b][s][8][8][8] fp32
 __global__ void __launch_bounds__(256) ffm_ctx_kernel(const float* __restrict__ partials, int nchunk,
-                                                      const float* __restrict__ wkv, const float* __restrict__ wend,
-                                                      bf16* __restrict__ folded, float* __restrict__ ctx_out) {
-  extern __shared__ float sm[];
-  float* G = sm;                 // [3][4096]
-  float* T = G + 3 * 4096;       // [4096]
-  float* ctx = T + 4096;         // [3][8][8][8]
-  const int b = blockIdx.x, tid = threadIdx.x;
-  const float* pb = partials + (int64_t)b * nchunk * 3 * 4096;
-  for (int idx = tid; idx < 3 * 4096; idx += 256) {
-    float s = 0.f;
-    for (int c = 0; c < nchunk; ++c) s += pb[(int64_t)c * 3 * 4096 + idx];
-    G[idx] = s;
+                                                      const float* __restrict__ wkv, float* __restrict__ ctx_out) {
+  __shared__ float G[4096];
+  __shared__ float T[4096];
+  __shared__ float lg[512];
+  const int s = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const float* pb = partials + ((int64_t)b * nchunk * 3 + s) * 4096;
+  for (int idx = tid; idx < 4096; idx += 256) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int c = 0;
+    for (; c + 4 <= nchunk; c += 4) {        // four independent loads in flight, fixed summation order
+      a0 += pb[(int64_t)(c + 0) * 3 * 4096 + idx];
+      a1 += pb[(int64_t)(c + 1) * 3 * 4096 + idx];
+      a2 += pb[(int64_t)(c + 2) * 3 * 4096 + idx];
+      a3 += pb[(int64_t)(c + 3) * 3 * 4096 + idx];
+    }
+    for (; c < nchunk; ++c) a0 += pb[(int64_t)c * 3 * 4096 + idx];
+    G[idx] = (a0 + a1) + (a2 + a3);
   }
   __syncthreads();
-  const float scale = 0.35355339059327379f;     // 8^-1/2 (head_dim 8)
-  for (int s = 0; s < 3; ++s) {
-    const float* Wk = wkv + (int64_t)s * 128 * 64;
-    const float* Wv = Wk + 64 * 64;
-    for (int idx = tid; idx < 4096; idx += 256) {     // T = Wk G_s
-      const int r = idx >> 6, c = idx & 63;
-      float a = 0.f;
-      for (int k = 0; k < 64; ++k) a = fmaf(Wk[r * 64 + k], G[s * 4096 + k * 64 + c], a);
-      T[idx] = a;
-    }
-    __syncthreads();
-    for (int idx = tid; idx < 512; idx += 256) {      // logits[h][i][j] = scale * T[h8+i,:] . Wv[h8+j,:]
-      const int h = idx >> 6, i = (idx >> 3) & 7, j = idx & 7;
-      float a = 0.f;
-      for (int c = 0; c < 64; ++c) a = fmaf(T[(h * 8 + i) * 64 + c], Wv[(h * 8 + j) * 64 + c], a);
-      ctx[s * 512 + idx] = a * scale;
-    }
-    __syncthreads();
+  const float* Wk = wkv + (int64_t)s * 128 * 64;
+  const float* Wv = Wk + 64 * 64;
+  for (int idx = tid; idx < 4096; idx += 256) {       // T = Wk G_s
+    const int r = idx >> 6, c = idx & 63;
+    float a = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < 64; ++k) a = fmaf(Wk[r * 64 + k], G[k * 64 + c], a);
+    T[idx] = a;
   }
-  if (tid < 192) {                                    // softmax over i (dim=-2) for every (s, h, j)
-    const int s = tid >> 6, h = (tid >> 3) & 7, j = tid & 7;
-    float* c = ctx + s * 512 + h * 64 + j;
+  __syncthreads();
+  const float scale = 0.35355339059327379f;           // 8^-1/2 (head_dim 8)
+  for (int idx = tid; idx < 512; idx += 256) {        // logits[h][i][j] = scale * T[h8+i,:] . Wv[h8+j,:]
+    const int h = idx >> 6, i = (idx >> 3) & 7, j = idx & 7;
+    float a = 0.f;
+#pragma unroll 8
+    for (int c = 0; c < 64; ++c) a = fmaf(T[(h * 8 + i) * 64 + c], Wv[(h * 8 + j) * 64 + c], a);
+    lg[idx] = a * scale;
+  }
+  __syncthreads();
+  if (tid < 64) {                                     // softmax over i (dim=-2) for every (h, j)
+    const int h = tid >> 3, j = tid & 7;
+    float* c = lg + h * 64 + j;
     float m = -INFINITY;
     for (int i = 0; i < 8; ++i) m = fmaxf(m, c[i * 8]);
     float e[8], sum = 0.f;
@@ -196,19 +203,24 @@ __global__ void __launch_bounds__(256) ffm_ctx_kernel(const float* __restrict__ 
     for (int i = 0; i < 8; ++i) c[i * 8] = e[i] / sum;
   }
   __syncthreads();
-  if (ctx_out)
-    for (int idx = tid; idx < 1536; idx += 256) ctx_out[(int64_t)b * 1536 + idx] = ctx[idx];
-  // folded[m][o][c]: m=0 Mz1 (ctx1, We1[:, :64]); 1 Mv1 (ctx3, We1[:, 64:]); 2 Mz2 (ctx2, We2[:, :64]); 3 Mv2 (ctx3, We2[:, 64:])
-  for (int idx = tid; idx < 4 * 4096; idx += 256) {
-    const int m = idx >> 12, o = (idx >> 6) & 63, c = idx & 63;
+  for (int idx = tid; idx < 512; idx += 256) ctx_out[((int64_t)b * 3 + s) * 512 + idx] = lg[idx];
+}
+
+// (b) folded[b][m][o][c]: m=0 Mz1 (ctx1, We1[:, :64]); 1 Mv1 (ctx3, We1[:, 64:]); 2 Mz2 (ctx2, We2[:, :64]); 3 Mv2 (ctx3, We2[:, 64:])
+__global__ void __launch_bounds__(256) ffm_fold_kernel(const float* __restrict__ ctx, const float* __restrict__ wend,
+                                                       bf16* __restrict__ folded) {
+  const int m = blockIdx.x, b = blockIdx.y;
+  const int stream = m >> 1, is_v = m & 1;
+  const float* cb = ctx + ((int64_t)b * 3 + (is_v ? 2 : stream)) * 512;
+  for (int idx = threadIdx.x; idx < 4096; idx += 256) {
+    const int o = idx >> 6, c = idx & 63;
     const int h = c >> 3, i = c & 7;
-    const int stream = m >> 1, is_v = m & 1;
-    const float* cx = ctx + (is_v ? 2 : stream) * 512 + h * 64 + i * 8;
+    const float* cx = cb + h * 64 + i * 8;
     const float* we = wend + (int64_t)stream * 64 * 128 + o * 128 + (is_v ? 64 : 0) + h * 8;
     float a = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) a = fmaf(cx[j], we[j], a);
-    folded[(int64_t)b * 4 * 4096 + idx] = __float2bfloat16_rn(a);
+    folded[((int64_t)b * 4 + m) * 4096 + idx] = __float2bfloat16_rn(a);
   }
 }
 
@@ -389,12 +401,14 @@ extern "C" int segmif_ffm_gram_fwd(const void* x1, int ld1, int coff1, const voi
 
 extern "C" int segmif_ffm_ctx_fwd(const float* partials, int nchunk, const float* wkv, const float* wend, void* folded,
                                   float* ctx_out, int B, segmif_stream_t stream) {
-  SEGMIF_REQUIRE(partials && wkv && wend && folded, "ffm_ctx: null pointer");
-  const size_t smem = (size_t)(3 * 4096 + 4096 + 1536) * sizeof(float);
-  int rc = set_smem((const void*)ffm_ctx_kernel, smem, "ffm_ctx");
+  SEGMIF_REQUIRE(partials && wkv && wend && folded && ctx_out, "ffm_ctx: null pointer (ctx_out [B,3,8,8,8] is required)");
+  SEGMIF_REQUIRE(nchunk > 0 && B > 0, "ffm_ctx: bad sizes");
+  cudaStream_t st = as_stream(stream);
+  ffm_ctx_kernel<<<dim3(3, B), 256, 0, st>>>(partials, nchunk, wkv, ctx_out);
+  int rc = check_launch("segmif_ffm_ctx_fwd");
   if (rc) return rc;
-  ffm_ctx_kernel<<<B, 256, smem, as_stream(stream)>>>(partials, nchunk, wkv, wend, (bf16*)folded, ctx_out);
-  return check_launch("segmif_ffm_ctx_fwd");
+  ffm_fold_kernel<<<dim3(4, B), 256, 0, st>>>(ctx_out, wend, (bf16*)folded);
+  return check_launch("segmif_ffm_ctx_fwd(fold)");
 }
 
 extern "C" int segmif_ffm_apply_fwd(const void* x1, int ld1, int coff1, const void* x2, int ld2, int coff2,

@@ -94,29 +94,32 @@ __device__ __forceinline__ void epilogue_row32(const TcEpilogue& e, float (&v)[3
 constexpr int kTcStages = 4;
 constexpr int kTcThreads = 192;
 
+// Persistent: each CTA walks output tiles (m-tile major, n-tile minor) with a stride of gridDim.x.  The 4-stage
+// operand ring runs across tile boundaries and the TMEM accumulator is double buffered, so TMA, MMA and the
+// epilogue of consecutive tiles overlap.
 template <int BN>
 __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB,
-                                                                const TcEpilogue e, const int num_k_blocks) {
+                                                                const TcEpilogue e, const int num_k_blocks,
+                                                                const int n_tiles, const int num_tiles) {
   constexpr int A_BYTES = 128 * 128, B_BYTES = BN * 128;
-  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sB = smem + kTcStages * A_BYTES;
   uint64_t* full = reinterpret_cast<uint64_t*>(sB + kTcStages * B_BYTES);
   uint64_t* empty = full + kTcStages;
   uint64_t* tmem_full = empty + kTcStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN;
-  const int m0 = blockIdx.y * 128;
 
   if (threadIdx.x == 0) {
     tc::prefetch_tmap(&tmA);
     tc::prefetch_tmap(&tmB);
     for (int s = 0; s < kTcStages; ++s) { tc::mbar_init(full + s, 1); tc::mbar_init(empty + s, 1); }
-    tc::mbar_init(tmem_full, 1);
+    for (int s = 0; s < 2; ++s) { tc::mbar_init(tmem_full + s, 1); tc::mbar_init(tmem_empty + s, 4); }
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(tmem_slot, TMEM_COLS);
@@ -126,48 +129,66 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      for (int kb = 0; kb < num_k_blocks; ++kb) {
-        const int s = kb % kTcStages;
-        const uint32_t ph = (kb / kTcStages) & 1;
-        tc::mbar_wait(empty + s, ph ^ 1);
-        tc::mbar_expect_tx(full + s, A_BYTES + B_BYTES);
-        tc::tma_load_2d(sA + s * A_BYTES, &tmA, full + s, kb * 64, m0);
-        tc::tma_load_2d(sB + s * B_BYTES, &tmB, full + s, kb * 64, n0);
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = tc::make_idesc_bf16(128, BN);
-      for (int kb = 0; kb < num_k_blocks; ++kb) {
-        const int s = kb % kTcStages;
-        const uint32_t ph = (kb / kTcStages) & 1;
-        tc::mbar_wait(full + s, ph);
-        tc::tc_fence_after();
-        const uint32_t a_addr = smem_u32(sA + s * A_BYTES);
-        const uint32_t b_addr = smem_u32(sB + s * B_BYTES);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t da = tc::make_smem_desc_sw128(a_addr + k * 32, 1024);
-          const uint64_t db = tc::make_smem_desc_sw128(b_addr + k * 32, 1024);
-          tc::umma_bf16(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+    if (tc::elect_one()) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles) * 128, n0 = (tile % n_tiles) * BN;
+        for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
+          const int s = it % kTcStages;
+          const uint32_t ph = (it / kTcStages) & 1;
+          tc::mbar_wait(empty + s, ph ^ 1);
+          tc::mbar_expect_tx(full + s, A_BYTES + B_BYTES);
+          tc::tma_load_2d(sA + s * A_BYTES, &tmA, full + s, kb * 64, m0);
+          tc::tma_load_2d(sB + s * B_BYTES, &tmB, full + s, kb * 64, n0);
         }
-        tc::umma_commit(empty + s);            // frees the smem stage when these MMAs have read it
       }
-      tc::umma_commit(tmem_full);              // accumulator complete
     }
     __syncwarp();
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = tc::make_idesc_bf16(128, BN);
+    constexpr uint32_t HI = tc::desc_hi_sw128(1024);
+    const bool leader = tc::elect_one();
+    int it = 0, lt = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      const int buf = lt & 1;
+      tc::mbar_wait(tmem_empty + buf, ((lt >> 1) & 1) ^ 1);
+      tc::tc_fence_after();
+      const uint32_t acc = tmem_base + (uint32_t)(buf * BN);
+      for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
+        const int s = it % kTcStages;
+        tc::mbar_wait(full + s, (it / kTcStages) & 1);
+        tc::tc_fence_after();
+        if (leader) {
+          const uint32_t a_lo = smem_u32(sA + s * A_BYTES) >> 4, b_lo = smem_u32(sB + s * B_BYTES) >> 4;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc::umma_bf16_lohi(acc, a_lo + k * 2, HI, b_lo + k * 2, HI, idesc, (kb | k) != 0 ? 1u : 0u);
+          tc::umma_commit(empty + s);          // frees the smem stage when these MMAs have read it
+        }
+        __syncwarp();
+      }
+      if (leader) tc::umma_commit(tmem_full + buf);   // accumulator of this tile complete
+      __syncwarp();
+    }
   } else {
     const int quad = warp & 3;                 // TMEM lanes [32*quad, 32*quad+32) are visible to this warp
-    tc::mbar_wait(tmem_full, 0);
-    tc::tc_fence_after();
-    const int64_t m = (int64_t)m0 + quad * 32 + lane;
     const float alpha = (e.act == SEGMIF_ACT_PRELU) ? *e.alpha : 0.f;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      const int buf = lt & 1;
+      const int m0 = (tile / n_tiles) * 128, n0 = (tile % n_tiles) * BN;
+      tc::mbar_wait(tmem_full + buf, (lt >> 1) & 1);
+      tc::tc_fence_after();
+      const int64_t m = (int64_t)m0 + quad * 32 + lane;
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-      float v[32];
-      tc::tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c, v);   // warp-collective: no divergence before it
-      if (m < e.M && (n0 + c) < e.N) epilogue_row32(e, v, m, n0 + c, alpha);
+      for (int c = 0; c < BN; c += 32) {
+        float v[32];
+        tc::tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN + c), v);   // warp-collective
+        if (m < e.M && (n0 + c) < e.N) epilogue_row32(e, v, m, n0 + c, alpha);
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(tmem_empty + buf);
     }
   }
   tc::tc_fence_before();
@@ -177,7 +198,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
 
 template <int BN>
 static int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcEpilogue& e, int K, cudaStream_t st) {
-  constexpr size_t smem = (size_t)kTcStages * (128 * 128 + BN * 128) + (2 * kTcStages + 1) * 8 + 16;
+  constexpr size_t smem = (size_t)kTcStages * (128 * 128 + BN * 128) + (2 * kTcStages + 4) * 8 + 16;
   auto kern = gemm_tc_kernel<BN>;
   static bool configured = false;
   if (!configured) {
@@ -185,8 +206,13 @@ static int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
     if (err != cudaSuccess) { set_error("linear_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(err)); return SEGMIF_ERR_CUDA; }
     configured = true;
   }
-  dim3 grid((unsigned)ceil_div(e.N, BN), (unsigned)ceil_div(e.M, 128));
-  kern<<<grid, kTcThreads, smem, st>>>(tmA, tmB, e, (int)ceil_div(K, 64));
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  const int n_tiles = (int)ceil_div(e.N, BN), m_tiles = (int)ceil_div(e.M, 128);
+  const int64_t num_tiles = (int64_t)n_tiles * m_tiles;
+  const int ctas_per_sm = BN <= 64 ? 2 : 1;          // 96 KB (BN=64) / 80 KB (BN=32) of smem: two CTAs fit and hide latency
+  const int grid = (int)std::min<int64_t>(num_tiles, (int64_t)sms * ctas_per_sm);
+  kern<<<grid, kTcThreads, smem, st>>>(tmA, tmB, e, (int)ceil_div(K, 64), n_tiles, (int)num_tiles);
   return check_launch("segmif_linear_tc_fwd");
 }
 

@@ -274,7 +274,7 @@ def ffm(x1, ld1, coff1, x2, ld2, coff2, x3, ld3, C3, packs, out1, ldo1, coffo1, 
     nchunk = max(1, min((148 * 4) // max(B, 1), (HW + 63) // 64))
     partials = torch.empty((B, nchunk, 3, 64, 64), dtype=torch.float32, device=dev)
     folded = torch.empty((B, 4, 64, 64), dtype=torch.bfloat16, device=dev)
-    ctx = torch.empty((B, 3, 8, 8, 8), dtype=torch.float32, device=dev) if want_ctx else None
+    ctx = torch.empty((B, 3, 8, 8, 8), dtype=torch.float32, device=dev)
     _lib.call("segmif_ffm_gram_fwd", _ptr(x1), ld1, coff1, _ptr(x2), ld2, coff2, _ptr(x3), ld3, C3,
               _ptr(packs["w_gram"]), _ptr(packs["b_gram"]), _ptr(partials), nchunk, B, HW, st)
     _lib.call("segmif_ffm_ctx_fwd", _ptr(partials), nchunk, _ptr(packs["wkv"]), _ptr(packs["wend"]), _ptr(folded),

@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--width", type=int, default=640)
     ap.add_argument("--backbone", default="mit_b2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying the captured CUDA graph")
     ap.add_argument("--profile", action="store_true", help="for ncu: 1 warm-up + K steps, no e2e / CPU legs (not a bench value)")
     return ap.parse_args()
 
@@ -221,18 +222,33 @@ def run_ours(a):
         return
     for _ in range(max(a.warmup, 3)):
         step_dev()
+    use_graph = not a.no_graph
+    launches_per_step = None
+    if use_graph:
+        l0 = _lib.launch_count
+        static = pipe.capture(a.batch, a.height, a.width, dev)       # 2 eager warm-ups + 1 captured step
+        launches_per_step = (_lib.launch_count - l0) // 3
+        for k in static:
+            static[k].copy_(devin[k])
+        step_timed = pipe.replay
+        for _ in range(2):
+            step_timed()
+    else:
+        step_timed = step_dev
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    instrument["on"] = True
     launches0 = _lib.launch_count
-    ms_total = timed(step_dev, a.steps)
-    launches = _lib.launch_count - launches0
-    instrument["on"] = False
+    ms_total = timed(step_timed, a.steps)
+    launches = launches_per_step * a.steps if use_graph else _lib.launch_count - launches0
     for _ in range(2):
         step_host()
     ms_e2e = timed(step_host, a.steps)
     clocks = sampler.stop() if rank == 0 else None
+    # dominant kernel: eager, event-instrumented pass of the same K steps (events cannot be timed inside a graph)
+    instrument["on"] = True
+    ms_instr = timed(step_dev, a.steps)
+    instrument["on"] = False
 
     torch.cuda.synchronize()
     drdb_ms = sum(e0.elapsed_time(e1) for e0, e1, _ in drdb_events)
@@ -258,12 +274,13 @@ def run_ours(a):
                 "dtype": "bf16", "data": "synthetic", "config": workload_config(a, world),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / a.steps},
-                "gpu_launches": launches, "clocks": clocks,
+                "gpu_launches": launches, "launch_mode": "cuda_graph" if use_graph else "eager", "clocks": clocks,
                 "roofline": {"kernel": "conv3x3_tc_kernel<32,2,NSUB> (DRDB Dcov1-5: 3x3 dil-2 implicit GEMM on tcgen05, N=32)",
                              "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                              "frac": (achieved / peak) if achieved else None, "traffic": None,
                              "peak_source": f"{peaks['source']} bf16_tflops_sustained",
-                             "launches": len(drdb_events), "share_of_step": drdb_ms / ms_total if ms_total else None,
+                             "launches": len(drdb_events), "share_of_step": drdb_ms / ms_instr if ms_instr else None,
+                             "measured_in": "eager event-instrumented pass of the same steps (%.2f ms/step)" % (ms_instr / a.steps),
                              "algorithmic": "2*B*H*W*9*Cin*32 FLOP per launch, Cin in {64,96,128,160,192}"},
                 "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)

@@ -6,6 +6,8 @@
 // stride and dilation cost nothing and no im2col buffer exists.  4-stage cp.async ring, XOR-swizzled
 // 64-byte smem rows, ldmatrix + mma.sync m16n8k16.  The epilogue fuses bias, ReLU/PReLU/GELU, the
 // residual add and the channel-offset store that implements DRDB's dense concatenation in place.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace segmif {
@@ -21,6 +23,7 @@ struct ConvArgs {
   int KH, KW, stride, pad, dil, Ho, Wo, Cout;
   int act, res_dtype, ld_res, res_coff, dst_dtype, ld_dst, dst_coff;
   int M;
+  int ksplit;      // > 1: blockIdx.z owns a slice of the k-blocks and accumulates into a pre-zeroed fp32 dst with atomics
 };
 
 constexpr int kBK = 32;      // channels per k-block (64 bytes per smem row)
@@ -46,7 +49,10 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32) conv_mma_kernel(const C
   const int warp_m = warp / WARPS_N, warp_n = warp % WARPS_N;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   const int taps = a.KH * a.KW;
-  const int KB = (a.Cin / kBK) * taps;
+  const int KB_all = (a.Cin / kBK) * taps;
+  const int kb_per = (KB_all + a.ksplit - 1) / a.ksplit;
+  const int kb_first = blockIdx.z * kb_per;
+  const int KB = max(0, min(KB_all, kb_first + kb_per) - kb_first);      // k-blocks of this split
 
   // ---- per-thread gather coordinates of the A rows this thread copies (fixed for the whole K loop)
   int a_iy0[A_ITERS], a_ix0[A_ITERS];
@@ -67,7 +73,8 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32) conv_mma_kernel(const C
     a_boff[i] = (int64_t)b * a.H * a.W;
   }
 
-  auto load_stage = [&](int stage, int kb) {
+  auto load_stage = [&](int stage, int kb_local) {
+    const int kb = kb_first + kb_local;
     const int cidx = kb / taps, tap = kb - cidx * taps;
     const int ky = tap / a.KW, kx = tap - ky * a.KW;
     bf16* dA = sA + stage * BM * kBK;
@@ -161,9 +168,15 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32) conv_mma_kernel(const C
         if (n >= a.Cout) continue;
         const bool pair = (n + 1) < a.Cout;
         float v0 = acc[mt][nt][half * 2 + 0], v1 = acc[mt][nt][half * 2 + 1];
-        if (a.bias) {
+        if (a.bias && blockIdx.z == 0) {
           v0 += a.bias[n];
           if (pair) v1 += a.bias[n + 1];
+        }
+        if (a.ksplit > 1) {                 // split-K: fp32 atomics into the zeroed destination, nothing else fused
+          float* d = reinterpret_cast<float*>(a.dst) + (int64_t)m * a.ld_dst + a.dst_coff + n;
+          atomicAdd(d, v0);
+          if (pair) atomicAdd(d + 1, v1);
+          continue;
         }
         v0 = apply_act(v0, a.act, alpha);
         v1 = apply_act(v1, a.act, alpha);
@@ -204,8 +217,21 @@ static int launch_conv(const ConvArgs& a, cudaStream_t st) {
     if (e != cudaSuccess) { set_error("conv: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return SEGMIF_ERR_CUDA; }
     configured = true;
   }
-  dim3 grid((unsigned)ceil_div(a.M, BM), (unsigned)ceil_div(a.Cout, BN));
-  kern<<<grid, WARPS_M * WARPS_N * 32, smem, st>>>(a);
+  ConvArgs b = a;
+  const int64_t tiles = ceil_div(a.M, BM) * ceil_div(a.Cout, BN);
+  const int KB = (a.Cin / kBK) * a.KH * a.KW;
+  b.ksplit = 1;
+  // Few output tiles but a long reduction (Attention.sr: M = B*Nk = 2400 rows, K up to 4096): spread K over CTAs.
+  if (tiles < 100 && KB >= 16 && a.dst_dtype == SEGMIF_F32 && a.act == SEGMIF_ACT_NONE && a.res == nullptr &&
+      a.ld_dst == a.Cout && a.dst_coff == 0) {
+    b.ksplit = (int)std::min<int64_t>(KB / 4, std::max<int64_t>(1, (148 * 2) / tiles));
+    if (b.ksplit > 1) {
+      cudaError_t e = cudaMemsetAsync(a.dst, 0, (size_t)a.M * a.Cout * sizeof(float), st);
+      if (e != cudaSuccess) { set_error("conv: cudaMemsetAsync failed: %s", cudaGetErrorString(e)); return SEGMIF_ERR_CUDA; }
+    }
+  }
+  dim3 grid((unsigned)ceil_div(a.M, BM), (unsigned)ceil_div(a.Cout, BN), (unsigned)b.ksplit);
+  kern<<<grid, WARPS_M * WARPS_N * 32, smem, st>>>(b);
   return check_launch("segmif_conv_fwd");
 }
 

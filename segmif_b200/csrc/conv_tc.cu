@@ -143,7 +143,9 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv3x3_tc_kernel(const __g
   } else {
     const int quad = warp & 3;
     const int r = quad * 32 + lane, ty = r >> 3, tx = r & 7;
-    const float alpha = (a.act == SEGMIF_ACT_PRELU) ? *a.alpha : 0.f;
+    // act(v) = v >= 0 ? v : slope * v covers none (slope 1), ReLU (0) and PReLU (alpha): branch-free, tiny code --
+    // the epilogue must stay resident in the instruction cache next to the unrolled MMA issue loop.
+    const float slope = a.act == SEGMIF_ACT_PRELU ? *a.alpha : (a.act == SEGMIF_ACT_RELU ? 0.f : 1.f);
     int lt = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
       const int buf = lt & 1;
@@ -152,22 +154,26 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv3x3_tc_kernel(const __g
       const int x0 = (rem % a.tiles_x) * Cfg::TW + tx;
       tc::mbar_wait(tmem_full + buf, (lt >> 1) & 1);
       tc::tc_fence_after();
-#pragma unroll
-      for (int sub = 0; sub < NSUB; ++sub) {
-        const int x = x0 + sub * 8;
 #pragma unroll 1
-        for (int c = 0; c < COUT; c += 32) {
-          float v[32];
-          tc::tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * Cfg::ACC_COLS + sub * COUT + c), v);
-          if (y < a.H && x < a.W) {
+      for (int sc = 0; sc < NSUB * (COUT / 32); ++sc) {
+        const int sub = sc / (COUT / 32), c = (sc % (COUT / 32)) * 32;
+        const int x = x0 + sub * 8;
+        float v[32];
+        tc::tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * Cfg::ACC_COLS + sub * COUT + c), v);
+        if (y < a.H && x < a.W) {
+          const float4* bp = reinterpret_cast<const float4*>(a.bias + c);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j] + __ldg(a.bias + c + j), a.act, alpha);
-            uint4* d = reinterpret_cast<uint4*>(a.dst + (((int64_t)b * a.H + y) * a.W + x) * a.ld_dst + a.dst_coff + c);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              d[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                                pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+          for (int j = 0; j < 8; ++j) {
+            const float4 bv = __ldg(bp + j);
+            v[4 * j] += bv.x; v[4 * j + 1] += bv.y; v[4 * j + 2] += bv.z; v[4 * j + 3] += bv.w;
           }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = v[j] >= 0.f ? v[j] : slope * v[j];
+          uint4* d = reinterpret_cast<uint4*>(a.dst + (((int64_t)b * a.H + y) * a.W + x) * a.ld_dst + a.dst_coff + c);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            d[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                              pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
         }
       }
       tc::tc_fence_before();
@@ -186,8 +192,16 @@ static int launch_conv_tc(const segmif_conv_params* p, cudaStream_t st) {
   const int nchunks = (p->Cin + 63) / 64;
   const size_t smem = (size_t)nchunks * 9 * Cfg::W_TILE_BYTES + 2 * (size_t)Cfg::A_BYTES + 9 * 8 + 16;
   auto kern = conv3x3_tc_kernel<COUT, DIL, NSUB>;
-  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (err != cudaSuccess) { set_error("conv3x3_tc: %zu bytes of shared memory refused: %s", smem, cudaGetErrorString(err)); return SEGMIF_ERR_CUDA; }
+  static bool configured = false;          // opt in once to the full 227 KB (the size varies with Cin; never during graph capture)
+  static int sms = 148;
+  if (!configured) {
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (err != cudaSuccess) { set_error("conv3x3_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(err)); return SEGMIF_ERR_CUDA; }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    configured = true;
+  }
   CUtensorMap tmA, tmW;
   {
     const uint64_t dims[4] = {(uint64_t)p->Cin, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B};
@@ -208,9 +222,6 @@ static int launch_conv_tc(const segmif_conv_params* p, cudaStream_t st) {
   a.B = p->B; a.H = p->H; a.W = p->W; a.nchunks = nchunks; a.act = p->act; a.ld_dst = p->ld_dst; a.dst_coff = p->dst_coff;
   a.tiles_x = (p->W + Cfg::TW - 1) / Cfg::TW; a.tiles_y = (p->H + Cfg::TH - 1) / Cfg::TH;
   a.cin = p->Cin;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int num_tiles = a.tiles_x * a.tiles_y * a.B;
   kern<<<std::min(num_tiles, sms), kConvTcThreads, smem, st>>>(tmA, tmW, a);
   return check_launch("segmif_conv3x3_tc_fwd");

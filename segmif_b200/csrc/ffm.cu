@@ -373,7 +373,10 @@ __global__ void __launch_bounds__(kFfmThreads) ffm_apply_kernel(
   cp_async_wait<0>();
 }
 
-static int set_smem(const void* fn, size_t bytes, const char* what) {
+// one-time opt-in to the largest configuration of each kernel (never called again, e.g. during graph capture)
+static int set_smem(const void* fn, size_t bytes, const char* what, bool* done) {
+  if (*done) return SEGMIF_OK;
+  *done = true;
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
   if (e != cudaSuccess) { set_error("%s: cudaFuncSetAttribute(%zu) failed: %s", what, bytes, cudaGetErrorString(e)); return SEGMIF_ERR_CUDA; }
   return SEGMIF_OK;
@@ -391,7 +394,8 @@ extern "C" int segmif_ffm_gram_fwd(const void* x1, int ld1, int coff1, const voi
   SEGMIF_REQUIRE(ld1 % 8 == 0 && ld2 % 8 == 0 && ld3 % 8 == 0 && coff1 % 8 == 0 && coff2 % 8 == 0, "ffm_gram: pitches/offsets must be multiples of 8");
   SEGMIF_REQUIRE(nchunk > 0 && B > 0 && HW > 0, "ffm_gram: bad sizes");
   const size_t smem = (size_t)(64 * (128 + C3) + kTilePx * 128 + kTilePx * 64) * sizeof(bf16);
-  int rc = set_smem((const void*)ffm_gram_kernel, smem, "ffm_gram");
+  static bool cfg = false;
+  int rc = set_smem((const void*)ffm_gram_kernel, (size_t)(64 * 256 + kTilePx * 128 + kTilePx * 64) * sizeof(bf16), "ffm_gram", &cfg);
   if (rc) return rc;
   dim3 grid(nchunk, B);
   ffm_gram_kernel<<<grid, kFfmThreads, smem, as_stream(stream)>>>((const bf16*)x1 + coff1, ld1, (const bf16*)x2 + coff2, ld2,
@@ -421,7 +425,8 @@ extern "C" int segmif_ffm_apply_fwd(const void* x1, int ld1, int coff1, const vo
   SEGMIF_REQUIRE(ld1 % 8 == 0 && ld2 % 8 == 0 && ld3 % 8 == 0 && coff1 % 8 == 0 && coff2 % 8 == 0, "ffm_apply: input pitches/offsets must be multiples of 8");
   SEGMIF_REQUIRE(ldo1 % 2 == 0 && ldo2 % 2 == 0 && coffo1 % 2 == 0 && coffo2 % 2 == 0, "ffm_apply: output pitches/offsets must be even");
   const size_t smem = (size_t)(64 * C3 + 2 * 4096 + 4 * 4096 + 2 * kTilePx * 64 + kTilePx * C3) * sizeof(bf16);
-  int rc = set_smem((const void*)ffm_apply_kernel, smem, "ffm_apply");
+  static bool cfg = false;
+  int rc = set_smem((const void*)ffm_apply_kernel, (size_t)(64 * 128 + 2 * 4096 + 4 * 4096 + 2 * kTilePx * 64 + kTilePx * 128) * sizeof(bf16), "ffm_apply", &cfg);
   if (rc) return rc;
   const int64_t ntiles = (HW + kTilePx - 1) / kTilePx;
   const int per_image = (int)std::min<int64_t>(ntiles, std::max<int64_t>(1, (148 * 2 * 4) / B));

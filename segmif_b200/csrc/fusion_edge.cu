@@ -5,40 +5,65 @@
 namespace segmif {
 
 // conv1_ir / conv1_vis: fp32 plane [B,H,W] -> bf16 pixel-major, Cout channels (multiple of 8).
-// thread = (pixel, 8-channel group); the 9 input taps come from L1.
+// A thread owns one 8-channel group (its 72 weights stay in registers) and 4 horizontally consecutive pixels (18 input
+// loads instead of 36); a warp covers 16 consecutive pixels x 8 groups, so every store instruction writes whole
+// 128-byte pixel records.  Requires Cout == 64 (8 groups); other widths use more warps per pixel block.
 __global__ void __launch_bounds__(256) conv3x3_in1_kernel(const float* __restrict__ plane, int64_t bstride,
                                                           const float* __restrict__ w, const float* __restrict__ bias,
                                                           const float* __restrict__ alpha_p, bf16* __restrict__ dst,
                                                           int ld_dst, int dst_coff, int B, int H, int W, int Cout) {
-  const int cg = Cout >> 3;
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (int64_t)B * H * W * cg) return;
-  const int c = (int)(idx % cg) * 8;
-  const int64_t pix = idx / cg;
-  const int X = (int)(pix % W), Y = (int)((pix / W) % H);
-  const int64_t b = pix / ((int64_t)W * H);
+  const int lane = threadIdx.x & 31, warp_in_blk = threadIdx.x >> 5;
+  const int ngroups = Cout >> 3;                       // channel groups of 8
+  const int gpw = ngroups < 8 ? ngroups : 8;           // groups handled by one warp (8 lanes-groups)
+  const int cg_sets = (ngroups + 7) / 8;               // warps needed to cover all channels of one pixel block
+  const int xblocks = (W + 15) / 16;
+  const int64_t units = (int64_t)B * H * xblocks * cg_sets;
+  const int64_t unit = (int64_t)blockIdx.x * 8 + warp_in_blk;
+  if (unit >= units) return;
+  const int cset = (int)(unit % cg_sets);
+  const int64_t u2 = unit / cg_sets;
+  const int xb = (int)(u2 % xblocks);
+  const int y = (int)((u2 / xblocks) % H);
+  const int64_t b = u2 / ((int64_t)xblocks * H);
+  const int grp = cset * 8 + (lane & 7), q = lane >> 3;
+  if ((lane & 7) >= gpw || grp >= ngroups) return;
+  const int c = grp * 8;
   const float alpha = *alpha_p;
+  float wr[9][8], bs[8];
+  load8(bias + c, bs);
+#pragma unroll
+  for (int t = 0; t < 9; ++t) load8(w + t * Cout + c, wr[t]);
+  const int x0 = xb * 16 + q * 4;
   const float* src = plane + b * bstride;
-  float acc[8];
-  load8(bias + c, acc);
+  float in[3][6];
 #pragma unroll
-  for (int ky = 0; ky < 3; ++ky) {
-    const int iy = Y + ky - 1;
-    if ((unsigned)iy >= (unsigned)H) continue;
+  for (int r = 0; r < 3; ++r) {
+    const int iy = y + r - 1;
 #pragma unroll
-    for (int kx = 0; kx < 3; ++kx) {
-      const int ix = X + kx - 1;
-      if ((unsigned)ix >= (unsigned)W) continue;
-      const float v = src[(int64_t)iy * W + ix];
-      float wv[8];
-      load8(w + (ky * 3 + kx) * Cout + c, wv);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wv[j], acc[j]);
+    for (int cc = 0; cc < 6; ++cc) {
+      const int ix = x0 + cc - 1;
+      in[r][cc] = ((unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W) ? src[(int64_t)iy * W + ix] : 0.f;
     }
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = acc[j] >= 0.f ? acc[j] : alpha * acc[j];
-  store8(dst + pix * ld_dst + dst_coff + c, acc);
+  for (int i = 0; i < 4; ++i) {
+    const int x = x0 + i;
+    if (x >= W) break;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = bs[j];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const float v = in[r][i + kx];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wr[r * 3 + kx][j], acc[j]);
+      }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = acc[j] >= 0.f ? acc[j] : alpha * acc[j];
+    store8(dst + ((b * H + y) * W + x) * ld_dst + dst_coff + c, acc);
+  }
 }
 
 // conv22: bf16 pixel-major Cin channels -> fp32 plane [B,1,H,W]; a quad of 4 lanes shares one pixel
@@ -146,9 +171,9 @@ extern "C" int segmif_conv3x3_in1_fwd(const float* plane, int64_t bstride, const
                                       int W, int Cout, segmif_stream_t stream) {
   SEGMIF_REQUIRE(plane && w && bias && prelu_alpha && dst, "conv3x3_in1: null pointer");
   SEGMIF_REQUIRE(Cout % 8 == 0 && ld_dst % 8 == 0 && dst_coff % 8 == 0, "conv3x3_in1: channel counts must be multiples of 8");
-  const int64_t total = (int64_t)B * H * W * (Cout / 8);
-  if (total == 0) return SEGMIF_OK;
-  conv3x3_in1_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, as_stream(stream)>>>(
+  const int64_t units = (int64_t)B * H * ((W + 15) / 16) * ((Cout / 8 + 7) / 8);     // one warp each
+  if (units == 0) return SEGMIF_OK;
+  conv3x3_in1_kernel<<<(unsigned)ceil_div(units, 8), 256, 0, as_stream(stream)>>>(
       plane, bstride, w, bias, prelu_alpha, (bf16*)dst, ld_dst, dst_coff, B, H, W, Cout);
   return check_launch("segmif_conv3x3_in1_fwd");
 }

@@ -50,15 +50,25 @@ struct TcEpilogue {
   int M, N, act, res_dtype, ld_res, res_coff, dst_dtype, ld_dst, dst_coff;
 };
 
-// one output row (this thread) x 32 columns starting at n
-__device__ __forceinline__ void epilogue_row32(const TcEpilogue& e, float (&v)[32], int64_t m, int n, float alpha) {
+// one output row (this thread) x 32 columns starting at n.  `slope`: act(v) = v >= 0 ? v : slope*v covers none (1),
+// ReLU (0) and PReLU (alpha) without branches; GELU is a separate template flag so that its 32 inlined erf bodies do
+// not bloat the common instantiation (the epilogue has to stay in the instruction cache).
+template <bool GELU>
+__device__ __forceinline__ void epilogue_row32(const TcEpilogue& e, float (&v)[32], int64_t m, int n, float slope) {
   if (e.bias) {
+    const float4* bp = reinterpret_cast<const float4*>(e.bias + n);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] += __ldg(e.bias + n + j);
+    for (int j = 0; j < 8; ++j) {
+      const float4 bv = __ldg(bp + j);
+      v[4 * j] += bv.x; v[4 * j + 1] += bv.y; v[4 * j + 2] += bv.z; v[4 * j + 3] += bv.w;
+    }
   }
-  if (e.act != SEGMIF_ACT_NONE) {
+  if (GELU) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], e.act, alpha);
+    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = v[j] >= 0.f ? v[j] : slope * v[j];
   }
   if (e.res) {
     const int64_t ro = m * e.ld_res + e.res_coff + n;
@@ -97,7 +107,7 @@ constexpr int kTcThreads = 192;
 // Persistent: each CTA walks output tiles (m-tile major, n-tile minor) with a stride of gridDim.x.  The 4-stage
 // operand ring runs across tile boundaries and the TMEM accumulator is double buffered, so TMA, MMA and the
 // epilogue of consecutive tiles overlap.
-template <int BN>
+template <int BN, bool GELU>
 __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB,
                                                                 const TcEpilogue e, const int num_k_blocks,
@@ -172,7 +182,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
     }
   } else {
     const int quad = warp & 3;                 // TMEM lanes [32*quad, 32*quad+32) are visible to this warp
-    const float alpha = (e.act == SEGMIF_ACT_PRELU) ? *e.alpha : 0.f;
+    const float slope = e.act == SEGMIF_ACT_PRELU ? *e.alpha : (e.act == SEGMIF_ACT_RELU ? 0.f : 1.f);
     int lt = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
       const int buf = lt & 1;
@@ -184,7 +194,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
       for (int c = 0; c < BN; c += 32) {
         float v[32];
         tc::tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN + c), v);   // warp-collective
-        if (m < e.M && (n0 + c) < e.N) epilogue_row32(e, v, m, n0 + c, alpha);
+        if (m < e.M && (n0 + c) < e.N) epilogue_row32<GELU>(e, v, m, n0 + c, slope);
       }
       tc::tc_fence_before();
       __syncwarp();
@@ -196,10 +206,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
   if (warp == 1) tc::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-template <int BN>
+template <int BN, bool GELU>
 static int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcEpilogue& e, int K, cudaStream_t st) {
   constexpr size_t smem = (size_t)kTcStages * (128 * 128 + BN * 128) + (2 * kTcStages + 4) * 8 + 16;
-  auto kern = gemm_tc_kernel<BN>;
+  auto kern = gemm_tc_kernel<BN, GELU>;
   static bool configured = false;
   if (!configured) {
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -221,6 +231,7 @@ static int linear_tc_impl(const segmif_linear_params* p, cudaStream_t st) {
   SEGMIF_REQUIRE(p->M > 0 && p->N > 0 && p->K > 0, "linear_tc: bad sizes");
   SEGMIF_REQUIRE(p->K % 8 == 0 && p->ld_src % 8 == 0 && p->src_coff % 8 == 0, "linear_tc: K, ld_src, src_coff must be multiples of 8");
   SEGMIF_REQUIRE(p->N % 32 == 0, "linear_tc: N=%d must be a multiple of 32", p->N);
+  SEGMIF_REQUIRE(p->bias == nullptr || ((uintptr_t)p->bias & 15) == 0, "linear_tc: bias must be 16-byte aligned");
   SEGMIF_REQUIRE(p->src_coff + p->K <= p->ld_src && p->dst_coff + p->N <= p->ld_dst, "linear_tc: channel slice exceeds pitch");
   const int dalign = p->dst_dtype == SEGMIF_F32 ? 4 : 8;
   SEGMIF_REQUIRE(p->ld_dst % dalign == 0 && p->dst_coff % dalign == 0, "linear_tc: dst pitch/offset must be 16-byte multiples");
@@ -251,9 +262,14 @@ static int linear_tc_impl(const segmif_linear_params* p, cudaStream_t st) {
   e.bias = p->bias; e.alpha = p->prelu_alpha; e.res = p->residual; e.dst = p->dst;
   e.M = p->M; e.N = p->N; e.act = p->act; e.res_dtype = p->res_dtype; e.ld_res = p->ld_res; e.res_coff = p->res_coff;
   e.dst_dtype = p->dst_dtype; e.ld_dst = p->ld_dst; e.dst_coff = p->dst_coff;
-  if (BN == 128) return launch_gemm_tc<128>(tmA, tmB, e, p->K, st);
-  if (BN == 64) return launch_gemm_tc<64>(tmA, tmB, e, p->K, st);
-  return launch_gemm_tc<32>(tmA, tmB, e, p->K, st);
+  if (p->act == SEGMIF_ACT_GELU) {
+    if (BN == 128) return launch_gemm_tc<128, true>(tmA, tmB, e, p->K, st);
+    if (BN == 64) return launch_gemm_tc<64, true>(tmA, tmB, e, p->K, st);
+    return launch_gemm_tc<32, true>(tmA, tmB, e, p->K, st);
+  }
+  if (BN == 128) return launch_gemm_tc<128, false>(tmA, tmB, e, p->K, st);
+  if (BN == 64) return launch_gemm_tc<64, false>(tmA, tmB, e, p->K, st);
+  return launch_gemm_tc<32, false>(tmA, tmB, e, p->K, st);
 }
 
 }  // namespace segmif

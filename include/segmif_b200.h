@@ -104,6 +104,27 @@ int segmif_linear_tc_fwd(const segmif_linear_params* p, segmif_stream_t stream);
  * segmif_conv_fwd (KH=KW=3, stride=1, pad=dil, no residual, bias required); weights resident in shared memory,
  * halo tiles fetched by 4-D TMA, nine taps = nine shifted views of one tile.                                     */
 int segmif_conv3x3_tc_fwd(const segmif_conv_params* p, segmif_stream_t stream);
+/* ---- K10 in push form: one DRDB growth step (core/model_fusion.py:135-151, the five Dcov layers) ---------------
+ * Convolution is linear in its input channels, so the five N=32 layer convolutions are evaluated slab by slab: the
+ * halo tile of ONE input slab (x0: 64 channels, or a freshly produced g_j: 32 channels) is multiplied with the
+ * 3x3 dil-2 weights of EVERY later layer restricted to that slab (n_out = 32 * #layers, up to 128).  Output group i
+ * (32 channels) is  dst = [relu]( partial_in + acc + bias )  -- the group that completes a layer writes g_j into the
+ * growth buffer, the others update bf16 partial pre-activations.  weight: bf16 [n_out][9*64] (slab 64, tap-major) or
+ * [n_out][10*32] (slab 32, taps 0..8 then a zero tap).  All tensors pixel-major bf16.                              */
+typedef struct {
+  const float* bias;        /* fp32 [32] or NULL                        */
+  const void* partial_in;   /* bf16 pixel-major, or NULL                */
+  void* dst;                /* bf16 pixel-major                         */
+  int ld_partial_in, coff_partial_in, ld_dst, coff_dst, relu;
+} segmif_drdb_push_group;
+typedef struct {
+  const void* src;          /* bf16 [B, H, W, ld_src] growth buffer     */
+  const void* weight;
+  int B, H, W, ld_src, slab_offset, slab_width, n_out;
+  segmif_drdb_push_group groups[4];
+} segmif_drdb_push_params;
+int segmif_drdb_push_tc_fwd(const segmif_drdb_push_params* p, segmif_stream_t stream);
+
 /* ---- K1 (stage 1): 7x7 stride-4 pad-3 patch embedding + LayerNorm --------------------------------
  * replaces core/mix_transformer.py:192-198 for patch_embed1, fused with the input affine of
  * Network3.forward core/model_fusion.py:1083-1085 (x*255 - mean)/std  (pass scale=1, shift=0 otherwise).

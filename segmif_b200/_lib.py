@@ -44,6 +44,17 @@ class LinearParams(ctypes.Structure):
     ]
 
 
+class DrdbPushGroup(ctypes.Structure):
+    _fields_ = [("bias", c_void_p), ("partial_in", c_void_p), ("dst", c_void_p), ("ld_partial_in", c_int),
+                ("coff_partial_in", c_int), ("ld_dst", c_int), ("coff_dst", c_int), ("relu", c_int)]
+
+
+class DrdbPushParams(ctypes.Structure):
+    """Mirror of segmif_drdb_push_params."""
+    _fields_ = [("src", c_void_p), ("weight", c_void_p), ("B", c_int), ("H", c_int), ("W", c_int), ("ld_src", c_int),
+                ("slab_offset", c_int), ("slab_width", c_int), ("n_out", c_int), ("groups", DrdbPushGroup * 4)]
+
+
 P = c_void_p
 # name -> argtypes; every function returns int except where noted in _RESTYPES
 SIGNATURES = {
@@ -54,6 +65,7 @@ SIGNATURES = {
     "segmif_conv_fwd": [ctypes.POINTER(ConvParams), P],
     "segmif_linear_tc_fwd": [ctypes.POINTER(LinearParams), P],
     "segmif_conv3x3_tc_fwd": [ctypes.POINTER(ConvParams), P],
+    "segmif_drdb_push_tc_fwd": [ctypes.POINTER(DrdbPushParams), P],
     "segmif_patch_embed7_ln_fwd": [P, P, P, P, P, c_float, P, P, P, c_int, c_int, c_int, c_int, P],
     "segmif_sr_attention_fwd": [P, c_int, P, P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P],
     "segmif_dwconv3x3_gelu_fwd": [P, P, P, P, c_int, c_int, c_int, c_int, P],

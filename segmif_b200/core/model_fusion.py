@@ -7,6 +7,8 @@ five dilated convs append their 32 channels in place (torch.cat never runs) and 
 conv3 / conv4 on the segmentation features are folded into channel_proj3 on the host (both are linear and
 nothing sits between them), so the FFM kernels read the upsampled encoder features directly.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -160,6 +162,7 @@ Network = Network3     # core/__init__.py:4 of the reference imports a `Network`
 class DRDB(nn.Module):
     """Dilated residual dense block (core/model_fusion.py:117-157)."""
     GROWTH_LD = 224
+    USE_PUSH = os.environ.get("SEGMIF_DRDB_PULL", "0") != "1"
 
     def __init__(self, in_ch=64, growth_rate=32):
         super().__init__()
@@ -171,12 +174,50 @@ class DRDB(nn.Module):
         self.in_ch, self.growth, self.total = in_ch, growth_rate, c
         self._packs = PackCache()
 
-    def forward_buffer(self, buf, B, H, W, out=None, ld_dst=None, dst_coff=0):
+    # ---- push form of the five growth layers (see csrc/drdb_tc.cu) -------------------------------------------------
+    def _push_packs(self):
+        """Per step: bf16 weights of every later layer restricted to one input slab, [n_out][taps*slab] tap-major."""
+        convs = [getattr(self, f"Dcov{i}") for i in range(1, 6)]
+
+        def build(*ws):
+            def slab(layers, c0, c1):
+                w = torch.cat([ws[j - 1].detach().float()[:, c0:c1] for j in layers], 0)          # [n_out, slab, 3, 3]
+                w = w.permute(0, 2, 3, 1).reshape(w.shape[0], 9, c1 - c0)                          # [n_out, tap, slab]
+                if c1 - c0 == 32:                                                                   # two taps per 128-byte row
+                    w = torch.cat([w, torch.zeros_like(w[:, :1])], 1)
+                return w.reshape(w.shape[0], -1).to(torch.bfloat16).contiguous()
+            g = self.growth
+            c = self.in_ch
+            return [slab((1, 2, 3), 0, c), slab((4, 5), 0, c), slab((2, 3, 4, 5), c, c + g),
+                    slab((3, 4, 5), c + g, c + 2 * g), slab((4, 5), c + 2 * g, c + 3 * g), slab((5,), c + 3 * g, c + 4 * g)]
+        return self._packs.get_multi([cv.weight for cv in convs], build, "push")
+
+    def _growth_push(self, buf, part, B, H, W):
+        """buf [B,H,W,224] holds x0 in channels 0..63; part [B,H,W,128] receives the partial pre-activations P2..P5."""
+        w = self._push_packs()
+        b = [getattr(self, f"Dcov{i}").bias.detach() for i in range(1, 6)]
+        c, g = self.in_ch, self.growth
+        G = lambda coff, bias, pin_off: dict(bias=bias, partial_in=part if pin_off is not None else None,
+                                             coff_partial_in=pin_off or 0, dst=buf, coff_dst=coff, relu=True)
+        Pn = lambda off, fresh: dict(bias=None, partial_in=None if fresh else part, coff_partial_in=off, dst=part,
+                                     coff_dst=off, relu=False)
+        ops.drdb_push(buf, w[0], B, H, W, 0, c, [G(c, b[0], None), Pn(0, True), Pn(g, True)])
+        ops.drdb_push(buf, w[1], B, H, W, 0, c, [Pn(2 * g, True), Pn(3 * g, True)])
+        ops.drdb_push(buf, w[2], B, H, W, c, g, [G(c + g, b[1], 0), Pn(g, False), Pn(2 * g, False), Pn(3 * g, False)])
+        ops.drdb_push(buf, w[3], B, H, W, c + g, g, [G(c + 2 * g, b[2], g), Pn(2 * g, False), Pn(3 * g, False)])
+        ops.drdb_push(buf, w[4], B, H, W, c + 2 * g, g, [G(c + 3 * g, b[3], 2 * g), Pn(3 * g, False)])
+        ops.drdb_push(buf, w[5], B, H, W, c + 3 * g, g, [G(c + 4 * g, b[4], 3 * g)])
+
+    def forward_buffer(self, buf, B, H, W, out=None, ld_dst=None, dst_coff=0, partials=None):
         """`buf` bf16 [B, H, W, total] with the block input in channels 0..in_ch; appends the five growth slices
-        in place, then writes x + relu(conv1x1(all)) to `out` (pixel-major bf16)."""
+        in place, then writes x + relu(conv1x1(all)) to `out` (pixel-major bf16).  `partials` (bf16 [B,H,W,128]
+        scratch) selects the push form of the growth layers; without it the per-layer (pull) kernels run."""
         ld = buf.shape[-1]
         cin = self.in_ch
-        for i in range(1, 6):
+        if partials is not None and DRDB.USE_PUSH and self.in_ch == 64 and self.growth == 32:
+            self._growth_push(buf, partials, B, H, W)
+            cin = self.total
+        for i in range(1, 6) if cin == self.in_ch else ():
             cv = getattr(self, f"Dcov{i}")
             ops.conv(buf, self._packs.conv(cv.weight), cv.bias.detach(), B=B, H=H, W=W, Cin=cin, ld_src=ld, KH=3, KW=3,
                      pad=2, dil=2, Cout=self.growth, act=ACT_RELU, out=buf.view(-1, ld), ld_dst=ld, dst_coff=cin)
@@ -190,7 +231,8 @@ class DRDB(nn.Module):
         B, C, H, W = x.shape
         buf = torch.empty((B, H, W, self.total), dtype=torch.bfloat16, device=x.device)
         ops.nchw_to_nhwc(x.float().contiguous(), out=buf.view(B, H * W, self.total), ld_dst=self.total)
-        y = self.forward_buffer(buf, B, H, W)
+        part = torch.empty((B, H, W, 128), dtype=torch.bfloat16, device=x.device)
+        y = self.forward_buffer(buf, B, H, W, partials=part)
         return ops.nhwc_to_nchw(y, B, H * W, C).view(B, C, H, W)
 
 
@@ -344,13 +386,14 @@ class Fusion_Network3_ac(nn.Module):
         # x = PReLU(conv1(channel 0)) written straight into the DRDB growth buffers
         ops.conv3x3_in1(ir, self._packs.taps_f32(self.conv1_ir.weight), self.conv1_ir.bias.detach(), alpha, buf1, G, 0, 64)
         ops.conv3x3_in1(vis, self._packs.taps_f32(self.conv1_vis.weight), self.conv1_vis.bias.detach(), alpha, buf2, G, 0, 64)
-        x1 = self.DRDB1.forward_buffer(buf1, B, H, W)                    # [B*HW, 64] bf16
-        x2 = self.DRDB2.forward_buffer(buf2, B, H, W)
+        part = torch.empty((B, H, W, 128), dtype=torch.bfloat16, device=dev)   # P2..P5 scratch, reused by all four DRDBs
+        x1 = self.DRDB1.forward_buffer(buf1, B, H, W, partials=part)    # [B*HW, 64] bf16
+        x2 = self.DRDB2.forward_buffer(buf2, B, H, W, partials=part)
         # ffm(x1, x2, conv3(out1)) -> inputs of DRDB3 / DRDB4 (channels 0..63 of the growth buffers)
         self.ffm.forward_pixel_major(x1, 64, x2, 64, seg1, seg1.shape[-1], buf1, G, 0, buf2, G, 0, B, HW,
                                      pre_conv=self.conv3)
-        x1 = self.DRDB3.forward_buffer(buf1, B, H, W, out=x1, ld_dst=64)
-        x2 = self.DRDB4.forward_buffer(buf2, B, H, W, out=x2, ld_dst=64)
+        x1 = self.DRDB3.forward_buffer(buf1, B, H, W, out=x1, ld_dst=64, partials=part)
+        x2 = self.DRDB4.forward_buffer(buf2, B, H, W, out=x2, ld_dst=64, partials=part)
         # second pass of the SAME ffm with conv4(out2); outputs land side by side = torch.cat([x1, x2], 1)
         cat = torch.empty((B, H, W, 128), dtype=torch.bfloat16, device=dev)
         self.ffm.forward_pixel_major(x1, 64, x2, 64, seg2, seg2.shape[-1], cat, 128, 0, cat, 128, 64, B, HW,

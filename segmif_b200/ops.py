@@ -119,6 +119,27 @@ def conv3x3_tc(src, weight, bias, **kw):
     return conv(src, weight, bias, KH=3, KW=3, entry="segmif_conv3x3_tc_fwd", **kw)
 
 
+def drdb_push(buf, weight, B, H, W, slab_offset, slab_width, groups):
+    """One DRDB growth step in push form (segmif_drdb_push_tc_fwd).  `groups`: list of dicts
+    (bias, partial_in, coff_partial_in, dst, coff_dst, relu), one per 32 output channels."""
+    tensors = [buf, weight] + [g.get("bias") for g in groups] + [g.get("partial_in") for g in groups] + [g["dst"] for g in groups]
+    st = _prep(*tensors)
+    p = _lib.DrdbPushParams()
+    p.src, p.weight = buf.data_ptr(), weight.data_ptr()
+    p.B, p.H, p.W, p.ld_src = B, H, W, buf.shape[-1]
+    p.slab_offset, p.slab_width, p.n_out = slab_offset, slab_width, 32 * len(groups)
+    for i, g in enumerate(groups):
+        q = p.groups[i]
+        q.bias = g["bias"].data_ptr() if g.get("bias") is not None else None
+        pin = g.get("partial_in")
+        q.partial_in = pin.data_ptr() if pin is not None else None
+        q.ld_partial_in = pin.shape[-1] if pin is not None else 0
+        q.coff_partial_in = g.get("coff_partial_in", 0)
+        q.dst, q.ld_dst, q.coff_dst = g["dst"].data_ptr(), g["dst"].shape[-1], g["coff_dst"]
+        q.relu = 1 if g.get("relu") else 0
+    _lib.call("segmif_drdb_push_tc_fwd", ctypes.byref(p), st)
+
+
 def conv_mma(src, weight, bias, **kw):
     """Forces the mma.sync implicit-GEMM kernel (segmif_conv_fwd)."""
     return conv(src, weight, bias, entry="segmif_conv_fwd", **kw)

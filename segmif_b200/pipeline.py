@@ -76,6 +76,74 @@ class FusionSegPipeline:
             self._pinned[name] = t
         return t
 
+    # ---- pipelined host-buffer path: H2D of step k+1 and D2H of step k-1 overlap the compute of step k ------------
+    def _pipe_state(self, device):
+        if getattr(self, "_ps", None) is None:
+            dev = torch.device(device)
+            si = self._static_in
+            mk = lambda t: [torch.empty_like(t) for _ in range(2)]
+            self._ps = dict(
+                h2d=torch.cuda.Stream(device=dev), d2h=torch.cuda.Stream(device=dev),
+                stage_in=[{k: torch.empty_like(v) for k, v in si.items()} for _ in range(2)],
+                stage_out=None, in_ready=[torch.cuda.Event() for _ in range(2)], in_free=[None, None],
+                out_ready=[torch.cuda.Event() for _ in range(2)], out_free=[None, None], k=0)
+        return self._ps
+
+    @torch.no_grad()
+    def submit_host(self, ir_host, vis_host, mask_host, device):
+        """Asynchronous variant of run_host for streams of batches (requires capture()): the inputs are copied on a
+        dedicated H2D stream into one of two staging sets, the captured graph runs on the current stream, and the
+        results are copied back on a dedicated D2H stream into one of two pinned host sets.  Returns
+        (fused_host, labels_host, done_event); the host buffers are valid once `done_event` has completed and are
+        reused two submissions later."""
+        if self._graph is None:
+            raise RuntimeError("submit_host: call capture() first")
+        ps = self._pipe_state(device)
+        cur = torch.cuda.current_stream(torch.device(device))
+        slot = ps["k"] & 1
+        ps["k"] += 1
+        st = ps["stage_in"][slot]
+        with torch.cuda.stream(ps["h2d"]):
+            if ps["in_free"][slot] is not None:
+                ps["h2d"].wait_event(ps["in_free"][slot])          # staging set consumed by the step two submissions ago
+            st["ir"].copy_(ir_host, non_blocking=True)
+            st["vis"].copy_(vis_host, non_blocking=True)
+            st["mask"].copy_(mask_host, non_blocking=True)
+            ps["in_ready"][slot].record(ps["h2d"])
+        cur.wait_event(ps["in_ready"][slot])
+        for k2, v in self._static_in.items():
+            v.copy_(st[k2], non_blocking=True)                      # device-to-device into the graph's static inputs
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        ps["in_free"][slot] = ev
+        fused, labels = self.replay()
+        if ps["stage_out"] is None:
+            ps["stage_out"] = [(torch.empty_like(fused), torch.empty_like(labels)) for _ in range(2)]
+            ps["host_out"] = [(torch.empty(fused.shape, dtype=fused.dtype, pin_memory=True),
+                               torch.empty(labels.shape, dtype=labels.dtype, pin_memory=True)) for _ in range(2)]
+        so = ps["stage_out"][slot]
+        if ps["out_free"][slot] is not None:
+            cur.wait_event(ps["out_free"][slot])                     # D2H of two submissions ago has drained this set
+        so[0].copy_(fused, non_blocking=True)
+        so[1].copy_(labels, non_blocking=True)
+        ps["out_ready"][slot].record(cur)
+        ho = ps["host_out"][slot]
+        with torch.cuda.stream(ps["d2h"]):
+            ps["d2h"].wait_event(ps["out_ready"][slot])
+            ho[0].copy_(so[0], non_blocking=True)
+            ho[1].copy_(so[1], non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(ps["d2h"])
+        ps["out_free"][slot] = done
+        ps["last_done"] = done
+        return ho[0], ho[1], done
+
+    def drain(self, device):
+        """Makes the current stream wait for every outstanding submit_host() copy."""
+        ps = getattr(self, "_ps", None)
+        if ps is not None and ps.get("last_done") is not None:
+            torch.cuda.current_stream(torch.device(device)).wait_event(ps["last_done"])
+
     @torch.no_grad()
     def run_host(self, ir_host, vis_host, mask_host, device):
         """Inputs: pinned (or pageable) CPU tensors.  Copies them to `device`, runs the pipeline (through the

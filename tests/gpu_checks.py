@@ -451,13 +451,27 @@ def models(backbone="mit_b1"):
 
 @check
 def drdb_module():
+    """DRDB against the oracle in both formulations of the growth layers: push (default; every new slab is multiplied
+    into all later layers, N up to 128, bf16 partial pre-activations) and pull (one N=32 conv per layer)."""
+    from segmif_b200.core.model_fusion import DRDB
     seg, fus, (seg_sd, fus_sd) = models()
-    x = rnd(1, 64, 24, 40, seed=1)
-    with torch.no_grad():
-        ref = O.drdb(x, fus_sd, "DRDB1")
-        got = fus.DRDB1(x.to(DEV))
-    # 6 chained bf16 tensor-core layers with bf16 storage between them
-    return result("DRDB_vs_oracle", rel_err(got, ref), 2e-2)
+    rs = []
+    for shape in ((1, 64, 24, 40), (2, 64, 37, 53)):           # second one: sizes that are not tile multiples
+        x = rnd(*shape, seed=shape[2])
+        with torch.no_grad():
+            ref = O.drdb(x, fus_sd, "DRDB1")
+            keep = DRDB.USE_PUSH
+            try:
+                DRDB.USE_PUSH = True
+                push = fus.DRDB1(x.to(DEV))
+                DRDB.USE_PUSH = False
+                pull = fus.DRDB1(x.to(DEV))
+            finally:
+                DRDB.USE_PUSH = keep
+        # 6 chained bf16 tensor-core layers with bf16 storage (and, for push, bf16 partial sums) between them
+        rs.append(result(f"DRDB_push_vs_oracle_{shape[2]}x{shape[3]}", rel_err(push, ref), 2e-2))
+        rs.append(result(f"DRDB_pull_vs_oracle_{shape[2]}x{shape[3]}", rel_err(pull, ref), 2e-2))
+    return rs
 
 
 @check

@@ -182,7 +182,7 @@ def run_ours(a):
     instrument = {"on": False}
 
     def conv_hook(src, weight, bias, **kw):
-        if instrument["on"] and kw.get("dil", 1) == 2 and kw.get("Cout") == 32:
+        if instrument["on"] and kw.get("dil", 1) == 2 and kw.get("Cout") == 32:      # DRDB growth conv (pull part)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             out = orig_conv(src, weight, bias, **kw)
@@ -311,14 +311,16 @@ def run_ours(a):
                         "ms_per_step": ms_e2e / a.steps,
                         "mode": "submit_host: copies on dedicated streams overlap neighbouring steps" if use_graph else "run_host: serial"},
                 "gpu_launches": launches, "launch_mode": "cuda_graph" if use_graph else "eager", "clocks": clocks,
-                "roofline": {"kernel": "drdb_push_tc_kernel<N,NSUB,KSLAB> (DRDB Dcov1-5: 3x3 dil-2 implicit GEMM on tcgen05, push form, N=32..128)",
+                "roofline": {"kernel": "DRDB Dcov1-5 (3x3 dil-2 implicit GEMM on tcgen05): drdb_push_tc_kernel<96|64,.,64> for the x0 slab + "
+                                       "conv3x3_tc_kernel<32,2,2> over the g-slabs",
                              "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                              "frac": (achieved / peak) if achieved else None, "traffic": None,
                              "peak_source": f"{peaks['source']} bf16_tflops_sustained",
                              "launches": len(drdb_events), "share_of_step": drdb_ms / ms_instr if ms_instr else None,
                              "measured_in": "eager event-instrumented pass of the same steps (%.2f ms/step)" % (ms_instr / a.steps),
-                             "algorithmic": "2*B*H*W*9*slab*n_out FLOP per launch; per DRDB the six launches sum to 2*B*H*W*9*640*32, "
-                                            "the FLOPs of the five reference layers (Cin 64..192 -> 32)"},
+                             "algorithmic": "2*B*H*W*9*K*N FLOP per launch (K = input channels of the launch, N = its output channels); "
+                                            "per DRDB the launches sum to 2*B*H*W*9*640*32, the FLOPs of the five reference "
+                                            "layers (Cin 64..192 -> 32)"},
                 "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:

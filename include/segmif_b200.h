@@ -79,6 +79,8 @@ typedef struct {
   int act;
   int res_dtype, ld_res, res_coff;
   int dst_dtype, ld_dst, dst_coff;
+  const void* pre_add;    /* bf16 [M, ld_pre] or NULL: added BEFORE the activation (segmif_conv3x3_tc_fwd only) --  */
+  int ld_pre, pre_coff;   /* the x0-slab partial pre-activation of a DRDB layer, see segmif_drdb_push_tc_fwd        */
 } segmif_conv_params;
 int segmif_conv_fwd(const segmif_conv_params* p, segmif_stream_t stream);
 

@@ -29,6 +29,7 @@ class ConvParams(ctypes.Structure):
         ("act", c_int),
         ("res_dtype", c_int), ("ld_res", c_int), ("res_coff", c_int),
         ("dst_dtype", c_int), ("ld_dst", c_int), ("dst_coff", c_int),
+        ("pre_add", c_void_p), ("ld_pre", c_int), ("pre_coff", c_int),
     ]
 
 

@@ -162,7 +162,9 @@ Network = Network3     # core/__init__.py:4 of the reference imports a `Network`
 class DRDB(nn.Module):
     """Dilated residual dense block (core/model_fusion.py:117-157)."""
     GROWTH_LD = 224
-    USE_PUSH = os.environ.get("SEGMIF_DRDB_PULL", "0") != "1"
+    # growth-layer formulation: "hybrid" (x0 slab pushed with N = 96/64, g-slabs pulled with N = 32 + partial add;
+    # fastest), "push" (every slab pushed, bf16 partials read-modify-written), "pull" (one N = 32 conv per layer)
+    MODE = os.environ.get("SEGMIF_DRDB_MODE", "hybrid")
 
     def __init__(self, in_ch=64, growth_rate=32):
         super().__init__()
@@ -208,14 +210,40 @@ class DRDB(nn.Module):
         ops.drdb_push(buf, w[4], B, H, W, c + 2 * g, g, [G(c + 3 * g, b[3], 2 * g), Pn(3 * g, False)])
         ops.drdb_push(buf, w[5], B, H, W, c + 3 * g, g, [G(c + 4 * g, b[4], 3 * g)])
 
+    def _hybrid_packs(self):
+        """Layer j >= 2 restricted to the g-slabs (input channels in_ch..Cin_j): bf16 [32][9][Cin_j - in_ch]."""
+        convs = [getattr(self, f"Dcov{i}") for i in range(2, 6)]
+
+        def build(*ws):
+            c = self.in_ch
+            return [w.detach().float()[:, c:].permute(0, 2, 3, 1).reshape(w.shape[0], 9, w.shape[1] - c)
+                    .to(torch.bfloat16).contiguous() for w in ws]
+        return self._packs.get_multi([cv.weight for cv in convs], build, "hybrid")
+
+    def _growth_hybrid(self, buf, part, B, H, W):
+        """x0 slab in push form (two launches, N = 96 and 64: layer 1 finished, P2..P5 = x0's share of layers 2..5),
+        then layers 2..5 as N = 32 pull convolutions over the g-slabs only, with P_j added before the ReLU."""
+        w = self._push_packs()
+        wh = self._hybrid_packs()
+        b = [getattr(self, f"Dcov{i}").bias.detach() for i in range(1, 6)]
+        c, g, ld = self.in_ch, self.growth, buf.shape[-1]
+        Pn = lambda off: dict(bias=None, partial_in=None, dst=part, coff_dst=off, relu=False)
+        ops.drdb_push(buf, w[0], B, H, W, 0, c, [dict(bias=b[0], partial_in=None, dst=buf, coff_dst=c, relu=True), Pn(0), Pn(g)])
+        ops.drdb_push(buf, w[1], B, H, W, 0, c, [Pn(2 * g), Pn(3 * g)])
+        for j in range(2, 6):
+            cin = g * (j - 1)
+            ops.conv(buf, wh[j - 2], b[j - 1], B=B, H=H, W=W, Cin=cin, ld_src=ld, src_coff=c, KH=3, KW=3, pad=2, dil=2,
+                     Cout=g, act=ACT_RELU, out=buf.view(-1, ld), ld_dst=ld, dst_coff=c + cin, pre_add=part.view(-1, part.shape[-1]),
+                     pre_coff=g * (j - 2), entry="segmif_conv3x3_tc_fwd")
+
     def forward_buffer(self, buf, B, H, W, out=None, ld_dst=None, dst_coff=0, partials=None):
         """`buf` bf16 [B, H, W, total] with the block input in channels 0..in_ch; appends the five growth slices
         in place, then writes x + relu(conv1x1(all)) to `out` (pixel-major bf16).  `partials` (bf16 [B,H,W,128]
         scratch) selects the push form of the growth layers; without it the per-layer (pull) kernels run."""
         ld = buf.shape[-1]
         cin = self.in_ch
-        if partials is not None and DRDB.USE_PUSH and self.in_ch == 64 and self.growth == 32:
-            self._growth_push(buf, partials, B, H, W)
+        if partials is not None and DRDB.MODE != "pull" and self.in_ch == 64 and self.growth == 32:
+            (self._growth_push if DRDB.MODE == "push" else self._growth_hybrid)(buf, partials, B, H, W)
             cin = self.total
         for i in range(1, 6) if cin == self.in_ch else ():
             cv = getattr(self, f"Dcov{i}")

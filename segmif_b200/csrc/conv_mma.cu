@@ -248,6 +248,7 @@ extern "C" int segmif_conv_fwd(const segmif_conv_params* p, segmif_stream_t stre
   SEGMIF_REQUIRE(p->src_coff + p->Cin <= p->ld_src, "conv: src channels exceed pitch");
   SEGMIF_REQUIRE(p->dst_coff + p->Cout <= p->ld_dst, "conv: dst channels exceed pitch");
   SEGMIF_REQUIRE(p->act != SEGMIF_ACT_PRELU || p->prelu_alpha, "conv: PReLU needs prelu_alpha");
+  SEGMIF_REQUIRE(p->pre_add == nullptr, "conv: pre_add is only supported by segmif_conv3x3_tc_fwd");
   SEGMIF_REQUIRE((reinterpret_cast<uintptr_t>(p->src) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->weight) & 15) == 0,
                  "conv: src/weight must be 16-byte aligned");
   const int64_t M = (int64_t)p->B * p->Ho * p->Wo;

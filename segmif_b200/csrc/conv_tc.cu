@@ -22,8 +22,9 @@ struct ConvTcArgs {
   const float* bias;
   const float* alpha;
   bf16* dst;
-  int B, H, W, nchunks, act, ld_dst, dst_coff;
-  int tiles_x, tiles_y, cin;
+  const bf16* pre;     // optional bf16 partial pre-activation added before the activation
+  int B, H, W, nchunks, act, ld_dst, dst_coff, ld_pre, pre_coff;
+  int tiles_x, tiles_y, cin, ksteps_last;
 };
 
 constexpr int kConvTcThreads = 192;
@@ -119,6 +120,7 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv3x3_tc_kernel(const __g
           const uint32_t a_lo0 = smem_u32(sA + s * Cfg::A_BYTES) >> 4;
           const uint32_t w_lo = w_lo0 + (uint32_t)(c * 9 * (Cfg::W_TILE_BYTES >> 4));
           const uint32_t first = c != 0 ? 1u : 0u;
+          const int klim = (c == a.nchunks - 1) ? a.ksteps_last : 4;
 #pragma unroll
           for (int t = 0; t < 9; ++t) {
             const int ky = t / 3, kx = t % 3;
@@ -126,6 +128,7 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv3x3_tc_kernel(const __g
             for (int sub = 0; sub < NSUB; ++sub) {
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
+                if (k >= klim) continue;                 // trailing channels of a partly filled last slab are zeros: skip
                 const uint32_t a_off = (uint32_t)(((ky * DIL * Cfg::HXP + kx * DIL + sub * 8) * 128 + k * 32) >> 4);
                 const uint32_t w_off = (uint32_t)((t * Cfg::W_TILE_BYTES + k * 32) >> 4);
                 tc::umma_bf16_lohi(acc + (uint32_t)(sub * COUT), a_lo0 + a_off, A_HI, w_lo + w_off, B_HI, idesc,
@@ -152,15 +155,38 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv3x3_tc_kernel(const __g
       const int b = tile / tiles_per_img, rem = tile - b * tiles_per_img;
       const int y = (rem / a.tiles_x) * Cfg::TH + ty;
       const int x0 = (rem % a.tiles_x) * Cfg::TW + tx;
+      // the partial pre-activation does not depend on this tile's MMAs: fetch it while they run
+      uint4 pre[NSUB * (COUT / 32)][4];
+      if (a.pre) {
+#pragma unroll
+        for (int sc = 0; sc < NSUB * (COUT / 32); ++sc) {
+          const int sub = sc / (COUT / 32), c = (sc % (COUT / 32)) * 32;
+          const int x = x0 + sub * 8;
+          if (y < a.H && x < a.W) {
+            const uint4* pp = reinterpret_cast<const uint4*>(a.pre + (((int64_t)b * a.H + y) * a.W + x) * a.ld_pre + a.pre_coff + c);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pre[sc][j] = __ldg(pp + j);
+          }
+        }
+      }
       tc::mbar_wait(tmem_full + buf, (lt >> 1) & 1);
       tc::tc_fence_after();
-#pragma unroll 1
+#pragma unroll
       for (int sc = 0; sc < NSUB * (COUT / 32); ++sc) {
         const int sub = sc / (COUT / 32), c = (sc % (COUT / 32)) * 32;
         const int x = x0 + sub * 8;
         float v[32];
         tc::tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * Cfg::ACC_COLS + sub * COUT + c), v);
         if (y < a.H && x < a.W) {
+          if (a.pre) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 t = pre[sc][j];
+              const float2 p0 = unpack_bf16x2(t.x), p1 = unpack_bf16x2(t.y), p2 = unpack_bf16x2(t.z), p3 = unpack_bf16x2(t.w);
+              v[8 * j] += p0.x; v[8 * j + 1] += p0.y; v[8 * j + 2] += p1.x; v[8 * j + 3] += p1.y;
+              v[8 * j + 4] += p2.x; v[8 * j + 5] += p2.y; v[8 * j + 6] += p3.x; v[8 * j + 7] += p3.y;
+            }
+          }
           const float4* bp = reinterpret_cast<const float4*>(a.bias + c);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -222,6 +248,8 @@ static int launch_conv_tc(const segmif_conv_params* p, cudaStream_t st) {
   a.B = p->B; a.H = p->H; a.W = p->W; a.nchunks = nchunks; a.act = p->act; a.ld_dst = p->ld_dst; a.dst_coff = p->dst_coff;
   a.tiles_x = (p->W + Cfg::TW - 1) / Cfg::TW; a.tiles_y = (p->H + Cfg::TH - 1) / Cfg::TH;
   a.cin = p->Cin;
+  a.pre = reinterpret_cast<const bf16*>(p->pre_add); a.ld_pre = p->ld_pre; a.pre_coff = p->pre_coff;
+  a.ksteps_last = ((p->Cin - 1) % 64) / 16 + 1;
   const int num_tiles = a.tiles_x * a.tiles_y * a.B;
   kern<<<std::min(num_tiles, sms), kConvTcThreads, smem, st>>>(tmA, tmW, a);
   return check_launch("segmif_conv3x3_tc_fwd");
@@ -239,6 +267,8 @@ extern "C" int segmif_conv3x3_tc_fwd(const segmif_conv_params* p, segmif_stream_
   SEGMIF_REQUIRE(p->Cin % 8 == 0 && p->Cin > 0 && p->ld_src % 8 == 0 && p->src_coff % 8 == 0, "conv3x3_tc: Cin/pitch/offset must be multiples of 8");
   SEGMIF_REQUIRE(p->dst_dtype == SEGMIF_BF16 && p->ld_dst % 8 == 0 && p->dst_coff % 8 == 0, "conv3x3_tc: dst must be bf16 with 16-byte aligned slices");
   SEGMIF_REQUIRE(p->residual == nullptr, "conv3x3_tc: residual is not supported");
+  SEGMIF_REQUIRE(p->pre_add == nullptr || (((uintptr_t)p->pre_add & 15) == 0 && p->ld_pre % 8 == 0 && p->pre_coff % 8 == 0), "conv3x3_tc: pre_add must be 16-byte aligned");
+  SEGMIF_REQUIRE(p->Cin % 16 == 0, "conv3x3_tc: Cin must be a multiple of 16");
   SEGMIF_REQUIRE(p->act != SEGMIF_ACT_GELU, "conv3x3_tc: GELU is not supported");
   SEGMIF_REQUIRE(p->act != SEGMIF_ACT_PRELU || p->prelu_alpha, "conv3x3_tc: PReLU needs prelu_alpha");
   SEGMIF_REQUIRE(p->src_coff + p->Cin <= p->ld_src && p->dst_coff + p->Cout <= p->ld_dst, "conv3x3_tc: channel slice exceeds pitch");

@@ -53,13 +53,13 @@ def layernorm(x, gamma, beta, eps, out_dtype=torch.bfloat16, out=None):
 
 def conv(src, weight, bias, *, B, H, W, Cin, KH=1, KW=1, stride=1, pad=0, dil=1, Cout, ld_src=None, src_coff=0,
          act=ACT_NONE, prelu_alpha=None, residual=None, ld_res=None, res_coff=0, out=None, out_dtype=torch.bfloat16,
-         ld_dst=None, dst_coff=0, entry=None):
+         ld_dst=None, dst_coff=0, entry=None, pre_add=None, pre_coff=0):
     """Dense contraction on the tensor cores.  `src` is pixel-major bf16 with channel pitch ld_src; `weight` is the
     packed bf16 [Cout, KH*KW, Cin] tensor.  Returns `out` ([B*Ho*Wo, ld_dst]).  Kernel selection (entry=None):
     1x1 -> segmif_linear_tc_fwd and 3x3 stride-1 'same' -> segmif_conv3x3_tc_fwd (tcgen05 + TMA) whenever the shape
     qualifies; strided / odd-width cases (patch_embed2-4, Attention.sr, linear_pred's 9 classes) ->
     segmif_conv_fwd (mma.sync implicit GEMM)."""
-    st = _prep(src, weight, bias, prelu_alpha, residual, out)
+    st = _prep(src, weight, bias, prelu_alpha, residual, out, pre_add)
     if src.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16:
         raise TypeError("segmif_b200.conv: src and weight must be bf16")
     Ho = (H + 2 * pad - dil * (KH - 1) - 1) // stride + 1
@@ -84,6 +84,8 @@ def conv(src, weight, bias, *, B, H, W, Cin, KH=1, KW=1, stride=1, pad=0, dil=1,
     p.res_dtype = _dt(residual) if residual is not None else F32
     p.ld_res, p.res_coff = (ld_res or 0), res_coff
     p.dst_dtype, p.ld_dst, p.dst_coff = _dt(out), ld_dst, dst_coff
+    if pre_add is not None:
+        p.pre_add, p.ld_pre, p.pre_coff = pre_add.data_ptr(), pre_add.shape[-1], pre_coff
     if entry is None:
         entry = "segmif_conv_fwd"
         if USE_TCGEN05:
@@ -91,7 +93,7 @@ def conv(src, weight, bias, *, B, H, W, Cin, KH=1, KW=1, stride=1, pad=0, dil=1,
             ral = 4 if (residual is not None and residual.dtype == torch.float32) else 8
             aligned = (ld_src % 8 == 0 and src_coff % 8 == 0 and ld_dst % dal == 0 and dst_coff % dal == 0
                        and (residual is None or ((ld_res or 0) % ral == 0 and res_coff % ral == 0)))
-            if KH == 1 and KW == 1 and stride == 1 and pad == 0 and Cout % 32 == 0 and Cin % 8 == 0 and aligned:
+            if KH == 1 and KW == 1 and stride == 1 and pad == 0 and Cout % 32 == 0 and Cin % 8 == 0 and aligned and pre_add is None:
                 lp = _linear_params(src, weight, bias, M, Cout, Cin, ld_src, src_coff, act, prelu_alpha, residual, ld_res,
                                     res_coff, out, ld_dst, dst_coff)
                 _lib.call("segmif_linear_tc_fwd", ctypes.byref(lp), st)

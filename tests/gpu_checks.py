@@ -451,8 +451,7 @@ def models(backbone="mit_b1"):
 
 @check
 def drdb_module():
-    """DRDB against the oracle in both formulations of the growth layers: push (default; every new slab is multiplied
-    into all later layers, N up to 128, bf16 partial pre-activations) and pull (one N=32 conv per layer)."""
+    """DRDB against the oracle in the three formulations of the growth layers (hybrid = default)."""
     from segmif_b200.core.model_fusion import DRDB
     seg, fus, (seg_sd, fus_sd) = models()
     rs = []
@@ -460,17 +459,17 @@ def drdb_module():
         x = rnd(*shape, seed=shape[2])
         with torch.no_grad():
             ref = O.drdb(x, fus_sd, "DRDB1")
-            keep = DRDB.USE_PUSH
+            keep = DRDB.MODE
             try:
-                DRDB.USE_PUSH = True
-                push = fus.DRDB1(x.to(DEV))
-                DRDB.USE_PUSH = False
-                pull = fus.DRDB1(x.to(DEV))
+                got = {}
+                for mode in ("hybrid", "push", "pull"):
+                    DRDB.MODE = mode
+                    got[mode] = fus.DRDB1(x.to(DEV))
             finally:
-                DRDB.USE_PUSH = keep
-        # 6 chained bf16 tensor-core layers with bf16 storage (and, for push, bf16 partial sums) between them
-        rs.append(result(f"DRDB_push_vs_oracle_{shape[2]}x{shape[3]}", rel_err(push, ref), 2e-2))
-        rs.append(result(f"DRDB_pull_vs_oracle_{shape[2]}x{shape[3]}", rel_err(pull, ref), 2e-2))
+                DRDB.MODE = keep
+        # 6 chained bf16 tensor-core layers with bf16 storage (and, for push / hybrid, bf16 partial sums) between them
+        for mode in ("hybrid", "push", "pull"):
+            rs.append(result(f"DRDB_{mode}_vs_oracle_{shape[2]}x{shape[3]}", rel_err(got[mode], ref), 2e-2))
     return rs
 
 

@@ -24,7 +24,7 @@ struct ConvTcArgs {
   bf16* dst;
   const bf16* pre;     // optional bf16 partial pre-activation added before the activation
   int B, H, W, nchunks, act, ld_dst, dst_coff, ld_pre, pre_coff;
-  int tiles_x, tiles_y, cin, ksteps_last;
+  int tiles_x, tiles_y, cin, ksteps_last, nstages;
 };
 
 constexpr int kConvTcThreads = 192;
@@ -33,8 +33,9 @@ template <int COUT, int DIL, int NSUB>
 struct ConvTcCfg {
   static constexpr int TH = 16, TW = 8 * NSUB;
   static constexpr int HROWS = TH + 2 * DIL;
-  static constexpr int HXP = ((TW + 2 * DIL + 7) / 8) * 8;            // halo columns padded to a multiple of 8 lines
-  static constexpr int A_BYTES = HROWS * HXP * 128;
+  static constexpr int HXP = TW + 2 * DIL;     // halo columns; any pitch works: the swizzle follows absolute smem address bits
+  static constexpr int A_BYTES = HROWS * HXP * 128;                    // bytes one TMA box delivers
+  static constexpr int A_STRIDE = (A_BYTES + 1023) & ~1023;            // ring slots start on 1024-byte boundaries
   static constexpr int W_TILE_BYTES = COUT * 128;                      // one (slab, tap) weight tile
   static constexpr int ACC_COLS = NSUB * COUT;                         // TMEM columns per accumulator buffer
   static constexpr uint32_t TMEM_COLS = (2 * ACC_COLS) <= 32 ? 32 : (2 * ACC_COLS) <= 64 ? 64 : (2 * ACC_COLS) <= 128 ? 128 : 256;
@@ -49,9 +50,10 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv3x3_tc_kernel(const __g
   const int w_bytes = a.nchunks * 9 * Cfg::W_TILE_BYTES;
   uint8_t* sW = smem;
   uint8_t* sA = smem + w_bytes;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sA + 2 * Cfg::A_BYTES);
-  uint64_t* empty = full + 2;
-  uint64_t* wfull = empty + 2;
+  const int NS = a.nstages;                      // halo-tile ring depth (2..4), chosen by the host to fill shared memory
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + w_bytes + NS * Cfg::A_STRIDE);
+  uint64_t* empty = full + 4;
+  uint64_t* wfull = empty + 4;
   uint64_t* tmem_full = wfull + 1;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
@@ -63,9 +65,11 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv3x3_tc_kernel(const __g
   if (threadIdx.x == 0) {
     tc::prefetch_tmap(&tmA);
     tc::prefetch_tmap(&tmW);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < 4; ++s) {
       tc::mbar_init(full + s, 1);
       tc::mbar_init(empty + s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
       tc::mbar_init(tmem_full + s, 1);
       tc::mbar_init(tmem_empty + s, 4);        // one arrive per epilogue warp
     }
@@ -90,11 +94,11 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv3x3_tc_kernel(const __g
         const int b = tile / tiles_per_img, rem = tile - b * tiles_per_img;
         const int y0 = (rem / a.tiles_x) * Cfg::TH, x0 = (rem % a.tiles_x) * Cfg::TW;
         for (int c = 0; c < a.nchunks; ++c, ++it) {
-          const int s = it & 1;
-          const uint32_t ph = (it >> 1) & 1;
+          const int s = it % NS;
+          const uint32_t ph = (it / NS) & 1;
           tc::mbar_wait(empty + s, ph ^ 1);
           tc::mbar_expect_tx(full + s, Cfg::A_BYTES);
-          tc::tma_load_4d(sA + s * Cfg::A_BYTES, &tmA, full + s, c * 64, x0 - DIL, y0 - DIL, b);
+          tc::tma_load_4d(sA + s * Cfg::A_STRIDE, &tmA, full + s, c * 64, x0 - DIL, y0 - DIL, b);
         }
       }
     }
@@ -113,11 +117,11 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv3x3_tc_kernel(const __g
       tc::tc_fence_after();
       const uint32_t acc = tmem_base + (uint32_t)(buf * Cfg::ACC_COLS);
       for (int c = 0; c < a.nchunks; ++c, ++it) {
-        const int s = it & 1;
-        tc::mbar_wait(full + s, (it >> 1) & 1);
+        const int s = it % NS;
+        tc::mbar_wait(full + s, (it / NS) & 1);
         tc::tc_fence_after();
         if (leader) {
-          const uint32_t a_lo0 = smem_u32(sA + s * Cfg::A_BYTES) >> 4;
+          const uint32_t a_lo0 = smem_u32(sA + s * Cfg::A_STRIDE) >> 4;
           const uint32_t w_lo = w_lo0 + (uint32_t)(c * 9 * (Cfg::W_TILE_BYTES >> 4));
           const uint32_t first = c != 0 ? 1u : 0u;
           const int klim = (c == a.nchunks - 1) ? a.ksteps_last : 4;
@@ -216,7 +220,9 @@ template <int COUT, int DIL, int NSUB>
 static int launch_conv_tc(const segmif_conv_params* p, cudaStream_t st) {
   using Cfg = ConvTcCfg<COUT, DIL, NSUB>;
   const int nchunks = (p->Cin + 63) / 64;
-  const size_t smem = (size_t)nchunks * 9 * Cfg::W_TILE_BYTES + 2 * (size_t)Cfg::A_BYTES + 9 * 8 + 16;
+  const size_t wb = (size_t)nchunks * 9 * Cfg::W_TILE_BYTES, limit = 227 * 1024 - 2048;
+  const int nstages = (int)std::max<size_t>(2, std::min<size_t>(4, (limit - wb) / Cfg::A_STRIDE));
+  const size_t smem = wb + (size_t)nstages * Cfg::A_STRIDE + 13 * 8 + 16;
   auto kern = conv3x3_tc_kernel<COUT, DIL, NSUB>;
   static bool configured = false;          // opt in once to the full 227 KB (the size varies with Cin; never during graph capture)
   static int sms = 148;
@@ -250,6 +256,7 @@ static int launch_conv_tc(const segmif_conv_params* p, cudaStream_t st) {
   a.cin = p->Cin;
   a.pre = reinterpret_cast<const bf16*>(p->pre_add); a.ld_pre = p->ld_pre; a.pre_coff = p->pre_coff;
   a.ksteps_last = ((p->Cin - 1) % 64) / 16 + 1;
+  a.nstages = nstages;
   const int num_tiles = a.tiles_x * a.tiles_y * a.B;
   kern<<<std::min(num_tiles, sms), kConvTcThreads, smem, st>>>(tmA, tmW, a);
   return check_launch("segmif_conv3x3_tc_fwd");
@@ -275,11 +282,11 @@ extern "C" int segmif_conv3x3_tc_fwd(const segmif_conv_params* p, segmif_stream_
   SEGMIF_REQUIRE(((uintptr_t)p->src & 15) == 0 && ((uintptr_t)p->weight & 15) == 0 && ((uintptr_t)p->dst & 15) == 0, "conv3x3_tc: pointers must be 16-byte aligned");
   cudaStream_t st = as_stream(stream);
   const size_t nchunks = (size_t)(p->Cin + 63) / 64;
-  const size_t limit = 227 * 1024 - 256;
+  const size_t limit = 227 * 1024 - 2048;
   const size_t wbytes = nchunks * 9 * (size_t)p->Cout * 128;
-  constexpr size_t a_32_2_2 = 2 * (size_t)ConvTcCfg<32, 2, 2>::A_BYTES, a_32_2_1 = 2 * (size_t)ConvTcCfg<32, 2, 1>::A_BYTES;
-  constexpr size_t a_32_1_2 = 2 * (size_t)ConvTcCfg<32, 1, 2>::A_BYTES, a_32_1_1 = 2 * (size_t)ConvTcCfg<32, 1, 1>::A_BYTES;
-  constexpr size_t a_64_1_1 = 2 * (size_t)ConvTcCfg<64, 1, 1>::A_BYTES, a_64_2_1 = 2 * (size_t)ConvTcCfg<64, 2, 1>::A_BYTES;
+  constexpr size_t a_32_2_2 = 2 * (size_t)ConvTcCfg<32, 2, 2>::A_STRIDE, a_32_2_1 = 2 * (size_t)ConvTcCfg<32, 2, 1>::A_STRIDE;
+  constexpr size_t a_32_1_2 = 2 * (size_t)ConvTcCfg<32, 1, 2>::A_STRIDE, a_32_1_1 = 2 * (size_t)ConvTcCfg<32, 1, 1>::A_STRIDE;
+  constexpr size_t a_64_1_1 = 2 * (size_t)ConvTcCfg<64, 1, 1>::A_STRIDE, a_64_2_1 = 2 * (size_t)ConvTcCfg<64, 2, 1>::A_STRIDE;
   if (p->Cout == 32 && p->dil == 2) {
     if (wbytes + a_32_2_2 <= limit) return launch_conv_tc<32, 2, 2>(p, st);
     SEGMIF_REQUIRE(wbytes + a_32_2_1 <= limit, "conv3x3_tc: Cin=%d too large for resident weights", p->Cin);

@@ -37,14 +37,16 @@ template <int NOUT, int NSUB, int KSLAB>
 struct PushCfg {
   static constexpr int TH = 16, TW = 8 * NSUB, DIL = 2;
   static constexpr int HROWS = TH + 2 * DIL;
-  static constexpr int HXP = ((TW + 2 * DIL + 7) / 8) * 8;
+  static constexpr int HXP = TW + 2 * DIL;                             // exact: swizzle follows absolute address bits
   static constexpr int A_BYTES = HROWS * HXP * 128;
+  static constexpr int A_STRIDE = (A_BYTES + 1023) & ~1023;
   static constexpr int NWT = KSLAB == 64 ? 9 : 5;                    // weight tiles: one per tap, or one per tap pair
   static constexpr int W_TILE_BYTES = NOUT * 128;
   static constexpr int W_BYTES = NWT * W_TILE_BYTES;
   static constexpr int ACC_COLS = NSUB * NOUT;
   static constexpr uint32_t TMEM_COLS = (2 * ACC_COLS) <= 64 ? 64 : (2 * ACC_COLS) <= 128 ? 128 : (2 * ACC_COLS) <= 256 ? 256 : 512;
-  static constexpr size_t SMEM = (size_t)W_BYTES + 2 * (size_t)A_BYTES + 9 * 8 + 16;
+  static constexpr int NSTAGES = ((227 * 1024 - 2048 - W_BYTES) / A_STRIDE) >= 4 ? 4 : ((227 * 1024 - 2048 - W_BYTES) / A_STRIDE) >= 3 ? 3 : 2;
+  static constexpr size_t SMEM = (size_t)W_BYTES + (size_t)NSTAGES * A_STRIDE + 13 * 8 + 16;
 };
 
 template <int NOUT, int NSUB, int KSLAB>
@@ -55,9 +57,10 @@ __global__ void __launch_bounds__(kPushThreads, 1) drdb_push_tc_kernel(const __g
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sW = smem;
   uint8_t* sA = smem + Cfg::W_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sA + 2 * Cfg::A_BYTES);
-  uint64_t* empty = full + 2;
-  uint64_t* wfull = empty + 2;
+  constexpr int NS = Cfg::NSTAGES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::W_BYTES + NS * Cfg::A_STRIDE);
+  uint64_t* empty = full + 4;
+  uint64_t* wfull = empty + 4;
   uint64_t* tmem_full = wfull + 1;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
@@ -69,9 +72,11 @@ __global__ void __launch_bounds__(kPushThreads, 1) drdb_push_tc_kernel(const __g
   if (threadIdx.x == 0) {
     tc::prefetch_tmap(&tmA);
     tc::prefetch_tmap(&tmW);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < 4; ++s) {
       tc::mbar_init(full + s, 1);
       tc::mbar_init(empty + s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
       tc::mbar_init(tmem_full + s, 1);
       tc::mbar_init(tmem_empty + s, 4);
     }
@@ -92,10 +97,10 @@ __global__ void __launch_bounds__(kPushThreads, 1) drdb_push_tc_kernel(const __g
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
         const int b = tile / tiles_per_img, rem = tile - b * tiles_per_img;
         const int y0 = (rem / a.tiles_x) * Cfg::TH, x0 = (rem % a.tiles_x) * Cfg::TW;
-        const int s = lt & 1;
-        tc::mbar_wait(empty + s, ((lt >> 1) & 1) ^ 1);
+        const int s = lt % NS;
+        tc::mbar_wait(empty + s, ((lt / NS) & 1) ^ 1);
         tc::mbar_expect_tx(full + s, Cfg::A_BYTES);
-        tc::tma_load_4d(sA + s * Cfg::A_BYTES, &tmA, full + s, 0, x0 - Cfg::DIL, y0 - Cfg::DIL, b);
+        tc::tma_load_4d(sA + s * Cfg::A_STRIDE, &tmA, full + s, 0, x0 - Cfg::DIL, y0 - Cfg::DIL, b);
       }
     }
     __syncwarp();
@@ -107,13 +112,13 @@ __global__ void __launch_bounds__(kPushThreads, 1) drdb_push_tc_kernel(const __g
     const uint32_t w_lo = smem_u32(sW) >> 4;
     int lt = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
-      const int s = lt & 1;                    // smem stage and TMEM buffer advance together (one slab per tile)
-      tc::mbar_wait(tmem_empty + s, ((lt >> 1) & 1) ^ 1);
-      tc::mbar_wait(full + s, (lt >> 1) & 1);
+      const int s = lt % NS, buf = lt & 1;     // halo-tile ring slot and TMEM accumulator buffer of this tile
+      tc::mbar_wait(tmem_empty + buf, ((lt >> 1) & 1) ^ 1);
+      tc::mbar_wait(full + s, (lt / NS) & 1);
       tc::tc_fence_after();
       if (leader) {
-        const uint32_t acc = tmem_base + (uint32_t)(s * Cfg::ACC_COLS);
-        const uint32_t a_lo0 = smem_u32(sA + s * Cfg::A_BYTES) >> 4;
+        const uint32_t acc = tmem_base + (uint32_t)(buf * Cfg::ACC_COLS);
+        const uint32_t a_lo0 = smem_u32(sA + s * Cfg::A_STRIDE) >> 4;
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
           const int ky = t / 3, kx = t % 3;
@@ -129,7 +134,7 @@ __global__ void __launch_bounds__(kPushThreads, 1) drdb_push_tc_kernel(const __g
           }
         }
         tc::umma_commit(empty + s);
-        tc::umma_commit(tmem_full + s);
+        tc::umma_commit(tmem_full + buf);
       }
       __syncwarp();
     }

@@ -112,8 +112,8 @@ USE_TCGEN05 = os.environ.get("SEGMIF_TCGEN05", "1") != "0"
 def _conv3x3_tc_fits(Cin, Cout, dil):
     """Resident weights + two halo-tile stages must fit the 227 KB of shared memory (mirrors conv_tc.cu)."""
     wbytes = ((Cin + 63) // 64) * 9 * Cout * 128
-    a_bytes = (16 + 2 * dil) * (((8 + 2 * dil + 7) // 8) * 8) * 128          # NSUB = 1 tile
-    return wbytes + 2 * a_bytes <= 227 * 1024 - 256
+    a_bytes = ((16 + 2 * dil) * (8 + 2 * dil) * 128 + 1023) // 1024 * 1024     # NSUB = 1 halo tile, 1024-aligned slot
+    return wbytes + 2 * a_bytes <= 227 * 1024 - 2048
 
 
 def conv3x3_tc(src, weight, bias, **kw):

@@ -196,6 +196,19 @@ int segmif_ffm_apply_fwd(const void* x1, int ld1, int coff1, const void* x2, int
                          const float* ln_beta /* [2][64] */, float eps, void* out1, int ldo1, int coffo1, void* out2,
                          int ldo2, int coffo2, int B, int64_t HW, segmif_stream_t stream);
 
+/* K13 with the segmentation stream kept at the encoder's resolution: relu(channel_proj3(conv3|4(upsample(f)))) equals
+ * relu(upsample(Q)), Q = (channel_proj3 o conv3|4)(f) + bias computed once at low resolution (all three maps are linear
+ * and bilinear weights sum to one).  q3: bf16 [B, qh, qw, 128] ([0,64) = y3 half, [64,128) = u3 half); the kernels
+ * interpolate it per pixel (align_corners=False) instead of reading an upsampled feature map.  wproj / bproj hold only
+ * the two remaining projections: gram [w1y][w2y] / [b1y][b2y], apply [w1u][w2u] / [b1u][b2u].                          */
+int segmif_ffm_gram_lr_fwd(const void* x1, int ld1, int coff1, const void* x2, int ld2, int coff2, const void* q3,
+                           int qh, int qw, int H, int W, const void* wproj, const float* bproj, float* partials,
+                           int nchunk, int B, segmif_stream_t stream);
+int segmif_ffm_apply_lr_fwd(const void* x1, int ld1, int coff1, const void* x2, int ld2, int coff2, const void* q3,
+                            int qh, int qw, int H, int W, const void* wproj, const float* bproj, const void* folded,
+                            const float* bend, const float* ln_gamma, const float* ln_beta, float eps, void* out1,
+                            int ldo1, int coffo1, void* out2, int ldo2, int coffo2, int B, segmif_stream_t stream);
+
 /* ---- K14: colour transforms (NCHW fp32) ------------------------------------------------------------------
  * replaces core/model_fusion.py:69-92 (RGB2YCrCb), :94-111 (YCrCb2RGB) and the recompose chain
  * train.py:364-366 / test_fusion.py:102-111 (replace Y by the fused image, back to RGB, clamp to [0,1]). */

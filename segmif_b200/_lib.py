@@ -80,6 +80,9 @@ SIGNATURES = {
     "segmif_ffm_ctx_fwd": [P, c_int, P, P, P, P, c_int, P],
     "segmif_ffm_apply_fwd": [P, c_int, c_int, P, c_int, c_int, P, c_int, c_int, P, P, P, P, P, P, c_float,
                              P, c_int, c_int, P, c_int, c_int, c_int, c_int64, P],
+    "segmif_ffm_gram_lr_fwd": [P, c_int, c_int, P, c_int, c_int, P, c_int, c_int, c_int, c_int, P, P, P, c_int, c_int, P],
+    "segmif_ffm_apply_lr_fwd": [P, c_int, c_int, P, c_int, c_int, P, c_int, c_int, c_int, c_int, P, P, P, P, P, P, c_float,
+                                P, c_int, c_int, P, c_int, c_int, c_int, P],
     "segmif_rgb2ycrcb": [P, P, c_int, c_int64, P],
     "segmif_ycrcb2rgb": [P, P, c_int, c_int64, P],
     "segmif_recompose_rgb": [P, P, P, c_int, c_int, c_int64, P],

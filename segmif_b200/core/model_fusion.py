@@ -341,6 +341,23 @@ class CrossPath(nn.Module):
                 ln_g=fl(f(g1), f(g2)), ln_b=fl(f(n1), f(n2)))
         return self._packs.get_multi(plist, build, "ffm" if pre_conv is None else f"ffm+{id(pre_conv)}")
 
+    def packs_lr(self, pre_conv):
+        """Operand packs for the low-resolution seg path: Q = (channel_proj3 o pre_conv)(f) is evaluated at the encoder's
+        resolution with q_w / q_b; the FFM kernels keep only the projections of the two image streams."""
+        pk = self.packs(pre_conv)
+
+        def build(wg, bg, wa, ba):
+            c3 = pk["C3"]
+            w3u, w3y = wg[2 * 4096:].reshape(64, c3), wa[:64 * c3].reshape(64, c3)
+            return dict(q_w=torch.cat([w3y, w3u], 0).reshape(128, 1, c3).contiguous(),
+                        q_b=torch.cat([ba[:64], bg[128:]]).contiguous(),
+                        w_gram=wg[:2 * 4096].contiguous(), b_gram=bg[:128].contiguous(),
+                        w_apply=wa[64 * c3:].contiguous(), b_apply=ba[64:].contiguous())
+        lr = self._packs.get_multi([pk["w_gram"], pk["b_gram"], pk["w_apply"], pk["b_apply"]], build, f"lr+{id(pre_conv)}")
+        out = dict(pk)
+        out.update(lr)
+        return out
+
     def forward(self, x1, x2, segfeature):
         """Token interface of the reference: three [B, N, 64] tensors -> two [B, N, 64] tensors (fp32)."""
         _no_autograd(self, x1, x2, segfeature)
@@ -366,6 +383,14 @@ class FeatureFusionModule(nn.Module):
                             pre_conv=None):
         pk = self.cross.packs(pre_conv)
         return ops.ffm(x1, ld1, 0, x2, ld2, 0, seg, ld3, pk["C3"], pk, out1, ldo1, coffo1, out2, ldo2, coffo2, B, HW)
+
+    def forward_pixel_major_lr(self, x1, ld1, x2, ld2, seg_tokens, qh, qw, out1, ldo1, coffo1, out2, ldo2, coffo2, B,
+                               H, W, pre_conv):
+        """Same as forward_pixel_major with the segmentation features given at the encoder's resolution
+        (bf16 tokens [B, qh*qw, Cin]); `pre_conv` is conv3 / conv4."""
+        pk = self.cross.packs_lr(pre_conv)
+        q = ops.linear(seg_tokens, pk["q_w"], pk["q_b"])                      # [B*qh*qw, 128] bf16, L2 resident
+        return ops.ffm_lr(x1, ld1, 0, x2, ld2, 0, q, qh, qw, H, W, pk, out1, ldo1, coffo1, out2, ldo2, coffo2, B)
 
     def forward(self, x1, x2, segfeature):
         _no_autograd(self, x1, x2, segfeature)
@@ -402,12 +427,30 @@ class Fusion_Network3_ac(nn.Module):
 
     def forward(self, ir, vis, out1, out2):
         _no_autograd(self, ir, vis, out1, out2)
+        return self._run(ir, vis, ("full", _pixel_major_bf16(out1)), ("full", _pixel_major_bf16(out2)))
+
+    def forward_lowres(self, ir, vis, stage1, stage2):
+        """Extension: same result as forward(ir, vis, upsample(f1), upsample(f2)) with the two encoder maps passed at
+        their own resolution as (tokens bf16 [B, h*w, C], h, w) -- what MixVisionTransformer.forward_stages returns.
+        The 1x1 convs, channel_proj3 and the bilinear resize commute (all linear), so the full-resolution feature
+        maps are never written; see csrc/ffm.cu."""
+        _no_autograd(self, ir, vis)
+        return self._run(ir, vis, ("lowres",) + tuple(stage1), ("lowres",) + tuple(stage2))
+
+    def _ffm(self, x1, x2, seg, out1, ldo1, coffo1, out2, ldo2, coffo2, B, H, W, pre_conv):
+        if seg[0] == "lowres":
+            _, tok, qh, qw = seg
+            self.ffm.forward_pixel_major_lr(x1, 64, x2, 64, tok, qh, qw, out1, ldo1, coffo1, out2, ldo2, coffo2, B, H, W, pre_conv)
+        else:
+            t = seg[1]
+            self.ffm.forward_pixel_major(x1, 64, x2, 64, t, t.shape[-1], out1, ldo1, coffo1, out2, ldo2, coffo2, B, H * W,
+                                         pre_conv=pre_conv)
+
+    def _run(self, ir, vis, seg1, seg2):
         B, _, H, W = ir.shape
-        HW = H * W
         dev = ir.device
         alpha = self.relu.weight.detach()
         ir, vis = ir.float(), vis.float()      # no-ops for fp32 inputs; channel 0 is read through the batch stride
-        seg1, seg2 = _pixel_major_bf16(out1), _pixel_major_bf16(out2)
         G = DRDB.GROWTH_LD
         buf1 = torch.empty((B, H, W, G), dtype=torch.bfloat16, device=dev)
         buf2 = torch.empty((B, H, W, G), dtype=torch.bfloat16, device=dev)
@@ -418,14 +461,12 @@ class Fusion_Network3_ac(nn.Module):
         x1 = self.DRDB1.forward_buffer(buf1, B, H, W, partials=part)    # [B*HW, 64] bf16
         x2 = self.DRDB2.forward_buffer(buf2, B, H, W, partials=part)
         # ffm(x1, x2, conv3(out1)) -> inputs of DRDB3 / DRDB4 (channels 0..63 of the growth buffers)
-        self.ffm.forward_pixel_major(x1, 64, x2, 64, seg1, seg1.shape[-1], buf1, G, 0, buf2, G, 0, B, HW,
-                                     pre_conv=self.conv3)
+        self._ffm(x1, x2, seg1, buf1, G, 0, buf2, G, 0, B, H, W, self.conv3)
         x1 = self.DRDB3.forward_buffer(buf1, B, H, W, out=x1, ld_dst=64, partials=part)
         x2 = self.DRDB4.forward_buffer(buf2, B, H, W, out=x2, ld_dst=64, partials=part)
         # second pass of the SAME ffm with conv4(out2); outputs land side by side = torch.cat([x1, x2], 1)
         cat = torch.empty((B, H, W, 128), dtype=torch.bfloat16, device=dev)
-        self.ffm.forward_pixel_major(x1, 64, x2, 64, seg2, seg2.shape[-1], cat, 128, 0, cat, 128, 64, B, HW,
-                                     pre_conv=self.conv4)
+        self._ffm(x1, x2, seg2, cat, 128, 0, cat, 128, 64, B, H, W, self.conv4)
         f = ops.conv(cat, self._packs.conv(self.conv2.weight), self.conv2.bias.detach(), B=B, H=H, W=W, Cin=128, KH=3,
                      KW=3, pad=1, Cout=64, act=ACT_PRELU, prelu_alpha=alpha)
         f = ops.conv(f, self._packs.conv(self.conv21.weight), self.conv21.bias.detach(), B=B, H=H, W=W, Cin=64, KH=3,

@@ -308,6 +308,26 @@ def ffm(x1, ld1, coff1, x2, ld2, coff2, x3, ld3, C3, packs, out1, ldo1, coffo1, 
     return ctx
 
 
+def ffm_lr(x1, ld1, coff1, x2, ld2, coff2, q3, qh, qw, H, W, packs, out1, ldo1, coffo1, out2, ldo2, coffo2, B):
+    """Hierarchical interactive attention with the seg stream given as the low-resolution pre-activation Q
+    (bf16 [B, qh, qw, 128]); `packs` from CrossPath.packs_lr."""
+    st = _prep(x1, x2, q3, out1, out2)
+    dev = x1.device
+    HW = H * W
+    nchunk = max(1, min((148 * 4) // max(B, 1), (HW + 63) // 64))
+    partials = torch.empty((B, nchunk, 3, 64, 64), dtype=torch.float32, device=dev)
+    folded = torch.empty((B, 4, 64, 64), dtype=torch.bfloat16, device=dev)
+    ctx = torch.empty((B, 3, 8, 8, 8), dtype=torch.float32, device=dev)
+    _lib.call("segmif_ffm_gram_lr_fwd", _ptr(x1), ld1, coff1, _ptr(x2), ld2, coff2, _ptr(q3), qh, qw, H, W,
+              _ptr(packs["w_gram"]), _ptr(packs["b_gram"]), _ptr(partials), nchunk, B, st)
+    _lib.call("segmif_ffm_ctx_fwd", _ptr(partials), nchunk, _ptr(packs["wkv"]), _ptr(packs["wend"]), _ptr(folded),
+              _ptr(ctx), B, st)
+    _lib.call("segmif_ffm_apply_lr_fwd", _ptr(x1), ld1, coff1, _ptr(x2), ld2, coff2, _ptr(q3), qh, qw, H, W,
+              _ptr(packs["w_apply"]), _ptr(packs["b_apply"]), _ptr(folded), _ptr(packs["bend"]), _ptr(packs["ln_g"]),
+              _ptr(packs["ln_b"]), 1e-5, _ptr(out1), ldo1, coffo1, _ptr(out2), ldo2, coffo2, B, st)
+    return ctx
+
+
 def rgb2ycrcb(x):
     st = _prep(x)
     assert x.dtype == torch.float32 and x.shape[1] == 3

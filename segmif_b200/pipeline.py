@@ -19,15 +19,21 @@ class FusionSegPipeline:
         self.seg = seg_net.eval()
         self.fus = fusion_net.eval()
         self._pinned = {}
+        self.lowres_seg = True            # FFM reads the encoder maps at their own resolution (see forward_lowres)
         self._graph = None
         self._static_in = None
         self._static_out = None
 
     @torch.no_grad()
     def __call__(self, ir, vis_rgb, mask, return_intermediates=False):
-        out0, out1 = self.seg.denoise_net.encoder.forward_fusion(mask)
         vis_ycc = RGB2YCrCb(vis_rgb)                                 # train.py:356 (the fusion net reads Y)
-        fused = self.fus(ir, vis_ycc, out0, out1)                     # [B,1,H,W] fp32
+        if return_intermediates or not self.lowres_seg:
+            out0, out1 = self.seg.denoise_net.encoder.forward_fusion(mask)      # reference interface: upsampled maps
+            fused = self.fus(ir, vis_ycc, out0, out1)                 # [B,1,H,W] fp32
+        else:
+            # same numbers without ever writing the two full-resolution feature maps (Fusion_Network3_ac.forward_lowres)
+            s1, s2 = self.seg.denoise_net.encoder.forward_stages(mask, n_stages=2)
+            fused = self.fus.forward_lowres(ir, vis_ycc, s1, s2)
         rgb = ops.recompose_rgb(fused, vis_rgb, clamp=True)           # train.py:364-366 + clamp test_fusion.py:108-111
         lg = self.seg.logits_pixel_major(rgb)                         # [B,h,w,nc] fp32
         B, h, w, nc = lg.shape

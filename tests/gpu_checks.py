@@ -506,6 +506,21 @@ def ffm_module():
 
 
 @check
+def fusion_lowres_path():
+    """Fusion_Network3_ac.forward_lowres (FFM interpolates the low-resolution pre-activation) against the oracle's
+    materialised path conv3(upsample(f)) -- checks that the commuted evaluation gives the same numbers."""
+    seg, fus, (seg_sd, fus_sd) = models()
+    inp = synth.synth_inputs(2, 48, 80, seed=11)
+    with torch.no_grad():
+        stages = seg.denoise_net.encoder.forward_stages(inp["mask"].to(DEV), n_stages=2)
+        vis_ycc = ops.rgb2ycrcb(inp["vis"].to(DEV))
+        got = fus.forward_lowres(inp["ir"].to(DEV), vis_ycc, stages[0], stages[1])
+        o0, o1 = O.mit_forward_fusion(inp["mask"], O._sub(seg_sd, "denoise_net.encoder"), "mit_b1")
+        ref = O.fusion_network3_ac(inp["ir"], O.rgb2ycrcb(inp["vis"]), o0, o1, fus_sd)
+    return result("fusion_lowres_vs_oracle", rel_err(got, ref), 5e-2)
+
+
+@check
 def encoder_features_golden():
     seg, fus, _ = models()
     g = _golden()

@@ -8,9 +8,13 @@
 //    the TMA unit = the conv's zero padding for free).  The nine taps are nine shifted VIEWS of that box:
 //    MMA row r = (ty, tx) = (r / 8, r % 8) sits at line (ty + ky*dil) * HXP + tx + kx*dil, i.e. a K-major SW128
 //    operand with 8-row groups HXP*128 bytes apart whose start is shifted by (ky*dil*HXP + kx*dil) lines --
-//    L2->SM traffic drops ~5x versus gathering every tap separately;
-//  * one thread issues tcgen05.mma (M=128, N=Cout, K=16); accumulators live in TMEM, double buffered so the
-//    epilogue (tcgen05.ld -> bias -> ReLU/PReLU -> bf16 channel-slice store) of tile i overlaps the MMAs of tile i+1.
+//    L2->SM traffic drops ~5x versus gathering every tap separately (2..4 boxes in flight, sized to shared memory);
+//  * one elected thread issues tcgen05.mma (M=128, N=Cout, K=16) with precomputed descriptor words; accumulators live
+//    in TMEM, double buffered so the epilogue of tile i overlaps the MMAs of tile i+1;
+//  * epilogue: tcgen05.ld -> (+ partial pre-activation tile, TMA-loaded) -> bias -> ReLU/PReLU -> bf16 -> shared-memory
+//    staging tile -> ONE TMA store per sub-tile into the channel slice of the destination (image borders clipped by
+//    the TMA unit).  No LSU global access in the loop: per-lane 16-byte stores of a row-per-thread layout cost 32
+//    L1tex wavefronts per instruction and capped the tensor pipe at 13-23 % (profiles/r1_ncu_conv3x3_tc_v3_*).
 // Warp roles: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = epilogue.
 #include <algorithm>
 
@@ -21,9 +25,7 @@ namespace segmif {
 struct ConvTcArgs {
   const float* bias;
   const float* alpha;
-  bf16* dst;
-  const bf16* pre;     // optional bf16 partial pre-activation added before the activation
-  int B, H, W, nchunks, act, ld_dst, dst_coff, ld_pre, pre_coff;
+  int B, H, W, nchunks, act, has_pre;
   int tiles_x, tiles_y, cin, ksteps_last, nstages;
 };
 
@@ -39,24 +41,33 @@ struct ConvTcCfg {
   static constexpr int W_TILE_BYTES = COUT * 128;                      // one (slab, tap) weight tile
   static constexpr int ACC_COLS = NSUB * COUT;                         // TMEM columns per accumulator buffer
   static constexpr uint32_t TMEM_COLS = (2 * ACC_COLS) <= 32 ? 32 : (2 * ACC_COLS) <= 64 ? 64 : (2 * ACC_COLS) <= 128 ? 128 : 256;
+  static constexpr int ROW_BYTES = COUT * 2;                           // one pixel of the output / partial tile
+  static constexpr int SUB_BYTES = 128 * ROW_BYTES;                    // one 16x8 sub-tile
+  static constexpr int OUT_BYTES = NSUB * SUB_BYTES;                   // staging for the TMA stores of one tile
 };
 
 template <int COUT, int DIL, int NSUB>
 __global__ void __launch_bounds__(kConvTcThreads, 1) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                        const __grid_constant__ CUtensorMap tmW,
+                                                                       const __grid_constant__ CUtensorMap tmO,
+                                                                       const __grid_constant__ CUtensorMap tmP,
                                                                        const ConvTcArgs a) {
   using Cfg = ConvTcCfg<COUT, DIL, NSUB>;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int w_bytes = a.nchunks * 9 * Cfg::W_TILE_BYTES;
+  const int NS = a.nstages;                      // halo-tile ring depth (2..4), chosen by the host to fill shared memory
   uint8_t* sW = smem;
   uint8_t* sA = smem + w_bytes;
-  const int NS = a.nstages;                      // halo-tile ring depth (2..4), chosen by the host to fill shared memory
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + w_bytes + NS * Cfg::A_STRIDE);
+  uint8_t* sOut = sA + NS * Cfg::A_STRIDE;                             // [NSUB][128 px][COUT] bf16
+  uint8_t* sPre = sOut + Cfg::OUT_BYTES;                               // [2][NSUB][128 px][COUT] bf16 (only with pre_add)
+  uint64_t* full = reinterpret_cast<uint64_t*>(sPre + (a.has_pre ? 2 * Cfg::OUT_BYTES : 0));
   uint64_t* empty = full + 4;
   uint64_t* wfull = empty + 4;
   uint64_t* tmem_full = wfull + 1;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* pfull = tmem_empty + 2;
+  uint64_t* pempty = pfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_per_img = a.tiles_x * a.tiles_y;
@@ -65,6 +76,8 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv3x3_tc_kernel(const __g
   if (threadIdx.x == 0) {
     tc::prefetch_tmap(&tmA);
     tc::prefetch_tmap(&tmW);
+    tc::prefetch_tmap(&tmO);
+    if (a.has_pre) tc::prefetch_tmap(&tmP);
     for (int s = 0; s < 4; ++s) {
       tc::mbar_init(full + s, 1);
       tc::mbar_init(empty + s, 1);
@@ -72,6 +85,8 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv3x3_tc_kernel(const __g
     for (int s = 0; s < 2; ++s) {
       tc::mbar_init(tmem_full + s, 1);
       tc::mbar_init(tmem_empty + s, 4);        // one arrive per epilogue warp
+      tc::mbar_init(pfull + s, 1);
+      tc::mbar_init(pempty + s, 4);
     }
     tc::mbar_init(wfull, 1);
     tc::fence_barrier_init();
@@ -89,10 +104,18 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv3x3_tc_kernel(const __g
       for (int c = 0; c < a.nchunks; ++c)
         for (int t = 0; t < 9; ++t)
           tc::tma_load_2d(sW + (c * 9 + t) * Cfg::W_TILE_BYTES, &tmW, wfull, t * a.cin + c * 64, 0);
-      int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
         const int b = tile / tiles_per_img, rem = tile - b * tiles_per_img;
         const int y0 = (rem / a.tiles_x) * Cfg::TH, x0 = (rem % a.tiles_x) * Cfg::TW;
+        if (a.has_pre) {                        // partial pre-activation tile of this output tile
+          const int pb = lt & 1;
+          tc::mbar_wait(pempty + pb, ((lt >> 1) & 1) ^ 1);
+          tc::mbar_expect_tx(pfull + pb, Cfg::OUT_BYTES);
+#pragma unroll
+          for (int sub = 0; sub < NSUB; ++sub)
+            tc::tma_load_4d(sPre + pb * Cfg::OUT_BYTES + sub * Cfg::SUB_BYTES, &tmP, pfull + pb, 0, x0 + sub * 8, y0, b);
+        }
         for (int c = 0; c < a.nchunks; ++c, ++it) {
           const int s = it % NS;
           const uint32_t ph = (it / NS) & 1;
@@ -149,67 +172,68 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv3x3_tc_kernel(const __g
     }
   } else {
     const int quad = warp & 3;
-    const int r = quad * 32 + lane, ty = r >> 3, tx = r & 7;
+    const int r = quad * 32 + lane;              // MMA row == TMEM lane == pixel (r / 8, r % 8) of the sub-tile
     // act(v) = v >= 0 ? v : slope * v covers none (slope 1), ReLU (0) and PReLU (alpha): branch-free, tiny code --
     // the epilogue must stay resident in the instruction cache next to the unrolled MMA issue loop.
     const float slope = a.act == SEGMIF_ACT_PRELU ? *a.alpha : (a.act == SEGMIF_ACT_RELU ? 0.f : 1.f);
+    float bias_r[COUT];
+#pragma unroll
+    for (int j = 0; j < COUT / 4; ++j) {
+      const float4 bv = __ldg(reinterpret_cast<const float4*>(a.bias) + j);
+      bias_r[4 * j] = bv.x; bias_r[4 * j + 1] = bv.y; bias_r[4 * j + 2] = bv.z; bias_r[4 * j + 3] = bv.w;
+    }
+    const bool store_leader = (warp == 2 && lane == 0);
     int lt = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
       const int buf = lt & 1;
       const int b = tile / tiles_per_img, rem = tile - b * tiles_per_img;
-      const int y = (rem / a.tiles_x) * Cfg::TH + ty;
-      const int x0 = (rem % a.tiles_x) * Cfg::TW + tx;
-      // the partial pre-activation does not depend on this tile's MMAs: fetch it while they run
-      uint4 pre[NSUB * (COUT / 32)][4];
-      if (a.pre) {
-#pragma unroll
-        for (int sc = 0; sc < NSUB * (COUT / 32); ++sc) {
-          const int sub = sc / (COUT / 32), c = (sc % (COUT / 32)) * 32;
-          const int x = x0 + sub * 8;
-          if (y < a.H && x < a.W) {
-            const uint4* pp = reinterpret_cast<const uint4*>(a.pre + (((int64_t)b * a.H + y) * a.W + x) * a.ld_pre + a.pre_coff + c);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) pre[sc][j] = __ldg(pp + j);
-          }
-        }
-      }
+      const int y0 = (rem / a.tiles_x) * Cfg::TH, x0 = (rem % a.tiles_x) * Cfg::TW;
+      if (a.has_pre) tc::mbar_wait(pfull + buf, (lt >> 1) & 1);
       tc::mbar_wait(tmem_full + buf, (lt >> 1) & 1);
       tc::tc_fence_after();
+      if (store_leader) tc::bulk_wait_read0();               // the previous tile's TMA stores have drained the staging tile
+      tc::named_bar_sync(1, 128);
 #pragma unroll
       for (int sc = 0; sc < NSUB * (COUT / 32); ++sc) {
         const int sub = sc / (COUT / 32), c = (sc % (COUT / 32)) * 32;
-        const int x = x0 + sub * 8;
         float v[32];
         tc::tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * Cfg::ACC_COLS + sub * COUT + c), v);
-        if (y < a.H && x < a.W) {
-          if (a.pre) {
+        if (a.has_pre) {
+          const uint4* pp = reinterpret_cast<const uint4*>(sPre + buf * Cfg::OUT_BYTES + sub * Cfg::SUB_BYTES + r * Cfg::ROW_BYTES + c * 2);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint4 t = pre[sc][j];
-              const float2 p0 = unpack_bf16x2(t.x), p1 = unpack_bf16x2(t.y), p2 = unpack_bf16x2(t.z), p3 = unpack_bf16x2(t.w);
-              v[8 * j] += p0.x; v[8 * j + 1] += p0.y; v[8 * j + 2] += p1.x; v[8 * j + 3] += p1.y;
-              v[8 * j + 4] += p2.x; v[8 * j + 5] += p2.y; v[8 * j + 6] += p3.x; v[8 * j + 7] += p3.y;
-            }
+          for (int j = 0; j < 4; ++j) {
+            const uint4 t = pp[j];
+            const float2 p0 = unpack_bf16x2(t.x), p1 = unpack_bf16x2(t.y), p2 = unpack_bf16x2(t.z), p3 = unpack_bf16x2(t.w);
+            v[8 * j] += p0.x; v[8 * j + 1] += p0.y; v[8 * j + 2] += p1.x; v[8 * j + 3] += p1.y;
+            v[8 * j + 4] += p2.x; v[8 * j + 5] += p2.y; v[8 * j + 6] += p3.x; v[8 * j + 7] += p3.y;
           }
-          const float4* bp = reinterpret_cast<const float4*>(a.bias + c);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 bv = __ldg(bp + j);
-            v[4 * j] += bv.x; v[4 * j + 1] += bv.y; v[4 * j + 2] += bv.z; v[4 * j + 3] += bv.w;
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = v[j] >= 0.f ? v[j] : slope * v[j];
-          uint4* d = reinterpret_cast<uint4*>(a.dst + (((int64_t)b * a.H + y) * a.W + x) * a.ld_dst + a.dst_coff + c);
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            d[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                              pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
         }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float t = v[j] + bias_r[c + j];
+          v[j] = t >= 0.f ? t : slope * t;
+        }
+        uint4* d = reinterpret_cast<uint4*>(sOut + sub * Cfg::SUB_BYTES + r * Cfg::ROW_BYTES + c * 2);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          d[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                            pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
       }
       tc::tc_fence_before();
+      tc::fence_proxy_async();                   // staging writes -> visible to the TMA (async proxy)
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(tmem_empty + buf);     // this warp has drained the accumulator buffer
+      if (lane == 0) {
+        tc::mbar_arrive(tmem_empty + buf);       // this warp has drained the accumulator buffer
+        if (a.has_pre) tc::mbar_arrive(pempty + buf);
+      }
+      tc::named_bar_sync(1, 128);
+      if (store_leader) {
+#pragma unroll
+        for (int sub = 0; sub < NSUB; ++sub) tc::tma_store_4d(&tmO, sOut + sub * Cfg::SUB_BYTES, 0, x0 + sub * 8, y0, b);
+        tc::bulk_commit();
+      }
     }
+    if (store_leader) tc::bulk_wait_all0();
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -217,12 +241,19 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv3x3_tc_kernel(const __g
 }
 
 template <int COUT, int DIL, int NSUB>
+static size_t conv_tc_fixed_smem(int nchunks, bool has_pre) {
+  using Cfg = ConvTcCfg<COUT, DIL, NSUB>;
+  return (size_t)nchunks * 9 * Cfg::W_TILE_BYTES + Cfg::OUT_BYTES + (has_pre ? 2 * Cfg::OUT_BYTES : 0) + 17 * 8 + 16;
+}
+
+template <int COUT, int DIL, int NSUB>
 static int launch_conv_tc(const segmif_conv_params* p, cudaStream_t st) {
   using Cfg = ConvTcCfg<COUT, DIL, NSUB>;
   const int nchunks = (p->Cin + 63) / 64;
-  const size_t wb = (size_t)nchunks * 9 * Cfg::W_TILE_BYTES, limit = 227 * 1024 - 2048;
-  const int nstages = (int)std::max<size_t>(2, std::min<size_t>(4, (limit - wb) / Cfg::A_STRIDE));
-  const size_t smem = wb + (size_t)nstages * Cfg::A_STRIDE + 13 * 8 + 16;
+  const bool has_pre = p->pre_add != nullptr;
+  const size_t fixed = conv_tc_fixed_smem<COUT, DIL, NSUB>(nchunks, has_pre), limit = 227 * 1024 - 1024;
+  const int nstages = (int)std::max<size_t>(2, std::min<size_t>(4, (limit - fixed) / Cfg::A_STRIDE));
+  const size_t smem = fixed + (size_t)nstages * Cfg::A_STRIDE;
   auto kern = conv3x3_tc_kernel<COUT, DIL, NSUB>;
   static bool configured = false;          // opt in once to the full 227 KB (the size varies with Cin; never during graph capture)
   static int sms = 148;
@@ -234,32 +265,50 @@ static int launch_conv_tc(const segmif_conv_params* p, cudaStream_t st) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     configured = true;
   }
-  CUtensorMap tmA, tmW;
+  CUtensorMap tmA, tmW, tmO, tmP;
   {
     const uint64_t dims[4] = {(uint64_t)p->Cin, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B};
     const uint64_t strides[3] = {(uint64_t)p->ld_src * 2, (uint64_t)p->W * p->ld_src * 2, (uint64_t)p->H * p->W * p->ld_src * 2};
     const uint32_t box[4] = {64, (uint32_t)Cfg::HXP, (uint32_t)Cfg::HROWS, 1};
-    int rc = make_tmap_bf16_sw128(&tmA, reinterpret_cast<const bf16*>(p->src) + p->src_coff, 4, dims, strides, box, "conv3x3_tc(A)");
+    int rc = make_tmap_bf16(&tmA, reinterpret_cast<const bf16*>(p->src) + p->src_coff, 4, dims, strides, box, true, "conv3x3_tc(A)");
     if (rc) return rc;
   }
   {
     const uint64_t dims[2] = {(uint64_t)9 * p->Cin, (uint64_t)COUT};
     const uint64_t strides[1] = {(uint64_t)9 * p->Cin * 2};
     const uint32_t box[2] = {64, (uint32_t)COUT};
-    int rc = make_tmap_bf16_sw128(&tmW, p->weight, 2, dims, strides, box, "conv3x3_tc(W)");
+    int rc = make_tmap_bf16(&tmW, p->weight, 2, dims, strides, box, true, "conv3x3_tc(W)");
     if (rc) return rc;
   }
+  {
+    // output: the COUT-channel slice of the pixel-major destination; boxes of 16 x 8 pixels, clipped at the borders
+    const uint64_t dims[4] = {(uint64_t)COUT, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B};
+    const uint64_t strides[3] = {(uint64_t)p->ld_dst * 2, (uint64_t)p->W * p->ld_dst * 2, (uint64_t)p->H * p->W * p->ld_dst * 2};
+    const uint32_t box[4] = {(uint32_t)COUT, 8, 16, 1};
+    int rc = make_tmap_bf16(&tmO, reinterpret_cast<bf16*>(p->dst) + p->dst_coff, 4, dims, strides, box, false, "conv3x3_tc(O)");
+    if (rc) return rc;
+    tmP = tmO;
+    if (has_pre) {
+      const uint64_t ps[3] = {(uint64_t)p->ld_pre * 2, (uint64_t)p->W * p->ld_pre * 2, (uint64_t)p->H * p->W * p->ld_pre * 2};
+      rc = make_tmap_bf16(&tmP, reinterpret_cast<const bf16*>(p->pre_add) + p->pre_coff, 4, dims, ps, box, false, "conv3x3_tc(P)");
+      if (rc) return rc;
+    }
+  }
   ConvTcArgs a;
-  a.bias = p->bias; a.alpha = p->prelu_alpha; a.dst = reinterpret_cast<bf16*>(p->dst);
-  a.B = p->B; a.H = p->H; a.W = p->W; a.nchunks = nchunks; a.act = p->act; a.ld_dst = p->ld_dst; a.dst_coff = p->dst_coff;
+  a.bias = p->bias; a.alpha = p->prelu_alpha;
+  a.B = p->B; a.H = p->H; a.W = p->W; a.nchunks = nchunks; a.act = p->act; a.has_pre = has_pre ? 1 : 0;
   a.tiles_x = (p->W + Cfg::TW - 1) / Cfg::TW; a.tiles_y = (p->H + Cfg::TH - 1) / Cfg::TH;
   a.cin = p->Cin;
-  a.pre = reinterpret_cast<const bf16*>(p->pre_add); a.ld_pre = p->ld_pre; a.pre_coff = p->pre_coff;
   a.ksteps_last = ((p->Cin - 1) % 64) / 16 + 1;
   a.nstages = nstages;
   const int num_tiles = a.tiles_x * a.tiles_y * a.B;
-  kern<<<std::min(num_tiles, sms), kConvTcThreads, smem, st>>>(tmA, tmW, a);
+  kern<<<std::min(num_tiles, sms), kConvTcThreads, smem, st>>>(tmA, tmW, tmO, tmP, a);
   return check_launch("segmif_conv3x3_tc_fwd");
+}
+
+template <int COUT, int DIL, int NSUB>
+static bool conv_tc_fits(int nchunks, bool has_pre) {
+  return conv_tc_fixed_smem<COUT, DIL, NSUB>(nchunks, has_pre) + 2 * (size_t)ConvTcCfg<COUT, DIL, NSUB>::A_STRIDE <= 227 * 1024 - 1024;
 }
 
 }  // namespace segmif
@@ -271,36 +320,32 @@ extern "C" int segmif_conv3x3_tc_fwd(const segmif_conv_params* p, segmif_stream_
   SEGMIF_REQUIRE(p->KH == 3 && p->KW == 3 && p->stride == 1 && (p->dil == 1 || p->dil == 2) && p->pad == p->dil,
                  "conv3x3_tc: only 3x3, stride 1, dilation 1 or 2 with 'same' padding");
   SEGMIF_REQUIRE(p->Cout == 32 || p->Cout == 64, "conv3x3_tc: Cout=%d must be 32 or 64", p->Cout);
-  SEGMIF_REQUIRE(p->Cin % 8 == 0 && p->Cin > 0 && p->ld_src % 8 == 0 && p->src_coff % 8 == 0, "conv3x3_tc: Cin/pitch/offset must be multiples of 8");
+  SEGMIF_REQUIRE(p->Cin % 16 == 0 && p->Cin > 0 && p->ld_src % 8 == 0 && p->src_coff % 8 == 0, "conv3x3_tc: Cin must be a multiple of 16, pitch/offset multiples of 8");
   SEGMIF_REQUIRE(p->dst_dtype == SEGMIF_BF16 && p->ld_dst % 8 == 0 && p->dst_coff % 8 == 0, "conv3x3_tc: dst must be bf16 with 16-byte aligned slices");
   SEGMIF_REQUIRE(p->residual == nullptr, "conv3x3_tc: residual is not supported");
   SEGMIF_REQUIRE(p->pre_add == nullptr || (((uintptr_t)p->pre_add & 15) == 0 && p->ld_pre % 8 == 0 && p->pre_coff % 8 == 0), "conv3x3_tc: pre_add must be 16-byte aligned");
-  SEGMIF_REQUIRE(p->Cin % 16 == 0, "conv3x3_tc: Cin must be a multiple of 16");
   SEGMIF_REQUIRE(p->act != SEGMIF_ACT_GELU, "conv3x3_tc: GELU is not supported");
   SEGMIF_REQUIRE(p->act != SEGMIF_ACT_PRELU || p->prelu_alpha, "conv3x3_tc: PReLU needs prelu_alpha");
   SEGMIF_REQUIRE(p->src_coff + p->Cin <= p->ld_src && p->dst_coff + p->Cout <= p->ld_dst, "conv3x3_tc: channel slice exceeds pitch");
-  SEGMIF_REQUIRE(((uintptr_t)p->src & 15) == 0 && ((uintptr_t)p->weight & 15) == 0 && ((uintptr_t)p->dst & 15) == 0, "conv3x3_tc: pointers must be 16-byte aligned");
+  SEGMIF_REQUIRE(((uintptr_t)p->src & 15) == 0 && ((uintptr_t)p->weight & 15) == 0 && ((uintptr_t)p->dst & 15) == 0 && ((uintptr_t)p->bias & 15) == 0,
+                 "conv3x3_tc: pointers must be 16-byte aligned");
   cudaStream_t st = as_stream(stream);
-  const size_t nchunks = (size_t)(p->Cin + 63) / 64;
-  const size_t limit = 227 * 1024 - 2048;
-  const size_t wbytes = nchunks * 9 * (size_t)p->Cout * 128;
-  constexpr size_t a_32_2_2 = 2 * (size_t)ConvTcCfg<32, 2, 2>::A_STRIDE, a_32_2_1 = 2 * (size_t)ConvTcCfg<32, 2, 1>::A_STRIDE;
-  constexpr size_t a_32_1_2 = 2 * (size_t)ConvTcCfg<32, 1, 2>::A_STRIDE, a_32_1_1 = 2 * (size_t)ConvTcCfg<32, 1, 1>::A_STRIDE;
-  constexpr size_t a_64_1_1 = 2 * (size_t)ConvTcCfg<64, 1, 1>::A_STRIDE, a_64_2_1 = 2 * (size_t)ConvTcCfg<64, 2, 1>::A_STRIDE;
+  const int nchunks = (p->Cin + 63) / 64;
+  const bool pre = p->pre_add != nullptr;
   if (p->Cout == 32 && p->dil == 2) {
-    if (wbytes + a_32_2_2 <= limit) return launch_conv_tc<32, 2, 2>(p, st);
-    SEGMIF_REQUIRE(wbytes + a_32_2_1 <= limit, "conv3x3_tc: Cin=%d too large for resident weights", p->Cin);
+    if (conv_tc_fits<32, 2, 2>(nchunks, pre)) return launch_conv_tc<32, 2, 2>(p, st);
+    SEGMIF_REQUIRE((conv_tc_fits<32, 2, 1>(nchunks, pre)), "conv3x3_tc: Cin=%d too large for resident weights", p->Cin);
     return launch_conv_tc<32, 2, 1>(p, st);
   }
   if (p->Cout == 32 && p->dil == 1) {
-    if (wbytes + a_32_1_2 <= limit) return launch_conv_tc<32, 1, 2>(p, st);
-    SEGMIF_REQUIRE(wbytes + a_32_1_1 <= limit, "conv3x3_tc: Cin=%d too large for resident weights", p->Cin);
+    if (conv_tc_fits<32, 1, 2>(nchunks, pre)) return launch_conv_tc<32, 1, 2>(p, st);
+    SEGMIF_REQUIRE((conv_tc_fits<32, 1, 1>(nchunks, pre)), "conv3x3_tc: Cin=%d too large for resident weights", p->Cin);
     return launch_conv_tc<32, 1, 1>(p, st);
   }
   if (p->Cout == 64 && p->dil == 1) {
-    SEGMIF_REQUIRE(wbytes + a_64_1_1 <= limit, "conv3x3_tc: Cin=%d too large for resident weights", p->Cin);
+    SEGMIF_REQUIRE((conv_tc_fits<64, 1, 1>(nchunks, pre)), "conv3x3_tc: Cin=%d too large for resident weights", p->Cin);
     return launch_conv_tc<64, 1, 1>(p, st);
   }
-  SEGMIF_REQUIRE(wbytes + a_64_2_1 <= limit, "conv3x3_tc: Cin=%d too large for resident weights", p->Cin);
+  SEGMIF_REQUIRE((conv_tc_fits<64, 2, 1>(nchunks, pre)), "conv3x3_tc: Cin=%d too large for resident weights", p->Cin);
   return launch_conv_tc<64, 2, 1>(p, st);
 }

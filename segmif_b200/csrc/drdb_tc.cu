@@ -217,7 +217,7 @@ static int launch_push(const segmif_drdb_push_params* p, cudaStream_t st) {
     const uint64_t dims[4] = {(uint64_t)p->slab_width, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B};
     const uint64_t strides[3] = {(uint64_t)p->ld_src * 2, (uint64_t)p->W * p->ld_src * 2, (uint64_t)p->H * p->W * p->ld_src * 2};
     const uint32_t box[4] = {64, (uint32_t)Cfg::HXP, (uint32_t)Cfg::HROWS, 1};
-    int rc = make_tmap_bf16_sw128(&tmA, reinterpret_cast<const bf16*>(p->src) + p->slab_offset, 4, dims, strides, box, "drdb_push(A)");
+    int rc = make_tmap_bf16(&tmA, reinterpret_cast<const bf16*>(p->src) + p->slab_offset, 4, dims, strides, box, true, "drdb_push(A)");
     if (rc) return rc;
   }
   {
@@ -225,7 +225,7 @@ static int launch_push(const segmif_drdb_push_params* p, cudaStream_t st) {
     const uint64_t dims[2] = {wcols, (uint64_t)NOUT};
     const uint64_t strides[1] = {wcols * 2};
     const uint32_t box[2] = {64, (uint32_t)NOUT};
-    int rc = make_tmap_bf16_sw128(&tmW, p->weight, 2, dims, strides, box, "drdb_push(W)");
+    int rc = make_tmap_bf16(&tmW, p->weight, 2, dims, strides, box, true, "drdb_push(W)");
     if (rc) return rc;
   }
   PushArgs a;

@@ -24,8 +24,8 @@ EncodeTiledFn get_encode_tiled() {
   return fn;
 }
 
-int make_tmap_bf16_sw128(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                         const uint32_t* box, const char* what) {
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box, bool swizzle128, const char* what) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return SEGMIF_ERR_CUDA;
   cuuint64_t gd[5], gs[5];
@@ -33,7 +33,7 @@ int make_tmap_bf16_sw128(CUtensorMap* out, const void* base, int rank, const uin
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("%s: cuTensorMapEncodeTiled failed (CUresult %d)", what, (int)r);
@@ -248,14 +248,14 @@ static int linear_tc_impl(const segmif_linear_params* p, cudaStream_t st) {
     const uint64_t dims[2] = {(uint64_t)p->K, (uint64_t)p->M};
     const uint64_t strides[1] = {(uint64_t)p->ld_src * 2};
     const uint32_t box[2] = {64, 128};
-    int rc = make_tmap_bf16_sw128(&tmA, reinterpret_cast<const bf16*>(p->src) + p->src_coff, 2, dims, strides, box, "linear_tc(A)");
+    int rc = make_tmap_bf16(&tmA, reinterpret_cast<const bf16*>(p->src) + p->src_coff, 2, dims, strides, box, true, "linear_tc(A)");
     if (rc) return rc;
   }
   {
     const uint64_t dims[2] = {(uint64_t)p->K, (uint64_t)p->N};
     const uint64_t strides[1] = {(uint64_t)p->K * 2};
     const uint32_t box[2] = {64, (uint32_t)BN};
-    int rc = make_tmap_bf16_sw128(&tmB, p->weight, 2, dims, strides, box, "linear_tc(W)");
+    int rc = make_tmap_bf16(&tmB, p->weight, 2, dims, strides, box, true, "linear_tc(W)");
     if (rc) return rc;
   }
   TcEpilogue e;

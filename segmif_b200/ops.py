@@ -100,7 +100,7 @@ def conv(src, weight, bias, *, B, H, W, Cin, KH=1, KW=1, stride=1, pad=0, dil=1,
                 return out
             if (KH == 3 and KW == 3 and stride == 1 and pad == dil and dil in (1, 2) and Cout in (32, 64)
                     and out.dtype == torch.bfloat16 and residual is None and bias is not None and act != ACT_GELU
-                    and aligned and _conv3x3_tc_fits(Cin, Cout, dil)):
+                    and aligned and _conv3x3_tc_fits(Cin, Cout, dil, pre_add is not None)):
                 entry = "segmif_conv3x3_tc_fwd"
     _lib.call(entry, ctypes.byref(p), st)
     return out
@@ -109,11 +109,13 @@ def conv(src, weight, bias, *, B, H, W, Cin, KH=1, KW=1, stride=1, pad=0, dil=1,
 USE_TCGEN05 = os.environ.get("SEGMIF_TCGEN05", "1") != "0"
 
 
-def _conv3x3_tc_fits(Cin, Cout, dil):
-    """Resident weights + two halo-tile stages must fit the 227 KB of shared memory (mirrors conv_tc.cu)."""
+def _conv3x3_tc_fits(Cin, Cout, dil, has_pre=False):
+    """Resident weights + output / partial staging tiles + two halo-tile slots must fit the 227 KB of shared memory
+    (mirrors conv_tc.cu for the smallest tile, NSUB = 1)."""
     wbytes = ((Cin + 63) // 64) * 9 * Cout * 128
-    a_bytes = ((16 + 2 * dil) * (8 + 2 * dil) * 128 + 1023) // 1024 * 1024     # NSUB = 1 halo tile, 1024-aligned slot
-    return wbytes + 2 * a_bytes <= 227 * 1024 - 2048
+    out_bytes = 128 * Cout * 2
+    a_stride = ((16 + 2 * dil) * (8 + 2 * dil) * 128 + 1023) // 1024 * 1024
+    return wbytes + out_bytes * (3 if has_pre else 1) + 17 * 8 + 16 + 2 * a_stride <= 227 * 1024 - 1024
 
 
 def conv3x3_tc(src, weight, bias, **kw):

@@ -152,6 +152,18 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def dominant_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel family, from the committed
+    `ncu --set full` capture summarised in profiles/r1_ncu_dominant_kernel.json (null when that file is absent)."""
+    p = os.path.join(ROOT, "profiles", "r1_ncu_dominant_kernel.json")
+    if not os.path.exists(p):
+        return None
+    try:
+        return json.load(open(p))["traffic_bytes_per_launch"]
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -314,9 +326,9 @@ def run_ours(a):
                 "roofline": {"kernel": "DRDB Dcov1-5 (3x3 dil-2 implicit GEMM on tcgen05): drdb_push_tc_kernel<96|64,.,64> for the x0 slab + "
                                        "conv3x3_tc_kernel<32,2,2> over the g-slabs",
                              "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                             "frac": (achieved / peak) if achieved else None, "traffic": None,
+                             "frac": (achieved / peak) if achieved else None, "traffic": dominant_traffic(),
                              "peak_source": f"{peaks['source']} bf16_tflops_sustained",
-                             "launches": len(drdb_events), "share_of_step": drdb_ms / ms_instr if ms_instr else None,
+                             "launches": len(drdb_events), "share_of_step": (drdb_ms / ms_total) if ms_total else None,
                              "measured_in": "eager event-instrumented pass of the same steps (%.2f ms/step)" % (ms_instr / a.steps),
                              "algorithmic": "2*B*H*W*9*K*N FLOP per launch (K = input channels of the launch, N = its output channels); "
                                             "per DRDB the launches sum to 2*B*H*W*9*640*32, the FLOPs of the five reference "

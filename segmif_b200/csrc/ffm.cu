@@ -513,7 +513,7 @@ __global__ void __launch_bounds__(kFfmThreads) ffm_gram_lr_kernel(const bf16* __
       }
 }
 
-__global__ void __launch_bounds__(kFfmThreads) ffm_apply_lr_kernel(
+__global__ void __launch_bounds__(kFfmThreads, 3) ffm_apply_lr_kernel(
     const bf16* __restrict__ x1, int ld1, const bf16* __restrict__ x2, int ld2, const LrSeg L,
     const bf16* __restrict__ wproj, const float* __restrict__ bproj, const bf16* __restrict__ folded,
     const float* __restrict__ bend, const float* __restrict__ ln_g, const float* __restrict__ ln_b, float eps,

@@ -46,189 +46,112 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__
 // ------------------------------------------------------------------------------------------------ SSIM
 struct Gauss11 { float g[11]; };
 
-// Tile = 64 x 32 outputs.  Both passes are register blocked: a thread produces 16 (horizontal) / 8 (vertical)
-// consecutive outputs from a sliding window, so each shared-memory value is loaded once per thread instead of 11 times
-// (the first version was LSU-bound at 8 % of the HBM peak).
-constexpr int kSsimTX = 64, kSsimTY = 32, kSsimR = 5;
-constexpr int kSsimIW = kSsimTX + 2 * kSsimR;      // 74 input columns
-constexpr int kSsimIH = kSsimTY + 2 * kSsimR;      // 42 input rows
-constexpr int kSsimIP = kSsimIW + 1;               // odd pitch: rows hit different banks
-constexpr size_t kSsimSmem = (size_t)(2 * kSsimIH * kSsimIP + 5 * kSsimIH * kSsimTX) * sizeof(float);
-
 __global__ void __launch_bounds__(256) ssim_kernel(const float* __restrict__ a, const float* __restrict__ b, int H,
                                                    int W, Gauss11 win, float* __restrict__ partials) {
-  extern __shared__ float ssm[];
-  float* sa = ssm;                                  // [42][75]
-  float* sb = sa + kSsimIH * kSsimIP;
-  float* hz = sb + kSsimIH * kSsimIP;               // [5][42][64]
+  constexpr int T = 32, R = 5, TW = T + 2 * R;   // 42
+  __shared__ float sa[TW][TW + 1], sb[TW][TW + 1];
+  __shared__ float hz[5][TW][T + 1];
   __shared__ float sred[8];
-  const int bx = blockIdx.x * kSsimTX, by = blockIdx.y * kSsimTY;
+  const int bx = blockIdx.x * T, by = blockIdx.y * T;
   const int64_t img = blockIdx.z;
   const float* pa = a + img * H * W;
   const float* pb = b + img * H * W;
-  for (int i = threadIdx.x; i < kSsimIH * kSsimIW; i += 256) {
-    const int r = i / kSsimIW, c = i - r * kSsimIW;
-    const int y = by + r - kSsimR, x = bx + c - kSsimR;
+  for (int i = threadIdx.x; i < TW * TW; i += 256) {
+    const int r = i / TW, c = i % TW;
+    const int y = by + r - R, x = bx + c - R;
     const bool ok = (unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W;
-    sa[r * kSsimIP + c] = ok ? pa[(int64_t)y * W + x] : 0.f;
-    sb[r * kSsimIP + c] = ok ? pb[(int64_t)y * W + x] : 0.f;
+    sa[r][c] = ok ? pa[(int64_t)y * W + x] : 0.f;
+    sb[r][c] = ok ? pb[(int64_t)y * W + x] : 0.f;
   }
   __syncthreads();
-  // horizontal: item = (column block of 16, row); rows vary fastest across lanes -> conflict-free (odd pitch)
-  for (int item = threadIdx.x; item < (kSsimTX / 16) * kSsimIH; item += 256) {
-    const int r = item % kSsimIH, c0 = (item / kSsimIH) * 16;
-    float m1[16], m2[16], s11[16], s22[16], s12[16];
+  for (int i = threadIdx.x; i < TW * T; i += 256) {
+    const int r = i / T, c = i % T;
+    float m1 = 0.f, m2 = 0.f, s11 = 0.f, s22 = 0.f, s12 = 0.f;
 #pragma unroll
-    for (int o = 0; o < 16; ++o) { m1[o] = m2[o] = s11[o] = s22[o] = s12[o] = 0.f; }
-#pragma unroll
-    for (int k = 0; k < 26; ++k) {
-      const float x = sa[r * kSsimIP + c0 + k], y = sb[r * kSsimIP + c0 + k];
-      const float xx = x * x, yy = y * y, xy = x * y;
-#pragma unroll
-      for (int o = 0; o < 16; ++o) {
-        const int t = k - o;                         // tap index of output o for input k
-        if (t >= 0 && t < 11) {
-          const float g = win.g[t];
-          m1[o] = fmaf(g, x, m1[o]); m2[o] = fmaf(g, y, m2[o]);
-          s11[o] = fmaf(g, xx, s11[o]); s22[o] = fmaf(g, yy, s22[o]); s12[o] = fmaf(g, xy, s12[o]);
-        }
-      }
+    for (int k = 0; k < 11; ++k) {
+      const float x = sa[r][c + k], y = sb[r][c + k], g = win.g[k];
+      m1 = fmaf(g, x, m1); m2 = fmaf(g, y, m2);
+      s11 = fmaf(g, x * x, s11); s22 = fmaf(g, y * y, s22); s12 = fmaf(g, x * y, s12);
     }
-#pragma unroll
-    for (int o = 0; o < 16; ++o) {
-      const int idx = r * kSsimTX + c0 + o;
-      hz[idx] = m1[o]; hz[kSsimIH * kSsimTX + idx] = m2[o]; hz[2 * kSsimIH * kSsimTX + idx] = s11[o];
-      hz[3 * kSsimIH * kSsimTX + idx] = s22[o]; hz[4 * kSsimIH * kSsimTX + idx] = s12[o];
-    }
+    hz[0][r][c] = m1; hz[1][r][c] = m2; hz[2][r][c] = s11; hz[3][r][c] = s22; hz[4][r][c] = s12;
   }
   __syncthreads();
-  // vertical: thread = (column, block of 8 rows); columns vary fastest across lanes -> conflict-free
   float local = 0.f;
-  {
-    const int c = threadIdx.x & 63, r0 = (threadIdx.x >> 6) * 8;
-    float acc[5][8];
+  for (int i = threadIdx.x; i < T * T; i += 256) {
+    const int r = i / T, c = i % T;
+    if (by + r >= H || bx + c >= W) continue;
+    float m1 = 0.f, m2 = 0.f, s11 = 0.f, s22 = 0.f, s12 = 0.f;
 #pragma unroll
-    for (int q = 0; q < 5; ++q)
-#pragma unroll
-      for (int o = 0; o < 8; ++o) acc[q][o] = 0.f;
-#pragma unroll
-    for (int k = 0; k < 18; ++k) {
-      float v[5];
-#pragma unroll
-      for (int q = 0; q < 5; ++q) v[q] = hz[q * kSsimIH * kSsimTX + (r0 + k) * kSsimTX + c];
-#pragma unroll
-      for (int o = 0; o < 8; ++o) {
-        const int t = k - o;
-        if (t >= 0 && t < 11) {
-          const float g = win.g[t];
-#pragma unroll
-          for (int q = 0; q < 5; ++q) acc[q][o] = fmaf(g, v[q], acc[q][o]);
-        }
-      }
+    for (int k = 0; k < 11; ++k) {
+      const float g = win.g[k];
+      m1 = fmaf(g, hz[0][r + k][c], m1); m2 = fmaf(g, hz[1][r + k][c], m2);
+      s11 = fmaf(g, hz[2][r + k][c], s11); s22 = fmaf(g, hz[3][r + k][c], s22); s12 = fmaf(g, hz[4][r + k][c], s12);
     }
-#pragma unroll
-    for (int o = 0; o < 8; ++o) {
-      if (by + r0 + o < H && bx + c < W) {
-        const float m1 = acc[0][o], m2 = acc[1][o];
-        const float mu1_sq = m1 * m1, mu2_sq = m2 * m2, mu12 = m1 * m2;
-        const float sg1 = acc[2][o] - mu1_sq, sg2 = acc[3][o] - mu2_sq, sg12 = acc[4][o] - mu12;
-        const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
-        local += ((2.f * mu12 + C1) * (2.f * sg12 + C2)) / ((mu1_sq + mu2_sq + C1) * (sg1 + sg2 + C2));
-      }
-    }
+    const float mu1_sq = m1 * m1, mu2_sq = m2 * m2, mu12 = m1 * m2;
+    const float sg1 = s11 - mu1_sq, sg2 = s22 - mu2_sq, sg12 = s12 - mu12;
+    const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+    local += ((2.f * mu12 + C1) * (2.f * sg12 + C2)) / ((mu1_sq + mu2_sq + C1) * (sg1 + sg2 + C2));
   }
   const float tot = block_sum_256(local, sred);
   if (threadIdx.x == 0) partials[((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = tot;
 }
 
 // ------------------------------------------------------------------------------------------------ Laplacian
-// The reference's 2-D kernel exp(-(dx^2+dy^2)/(2 s^2)) / sum is the outer product of the normalised 1-D Gaussian with
-// itself, so every scale is filtered separably.  Tile = 64 x 32 outputs; images are processed one after the other
-// through the same shared-memory planes, their residuals (3 scales x 8 rows) stay in registers.
-struct LapKernels { float g3[3], g5[5], g7[7]; };
+struct LapKernels { float k3[9], k5[25], k7[49]; };
 
-constexpr int kLapTX = 64, kLapTY = 32, kLapR = 3;
-constexpr int kLapIW = kLapTX + 2 * kLapR;        // 70
-constexpr int kLapIH = kLapTY + 2 * kLapR;        // 38
-constexpr int kLapIP = kLapIW + 1;                // 71 (odd)
-constexpr size_t kLapSmem = (size_t)(kLapIH * kLapIP + 3 * kLapIH * kLapTX) * sizeof(float);
+template <int K>
+__device__ __forceinline__ float lap_residual(const float (*t)[39], int r, int c, const float* ker) {
+  // t has a 3-pixel halo; residual = centre - (G_K * img)
+  constexpr int R = K / 2;
+  float s = 0.f;
+#pragma unroll
+  for (int dy = 0; dy < K; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < K; ++dx) s = fmaf(ker[dy * K + dx], t[r + 3 - R + dy][c + 3 - R + dx], s);
+  return t[r + 3][c + 3] - s;
+}
 
 // NIMG = 3: LapLoss2 (input, ir, vis -> target = max(res ir, res vis));  NIMG = 2: LapLoss (input, target)
 template <int NIMG>
 __global__ void __launch_bounds__(256) laploss_kernel(const float* __restrict__ inp, const float* __restrict__ p1,
                                                       const float* __restrict__ p2, int H, int W, LapKernels ker,
                                                       float* __restrict__ partials) {
-  extern __shared__ float lsm[];
-  float* tile = lsm;                                // [38][71]
-  float* hz = tile + kLapIH * kLapIP;               // [3 scales][38][64]
+  constexpr int T = 32, R = 3, TW = T + 2 * R;   // 38
+  __shared__ float s0[TW][39], s1[TW][39], s2[NIMG == 3 ? TW : 1][39];
   __shared__ float sred[8];
-  const int bx = blockIdx.x * kLapTX, by = blockIdx.y * kLapTY;
+  const int bx = blockIdx.x * T, by = blockIdx.y * T;
   const int64_t off = (int64_t)blockIdx.z * H * W;
-  const int c = threadIdx.x & 63, r0 = (threadIdx.x >> 6) * 8;
-  float res[NIMG][3][8];
-#pragma unroll
-  for (int im = 0; im < NIMG; ++im) {
-    const float* src = (im == 0 ? inp : im == 1 ? p1 : p2) + off;
-    __syncthreads();                                // previous image's planes are fully consumed
-    for (int i = threadIdx.x; i < kLapIH * kLapIW; i += 256) {
-      const int r = i / kLapIW, cc = i - r * kLapIW;
-      const int y = by + r - kLapR, x = bx + cc - kLapR;
-      tile[r * kLapIP + cc] = ((unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W) ? src[(int64_t)y * W + x] : 0.f;
-    }
-    __syncthreads();
-    // horizontal pass of the three scales: item = (column block of 16, row), rows fastest across lanes
-    for (int item = threadIdx.x; item < (kLapTX / 16) * kLapIH; item += 256) {
-      const int r = item % kLapIH, c0 = (item / kLapIH) * 16;
-      float h3[16], h5[16], h7[16];
-#pragma unroll
-      for (int o = 0; o < 16; ++o) { h3[o] = h5[o] = h7[o] = 0.f; }
-#pragma unroll
-      for (int k = 0; k < 22; ++k) {                 // input column c0 + k covers output o at tap k - o (7-tap frame)
-        const float x = tile[r * kLapIP + c0 + k];
-#pragma unroll
-        for (int o = 0; o < 16; ++o) {
-          const int t = k - o;
-          if (t >= 0 && t < 7) h7[o] = fmaf(ker.g7[t], x, h7[o]);
-          if (t >= 1 && t < 6) h5[o] = fmaf(ker.g5[t - 1], x, h5[o]);
-          if (t >= 2 && t < 5) h3[o] = fmaf(ker.g3[t - 2], x, h3[o]);
-        }
-      }
-#pragma unroll
-      for (int o = 0; o < 16; ++o) {
-        const int idx = r * kLapTX + c0 + o;
-        hz[idx] = h3[o]; hz[kLapIH * kLapTX + idx] = h5[o]; hz[2 * kLapIH * kLapTX + idx] = h7[o];
-      }
-    }
-    __syncthreads();
-    // vertical pass: thread = (column, 8 rows); residual = centre - blurred
-    float v3[8], v5[8], v7[8];
-#pragma unroll
-    for (int o = 0; o < 8; ++o) { v3[o] = v5[o] = v7[o] = 0.f; }
-#pragma unroll
-    for (int k = 0; k < 14; ++k) {
-      const float a3 = hz[(r0 + k) * kLapTX + c], a5 = hz[kLapIH * kLapTX + (r0 + k) * kLapTX + c],
-                  a7 = hz[2 * kLapIH * kLapTX + (r0 + k) * kLapTX + c];
-#pragma unroll
-      for (int o = 0; o < 8; ++o) {
-        const int t = k - o;
-        if (t >= 0 && t < 7) v7[o] = fmaf(ker.g7[t], a7, v7[o]);
-        if (t >= 1 && t < 6) v5[o] = fmaf(ker.g5[t - 1], a5, v5[o]);
-        if (t >= 2 && t < 5) v3[o] = fmaf(ker.g3[t - 2], a3, v3[o]);
-      }
-    }
-#pragma unroll
-    for (int o = 0; o < 8; ++o) {
-      const float centre = tile[(r0 + o + kLapR) * kLapIP + c + kLapR];
-      res[im][0][o] = centre - v3[o]; res[im][1][o] = centre - v5[o]; res[im][2][o] = centre - v7[o];
-    }
+  for (int i = threadIdx.x; i < TW * TW; i += 256) {
+    const int r = i / TW, c = i % TW;
+    const int y = by + r - R, x = bx + c - R;
+    const bool ok = (unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W;
+    const int64_t o = off + (int64_t)y * W + x;
+    s0[r][c] = ok ? inp[o] : 0.f;
+    s1[r][c] = ok ? p1[o] : 0.f;
+    if (NIMG == 3) s2[r][c] = ok ? p2[o] : 0.f;
   }
+  __syncthreads();
   float l3 = 0.f, l5 = 0.f, l7 = 0.f;
-#pragma unroll
-  for (int o = 0; o < 8; ++o) {
-    if (by + r0 + o < H && bx + c < W) {
-      float t3 = res[1][0][o], t5 = res[1][1][o], t7 = res[1][2][o];
-      if (NIMG == 3) { t3 = fmaxf(t3, res[NIMG - 1][0][o]); t5 = fmaxf(t5, res[NIMG - 1][1][o]); t7 = fmaxf(t7, res[NIMG - 1][2][o]); }
-      l3 += fabsf(res[0][0][o] - t3); l5 += fabsf(res[0][1][o] - t5); l7 += fabsf(res[0][2][o] - t7);
+  for (int i = threadIdx.x; i < T * T; i += 256) {
+    const int r = i / T, c = i % T;
+    if (by + r >= H || bx + c >= W) continue;
+    {
+      const float a = lap_residual<3>(s0, r, c, ker.k3);
+      float t = lap_residual<3>(s1, r, c, ker.k3);
+      if (NIMG == 3) t = fmaxf(t, lap_residual<3>(s2, r, c, ker.k3));
+      l3 += fabsf(a - t);
+    }
+    {
+      const float a = lap_residual<5>(s0, r, c, ker.k5);
+      float t = lap_residual<5>(s1, r, c, ker.k5);
+      if (NIMG == 3) t = fmaxf(t, lap_residual<5>(s2, r, c, ker.k5));
+      l5 += fabsf(a - t);
+    }
+    {
+      const float a = lap_residual<7>(s0, r, c, ker.k7);
+      float t = lap_residual<7>(s1, r, c, ker.k7);
+      if (NIMG == 3) t = fmaxf(t, lap_residual<7>(s2, r, c, ker.k7));
+      l7 += fabsf(a - t);
     }
   }
   const int64_t blk = ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
@@ -424,7 +347,7 @@ static int finish(float* workspace, int groups, int nblocks, int nout, int mode,
 using namespace segmif;
 
 extern "C" size_t segmif_loss_workspace_bytes(int B, int H, int W) {
-  const size_t tiles = (size_t)B * ((H + 31) / 32) * ((W + 63) / 64);
+  const size_t tiles = (size_t)B * ((H + 31) / 32) * ((W + 31) / 32);
   const size_t blocks = tiles > 4096 ? tiles : 4096;
   return 256 + blocks * 3 * sizeof(float);
 }
@@ -445,11 +368,9 @@ extern "C" int segmif_ssim_fwd(const float* img1, const float* img2, int B, int 
   SEGMIF_REQUIRE(B > 0 && H > 0 && W > 0, "ssim: empty input");
   SEGMIF_REQUIRE(!per_image || B <= 32, "ssim: per-image mode supports at most 32 images per call");
   static const Gauss11 win = make_gauss11();
-  dim3 grid((W + kSsimTX - 1) / kSsimTX, (H + kSsimTY - 1) / kSsimTY, B);
+  dim3 grid((W + 31) / 32, (H + 31) / 32, B);
   cudaStream_t st = as_stream(stream);
-  static bool cfg = false;
-  if (!cfg) { cudaFuncSetAttribute(ssim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSsimSmem); cfg = true; }
-  ssim_kernel<<<grid, 256, kSsimSmem, st>>>(img1, img2, H, W, win, partial_area(workspace));
+  ssim_kernel<<<grid, 256, 0, st>>>(img1, img2, H, W, win, partial_area(workspace));
   int rc = check_launch("segmif_ssim_fwd");
   if (rc) return rc;
   const int per = grid.x * grid.y;
@@ -458,29 +379,35 @@ extern "C" int segmif_ssim_fwd(const float* img1, const float* img2, int B, int 
 }
 
 static LapKernels make_lap_kernels() {
-  // lap_loss.py:39-60: exp(-(dx^2+dy^2)/(2*sigma^2)) normalised to sum 1 == outer product of n[i] = g[i] / sum(g)
+  // lap_loss.py:39-60: fp32 exp of -(dx^2+dy^2)/(2*sigma^2), times 1/(2 pi sigma^2), normalised by its fp32 sum
   LapKernels k;
   const int sizes[3] = {3, 5, 7};
-  float* dst[3] = {k.g3, k.g5, k.g7};
+  float* dst[3] = {k.k3, k.k5, k.k7};
   for (int s = 0; s < 3; ++s) {
     const int n = sizes[s];
-    const double mean = (n - 1) / 2.0;
-    double g[7], sum = 0.0;
-    for (int i = 0; i < n; ++i) { g[i] = exp(-(i - mean) * (i - mean) / 8.0); sum += g[i]; }
-    for (int i = 0; i < n; ++i) dst[s][i] = (float)(g[i] / sum);
+    const float mean = (n - 1) / 2.0f, var = 4.0f;
+    float sum = 0.f;
+    for (int y = 0; y < n; ++y)
+      for (int x = 0; x < n; ++x) {
+        const float d2 = (x - mean) * (x - mean) + (y - mean) * (y - mean);
+        const float e = expf(-d2 / (2.f * var));
+        const float v = (float)(1.0 / (2.0 * 3.14159265358979323846 * 4.0)) * e;
+        dst[s][y * n + x] = v;
+        sum += v;
+      }
+    for (int i = 0; i < n * n; ++i) dst[s][i] /= sum;
   }
   return k;
 }
+
 extern "C" int segmif_laploss2_fwd(const float* inp, const float* ir, const float* vis, int B, int H, int W,
                                    float* workspace, float* out, segmif_stream_t stream) {
   SEGMIF_REQUIRE(inp && ir && vis && workspace && out, "laploss2: null pointer");
   SEGMIF_REQUIRE(B > 0 && H > 0 && W > 0, "laploss2: empty input");
   static const LapKernels ker = make_lap_kernels();
-  dim3 grid((W + kLapTX - 1) / kLapTX, (H + kLapTY - 1) / kLapTY, B);
+  dim3 grid((W + 31) / 32, (H + 31) / 32, B);
   cudaStream_t st = as_stream(stream);
-  static bool cfg = false;
-  if (!cfg) { cudaFuncSetAttribute(laploss_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLapSmem); cfg = true; }
-  laploss_kernel<3><<<grid, 256, kLapSmem, st>>>(inp, ir, vis, H, W, ker, partial_area(workspace));
+  laploss_kernel<3><<<grid, 256, 0, st>>>(inp, ir, vis, H, W, ker, partial_area(workspace));
   int rc = check_launch("segmif_laploss2_fwd");
   if (rc) return rc;
   return finish(workspace, 1, grid.x * grid.y * B, 3, 1, 1.0 / ((double)B * H * W), out, st, "segmif_laploss2_fwd");
@@ -491,11 +418,9 @@ extern "C" int segmif_laploss_fwd(const float* inp, const float* target, int B, 
   SEGMIF_REQUIRE(inp && target && workspace && out, "laploss: null pointer");
   SEGMIF_REQUIRE(B > 0 && H > 0 && W > 0, "laploss: empty input");
   static const LapKernels ker = make_lap_kernels();
-  dim3 grid((W + kLapTX - 1) / kLapTX, (H + kLapTY - 1) / kLapTY, B);
+  dim3 grid((W + 31) / 32, (H + 31) / 32, B);
   cudaStream_t st = as_stream(stream);
-  static bool cfg = false;
-  if (!cfg) { cudaFuncSetAttribute(laploss_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLapSmem); cfg = true; }
-  laploss_kernel<2><<<grid, 256, kLapSmem, st>>>(inp, target, nullptr, H, W, ker, partial_area(workspace));
+  laploss_kernel<2><<<grid, 256, 0, st>>>(inp, target, nullptr, H, W, ker, partial_area(workspace));
   int rc = check_launch("segmif_laploss_fwd");
   if (rc) return rc;
   return finish(workspace, 1, grid.x * grid.y * B, 3, 1, 1.0 / ((double)B * H * W), out, st, "segmif_laploss_fwd");

@@ -513,117 +513,7 @@ __global__ void __launch_bounds__(kFfmThreads) ffm_gram_lr_kernel(const bf16* __
       }
 }
 
-__global__ void __launch_bounds__(kFfmThreads, 3) ffm_apply_lr_kernel(
-    const bf16* __restrict__ x1, int ld1, const bf16* __restrict__ x2, int ld2, const LrSeg L,
-    const bf16* __restrict__ wproj, const float* __restrict__ bproj, const bf16* __restrict__ folded,
-    const float* __restrict__ bend, const float* __restrict__ ln_g, const float* __restrict__ ln_b, float eps,
-    bf16* __restrict__ out1, int ldo1, bf16* __restrict__ out2, int ldo2, int64_t HW) {
-  extern __shared__ __align__(128) uint8_t smem_raw[];
-  bf16* sW1 = reinterpret_cast<bf16*>(smem_raw);   // [64][64]   channel_proj1 (u half)
-  bf16* sW2 = sW1 + 64 * 64;                       // [64][64]   channel_proj2 (u half)
-  bf16* sM = sW2 + 64 * 64;                        // [4][64][64] folded Mz1, Mv1, Mz2, Mv2 of this image
-  bf16* sX1 = sM + 4 * 64 * 64;                    // [64 px][64]
-  bf16* sX2 = sX1 + kTilePx * 64;
-  bf16* sY = sX2 + kTilePx * 64;                   // [64 px][64]  y3 = relu(upsample(Q)[0:64])
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int b = blockIdx.y;
-  {
-    for (int i = tid; i < 2 * 64 * 8; i += kFfmThreads) {
-      const int m = i >> 9, row = (i >> 3) & 63, chunk = i & 7;
-      cp_async16_cg(smem_u32(sW1 + m * 4096 + row * 64 + swz128(row, chunk) * 8), wproj + m * 4096 + row * 64 + chunk * 8, 16);
-    }
-    const bf16* fb = folded + (int64_t)b * 4 * 4096;
-    for (int i = tid; i < 4 * 64 * 8; i += kFfmThreads) {
-      const int m = i >> 9, row = (i >> 3) & 63, chunk = i & 7;
-      cp_async16_cg(smem_u32(sM + m * 4096 + row * 64 + swz128(row, chunk) * 8), fb + m * 4096 + row * 64 + chunk * 8, 16);
-    }
-    cp_async_commit();
-  }
-  const int g = lane >> 2, tq = lane & 3;
-  const int64_t ntiles = (HW + kTilePx - 1) / kTilePx;
-  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    const int64_t p0 = t * kTilePx;
-    __syncthreads();
-    load_rows_async(sX1, x1 + (int64_t)b * HW * ld1, p0, HW, ld1, 64, kTilePx, tid);
-    load_rows_async(sX2, x2 + (int64_t)b * HW * ld2, p0, HW, ld2, 64, kTilePx, tid);
-    cp_async_commit();
-    lerp_relu_tile(sY, L, b, 0, p0, HW, tid);        // overlaps the asynchronous x1 / x2 loads
-    cp_async_wait<0>();
-    __syncthreads();
-    const int row0 = warp * 16;
-    uint32_t ay[4][4];
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-      const int row = row0 + (lane & 15), chunk = kk * 2 + (lane >> 4);
-      ldmatrix_x4(ay[kk], smem_u32(sY + row * 64 + swz128(row, chunk) * 8));
-    }
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      const bf16* sX = s == 0 ? sX1 : sX2;
-      uint32_t au[4][4];
-      {
-        float acc[8][4];
-        proj16x64(acc, sX, 64, row0, s == 0 ? sW1 : sW2, lane);
-        relu_bias_to_afrag(au, acc, bproj + 64 * s, tq);
-      }
-      float acc[8][4];
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-      apply64(acc, ay, sM + (2 * s) * 4096, lane);
-      apply64(acc, au, sM + (2 * s + 1) * 4096, lane);
-      float sum[2] = {0.f, 0.f};
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        const int ch = nt * 8 + tq * 2;
-        const float b0 = bend[s * 64 + ch], b1 = bend[s * 64 + ch + 1];
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const int row = row0 + g + half * 8;
-          const float2 xr = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(sX + row * 64 + swz128(row, nt) * 8 + tq * 2));
-          acc[nt][half * 2] += b0 + xr.x;
-          acc[nt][half * 2 + 1] += b1 + xr.y;
-          sum[half] += acc[nt][half * 2] + acc[nt][half * 2 + 1];
-        }
-      }
-      float mean[2], rstd[2];
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        sum[half] += __shfl_xor_sync(0xffffffffu, sum[half], 1);
-        sum[half] += __shfl_xor_sync(0xffffffffu, sum[half], 2);
-        mean[half] = sum[half] * (1.f / 64.f);
-      }
-      float sq[2] = {0.f, 0.f};
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { const float d = acc[nt][j] - mean[j >> 1]; sq[j >> 1] += d * d; }
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        sq[half] += __shfl_xor_sync(0xffffffffu, sq[half], 1);
-        sq[half] += __shfl_xor_sync(0xffffffffu, sq[half], 2);
-        rstd[half] = rsqrtf(sq[half] * (1.f / 64.f) + eps);
-      }
-      bf16* op = (s == 0 ? out1 : out2);
-      const int ldo = s == 0 ? ldo1 : ldo2;
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int64_t px = p0 + row0 + g + half * 8;
-        if (px >= HW) continue;
-        bf16* o = op + ((int64_t)b * HW + px) * ldo + tq * 2;
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-          const int ch = nt * 8 + tq * 2;
-          const float v0 = (acc[nt][half * 2] - mean[half]) * rstd[half] * ln_g[s * 64 + ch] + ln_b[s * 64 + ch];
-          const float v1 = (acc[nt][half * 2 + 1] - mean[half]) * rstd[half] * ln_g[s * 64 + ch + 1] + ln_b[s * 64 + ch + 1];
-          *reinterpret_cast<uint32_t*>(o + nt * 8) = pack_bf16x2(v0, v1);
-        }
-      }
-    }
-  }
-  cp_async_wait<0>();
-}
+// (pass 3 of the low-resolution form runs on tcgen05: ffm_tc.cu)
 
 // one-time opt-in to the largest configuration of each kernel (never called again, e.g. during graph capture)
 static int set_smem(const void* fn, size_t bytes, const char* what, bool* done) {
@@ -711,29 +601,4 @@ extern "C" int segmif_ffm_gram_lr_fwd(const void* x1, int ld1, int coff1, const 
   ffm_gram_lr_kernel<<<grid, kFfmThreads, smem, as_stream(stream)>>>((const bf16*)x1 + coff1, ld1, (const bf16*)x2 + coff2, ld2, L,
                                                                       (const bf16*)wproj, bproj, partials, (int64_t)H * W);
   return check_launch("segmif_ffm_gram_lr_fwd");
-}
-
-extern "C" int segmif_ffm_apply_lr_fwd(const void* x1, int ld1, int coff1, const void* x2, int ld2, int coff2,
-                                       const void* q3, int qh, int qw, int H, int W, const void* wproj,
-                                       const float* bproj, const void* folded, const float* bend, const float* ln_gamma,
-                                       const float* ln_beta, float eps, void* out1, int ldo1, int coffo1, void* out2,
-                                       int ldo2, int coffo2, int B, segmif_stream_t stream) {
-  SEGMIF_REQUIRE(x1 && x2 && wproj && bproj && folded && bend && ln_gamma && ln_beta && out1 && out2, "ffm_apply_lr: null pointer");
-  SEGMIF_REQUIRE(ld1 % 8 == 0 && ld2 % 8 == 0 && coff1 % 8 == 0 && coff2 % 8 == 0, "ffm_apply_lr: input pitches/offsets must be multiples of 8");
-  SEGMIF_REQUIRE(ldo1 % 2 == 0 && ldo2 % 2 == 0 && coffo1 % 2 == 0 && coffo2 % 2 == 0, "ffm_apply_lr: output pitches/offsets must be even");
-  LrSeg L;
-  int rc = make_lrseg(&L, q3, qh, qw, H, W);
-  if (rc) return rc;
-  const size_t smem = (size_t)(2 * 4096 + 4 * 4096 + 3 * kTilePx * 64) * sizeof(bf16);
-  static bool cfg = false;
-  rc = set_smem((const void*)ffm_apply_lr_kernel, smem, "ffm_apply_lr", &cfg);
-  if (rc) return rc;
-  const int64_t HW = (int64_t)H * W;
-  const int64_t ntiles = (HW + kTilePx - 1) / kTilePx;
-  const int per_image = (int)std::min<int64_t>(ntiles, std::max<int64_t>(1, (148 * 3 * 4) / B));
-  dim3 grid(per_image, B);
-  ffm_apply_lr_kernel<<<grid, kFfmThreads, smem, as_stream(stream)>>>(
-      (const bf16*)x1 + coff1, ld1, (const bf16*)x2 + coff2, ld2, L, (const bf16*)wproj, bproj, (const bf16*)folded, bend,
-      ln_gamma, ln_beta, eps, (bf16*)out1 + coffo1, ldo1, (bf16*)out2 + coffo2, ldo2, HW);
-  return check_launch("segmif_ffm_apply_lr_fwd");
 }

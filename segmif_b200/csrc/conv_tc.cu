@@ -15,8 +15,13 @@
 //    staging tile -> ONE TMA store per sub-tile into the channel slice of the destination (image borders clipped by
 //    the TMA unit).  No LSU global access in the loop: per-lane 16-byte stores of a row-per-thread layout cost 32
 //    L1tex wavefronts per instruction and capped the tensor pipe at 13-23 % (profiles/r1_ncu_conv3x3_tc_v3_*).
+//    The staging tiles cost 16..48 KB; when they would take a slot from the halo ring (wide layers: weights 72 KB) the
+//    host selects the DIRECT epilogue instead: partial rows prefetched into registers before the accumulator wait,
+//    16-byte global stores.  The ring depth matters more: with two 51 KB slots a 2-slab layer holds ONE tile in
+//    flight and every tile pays the ~1.8 us box-load latency (profiles/r1_ncu_conv3x3_tc_v7_*: MMA warp 50 % in wait).
 // Warp roles: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = epilogue.
 #include <algorithm>
+#include <type_traits>
 
 #include "tc_common.cuh"
 
@@ -27,6 +32,10 @@ struct ConvTcArgs {
   const float* alpha;
   int B, H, W, nchunks, act, has_pre;
   int tiles_x, tiles_y, cin, ksteps_last, nstages;
+  int staged;              // 1: partial / output tiles go through shared-memory staging + TMA; 0: per-thread global access
+  const bf16* pre;         // direct mode: partial pre-activations (channel offset applied), pitch ld_pre
+  bf16* dst;               // direct mode: destination slice (channel offset applied), pitch ld_dst
+  int ld_pre, ld_dst;
 };
 
 constexpr int kConvTcThreads = 192;
@@ -59,8 +68,8 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv3x3_tc_kernel(const __g
   uint8_t* sW = smem;
   uint8_t* sA = smem + w_bytes;
   uint8_t* sOut = sA + NS * Cfg::A_STRIDE;                             // [NSUB][128 px][COUT] bf16
-  uint8_t* sPre = sOut + Cfg::OUT_BYTES;                               // [2][NSUB][128 px][COUT] bf16 (only with pre_add)
-  uint64_t* full = reinterpret_cast<uint64_t*>(sPre + (a.has_pre ? 2 * Cfg::OUT_BYTES : 0));
+  uint8_t* sPre = sOut + (a.staged ? Cfg::OUT_BYTES : 0);              // [2][NSUB][128 px][COUT] bf16 (only with pre_add)
+  uint64_t* full = reinterpret_cast<uint64_t*>(sPre + ((a.staged && a.has_pre) ? 2 * Cfg::OUT_BYTES : 0));
   uint64_t* empty = full + 4;
   uint64_t* wfull = empty + 4;
   uint64_t* tmem_full = wfull + 1;
@@ -108,7 +117,7 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv3x3_tc_kernel(const __g
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
         const int b = tile / tiles_per_img, rem = tile - b * tiles_per_img;
         const int y0 = (rem / a.tiles_x) * Cfg::TH, x0 = (rem % a.tiles_x) * Cfg::TW;
-        if (a.has_pre) {                        // partial pre-activation tile of this output tile
+        if (a.has_pre && a.staged) {            // partial pre-activation tile of this output tile
           const int pb = lt & 1;
           tc::mbar_wait(pempty + pb, ((lt >> 1) & 1) ^ 1);
           tc::mbar_expect_tx(pfull + pb, Cfg::OUT_BYTES);
@@ -129,10 +138,12 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv3x3_tc_kernel(const __g
   } else if (warp == 1) {
     // Whole warp walks the loop (uniform control flow -> descriptors live in uniform registers); the elected lane issues.
     constexpr uint32_t idesc = tc::make_idesc_bf16(128, COUT);
-    constexpr uint32_t A_HI = tc::desc_hi_sw128(Cfg::HXP * 128), B_HI = tc::desc_hi_sw128(1024);
+    // 64-bit descriptors advanced with ONE uniform 64-bit add each (UIADD3.64): ~2 SASS instructions per MMA.  Building them
+    // from separate lo / hi words cost 8 per MMA, which made every N=32 launch issue-bound (55 cycles per 17-cycle MMA).
+    constexpr uint64_t A_HI = (uint64_t)tc::desc_hi_sw128(Cfg::HXP * 128) << 32, B_HI = (uint64_t)tc::desc_hi_sw128(1024) << 32;
     const bool leader = tc::elect_one();
     tc::mbar_wait(wfull, 0);
-    const uint32_t w_lo0 = smem_u32(sW) >> 4;
+    const uint64_t w_d0 = B_HI | (uint64_t)(smem_u32(sW) >> 4);
     int it = 0, lt = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
       const int buf = lt & 1;
@@ -144,25 +155,33 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv3x3_tc_kernel(const __g
         tc::mbar_wait(full + s, (it / NS) & 1);
         tc::tc_fence_after();
         if (leader) {
-          const uint32_t a_lo0 = smem_u32(sA + s * Cfg::A_STRIDE) >> 4;
-          const uint32_t w_lo = w_lo0 + (uint32_t)(c * 9 * (Cfg::W_TILE_BYTES >> 4));
+          uint64_t a_d0 = A_HI | (uint64_t)(smem_u32(sA + s * Cfg::A_STRIDE) >> 4);
+          uint64_t w_d = w_d0 + (uint64_t)(c * 9 * (Cfg::W_TILE_BYTES >> 4));
+          asm volatile("" : "+l"(a_d0), "+l"(w_d));        // opaque bases: the per-MMA offsets stay 32-bit immediates of one UIADD3.64
           const uint32_t first = c != 0 ? 1u : 0u;
           const int klim = (c == a.nchunks - 1) ? a.ksteps_last : 4;
+          // trailing channels of a partly filled last slab are zeros: only the first klim k-steps are issued.  One uniform
+          // branch per slab selects a fully unrolled, predicate-free instance.
+          auto issue = [&](auto klim_c) {
+            constexpr int KL = decltype(klim_c)::value;
 #pragma unroll
-          for (int t = 0; t < 9; ++t) {
-            const int ky = t / 3, kx = t % 3;
+            for (int t = 0; t < 9; ++t) {
+              const int ky = t / 3, kx = t % 3;
 #pragma unroll
-            for (int sub = 0; sub < NSUB; ++sub) {
+              for (int sub = 0; sub < NSUB; ++sub) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                if (k >= klim) continue;                 // trailing channels of a partly filled last slab are zeros: skip
-                const uint32_t a_off = (uint32_t)(((ky * DIL * Cfg::HXP + kx * DIL + sub * 8) * 128 + k * 32) >> 4);
-                const uint32_t w_off = (uint32_t)((t * Cfg::W_TILE_BYTES + k * 32) >> 4);
-                tc::umma_bf16_lohi(acc + (uint32_t)(sub * COUT), a_lo0 + a_off, A_HI, w_lo + w_off, B_HI, idesc,
-                                   (t == 0 && k == 0) ? first : 1u);
+                for (int k = 0; k < KL; ++k) {
+                  const uint32_t a_off = (uint32_t)(((ky * DIL * Cfg::HXP + kx * DIL + sub * 8) * 128 + k * 32) >> 4);
+                  const uint32_t w_off = (uint32_t)((t * Cfg::W_TILE_BYTES + k * 32) >> 4);
+                  tc::umma_bf16(acc + (uint32_t)(sub * COUT), a_d0 + a_off, w_d + w_off, idesc, (t == 0 && k == 0) ? first : 1u);
+                }
               }
             }
-          }
+          };
+          if (klim == 4) issue(std::integral_constant<int, 4>{});
+          else if (klim == 2) issue(std::integral_constant<int, 2>{});
+          else if (klim == 1) issue(std::integral_constant<int, 1>{});
+          else issue(std::integral_constant<int, 3>{});
           tc::umma_commit(empty + s);
         }
         __syncwarp();
@@ -184,53 +203,108 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv3x3_tc_kernel(const __g
     }
     const bool store_leader = (warp == 2 && lane == 0);
     int lt = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
-      const int buf = lt & 1;
-      const int b = tile / tiles_per_img, rem = tile - b * tiles_per_img;
-      const int y0 = (rem / a.tiles_x) * Cfg::TH, x0 = (rem % a.tiles_x) * Cfg::TW;
-      if (a.has_pre) tc::mbar_wait(pfull + buf, (lt >> 1) & 1);
-      tc::mbar_wait(tmem_full + buf, (lt >> 1) & 1);
-      tc::tc_fence_after();
-      if (store_leader) tc::bulk_wait_read0();               // the previous tile's TMA stores have drained the staging tile
-      tc::named_bar_sync(1, 128);
+    if (a.staged) {
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+        const int buf = lt & 1;
+        const int b = tile / tiles_per_img, rem = tile - b * tiles_per_img;
+        const int y0 = (rem / a.tiles_x) * Cfg::TH, x0 = (rem % a.tiles_x) * Cfg::TW;
+        if (a.has_pre) tc::mbar_wait(pfull + buf, (lt >> 1) & 1);
+        tc::mbar_wait(tmem_full + buf, (lt >> 1) & 1);
+        tc::tc_fence_after();
+        if (store_leader) tc::bulk_wait_read0();               // the previous tile's TMA stores have drained the staging tile
+        tc::named_bar_sync(1, 128);
 #pragma unroll
-      for (int sc = 0; sc < NSUB * (COUT / 32); ++sc) {
-        const int sub = sc / (COUT / 32), c = (sc % (COUT / 32)) * 32;
-        float v[32];
-        tc::tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * Cfg::ACC_COLS + sub * COUT + c), v);
-        if (a.has_pre) {
-          const uint4* pp = reinterpret_cast<const uint4*>(sPre + buf * Cfg::OUT_BYTES + sub * Cfg::SUB_BYTES + r * Cfg::ROW_BYTES + c * 2);
+        for (int sc = 0; sc < NSUB * (COUT / 32); ++sc) {
+          const int sub = sc / (COUT / 32), c = (sc % (COUT / 32)) * 32;
+          float v[32];
+          tc::tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * Cfg::ACC_COLS + sub * COUT + c), v);
+          if (a.has_pre) {
+            const uint4* pp = reinterpret_cast<const uint4*>(sPre + buf * Cfg::OUT_BYTES + sub * Cfg::SUB_BYTES + r * Cfg::ROW_BYTES + c * 2);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint4 t = pp[j];
-            const float2 p0 = unpack_bf16x2(t.x), p1 = unpack_bf16x2(t.y), p2 = unpack_bf16x2(t.z), p3 = unpack_bf16x2(t.w);
-            v[8 * j] += p0.x; v[8 * j + 1] += p0.y; v[8 * j + 2] += p1.x; v[8 * j + 3] += p1.y;
-            v[8 * j + 4] += p2.x; v[8 * j + 5] += p2.y; v[8 * j + 6] += p3.x; v[8 * j + 7] += p3.y;
+            for (int j = 0; j < 4; ++j) {
+              const uint4 t = pp[j];
+              const float2 p0 = unpack_bf16x2(t.x), p1 = unpack_bf16x2(t.y), p2 = unpack_bf16x2(t.z), p3 = unpack_bf16x2(t.w);
+              v[8 * j] += p0.x; v[8 * j + 1] += p0.y; v[8 * j + 2] += p1.x; v[8 * j + 3] += p1.y;
+              v[8 * j + 4] += p2.x; v[8 * j + 5] += p2.y; v[8 * j + 6] += p3.x; v[8 * j + 7] += p3.y;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float t = v[j] + bias_r[c + j];
+            v[j] = t >= 0.f ? t : slope * t;
+          }
+          uint4* d = reinterpret_cast<uint4*>(sOut + sub * Cfg::SUB_BYTES + r * Cfg::ROW_BYTES + c * 2);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            d[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                              pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+        }
+        tc::tc_fence_before();
+        tc::fence_proxy_async();                   // staging writes -> visible to the TMA (async proxy)
+        __syncwarp();
+        if (lane == 0) {
+          tc::mbar_arrive(tmem_empty + buf);       // this warp has drained the accumulator buffer
+          if (a.has_pre) tc::mbar_arrive(pempty + buf);
+        }
+        tc::named_bar_sync(1, 128);
+        if (store_leader) {
+#pragma unroll
+          for (int sub = 0; sub < NSUB; ++sub) tc::tma_store_4d(&tmO, sOut + sub * Cfg::SUB_BYTES, 0, x0 + sub * 8, y0, b);
+          tc::bulk_commit();
+        }
+      }
+    } else {
+      // direct epilogue: this thread owns pixel (r / 8, r % 8) of every sub-tile
+      const int ty = r >> 3, tx = r & 7;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+        const int buf = lt & 1;
+        const int b = tile / tiles_per_img, rem = tile - b * tiles_per_img;
+        const int y = (rem / a.tiles_x) * Cfg::TH + ty, x0 = (rem % a.tiles_x) * Cfg::TW + tx;
+        const size_t rowpix = ((size_t)b * a.H + y) * a.W;
+        uint4 pv[NSUB][COUT / 8];
+        if (a.has_pre) {                           // partial rows in flight while the MMAs of this tile still run
+#pragma unroll
+          for (int sub = 0; sub < NSUB; ++sub) {
+            const int x = x0 + sub * 8;
+            const bool ok = y < a.H && x < a.W;
+            const uint4* pp = reinterpret_cast<const uint4*>(a.pre + (rowpix + x) * a.ld_pre);
+#pragma unroll
+            for (int j = 0; j < COUT / 8; ++j) pv[sub][j] = ok ? __ldg(pp + j) : make_uint4(0, 0, 0, 0);
           }
         }
+        tc::mbar_wait(tmem_full + buf, (lt >> 1) & 1);
+        tc::tc_fence_after();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float t = v[j] + bias_r[c + j];
-          v[j] = t >= 0.f ? t : slope * t;
+        for (int sc = 0; sc < NSUB * (COUT / 32); ++sc) {
+          const int sub = sc / (COUT / 32), c = (sc % (COUT / 32)) * 32;
+          float v[32];
+          tc::tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * Cfg::ACC_COLS + sub * COUT + c), v);
+          if (a.has_pre) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 t = pv[sub][c / 8 + j];
+              const float2 p0 = unpack_bf16x2(t.x), p1 = unpack_bf16x2(t.y), p2 = unpack_bf16x2(t.z), p3 = unpack_bf16x2(t.w);
+              v[8 * j] += p0.x; v[8 * j + 1] += p0.y; v[8 * j + 2] += p1.x; v[8 * j + 3] += p1.y;
+              v[8 * j + 4] += p2.x; v[8 * j + 5] += p2.y; v[8 * j + 6] += p3.x; v[8 * j + 7] += p3.y;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float t = v[j] + bias_r[c + j];
+            v[j] = t >= 0.f ? t : slope * t;
+          }
+          const int x = x0 + sub * 8;
+          if (y < a.H && x < a.W) {
+            uint4* d = reinterpret_cast<uint4*>(a.dst + (rowpix + x) * a.ld_dst + c);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              d[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+          }
         }
-        uint4* d = reinterpret_cast<uint4*>(sOut + sub * Cfg::SUB_BYTES + r * Cfg::ROW_BYTES + c * 2);
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          d[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                            pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
-      }
-      tc::tc_fence_before();
-      tc::fence_proxy_async();                   // staging writes -> visible to the TMA (async proxy)
-      __syncwarp();
-      if (lane == 0) {
-        tc::mbar_arrive(tmem_empty + buf);       // this warp has drained the accumulator buffer
-        if (a.has_pre) tc::mbar_arrive(pempty + buf);
-      }
-      tc::named_bar_sync(1, 128);
-      if (store_leader) {
-#pragma unroll
-        for (int sub = 0; sub < NSUB; ++sub) tc::tma_store_4d(&tmO, sOut + sub * Cfg::SUB_BYTES, 0, x0 + sub * 8, y0, b);
-        tc::bulk_commit();
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(tmem_empty + buf);
       }
     }
     if (store_leader) tc::bulk_wait_all0();
@@ -241,9 +315,9 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv3x3_tc_kernel(const __g
 }
 
 template <int COUT, int DIL, int NSUB>
-static size_t conv_tc_fixed_smem(int nchunks, bool has_pre) {
+static size_t conv_tc_fixed_smem(int nchunks, bool has_pre, bool staged) {
   using Cfg = ConvTcCfg<COUT, DIL, NSUB>;
-  return (size_t)nchunks * 9 * Cfg::W_TILE_BYTES + Cfg::OUT_BYTES + (has_pre ? 2 * Cfg::OUT_BYTES : 0) + 17 * 8 + 16;
+  return (size_t)nchunks * 9 * Cfg::W_TILE_BYTES + (staged ? Cfg::OUT_BYTES + (has_pre ? 2 * Cfg::OUT_BYTES : 0) : 0) + 17 * 8 + 16;
 }
 
 template <int COUT, int DIL, int NSUB>
@@ -251,8 +325,13 @@ static int launch_conv_tc(const segmif_conv_params* p, cudaStream_t st) {
   using Cfg = ConvTcCfg<COUT, DIL, NSUB>;
   const int nchunks = (p->Cin + 63) / 64;
   const bool has_pre = p->pre_add != nullptr;
-  const size_t fixed = conv_tc_fixed_smem<COUT, DIL, NSUB>(nchunks, has_pre), limit = 227 * 1024 - 1024;
-  const int nstages = (int)std::max<size_t>(2, std::min<size_t>(4, (limit - fixed) / Cfg::A_STRIDE));
+  const size_t limit = 227 * 1024 - 1024;
+  auto depth = [&](bool staged_) {
+    return (int)std::min<size_t>(4, (limit - conv_tc_fixed_smem<COUT, DIL, NSUB>(nchunks, has_pre, staged_)) / Cfg::A_STRIDE);
+  };
+  const bool staged = depth(true) >= depth(false);       // staging tiles only when they do not cost a ring slot
+  const size_t fixed = conv_tc_fixed_smem<COUT, DIL, NSUB>(nchunks, has_pre, staged);
+  const int nstages = std::max(2, depth(staged));
   const size_t smem = fixed + (size_t)nstages * Cfg::A_STRIDE;
   auto kern = conv3x3_tc_kernel<COUT, DIL, NSUB>;
   static bool configured = false;          // opt in once to the full 227 KB (the size varies with Cin; never during graph capture)
@@ -270,7 +349,8 @@ static int launch_conv_tc(const segmif_conv_params* p, cudaStream_t st) {
     const uint64_t dims[4] = {(uint64_t)p->Cin, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B};
     const uint64_t strides[3] = {(uint64_t)p->ld_src * 2, (uint64_t)p->W * p->ld_src * 2, (uint64_t)p->H * p->W * p->ld_src * 2};
     const uint32_t box[4] = {64, (uint32_t)Cfg::HXP, (uint32_t)Cfg::HROWS, 1};
-    int rc = make_tmap_bf16(&tmA, reinterpret_cast<const bf16*>(p->src) + p->src_coff, 4, dims, strides, box, true, "conv3x3_tc(A)");
+    int rc = make_tmap_bf16(&tmA, reinterpret_cast<const bf16*>(p->src) + p->src_coff, 4, dims, strides, box, true, "conv3x3_tc(A)",
+                            p->Cin == p->ld_src ? 256 : 64);       // a channel slab of wider rows: do not widen L2 misses
     if (rc) return rc;
   }
   {
@@ -290,7 +370,7 @@ static int launch_conv_tc(const segmif_conv_params* p, cudaStream_t st) {
     tmP = tmO;
     if (has_pre) {
       const uint64_t ps[3] = {(uint64_t)p->ld_pre * 2, (uint64_t)p->W * p->ld_pre * 2, (uint64_t)p->H * p->W * p->ld_pre * 2};
-      rc = make_tmap_bf16(&tmP, reinterpret_cast<const bf16*>(p->pre_add) + p->pre_coff, 4, dims, ps, box, false, "conv3x3_tc(P)");
+      rc = make_tmap_bf16(&tmP, reinterpret_cast<const bf16*>(p->pre_add) + p->pre_coff, 4, dims, ps, box, false, "conv3x3_tc(P)", COUT == p->ld_pre ? 256 : 64);
       if (rc) return rc;
     }
   }
@@ -301,6 +381,10 @@ static int launch_conv_tc(const segmif_conv_params* p, cudaStream_t st) {
   a.cin = p->Cin;
   a.ksteps_last = ((p->Cin - 1) % 64) / 16 + 1;
   a.nstages = nstages;
+  a.staged = staged ? 1 : 0;
+  a.pre = has_pre ? reinterpret_cast<const bf16*>(p->pre_add) + p->pre_coff : nullptr;
+  a.dst = reinterpret_cast<bf16*>(p->dst) + p->dst_coff;
+  a.ld_pre = p->ld_pre; a.ld_dst = p->ld_dst;
   const int num_tiles = a.tiles_x * a.tiles_y * a.B;
   kern<<<std::min(num_tiles, sms), kConvTcThreads, smem, st>>>(tmA, tmW, tmO, tmP, a);
   return check_launch("segmif_conv3x3_tc_fwd");
@@ -308,7 +392,7 @@ static int launch_conv_tc(const segmif_conv_params* p, cudaStream_t st) {
 
 template <int COUT, int DIL, int NSUB>
 static bool conv_tc_fits(int nchunks, bool has_pre) {
-  return conv_tc_fixed_smem<COUT, DIL, NSUB>(nchunks, has_pre) + 2 * (size_t)ConvTcCfg<COUT, DIL, NSUB>::A_STRIDE <= 227 * 1024 - 1024;
+  return conv_tc_fixed_smem<COUT, DIL, NSUB>(nchunks, has_pre, false) + 2 * (size_t)ConvTcCfg<COUT, DIL, NSUB>::A_STRIDE <= 227 * 1024 - 1024;
 }
 
 }  // namespace segmif

@@ -106,10 +106,11 @@ __global__ void __launch_bounds__(kPushThreads, 1) drdb_push_tc_kernel(const __g
     __syncwarp();
   } else if (warp == 1) {
     constexpr uint32_t idesc = tc::make_idesc_bf16(128, NOUT);
-    constexpr uint32_t A_HI = tc::desc_hi_sw128(Cfg::HXP * 128), B_HI = tc::desc_hi_sw128(1024);
+    constexpr uint64_t A_HI = (uint64_t)tc::desc_hi_sw128(Cfg::HXP * 128) << 32, B_HI = (uint64_t)tc::desc_hi_sw128(1024) << 32;
     const bool leader = tc::elect_one();
     tc::mbar_wait(wfull, 0);
-    const uint32_t w_lo = smem_u32(sW) >> 4;
+    uint64_t w_d = B_HI | (uint64_t)(smem_u32(sW) >> 4);         // 64-bit descriptors: one UIADD3.64 per operand per MMA
+    asm volatile("" : "+l"(w_d));
     int lt = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
       const int s = lt % NS, buf = lt & 1;     // halo-tile ring slot and TMEM accumulator buffer of this tile
@@ -118,7 +119,8 @@ __global__ void __launch_bounds__(kPushThreads, 1) drdb_push_tc_kernel(const __g
       tc::tc_fence_after();
       if (leader) {
         const uint32_t acc = tmem_base + (uint32_t)(buf * Cfg::ACC_COLS);
-        const uint32_t a_lo0 = smem_u32(sA + s * Cfg::A_STRIDE) >> 4;
+        uint64_t a_d0 = A_HI | (uint64_t)(smem_u32(sA + s * Cfg::A_STRIDE) >> 4);
+        asm volatile("" : "+l"(a_d0));                  // opaque base: per-MMA offsets stay immediates of one UIADD3.64
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
           const int ky = t / 3, kx = t % 3;
@@ -128,7 +130,7 @@ __global__ void __launch_bounds__(kPushThreads, 1) drdb_push_tc_kernel(const __g
             for (int k = 0; k < KSLAB / 16; ++k) {
               const uint32_t a_off = (uint32_t)(((ky * Cfg::DIL * Cfg::HXP + kx * Cfg::DIL + sub * 8) * 128 + k * 32) >> 4);
               const uint32_t w_off = (uint32_t)(((KSLAB == 64 ? t * Cfg::W_TILE_BYTES : (t >> 1) * Cfg::W_TILE_BYTES + (t & 1) * 64) + k * 32) >> 4);
-              tc::umma_bf16_lohi(acc + (uint32_t)(sub * NOUT), a_lo0 + a_off, A_HI, w_lo + w_off, B_HI, idesc,
+              tc::umma_bf16(acc + (uint32_t)(sub * NOUT), a_d0 + a_off, w_d + w_off, idesc,
                                  (t == 0 && k == 0) ? 0u : 1u);
             }
           }
@@ -217,7 +219,8 @@ static int launch_push(const segmif_drdb_push_params* p, cudaStream_t st) {
     const uint64_t dims[4] = {(uint64_t)p->slab_width, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B};
     const uint64_t strides[3] = {(uint64_t)p->ld_src * 2, (uint64_t)p->W * p->ld_src * 2, (uint64_t)p->H * p->W * p->ld_src * 2};
     const uint32_t box[4] = {64, (uint32_t)Cfg::HXP, (uint32_t)Cfg::HROWS, 1};
-    int rc = make_tmap_bf16(&tmA, reinterpret_cast<const bf16*>(p->src) + p->slab_offset, 4, dims, strides, box, true, "drdb_push(A)");
+    int rc = make_tmap_bf16(&tmA, reinterpret_cast<const bf16*>(p->src) + p->slab_offset, 4, dims, strides, box, true, "drdb_push(A)",
+                            p->slab_width == p->ld_src ? 256 : 64);   // a channel slab of wider rows: do not widen L2 misses
     if (rc) return rc;
   }
   {

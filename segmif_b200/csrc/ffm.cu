@@ -401,7 +401,8 @@ __device__ __forceinline__ void lerp_relu_tile(bf16* sDst, const LrSeg& L, int b
   const int64_t p = p0 + pixel;
   uint4 outv[4];
   if (p < HW) {
-    const int Y = (int)(p / L.W), X = (int)(p - (int64_t)Y * L.W);
+    const unsigned pu = (unsigned)p;                         // HW < 2^31 (checked by the host)
+    const int Y = (int)(pu / (unsigned)L.W), X = (int)(pu - (unsigned)Y * (unsigned)L.W);
     int y0, y1, x0, x1;
     float hy0, hy1, wx0, wx1;
     lr_src(Y, L.sy, L.h, y0, y1, hy0, hy1);
@@ -581,7 +582,7 @@ extern "C" int segmif_ffm_apply_fwd(const void* x1, int ld1, int coff1, const vo
 
 static int make_lrseg(LrSeg* L, const void* q3, int qh, int qw, int H, int W) {
   SEGMIF_REQUIRE(q3 && ((uintptr_t)q3 & 15) == 0, "ffm_lr: q3 must be a 16-byte aligned device pointer");
-  SEGMIF_REQUIRE(qh > 0 && qw > 0 && H > 0 && W > 0, "ffm_lr: bad sizes");
+  SEGMIF_REQUIRE(qh > 0 && qw > 0 && H > 0 && W > 0 && (int64_t)H * W < (1ll << 31), "ffm_lr: bad sizes");
   L->q = reinterpret_cast<const bf16*>(q3); L->h = qh; L->w = qw; L->H = H; L->W = W;
   L->sy = (float)qh / (float)H; L->sx = (float)qw / (float)W;
   return SEGMIF_OK;

@@ -106,10 +106,11 @@ __global__ void __launch_bounds__(kFfmTcThreads, 1) ffm_apply_tc_kernel(const __
     __syncwarp();
   } else if (warp == 1) {
     constexpr uint32_t idesc = tc::make_idesc_bf16(128, 64);
-    constexpr uint32_t HI = tc::desc_hi_sw128(1024);
+    constexpr uint64_t HI = (uint64_t)tc::desc_hi_sw128(1024) << 32;
     const bool leader = tc::elect_one();
     tc::mbar_wait(wfull, 0);
-    const uint32_t w_lo = smem_u32(sW) >> 4, m_lo = smem_u32(sM) >> 4, y_lo = smem_u32(sY) >> 4, u_lo = smem_u32(sU) >> 4;
+    uint64_t w_d = HI | (smem_u32(sW) >> 4), m_d = HI | (smem_u32(sM) >> 4), y_d = HI | (smem_u32(sY) >> 4), u_d = HI | (smem_u32(sU) >> 4);
+    asm volatile("" : "+l"(w_d), "+l"(m_d), "+l"(y_d), "+l"(u_d));   // opaque bases: offsets stay immediates of one UIADD3.64
     int it = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
       const int s = it & 1;
@@ -117,12 +118,13 @@ __global__ void __launch_bounds__(kFfmTcThreads, 1) ffm_apply_tc_kernel(const __
       tc::mbar_wait(xfull + s, (it >> 1) & 1);
       tc::tc_fence_after();
       if (leader) {
-        const uint32_t x_lo = smem_u32(sX + s * 2 * kTileBytes) >> 4;
+        uint64_t x_d = HI | (smem_u32(sX + s * 2 * kTileBytes) >> 4);
+        asm volatile("" : "+l"(x_d));
 #pragma unroll
         for (int st = 0; st < 2; ++st)
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            tc::umma_bf16_lohi(tmem_base + st * 64, x_lo + st * (kTileBytes >> 4) + k * 2, HI, w_lo + st * 512 + k * 2, HI, idesc, k > 0 ? 1u : 0u);
+            tc::umma_bf16(tmem_base + st * 64, x_d + (uint64_t)(st * (kTileBytes >> 4) + k * 2), w_d + (uint64_t)(st * 512 + k * 2), idesc, k > 0 ? 1u : 0u);
         tc::umma_commit(g1_full);
       }
       __syncwarp();
@@ -133,10 +135,10 @@ __global__ void __launch_bounds__(kFfmTcThreads, 1) ffm_apply_tc_kernel(const __
         for (int st = 0; st < 2; ++st) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)            // y3 Mz_s^T
-            tc::umma_bf16_lohi(tmem_base + 128 + st * 64, y_lo + k * 2, HI, m_lo + (2 * st) * 512 + k * 2, HI, idesc, k > 0 ? 1u : 0u);
+            tc::umma_bf16(tmem_base + 128 + st * 64, y_d + (uint64_t)(k * 2), m_d + (uint64_t)((2 * st) * 512 + k * 2), idesc, k > 0 ? 1u : 0u);
 #pragma unroll
           for (int k = 0; k < 4; ++k)            // + u_s Mv_s^T
-            tc::umma_bf16_lohi(tmem_base + 128 + st * 64, u_lo + st * (kTileBytes >> 4) + k * 2, HI, m_lo + (2 * st + 1) * 512 + k * 2, HI, idesc, 1u);
+            tc::umma_bf16(tmem_base + 128 + st * 64, u_d + (uint64_t)(st * (kTileBytes >> 4) + k * 2), m_d + (uint64_t)((2 * st + 1) * 512 + k * 2), idesc, 1u);
         }
         tc::umma_commit(g2_full);
       }
@@ -163,7 +165,8 @@ __global__ void __launch_bounds__(kFfmTcThreads, 1) ffm_apply_tc_kernel(const __
         const int64_t p = p0 + pixel;
         uint4 outv[4];
         if (p < a.HW) {
-          const int Y = (int)(p / a.W), X = (int)(p - (int64_t)Y * a.W);
+          const unsigned pu = (unsigned)p;                     // HW < 2^31 (checked by the host)
+          const int Y = (int)(pu / (unsigned)a.W), X = (int)(pu - (unsigned)Y * (unsigned)a.W);
           int y0, y1, x0, x1;
           float hy0, hy1, wx0, wx1;
           ffm_lr_src(Y, a.sy, a.qh, y0, y1, hy0, hy1);
@@ -295,6 +298,7 @@ extern "C" int segmif_ffm_apply_lr_fwd(const void* x1, int ld1, int coff1, const
   SEGMIF_REQUIRE((((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)q3 | (uintptr_t)wproj | (uintptr_t)folded | (uintptr_t)out1 | (uintptr_t)out2 |
                    (uintptr_t)bproj | (uintptr_t)bend | (uintptr_t)ln_gamma | (uintptr_t)ln_beta) & 15) == 0, "ffm_apply_lr: pointers must be 16-byte aligned");
   const int64_t HW = (int64_t)H * W;
+  SEGMIF_REQUIRE(HW < (1ll << 31), "ffm_apply_lr: H*W must be below 2^31");
   CUtensorMap tmX1, tmX2, tmW, tmM, tmO1, tmO2;
   int rc;
   if ((rc = make_px_map(&tmX1, x1, coff1, ld1, HW, B, "ffm_apply(x1)"))) return rc;

@@ -20,11 +20,13 @@ __global__ void __launch_bounds__(256) conv3x3_in1_kernel(const float* __restric
   const int64_t units = (int64_t)B * H * xblocks * cg_sets;
   const int64_t unit = (int64_t)blockIdx.x * 8 + warp_in_blk;
   if (unit >= units) return;
-  const int cset = (int)(unit % cg_sets);
-  const int64_t u2 = unit / cg_sets;
-  const int xb = (int)(u2 % xblocks);
-  const int y = (int)((u2 / xblocks) % H);
-  const int64_t b = u2 / ((int64_t)xblocks * H);
+  const unsigned uu = (unsigned)unit;                  // units < 2^31 (checked by the host): 32-bit divisions only
+  const int cset = (int)(uu % (unsigned)cg_sets);
+  const unsigned u2 = uu / (unsigned)cg_sets;
+  const int xb = (int)(u2 % (unsigned)xblocks);
+  const unsigned u3 = u2 / (unsigned)xblocks;
+  const int y = (int)(u3 % (unsigned)H);
+  const int64_t b = u3 / (unsigned)H;
   const int grp = cset * 8 + (lane & 7), q = lane >> 3;
   if ((lane & 7) >= gpw || grp >= ngroups) return;
   const int c = grp * 8;
@@ -78,8 +80,10 @@ __global__ void __launch_bounds__(256) conv3x3_out1_kernel(const bf16* __restric
   const int64_t npix = (int64_t)B * H * W;
   const bool live = pix < npix;
   const int64_t pp = live ? pix : 0;
-  const int X = (int)(pp % W), Y = (int)((pp / W) % H);
-  const int64_t b = pp / ((int64_t)W * H);
+  const unsigned pu = (unsigned)pp;                        // B*H*W < 2^31 (checked by the host)
+  const unsigned prow = pu / (unsigned)W;
+  const int X = (int)(pu - prow * (unsigned)W), Y = (int)(prow % (unsigned)H);
+  const int64_t b = prow / (unsigned)H;
   const int cpl = Cin >> 2;                 // channels per lane (multiple of 8)
   float acc = 0.f;
 #pragma unroll
@@ -173,6 +177,7 @@ extern "C" int segmif_conv3x3_in1_fwd(const float* plane, int64_t bstride, const
   SEGMIF_REQUIRE(Cout % 8 == 0 && ld_dst % 8 == 0 && dst_coff % 8 == 0, "conv3x3_in1: channel counts must be multiples of 8");
   const int64_t units = (int64_t)B * H * ((W + 15) / 16) * ((Cout / 8 + 7) / 8);     // one warp each
   if (units == 0) return SEGMIF_OK;
+  SEGMIF_REQUIRE(units < (1ll << 31), "conv3x3_in1: too many pixel blocks for the 32-bit unit index");
   conv3x3_in1_kernel<<<(unsigned)ceil_div(units, 8), 256, 0, as_stream(stream)>>>(
       plane, bstride, w, bias, prelu_alpha, (bf16*)dst, ld_dst, dst_coff, B, H, W, Cout);
   return check_launch("segmif_conv3x3_in1_fwd");
@@ -183,6 +188,7 @@ extern "C" int segmif_conv3x3_out1_fwd(const void* src, int ld_src, const float*
                                        segmif_stream_t stream) {
   SEGMIF_REQUIRE(src && w && bias && prelu_alpha && dst, "conv3x3_out1: null pointer");
   SEGMIF_REQUIRE(Cin % 32 == 0 && ld_src % 8 == 0, "conv3x3_out1: Cin must be a multiple of 32");
+  SEGMIF_REQUIRE((int64_t)B * H * W < (1ll << 31), "conv3x3_out1: B*H*W must be below 2^31");
   const int64_t total = (int64_t)B * H * W * 4;
   if (total == 0) return SEGMIF_OK;
   conv3x3_out1_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, as_stream(stream)>>>(

@@ -25,7 +25,7 @@ EncodeTiledFn get_encode_tiled() {
 }
 
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                   const uint32_t* box, bool swizzle128, const char* what) {
+                   const uint32_t* box, bool swizzle128, const char* what, int l2_promotion_bytes) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return SEGMIF_ERR_CUDA;
   cuuint64_t gd[5], gs[5];
@@ -33,7 +33,10 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   l2_promotion_bytes >= 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                   : l2_promotion_bytes >= 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                   : l2_promotion_bytes >= 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_NONE,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("%s: cuTensorMapEncodeTiled failed (CUresult %d)", what, (int)r);
@@ -156,7 +159,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
     __syncwarp();
   } else if (warp == 1) {
     constexpr uint32_t idesc = tc::make_idesc_bf16(128, BN);
-    constexpr uint32_t HI = tc::desc_hi_sw128(1024);
+    constexpr uint64_t HI = (uint64_t)tc::desc_hi_sw128(1024) << 32;
     const bool leader = tc::elect_one();
     int it = 0, lt = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
@@ -169,10 +172,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         tc::mbar_wait(full + s, (it / kTcStages) & 1);
         tc::tc_fence_after();
         if (leader) {
-          const uint32_t a_lo = smem_u32(sA + s * A_BYTES) >> 4, b_lo = smem_u32(sB + s * B_BYTES) >> 4;
+          uint64_t a_d = HI | (uint64_t)(smem_u32(sA + s * A_BYTES) >> 4), b_d = HI | (uint64_t)(smem_u32(sB + s * B_BYTES) >> 4);
+          asm volatile("" : "+l"(a_d), "+l"(b_d));     // opaque bases: k offsets stay immediates of one UIADD3.64 each
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            tc::umma_bf16_lohi(acc, a_lo + k * 2, HI, b_lo + k * 2, HI, idesc, (kb | k) != 0 ? 1u : 0u);
+            tc::umma_bf16(acc, a_d + (uint64_t)(k * 2), b_d + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
           tc::umma_commit(empty + s);          // frees the smem stage when these MMAs have read it
         }
         __syncwarp();

@@ -128,40 +128,39 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return 0.5f * x * (1.0f + copysignf(erf_abs, x));
 }
 
-// thread = (pixel, 8-channel group); neighbours come through L1/L2 (each input line is reused 9x).  (A two-pixel
+// thread = (pixel, 8-channel group); neighbours come through L1/L2 (each input line is reused 9x).  grid = (chunks of
+// one image row, H, B) so that every index is 32-bit: the first version decomposed a flat 64-bit index with four 64-bit
+// divisions per thread (12 CALLs, 1144 SASS instructions, 78% issue-bound at 151 us for the stage-1 map).  (A two-pixel
 // sliding window with the weights in registers was tried: 118 registers, lower occupancy, 1.5x slower.)
 __global__ void __launch_bounds__(256) dwconv3x3_gelu_kernel(const bf16* __restrict__ x, const float* __restrict__ w,
                                                              const float* __restrict__ bias, bf16* __restrict__ y,
-                                                             int B, int H, int W, int C) {
-  const int cg = C >> 3;
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t total = (int64_t)B * H * W * cg;
-  if (idx >= total) return;
-  const int c = (int)(idx % cg) * 8;
-  const int64_t pix = idx / cg;
-  const int xw = (int)(pix % W);
-  const int yh = (int)((pix / W) % H);
-  const int64_t b = pix / ((int64_t)W * H);
+                                                             int H, int W, int C) {
+  const unsigned cg = (unsigned)C >> 3;
+  const unsigned t = blockIdx.x * 256u + threadIdx.x;
+  if (t >= (unsigned)W * cg) return;
+  const unsigned xw = t / cg;
+  const int c = (int)(t - xw * cg) * 8;
+  const int yh = blockIdx.y;
+  const unsigned ctr = ((blockIdx.z * (unsigned)H + yh) * (unsigned)W + xw) * (unsigned)C + c;   // element index of the centre tap
+  const int rs = W * C;                                            // row stride in elements
   float acc[8];
   load8(bias + c, acc);
 #pragma unroll
   for (int ky = 0; ky < 3; ++ky) {
-    const int iy = yh + ky - 1;
-    if ((unsigned)iy >= (unsigned)H) continue;
+    if ((unsigned)(yh + ky - 1) >= (unsigned)H) continue;
 #pragma unroll
     for (int kx = 0; kx < 3; ++kx) {
-      const int ix = xw + kx - 1;
-      if ((unsigned)ix >= (unsigned)W) continue;
+      if (xw + kx - 1 >= (unsigned)W) continue;                    // unsigned wrap covers xw + kx - 1 < 0
       float v[8], wv[8];
-      load8(x + ((b * H + iy) * W + ix) * C + c, v);
-      load8(w + (ky * 3 + kx) * C + c, wv);
+      load8(x + (ctr + (unsigned)((ky - 1) * rs + (kx - 1) * C)), v);
+      load8(w + (unsigned)((ky * 3 + kx) * C + c), wv);
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] = fmaf(v[j], wv[j], acc[j]);
     }
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = gelu_fast(acc[j]);
-  store8(y + pix * C + c, acc);
+  store8(y + ctr, acc);
 }
 
 // ------------------------------------------------------------------------------------ patch embed 7x7 s4 + LN
@@ -384,10 +383,10 @@ extern "C" int segmif_dwconv3x3_gelu_fwd(const void* x, const float* w9c, const 
                                          int W, int C, segmif_stream_t stream) {
   SEGMIF_REQUIRE(x && w9c && bias && y, "dwconv: null pointer");
   SEGMIF_REQUIRE(C % 8 == 0, "dwconv: C=%d must be a multiple of 8", C);
-  const int64_t total = (int64_t)B * H * W * (C / 8);
-  if (total == 0) return SEGMIF_OK;
-  dwconv3x3_gelu_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, as_stream(stream)>>>(
-      (const bf16*)x, w9c, bias, (bf16*)y, B, H, W, C);
+  if ((int64_t)B * H * W == 0) return SEGMIF_OK;
+  SEGMIF_REQUIRE((int64_t)B * H * W * C < (1ll << 32) && H <= 65535 && B <= 65535, "dwconv: tensor of %d x %d x %d x %d elements exceeds the 32-bit element index", B, H, W, C);
+  dim3 grid((unsigned)ceil_div((int64_t)W * (C / 8), 256), (unsigned)H, (unsigned)B);
+  dwconv3x3_gelu_kernel<<<grid, 256, 0, as_stream(stream)>>>((const bf16*)x, w9c, bias, (bf16*)y, H, W, C);
   return check_launch("segmif_dwconv3x3_gelu_fwd");
 }
 

@@ -379,142 +379,7 @@ __global__ void __launch_bounds__(kFfmThreads) ffm_apply_kernel(
 // encoder's resolution ([B, h, w, 128] bf16, 39 MB / 10 MB at cfg 2: L2 resident).  The *_lr kernels interpolate Q on the
 // fly instead of projecting a materialised full-resolution feature map: the third projection GEMM of both passes, the
 // 0.9 GB of upsampled features and their upsample kernel all disappear.  Q channels: [0,64) = y3 half, [64,128) = u3.
-struct LrSeg {
-  const bf16* q;      // [B, h, w, 128]
-  int h, w, H, W;
-  float sy, sx;       // h/H, w/W (ATen's align_corners=False scales)
-};
-
-__device__ __forceinline__ void lr_src(int dst, float scale, int in_size, int& i0, int& i1, float& l0, float& l1) {
-  float s = scale * ((float)dst + 0.5f) - 0.5f;
-  s = s < 0.f ? 0.f : s;
-  i0 = (int)s;
-  if (i0 > in_size - 1) i0 = in_size - 1;
-  i1 = i0 + ((i0 < in_size - 1) ? 1 : 0);
-  l1 = s - (float)i0;
-  l0 = 1.f - l1;
-}
-
-// sDst[64 px][64 ch] (bf16, swizzled) = relu(bilerp(Q[b][.., coff..coff+64))) for pixels p0..p0+63 of image b
-__device__ __forceinline__ void lerp_relu_tile(bf16* sDst, const LrSeg& L, int b, int coff, int64_t p0, int64_t HW, int tid) {
-  const int pixel = tid >> 1, half = tid & 1;
-  const int64_t p = p0 + pixel;
-  uint4 outv[4];
-  if (p < HW) {
-    const unsigned pu = (unsigned)p;                         // HW < 2^31 (checked by the host)
-    const int Y = (int)(pu / (unsigned)L.W), X = (int)(pu - (unsigned)Y * (unsigned)L.W);
-    int y0, y1, x0, x1;
-    float hy0, hy1, wx0, wx1;
-    lr_src(Y, L.sy, L.h, y0, y1, hy0, hy1);
-    lr_src(X, L.sx, L.w, x0, x1, wx0, wx1);
-    const bf16* base = L.q + (int64_t)b * L.h * L.w * 128 + coff + half * 32;
-    const bf16* p00 = base + ((int64_t)y0 * L.w + x0) * 128;
-    const bf16* p01 = base + ((int64_t)y0 * L.w + x1) * 128;
-    const bf16* p10 = base + ((int64_t)y1 * L.w + x0) * 128;
-    const bf16* p11 = base + ((int64_t)y1 * L.w + x1) * 128;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      float a[8], bq[8], cc[8], d[8], o[8];
-      load8(p00 + c * 8, a); load8(p01 + c * 8, bq); load8(p10 + c * 8, cc); load8(p11 + c * 8, d);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = fmaxf(hy0 * (wx0 * a[j] + wx1 * bq[j]) + hy1 * (wx0 * cc[j] + wx1 * d[j]), 0.f);
-      outv[c] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
-    }
-  } else {
-#pragma unroll
-    for (int c = 0; c < 4; ++c) outv[c] = make_uint4(0, 0, 0, 0);
-  }
-#pragma unroll
-  for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(sDst + pixel * 64 + swz128(pixel, half * 4 + c) * 8) = outv[c];
-}
-
-__global__ void __launch_bounds__(kFfmThreads) ffm_gram_lr_kernel(const bf16* __restrict__ x1, int ld1,
-                                                                  const bf16* __restrict__ x2, int ld2, const LrSeg L,
-                                                                  const bf16* __restrict__ wproj,
-                                                                  const float* __restrict__ bproj,
-                                                                  float* __restrict__ partials, int64_t HW) {
-  extern __shared__ __align__(128) uint8_t smem_raw[];
-  bf16* sW = reinterpret_cast<bf16*>(smem_raw);            // [w1y 64x64][w2y 64x64]
-  bf16* sX = sW + 2 * 4096;                                // [64 px][64]
-  bf16* sP = sX + kTilePx * 64;                            // [64 px][64]
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int b = blockIdx.y, chunk_id = blockIdx.x, nchunk = gridDim.x;
-  for (int i = tid; i < 2 * 64 * 8; i += kFfmThreads) {
-    const int m = i >> 9, row = (i >> 3) & 63, chunk = i & 7;
-    cp_async16_cg(smem_u32(sW + m * 4096 + row * 64 + swz128(row, chunk) * 8), wproj + m * 4096 + row * 64 + chunk * 8, 16);
-  }
-  cp_async_commit();
-  float gacc[3][8][4];
-#pragma unroll
-  for (int s = 0; s < 3; ++s)
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) gacc[s][i][j] = 0.f;
-  const int64_t ntiles = (HW + kTilePx - 1) / kTilePx;
-  const int g = lane >> 2, tq = lane & 3;
-  for (int64_t t = chunk_id; t < ntiles; t += nchunk) {
-    const int64_t p0 = t * kTilePx;
-#pragma unroll
-    for (int s = 0; s < 3; ++s) {
-      __syncthreads();                                  // previous users of sX / sP are done
-      if (s < 2) {
-        const bf16* xs = (s == 0 ? x1 : x2) + (int64_t)b * HW * (s == 0 ? ld1 : ld2);
-        load_rows_async(sX, xs, p0, HW, s == 0 ? ld1 : ld2, 64, kTilePx, tid);
-        cp_async_commit();
-        cp_async_wait<0>();
-        __syncthreads();
-        float acc[8][4];
-        proj16x64(acc, sX, 64, warp * 16, sW + s * 4096, lane);
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const int row = warp * 16 + g + half * 8;
-          const bool live = (p0 + row) < HW;
-#pragma unroll
-          for (int nt = 0; nt < 8; ++nt) {
-            const int ch = nt * 8 + tq * 2;
-            float v0 = fmaxf(acc[nt][half * 2] + bproj[s * 64 + ch], 0.f);
-            float v1 = fmaxf(acc[nt][half * 2 + 1] + bproj[s * 64 + ch + 1], 0.f);
-            if (!live) { v0 = 0.f; v1 = 0.f; }
-            *reinterpret_cast<uint32_t*>(sP + row * 64 + swz128(row, nt) * 8 + tq * 2) = pack_bf16x2(v0, v1);
-          }
-        }
-      } else {
-        lerp_relu_tile(sP, L, b, 64, p0, HW, tid);      // u3 = relu(upsample(Q)[64:128]); rows past the image are zero
-      }
-      __syncthreads();
-#pragma unroll
-      for (int ks = 0; ks < kTilePx / 16; ++ks) {
-        uint32_t af[4];
-        {
-          const int row = ks * 16 + (lane & 7) + ((lane >> 4) << 3), chunk = warp * 2 + ((lane >> 3) & 1);
-          ldmatrix_x4_trans(af, smem_u32(sP + row * 64 + swz128(row, chunk) * 8));
-        }
-#pragma unroll
-        for (int np = 0; np < 4; ++np) {
-          uint32_t bfr[4];
-          const int row = ks * 16 + (lane & 7) + (((lane >> 3) & 1) << 3), chunk = np * 2 + (lane >> 4);
-          ldmatrix_x4_trans(bfr, smem_u32(sP + row * 64 + swz128(row, chunk) * 8));
-          mma_bf16_16816(gacc[s][np * 2], af, bfr[0], bfr[1]);
-          mma_bf16_16816(gacc[s][np * 2 + 1], af, bfr[2], bfr[3]);
-        }
-      }
-    }
-  }
-  cp_async_wait<0>();
-  float* out = partials + ((int64_t)b * nchunk + chunk_id) * 3 * 4096;
-#pragma unroll
-  for (int s = 0; s < 3; ++s)
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int i = warp * 16 + g + half * 8, j = nt * 8 + tq * 2;
-        *reinterpret_cast<float2*>(out + s * 4096 + i * 64 + j) = make_float2(gacc[s][nt][half * 2], gacc[s][nt][half * 2 + 1]);
-      }
-}
-
-// (pass 3 of the low-resolution form runs on tcgen05: ffm_tc.cu)
+// Both *_lr passes run on tcgen05 tensor cores: ffm_tc.cu.
 
 // one-time opt-in to the largest configuration of each kernel (never called again, e.g. during graph capture)
 static int set_smem(const void* fn, size_t bytes, const char* what, bool* done) {
@@ -578,28 +443,4 @@ extern "C" int segmif_ffm_apply_fwd(const void* x1, int ld1, int coff1, const vo
       (const bf16*)x1 + coff1, ld1, (const bf16*)x2 + coff2, ld2, (const bf16*)x3, ld3, C3, (const bf16*)wproj, bproj,
       (const bf16*)folded, bend, ln_gamma, ln_beta, eps, (bf16*)out1 + coffo1, ldo1, (bf16*)out2 + coffo2, ldo2, HW);
   return check_launch("segmif_ffm_apply_fwd");
-}
-
-static int make_lrseg(LrSeg* L, const void* q3, int qh, int qw, int H, int W) {
-  SEGMIF_REQUIRE(q3 && ((uintptr_t)q3 & 15) == 0, "ffm_lr: q3 must be a 16-byte aligned device pointer");
-  SEGMIF_REQUIRE(qh > 0 && qw > 0 && H > 0 && W > 0 && (int64_t)H * W < (1ll << 31), "ffm_lr: bad sizes");
-  L->q = reinterpret_cast<const bf16*>(q3); L->h = qh; L->w = qw; L->H = H; L->W = W;
-  L->sy = (float)qh / (float)H; L->sx = (float)qw / (float)W;
-  return SEGMIF_OK;
-}
-
-extern "C" int segmif_ffm_gram_lr_fwd(const void* x1, int ld1, int coff1, const void* x2, int ld2, int coff2,
-                                      const void* q3, int qh, int qw, int H, int W, const void* wproj,
-                                      const float* bproj, float* partials, int nchunk, int B, segmif_stream_t stream) {
-  SEGMIF_REQUIRE(x1 && x2 && wproj && bproj && partials, "ffm_gram_lr: null pointer");
-  SEGMIF_REQUIRE(ld1 % 8 == 0 && ld2 % 8 == 0 && coff1 % 8 == 0 && coff2 % 8 == 0, "ffm_gram_lr: pitches/offsets must be multiples of 8");
-  SEGMIF_REQUIRE(nchunk > 0 && B > 0, "ffm_gram_lr: bad sizes");
-  LrSeg L;
-  int rc = make_lrseg(&L, q3, qh, qw, H, W);
-  if (rc) return rc;
-  const size_t smem = (size_t)(2 * 4096 + 2 * kTilePx * 64) * sizeof(bf16);
-  dim3 grid(nchunk, B);
-  ffm_gram_lr_kernel<<<grid, kFfmThreads, smem, as_stream(stream)>>>((const bf16*)x1 + coff1, ld1, (const bf16*)x2 + coff2, ld2, L,
-                                                                      (const bf16*)wproj, bproj, partials, (int64_t)H * W);
-  return check_launch("segmif_ffm_gram_lr_fwd");
 }

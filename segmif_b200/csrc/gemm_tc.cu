@@ -56,8 +56,25 @@ struct TcEpilogue {
 // one output row (this thread) x 32 columns starting at n.  `slope`: act(v) = v >= 0 ? v : slope*v covers none (1),
 // ReLU (0) and PReLU (alpha) without branches; GELU is a separate template flag so that its 32 inlined erf bodies do
 // not bloat the common instantiation (the epilogue has to stay in the instruction cache).
+// The residual row segment (32 values) is fetched into registers ahead of the accumulator it is added to: issued before
+// the wait on the MMA barrier / while the previous 32 columns are processed, so its L2 / HBM latency is off the critical
+// path (ncu before: long-scoreboard 10.6 stalls per issue in the DRDB 1x1 launch, the epilogue waiting on these loads).
+struct ResRow32 { uint4 q[8]; };
+__device__ __forceinline__ void load_res_row32(const TcEpilogue& e, ResRow32& r, int64_t m, int n) {
+  const int64_t ro = m * e.ld_res + e.res_coff + n;
+  if (e.res_dtype == SEGMIF_F32) {
+    const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(e.res) + ro);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r.q[j] = p[j];
+  } else {
+    const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(e.res) + ro);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) r.q[j] = p[j];
+  }
+}
+
 template <bool GELU>
-__device__ __forceinline__ void epilogue_row32(const TcEpilogue& e, float (&v)[32], int64_t m, int n, float slope) {
+__device__ __forceinline__ void epilogue_row32(const TcEpilogue& e, float (&v)[32], const ResRow32& rr, int64_t m, int n, float slope) {
   if (e.bias) {
     const float4* bp = reinterpret_cast<const float4*>(e.bias + n);
 #pragma unroll
@@ -74,16 +91,16 @@ __device__ __forceinline__ void epilogue_row32(const TcEpilogue& e, float (&v)[3
     for (int j = 0; j < 32; ++j) v[j] = v[j] >= 0.f ? v[j] : slope * v[j];
   }
   if (e.res) {
-    const int64_t ro = m * e.ld_res + e.res_coff + n;
     if (e.res_dtype == SEGMIF_F32) {
-      const float4* r = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(e.res) + ro);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { const float4 t = r[j]; v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w; }
+      for (int j = 0; j < 8; ++j) {
+        const uint4 t = rr.q[j];
+        v[4 * j] += __uint_as_float(t.x); v[4 * j + 1] += __uint_as_float(t.y); v[4 * j + 2] += __uint_as_float(t.z); v[4 * j + 3] += __uint_as_float(t.w);
+      }
     } else {
-      const uint4* r = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(e.res) + ro);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const uint4 t = r[j];
+        const uint4 t = rr.q[j];
         const float2 a = unpack_bf16x2(t.x), b = unpack_bf16x2(t.y), c = unpack_bf16x2(t.z), d = unpack_bf16x2(t.w);
         v[8 * j] += a.x; v[8 * j + 1] += a.y; v[8 * j + 2] += b.x; v[8 * j + 3] += b.y;
         v[8 * j + 4] += c.x; v[8 * j + 5] += c.y; v[8 * j + 6] += d.x; v[8 * j + 7] += d.y;
@@ -191,14 +208,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
       const int buf = lt & 1;
       const int m0 = (tile / n_tiles) * 128, n0 = (tile % n_tiles) * BN;
+      const int64_t m = (int64_t)m0 + quad * 32 + lane;
+      const bool has_res = e.res != nullptr && m < e.M;
+      ResRow32 cur, nxt;
+      if (has_res && n0 < e.N) load_res_row32(e, cur, m, n0);          // in flight while the MMAs of this tile finish
       tc::mbar_wait(tmem_full + buf, (lt >> 1) & 1);
       tc::tc_fence_after();
-      const int64_t m = (int64_t)m0 + quad * 32 + lane;
 #pragma unroll 1
       for (int c = 0; c < BN; c += 32) {
+        if (has_res && c + 32 < BN && (n0 + c + 32) < e.N) load_res_row32(e, nxt, m, n0 + c + 32);
         float v[32];
         tc::tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN + c), v);   // warp-collective
-        if (m < e.M && (n0 + c) < e.N) epilogue_row32<GELU>(e, v, m, n0 + c, slope);
+        if (m < e.M && (n0 + c) < e.N) epilogue_row32<GELU>(e, v, cur, m, n0 + c, slope);
+        cur = nxt;
       }
       tc::tc_fence_before();
       __syncwarp();

@@ -145,17 +145,30 @@ __global__ void __launch_bounds__(256) dwconv3x3_gelu_kernel(const bf16* __restr
   const int rs = W * C;                                            // row stride in elements
   float acc[8];
   load8(bias + c, acc);
+  if (yh >= 1 && yh + 1 < H && xw >= 1 && xw + 1 < (unsigned)W) {       // interior pixel: nine unconditional taps
 #pragma unroll
-  for (int ky = 0; ky < 3; ++ky) {
-    if ((unsigned)(yh + ky - 1) >= (unsigned)H) continue;
+    for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-    for (int kx = 0; kx < 3; ++kx) {
-      if (xw + kx - 1 >= (unsigned)W) continue;                    // unsigned wrap covers xw + kx - 1 < 0
-      float v[8], wv[8];
-      load8(x + (ctr + (unsigned)((ky - 1) * rs + (kx - 1) * C)), v);
-      load8(w + (unsigned)((ky * 3 + kx) * C + c), wv);
+      for (int kx = 0; kx < 3; ++kx) {
+        float v[8], wv[8];
+        load8(x + (ctr + (unsigned)((ky - 1) * rs + (kx - 1) * C)), v);
+        load8(w + (unsigned)((ky * 3 + kx) * C + c), wv);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = fmaf(v[j], wv[j], acc[j]);
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(v[j], wv[j], acc[j]);
+      }
+  } else {
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      if ((unsigned)(yh + ky - 1) >= (unsigned)H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        if (xw + kx - 1 >= (unsigned)W) continue;                    // unsigned wrap covers xw + kx - 1 < 0
+        float v[8], wv[8];
+        load8(x + (ctr + (unsigned)((ky - 1) * rs + (kx - 1) * C)), v);
+        load8(w + (unsigned)((ky * 3 + kx) * C + c), wv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(v[j], wv[j], acc[j]);
+      }
     }
   }
 #pragma unroll

@@ -310,13 +310,23 @@ def ffm(x1, ld1, coff1, x2, ld2, coff2, x3, ld3, C3, packs, out1, ldo1, coffo1, 
     return ctx
 
 
+_SM_COUNT = {}
+
+
+def _sm_count(dev):
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    if idx not in _SM_COUNT:
+        _SM_COUNT[idx] = torch.cuda.get_device_properties(idx).multi_processor_count
+    return _SM_COUNT[idx]
+
+
 def ffm_lr(x1, ld1, coff1, x2, ld2, coff2, q3, qh, qw, H, W, packs, out1, ldo1, coffo1, out2, ldo2, coffo2, B):
     """Hierarchical interactive attention with the seg stream given as the low-resolution pre-activation Q
     (bf16 [B, qh, qw, 128]); `packs` from CrossPath.packs_lr."""
     st = _prep(x1, x2, q3, out1, out2)
     dev = x1.device
     HW = H * W
-    nchunk = max(1, min((148 * 4) // max(B, 1), (HW + 63) // 64))
+    nchunk = max(1, min(_sm_count(dev) // max(B, 1), (HW + 127) // 128))     # one persistent CTA per SM, 128-pixel tiles
     partials = torch.empty((B, nchunk, 3, 64, 64), dtype=torch.float32, device=dev)
     folded = torch.empty((B, 4, 64, 64), dtype=torch.bfloat16, device=dev)
     ctx = torch.empty((B, 3, 8, 8, 8), dtype=torch.float32, device=dev)

@@ -243,6 +243,94 @@ int segmif_mse_l1_fwd(const float* x, const float* y, int64_t n, float* workspac
 int segmif_upsample_ce_fwd(const float* logits, int B, int h, int w, int nc, const int64_t* labels, int H, int W,
                            int ignore_index, float* workspace, float* out, segmif_stream_t stream);
 
+/* ============================================================================================================
+ * Training side (train.py:266-413, train_fusion): gradients of the fusion losses and of Fusion_Network3_ac.
+ * The reference obtains all of these from torch.autograd over the implicit ATen/cuDNN backward kernels; each
+ * entry point below replaces the autograd node named in its comment.  Gradients of activations are bf16
+ * pixel-major slices (ld / coff as in the forward); parameter gradients are ACCUMULATED (+=) in fp32 straight
+ * into caller-provided buffers (the .grad tensors or a flat gradient buffer), so a module applied twice (ffm)
+ * needs no extra pass.  `gout*` arguments are DEVICE scalars/vectors holding the upstream gradient(s).
+ * ============================================================================================================ */
+
+/* ---- loss backward: gradient w.r.t. the FIRST image argument, fp32 [B,1,H,W]; accumulate != 0 adds into dx.
+ * mse_l1   F.mse_loss / F.l1_loss backward (core/loss.py:511-517, :464-476); gout2 = {d/d mse, d/d l1}
+ * sobel_l1 Fusionloss3 (core/loss.py:464-476 with Sobelxy :634-650); gout2 = {d/d l1, d/d sobel-l1}
+ * ssim     pytorch_ssim/__init__.py:19-43 backward; gout = 1 value (size_average) or B values (per_image)
+ * laploss2 / laploss  lap_loss.py:112-118 / :93-98 backward;  entropy  core/Entropy.py:15-56 backward           */
+int segmif_mse_l1_bwd(const float* x, const float* y, int64_t n, const float* gout2, float* dx, int accumulate,
+                      segmif_stream_t stream);
+int segmif_sobel_l1_bwd(const float* x, const float* y, int B, int H, int W, const float* gout2, float* dx,
+                        int accumulate, segmif_stream_t stream);
+int segmif_ssim_bwd(const float* img1, const float* img2, int B, int H, int W, int per_image, const float* gout,
+                    float* dimg1, int accumulate, segmif_stream_t stream);
+int segmif_laploss2_bwd(const float* inp, const float* ir, const float* vis, int B, int H, int W, const float* gout,
+                        float* dinp, int accumulate, segmif_stream_t stream);
+int segmif_laploss_bwd(const float* inp, const float* target, int B, int H, int W, const float* gout, float* dinp,
+                       int accumulate, segmif_stream_t stream);
+int segmif_entropy_bwd(const float* img, int B, int H, int W, int patch, const float* gout, float* dimg, int accumulate,
+                       segmif_stream_t stream);
+
+/* ---- activation backward from the layer OUTPUT y (F.relu core/model_fusion.py:135-156; the shared nn.PReLU
+ * :1038,1051-1065, slope must be > 0):  dz = dy * f'(y);  dbias[c] += sum_p dz[p][c];  dalpha += sum dy * z [z<=0].
+ * dbias / dalpha may be NULL.  C % 8 == 0, C <= 256.                                                             */
+int segmif_act_bwd(const void* y, int ldy, int coffy, const void* dy, int lddy, int coffdy, void* dz, int lddz,
+                   int coffdz, int64_t rows, int C, int act, const float* prelu_alpha, float* dbias, float* dalpha,
+                   segmif_stream_t stream);
+/* conv22's output plane (core/model_fusion.py:1065): out = prelu(z) fp32 [n], dout fp32 -> dz bf16 at channel
+ * coffdz of a pixel-major [n, lddz] tensor (the other channels are left untouched).                              */
+int segmif_prelu_plane_bwd(const float* out, const float* dout, int64_t n, const float* prelu_alpha, void* dz, int lddz,
+                           int coffdz, float* dbias, float* dalpha, segmif_stream_t stream);
+/* out[c] += sum_p x[p][coff + c] (bias gradients); out = a + b on bf16 slices (DRDB residual, :156). */
+int segmif_colsum(const void* x, int ld, int coff, int64_t rows, int C, float* out, segmif_stream_t stream);
+int segmif_add_bf16(const void* a, int lda, int coffa, const void* b, int ldb, int coffb, void* out, int ldo, int coffo,
+                    int64_t rows, int C, segmif_stream_t stream);
+
+/* ---- nn.LayerNorm backward (CrossPath.norm1/2 core/model_fusion.py:347-348,360-361; MiT norms later).
+ * x = the LayerNorm INPUT [rows, C] dense; dy, dx pixel-major slices.  dgamma / dbeta / dxsum (column sums of dx,
+ * = the gradient of a bias added right before the norm) are accumulated; any may be NULL.  C in {64,128,320,512}. */
+int segmif_layernorm_bwd(const void* x, int x_dtype, const void* dy, int dy_dtype, int lddy, int coffdy,
+                         const float* gamma, float eps, void* dx, int dx_dtype, int lddx, int coffdx, int64_t rows, int C,
+                         float* dgamma, float* dbeta, float* dxsum, segmif_stream_t stream);
+
+/* ---- weight gradient of nn.Conv2d (3x3, stride 1, 'same', dilation 1|2: DRDB Dcov1-5, conv1/2/21/22) and of
+ * nn.Linear / 1x1 conv (taps = 1; pass B = 1, W = 16, H = ceil(P/16)) as one tensor-core contraction over all pixels:
+ *   grad[co*s_co + tap*s_tap + ci*s_ci] += sum_p dy[p][coffy+co] * x[p + tap][coffx+ci]      co < co_take, ci < ci_take
+ * dy bf16 [P, ldy], x bf16 [B,H,W,ldx]; Cout % 32 == 0, Cin % 8 == 0; workspace: segmif_wgrad_workspace_bytes().   */
+size_t segmif_wgrad_workspace_bytes(int nchunk, int Cout, int taps, int Cin);
+int segmif_wgrad(const void* dy, int ldy, int coffy, const void* x, int ldx, int coffx, int B, int H, int W, int64_t P,
+                 int Cin, int Cout, int taps, int dil, float* workspace, int nchunk, float* grad, int64_t s_co,
+                 int64_t s_tap, int64_t s_ci, int co_take, int ci_take, segmif_stream_t stream);
+
+/* ---- K13 backward (FeatureFusionModule / CrossPath, core/model_fusion.py:350-361, :263-288, :303-328).
+ * Training forward = segmif_ffm_gram_fwd + segmif_ffm_ctx_fwd + segmif_ffm_apply_train_fwd, which also writes the
+ * LayerNorm inputs pre1 / pre2 (bf16 [B*HW, 64]).  Backward, with dr_i = segmif_layernorm_bwd(pre_i, dout_i):
+ *  bwd_gram : fp32 partials [B, nchunk, 4, 64, 64] of dr1^T y3, dr1^T u1, dr2^T y3, dr2^T u2;
+ *  bwd_ctx  : per image: dwend [2][64][128] and dwkv [3][128][64] (fp32, accumulated), and mats bf16 [B,7,64,64] =
+ *             {S1, S2, S3, Mz1^T, Mv1^T, Mz2^T, Mv2^T} with S_s = dG_s + dG_s^T;
+ *  bwd_apply: dP1, dP2, dP3 bf16 [B*HW, 128] = gradients of the channel_proj1/2/3 pre-activations.
+ * wfull bf16 [3][128][64] / bfull fp32 [3][128]: channel_proj1|2|3 weight and bias; x3 has 64 channels.           */
+int segmif_ffm_apply_train_fwd(const void* x1, int ld1, int coff1, const void* x2, int ld2, int coff2, const void* x3,
+                               int ld3, int C3, const void* wproj, const float* bproj, const void* folded,
+                               const float* bend, const float* ln_gamma, const float* ln_beta, float eps, void* out1,
+                               int ldo1, int coffo1, void* out2, int ldo2, int coffo2, int B, int64_t HW, void* pre1,
+                               void* pre2, segmif_stream_t stream);
+int segmif_ffm_bwd_gram(const void* x1, int ld1, int coff1, const void* x2, int ld2, int coff2, const void* x3, int ld3,
+                        int coff3, const void* dr1, const void* dr2, const void* wfull, const float* bfull,
+                        float* partials, int nchunk, int B, int64_t HW, segmif_stream_t stream);
+int segmif_ffm_bwd_ctx(const float* r_partials, int nchunk_r, const float* g_partials, int nchunk_g, const float* ctx,
+                       const float* wkv, const float* wend, const void* folded, void* mats, float* dwkv, float* dwend,
+                       int B, segmif_stream_t stream);
+int segmif_ffm_bwd_apply(const void* x1, int ld1, int coff1, const void* x2, int ld2, int coff2, const void* x3, int ld3,
+                         int coff3, const void* dr1, const void* dr2, const void* wfull, const float* bfull,
+                         const void* mats, void* dP1, void* dP2, void* dP3, int B, int64_t HW, segmif_stream_t stream);
+
+/* ---- fused AdamW step over a flat fp32 buffer (utils/optimizer.py:16-33 -> torch.optim.AdamW.step):
+ * g = grad * grad_scale (1/world_size after the gradient all-reduce); p *= 1 - lr*wd; Adam moments with bias
+ * correction for 1-based `step`.                                                                                   */
+int segmif_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                      float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                      segmif_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

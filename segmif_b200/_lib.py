@@ -94,8 +94,28 @@ SIGNATURES = {
     "segmif_sobel_l1_fwd": [P, P, c_int, c_int, c_int, P, P, P],
     "segmif_mse_l1_fwd": [P, P, c_int64, P, P, P],
     "segmif_upsample_ce_fwd": [P, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, P, P, P],
+    "segmif_mse_l1_bwd": [P, P, c_int64, P, P, c_int, P],
+    "segmif_sobel_l1_bwd": [P, P, c_int, c_int, c_int, P, P, c_int, P],
+    "segmif_ssim_bwd": [P, P, c_int, c_int, c_int, c_int, P, P, c_int, P],
+    "segmif_laploss2_bwd": [P, P, P, c_int, c_int, c_int, P, P, c_int, P],
+    "segmif_laploss_bwd": [P, P, c_int, c_int, c_int, P, P, c_int, P],
+    "segmif_entropy_bwd": [P, c_int, c_int, c_int, c_int, P, P, c_int, P],
+    "segmif_act_bwd": [P, c_int, c_int, P, c_int, c_int, P, c_int, c_int, c_int64, c_int, c_int, P, P, P, P],
+    "segmif_prelu_plane_bwd": [P, P, c_int64, P, P, c_int, c_int, P, P, P],
+    "segmif_colsum": [P, c_int, c_int, c_int64, c_int, P, P],
+    "segmif_add_bf16": [P, c_int, c_int, P, c_int, c_int, P, c_int, c_int, c_int64, c_int, P],
+    "segmif_layernorm_bwd": [P, c_int, P, c_int, c_int, c_int, P, c_float, P, c_int, c_int, c_int, c_int64, c_int, P, P, P, P],
+    "segmif_wgrad_workspace_bytes": [c_int, c_int, c_int, c_int],
+    "segmif_wgrad": [P, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int64, c_int, c_int, c_int, c_int, P, c_int, P,
+                     c_int64, c_int64, c_int64, c_int, c_int, P],
+    "segmif_ffm_apply_train_fwd": [P, c_int, c_int, P, c_int, c_int, P, c_int, c_int, P, P, P, P, P, P, c_float,
+                                   P, c_int, c_int, P, c_int, c_int, c_int, c_int64, P, P, P],
+    "segmif_ffm_bwd_gram": [P, c_int, c_int, P, c_int, c_int, P, c_int, c_int, P, P, P, P, P, c_int, c_int, c_int64, P],
+    "segmif_ffm_bwd_ctx": [P, c_int, P, c_int, P, P, P, P, P, P, P, c_int, P],
+    "segmif_ffm_bwd_apply": [P, c_int, c_int, P, c_int, c_int, P, c_int, c_int, P, P, P, P, P, P, P, P, c_int, c_int64, P],
+    "segmif_adamw_step": [P, P, P, P, c_int64, c_float, c_float, c_float, c_float, c_float, c_int, c_float, P],
 }
-_RESTYPES = {"segmif_last_error": c_char_p, "segmif_loss_workspace_bytes": c_size_t}
+_RESTYPES = {"segmif_last_error": c_char_p, "segmif_loss_workspace_bytes": c_size_t, "segmif_wgrad_workspace_bytes": c_size_t}
 
 _lib = None
 _lock = threading.Lock()

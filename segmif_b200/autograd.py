@@ -1,0 +1,115 @@
+"""torch.autograd registration of the loss kernels: each Function's forward is the fused forward kernel and its
+backward the hand-written backward kernel of csrc/losses_bwd.cu (gradient with respect to the FIRST image argument,
+the fused image in every loss train.py builds; the other arguments are data).  Autograd is used for graph
+bookkeeping only -- no torch op computes anything here."""
+import torch
+
+from . import ops
+
+
+def _need(ctx, idx=0):
+    return ctx.needs_input_grad[idx]
+
+
+def _no_second(ctx, *idx):
+    for i in idx:
+        if ctx.needs_input_grad[i]:
+            raise NotImplementedError("segmif_b200: loss gradients are implemented for the first image argument only "
+                                      "(the fused image); detach the other arguments")
+
+
+class MseL1Fn(torch.autograd.Function):
+    """(mean (x-y)^2, mean |x-y|)"""
+
+    @staticmethod
+    def forward(ctx, x, y):
+        x, y = x.float().contiguous(), y.float().contiguous()
+        ctx.save_for_backward(x, y)
+        return ops.mse_l1(x, y)
+
+    @staticmethod
+    def backward(ctx, g_mse, g_l1):
+        _no_second(ctx, 1)
+        x, y = ctx.saved_tensors
+        return ops.mse_l1_bwd(x, y, g_mse, g_l1), None
+
+
+class SobelL1Fn(torch.autograd.Function):
+    """(mean |x-y|, mean |sobel(x)-sobel(y)|)"""
+
+    @staticmethod
+    def forward(ctx, x, y):
+        x, y = x.float().contiguous(), y.float().contiguous()
+        ctx.save_for_backward(x, y)
+        return ops.sobel_l1(x, y)
+
+    @staticmethod
+    def backward(ctx, g_l1, g_sobel):
+        _no_second(ctx, 1)
+        x, y = ctx.saved_tensors
+        return ops.sobel_l1_bwd(x, y, g_l1, g_sobel), None
+
+
+class SsimFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, size_average):
+        a, b = a.float().contiguous(), b.float().contiguous()
+        ctx.save_for_backward(a, b)
+        ctx.size_average = size_average
+        return ops.ssim(a, b, size_average)
+
+    @staticmethod
+    def backward(ctx, g):
+        _no_second(ctx, 1)
+        a, b = ctx.saved_tensors
+        return ops.ssim_bwd(a, b, g, ctx.size_average), None, None
+
+
+class LapLoss2Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, inp, ir, vis):
+        inp, ir, vis = inp.float().contiguous(), ir.float().contiguous(), vis.float().contiguous()
+        ctx.save_for_backward(inp, ir, vis)
+        return ops.laploss2(inp, ir, vis)
+
+    @staticmethod
+    def backward(ctx, g):
+        _no_second(ctx, 1, 2)
+        inp, ir, vis = ctx.saved_tensors
+        return ops.laploss2_bwd(inp, ir, vis, g), None, None
+
+
+class LapLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, inp, target):
+        inp, target = inp.float().contiguous(), target.float().contiguous()
+        ctx.save_for_backward(inp, target)
+        return ops.laploss(inp, target)
+
+    @staticmethod
+    def backward(ctx, g):
+        _no_second(ctx, 1)
+        inp, target = ctx.saved_tensors
+        return ops.laploss_bwd(inp, target, g), None
+
+
+class EntropyFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, patch):
+        img = img.float().contiguous()
+        ctx.save_for_backward(img)
+        ctx.patch = patch
+        return ops.entropy(img, patch)
+
+    @staticmethod
+    def backward(ctx, g):
+        (img,) = ctx.saved_tensors
+        return ops.entropy_bwd(img, ctx.patch, g), None
+
+
+def mse_l1(x, y):
+    return MseL1Fn.apply(x, y)
+
+
+def sobel_l1(x, y):
+    return SobelL1Fn.apply(x, y)

@@ -5,7 +5,7 @@ histogram per warp in registers (lane == bin) and reads each pixel once."""
 import torch
 from torch import nn, Tensor
 
-from .. import ops
+from ..autograd import EntropyFn
 
 
 class Entropy(nn.Sequential):
@@ -14,8 +14,6 @@ class Entropy(nn.Sequential):
         self.psize = patch_size
 
     def forward(self, inputs: Tensor) -> torch.Tensor:
-        if torch.is_grad_enabled() and inputs.requires_grad:
-            raise NotImplementedError("segmif_b200: Entropy backward kernel is not built yet")
         self.width, self.height = inputs.shape[3], inputs.shape[2]
         self.patch_num = int(self.width * self.height / self.psize ** 2)
-        return ops.entropy(inputs.float(), self.psize)
+        return EntropyFn.apply(inputs, self.psize)

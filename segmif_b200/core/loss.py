@@ -2,20 +2,17 @@
 as thin compositions of the fused loss kernels: every term is ONE kernel launch that reduces to a device
 scalar (the reference chains five cuDNN convolutions and ~10 elementwise kernels per SSIM).  The detection
 leftovers of the reference file (FCOS / focal / OHEM, core/loss.py:18-397) are dead code there and are not
-reproduced.  Forward only for now: asking for gradients raises instead of silently returning none."""
+reproduced.  Gradients flow to the fused image (`generate_img`) through the hand-written backward kernels registered in
+segmif_b200/autograd.py; the other arguments are data."""
 import torch
 import torch.nn as nn
 
-from .. import ops
+from .. import ops  # noqa: F401
+from ..autograd import mse_l1, sobel_l1
 from ..lap_loss import LapLoss, LapLoss2
 from ..pytorch_ssim import ssim
 from .Entropy import Entropy
 from .model_fusion import RGB2YCrCb
-
-
-def _fwd_only(*ts):
-    if torch.is_grad_enabled() and any(t.requires_grad for t in ts):
-        raise NotImplementedError("segmif_b200: fusion-loss backward kernels are not built yet")
 
 
 def _y(t):
@@ -42,8 +39,7 @@ class Fusionloss3(nn.Module):
         self.sobelconv = Sobelxy()
 
     def forward(self, image_ir, image_vis, generate_img, mask):
-        _fwd_only(generate_img)
-        l1, lgrad = ops.sobel_l1(_y(mask), generate_img.float().contiguous())
+        l1, lgrad = sobel_l1(generate_img, _y(mask))
         return l1 + lgrad
 
 
@@ -55,8 +51,7 @@ class Fusionloss2(nn.Module):
         self.sobelconv = Sobelxy()
 
     def forward(self, image_ir, image_vis, generate_img, mask):
-        _fwd_only(generate_img)
-        return ops.mse_l1(_y(mask), generate_img.float().contiguous())[1]
+        return mse_l1(generate_img, _y(mask))[1]
 
 
 class Fusionloss_grad(nn.Module):
@@ -67,9 +62,8 @@ class Fusionloss_grad(nn.Module):
         self.lap = LapLoss2()
 
     def forward(self, image_ir, image_vis, generate_img, mask):
-        _fwd_only(generate_img)
-        g = generate_img.float().contiguous()
-        return ops.mse_l1(_y(mask), g)[1] + 0.8 * self.lap(g, _y(image_ir), _y(image_vis))
+        g = generate_img
+        return mse_l1(g, _y(mask))[1] + 0.8 * self.lap(g, _y(image_ir), _y(image_vis))
 
 
 class Fusionloss_grad2(nn.Module):
@@ -80,9 +74,8 @@ class Fusionloss_grad2(nn.Module):
         self.lap = LapLoss2()
 
     def forward(self, image_ir, image_vis, generate_img, mask):
-        _fwd_only(generate_img)
-        g, m = generate_img.float().contiguous(), _y(mask)
-        return ops.mse_l1(m, g)[1] + 0.1 * self.lap(g, _y(image_vis), _y(image_ir)) + 1.1 * (1 - ssim(g, m))
+        g, m = generate_img, _y(mask)
+        return mse_l1(g, m)[1] + 0.1 * self.lap(g, _y(image_vis), _y(image_ir)) + 1.1 * (1 - ssim(g, m))
 
 
 class Fusionloss_grad3(nn.Module):
@@ -93,9 +86,8 @@ class Fusionloss_grad3(nn.Module):
         self.lap = LapLoss2()
 
     def forward(self, image_ir, image_vis, generate_img, mask):
-        _fwd_only(generate_img)
-        g, m = generate_img.float().contiguous(), _y(mask)
-        return ops.mse_l1(m, g)[0] + 1.1 * (1 - ssim(g, m))
+        g, m = generate_img, _y(mask)
+        return mse_l1(g, m)[0] + 1.1 * (1 - ssim(g, m))
 
 
 def _unbuilt(name, where):

@@ -426,6 +426,10 @@ class Fusion_Network3_ac(nn.Module):
         self._packs = PackCache()
 
     def forward(self, ir, vis, out1, out2):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # training (train.py:360,381-386): forward that keeps what the hand-written backward needs
+            from .fusion_train import forward_with_grad
+            return forward_with_grad(self, ir, vis, out1, out2)
         _no_autograd(self, ir, vis, out1, out2)
         return self._run(ir, vis, ("full", _pixel_major_bf16(out1)), ("full", _pixel_major_bf16(out2)))
 

@@ -8,49 +8,9 @@
 // conv3 / conv4 (1x1 on the segmentation features) are folded into channel_proj3 by the host.
 #include <algorithm>
 
-#include "common.cuh"
+#include "ffm_mma.cuh"
 
 namespace segmif {
-
-constexpr int kTilePx = 64;          // pixels per tile (4 warps x 16 rows)
-constexpr int kFfmThreads = 128;
-
-__device__ __forceinline__ int swz128(int row, int chunk) { return chunk ^ (row & 7); }
-
-// copy a [rows x K] bf16 tile (K multiple of 8, rows of K*2 bytes) from pixel-major global memory
-__device__ __forceinline__ void load_rows_async(bf16* s, const bf16* g, int64_t first_row, int64_t nrows_total, int ld,
-                                                int K, int rows, int tid) {
-  const int cpr = K >> 3;
-  for (int i = tid; i < rows * cpr; i += kFfmThreads) {
-    const int row = i / cpr, chunk = i - row * cpr;
-    const bool ok = (first_row + row) < nrows_total;
-    const bf16* src = ok ? g + (first_row + row) * ld + chunk * 8 : g;
-    cp_async16_cg(smem_u32(s + row * K + swz128(row, chunk) * 8), src, ok ? 16 : 0);
-  }
-}
-
-// acc[8][4] (16 px x 64 out) = X[16 x K] * W[64 x K]^T for this warp's 16 rows
-__device__ __forceinline__ void proj16x64(float (&acc)[8][4], const bf16* sX, int K, int row0, const bf16* sW, int lane) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int ks = 0; ks < (K >> 4); ++ks) {
-    uint32_t af[4];
-    {
-      const int row = row0 + (lane & 15), chunk = ks * 2 + (lane >> 4);
-      ldmatrix_x4(af, smem_u32(sX + row * K + swz128(row, chunk) * 8));
-    }
-#pragma unroll
-    for (int np = 0; np < 4; ++np) {
-      uint32_t bfr[4];
-      const int row = np * 16 + (lane & 7) + ((lane >> 4) << 3), chunk = ks * 2 + ((lane >> 3) & 1);
-      ldmatrix_x4(bfr, smem_u32(sW + row * K + swz128(row, chunk) * 8));
-      mma_bf16_16816(acc[np * 2], af, bfr[0], bfr[1]);
-      mma_bf16_16816(acc[np * 2 + 1], af, bfr[2], bfr[3]);
-    }
-  }
-}
 
 // ------------------------------------------------------------------------------------------------ pass 1
 __global__ void __launch_bounds__(kFfmThreads) ffm_gram_kernel(const bf16* __restrict__ x1, int ld1,
@@ -225,39 +185,12 @@ __global__ void __launch_bounds__(256) ffm_fold_kernel(const float* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------ pass 3
-__device__ __forceinline__ void relu_bias_to_afrag(uint32_t (&af)[4][4], const float (&acc)[8][4], const float* bias, int tq) {
-#pragma unroll
-  for (int kk = 0; kk < 4; ++kk) {
-#pragma unroll
-    for (int sub = 0; sub < 2; ++sub) {
-      const int nt = kk * 2 + sub;
-      const float b0 = bias[nt * 8 + tq * 2], b1 = bias[nt * 8 + tq * 2 + 1];
-      af[kk][sub * 2 + 0] = pack_bf16x2(fmaxf(acc[nt][0] + b0, 0.f), fmaxf(acc[nt][1] + b1, 0.f));
-      af[kk][sub * 2 + 1] = pack_bf16x2(fmaxf(acc[nt][2] + b0, 0.f), fmaxf(acc[nt][3] + b1, 0.f));
-    }
-  }
-}
-
-// acc += A(16x64, register fragments) * M^T, M stored [64 out][64 in] bf16 swizzled
-__device__ __forceinline__ void apply64(float (&acc)[8][4], const uint32_t (&af)[4][4], const bf16* sM, int lane) {
-#pragma unroll
-  for (int kk = 0; kk < 4; ++kk) {
-#pragma unroll
-    for (int np = 0; np < 4; ++np) {
-      uint32_t bfr[4];
-      const int row = np * 16 + (lane & 7) + ((lane >> 4) << 3), chunk = kk * 2 + ((lane >> 3) & 1);
-      ldmatrix_x4(bfr, smem_u32(sM + row * 64 + swz128(row, chunk) * 8));
-      mma_bf16_16816(acc[np * 2], af[kk], bfr[0], bfr[1]);
-      mma_bf16_16816(acc[np * 2 + 1], af[kk], bfr[2], bfr[3]);
-    }
-  }
-}
-
 __global__ void __launch_bounds__(kFfmThreads) ffm_apply_kernel(
     const bf16* __restrict__ x1, int ld1, const bf16* __restrict__ x2, int ld2, const bf16* __restrict__ x3, int ld3,
     int C3, const bf16* __restrict__ wproj, const float* __restrict__ bproj, const bf16* __restrict__ folded,
     const float* __restrict__ bend, const float* __restrict__ ln_g, const float* __restrict__ ln_b, float eps,
-    bf16* __restrict__ out1, int ldo1, bf16* __restrict__ out2, int ldo2, int64_t HW) {
+    bf16* __restrict__ out1, int ldo1, bf16* __restrict__ out2, int ldo2, int64_t HW, bf16* __restrict__ pre1,
+    bf16* __restrict__ pre2) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   bf16* sW3 = reinterpret_cast<bf16*>(smem_raw);   // [64][C3]   channel_proj3 (y half) folded with conv3|conv4
   bf16* sW1 = sW3 + 64 * C3;                       // [64][64]   channel_proj1 (u half)
@@ -355,6 +288,17 @@ __global__ void __launch_bounds__(kFfmThreads) ffm_apply_kernel(
       }
       bf16* op = (s == 0 ? out1 : out2);
       const int ldo = s == 0 ? ldo1 : ldo2;
+      bf16* pre = s == 0 ? pre1 : pre2;             // training: the LayerNorm input, dense [B*HW, 64]
+      if (pre != nullptr) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int64_t px = p0 + row0 + g + half * 8;
+          if (px >= HW) continue;
+          bf16* o = pre + ((int64_t)b * HW + px) * 64 + tq * 2;
+#pragma unroll
+          for (int nt = 0; nt < 8; ++nt) *reinterpret_cast<uint32_t*>(o + nt * 8) = pack_bf16x2(acc[nt][half * 2], acc[nt][half * 2 + 1]);
+        }
+      }
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         const int64_t px = p0 + row0 + g + half * 8;
@@ -423,11 +367,11 @@ extern "C" int segmif_ffm_ctx_fwd(const float* partials, int nchunk, const float
   return check_launch("segmif_ffm_ctx_fwd(fold)");
 }
 
-extern "C" int segmif_ffm_apply_fwd(const void* x1, int ld1, int coff1, const void* x2, int ld2, int coff2,
+static int ffm_apply_impl(const void* x1, int ld1, int coff1, const void* x2, int ld2, int coff2,
                                     const void* x3, int ld3, int C3, const void* wproj, const float* bproj,
                                     const void* folded, const float* bend, const float* ln_gamma, const float* ln_beta,
                                     float eps, void* out1, int ldo1, int coffo1, void* out2, int ldo2, int coffo2, int B,
-                                    int64_t HW, segmif_stream_t stream) {
+                                    int64_t HW, void* pre1, void* pre2, segmif_stream_t stream) {
   SEGMIF_REQUIRE(x1 && x2 && x3 && wproj && bproj && folded && bend && ln_gamma && ln_beta && out1 && out2, "ffm_apply: null pointer");
   SEGMIF_REQUIRE(C3 == 64 || C3 == 128, "ffm_apply: C3=%d must be 64 or 128", C3);
   SEGMIF_REQUIRE(ld1 % 8 == 0 && ld2 % 8 == 0 && ld3 % 8 == 0 && coff1 % 8 == 0 && coff2 % 8 == 0, "ffm_apply: input pitches/offsets must be multiples of 8");
@@ -441,6 +385,26 @@ extern "C" int segmif_ffm_apply_fwd(const void* x1, int ld1, int coff1, const vo
   dim3 grid(per_image, B);
   ffm_apply_kernel<<<grid, kFfmThreads, smem, as_stream(stream)>>>(
       (const bf16*)x1 + coff1, ld1, (const bf16*)x2 + coff2, ld2, (const bf16*)x3, ld3, C3, (const bf16*)wproj, bproj,
-      (const bf16*)folded, bend, ln_gamma, ln_beta, eps, (bf16*)out1 + coffo1, ldo1, (bf16*)out2 + coffo2, ldo2, HW);
+      (const bf16*)folded, bend, ln_gamma, ln_beta, eps, (bf16*)out1 + coffo1, ldo1, (bf16*)out2 + coffo2, ldo2, HW, (bf16*)pre1, (bf16*)pre2);
   return check_launch("segmif_ffm_apply_fwd");
+}
+
+extern "C" int segmif_ffm_apply_fwd(const void* x1, int ld1, int coff1, const void* x2, int ld2, int coff2,
+                                    const void* x3, int ld3, int C3, const void* wproj, const float* bproj,
+                                    const void* folded, const float* bend, const float* ln_gamma, const float* ln_beta,
+                                    float eps, void* out1, int ldo1, int coffo1, void* out2, int ldo2, int coffo2, int B,
+                                    int64_t HW, segmif_stream_t stream) {
+  return ffm_apply_impl(x1, ld1, coff1, x2, ld2, coff2, x3, ld3, C3, wproj, bproj, folded, bend, ln_gamma, ln_beta, eps,
+                        out1, ldo1, coffo1, out2, ldo2, coffo2, B, HW, nullptr, nullptr, stream);
+}
+
+extern "C" int segmif_ffm_apply_train_fwd(const void* x1, int ld1, int coff1, const void* x2, int ld2, int coff2,
+                                          const void* x3, int ld3, int C3, const void* wproj, const float* bproj,
+                                          const void* folded, const float* bend, const float* ln_gamma,
+                                          const float* ln_beta, float eps, void* out1, int ldo1, int coffo1, void* out2,
+                                          int ldo2, int coffo2, int B, int64_t HW, void* pre1, void* pre2,
+                                          segmif_stream_t stream) {
+  SEGMIF_REQUIRE(pre1 && pre2, "ffm_apply_train: the pre-LayerNorm outputs are required");
+  return ffm_apply_impl(x1, ld1, coff1, x2, ld2, coff2, x3, ld3, C3, wproj, bproj, folded, bend, ln_gamma, ln_beta, eps,
+                        out1, ldo1, coffo1, out2, ldo2, coffo2, B, HW, pre1, pre2, stream);
 }

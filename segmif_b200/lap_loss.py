@@ -3,12 +3,8 @@ difference-of-Gaussian residuals (k = 3, 5, 7; sigma = 2; zero padding) and L1 t
 One kernel produces all three residuals of all images from a single 3-pixel-halo shared-memory tile."""
 import torch
 
-from . import ops
-
-
-def _no_grad(*ts):
-    if torch.is_grad_enabled() and any(t.requires_grad for t in ts):
-        raise NotImplementedError("segmif_b200: LapLoss backward kernel is not built yet")
+from . import ops  # noqa: F401
+from .autograd import LapLoss2Fn, LapLossFn
 
 
 def _planes(t, channels):
@@ -26,8 +22,7 @@ class LapLoss(torch.nn.Module):
         self.max_levels, self.channels = max_levels, channels
 
     def forward(self, input, target):
-        _no_grad(input, target)
-        return ops.laploss(_planes(input, self.channels), _planes(target, self.channels))
+        return LapLossFn.apply(_planes(input, self.channels), _planes(target, self.channels))
 
 
 class LapLoss2(torch.nn.Module):
@@ -38,5 +33,4 @@ class LapLoss2(torch.nn.Module):
         self.max_levels, self.channels = max_levels, channels
 
     def forward(self, input, ir, vis):
-        _no_grad(input, ir, vis)
-        return ops.laploss2(_planes(input, self.channels), _planes(ir, self.channels), _planes(vis, self.channels))
+        return LapLoss2Fn.apply(_planes(input, self.channels), _planes(ir, self.channels), _planes(vis, self.channels))

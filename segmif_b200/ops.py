@@ -446,3 +446,184 @@ def upsample_ce(logits_nhwc, B, h, w, nc, labels, ignore_index=255):
     _lib.call("segmif_upsample_ce_fwd", _ptr(logits_nhwc), B, h, w, nc, _ptr(labels), H, W, int(ignore_index),
               _ptr(ws), _ptr(out), st)
     return out[0]
+
+
+# ---------------------------------------------------------------------------------------------- training side
+def _gout(g, n, like):
+    """Upstream gradient(s) as a contiguous fp32 device vector of n entries (None -> 0)."""
+    if isinstance(g, (list, tuple)):
+        parts = [torch.zeros((), dtype=torch.float32, device=like.device) if x is None else x.reshape(()).float() for x in g]
+        g = torch.stack(parts)
+    g = g.reshape(-1).float().contiguous()
+    assert g.numel() == n, (g.shape, n)
+    return g
+
+
+def mse_l1_bwd(x, y, g_mse, g_l1, out=None):
+    """d(g_mse * mse + g_l1 * l1)/dx for the two outputs of mse_l1; accumulates into `out` when given."""
+    x = x if x.is_contiguous() else x.contiguous()
+    y = y if y.is_contiguous() else y.contiguous()
+    g = _gout([g_mse, g_l1], 2, x)
+    st = _prep(x, y, g, out)
+    acc = out is not None
+    out = torch.empty_like(x) if out is None else out
+    _lib.call("segmif_mse_l1_bwd", _ptr(x), _ptr(y), x.numel(), _ptr(g), _ptr(out), 1 if acc else 0, st)
+    return out
+
+
+def sobel_l1_bwd(x, y, g_l1, g_sobel, out=None):
+    x, y = _plane(x), _plane(y)
+    g = _gout([g_l1, g_sobel], 2, x)
+    st = _prep(x, y, g, out)
+    B, _, H, W = x.shape
+    acc = out is not None
+    out = torch.empty_like(x) if out is None else out
+    _lib.call("segmif_sobel_l1_bwd", _ptr(x), _ptr(y), B, H, W, _ptr(g), _ptr(out), 1 if acc else 0, st)
+    return out
+
+
+def ssim_bwd(a, b, gout, size_average=True, out=None):
+    a, b = _plane(a), _plane(b)
+    B, _, H, W = a.shape
+    g = _gout(gout, 1 if size_average else B, a)
+    st = _prep(a, b, g, out)
+    acc = out is not None
+    out = torch.empty_like(a) if out is None else out
+    _lib.call("segmif_ssim_bwd", _ptr(a), _ptr(b), B, H, W, 0 if size_average else 1, _ptr(g), _ptr(out), 1 if acc else 0, st)
+    return out
+
+
+def laploss2_bwd(inp, ir, vis, gout, out=None):
+    inp, ir, vis = _plane(inp), _plane(ir), _plane(vis)
+    g = _gout(gout, 1, inp)
+    st = _prep(inp, ir, vis, g, out)
+    B, _, H, W = inp.shape
+    acc = out is not None
+    out = torch.empty_like(inp) if out is None else out
+    _lib.call("segmif_laploss2_bwd", _ptr(inp), _ptr(ir), _ptr(vis), B, H, W, _ptr(g), _ptr(out), 1 if acc else 0, st)
+    return out
+
+
+def laploss_bwd(inp, target, gout, out=None):
+    inp, target = _plane(inp), _plane(target)
+    g = _gout(gout, 1, inp)
+    st = _prep(inp, target, g, out)
+    B, _, H, W = inp.shape
+    acc = out is not None
+    out = torch.empty_like(inp) if out is None else out
+    _lib.call("segmif_laploss_bwd", _ptr(inp), _ptr(target), B, H, W, _ptr(g), _ptr(out), 1 if acc else 0, st)
+    return out
+
+
+def entropy_bwd(img, patch, gout, out=None):
+    img = _plane(img)
+    g = _gout(gout, 1, img)
+    st = _prep(img, g, out)
+    B, _, H, W = img.shape
+    acc = out is not None
+    out = torch.empty_like(img) if out is None else out
+    _lib.call("segmif_entropy_bwd", _ptr(img), B, H, W, int(patch), _ptr(g), _ptr(out), 1 if acc else 0, st)
+    return out
+
+
+def act_bwd(y, ldy, coffy, dy, lddy, coffdy, dz, lddz, coffdz, rows, C, act, alpha=None, dbias=None, dalpha=None):
+    st = _prep(y, dy, dz, alpha, dbias, dalpha)
+    _lib.call("segmif_act_bwd", _ptr(y), ldy, coffy, _ptr(dy), lddy, coffdy, _ptr(dz), lddz, coffdz, rows, C, act,
+              _ptr(alpha), _ptr(dbias), _ptr(dalpha), st)
+    return dz
+
+
+def prelu_plane_bwd(out, dout, alpha, dz, lddz, coffdz, dbias=None, dalpha=None):
+    st = _prep(out, dout, alpha, dz, dbias, dalpha)
+    _lib.call("segmif_prelu_plane_bwd", _ptr(out), _ptr(dout), out.numel(), _ptr(alpha), _ptr(dz), lddz, coffdz,
+              _ptr(dbias), _ptr(dalpha), st)
+    return dz
+
+
+def colsum(x, ld, coff, rows, C, out):
+    st = _prep(x, out)
+    _lib.call("segmif_colsum", _ptr(x), ld, coff, rows, C, _ptr(out), st)
+    return out
+
+
+def add_bf16(a, lda, coffa, b, ldb, coffb, out, ldo, coffo, rows, C):
+    st = _prep(a, b, out)
+    _lib.call("segmif_add_bf16", _ptr(a), lda, coffa, _ptr(b), ldb, coffb, _ptr(out), ldo, coffo, rows, C, st)
+    return out
+
+
+def layernorm_bwd(x, dy, lddy, coffdy, gamma, eps, dx, lddx, coffdx, rows, C, dgamma=None, dbeta=None, dxsum=None):
+    st = _prep(x, dy, gamma, dx, dgamma, dbeta, dxsum)
+    _lib.call("segmif_layernorm_bwd", _ptr(x), _dt(x), _ptr(dy), _dt(dy), lddy, coffdy, _ptr(gamma), float(eps), _ptr(dx),
+              _dt(dx), lddx, coffdx, rows, C, _ptr(dgamma), _ptr(dbeta), _ptr(dxsum), st)
+    return dx
+
+
+def wgrad(dy, ldy, coffy, x, ldx, coffx, *, B, H, W, Cin, Cout, taps, dil, grad, s_co, s_tap, s_ci, co_take=None,
+          ci_take=None, P=None):
+    """grad[co*s_co + tap*s_tap + ci*s_ci] += sum_p dy[p][co] * x[p + tap][ci]  (fp32 `grad`, accumulated).
+    taps = 1: linear layer over P rows (B, H, W ignored);  taps = 9: 3x3 'same' conv with dilation `dil`."""
+    st = _prep(dy, x, grad)
+    if taps == 1:
+        P = B * H * W if P is None else P
+        B, W = 1, 16
+        H = (P + 15) // 16
+    else:
+        P = B * H * W
+    ntiles = B * ((H + 7) // 8) * ((W + 15) // 16)
+    nchunk = max(1, min(ntiles, (2 * _sm_count(dy.device)) // (((Cin + 63) // 64) * (Cout // 32))))
+    ws = torch.empty((nchunk * Cout * taps * Cin,), dtype=torch.float32, device=dy.device)
+    _lib.call("segmif_wgrad", _ptr(dy), ldy, coffy, _ptr(x), ldx, coffx, B, H, W, P, Cin, Cout, taps, dil, _ptr(ws), nchunk,
+              _ptr(grad), s_co, s_tap, s_ci, Cout if co_take is None else co_take, Cin if ci_take is None else ci_take, st)
+    return grad
+
+
+def ffm_train_fwd(x1, ld1, coff1, x2, ld2, coff2, x3, ld3, packs, out1, ldo1, coffo1, out2, ldo2, coffo2, B, HW):
+    """Training forward of the HIA module (C3 = 64): returns the tensors the backward needs."""
+    st = _prep(x1, x2, x3, out1, out2)
+    dev = x1.device
+    nchunk = max(1, min((_sm_count(dev) * 4) // max(B, 1), (HW + 63) // 64))
+    partials = torch.empty((B, nchunk, 3, 64, 64), dtype=torch.float32, device=dev)
+    folded = torch.empty((B, 4, 64, 64), dtype=torch.bfloat16, device=dev)
+    ctx = torch.empty((B, 3, 8, 8, 8), dtype=torch.float32, device=dev)
+    pre1 = torch.empty((B * HW, 64), dtype=torch.bfloat16, device=dev)
+    pre2 = torch.empty_like(pre1)
+    _lib.call("segmif_ffm_gram_fwd", _ptr(x1), ld1, coff1, _ptr(x2), ld2, coff2, _ptr(x3), ld3, 64,
+              _ptr(packs["w_gram"]), _ptr(packs["b_gram"]), _ptr(partials), nchunk, B, HW, st)
+    _lib.call("segmif_ffm_ctx_fwd", _ptr(partials), nchunk, _ptr(packs["wkv"]), _ptr(packs["wend"]), _ptr(folded),
+              _ptr(ctx), B, st)
+    _lib.call("segmif_ffm_apply_train_fwd", _ptr(x1), ld1, coff1, _ptr(x2), ld2, coff2, _ptr(x3), ld3, 64,
+              _ptr(packs["w_apply"]), _ptr(packs["b_apply"]), _ptr(folded), _ptr(packs["bend"]), _ptr(packs["ln_g"]),
+              _ptr(packs["ln_b"]), 1e-5, _ptr(out1), ldo1, coffo1, _ptr(out2), ldo2, coffo2, B, HW, _ptr(pre1), _ptr(pre2), st)
+    return dict(partials=partials, nchunk=nchunk, folded=folded, ctx=ctx, pre1=pre1, pre2=pre2)
+
+
+def ffm_bwd_gram(x1, ld1, coff1, x2, ld2, coff2, x3, ld3, coff3, dr1, dr2, wfull, bfull, B, HW):
+    st = _prep(x1, x2, x3, dr1, dr2, wfull, bfull)
+    nchunk = max(1, min((_sm_count(x1.device) * 2) // max(B, 1), (HW + 63) // 64))
+    partials = torch.empty((B, nchunk, 4, 64, 64), dtype=torch.float32, device=x1.device)
+    _lib.call("segmif_ffm_bwd_gram", _ptr(x1), ld1, coff1, _ptr(x2), ld2, coff2, _ptr(x3), ld3, coff3, _ptr(dr1), _ptr(dr2),
+              _ptr(wfull), _ptr(bfull), _ptr(partials), nchunk, B, HW, st)
+    return partials, nchunk
+
+
+def ffm_bwd_ctx(rpart, nchunk_r, gpart, nchunk_g, ctx, wkv, wend, folded, dwkv, dwend, B):
+    st = _prep(rpart, gpart, ctx, wkv, wend, folded, dwkv, dwend)
+    mats = torch.empty((B, 7, 64, 64), dtype=torch.bfloat16, device=rpart.device)
+    _lib.call("segmif_ffm_bwd_ctx", _ptr(rpart), nchunk_r, _ptr(gpart), nchunk_g, _ptr(ctx), _ptr(wkv), _ptr(wend),
+              _ptr(folded), _ptr(mats), _ptr(dwkv), _ptr(dwend), B, st)
+    return mats
+
+
+def ffm_bwd_apply(x1, ld1, coff1, x2, ld2, coff2, x3, ld3, coff3, dr1, dr2, wfull, bfull, mats, B, HW):
+    st = _prep(x1, x2, x3, dr1, dr2, wfull, bfull, mats)
+    dP = [torch.empty((B * HW, 128), dtype=torch.bfloat16, device=x1.device) for _ in range(3)]
+    _lib.call("segmif_ffm_bwd_apply", _ptr(x1), ld1, coff1, _ptr(x2), ld2, coff2, _ptr(x3), ld3, coff3, _ptr(dr1), _ptr(dr2),
+              _ptr(wfull), _ptr(bfull), _ptr(mats), _ptr(dP[0]), _ptr(dP[1]), _ptr(dP[2]), B, HW, st)
+    return dP
+
+
+def adamw_step(param, grad, exp_avg, exp_avg_sq, *, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+    st = _prep(param, grad, exp_avg, exp_avg_sq)
+    _lib.call("segmif_adamw_step", _ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), param.numel(), float(lr),
+              float(beta1), float(beta2), float(eps), float(weight_decay), int(step), float(grad_scale), st)

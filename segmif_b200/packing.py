@@ -3,6 +3,15 @@ fp32 master parameters -> the bf16 / tap-major layouts the kernels consume."""
 import torch
 
 
+_EPOCH = [0]
+
+
+def invalidate_all():
+    """Called by the fused optimizer: its kernel updates parameters through raw pointers, which does not bump
+    torch's per-tensor version counters, so every cached pack is declared stale explicitly."""
+    _EPOCH[0] += 1
+
+
 class PackCache:
     """Caches packed copies of parameters; an entry is rebuilt when the parameter is modified in place
     (optimizer step, load_state_dict), moved, or replaced."""
@@ -21,7 +30,7 @@ class PackCache:
 
     def get(self, param, fn, tag=""):
         key = (id(param), tag)
-        stamp = (param.data_ptr(), param._version, param.device)
+        stamp = (param.data_ptr(), param._version, param.device, _EPOCH[0])
         hit = self._c.get(key)
         if hit is not None and hit[0] == stamp:
             return hit[1]
@@ -33,7 +42,7 @@ class PackCache:
     def get_multi(self, params, fn, tag):
         """One packed object derived from several parameters."""
         key = ("multi", tag)
-        stamp = tuple((p.data_ptr(), p._version, p.device) for p in params)
+        stamp = tuple((p.data_ptr(), p._version, p.device) for p in params) + (_EPOCH[0],)
         hit = self._c.get(key)
         if hit is not None and hit[0] == stamp:
             return hit[1]

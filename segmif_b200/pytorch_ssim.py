@@ -1,17 +1,17 @@
 """SSIM with the reference's surface (pytorch_ssim/__init__.py of SegMiF): 11x11 Gaussian (sigma 1.5) window,
 zero padding 5, C1 = 0.01^2, C2 = 0.03^2.  One kernel computes the five windowed moments separably in shared
-memory and the SSIM map + reduction in registers; nothing but the two input planes touches HBM."""
+memory and the SSIM map + reduction in registers; nothing but the two input planes touches HBM.  The backward
+(gradient w.r.t. img1) is csrc/losses_bwd.cu::ssim_bwd_kernel, registered through autograd.SsimFn."""
 import torch
 
 from . import ops
+from .autograd import SsimFn
 
 
 def _check(img1, img2, window_size):
     if window_size != 11:
         raise NotImplementedError("segmif_b200: the SSIM kernel is specialised for window_size=11 (the only value the "
                                   "reference uses)")
-    if torch.is_grad_enabled() and (img1.requires_grad or img2.requires_grad):
-        raise NotImplementedError("segmif_b200: SSIM backward kernel is not built yet")
     if img1.shape != img2.shape or img1.dim() != 4:
         raise ValueError("ssim expects two [B,C,H,W] tensors of equal shape")
 
@@ -21,8 +21,8 @@ def _ssim_planes(img1, img2, size_average):
     a = img1.float().reshape(B * C, 1, H, W)
     b = img2.float().reshape(B * C, 1, H, W)
     if size_average:
-        return ops.ssim(a, b, True)
-    per_plane = torch.cat([ops.ssim(a[i:i + 32], b[i:i + 32], False) for i in range(0, B * C, 32)])
+        return SsimFn.apply(a, b, True)
+    per_plane = torch.cat([SsimFn.apply(a[i:i + 32], b[i:i + 32], False) for i in range(0, B * C, 32)])
     return per_plane.view(B, C).mean(1)
 
 

@@ -1,0 +1,313 @@
+"""Parity checks of the TRAINING side (backward kernels, fused AdamW, the fusion network's hand-written backward)
+against torch.autograd run over the CPU oracle (oracle/segmif_oracle.py is plain differentiable torch code, so its
+autograd gradients are the reference's gradients).  Same conventions as tests/gpu_checks.py.
+
+Tolerances: fp32 loss gradients <= 1e-4 of the gradient's max |value| (SSIM 2e-3: the sigma^2 = E[x^2]-mu^2
+cancellation amplifies fp32 reordering, as in the forward); tensor-core weight/data gradients on bf16-representable
+operands <= 2e-3 (bf16 output rounding 2^-8 where the output is bf16); module-level bf16 backward chains 3e-2 .. 6e-2
+of each gradient tensor's max |value| (bounds set from measured error with ~3x headroom)."""
+import copy
+
+import torch
+import torch.nn.functional as F
+
+from gpu_checks import CHECKS, DEV, check, rel_err, result, rnd  # noqa: F401
+from oracle import segmif_oracle as O
+from segmif_b200 import ops, synth
+from segmif_b200.ops import ACT_PRELU, ACT_RELU
+
+
+def _grad_of(fn, x, *rest):
+    x = x.clone().requires_grad_(True)
+    out = fn(x, *rest)
+    out.backward()
+    return x.grad
+
+
+# ----------------------------------------------------------------------------------------- loss gradients
+@check
+def loss_gradients():
+    res = []
+    g = torch.Generator().manual_seed(3)
+    for (B, H, W) in ((2, 64, 96), (1, 72, 104), (3, 40, 56)):
+        a, b, c = (torch.rand(B, 1, H, W, generator=g) for _ in range(3))
+        one = torch.ones((), device=DEV)
+        tag = f"{B}x{H}x{W}"
+        da = ops.ssim_bwd(a.to(DEV), b.to(DEV), one * 0.7, True)
+        res.append(result(f"ssim_bwd_{tag}", rel_err(da, _grad_of(lambda x: 0.7 * O.ssim(x, b), a)), 2e-3))
+        gv = torch.linspace(0.5, 1.5, B)
+        da = ops.ssim_bwd(a.to(DEV), b.to(DEV), gv.to(DEV), False)
+        res.append(result(f"ssim_bwd_per_image_{tag}", rel_err(da, _grad_of(lambda x: (gv * O.ssim(x, b, size_average=False)).sum(), a)), 2e-3))
+        da = ops.laploss2_bwd(a.to(DEV), b.to(DEV), c.to(DEV), one * 1.3)
+        res.append(result(f"laploss2_bwd_{tag}", rel_err(da, _grad_of(lambda x: 1.3 * O.lap_loss2(x, b, c), a)), 1e-4))
+        da = ops.laploss_bwd(a.to(DEV), b.to(DEV), one)
+        res.append(result(f"laploss_bwd_{tag}", rel_err(da, _grad_of(lambda x: O.lap_loss(x, b), a)), 1e-4))
+        da = ops.sobel_l1_bwd(a.to(DEV), b.to(DEV), one * 0.5, one * 2.0)
+        ref = _grad_of(lambda x: 0.5 * F.l1_loss(x, b) + 2.0 * F.l1_loss(O.sobelxy(x), O.sobelxy(b)), a)
+        res.append(result(f"sobel_l1_bwd_{tag}", rel_err(da, ref), 1e-4))
+        da = ops.mse_l1_bwd(a.to(DEV), b.to(DEV), one * 0.3, one * 1.1)
+        ref = _grad_of(lambda x: 0.3 * F.mse_loss(x, b) + 1.1 * F.l1_loss(x, b), a)
+        res.append(result(f"mse_l1_bwd_{tag}", rel_err(da, ref), 1e-5))
+        for p in (4, 8):
+            da = ops.entropy_bwd(a.to(DEV), p, one)
+            res.append(result(f"entropy{p}_bwd_{tag}", rel_err(da, _grad_of(lambda x: O.entropy(x, p), a)), 2e-3))
+        # accumulate flag: two terms into one plane
+        acc = ops.mse_l1_bwd(a.to(DEV), b.to(DEV), one, None)
+        ops.laploss_bwd(a.to(DEV), b.to(DEV), one, out=acc)
+        ref = _grad_of(lambda x: F.mse_loss(x, b) + O.lap_loss(x, b), a)
+        res.append(result(f"accumulate_{tag}", rel_err(acc, ref), 1e-4))
+    return res
+
+
+@check
+def loss_modules_autograd():
+    """The reference-named loss modules with gradients flowing through autograd.Function registration."""
+    from segmif_b200.core.loss import Fusionloss3, Fusionloss_grad2, Fusionloss_grad3
+    inp = synth.synth_inputs(2, 64, 96, seed=5)
+    fused = torch.rand(2, 1, 64, 96, generator=torch.Generator().manual_seed(9))
+    res = []
+    for cls, ofn in ((Fusionloss3, O.fusionloss3), (Fusionloss_grad3, O.fusionloss_grad3), (Fusionloss_grad2, O.fusionloss_grad2)):
+        f = fused.to(DEV).requires_grad_(True)
+        loss = cls()(inp["ir"].to(DEV), inp["vis"].to(DEV), f, inp["mask"].to(DEV))
+        loss.backward()
+        fr = fused.clone().requires_grad_(True)
+        lr = ofn(inp["ir"], inp["vis"], fr, inp["mask"])
+        lr.backward()
+        res.append(result(f"{cls.__name__}_value", rel_err(loss, lr), 5e-5))
+        res.append(result(f"{cls.__name__}_grad", rel_err(f.grad, fr.grad), 2e-3))
+    return res
+
+
+# ----------------------------------------------------------------------------------------- elementwise / norm
+@check
+def act_and_layernorm_bwd():
+    res = []
+    N = 1000
+    for C, ld, coff in ((32, 224, 64), (64, 64, 0), (224, 224, 0), (128, 128, 0)):
+        z = rnd(N, ld, seed=C, scale=1.0)
+        dy = rnd(N, ld, seed=C + 1, scale=1.0)
+        for act, alpha in ((ACT_RELU, None), (ACT_PRELU, 0.25)):
+            y = F.relu(z) if act == ACT_RELU else F.prelu(z, torch.tensor([alpha]))
+            y16 = y.bfloat16()
+            ys = y16.float()[:, coff:coff + C]
+            slope = torch.where(ys > 0, torch.ones_like(ys), torch.full_like(ys, alpha or 0.0))
+            ref = dy[:, coff:coff + C] * slope
+            dz = torch.zeros((N, C), dtype=torch.bfloat16, device=DEV)
+            dbias = torch.zeros((C,), device=DEV)
+            dalpha = torch.zeros((1,), device=DEV)
+            a_t = torch.tensor([alpha], device=DEV) if alpha else None
+            ops.act_bwd(y16.to(DEV), ld, coff, dy.bfloat16().to(DEV), ld, coff, dz, C, 0, N, C, act, alpha=a_t, dbias=dbias,
+                        dalpha=dalpha if alpha else None)
+            tag = f"{'prelu' if alpha else 'relu'}_C{C}"
+            res.append(result(f"act_bwd_{tag}", rel_err(dz.float(), ref), 4e-3))
+            res.append(result(f"act_bwd_dbias_{tag}", rel_err(dbias, ref.sum(0)), 1e-4))
+            if alpha:
+                refa = (dy[:, coff:coff + C] * torch.where(ys > 0, torch.zeros_like(ys), ys / alpha)).sum()
+                res.append(result(f"act_bwd_dalpha_{tag}", rel_err(dalpha[0], refa), 1e-4))
+        cs = torch.zeros((C,), device=DEV)
+        ops.colsum(dy.bfloat16().to(DEV), ld, coff, N, C, cs)
+        res.append(result(f"colsum_C{C}", rel_err(cs, dy[:, coff:coff + C].sum(0)), 1e-5))
+    a, b = rnd(N, 224, seed=1), rnd(N, 64, seed=2)
+    o = torch.empty((N, 64), dtype=torch.bfloat16, device=DEV)
+    ops.add_bf16(a.bfloat16().to(DEV), 224, 0, b.bfloat16().to(DEV), 64, 0, o, 64, 0, N, 64)
+    res.append(result("add_bf16", rel_err(o.float(), a[:, :64] + b), 4e-3))
+    # conv22's plane
+    zf = rnd(2, 1, 20, 30, seed=4, bf16=False)
+    of = F.prelu(zf, torch.tensor([0.25]))
+    df = rnd(2, 1, 20, 30, seed=5, bf16=False)
+    dz = torch.zeros((1200, 32), dtype=torch.bfloat16, device=DEV)
+    db, da = torch.zeros((1,), device=DEV), torch.zeros((1,), device=DEV)
+    ops.prelu_plane_bwd(of.to(DEV), df.to(DEV), torch.tensor([0.25], device=DEV), dz, 32, 0, dbias=db, dalpha=da)
+    refz = df * torch.where(zf > 0, torch.ones_like(zf), torch.full_like(zf, 0.25))
+    res.append(result("prelu_plane_bwd", rel_err(dz[:, 0].float(), refz.reshape(-1)), 4e-3))
+    res.append(result("prelu_plane_dbias", rel_err(db[0], refz.sum()), 1e-4))
+    res.append(result("prelu_plane_dalpha", rel_err(da[0], (df * torch.where(zf > 0, torch.zeros_like(zf), zf)).sum()), 1e-4))
+    res.append(result("prelu_plane_untouched", float(dz[:, 1:].abs().max()), 0.0))
+    # LayerNorm backward
+    for C in (64, 128, 320, 512):
+        x = (rnd(333, C, seed=C, scale=2.0) + 0.3).bfloat16().float()
+        dy = rnd(333, C, seed=C + 7)
+        gam = 1 + 0.1 * rnd(C, seed=C + 8, bf16=False)
+        xr = x.clone().requires_grad_(True)
+        gr = gam.clone().requires_grad_(True)
+        br = torch.zeros(C, requires_grad=True)
+        F.layer_norm(xr, (C,), gr, br, 1e-5).backward(dy)
+        for dt, tol in ((torch.bfloat16, 6e-3), (torch.float32, 2e-5)):
+            dx = torch.empty((333, C), dtype=dt, device=DEV)
+            dg, dbt, dxs = (torch.zeros((C,), device=DEV) for _ in range(3))
+            ops.layernorm_bwd(x.to(dt).to(DEV), dy.to(dt).to(DEV), C, 0, gam.to(DEV), 1e-5, dx, C, 0, 333, C, dgamma=dg, dbeta=dbt, dxsum=dxs)
+            tag = f"C{C}_{'bf16' if dt == torch.bfloat16 else 'f32'}"
+            res.append(result(f"layernorm_bwd_dx_{tag}", rel_err(dx.float(), xr.grad), tol))
+            res.append(result(f"layernorm_bwd_dgamma_{tag}", rel_err(dg, gr.grad), 1e-4))
+            res.append(result(f"layernorm_bwd_dbeta_{tag}", rel_err(dbt, br.grad), 1e-4))
+            res.append(result(f"layernorm_bwd_dxsum_{tag}", float((dxs.cpu() - dx.float().sum(0).cpu()).abs().max()) / (float(xr.grad.abs().max()) * 333), 1e-3))
+    return res
+
+
+# ----------------------------------------------------------------------------------------- wgrad / dgrad / AdamW
+@check
+def conv_weight_and_data_gradients():
+    from segmif_b200.core.fusion_train import _conv_dgrad, _dgrad_pack, _zeros_bias  # noqa: F401
+    res = []
+    for (B, H, W, Cin, Cout, dil) in ((2, 24, 40, 64, 32, 2), (1, 19, 37, 96, 32, 2), (2, 16, 32, 224, 32, 2), (1, 24, 24, 128, 64, 1),
+                                      (1, 20, 28, 32, 32, 1), (1, 17, 23, 8, 64, 1)):
+        x = rnd(B, Cin, H, W, seed=Cin + dil)
+        dy = rnd(B, Cout, H, W, seed=Cin + 11)
+        w = (rnd(Cout, Cin, 3, 3, seed=Cin + 3, scale=0.1)).requires_grad_(True)
+        xr = x.clone().requires_grad_(True)
+        F.conv2d(xr, w, None, padding=dil, dilation=dil).backward(dy)
+        xp = x.permute(0, 2, 3, 1).contiguous().bfloat16().to(DEV)
+        dyp = dy.permute(0, 2, 3, 1).reshape(-1, Cout).contiguous().bfloat16().to(DEV)
+        grad = torch.zeros((Cout, Cin, 3, 3), device=DEV)
+        ops.wgrad(dyp, Cout, 0, xp, Cin, 0, B=B, H=H, W=W, Cin=Cin, Cout=Cout, taps=9, dil=dil, grad=grad, s_co=Cin * 9, s_tap=1, s_ci=9)
+        res.append(result(f"wgrad3x3_{Cin}to{Cout}_d{dil}_{H}x{W}", rel_err(grad, w.grad), 1e-3))
+        ops.wgrad(dyp, Cout, 0, xp, Cin, 0, B=B, H=H, W=W, Cin=Cin, Cout=Cout, taps=9, dil=dil, grad=grad, s_co=Cin * 9, s_tap=1, s_ci=9)
+        res.append(result(f"wgrad3x3_accumulates_{Cin}to{Cout}", rel_err(grad, 2 * w.grad), 1e-3))
+        if Cin % 32 == 0:
+            dx = torch.empty((B * H * W, Cin), dtype=torch.bfloat16, device=DEV)
+            _conv_dgrad(dyp, Cout, _dgrad_pack(w).to(DEV), B, H, W, dil, dx, Cin, 0, accumulate=False)
+            ref = xr.grad.permute(0, 2, 3, 1).reshape(-1, Cin)
+            res.append(result(f"dgrad3x3_{Cin}to{Cout}_d{dil}", rel_err(dx.float(), ref), 5e-3))
+            base = rnd(B * H * W, Cin, seed=77)
+            dx2 = base.bfloat16().to(DEV)
+            _conv_dgrad(dyp, Cout, _dgrad_pack(w).to(DEV), B, H, W, dil, dx2, Cin, 0, accumulate=True)
+            res.append(result(f"dgrad3x3_inplace_accumulate_{Cin}to{Cout}", rel_err(dx2.float(), ref + base), 6e-3))
+    for (P, K, N) in ((1000, 64, 128), (777, 224, 64), (4096, 128, 64), (50, 64, 64)):
+        x = rnd(P, K, seed=K)
+        dy = rnd(P, N, seed=N + 1)
+        grad = torch.zeros((N, K), device=DEV)
+        ops.wgrad(dy.bfloat16().to(DEV), N, 0, x.bfloat16().to(DEV), K, 0, B=1, H=1, W=1, P=P, Cin=K, Cout=N, taps=1, dil=1,
+                  grad=grad, s_co=K, s_tap=1, s_ci=1)
+        res.append(result(f"wgrad_linear_{P}x{K}x{N}", rel_err(grad, dy.t() @ x), 1e-3))
+    # slices: dy / x inside wider pitches, co_take / ci_take
+    x = rnd(1, 16, 24, 40, seed=5)
+    dy = rnd(1, 16, 24, 64, seed=6)
+    grad = torch.zeros((1, 8, 3, 3), device=DEV)
+    ops.wgrad(dy.bfloat16().to(DEV).reshape(-1, 64), 64, 32, x.bfloat16().to(DEV), 40, 8, B=1, H=16, W=24, Cin=8, Cout=32, taps=9,
+              dil=1, grad=grad, s_co=72, s_tap=1, s_ci=9, co_take=1)
+    xs = x[..., 8:16].permute(0, 3, 1, 2).clone()
+    ws = torch.zeros(1, 8, 3, 3, requires_grad=True)
+    F.conv2d(xs, ws, None, padding=1).backward(dy[..., 32:33].permute(0, 3, 1, 2))
+    res.append(result("wgrad3x3_slices_co_take", rel_err(grad, ws.grad), 1e-3))
+    return res
+
+
+@check
+def adamw_kernel():
+    n = 10007
+    p0 = rnd(n, seed=1, bf16=False)
+    p = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([p], lr=3e-4, betas=(0.9, 0.999), weight_decay=0.01, eps=1e-8)
+    pd = p0.clone().to(DEV)
+    m, v = torch.zeros_like(pd), torch.zeros_like(pd)
+    for t in range(1, 6):
+        g = rnd(n, seed=10 + t, bf16=False)
+        p.grad = g.clone() * 0.5
+        opt.step()
+        ops.adamw_step(pd, g.to(DEV), m, v, lr=3e-4, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.01, step=t, grad_scale=0.5)
+    return [result("adamw_5_steps_param", rel_err(pd, p.detach()), 1e-6),
+            result("adamw_5_steps_update", rel_err(pd.cpu() - p0, p.detach() - p0), 1e-4)]
+
+
+# ----------------------------------------------------------------------------------------- module-level backward
+def _param_grads_oracle(loss_fn, sd, names):
+    leaves = {k: sd[k].clone().requires_grad_(True) for k in names}
+    full = dict(sd)
+    full.update(leaves)
+    loss_fn(full).backward()
+    return {k: v.grad for k, v in leaves.items()}
+
+
+def _fusion_case(B=1, H=64, W=96, seed=0):
+    from segmif_b200.core.model_fusion import Fusion_Network3_ac
+    fus = synth.load_synthetic(Fusion_Network3_ac(), seed)
+    sd = {k: v.clone() for k, v in fus.state_dict().items()}
+    inp = synth.synth_inputs(B, H, W, seed=seed)
+    g = torch.Generator().manual_seed(seed + 50)
+    out1 = (torch.randn(B, 64, H, W, generator=g) * 0.5).bfloat16().float()
+    out2 = (torch.randn(B, 128, H, W, generator=g) * 0.5).bfloat16().float()
+    vis = O.rgb2ycrcb(inp["vis"])
+    return fus, sd, inp, vis, out1, out2
+
+
+@check
+def fusion_network_backward():
+    """Every parameter gradient of Fusion_Network3_ac under Fusionloss3 (train.py round 1) and Fusionloss_grad3
+    against autograd over the oracle."""
+    from segmif_b200.core.loss import Fusionloss3, Fusionloss_grad3
+    res = []
+    for B, H, W, cls, ofn in ((1, 64, 96, Fusionloss3, O.fusionloss3), (2, 40, 56, Fusionloss_grad3, O.fusionloss_grad3)):
+        fus, sd, inp, vis, out1, out2 = _fusion_case(B, H, W, seed=B)
+        names = [k for k, _ in fus.named_parameters() if not k.startswith("ffm2.")]
+        ref = _param_grads_oracle(lambda s: ofn(inp["ir"], vis, O.fusion_network3_ac(inp["ir"], vis, out1, out2, s), inp["mask"]), sd, names)
+        net = copy.deepcopy(fus).to(DEV).train()
+        fused = net(inp["ir"].to(DEV), vis.to(DEV), out1.to(DEV), out2.to(DEV))
+        with torch.no_grad():
+            fref = O.fusion_network3_ac(inp["ir"], vis, out1, out2, sd)
+        res.append(result(f"train_forward_fused_{cls.__name__}", rel_err(fused, fref), 3e-2))
+        loss = cls()(inp["ir"].to(DEV), vis.to(DEV), fused, inp["mask"].to(DEV))
+        loss.backward()
+        worst, worst_name = 0.0, ""
+        got = dict(net.named_parameters())
+        groups = {}
+        for k in names:
+            if got[k].grad is None:
+                res.append(result(f"grad_missing_{k}", float("nan"), 0.0))
+                continue
+            e = rel_err(got[k].grad, ref[k])
+            grp = k.split(".")[0] + ("." + k.split(".")[2] if k.startswith("ffm.") else "")
+            groups[grp] = max(groups.get(grp, 0.0), e)
+            if e > worst:
+                worst, worst_name = e, k
+        for grp, e in sorted(groups.items()):
+            res.append(result(f"grad_{cls.__name__}_{grp}", e, 6e-2))
+        res.append(result(f"grad_worst_{cls.__name__}", worst, 6e-2, note=worst_name))
+        res.append(result(f"ffm2_untouched_{cls.__name__}", 0.0 if all(p.grad is None for k, p in got.items() if k.startswith("ffm2.")) else 1.0, 0.0))
+    return res
+
+
+@check
+def fusion_trainer_steps():
+    """Three optimisation steps of FusionTrainer (flat gradient buffer + fused AdamW) against torch.optim.AdamW over
+    the oracle's autograd gradients: loss trajectory and parameter updates."""
+    from segmif_b200.core.loss import Fusionloss3
+    from segmif_b200.ddp import FusionTrainer
+    fus, sd, inp, vis, out1, out2 = _fusion_case(1, 48, 64, seed=3)
+    names = [k for k, _ in fus.named_parameters() if not k.startswith("ffm2.")]
+    leaves = {k: sd[k].clone().requires_grad_(True) for k in names}
+    opt = torch.optim.AdamW(list(leaves.values()), lr=3e-4, betas=(0.9, 0.999), weight_decay=0.01, eps=1e-8)
+    ref_losses = []
+    for it in range(3):
+        full = dict(sd)
+        full.update(leaves)
+        opt.param_groups[0]["lr"] = 3e-4 * (1e-6 if it == 0 else (1 - it / 100.0))     # utils/optimizer.py:16-27
+        opt.zero_grad()
+        l = O.fusionloss3(inp["ir"], vis, O.fusion_network3_ac(inp["ir"], vis, out1, out2, full), inp["mask"])
+        l.backward()
+        opt.step()
+        ref_losses.append(float(l))
+    net = copy.deepcopy(fus).to(DEV).train()
+    tr = FusionTrainer(net, Fusionloss3(), lr=3e-4, weight_decay=0.01, betas=(0.9, 0.999), warmup_iter=3e-5, max_iter=100,
+                       warmup_ratio=1e-6, power=1.0)
+    got_losses = []
+    args = [t.to(DEV) for t in (inp["ir"], vis, out1, out2, inp["mask"])]
+    for it in range(3):
+        l, _ = tr.step(*args)
+        got_losses.append(float(l))
+    res = [result("trainer_loss_trajectory", max(abs(a - b) / abs(b) for a, b in zip(got_losses, ref_losses)), 2e-2,
+                  note=f"{got_losses} vs {ref_losses}")]
+    # parameter updates: sign-SGD-like first steps of Adam make the update direction the sensitive quantity
+    num = den = 0.0
+    agree = tot = 0
+    for k, p in net.named_parameters():
+        if k.startswith("ffm2."):
+            continue
+        du, dr = (p.detach().cpu() - sd[k]), (leaves[k].detach() - sd[k])
+        num += float((du - dr).pow(2).sum())
+        den += float(dr.pow(2).sum())
+        agree += int((torch.sign(du) == torch.sign(dr)).sum())
+        tot += du.numel()
+    res.append(result("trainer_update_rel_l2", (num / den) ** 0.5, 0.35, note=f"sign agreement {agree / tot:.3f}"))
+    res.append(result("trainer_ffm2_frozen", max(float((p.detach().cpu() - sd[k]).abs().max()) for k, p in net.named_parameters() if k.startswith("ffm2.")), 0.0))
+    res.append(result("trainer_lr_schedule", abs(tr.opt.lr - 3e-4 * (1 - 2 / 100.0)) / 3e-4, 1e-6))
+    return res

@@ -1,0 +1,103 @@
+"""Host-side logic of the data-parallel training path, exercised with world_size 2 over gloo on CPU: the flat
+parameter / gradient buffers, the single all-reduce, exclusion of parameters that never receive gradients, and the
+PolyWarmup schedule.  (The fused AdamW kernel itself is CUDA-only and is checked on the GPU.)"""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+
+
+class _Toy(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        torch.manual_seed(0)
+        self.a = torch.nn.Linear(4, 3)
+        self.ffm2 = torch.nn.Linear(4, 3)          # never used, like Fusion_Network3_ac.ffm2
+        self.b = torch.nn.Conv2d(2, 2, 3)
+
+    def forward(self, x, img):
+        return self.a(x).sum() + self.b(img).sum()
+
+
+def _worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from segmif_b200.ddp import FlatParams
+    m = _Toy()
+    before = {k: p.detach().clone() for k, p in m.named_parameters()}
+    flat = FlatParams(m, used=lambda k: not k.startswith("ffm2."))
+    assert flat.skipped == ["ffm2.weight", "ffm2.bias"]
+    for k, p in m.named_parameters():                       # values preserved, storage re-homed
+        assert torch.equal(p.detach(), before[k])
+        if not k.startswith("ffm2."):
+            off, n = flat.offsets[k]
+            assert p.data_ptr() == flat.param.data_ptr() + 4 * off
+    flat.zero_grad()
+    g = torch.Generator().manual_seed(100 + rank)          # each rank sees its own shard of the batch
+    x, img = torch.randn(5, 4, generator=g), torch.randn(2, 2, 6, 6, generator=g)
+    m(x, img).backward()
+    local = flat.grad.clone()
+    assert m.ffm2.weight.grad is None
+    world_seen = flat.all_reduce()
+    assert world_seen == world
+    gathered = [torch.zeros_like(local) for _ in range(world)]
+    dist.all_gather(gathered, local)
+    assert torch.allclose(flat.grad, sum(gathered), atol=1e-6)
+    assert m.a.weight.grad.data_ptr() == flat.grad.data_ptr() + 4 * flat.offsets["a.weight"][0]   # still views
+    # a second step accumulates into the same (re-zeroed) buffer
+    flat.zero_grad()
+    assert float(flat.grad.abs().max()) == 0.0
+    m(x, img).backward()
+    assert torch.allclose(flat.grad, local, atol=1e-6)
+    if rank == 0:
+        torch.save(dict(ok=True, numel=flat.numel), out)
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_allreduce_world2(tmp_path):
+    out = str(tmp_path / "r0.pt")
+    port = 29500 + (os.getpid() % 500)
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    r = torch.load(out)
+    assert r["ok"] and r["numel"] == 4 * 3 + 3 + 2 * 2 * 9 + 2
+
+
+def test_poly_warmup_schedule_matches_reference_optimizer():
+    from segmif_b200.ddp import poly_warmup_lr
+    from segmif_b200.utils.optimizer import PolyWarmupAdamW
+    p = torch.nn.Parameter(torch.zeros(3))
+    for warm in (10, 3e-5):
+        opt = PolyWarmupAdamW([{"params": [p], "lr": 3e-4}], lr=3e-4, weight_decay=0.01, betas=(0.9, 0.999),
+                              warmup_iter=warm, max_iter=40, warmup_ratio=1e-6, power=1.0)
+        lr = 3e-4
+        for step in range(50):
+            p.grad = torch.ones(3)
+            opt.step()
+            lr = poly_warmup_lr(3e-4, step, warm, 40, 1e-6, 1.0, lr)
+            assert abs(lr - opt.param_groups[0]["lr"]) < 1e-15, (warm, step)
+
+
+def test_fusion_net_flat_params_exclude_ffm2():
+    from segmif_b200.core.model_fusion import Fusion_Network3_ac
+    from segmif_b200.ddp import FlatParams
+    net = Fusion_Network3_ac()
+    keys_before = list(net.state_dict().keys())
+    flat = FlatParams(net, used=lambda k: not k.startswith("ffm2."))
+    assert all(k.startswith("ffm2.") for k in flat.skipped) and flat.skipped
+    assert flat.numel == sum(p.numel() for k, p in net.named_parameters() if not k.startswith("ffm2."))
+    assert list(net.state_dict().keys()) == keys_before          # checkpoint surface unchanged
+
+
+def test_training_forward_refuses_cpu():
+    from segmif_b200.core.model_fusion import Fusion_Network3_ac
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    net = Fusion_Network3_ac().train()
+    with pytest.raises(RuntimeError, match="no CPU path|CUDA"):
+        net(torch.zeros(1, 1, 16, 16), torch.zeros(1, 3, 16, 16), torch.zeros(1, 64, 16, 16), torch.zeros(1, 128, 16, 16))

@@ -8,6 +8,7 @@ pytestmark = pytest.mark.gpu
 
 def _checks():
     import gpu_checks
+    import gpu_checks_train  # noqa: F401  (registers the training-side checks in the same list)
     return gpu_checks.CHECKS
 
 
@@ -20,8 +21,7 @@ def _names():
 
 @pytest.mark.parametrize("name", _names())
 def test_parity(name):
-    import gpu_checks
-    fn = {c.__name__: c for c in gpu_checks.CHECKS}[name]
+    fn = {c.__name__: c for c in _checks()}[name]
     res = fn()
     res = res if isinstance(res, list) else [res]
     torch.cuda.synchronize()

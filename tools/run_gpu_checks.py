@@ -8,8 +8,12 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import gpu_checks  # noqa: E402
+import gpu_checks_train  # noqa: E402,F401
 
 if __name__ == "__main__":
+    only = sys.argv[1:]
+    if only:
+        gpu_checks.CHECKS[:] = [c for c in gpu_checks.CHECKS if any(o in c.__name__ for o in only)]
     res = gpu_checks.run_all()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "gpu_checks.json"), "w") as f:

@@ -23,8 +23,9 @@ class FlatParams:
         if not self.named:
             raise ValueError("FlatParams: no parameters selected")
         dev = self.named[0][1].device
-        self.numel = sum(p.numel() for _, p in self.named)
-        self.param = torch.empty((self.numel,), dtype=torch.float32, device=dev)
+        pad4 = lambda n: (n + 3) & ~3              # every view starts 16-byte aligned (the kernels read biases / gains as float4)
+        self.numel = sum(pad4(p.numel()) for _, p in self.named)
+        self.param = torch.zeros((self.numel,), dtype=torch.float32, device=dev)
         self.grad = torch.zeros((self.numel,), dtype=torch.float32, device=dev)
         self.offsets = {}
         off = 0
@@ -35,7 +36,7 @@ class FlatParams:
                 p.data = self.param[off:off + n].view(p.shape)
                 p.grad = self.grad[off:off + n].view(p.shape)
                 self.offsets[k] = (off, n)
-                off += n
+                off += pad4(n)
 
     def zero_grad(self):
         self.grad.zero_()

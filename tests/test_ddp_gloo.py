@@ -65,7 +65,7 @@ def test_flat_gradient_allreduce_world2(tmp_path):
     port = 29500 + (os.getpid() % 500)
     mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
     r = torch.load(out)
-    assert r["ok"] and r["numel"] == 4 * 3 + 3 + 2 * 2 * 9 + 2
+    assert r["ok"] and r["numel"] == 12 + 4 + 36 + 4          # a.weight, a.bias (3 -> 4), b.weight, b.bias (2 -> 4)
 
 
 def test_poly_warmup_schedule_matches_reference_optimizer():
@@ -90,7 +90,8 @@ def test_fusion_net_flat_params_exclude_ffm2():
     keys_before = list(net.state_dict().keys())
     flat = FlatParams(net, used=lambda k: not k.startswith("ffm2."))
     assert all(k.startswith("ffm2.") for k in flat.skipped) and flat.skipped
-    assert flat.numel == sum(p.numel() for k, p in net.named_parameters() if not k.startswith("ffm2."))
+    assert flat.numel == sum((p.numel() + 3) // 4 * 4 for k, p in net.named_parameters() if not k.startswith("ffm2."))
+    assert all(off % 4 == 0 for off, _ in flat.offsets.values())
     assert list(net.state_dict().keys()) == keys_before          # checkpoint surface unchanged
 
 

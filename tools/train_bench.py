@@ -1,0 +1,88 @@
+"""Times the data-parallel train_fusion step (train.py:343-386, round 1: Fusionloss3; --loss grad3 for rounds >= 2 without
+the CE term): frozen-encoder forward_fusion (no_grad) -> Fusion_Network3_ac forward -> loss -> hand-written backward ->
+ONE gradient all-reduce -> fused AdamW.  Not the headline bench (bench.py measures BASELINE configs[1]); this is the
+configs[2] workload restricted to the fusion network, per-GPU batch 4 at 480x640.
+    python tools/train_bench.py [--batch 4] [--steps 10]            # 1 GPU
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/train_bench.py"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=4)
+    ap.add_argument("--height", type=int, default=480)
+    ap.add_argument("--width", type=int, default=640)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--backbone", default="mit_b2")
+    ap.add_argument("--loss", default="loss3", choices=["loss3", "grad3", "grad2"])
+    a = ap.parse_args()
+    from segmif_b200 import _lib, synth
+    from segmif_b200.core.loss import Fusionloss3, Fusionloss_grad2, Fusionloss_grad3
+    from segmif_b200.core.model_fusion import Fusion_Network3_ac, Network3, RGB2YCrCb
+    from segmif_b200.ddp import FusionTrainer
+    world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    seg = synth.load_synthetic(Network3(a.backbone, 9, 256, None), 0).eval().to(dev)
+    fus = synth.load_synthetic(Fusion_Network3_ac(), 0).train().to(dev)
+    crit = {"loss3": Fusionloss3, "grad3": Fusionloss_grad3, "grad2": Fusionloss_grad2}[a.loss]()
+    tr = FusionTrainer(fus, crit, lr=3e-4, weight_decay=0.01, betas=(0.9, 0.999), warmup_iter=3e-5, max_iter=6000,
+                       warmup_ratio=1e-6, power=1.0)
+    inp = {k: v.to(dev) for k, v in synth.synth_inputs(a.batch, a.height, a.width, seed=rank).items()}
+
+    def step():
+        with torch.no_grad():
+            vis = RGB2YCrCb(inp["vis"])                                              # train.py:356
+            out0, out1 = seg.denoise_net.encoder.forward_fusion(inp["mask"])         # train.py:358-359
+        return tr.step(inp["ir"], vis, out0, out1, inp["mask"])
+
+    losses = []
+    for _ in range(max(a.warmup, 1)):
+        losses.append(step()[0])
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = _lib.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        losses.append(step()[0])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        # replicas must stay bit-identical: same all-reduced gradients, same update
+        chk = tr.flat.param.double().sum().reshape(1)
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        in_sync = bool((hi - lo).abs().item() == 0.0)
+    else:
+        in_sync = True
+    if rank == 0:
+        ms = float(ms.item())
+        print(json.dumps({"metric": "train_fusion_pairs_per_sec", "value": a.batch * world * a.steps / (ms * 1e-3), "unit": "pairs/s",
+                          "n_gpus": world, "steps": a.steps, "ms_per_step": ms / a.steps, "batch_per_gpu": a.batch,
+                          "height": a.height, "width": a.width, "loss": a.loss, "scaling": "weak",
+                          "launches_per_step": (_lib.launch_count - l0) / a.steps, "replicas_in_sync": in_sync,
+                          "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30,
+                          "loss_first_last": [float(losses[0]), float(losses[-1])]}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -131,8 +131,8 @@ __global__ void __launch_bounds__(kFfmThreads) ffm_bwd_gram_kernel(const bf16* _
 }
 
 // ------------------------------------------------------------------------------------------------ (2) per-image algebra
-__device__ __forceinline__ void reduce_partials(float* dst, const float* src, int nchunk, int64_t stride, int tid) {
-  for (int idx = tid; idx < 4096; idx += 256) {
+__device__ __forceinline__ void reduce_partials(float* dst, const float* src, int nchunk, int64_t stride, int tid, int nthreads) {
+  for (int idx = tid; idx < 4096; idx += nthreads) {
     float a0 = 0.f, a1 = 0.f;
     int c = 0;
     for (; c + 2 <= nchunk; c += 2) { a0 += src[(int64_t)c * stride + idx]; a1 += src[(int64_t)(c + 1) * stride + idx]; }
@@ -141,108 +141,119 @@ __device__ __forceinline__ void reduce_partials(float* dst, const float* src, in
   }
 }
 
-__global__ void __launch_bounds__(256) ffm_bwd_ctx_kernel(const float* __restrict__ Rpart, int nchunkR,
-                                                          const float* __restrict__ Gpart, int nchunkG,
-                                                          const float* __restrict__ ctx, const float* __restrict__ wkv,
-                                                          const float* __restrict__ wend, const bf16* __restrict__ folded,
-                                                          bf16* __restrict__ mats, float* __restrict__ dwkv,
-                                                          float* __restrict__ dwend) {
+// grid (3, B): CTA (s, b) owns context stream s of image b (s = 0: kv1 / y1, 1: kv2 / y2, 2: kv3 / u3) and the folded
+// matrices that use it (m = 0 | 2 | {1, 3}), so the twelve CTAs of a batch of four run concurrently; Wk / Wv are staged
+// in shared memory (the inner products below walk them with stride 64).
+constexpr int kCtxThreads = 512;
+
+__global__ void __launch_bounds__(kCtxThreads) ffm_bwd_ctx_kernel(const float* __restrict__ Rpart, int nchunkR,
+                                                                  const float* __restrict__ Gpart, int nchunkG,
+                                                                  const float* __restrict__ ctx, const float* __restrict__ wkv,
+                                                                  const float* __restrict__ wend, const bf16* __restrict__ folded,
+                                                                  bf16* __restrict__ mats, float* __restrict__ dwkv,
+                                                                  float* __restrict__ dwend) {
   extern __shared__ float smf[];
   float* A0 = smf;             // reduced partial (R_m, then G_s)
   float* T = smf + 4096;       // Wk G
   float* U = smf + 8192;       // G Wv^T, then V
   float* DG = smf + 12288;
-  float* dctx = smf + 16384;   // [3][512]
-  float* dA = dctx + 1536;     // [512]  [h][i][j], scale folded in
-  const int b = blockIdx.x, tid = threadIdx.x;
-  for (int i = tid; i < 1536; i += 256) dctx[i] = 0.f;
+  float* sWk = smf + 16384;    // [64][65] padded
+  float* sWv = sWk + 64 * 65;
+  float* dctx = sWv + 64 * 65; // [512]
+  float* dA = dctx + 512;      // [512]  [h][i][j], scale folded in
+  float* sWe = dA + 512;       // [64][8*8 + 1]: the We columns of the current m (64 rows x 64 cols), padded
+  const int s = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const float* cx = ctx + ((int64_t)b * 3 + s) * 512;
+  for (int i = tid; i < 512; i += kCtxThreads) dctx[i] = 0.f;
+  {
+    const float* Wk = wkv + (int64_t)s * 128 * 64;
+    for (int i = tid; i < 4096; i += kCtxThreads) { sWk[(i >> 6) * 65 + (i & 63)] = Wk[i]; sWv[(i >> 6) * 65 + (i & 63)] = Wk[4096 + i]; }
+  }
   __syncthreads();
-  for (int m = 0; m < 4; ++m) {
-    reduce_partials(A0, Rpart + ((int64_t)b * nchunkR * 4 + m) * 4096, nchunkR, 4 * 4096, tid);
-    __syncthreads();
-    const int stream = m >> 1, is_v = m & 1, src = is_v ? 2 : stream;
-    const float* cx = ctx + ((int64_t)b * 3 + src) * 512;
+  const int nm = s == 2 ? 2 : 1;
+  for (int q = 0; q < nm; ++q) {
+    const int m = s == 2 ? 1 + 2 * q : 2 * s;             // folded matrix index: Mz1, Mv1, Mz2, Mv2
+    const int stream = m >> 1, is_v = m & 1;
+    reduce_partials(A0, Rpart + ((int64_t)b * nchunkR * 4 + m) * 4096, nchunkR, 4 * 4096, tid, kCtxThreads);
     const float* We = wend + (int64_t)stream * 64 * 128 + (is_v ? 64 : 0);
-    for (int idx = tid; idx < 4096; idx += 256) {           // dW_end[o][h8+j] += sum_i dM[o][h8+i] ctx[h][i][j]
+    for (int i = tid; i < 4096; i += kCtxThreads) sWe[(i >> 6) * 65 + (i & 63)] = We[(i >> 6) * 128 + (i & 63)];
+    __syncthreads();
+    for (int idx = tid; idx < 4096; idx += kCtxThreads) {    // dW_end[o][h8+j] += sum_i dM[o][h8+i] ctx[h][i][j]
       const int o = idx >> 6, c = idx & 63, h = c >> 3, j = c & 7;
       float a = 0.f;
 #pragma unroll
       for (int i = 0; i < 8; ++i) a = fmaf(A0[o * 64 + h * 8 + i], cx[h * 64 + i * 8 + j], a);
       atomicAdd(dwend + (int64_t)stream * 64 * 128 + o * 128 + (is_v ? 64 : 0) + c, a);
     }
-    for (int idx = tid; idx < 512; idx += 256) {            // d ctx[h][i][j] += sum_o dM[o][h8+i] We[o][h8+j]
+    {                                                        // d ctx[h][i][j] += sum_o dM[o][h8+i] We[o][h8+j]
+      const int idx = tid;                                   // kCtxThreads == 512 == number of context entries
       const int h = idx >> 6, i = (idx >> 3) & 7, j = idx & 7;
       float a = 0.f;
 #pragma unroll 8
-      for (int o = 0; o < 64; ++o) a = fmaf(A0[o * 64 + h * 8 + i], We[o * 128 + h * 8 + j], a);
-      dctx[src * 512 + idx] += a;
+      for (int o = 0; o < 64; ++o) a = fmaf(A0[o * 64 + h * 8 + i], sWe[o * 65 + h * 8 + j], a);
+      dctx[idx] += a;
     }
     __syncthreads();
   }
   const float scale = 0.35355339059327379f;
-  for (int s = 0; s < 3; ++s) {
-    const float* cx = ctx + ((int64_t)b * 3 + s) * 512;
-    if (tid < 64) {                                         // softmax (over i) backward for every (h, j)
-      const int h = tid >> 3, j = tid & 7;
-      float dot = 0.f;
-      for (int i = 0; i < 8; ++i) dot = fmaf(dctx[s * 512 + h * 64 + i * 8 + j], cx[h * 64 + i * 8 + j], dot);
-      for (int i = 0; i < 8; ++i) dA[h * 64 + i * 8 + j] = scale * cx[h * 64 + i * 8 + j] * (dctx[s * 512 + h * 64 + i * 8 + j] - dot);
-    }
-    reduce_partials(A0, Gpart + ((int64_t)b * nchunkG * 3 + s) * 4096, nchunkG, 3 * 4096, tid);
-    __syncthreads();
-    const float* Wk = wkv + (int64_t)s * 128 * 64;
-    const float* Wv = Wk + 64 * 64;
-    for (int idx = tid; idx < 4096; idx += 256) {
-      const int r = idx >> 6, c = idx & 63;
-      float t = 0.f, u = 0.f;
-#pragma unroll 8
-      for (int k = 0; k < 64; ++k) {
-        t = fmaf(Wk[r * 64 + k], A0[k * 64 + c], t);        // T[r][c] = sum_k Wk[r][k] G[k][c]
-        u = fmaf(A0[r * 64 + k], Wv[c * 64 + k], u);        // U[r][c] = sum_k G[r][k] Wv[c][k]
-      }
-      T[idx] = t;
-      U[idx] = u;
-    }
-    __syncthreads();
-    for (int idx = tid; idx < 4096; idx += 256) {
-      const int a = idx >> 6, c = idx & 63, h = a >> 3, ij = a & 7;
-      float dk = 0.f, dv = 0.f;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        dk = fmaf(dA[h * 64 + ij * 8 + q], U[c * 64 + h * 8 + q], dk);     // dWk[8h+i][c] = sum_j dA[h][i][j] U[c][8h+j]
-        dv = fmaf(dA[h * 64 + q * 8 + ij], T[(h * 8 + q) * 64 + c], dv);   // dWv[8h+j][c] = sum_i dA[h][i][j] T[8h+i][c]
-      }
-      atomicAdd(dwkv + (int64_t)s * 8192 + a * 64 + c, dk);
-      atomicAdd(dwkv + (int64_t)s * 8192 + 4096 + a * 64 + c, dv);
-    }
-    __syncthreads();
-    for (int idx = tid; idx < 4096; idx += 256) {           // V[8h+i][c] = sum_j dA[h][i][j] Wv[8h+j][c]
-      const int a = idx >> 6, c = idx & 63, h = a >> 3, i = a & 7;
-      float v = 0.f;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v = fmaf(dA[h * 64 + i * 8 + j], Wv[(h * 8 + j) * 64 + c], v);
-      U[idx] = v;
-    }
-    __syncthreads();
-    for (int idx = tid; idx < 4096; idx += 256) {           // dG[c][c'] = sum_a Wk[a][c] V[a][c']
-      const int c = idx >> 6, c2 = idx & 63;
-      float v = 0.f;
-#pragma unroll 8
-      for (int a = 0; a < 64; ++a) v = fmaf(Wk[a * 64 + c], U[a * 64 + c2], v);
-      DG[idx] = v;
-    }
-    __syncthreads();
-    bf16* ms = mats + ((int64_t)b * 7 + s) * 4096;
-    for (int idx = tid; idx < 4096; idx += 256) {
-      const int c = idx >> 6, c2 = idx & 63;
-      ms[idx] = __float2bfloat16_rn(DG[idx] + DG[c2 * 64 + c]);
-    }
-    __syncthreads();
+  if (tid < 64) {                                           // softmax (over i) backward for every (h, j)
+    const int h = tid >> 3, j = tid & 7;
+    float dot = 0.f;
+    for (int i = 0; i < 8; ++i) dot = fmaf(dctx[h * 64 + i * 8 + j], cx[h * 64 + i * 8 + j], dot);
+    for (int i = 0; i < 8; ++i) dA[h * 64 + i * 8 + j] = scale * cx[h * 64 + i * 8 + j] * (dctx[h * 64 + i * 8 + j] - dot);
   }
-  for (int m = 0; m < 4; ++m) {                             // transposes of the folded forward matrices
+  reduce_partials(A0, Gpart + ((int64_t)b * nchunkG * 3 + s) * 4096, nchunkG, 3 * 4096, tid, kCtxThreads);
+  __syncthreads();
+  for (int idx = tid; idx < 4096; idx += kCtxThreads) {
+    const int r = idx >> 6, c = idx & 63;
+    float t = 0.f, u = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < 64; ++k) {
+      t = fmaf(sWk[r * 65 + k], A0[k * 64 + c], t);         // T[r][c] = sum_k Wk[r][k] G[k][c]
+      u = fmaf(A0[r * 64 + k], sWv[c * 65 + k], u);         // U[r][c] = sum_k G[r][k] Wv[c][k]
+    }
+    T[idx] = t;
+    U[idx] = u;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < 4096; idx += kCtxThreads) {
+    const int a = idx >> 6, c = idx & 63, h = a >> 3, ij = a & 7;
+    float dk = 0.f, dv = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      dk = fmaf(dA[h * 64 + ij * 8 + q], U[c * 64 + h * 8 + q], dk);     // dWk[8h+i][c] = sum_j dA[h][i][j] U[c][8h+j]
+      dv = fmaf(dA[h * 64 + q * 8 + ij], T[(h * 8 + q) * 64 + c], dv);   // dWv[8h+j][c] = sum_i dA[h][i][j] T[8h+i][c]
+    }
+    atomicAdd(dwkv + (int64_t)s * 8192 + a * 64 + c, dk);
+    atomicAdd(dwkv + (int64_t)s * 8192 + 4096 + a * 64 + c, dv);
+  }
+  __syncthreads();
+  for (int idx = tid; idx < 4096; idx += kCtxThreads) {     // V[8h+i][c] = sum_j dA[h][i][j] Wv[8h+j][c]
+    const int a = idx >> 6, c = idx & 63, h = a >> 3, i = a & 7;
+    float v = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v = fmaf(dA[h * 64 + i * 8 + j], sWv[(h * 8 + j) * 65 + c], v);
+    U[idx] = v;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < 4096; idx += kCtxThreads) {     // dG[c][c'] = sum_a Wk[a][c] V[a][c']
+    const int c = idx >> 6, c2 = idx & 63;
+    float v = 0.f;
+#pragma unroll 8
+    for (int a = 0; a < 64; ++a) v = fmaf(sWk[a * 65 + c], U[a * 64 + c2], v);
+    DG[idx] = v;
+  }
+  __syncthreads();
+  bf16* ms = mats + ((int64_t)b * 7 + s) * 4096;
+  for (int idx = tid; idx < 4096; idx += kCtxThreads) {
+    const int c = idx >> 6, c2 = idx & 63;
+    ms[idx] = __float2bfloat16_rn(DG[idx] + DG[c2 * 64 + c]);
+  }
+  for (int q = 0; q < nm; ++q) {                            // transposes of the folded forward matrices this CTA owns
+    const int m = s == 2 ? 1 + 2 * q : 2 * s;
     const bf16* f = folded + ((int64_t)b * 4 + m) * 4096;
     bf16* mt = mats + ((int64_t)b * 7 + 3 + m) * 4096;
-    for (int idx = tid; idx < 4096; idx += 256) mt[idx] = f[(idx & 63) * 64 + (idx >> 6)];
+    for (int idx = tid; idx < 4096; idx += kCtxThreads) mt[idx] = f[(idx & 63) * 64 + (idx >> 6)];
   }
 }
 
@@ -378,11 +389,11 @@ extern "C" int segmif_ffm_bwd_ctx(const float* r_partials, int nchunk_r, const f
                                   float* dwkv, float* dwend, int B, segmif_stream_t stream) {
   SEGMIF_REQUIRE(r_partials && g_partials && ctx && wkv && wend && folded && mats && dwkv && dwend, "ffm_bwd_ctx: null pointer");
   SEGMIF_REQUIRE(nchunk_r > 0 && nchunk_g > 0 && B > 0, "ffm_bwd_ctx: bad sizes");
-  const size_t smem = (size_t)(4 * 4096 + 1536 + 512) * sizeof(float);
+  const size_t smem = (size_t)(4 * 4096 + 3 * 64 * 65 + 2 * 512) * sizeof(float);
   static bool cfg = false;
   int rc = opt_in_smem((const void*)ffm_bwd_ctx_kernel, smem, "ffm_bwd_ctx", &cfg);
   if (rc) return rc;
-  ffm_bwd_ctx_kernel<<<B, 256, smem, as_stream(stream)>>>(r_partials, nchunk_r, g_partials, nchunk_g, ctx, wkv, wend,
+  ffm_bwd_ctx_kernel<<<dim3(3, B), kCtxThreads, smem, as_stream(stream)>>>(r_partials, nchunk_r, g_partials, nchunk_g, ctx, wkv, wend,
                                                           (const bf16*)folded, (bf16*)mats, dwkv, dwend);
   return check_launch("segmif_ffm_bwd_ctx");
 }

@@ -239,7 +239,8 @@ int segmif_sobel_l1_fwd(const float* x, const float* y, int B, int H, int W, flo
 int segmif_mse_l1_fwd(const float* x, const float* y, int64_t n, float* workspace, float* out,
                       segmif_stream_t stream);
 /* CE(ignore_index) over bilinearly upsampled logits: core/model_fusion.py:1095-1096 + train.py:156.
- * logits fp32 [B,h,w,nc] pixel-major, labels int64 [B,H,W]; out[0] = mean over non-ignored pixels. */
+ * logits fp32 [B,h,w,nc] pixel-major, labels int64 [B,H,W]; out[0] = mean over non-ignored pixels, out[1] = their
+ * number (the normaliser segmif_upsample_ce_bwd needs): `out` holds TWO floats. */
 int segmif_upsample_ce_fwd(const float* logits, int B, int h, int w, int nc, const int64_t* labels, int H, int W,
                            int ignore_index, float* workspace, float* out, segmif_stream_t stream);
 
@@ -290,7 +291,8 @@ int segmif_add_bf16(const void* a, int lda, int coffa, const void* b, int ldb, i
  * = the gradient of a bias added right before the norm) are accumulated; any may be NULL.  C in {64,128,320,512}. */
 int segmif_layernorm_bwd(const void* x, int x_dtype, const void* dy, int dy_dtype, int lddy, int coffdy,
                          const float* gamma, float eps, void* dx, int dx_dtype, int lddx, int coffdx, int64_t rows, int C,
-                         float* dgamma, float* dbeta, float* dxsum, segmif_stream_t stream);
+                         float* dgamma, float* dbeta, float* dxsum, int accumulate /* dx += instead of = */,
+                         segmif_stream_t stream);
 
 /* ---- weight gradient of nn.Conv2d (3x3, stride 1, 'same', dilation 1|2: DRDB Dcov1-5, conv1/2/21/22) and of
  * nn.Linear / 1x1 conv (taps = 1; pass B = 1, W = 16, H = ceil(P/16)) as one tensor-core contraction over all pixels:
@@ -330,6 +332,54 @@ int segmif_ffm_bwd_apply(const void* x1, int ld1, int coff1, const void* x2, int
 int segmif_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                       float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
                       segmif_stream_t stream);
+
+/* ---- segmentation-network training (train.py:115-245 train_seg; the CE term of train_fusion :368) ---------------
+ * sr_attention_train_fwd  = segmif_sr_attention_fwd that also stores the per-row log-sum-exp (exp2 domain) [B*heads, N].
+ * sr_attention_bwd        core/mix_transformer.py:107-111 backward: dq bf16 (same layout as q); dK / dV ADDED into the
+ *                         fp32 accumulator dkv [B, Nk, lddkv] (dK at column h*D, dV at v_off + h*D); D = 64.          */
+int segmif_sr_attention_train_fwd(const void* q, int ldq, const void* k, const void* v, int ldkv, void* out, int ldo,
+                                  int B, int heads, int N, int Nk, int D, float scale, float* lse, segmif_stream_t stream);
+int segmif_sr_attention_bwd(const void* q, int ldq, const void* k, const void* v, int ldkv, const void* out,
+                            const void* dout, int ldo, const float* lse, void* dq, int lddq, float* dkv, int lddkv,
+                            int v_off, int B, int heads, int N, int Nk, int D, float scale, segmif_stream_t stream);
+/* d logits of mean CrossEntropy(ignore_index) over bilinearly upsampled logits (core/model_fusion.py:1095-1096):
+ * gout = upstream gradient (device scalar), count = out[1] of segmif_upsample_ce_fwd; dlogits fp32 [B,h,w,nc].     */
+int segmif_upsample_ce_bwd(const float* logits, int B, int h, int w, int nc, const int64_t* labels, int H, int W,
+                           int ignore_index, const float* gout, const float* count, float* dlogits,
+                           segmif_stream_t stream);
+/* adjoint of segmif_bilinear_nhwc_fwd (core/segformer_head.py:67-73): ddst bf16 [B,H,W,ld_dst] slice -> dsrc [B,h,w,C] */
+int segmif_bilinear_nhwc_bwd(const void* ddst, int ld_dst, int dst_coff, int H, int W, void* dsrc, int B, int h, int w,
+                             int C, segmif_stream_t stream);
+/* train-mode nn.BatchNorm2d + ReLU of linear_fuse (core/segformer_head.py:50-55) over z bf16 [rows, C]: batch
+ * statistics (biased variance) -> stats fp32 [2][C] = {mean, rstd}; running_mean / running_var updated with `momentum`
+ * and the unbiased variance (either may be NULL); workspace = 2*C doubles zeroed by the caller.  Backward: dz, and
+ * dgamma / dbeta accumulated.                                                                                        */
+int segmif_bn_train_fwd(const void* z, int64_t rows, int C, const float* gamma, const float* beta, float eps,
+                        float momentum, float* running_mean, float* running_var, double* workspace, float* stats, void* y,
+                        segmif_stream_t stream);
+int segmif_bn_train_bwd(const void* z, const void* y, const void* dy, const float* stats, const float* gamma, int64_t rows,
+                        int C, double* workspace, void* dz, float* dgamma, float* dbeta, segmif_stream_t stream);
+/* y[b,p,c] = x[b,p,c] * scale[b,c]: nn.Dropout2d forward and backward (core/segformer_head.py:57,79), bf16 [B,HW,C]. */
+int segmif_channel_scale(const void* x, const float* scale, void* y, int B, int64_t HW, int C, segmif_stream_t stream);
+/* depthwise 3x3 without activation (flip != 0: transposed taps = the data gradient of DWConv, mix_transformer.py:381-387)
+ * and the backward of dwconv + GELU w.r.t. the pre-activation: dz = dy * gelu'(dwconv(x) + b), dw9c / dbias accumulated. */
+int segmif_dwconv3x3(const void* x, const float* w9c, const float* bias, void* y, int B, int H, int W, int C, int flip,
+                     segmif_stream_t stream);
+int segmif_dwconv3x3_gelu_bwd(const void* x, const float* w9c, const float* bias, const void* dy, void* dz, int B, int H,
+                              int W, int C, float* dw9c, float* dbias, segmif_stream_t stream);
+/* adjoint of im2col for the strided convolutions (OverlapPatchEmbed.proj mix_transformer.py:193, Attention.sr :100):
+ * dcol bf16 [B*Ho*Wo, ldc], column (c*k + ky)*k + kx  ->  dx [B,H,W,C] pixel-major (fp32 or bf16).                   */
+int segmif_col2im(const void* dcol, int ldc, void* dx, int dx_dtype, int B, int H, int W, int C, int k, int stride, int pad,
+                  segmif_stream_t stream);
+/* Network3.forward's x*255 / mean / std as its own op (core/model_fusion.py:1083-1085), the gradient of the colour
+ * recompose + clamp (train.py:364-366) w.r.t. the fused Y plane, dtype casts, and x + scale[sample] * y (DropPath). */
+int segmif_channel_affine_nchw(const float* x, const float* scale, const float* shift, float* y, int B, int C, int64_t HW,
+                               segmif_stream_t stream);
+int segmif_recompose_rgb_bwd(const float* rgb, const float* drgb, float* dfused, int clamp01, int B, int64_t HW,
+                             segmif_stream_t stream);
+int segmif_cast(const void* x, int x_dtype, void* y, int y_dtype, int64_t n, segmif_stream_t stream);
+int segmif_scale_add_rows(const float* x, const void* y, int y_dtype, const float* scale, float* out, int64_t rows,
+                          int64_t rows_per_sample, int C, segmif_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -104,7 +104,7 @@ SIGNATURES = {
     "segmif_prelu_plane_bwd": [P, P, c_int64, P, P, c_int, c_int, P, P, P],
     "segmif_colsum": [P, c_int, c_int, c_int64, c_int, P, P],
     "segmif_add_bf16": [P, c_int, c_int, P, c_int, c_int, P, c_int, c_int, c_int64, c_int, P],
-    "segmif_layernorm_bwd": [P, c_int, P, c_int, c_int, c_int, P, c_float, P, c_int, c_int, c_int, c_int64, c_int, P, P, P, P],
+    "segmif_layernorm_bwd": [P, c_int, P, c_int, c_int, c_int, P, c_float, P, c_int, c_int, c_int, c_int64, c_int, P, P, P, c_int, P],
     "segmif_wgrad_workspace_bytes": [c_int, c_int, c_int, c_int],
     "segmif_wgrad": [P, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int64, c_int, c_int, c_int, c_int, P, c_int, P,
                      c_int64, c_int64, c_int64, c_int, c_int, P],
@@ -114,6 +114,21 @@ SIGNATURES = {
     "segmif_ffm_bwd_ctx": [P, c_int, P, c_int, P, P, P, P, P, P, P, c_int, P],
     "segmif_ffm_bwd_apply": [P, c_int, c_int, P, c_int, c_int, P, c_int, c_int, P, P, P, P, P, P, P, P, c_int, c_int64, P],
     "segmif_adamw_step": [P, P, P, P, c_int64, c_float, c_float, c_float, c_float, c_float, c_int, c_float, P],
+    "segmif_sr_attention_train_fwd": [P, c_int, P, P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P, P],
+    "segmif_sr_attention_bwd": [P, c_int, P, P, c_int, P, P, c_int, P, P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int,
+                                c_int, c_float, P],
+    "segmif_upsample_ce_bwd": [P, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, P, P, P, P],
+    "segmif_bilinear_nhwc_bwd": [P, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, c_int, P],
+    "segmif_bn_train_fwd": [P, c_int64, c_int, P, P, c_float, c_float, P, P, P, P, P, P],
+    "segmif_bn_train_bwd": [P, P, P, P, P, c_int64, c_int, P, P, P, P, P],
+    "segmif_channel_scale": [P, P, P, c_int, c_int64, c_int, P],
+    "segmif_dwconv3x3": [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P],
+    "segmif_dwconv3x3_gelu_bwd": [P, P, P, P, P, c_int, c_int, c_int, c_int, P, P, P],
+    "segmif_col2im": [P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P],
+    "segmif_channel_affine_nchw": [P, P, P, P, c_int, c_int, c_int64, P],
+    "segmif_recompose_rgb_bwd": [P, P, P, c_int, c_int, c_int64, P],
+    "segmif_cast": [P, c_int, P, c_int, c_int64, P],
+    "segmif_scale_add_rows": [P, P, c_int, P, P, c_int64, c_int64, c_int, P],
 }
 _RESTYPES = {"segmif_last_error": c_char_p, "segmif_loss_workspace_bytes": c_size_t, "segmif_wgrad_workspace_bytes": c_size_t}
 

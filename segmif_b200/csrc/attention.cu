@@ -16,7 +16,7 @@ template <int D>
 __global__ void __launch_bounds__(128) sr_attention_kernel(const bf16* __restrict__ q, int ldq,
                                                            const bf16* __restrict__ k, const bf16* __restrict__ v,
                                                            int ldkv, bf16* __restrict__ out, int ldo, int heads, int N,
-                                                           int Nk, float scale_log2e) {
+                                                           int Nk, float scale_log2e, float* __restrict__ lse) {
   constexpr int BQ = 64, BK = 64, CH = D / 8;      // CH = 16-byte chunks per row
   constexpr int KS = D / 16;                       // k16 steps over head dim
   constexpr int NT_O = D / 8;                      // output n-tiles
@@ -158,6 +158,7 @@ __global__ void __launch_bounds__(128) sr_attention_kernel(const bf16* __restric
     const int row = q0 + warp * 16 + g + r * 8;
     if (row >= N) continue;
     const float inv = 1.f / l_run[r];
+    if (lse != nullptr && tq == 0) lse[(int64_t)bh * N + row] = m_run[r] + log2f(l_run[r]);   // exp2 domain, for the backward
     bf16* op = out + ((int64_t)b * N + row) * ldo + h * D + tq * 2;
 #pragma unroll
     for (int nt = 0; nt < NT_O; ++nt)
@@ -169,9 +170,8 @@ __global__ void __launch_bounds__(128) sr_attention_kernel(const bf16* __restric
 
 using namespace segmif;
 
-extern "C" int segmif_sr_attention_fwd(const void* q, int ldq, const void* k, const void* v, int ldkv, void* out,
-                                       int ldo, int B, int heads, int N, int Nk, int D, float scale,
-                                       segmif_stream_t stream) {
+static int sr_attention_impl(const void* q, int ldq, const void* k, const void* v, int ldkv, void* out, int ldo, int B,
+                             int heads, int N, int Nk, int D, float scale, float* lse, segmif_stream_t stream) {
   SEGMIF_REQUIRE(q && k && v && out, "sr_attention: null pointer");
   SEGMIF_REQUIRE(D == 64 || D == 32, "sr_attention: head dim %d unsupported (32 or 64)", D);
   SEGMIF_REQUIRE(ldq % 8 == 0 && ldkv % 8 == 0 && ldo % 2 == 0, "sr_attention: pitches must be multiples of 8");
@@ -180,8 +180,21 @@ extern "C" int segmif_sr_attention_fwd(const void* q, int ldq, const void* k, co
   dim3 grid((unsigned)ceil_div(N, 64), (unsigned)(B * heads));
   const float sl2 = scale * 1.4426950408889634f;
   if (D == 64)
-    sr_attention_kernel<64><<<grid, 128, 0, as_stream(stream)>>>((const bf16*)q, ldq, (const bf16*)k, (const bf16*)v, ldkv, (bf16*)out, ldo, heads, N, Nk, sl2);
+    sr_attention_kernel<64><<<grid, 128, 0, as_stream(stream)>>>((const bf16*)q, ldq, (const bf16*)k, (const bf16*)v, ldkv, (bf16*)out, ldo, heads, N, Nk, sl2, lse);
   else
-    sr_attention_kernel<32><<<grid, 128, 0, as_stream(stream)>>>((const bf16*)q, ldq, (const bf16*)k, (const bf16*)v, ldkv, (bf16*)out, ldo, heads, N, Nk, sl2);
+    sr_attention_kernel<32><<<grid, 128, 0, as_stream(stream)>>>((const bf16*)q, ldq, (const bf16*)k, (const bf16*)v, ldkv, (bf16*)out, ldo, heads, N, Nk, sl2, lse);
   return check_launch("segmif_sr_attention_fwd");
+}
+
+extern "C" int segmif_sr_attention_fwd(const void* q, int ldq, const void* k, const void* v, int ldkv, void* out,
+                                       int ldo, int B, int heads, int N, int Nk, int D, float scale,
+                                       segmif_stream_t stream) {
+  return sr_attention_impl(q, ldq, k, v, ldkv, out, ldo, B, heads, N, Nk, D, scale, nullptr, stream);
+}
+
+extern "C" int segmif_sr_attention_train_fwd(const void* q, int ldq, const void* k, const void* v, int ldkv, void* out,
+                                             int ldo, int B, int heads, int N, int Nk, int D, float scale, float* lse,
+                                             segmif_stream_t stream) {
+  SEGMIF_REQUIRE(lse, "sr_attention_train: the log-sum-exp output [B*heads, N] is required");
+  return sr_attention_impl(q, ldq, k, v, ldkv, out, ldo, B, heads, N, Nk, D, scale, lse, stream);
 }

@@ -326,8 +326,9 @@ __global__ void loss_epilogue_kernel(const double* __restrict__ sums, int mode, 
       out[0] = (float)(sums[0] * inv_n);
       out[1] = (float)(sums[1] * inv_n);
       break;
-    case 4:  // ratio (cross entropy: sum / count)
+    case 4:  // ratio (cross entropy: sum / count); out[1] = count (the backward's normaliser)
       out[0] = (float)(sums[0] / sums[1]);
+      out[1] = (float)sums[1];
       break;
   }
 }

@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TX* __restrict
                                                             const float* __restrict__ gamma, float eps,
                                                             TO* __restrict__ dx, int lddx, int64_t rows,
                                                             float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                            float* __restrict__ dxsum) {
+                                                            float* __restrict__ dxsum, int accumulate) {
   constexpr int C = NC * 32;
   __shared__ float sacc[3][C];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -182,7 +182,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TX* __restrict
     for (int i = 0; i < NC; ++i) {
       const float v = rstd * (dv[i] - s1 - xv[i] * s2);
       as[i] += v;
-      st_from_float(dx + r * lddx + lane + 32 * i, v);
+      TO* o = dx + r * lddx + lane + 32 * i;
+      st_from_float(o, accumulate ? ld_as_float(o) + v : v);      // accumulate: dx holds the residual-stream gradient
     }
   }
   for (int i = threadIdx.x; i < 3 * C; i += 256) (&sacc[0][0])[i] = 0.f;
@@ -398,11 +399,11 @@ extern "C" int segmif_add_bf16(const void* a, int lda, int coffa, const void* b,
 
 template <typename TX, typename TD, typename TO>
 static int launch_ln_bwd(const void* x, const void* dy, int lddy, const float* gamma, float eps, void* dx, int lddx,
-                         int64_t rows, int C, float* dgamma, float* dbeta, float* dxsum, cudaStream_t st) {
+                         int64_t rows, int C, float* dgamma, float* dbeta, float* dxsum, int accumulate, cudaStream_t st) {
   const int grid = grid_for(rows, 32);
 #define SEGMIF_LNB(NC)                                                                                                   \
   layernorm_bwd_kernel<TX, TD, TO, NC><<<grid, 256, 0, st>>>((const TX*)x, (const TD*)dy, lddy, gamma, eps, (TO*)dx, lddx, \
-                                                             rows, dgamma, dbeta, dxsum)
+                                                             rows, dgamma, dbeta, dxsum, accumulate)
   switch (C) {
     case 64: SEGMIF_LNB(2); break;
     case 128: SEGMIF_LNB(4); break;
@@ -416,16 +417,16 @@ static int launch_ln_bwd(const void* x, const void* dy, int lddy, const float* g
 
 extern "C" int segmif_layernorm_bwd(const void* x, int x_dtype, const void* dy, int dy_dtype, int lddy, int coffdy,
                                     const float* gamma, float eps, void* dx, int dx_dtype, int lddx, int coffdx,
-                                    int64_t rows, int C, float* dgamma, float* dbeta, float* dxsum,
+                                    int64_t rows, int C, float* dgamma, float* dbeta, float* dxsum, int accumulate,
                                     segmif_stream_t stream) {
   SEGMIF_REQUIRE(x && dy && gamma && dx && rows > 0, "layernorm_bwd: bad arguments");
   cudaStream_t st = as_stream(stream);
   if (x_dtype == SEGMIF_BF16 && dy_dtype == SEGMIF_BF16 && dx_dtype == SEGMIF_BF16)
-    return launch_ln_bwd<bf16, bf16, bf16>(x, (const bf16*)dy + coffdy, lddy, gamma, eps, (bf16*)dx + coffdx, lddx, rows, C, dgamma, dbeta, dxsum, st);
+    return launch_ln_bwd<bf16, bf16, bf16>(x, (const bf16*)dy + coffdy, lddy, gamma, eps, (bf16*)dx + coffdx, lddx, rows, C, dgamma, dbeta, dxsum, accumulate, st);
   if (x_dtype == SEGMIF_F32 && dy_dtype == SEGMIF_F32 && dx_dtype == SEGMIF_F32)
-    return launch_ln_bwd<float, float, float>(x, (const float*)dy + coffdy, lddy, gamma, eps, (float*)dx + coffdx, lddx, rows, C, dgamma, dbeta, dxsum, st);
+    return launch_ln_bwd<float, float, float>(x, (const float*)dy + coffdy, lddy, gamma, eps, (float*)dx + coffdx, lddx, rows, C, dgamma, dbeta, dxsum, accumulate, st);
   if (x_dtype == SEGMIF_F32 && dy_dtype == SEGMIF_BF16 && dx_dtype == SEGMIF_F32)
-    return launch_ln_bwd<float, bf16, float>(x, (const bf16*)dy + coffdy, lddy, gamma, eps, (float*)dx + coffdx, lddx, rows, C, dgamma, dbeta, dxsum, st);
+    return launch_ln_bwd<float, bf16, float>(x, (const bf16*)dy + coffdy, lddy, gamma, eps, (float*)dx + coffdx, lddx, rows, C, dgamma, dbeta, dxsum, accumulate, st);
   set_error("layernorm_bwd: unsupported dtype combination (x %d, dy %d, dx %d)", x_dtype, dy_dtype, dx_dtype);
   return SEGMIF_ERR_INVALID;
 }

@@ -438,14 +438,14 @@ def mse_l1(x, y):
     return out[0], out[1]
 
 
-def upsample_ce(logits_nhwc, B, h, w, nc, labels, ignore_index=255):
+def upsample_ce(logits_nhwc, B, h, w, nc, labels, ignore_index=255, return_count=False):
     st = _prep(logits_nhwc, labels)
     H, W = labels.shape[1], labels.shape[2]
     ws = _loss_ws(logits_nhwc, 1, 32, 32)
-    out = torch.empty((1,), dtype=torch.float32, device=labels.device)
+    out = torch.empty((2,), dtype=torch.float32, device=labels.device)       # {mean loss, number of valid labels}
     _lib.call("segmif_upsample_ce_fwd", _ptr(logits_nhwc), B, h, w, nc, _ptr(labels), H, W, int(ignore_index),
               _ptr(ws), _ptr(out), st)
-    return out[0]
+    return (out[0], out[1:2]) if return_count else out[0]
 
 
 # ---------------------------------------------------------------------------------------------- training side
@@ -552,10 +552,11 @@ def add_bf16(a, lda, coffa, b, ldb, coffb, out, ldo, coffo, rows, C):
     return out
 
 
-def layernorm_bwd(x, dy, lddy, coffdy, gamma, eps, dx, lddx, coffdx, rows, C, dgamma=None, dbeta=None, dxsum=None):
+def layernorm_bwd(x, dy, lddy, coffdy, gamma, eps, dx, lddx, coffdx, rows, C, dgamma=None, dbeta=None, dxsum=None,
+                  accumulate=False):
     st = _prep(x, dy, gamma, dx, dgamma, dbeta, dxsum)
     _lib.call("segmif_layernorm_bwd", _ptr(x), _dt(x), _ptr(dy), _dt(dy), lddy, coffdy, _ptr(gamma), float(eps), _ptr(dx),
-              _dt(dx), lddx, coffdx, rows, C, _ptr(dgamma), _ptr(dbeta), _ptr(dxsum), st)
+              _dt(dx), lddx, coffdx, rows, C, _ptr(dgamma), _ptr(dbeta), _ptr(dxsum), 1 if accumulate else 0, st)
     return dx
 
 
@@ -627,3 +628,131 @@ def adamw_step(param, grad, exp_avg, exp_avg_sq, *, lr, beta1, beta2, eps, weigh
     st = _prep(param, grad, exp_avg, exp_avg_sq)
     _lib.call("segmif_adamw_step", _ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), param.numel(), float(lr),
               float(beta1), float(beta2), float(eps), float(weight_decay), int(step), float(grad_scale), st)
+
+
+# ---------------------------------------------------------------------------------------------- segmentation-net training
+def sr_attention_train(q, kv, B, heads, N, Nk, D, scale):
+    """Forward as sr_attention, plus the per-row log-sum-exp (exp2 domain) the backward recomputes P from."""
+    st = _prep(q, kv)
+    C = heads * D
+    out = torch.empty((B * N, C), dtype=torch.bfloat16, device=q.device)
+    lse = torch.empty((B * heads, N), dtype=torch.float32, device=q.device)
+    kptr = kv.data_ptr()
+    _lib.call("segmif_sr_attention_train_fwd", _ptr(q), C, ctypes.c_void_p(kptr), ctypes.c_void_p(kptr + 2 * C), 2 * C,
+              _ptr(out), C, B, heads, N, Nk, D, float(scale), _ptr(lse), st)
+    return out, lse
+
+
+def sr_attention_bwd(q, kv, out, dout, lse, B, heads, N, Nk, D, scale):
+    """Returns (dq bf16 [B*N, C], dkv fp32 [B*Nk, 2C])."""
+    st = _prep(q, kv, out, dout, lse)
+    C = heads * D
+    dq = torch.empty((B * N, C), dtype=torch.bfloat16, device=q.device)
+    dkv = torch.zeros((B * Nk, 2 * C), dtype=torch.float32, device=q.device)
+    kptr = kv.data_ptr()
+    _lib.call("segmif_sr_attention_bwd", _ptr(q), C, ctypes.c_void_p(kptr), ctypes.c_void_p(kptr + 2 * C), 2 * C, _ptr(out),
+              _ptr(dout), C, _ptr(lse), _ptr(dq), C, _ptr(dkv), 2 * C, C, B, heads, N, Nk, D, float(scale), st)
+    return dq, dkv
+
+
+def upsample_ce_bwd(logits_nhwc, B, h, w, nc, labels, gout, count, ignore_index=255):
+    g = _gout(gout, 1, logits_nhwc)
+    st = _prep(logits_nhwc, labels, g, count)
+    H, W = labels.shape[1], labels.shape[2]
+    dl = torch.empty_like(logits_nhwc)
+    _lib.call("segmif_upsample_ce_bwd", _ptr(logits_nhwc), B, h, w, nc, _ptr(labels), H, W, int(ignore_index), _ptr(g),
+              _ptr(count), _ptr(dl), st)
+    return dl
+
+
+def bilinear_nhwc_bwd(ddst, ld_dst, dst_coff, B, H, W, h, w, C):
+    """Adjoint of bilinear_nhwc: ddst bf16 [B, H, W, ld_dst] slice -> dsrc bf16 [B, h, w, C]."""
+    st = _prep(ddst)
+    dsrc = torch.empty((B, h, w, C), dtype=torch.bfloat16, device=ddst.device)
+    _lib.call("segmif_bilinear_nhwc_bwd", _ptr(ddst), ld_dst, dst_coff, H, W, _ptr(dsrc), B, h, w, C, st)
+    return dsrc
+
+
+def bn_train_fwd(z, gamma, beta, eps, momentum, running_mean, running_var):
+    """Train-mode BatchNorm + ReLU over rows of z bf16 [rows, C]; returns (y bf16, stats fp32 [2, C] = mean, rstd)."""
+    st = _prep(z, gamma, beta, running_mean, running_var)
+    rows, C = z.shape
+    ws = torch.zeros((2 * C,), dtype=torch.float64, device=z.device)
+    stats = torch.empty((2, C), dtype=torch.float32, device=z.device)
+    y = torch.empty_like(z)
+    _lib.call("segmif_bn_train_fwd", _ptr(z), rows, C, _ptr(gamma), _ptr(beta), float(eps), float(momentum),
+              _ptr(running_mean), _ptr(running_var), _ptr(ws), _ptr(stats), _ptr(y), st)
+    return y, stats
+
+
+def bn_train_bwd(z, y, dy, stats, gamma, dgamma, dbeta):
+    st = _prep(z, y, dy, stats, gamma, dgamma, dbeta)
+    rows, C = z.shape
+    ws = torch.zeros((2 * C,), dtype=torch.float64, device=z.device)
+    dz = torch.empty_like(z)
+    _lib.call("segmif_bn_train_bwd", _ptr(z), _ptr(y), _ptr(dy), _ptr(stats), _ptr(gamma), rows, C, _ptr(ws), _ptr(dz),
+              _ptr(dgamma), _ptr(dbeta), st)
+    return dz
+
+
+def channel_scale(x, scale, B, HW, C, out=None):
+    st = _prep(x, scale, out)
+    out = torch.empty_like(x) if out is None else out
+    _lib.call("segmif_channel_scale", _ptr(x), _ptr(scale), _ptr(out), B, HW, C, st)
+    return out
+
+
+def dwconv3x3(x, w9c, bias, B, H, W, flip=False):
+    st = _prep(x, w9c, bias)
+    y = torch.empty_like(x)
+    _lib.call("segmif_dwconv3x3", _ptr(x), _ptr(w9c), _ptr(bias), _ptr(y), B, H, W, x.shape[-1], 1 if flip else 0, st)
+    return y
+
+
+def dwconv3x3_gelu_bwd(x, w9c, bias, dy, B, H, W, dw9c, dbias):
+    st = _prep(x, w9c, bias, dy, dw9c, dbias)
+    dz = torch.empty_like(x)
+    _lib.call("segmif_dwconv3x3_gelu_bwd", _ptr(x), _ptr(w9c), _ptr(bias), _ptr(dy), _ptr(dz), B, H, W, x.shape[-1],
+              _ptr(dw9c), _ptr(dbias), st)
+    return dz
+
+
+def col2im(dcol, B, H, W, C, k, stride, pad, out_dtype=torch.bfloat16):
+    st = _prep(dcol)
+    dx = torch.empty((B, H, W, C), dtype=out_dtype, device=dcol.device)
+    _lib.call("segmif_col2im", _ptr(dcol), dcol.shape[-1], _ptr(dx), _dt(dx), B, H, W, C, k, stride, pad, st)
+    return dx
+
+
+def channel_affine_nchw(x, scale, shift):
+    st = _prep(x, scale, shift)
+    y = torch.empty_like(x)
+    B, C = x.shape[0], x.shape[1]
+    _lib.call("segmif_channel_affine_nchw", _ptr(x), _ptr(scale), _ptr(shift), _ptr(y), B, C, x.numel() // (B * C), st)
+    return y
+
+
+def recompose_rgb_bwd(rgb, drgb, clamp=True):
+    st = _prep(rgb, drgb)
+    B, _, H, W = rgb.shape
+    d = torch.empty((B, 1, H, W), dtype=torch.float32, device=rgb.device)
+    _lib.call("segmif_recompose_rgb_bwd", _ptr(rgb), _ptr(drgb), _ptr(d), 1 if clamp else 0, B, H * W, st)
+    return d
+
+
+def cast(x, dtype):
+    if x.dtype == dtype:
+        return x
+    st = _prep(x)
+    y = torch.empty(x.shape, dtype=dtype, device=x.device)
+    _lib.call("segmif_cast", _ptr(x), _dt(x), _ptr(y), _dt(y), x.numel(), st)
+    return y
+
+
+def scale_add_rows(x, y, scale, rows_per_sample):
+    """x fp32 [rows, C] + scale[row // rows_per_sample] * y  (scale None -> 1)."""
+    st = _prep(x, y, scale)
+    C = x.shape[-1]
+    out = torch.empty_like(x)
+    _lib.call("segmif_scale_add_rows", _ptr(x), _ptr(y), _dt(y), _ptr(scale), _ptr(out), x.numel() // C, rows_per_sample, C, st)
+    return out

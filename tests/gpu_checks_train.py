@@ -325,3 +325,146 @@ def fusion_trainer_steps():
     res.append(result("trainer_ffm2_frozen", max(float((p.detach().cpu() - sd[k]).abs().max()) for k, p in net.named_parameters() if k.startswith("ffm2.")), 0.0))
     res.append(result("trainer_lr_schedule", abs(tr.opt.lr - 3e-4 * (1 - 2 / 100.0)) / 3e-4, 1e-6))
     return res
+
+
+# ----------------------------------------------------------------------------------------- segmentation-net training kernels
+@check
+def attention_backward():
+    res = []
+    for (B, heads, N, Nk) in ((2, 1, 384, 6), (1, 2, 200, 200), (2, 5, 150, 70), (1, 8, 300, 300), (1, 1, 1000, 130)):
+        D, C = 64, heads * 64
+        scale = D ** -0.5
+        q = rnd(B, N, C, seed=N, scale=1.0)
+        kv = rnd(B, Nk, 2 * C, seed=N + 1, scale=1.0)
+        do = rnd(B, N, C, seed=N + 2, scale=1.0)
+        qr, kvr = q.clone().requires_grad_(True), kv.clone().requires_grad_(True)
+        qh = qr.reshape(B, N, heads, D).permute(0, 2, 1, 3)
+        kh = kvr[..., :C].reshape(B, Nk, heads, D).permute(0, 2, 1, 3)
+        vh = kvr[..., C:].reshape(B, Nk, heads, D).permute(0, 2, 1, 3)
+        ref = ((qh @ kh.transpose(-2, -1)) * scale).softmax(-1) @ vh
+        ref = ref.transpose(1, 2).reshape(B, N, C)
+        ref.backward(do)
+        qd, kvd = q.bfloat16().to(DEV).reshape(B * N, C), kv.bfloat16().to(DEV).reshape(B * Nk, 2 * C)
+        out, lse = ops.sr_attention_train(qd, kvd, B, heads, N, Nk, D, scale)
+        tag = f"B{B}h{heads}N{N}Nk{Nk}"
+        res.append(result(f"attn_train_fwd_{tag}", rel_err(out.float().reshape(B, N, C), ref), 1e-2))
+        dq, dkv = ops.sr_attention_bwd(qd, kvd, out, do.bfloat16().to(DEV).reshape(B * N, C), lse, B, heads, N, Nk, D, scale)
+        res.append(result(f"attn_bwd_dq_{tag}", rel_err(dq.float().reshape(B, N, C), qr.grad), 2e-2))
+        res.append(result(f"attn_bwd_dkv_{tag}", rel_err(dkv.reshape(B, Nk, 2 * C), kvr.grad), 2e-2))
+    return res
+
+
+@check
+def seg_head_training_kernels():
+    res = []
+    g = torch.Generator().manual_seed(11)
+    # upsample + CE backward
+    for (B, h, w, H, W) in ((2, 16, 24, 64, 96), (1, 15, 20, 60, 77), (1, 12, 12, 12, 12)):
+        lg = torch.randn(B, 9, h, w, generator=g) * 2
+        lab = torch.randint(0, 9, (B, H, W), generator=g)
+        lab[torch.rand(B, H, W, generator=g) < 0.1] = 255
+        lr = lg.clone().requires_grad_(True)
+        O.seg_cross_entropy(lr, lab).backward()
+        lgp = lg.permute(0, 2, 3, 1).contiguous().to(DEV)
+        loss, cnt = ops.upsample_ce(lgp, B, h, w, 9, lab.to(DEV), 255, return_count=True)
+        dl = ops.upsample_ce_bwd(lgp, B, h, w, 9, lab.to(DEV), torch.ones((), device=DEV), cnt, 255)
+        res.append(result(f"upsample_ce_bwd_{h}x{w}to{H}x{W}", rel_err(dl, lr.grad.permute(0, 2, 3, 1)), 1e-4))
+    # bilinear adjoint
+    for (B, h, w, H, W, C, ld, coff) in ((2, 8, 12, 16, 24, 64, 128, 32), (1, 5, 7, 40, 56, 256, 1024, 512), (1, 10, 10, 10, 10, 32, 32, 0)):
+        dd = rnd(B, H, W, ld, seed=h)
+        xr = torch.zeros(B, C, h, w, requires_grad=True)
+        F.interpolate(xr, size=(H, W), mode="bilinear", align_corners=False).backward(dd[..., coff:coff + C].permute(0, 3, 1, 2))
+        ds = ops.bilinear_nhwc_bwd(dd.bfloat16().to(DEV), ld, coff, B, H, W, h, w, C)
+        res.append(result(f"bilinear_bwd_{h}x{w}to{H}x{W}_C{C}", rel_err(ds.float(), xr.grad.permute(0, 2, 3, 1)), 5e-3))
+    # train-mode BatchNorm + ReLU
+    for (rows, C) in ((1000, 256), (333, 64)):
+        z = (rnd(rows, C, seed=C, scale=1.5) + 0.2).bfloat16().float()
+        gam, bet = 1 + 0.1 * rnd(C, seed=1, bf16=False), 0.1 * rnd(C, seed=2, bf16=False)
+        rm, rv = 0.1 * rnd(C, seed=3, bf16=False), 1 + 0.1 * rnd(C, seed=4, bf16=False).abs()
+        dy = rnd(rows, C, seed=5)
+        zr, gr, br = z.clone().requires_grad_(True), gam.clone().requires_grad_(True), bet.clone().requires_grad_(True)
+        rm_ref, rv_ref = rm.clone(), rv.clone()
+        yr = F.relu(F.batch_norm(zr, rm_ref, rv_ref, gr, br, True, 0.1, 1e-5))
+        yr.backward(dy)
+        rmd, rvd = rm.clone().to(DEV), rv.clone().to(DEV)
+        y, stats = ops.bn_train_fwd(z.bfloat16().to(DEV), gam.to(DEV), bet.to(DEV), 1e-5, 0.1, rmd, rvd)
+        res.append(result(f"bn_train_fwd_C{C}", rel_err(y.float(), yr), 5e-3))
+        res.append(result(f"bn_running_mean_C{C}", rel_err(rmd, rm_ref), 1e-5))
+        res.append(result(f"bn_running_var_C{C}", rel_err(rvd, rv_ref), 1e-5))
+        dg, db = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+        dz = ops.bn_train_bwd(z.bfloat16().to(DEV), y, dy.bfloat16().to(DEV), stats, gam.to(DEV), dg, db)
+        res.append(result(f"bn_train_bwd_dz_C{C}", rel_err(dz.float(), zr.grad), 8e-3))
+        res.append(result(f"bn_train_bwd_dgamma_C{C}", rel_err(dg, gr.grad), 5e-3))
+        res.append(result(f"bn_train_bwd_dbeta_C{C}", rel_err(db, br.grad), 5e-3))
+    x = rnd(2, 50, 64, seed=8)
+    sc = torch.tensor([[0.0, 1 / 0.9] * 32, [1 / 0.9, 0.0] * 32])
+    y = ops.channel_scale(x.bfloat16().to(DEV), sc.to(DEV), 2, 50, 64)
+    res.append(result("channel_scale", rel_err(y.float(), x * sc[:, None, :]), 4e-3))
+    return res
+
+
+@check
+def encoder_training_kernels():
+    res = []
+    # depthwise conv (+ flipped) and dwconv + GELU backward
+    for (B, H, W, C) in ((2, 12, 20, 256), (1, 7, 9, 2048), (1, 16, 16, 64)):
+        x = rnd(B, C, H, W, seed=C)
+        w = rnd(C, 1, 3, 3, seed=C + 1, scale=0.3, bf16=False)
+        b = 0.1 * rnd(C, seed=C + 2, bf16=False)
+        dy = rnd(B, C, H, W, seed=C + 3)
+        xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+        zr = F.conv2d(xr, wr, br, padding=1, groups=C)
+        zr.retain_grad()
+        F.gelu(zr).backward(dy)
+        pm = lambda t: t.permute(0, 2, 3, 1).contiguous()
+        w9c = w.reshape(C, 9).t().contiguous().to(DEV)
+        xd, dyd = pm(x).bfloat16().to(DEV), pm(dy).bfloat16().to(DEV)
+        z = ops.dwconv3x3(xd, w9c, b.to(DEV), B, H, W)
+        res.append(result(f"dwconv3x3_C{C}", rel_err(z.float(), pm(zr.detach())), 5e-3))
+        dw, db = torch.zeros(9, C, device=DEV), torch.zeros(C, device=DEV)
+        dz = ops.dwconv3x3_gelu_bwd(xd, w9c, b.to(DEV), dyd, B, H, W, dw, db)
+        res.append(result(f"dwconv_gelu_bwd_dz_C{C}", rel_err(dz.float(), pm(zr.grad)), 5e-3))
+        res.append(result(f"dwconv_gelu_bwd_dw_C{C}", rel_err(dw, wr.grad.reshape(C, 9).t()), 1e-3))
+        res.append(result(f"dwconv_gelu_bwd_db_C{C}", rel_err(db, br.grad), 1e-3))
+        dx = ops.dwconv3x3(dz, w9c, None, B, H, W, flip=True)
+        res.append(result(f"dwconv_dgrad_C{C}", rel_err(dx.float(), pm(xr.grad)), 1e-2))
+    # col2im against F.fold
+    for (B, H, W, C, k, s, p) in ((2, 12, 16, 64, 3, 2, 1), (1, 16, 24, 3, 7, 4, 3), (1, 8, 8, 32, 2, 2, 0), (1, 9, 11, 16, 3, 2, 1)):
+        Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+        ld = (C * k * k + 7) // 8 * 8
+        dcol = rnd(B * Ho * Wo, ld, seed=k)
+        cols = dcol[:, :C * k * k].reshape(B, Ho * Wo, C * k * k).transpose(1, 2)
+        ref = F.fold(cols, (H, W), kernel_size=k, stride=s, padding=p)
+        for dt in (torch.float32, torch.bfloat16):
+            dx = ops.col2im(dcol.bfloat16().to(DEV), B, H, W, C, k, s, p, out_dtype=dt)
+            res.append(result(f"col2im_k{k}s{s}_C{C}_{'f32' if dt == torch.float32 else 'bf16'}", rel_err(dx.float(), ref.permute(0, 2, 3, 1)),
+                              1e-6 if dt == torch.float32 else 4e-3))
+    # small pieces
+    img = torch.rand(2, 3, 10, 14, generator=torch.Generator().manual_seed(2))
+    sc, sh = torch.tensor([4.3, 4.5, 4.4]), torch.tensor([-2.1, -2.0, -1.8])
+    y = ops.channel_affine_nchw(img.to(DEV), sc.to(DEV), sh.to(DEV))
+    res.append(result("channel_affine_nchw", rel_err(y, img * sc.view(1, 3, 1, 1) + sh.view(1, 3, 1, 1)), 1e-6))
+    fused = torch.rand(2, 1, 10, 14, generator=torch.Generator().manual_seed(3)) * 1.4 - 0.2
+    ycc = O.rgb2ycrcb(img)
+    fr = fused.clone().requires_grad_(True)
+    rgb = O.recompose_rgb(fr, ycc)
+    drgb = torch.randn(2, 3, 10, 14, generator=torch.Generator().manual_seed(4))
+    rgb.backward(drgb)
+    d = ops.recompose_rgb_bwd(rgb.detach().to(DEV), drgb.to(DEV), True)
+    res.append(result("recompose_rgb_bwd", rel_err(d, fr.grad), 1e-6))
+    xf = rnd(300, 64, seed=9, bf16=False)
+    res.append(result("cast_f32_bf16", rel_err(ops.cast(xf.to(DEV), torch.bfloat16).float(), xf.bfloat16().float()), 0.0))
+    yb = rnd(300, 64, seed=10)
+    s2 = torch.tensor([0.0, 1.0 / 0.9, 1.0])
+    out = ops.scale_add_rows(xf.to(DEV), yb.bfloat16().to(DEV), s2.to(DEV), 100)
+    res.append(result("scale_add_rows", rel_err(out, xf + s2.repeat_interleave(100)[:, None] * yb), 1e-6))
+    # LayerNorm backward accumulating into the residual-stream gradient
+    x = rnd(100, 128, seed=12, bf16=False)
+    dy = rnd(100, 128, seed=13)
+    base = rnd(100, 128, seed=14, bf16=False)
+    xr = x.clone().requires_grad_(True)
+    F.layer_norm(xr, (128,), torch.ones(128), torch.zeros(128), 1e-6).backward(dy)
+    dx = base.clone().to(DEV)
+    ops.layernorm_bwd(x.to(DEV), dy.bfloat16().to(DEV), 128, 0, torch.ones(128, device=DEV), 1e-6, dx, 128, 0, 100, 128, accumulate=True)
+    res.append(result("layernorm_bwd_accumulate", rel_err(dx, base + xr.grad), 1e-5))
+    return res

@@ -96,23 +96,29 @@ def mix_ffn(x, h, w, sd, name):
     return _linear(y, sd, name + ".fc2")
 
 
-def mit_block(x, h, w, sd, name, heads, sr):
-    """core/mix_transformer.py:151-155 (eval: DropPath is the identity)."""
-    x = x + sr_attention(layer_norm(x, sd, name + ".norm1", BLOCK_LN_EPS), h, w, sd, name + ".attn", heads, sr)
-    x = x + mix_ffn(layer_norm(x, sd, name + ".norm2", BLOCK_LN_EPS), h, w, sd, name + ".mlp")
+def mit_block(x, h, w, sd, name, heads, sr, droppath=None):
+    """core/mix_transformer.py:151-155.  Eval: DropPath is the identity; `droppath` = (s1, s2), two per-sample scale
+    vectors [B] (0 or 1/keep_prob), reproduces a train-mode draw of timm's DropPath (:129,152-153)."""
+    a = sr_attention(layer_norm(x, sd, name + ".norm1", BLOCK_LN_EPS), h, w, sd, name + ".attn", heads, sr)
+    x = x + (a if droppath is None else a * droppath[0].view(-1, 1, 1))
+    m = mix_ffn(layer_norm(x, sd, name + ".norm2", BLOCK_LN_EPS), h, w, sd, name + ".mlp")
+    x = x + (m if droppath is None else m * droppath[1].view(-1, 1, 1))
     return x
 
 
-def mit_forward_features(x, sd, backbone):
-    """core/mix_transformer.py:312-348 -- returns the four NCHW stage outputs."""
+def mit_forward_features(x, sd, backbone, droppath=None):
+    """core/mix_transformer.py:312-348 -- returns the four NCHW stage outputs.  `droppath`: optional list with one
+    (s1, s2) pair per block (train-mode stochastic depth with the masks given)."""
     cfg = MIT_CONFIGS[backbone]
     outs = []
     b = x.shape[0]
+    bi = 0
     for s in range(4):
         patch, stride = (7, 4) if s == 0 else (3, 2)
         tok, h, w = overlap_patch_embed(x, sd, f"patch_embed{s + 1}", patch, stride)
         for i in range(cfg["depths"][s]):
-            tok = mit_block(tok, h, w, sd, f"block{s + 1}.{i}", MIT_HEADS[s], MIT_SR[s])
+            tok = mit_block(tok, h, w, sd, f"block{s + 1}.{i}", MIT_HEADS[s], MIT_SR[s], None if droppath is None else droppath[bi])
+            bi += 1
         tok = layer_norm(tok, sd, f"norm{s + 1}", BLOCK_LN_EPS)
         x = tok.reshape(b, h, w, -1).permute(0, 3, 1, 2).contiguous()
         outs.append(x)
@@ -130,8 +136,10 @@ def mit_forward_fusion(x, sd, backbone):
 # ----------------------------------------------------------------------------- SegFormer head
 
 
-def segformer_head(feats, sd, bn_eps=1e-5):
-    """core/segformer_head.py:59-82 in eval mode: BN uses running stats, Dropout2d is identity."""
+def segformer_head(feats, sd, bn_eps=1e-5, train_bn=False, dropout_scale=None):
+    """core/segformer_head.py:59-82.  Default = eval mode: BN uses running stats, Dropout2d is identity.  train_bn=True
+    uses batch statistics (nn.BatchNorm2d in training mode; running stats are not touched here) and `dropout_scale`
+    [B, E] (0 or 1/(1-p) per sample and channel) reproduces a train-mode draw of Dropout2d (:57,79)."""
     c1, c2, c3, c4 = feats
     n = c1.shape[0]
     size = c1.shape[2:]
@@ -144,9 +152,14 @@ def segformer_head(feats, sd, bn_eps=1e-5):
         parts.append(y)
     cat = torch.cat(parts, dim=1)
     y = F.conv2d(cat, sd["linear_fuse.conv.weight"])                           # bias=False: BN follows
-    y = F.batch_norm(y, sd["linear_fuse.bn.running_mean"], sd["linear_fuse.bn.running_var"],
-                     sd["linear_fuse.bn.weight"], sd["linear_fuse.bn.bias"], False, 0.0, bn_eps)
+    if train_bn:
+        y = F.batch_norm(y, None, None, sd["linear_fuse.bn.weight"], sd["linear_fuse.bn.bias"], True, 0.0, bn_eps)
+    else:
+        y = F.batch_norm(y, sd["linear_fuse.bn.running_mean"], sd["linear_fuse.bn.running_var"],
+                         sd["linear_fuse.bn.weight"], sd["linear_fuse.bn.bias"], False, 0.0, bn_eps)
     y = F.relu(y)
+    if dropout_scale is not None:
+        y = y * dropout_scale.view(y.shape[0], -1, 1, 1)
     return F.conv2d(y, sd["linear_pred.weight"], sd["linear_pred.bias"])
 
 
@@ -154,14 +167,15 @@ IMAGENET_MEAN = [123.675, 116.28, 103.53]
 IMAGENET_STD = [58.395, 57.12, 57.375]
 
 
-def network3_forward(x, sd, backbone):
+def network3_forward(x, sd, backbone, train_bn=False, dropout_scale=None, droppath=None):
     """core/model_fusion.py:1081-1088 + WeTr.forward :62-68 -- x*255, ImageNet mean/std, encoder, head.
-    `sd` is the Network3 state dict (keys start with denoise_net.)."""
+    `sd` is the Network3 state dict (keys start with denoise_net.).  The keyword arguments select train-mode behaviour
+    with injected masks (see segformer_head / mit_block)."""
     mean = torch.tensor(IMAGENET_MEAN, dtype=x.dtype).view(1, 3, 1, 1)
     std = torch.tensor(IMAGENET_STD, dtype=x.dtype).view(1, 3, 1, 1)
     xn = (x * 255 - mean) / std
-    feats = mit_forward_features(xn, _sub(sd, "denoise_net.encoder"), backbone)
-    return segformer_head(feats, _sub(sd, "denoise_net.decoder"))
+    feats = mit_forward_features(xn, _sub(sd, "denoise_net.encoder"), backbone, droppath)
+    return segformer_head(feats, _sub(sd, "denoise_net.decoder"), train_bn=train_bn, dropout_scale=dropout_scale)
 
 
 def seg_labels(logits, size):

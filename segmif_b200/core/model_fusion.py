@@ -123,8 +123,15 @@ class Network3(nn.Module):
         sc, sh = self._input_affine(fused_seg1.device)
         return self.denoise_net.forward_pixel_major(fused_seg1, sc, sh)
 
+    def _wants_grad(self, x):
+        return torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
+
     def forward(self, fused_seg1):
-        _no_autograd(self, fused_seg1)
+        if self._wants_grad(fused_seg1):
+            # training (train.py:222): one autograd node for encoder + head; the NCHW view is what the caller upsamples
+            from .seg_train import logits_with_grad
+            lg = logits_with_grad(self, fused_seg1)
+            return fused_seg1, fused_seg1, lg.permute(0, 3, 1, 2)
         lg = self.logits_pixel_major(fused_seg1)
         B, h, w, nc = lg.shape
         seg_map = ops.nhwc_to_nchw(lg, B, h * w, nc).view(B, nc, h, w)
@@ -140,10 +147,12 @@ class Network3(nn.Module):
 
     def _loss(self, fused_seg1, label, criterion):
         """core/model_fusion.py:1090-1097 for criterion = CrossEntropyLoss(ignore_index=...): upsample + CE fused."""
-        _no_autograd(self, fused_seg1)
         if not isinstance(criterion, nn.CrossEntropyLoss) or criterion.weight is not None \
                 or criterion.reduction != "mean" or getattr(criterion, "label_smoothing", 0.0) != 0.0:
             raise NotImplementedError("segmif_b200: _loss supports plain mean CrossEntropyLoss(ignore_index=...) only")
+        if self._wants_grad(fused_seg1):
+            from .seg_train import CeFn, logits_with_grad
+            return CeFn.apply(logits_with_grad(self, fused_seg1), label, criterion.ignore_index)
         lg = self.logits_pixel_major(fused_seg1)
         B, h, w, nc = lg.shape
         return ops.upsample_ce(lg, B, h, w, nc, label.long().contiguous(), criterion.ignore_index)

@@ -468,3 +468,67 @@ def encoder_training_kernels():
     ops.layernorm_bwd(x.to(DEV), dy.bfloat16().to(DEV), 128, 0, torch.ones(128, device=DEV), 1e-6, dx, 128, 0, 100, 128, accumulate=True)
     res.append(result("layernorm_bwd_accumulate", rel_err(dx, base + xr.grad), 1e-5))
     return res
+
+
+@check
+def seg_network_backward():
+    """Every parameter gradient of Network3 (MiT-B1 encoder + SegFormer head, train mode: batch-statistics BatchNorm,
+    injected Dropout2d / DropPath masks) and the gradient w.r.t. the input image against autograd over the oracle:
+    (a) fixed cotangent on the logits, DropPath off; (b) the same with DropPath masks; (c) end to end through
+    Network3._loss (upsample + CrossEntropy(ignore_index=255)).  Bounds: bf16 activations / gradients through 8 blocks."""
+    from segmif_b200.core.model_fusion import Network3
+    from segmif_b200.core.seg_train import logits_with_grad
+    res = []
+    B, H, W = 2, 64, 96
+    net0 = synth.load_synthetic(Network3("mit_b1", 9, 256, None), 0)
+    sd = {k: v.clone() for k, v in net0.state_dict().items()}
+    names = [k for k, _ in net0.named_parameters() if not k.endswith("classifier.weight")]
+    gen = torch.Generator().manual_seed(21)
+    x = torch.rand(B, 3, H, W, generator=gen)
+    drop = ((torch.rand(B, 256, generator=gen) >= 0.1).float() / 0.9)
+    labels = synth.synth_inputs(B, H, W, seed=4)["labels"]
+    h, w = H // 4, W // 4
+    cot = torch.randn(B, 9, h, w, generator=gen) / (B * h * w)
+    nblocks = 8
+    dps = [((torch.rand(B, generator=gen) < 0.8).float() / 0.8, (torch.rand(B, generator=gen) < 0.8).float() / 0.8) for _ in range(nblocks)]
+    for tag, droppath, use_ce in (("cotangent", None, False), ("droppath", dps, False), ("ce", None, True)):
+        leaves = {k: sd[k].clone().requires_grad_(True) for k in names}
+        full = dict(sd)
+        full.update(leaves)
+        xr = x.clone().requires_grad_(True)
+        lg_ref = O.network3_forward(xr, full, "mit_b1", train_bn=True, dropout_scale=drop, droppath=droppath)
+        (O.seg_cross_entropy(lg_ref, labels) if use_ce else (lg_ref * cot).sum()).backward()
+        net = copy.deepcopy(net0).to(DEV).train()
+        masks = {"dropout2d": drop.to(DEV)}
+        if droppath is not None:
+            for i, (a, b) in enumerate(droppath):
+                masks[("droppath", i)] = (a.to(DEV), b.to(DEV))
+        xd = x.to(DEV).requires_grad_(True)
+        lg = logits_with_grad(net, xd, masks)
+        res.append(result(f"seg_train_logits_{tag}", rel_err(lg.permute(0, 3, 1, 2), lg_ref), 5e-2))
+        if use_ce:
+            from segmif_b200.core.seg_train import CeFn
+            CeFn.apply(lg, labels.to(DEV), 255).backward()
+        else:
+            lg.backward(cot.permute(0, 2, 3, 1).contiguous().to(DEV))
+        got = dict(net.named_parameters())
+        groups, worst, worst_name = {}, 0.0, ""
+        for k in names:
+            if got[k].grad is None:
+                res.append(result(f"seg_grad_missing_{k}", float("nan"), 0.0))
+                continue
+            e = rel_err(got[k].grad, leaves[k].grad)
+            parts = k.split(".")
+            grp = ".".join(parts[1:3]) if parts[1] == "decoder" else parts[2]
+            groups[grp] = max(groups.get(grp, 0.0), e)
+            if e > worst:
+                worst, worst_name = e, k
+        for grp, e in sorted(groups.items()):
+            res.append(result(f"seg_grad_{tag}_{grp}", e, 0.12))
+        res.append(result(f"seg_grad_worst_{tag}", worst, 0.12, note=worst_name))
+        res.append(result(f"seg_grad_input_{tag}", rel_err(xd.grad, xr.grad), 0.12))
+        res.append(result(f"seg_classifier_untouched_{tag}", 0.0 if got["denoise_net.classifier.weight"].grad is None else 1.0, 0.0))
+    # running statistics follow nn.BatchNorm2d's update rule
+    bn = net.denoise_net.decoder.linear_fuse.bn
+    res.append(result("seg_bn_batches_tracked", abs(int(bn.num_batches_tracked) - 1), 0.0))
+    return res

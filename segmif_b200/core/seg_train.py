@@ -146,7 +146,7 @@ def encoder_forward(enc, x, in_scale, in_shift, masks):
         if s == 0:
             pt = F.pad(xn, (p, p, p, p)).unfold(2, k, st).unfold(3, k, st)                  # [B, 3, Ho, Wo, k, k]
             Ho, Wo = pt.shape[2], pt.shape[3]
-            Kp = (3 * k * k + 7) // 8 * 8
+            Kp = (3 * k * k + 31) // 32 * 32             # the data-gradient GEMM has N = Kp (multiple of 32)
             P = torch.zeros((B * Ho * Wo, Kp), dtype=BF16, device=x.device)
             P[:, :3 * k * k] = pt.permute(0, 2, 3, 1, 4, 5).reshape(B * Ho * Wo, 3 * k * k)
             Cin = 3

@@ -470,15 +470,8 @@ def encoder_training_kernels():
     return res
 
 
-@check
-def seg_network_backward():
-    """Every parameter gradient of Network3 (MiT-B1 encoder + SegFormer head, train mode: batch-statistics BatchNorm,
-    injected Dropout2d / DropPath masks) and the gradient w.r.t. the input image against autograd over the oracle:
-    (a) fixed cotangent on the logits, DropPath off; (b) the same with DropPath masks; (c) end to end through
-    Network3._loss (upsample + CrossEntropy(ignore_index=255)).  Bounds: bf16 activations / gradients through 8 blocks."""
+def _seg_case():
     from segmif_b200.core.model_fusion import Network3
-    from segmif_b200.core.seg_train import logits_with_grad
-    res = []
     B, H, W = 2, 64, 96
     net0 = synth.load_synthetic(Network3("mit_b1", 9, 256, None), 0)
     sd = {k: v.clone() for k, v in net0.state_dict().items()}
@@ -489,8 +482,113 @@ def seg_network_backward():
     labels = synth.synth_inputs(B, H, W, seed=4)["labels"]
     h, w = H // 4, W // 4
     cot = torch.randn(B, 9, h, w, generator=gen) / (B * h * w)
-    nblocks = 8
-    dps = [((torch.rand(B, generator=gen) < 0.8).float() / 0.8, (torch.rand(B, generator=gen) < 0.8).float() / 0.8) for _ in range(nblocks)]
+    dps = [((torch.rand(B, generator=gen) < 0.8).float() / 0.8, (torch.rand(B, generator=gen) < 0.8).float() / 0.8) for _ in range(8)]
+    return net0, sd, names, x, drop, labels, cot, dps
+
+
+def _floored_err(got, ref, floor):
+    """max |got - ref| over max(max |ref|, floor): gradients that are analytically zero (a per-channel constant in front
+    of the train-mode BatchNorm: decoder.linear_c*.proj.bias, encoder.norm4.bias -- the reference's own values are 1e-9
+    rounding noise) are judged on the scale of the network's largest gradient instead of their own."""
+    got, ref = got.detach().double().cpu(), ref.detach().double().cpu()
+    return float((got - ref).abs().max()) / max(float(ref.abs().max()), floor)
+
+
+@check
+def seg_modules_isolated():
+    """Every MiT block and the decode head of Network3 run ALONE through the training tape, fed with the oracle's exact
+    input and the oracle's exact output gradient, so an error is attributable to one module instead of being noise
+    accumulated over the chain.  Bounds: one block 5e-2 of each tensor's max |grad| (measured <= 2e-2); the head 0.12:
+    a CPU emulation of nothing but bf16 rounding of the GEMM operands (train-mode BatchNorm + ReLU in front of a random
+    cotangent) already gives 6.7e-2 on linear_fuse.conv.weight and 0.12 on the stage-1 feature gradient."""
+    from segmif_b200.core import seg_train as T
+    net0, sd, names, x, drop, labels, cot, dps = _seg_case()
+    B = x.shape[0]
+    res = []
+    leaves = {k: sd[k].clone().requires_grad_(True) for k in names}
+    full = dict(sd)
+    full.update(leaves)
+    esd = O._sub(full, "denoise_net.encoder")
+    mean = torch.tensor(O.IMAGENET_MEAN).view(1, 3, 1, 1)
+    std = torch.tensor(O.IMAGENET_STD).view(1, 3, 1, 1)
+    cur = (x * 255 - mean) / std
+    cfg = O.MIT_CONFIGS["mit_b1"]
+    toks, feats, bi = [], [], 0
+    for s in range(4):
+        patch, stride = (7, 4) if s == 0 else (3, 2)
+        tok, hh, ww = O.overlap_patch_embed(cur, esd, f"patch_embed{s + 1}", patch, stride)
+        tok.retain_grad()
+        lst = [tok]
+        for i in range(cfg["depths"][s]):
+            tok = O.mit_block(tok, hh, ww, esd, f"block{s + 1}.{i}", O.MIT_HEADS[s], O.MIT_SR[s], dps[bi])
+            tok.retain_grad()
+            lst.append(tok)
+            bi += 1
+        toks.append((lst, hh, ww))
+        cur = O.layer_norm(tok, esd, f"norm{s + 1}", O.BLOCK_LN_EPS).reshape(B, hh, ww, -1).permute(0, 3, 1, 2).contiguous()
+        cur.retain_grad()
+        feats.append(cur)
+    lg_ref = O.segformer_head(feats, O._sub(full, "denoise_net.decoder"), train_bn=True, dropout_scale=drop)
+    (lg_ref * cot).sum().backward()
+    gmax = max(float(leaves[n].grad.abs().max()) for n in names)
+
+    net = copy.deepcopy(net0).to(DEV).train()
+    enc, head = net.denoise_net.encoder, net.denoise_net.decoder
+    lookup = dict(net.named_parameters())
+    newg = lambda: {n: torch.zeros(lookup[n].shape, dtype=torch.float32, device=DEV) for n in names}
+
+    def worst(g, prefix):
+        w, wn = 0.0, ""
+        for n in names:
+            if n.startswith(prefix):
+                e = _floored_err(g[n], leaves[n].grad, 1e-2 * gmax)
+                if e > w:
+                    w, wn = e, n
+        return w, wn
+
+    bi = 0
+    for s in range(4):
+        lst, hh, ww = toks[s]
+        N = hh * ww
+        for i, blk in enumerate(getattr(enc, f"block{s + 1}")):
+            xin = lst[i].detach().reshape(B * N, -1).contiguous().to(DEV)
+            x3, sv = T._block_forward(blk, xin, B, N, hh, ww, (dps[bi][0].to(DEV), dps[bi][1].to(DEV)))
+            res.append(result(f"seg_block{s + 1}.{i}_alone_fwd", rel_err(x3.reshape(B, N, -1), lst[i + 1]), 5e-3))
+            dx = lst[i + 1].grad.reshape(B * N, -1).contiguous().to(DEV).clone()
+            g = newg()
+            pre = f"denoise_net.encoder.block{s + 1}.{i}."
+            T._block_backward(blk, sv, dx, B, N, g, pre)
+            res.append(result(f"seg_block{s + 1}.{i}_alone_dx", rel_err(dx.reshape(B, N, -1), lst[i].grad), 1e-2))
+            w, wn = worst(g, pre)
+            res.append(result(f"seg_block{s + 1}.{i}_alone_param_grads", w, 5e-2, note=wn))
+            bi += 1
+    stages = [(f.detach().permute(0, 2, 3, 1).reshape(-1, f.shape[1]).contiguous().bfloat16().to(DEV), f.shape[2], f.shape[3]) for f in feats]
+    logits, htape = T.head_forward(head, stages, B, {"dropout2d": drop.to(DEV)})
+    res.append(result("seg_head_alone_logits", rel_err(logits.permute(0, 3, 1, 2), lg_ref), 2e-2))
+    g = newg()
+    douts = T.head_backward(head, htape, cot.permute(0, 2, 3, 1).contiguous().to(DEV), B, g, "denoise_net.decoder.")
+    f4 = feats[3]           # the only stage output whose oracle gradient has no share from a later patch embedding
+    res.append(result("seg_head_alone_dfeat4", rel_err(douts[3].float().reshape(B, f4.shape[2], f4.shape[3], -1).permute(0, 3, 1, 2), f4.grad), 0.12))
+    w, wn = worst(g, "denoise_net.decoder.")
+    res.append(result("seg_head_alone_param_grads", w, 0.12, note=wn))
+    return res
+
+
+@check
+def seg_network_backward():
+    """Every parameter gradient of Network3 (MiT-B1 encoder + SegFormer head, train mode: batch-statistics BatchNorm,
+    injected Dropout2d / DropPath masks) and the gradient w.r.t. the input image against autograd over the oracle:
+    (a) fixed cotangent on the logits, DropPath masks all ones; (b) the same with DropPath masks; (c) end to end through
+    Network3._loss (upsample + CrossEntropy(ignore_index=255)).  Bound 0.2 of each tensor's max |grad| over the whole
+    chain (8 blocks, bf16 activations AND gradients): a CPU emulation that only rounds the GEMM operands of the oracle
+    to bf16 already differs from the fp32 oracle by 6e-2 (median tensor) to 0.15 (worst tensor) on this case, while
+    every module fed alone with exact inputs is within 2e-2 (seg_modules_isolated) -- the chain is noise-, not
+    bug-limited."""
+    from segmif_b200.core.seg_train import logits_with_grad
+    res = []
+    net0, sd, names, x, drop, labels, cot, dps = _seg_case()
+    B, H, W = x.shape[0], x.shape[2], x.shape[3]
+    ones = [(torch.ones(B), torch.ones(B)) for _ in range(8)]
     for tag, droppath, use_ce in (("cotangent", None, False), ("droppath", dps, False), ("ce", None, True)):
         leaves = {k: sd[k].clone().requires_grad_(True) for k in names}
         full = dict(sd)
@@ -498,14 +596,15 @@ def seg_network_backward():
         xr = x.clone().requires_grad_(True)
         lg_ref = O.network3_forward(xr, full, "mit_b1", train_bn=True, dropout_scale=drop, droppath=droppath)
         (O.seg_cross_entropy(lg_ref, labels) if use_ce else (lg_ref * cot).sum()).backward()
+        gmax = max(float(leaves[n].grad.abs().max()) for n in names)
         net = copy.deepcopy(net0).to(DEV).train()
         masks = {"dropout2d": drop.to(DEV)}
-        if droppath is not None:
-            for i, (a, b) in enumerate(droppath):
-                masks[("droppath", i)] = (a.to(DEV), b.to(DEV))
+        # the modules are in train mode: without injected masks every block would draw its own DropPath mask
+        for i, (a, b) in enumerate(droppath if droppath is not None else ones):
+            masks[("droppath", i)] = (a.to(DEV), b.to(DEV))
         xd = x.to(DEV).requires_grad_(True)
         lg = logits_with_grad(net, xd, masks)
-        res.append(result(f"seg_train_logits_{tag}", rel_err(lg.permute(0, 3, 1, 2), lg_ref), 5e-2))
+        res.append(result(f"seg_train_logits_{tag}", rel_err(lg.permute(0, 3, 1, 2), lg_ref), 3e-2))
         if use_ce:
             from segmif_b200.core.seg_train import CeFn
             CeFn.apply(lg, labels.to(DEV), 255).backward()
@@ -517,16 +616,16 @@ def seg_network_backward():
             if got[k].grad is None:
                 res.append(result(f"seg_grad_missing_{k}", float("nan"), 0.0))
                 continue
-            e = rel_err(got[k].grad, leaves[k].grad)
+            e = _floored_err(got[k].grad, leaves[k].grad, 1e-2 * gmax)
             parts = k.split(".")
             grp = ".".join(parts[1:3]) if parts[1] == "decoder" else parts[2]
             groups[grp] = max(groups.get(grp, 0.0), e)
             if e > worst:
                 worst, worst_name = e, k
         for grp, e in sorted(groups.items()):
-            res.append(result(f"seg_grad_{tag}_{grp}", e, 0.12))
-        res.append(result(f"seg_grad_worst_{tag}", worst, 0.12, note=worst_name))
-        res.append(result(f"seg_grad_input_{tag}", rel_err(xd.grad, xr.grad), 0.12))
+            res.append(result(f"seg_grad_{tag}_{grp}", e, 0.2))
+        res.append(result(f"seg_grad_worst_{tag}", worst, 0.2, note=worst_name))
+        res.append(result(f"seg_grad_input_{tag}", rel_err(xd.grad, xr.grad), 0.2))
         res.append(result(f"seg_classifier_untouched_{tag}", 0.0 if got["denoise_net.classifier.weight"].grad is None else 1.0, 0.0))
     # running statistics follow nn.BatchNorm2d's update rule
     bn = net.denoise_net.decoder.linear_fuse.bn

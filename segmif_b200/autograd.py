@@ -107,6 +107,28 @@ class EntropyFn(torch.autograd.Function):
         return ops.entropy_bwd(img, ctx.patch, g), None
 
 
+class RecomposeRgbFn(torch.autograd.Function):
+    """train.py:363-366: the visible image's YCrCb with Y replaced by the fused plane, back to RGB (optionally clamped
+    to [0, 1] as test_fusion.py:108-111 does).  Gradient w.r.t. the fused plane only; `vis_rgb` is data."""
+
+    @staticmethod
+    def forward(ctx, fused_y, vis_rgb, clamp):
+        rgb = ops.recompose_rgb(fused_y.float().contiguous(), vis_rgb.float().contiguous(), clamp)
+        ctx.save_for_backward(rgb)
+        ctx.clamp = clamp
+        return rgb
+
+    @staticmethod
+    def backward(ctx, drgb):
+        _no_second(ctx, 1)
+        (rgb,) = ctx.saved_tensors
+        return ops.recompose_rgb_bwd(rgb, drgb.float().contiguous(), ctx.clamp), None, None
+
+
+def recompose_rgb(fused_y, vis_rgb, clamp=False):
+    return RecomposeRgbFn.apply(fused_y, vis_rgb, clamp)
+
+
 def mse_l1(x, y):
     return MseL1Fn.apply(x, y)
 

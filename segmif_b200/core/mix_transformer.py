@@ -27,7 +27,8 @@ def to_2tuple(x):
 
 
 class DropPath(nn.Module):
-    """Per-sample stochastic depth (timm semantics); identity in eval, which is all the forward kernels serve."""
+    """Per-sample stochastic depth (timm semantics).  Block applies it itself (a per-sample scale fused into the residual
+    add, Block._droppath_scale / core/seg_train.py); this module only carries drop_prob and is the identity in eval."""
 
     def __init__(self, drop_prob=0.0):
         super().__init__()
@@ -36,7 +37,7 @@ class DropPath(nn.Module):
     def forward(self, x):
         if self.drop_prob == 0.0 or not self.training:
             return x
-        raise NotImplementedError("segmif_b200: train-mode DropPath needs the backward kernels (not built yet)")
+        raise NotImplementedError("segmif_b200: train-mode DropPath is applied inside Block (fused residual scale), not as a module call")
 
 
 def _reference_init(m):
@@ -171,14 +172,34 @@ class Block(nn.Module):
         self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
         self.apply(_reference_init)
 
+    def _droppath_scale(self, B, device):
+        """timm.DropPath in train mode (core/mix_transformer.py:129,152-153): per-sample bernoulli(keep) / keep, drawn
+        with torch's device RNG; None = identity (eval mode or drop_prob 0)."""
+        dp = getattr(self.drop_path, "drop_prob", 0.0) or 0.0
+        if not self.training or dp == 0.0:
+            return None
+        keep = 1.0 - dp
+        return (torch.rand((B,), device=device) < keep).float() / keep
+
     def forward(self, x, H, W):
-        if self.training and isinstance(self.drop_path, DropPath) and self.drop_path.drop_prob > 0:
-            raise NotImplementedError("segmif_b200: train-mode forward (DropPath / autograd) is not built yet; call .eval()")
+        """Gradient-free forward (inference, and train.py:358-359's no_grad feature pass, which the reference runs with
+        the module still in train mode: DropPath active).  Gradients go through core/seg_train.py's tape instead."""
+        if self.training and torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise NotImplementedError("segmif_b200: Block.forward is the gradient-free path; training runs through "
+                                      "Network3.forward/_loss (core/seg_train.py) or under torch.no_grad()")
         x = x.contiguous() if x.dtype == torch.float32 else x.float().contiguous()
+        B, N, C = x.shape
+        s1, s2 = self._droppath_scale(B, x.device), self._droppath_scale(B, x.device)
         n1 = ops.layernorm(x, self.norm1.weight.detach(), self.norm1.bias.detach(), self.norm1.eps)
-        x = self.attn._forward(n1, H, W, residual=x.view(-1, x.shape[-1]))
+        if s1 is None:
+            x = self.attn._forward(n1, H, W, residual=x.view(-1, C))
+        else:
+            x = ops.scale_add_rows(x.view(-1, C), self.attn._forward(n1, H, W).view(-1, C), s1, N).view(B, N, C)
         n2 = ops.layernorm(x, self.norm2.weight.detach(), self.norm2.bias.detach(), self.norm2.eps)
-        x = self.mlp._forward(n2, H, W, residual=x.view(-1, x.shape[-1]))
+        if s2 is None:
+            x = self.mlp._forward(n2, H, W, residual=x.view(-1, C))
+        else:
+            x = ops.scale_add_rows(x.view(-1, C), self.mlp._forward(n2, H, W).view(-1, C), s2, N).view(B, N, C)
         return x
 
 

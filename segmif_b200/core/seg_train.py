@@ -48,7 +48,20 @@ def _flat_t_pack(cache, w_param, kpad, tag):
     return cache.get(w_param, f, tag)
 
 
-def _colsum(dy, N, rows, out):
+class _Grads(dict):
+    """name -> fp32 gradient tensor.  `frozen`: the parameters take no gradient (train_fusion differentiates through the
+    frozen segmentation network, train.py:368): the weight-gradient GEMMs and bias column sums are skipped."""
+    frozen = False
+
+
+def _wgrad(g, *args, **kw):
+    if not g.frozen:
+        ops.wgrad(*args, **kw)
+
+
+def _colsum(dy, N, rows, out, g=None):
+    if g is not None and g.frozen:
+        return
     for c0 in range(0, N, 256):
         ops.colsum(dy, N, c0, rows, min(256, N - c0), out[c0:])
 
@@ -57,9 +70,9 @@ def _lin_bwd(dy, x, weight_param, cache, g, wname, bname, need_dx=True, residual
     """dy bf16 [M, N], x bf16 [M, K] -> weight / bias gradients accumulated; returns dx bf16 [M, K] (+ residual)."""
     M, N = dy.shape
     K = x.shape[1]
-    ops.wgrad(dy, N, 0, x, K, 0, B=1, H=1, W=1, P=M, Cin=K, Cout=N, taps=1, dil=1, grad=g[wname], s_co=K, s_tap=1, s_ci=1)
+    _wgrad(g, dy, N, 0, x, K, 0, B=1, H=1, W=1, P=M, Cin=K, Cout=N, taps=1, dil=1, grad=g[wname], s_co=K, s_tap=1, s_ci=1)
     if bname is not None:
-        _colsum(dy, N, M, g[bname])
+        _colsum(dy, N, M, g[bname], g)
     if not need_dx:
         return None
     return ops.linear_tc(dy, _t_pack(cache, weight_param, "lin_t"), None, residual=residual)
@@ -246,9 +259,9 @@ def _block_backward(blk, sv, dx, B, N, g, pre):
                           dgamma=g[pre + "attn.norm.weight"], dbeta=g[pre + "attn.norm.bias"])
         dred16 = ops.cast(dred, BF16)
         K = C * r * r
-        ops.wgrad(dred16, C, 0, sv["P_sr"], K, 0, B=1, H=1, W=1, P=Mk, Cin=K, Cout=C, taps=1, dil=1, grad=g[pre + "attn.sr.weight"],
+        _wgrad(g, dred16, C, 0, sv["P_sr"], K, 0, B=1, H=1, W=1, P=Mk, Cin=K, Cout=C, taps=1, dil=1, grad=g[pre + "attn.sr.weight"],
                   s_co=K, s_tap=1, s_ci=1)
-        _colsum(dred16, C, Mk, g[pre + "attn.sr.bias"])
+        _colsum(dred16, C, Mk, g[pre + "attn.sr.bias"], g)
         dP = ops.linear_tc(dred16, _flat_t_pack(at._packs, at.sr.weight, K, "sr_flat_t"), None)
         extra = _patches_to_map(dP, B, sv["Hk"], sv["Wk"], C, r, H, W)
         extra = extra if extra.is_contiguous() else extra.contiguous()
@@ -291,9 +304,9 @@ def encoder_backward(enc, tape, douts, g, prefix, want_input_grad):
                           dgamma=g[pp + "norm.weight"], dbeta=g[pp + "norm.bias"])
         dy16 = ops.cast(dy, BF16)
         Kp, k, Cin = st["Kp"], st["k"], st["Cin"]
-        ops.wgrad(dy16, C, 0, st["P"], Kp, 0, B=1, H=1, W=1, P=M, Cin=Kp, Cout=C, taps=1, dil=1, grad=g[pp + "proj.weight"],
+        _wgrad(g, dy16, C, 0, st["P"], Kp, 0, B=1, H=1, W=1, P=M, Cin=Kp, Cout=C, taps=1, dil=1, grad=g[pp + "proj.weight"],
                   s_co=Cin * k * k, s_tap=1, s_ci=1, ci_take=Cin * k * k)
-        _colsum(dy16, C, M, g[pp + "proj.bias"])
+        _colsum(dy16, C, M, g[pp + "proj.bias"], g)
         if s > 0 or want_input_grad:
             dP = ops.linear_tc(dy16, _flat_t_pack(pe._packs, pe.proj.weight, Kp, "pe_flat_t"), None)
             if s > 0:
@@ -312,7 +325,7 @@ def head_backward(head, tape, dlogits, B, g, prefix):
     M = B * h1 * w1
     dl = torch.zeros((M, 32), dtype=BF16, device=dev)                       # class gradients padded to 32 channels
     dl[:, :nc] = dlogits.reshape(M, nc)
-    ops.wgrad(dl, 32, 0, tape["yd"], E, 0, B=1, H=1, W=1, P=M, Cin=E, Cout=32, taps=1, dil=1, grad=g[prefix + "linear_pred.weight"],
+    _wgrad(g, dl, 32, 0, tape["yd"], E, 0, B=1, H=1, W=1, P=M, Cin=E, Cout=32, taps=1, dil=1, grad=g[prefix + "linear_pred.weight"],
               s_co=E, s_tap=1, s_ci=1, co_take=nc)
     db = torch.zeros((32,), dtype=F32, device=dev)
     ops.colsum(dl, 32, 0, M, 32, db)
@@ -328,7 +341,7 @@ def head_backward(head, tape, dlogits, B, g, prefix):
     dz = ops.bn_train_bwd(tape["z"], tape["y"], dy, tape["stats"], bn.weight.detach(), g[prefix + "linear_fuse.bn.weight"],
                           g[prefix + "linear_fuse.bn.bias"])
     cat2 = tape["cat"].view(M, 4 * E)
-    ops.wgrad(dz, E, 0, cat2, 4 * E, 0, B=1, H=1, W=1, P=M, Cin=4 * E, Cout=E, taps=1, dil=1, grad=g[prefix + "linear_fuse.conv.weight"],
+    _wgrad(g, dz, E, 0, cat2, 4 * E, 0, B=1, H=1, W=1, P=M, Cin=4 * E, Cout=E, taps=1, dil=1, grad=g[prefix + "linear_fuse.conv.weight"],
               s_co=4 * E, s_tap=1, s_ci=1)
     dcat = ops.linear_tc(dz, _t_pack(head._packs, conv.weight, "fuse_t"), None)            # [M, 4E]
     t1, t2, t3, t4 = tape["toks"]
@@ -364,7 +377,8 @@ class SegNetFn(torch.autograd.Function):
         dev = dlogits.device
         B = ctx.etape["B"]
         lookup = dict(net3.named_parameters())
-        g = {n: torch.zeros(lookup[n].shape, dtype=F32, device=dev) for n in ctx.names}
+        g = _Grads((n, torch.zeros(lookup[n].shape, dtype=F32, device=dev)) for n in ctx.names)
+        g.frozen = not any(ctx.needs_input_grad[4:])
         douts = head_backward(wetr.decoder, ctx.htape, dlogits.float().contiguous(), B, g, "denoise_net.decoder.")
         dimg = encoder_backward(wetr.encoder, ctx.etape, douts, g, "denoise_net.encoder.", ctx.want_x)
         ctx.etape = ctx.htape = None

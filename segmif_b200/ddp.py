@@ -17,11 +17,13 @@ class FlatParams:
     """Re-homes the selected parameters of `module` as views of one flat fp32 buffer and gives them gradient views
     of a second flat buffer, so the all-reduce and the optimizer each touch a single contiguous tensor."""
 
-    def __init__(self, module, used=lambda name: True):
+    def __init__(self, module, used=lambda name: True, group_of=None):
         self.named = [(k, p) for k, p in module.named_parameters() if p.requires_grad and used(k)]
         self.skipped = [k for k, p in module.named_parameters() if p.requires_grad and not used(k)]
         if not self.named:
             raise ValueError("FlatParams: no parameters selected")
+        if group_of is not None:                      # optimizer param groups become contiguous ranges of the buffer
+            self.named.sort(key=lambda kp: group_of(kp[0]))
         dev = self.named[0][1].device
         pad4 = lambda n: (n + 3) & ~3              # every view starts 16-byte aligned (the kernels read biases / gains as float4)
         self.numel = sum(pad4(p.numel()) for _, p in self.named)
@@ -37,6 +39,13 @@ class FlatParams:
                 p.grad = self.grad[off:off + n].view(p.shape)
                 self.offsets[k] = (off, n)
                 off += pad4(n)
+        self.group_ranges = None
+        if group_of is not None:
+            self.group_ranges = {}
+            for k, p in self.named:
+                o, n = self.offsets[k]
+                lo, hi = self.group_ranges.get(group_of(k), (o, o))
+                self.group_ranges[group_of(k)] = (min(lo, o), max(hi, o + pad4(n)))
 
     def zero_grad(self):
         self.grad.zero_()
@@ -63,45 +72,125 @@ def poly_warmup_lr(base_lr, global_step, warmup_iter, max_iter, warmup_ratio, po
 
 
 class FusedPolyWarmupAdamW:
-    """PolyWarmupAdamW (utils/optimizer.py:3-33) over a FlatParams buffer: one segmif_adamw_step launch per step."""
+    """PolyWarmupAdamW / PolyWarmupAdamW_seg (utils/optimizer.py:3-33,36-66) over a FlatParams buffer: one
+    segmif_adamw_step launch per param group and step.  `groups`: {group id: dict(lr=, weight_decay=)} matching the
+    FlatParams' group_of (train.py:170-189: encoder weights / encoder norms with weight_decay 0 / decoder at 10x lr);
+    None = one group.  `iter_curr` is PolyWarmupAdamW_seg's starting global step (the schedule position); AdamW's own
+    bias-correction step count starts at 1 either way, as torch.optim.AdamW's per-parameter state does."""
 
-    def __init__(self, flat, lr, weight_decay, betas, warmup_iter, max_iter, warmup_ratio, power, eps=1e-8):
+    def __init__(self, flat, lr, weight_decay, betas, warmup_iter, max_iter, warmup_ratio, power, eps=1e-8, groups=None,
+                 iter_curr=0):
         self.flat = flat
-        self.base_lr = self.lr = float(lr)
-        self.weight_decay, self.betas, self.eps = float(weight_decay), tuple(betas), float(eps)
+        self.betas, self.eps = tuple(betas), float(eps)
         self.warmup_iter, self.max_iter, self.warmup_ratio, self.power = warmup_iter, max_iter, warmup_ratio, power
-        self.global_step = 0
+        self.global_step = int(iter_curr)
+        self.opt_steps = 0
+        if groups is None:
+            self.groups = [dict(range=(0, flat.numel), base_lr=float(lr), lr=float(lr), weight_decay=float(weight_decay))]
+        else:
+            self.groups = [dict(range=flat.group_ranges[gid], base_lr=float(g.get("lr", lr)), lr=float(g.get("lr", lr)),
+                                weight_decay=float(g.get("weight_decay", weight_decay)))
+                           for gid, g in sorted(groups.items()) if gid in flat.group_ranges]
         self.exp_avg = torch.zeros_like(flat.param)
         self.exp_avg_sq = torch.zeros_like(flat.param)
 
+    @property
+    def lr(self):
+        return self.groups[0]["lr"]
+
+    @property
+    def base_lr(self):
+        return self.groups[0]["base_lr"]
+
+    @property
+    def weight_decay(self):
+        return self.groups[0]["weight_decay"]
+
     def step(self, grad_scale=1.0):
         from . import ops
-        self.lr = poly_warmup_lr(self.base_lr, self.global_step, self.warmup_iter, self.max_iter, self.warmup_ratio,
-                                 self.power, self.lr)
-        ops.adamw_step(self.flat.param, self.flat.grad, self.exp_avg, self.exp_avg_sq, lr=self.lr, beta1=self.betas[0],
-                       beta2=self.betas[1], eps=self.eps, weight_decay=self.weight_decay, step=self.global_step + 1,
-                       grad_scale=grad_scale)
+        for g in self.groups:
+            g["lr"] = poly_warmup_lr(g["base_lr"], self.global_step, self.warmup_iter, self.max_iter, self.warmup_ratio,
+                                     self.power, g["lr"])
+            lo, hi = g["range"]
+            ops.adamw_step(self.flat.param[lo:hi], self.flat.grad[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi],
+                           lr=g["lr"], beta1=self.betas[0], beta2=self.betas[1], eps=self.eps,
+                           weight_decay=g["weight_decay"], step=self.opt_steps + 1, grad_scale=grad_scale)
         packing.invalidate_all()
         self.global_step += 1
+        self.opt_steps += 1
 
 
 class FusionTrainer:
     """One optimisation step of train_fusion (train.py:343-386) for the fusion network, data parallel:
         fused = model2(ir, vis_ycrcb, out0, out1);  loss = criterion(ir, vis, fused, mask);  loss.backward();
         all-reduce;  AdamW.
-    The encoder features out0 / out1 come from the frozen segmentation network (train.py:358-359, no_grad)."""
+    The encoder features out0 / out1 come from the frozen segmentation network (train.py:358-359, no_grad).
+
+    With `seg_net` given, the step is the rounds >= 2 composite (train.py:361-380, iter_ > 1):
+        loss1 = criterion(...);  loss2 = seg_net._loss(YCrCb2RGB([fused, Cr, Cb]), labels, CE);
+        loss = w0 * loss1 * (0.4 / iter_) + w1 * loss2 * 0.8,   (w0, w1) = 2 softmax(ratio of the two previous losses / 1000)
+    The reference reads the loss history on the host with .item() every step; here it is a device-resident [2, 3] ring
+    (no synchronisation), weights all ones for the first 11 steps as in train.py:377-380.  The segmentation network is
+    differentiated through but frozen: its weight gradients (which the reference computes and never uses, SURVEY.md
+    App. B) are skipped."""
 
     def __init__(self, fusion_net, criterion, lr=3e-4, weight_decay=0.01, betas=(0.9, 0.999), warmup_iter=3e-5,
-                 max_iter=40000, warmup_ratio=1e-6, power=1.0, group=None):
+                 max_iter=40000, warmup_ratio=1e-6, power=1.0, group=None, seg_net=None, iter_=1, ignore_index=255):
         self.net, self.criterion, self.group = fusion_net, criterion, group
         self.flat = FlatParams(fusion_net, used=lambda k: not k.startswith("ffm2."))
         self.opt = FusedPolyWarmupAdamW(self.flat, lr, weight_decay, betas, warmup_iter, max_iter, warmup_ratio, power)
+        self.seg_net, self.iter_ = seg_net, iter_
+        self.n_iter = 0
+        if seg_net is not None:
+            for p in seg_net.parameters():
+                p.requires_grad_(False)
+            self.ce = torch.nn.CrossEntropyLoss(ignore_index=ignore_index)
+            self.history = torch.ones((2, 3), dtype=torch.float32, device=self.flat.param.device)
 
-    def step(self, ir, vis_ycrcb, out0, out1, mask):
+    def step(self, ir, vis_ycrcb, out0, out1, mask, vis_rgb=None, labels=None):
         self.flat.zero_grad()
         fused = self.net(ir, vis_ycrcb, out0, out1)
         loss = self.criterion(ir, vis_ycrcb, fused, mask)
+        if self.seg_net is not None:
+            from .autograd import recompose_rgb
+            loss2 = self.seg_net._loss(recompose_rgb(fused, vis_rgb, False), labels, self.ce)
+            h = self.history
+            slot = self.n_iter % 3
+            h[0, slot], h[1, slot] = loss.detach(), loss2.detach()
+            if self.n_iter > 10:
+                w_i = h[:, (self.n_iter - 1) % 3] / h[:, (self.n_iter - 2) % 3]
+                bw = 2 * torch.softmax(w_i / 1000.0, dim=-1)
+                loss = bw[0] * loss * (0.4 / self.iter_) + bw[1] * loss2 * 0.8
+            else:
+                loss = (0.4 / self.iter_) * loss + 0.8 * loss2
         loss.backward()
         world = self.flat.all_reduce(self.group)
         self.opt.step(grad_scale=1.0 / world)
+        self.n_iter += 1
         return loss.detach(), fused.detach()
+
+
+class SegTrainer:
+    """One optimisation step of train_seg (train.py:207-226), data parallel:
+        _, _, segmap = model(mask);  loss = CE(bilinear(segmap -> label size), labels);  backward;  all-reduce;  AdamW
+    with train.py:170-189's three param groups (WeTr.get_param_groups: encoder weights, encoder norms with weight_decay 0,
+    decode head at 10x the learning rate).  WeTr.classifier.weight never receives a gradient (its output is discarded,
+    core/model_fusion.py:66), so torch.optim.AdamW never touches it: it stays out of the flat buffer."""
+
+    def __init__(self, seg_net, lr=6e-5, weight_decay=0.01, betas=(0.9, 0.999), warmup_iter=1500, max_iter=40000,
+                 warmup_ratio=1e-6, power=1.0, iter_curr=0, ignore_index=255, group=None):
+        self.net, self.group = seg_net, group
+        gid = lambda k: 2 if ".decoder." in k else (1 if "norm" in k.split("encoder.", 1)[-1] else 0)
+        self.flat = FlatParams(seg_net, used=lambda k: not k.endswith("classifier.weight"), group_of=gid)
+        self.opt = FusedPolyWarmupAdamW(self.flat, lr, weight_decay, betas, warmup_iter, max_iter, warmup_ratio, power,
+                                        groups={0: dict(lr=lr, weight_decay=weight_decay), 1: dict(lr=lr, weight_decay=0.0),
+                                                2: dict(lr=lr * 10, weight_decay=weight_decay)}, iter_curr=iter_curr)
+        self.ce = torch.nn.CrossEntropyLoss(ignore_index=ignore_index)
+
+    def step(self, mask, labels):
+        self.flat.zero_grad()
+        loss = self.net._loss(mask, labels, self.ce)
+        loss.backward()
+        world = self.flat.all_reduce(self.group)
+        self.opt.step(grad_scale=1.0 / world)
+        return loss.detach()

@@ -535,7 +535,7 @@ def seg_modules_isolated():
     net = copy.deepcopy(net0).to(DEV).train()
     enc, head = net.denoise_net.encoder, net.denoise_net.decoder
     lookup = dict(net.named_parameters())
-    newg = lambda: {n: torch.zeros(lookup[n].shape, dtype=torch.float32, device=DEV) for n in names}
+    newg = lambda: T._Grads((n, torch.zeros(lookup[n].shape, dtype=torch.float32, device=DEV)) for n in names)
 
     def worst(g, prefix):
         w, wn = 0.0, ""
@@ -630,4 +630,101 @@ def seg_network_backward():
     # running statistics follow nn.BatchNorm2d's update rule
     bn = net.denoise_net.decoder.linear_fuse.bn
     res.append(result("seg_bn_batches_tracked", abs(int(bn.num_batches_tracked) - 1), 0.0))
+    return res
+
+
+@check
+def seg_trainer_steps():
+    """Three optimisation steps of SegTrainer (train.py:207-226: three AdamW param groups over the flat buffer) against
+    torch.optim.AdamW with the same groups over the oracle's autograd gradients.  DropPath / Dropout2d masks are pinned
+    to the identity on both sides (drop rates set to 0), BatchNorm uses batch statistics."""
+    from segmif_b200.ddp import SegTrainer
+    net0, sd, names, x, drop, labels, cot, dps = _seg_case()
+    res = []
+    gid = lambda k: 2 if ".decoder." in k else (1 if "norm" in k.split("encoder.", 1)[-1] else 0)
+    leaves = {k: sd[k].clone().requires_grad_(True) for k in names}
+    lr, wd = 6e-5, 0.01
+    groups = [dict(params=[leaves[k] for k in names if gid(k) == g], lr=lr * (10 if g == 2 else 1), weight_decay=0.0 if g == 1 else wd)
+              for g in range(3)]
+    opt = torch.optim.AdamW(groups, lr=lr, betas=(0.9, 0.999), weight_decay=wd, eps=1e-8)
+    base = [g["lr"] for g in opt.param_groups]
+    ref_losses = []
+    for it in range(3):
+        full = dict(sd)
+        full.update(leaves)
+        mult = 1 - (1 - it / 2) * (1 - 1e-6) if it < 2 else (1 - it / 100.0)          # warmup_iter = 2 (utils/optimizer.py:49-60)
+        for g, b in zip(opt.param_groups, base):
+            g["lr"] = b * mult
+        opt.zero_grad()
+        l = O.seg_cross_entropy(O.network3_forward(x, full, "mit_b1", train_bn=True), labels)
+        l.backward()
+        opt.step()
+        ref_losses.append(float(l.detach()))
+    net = copy.deepcopy(net0).to(DEV).train()
+    net.denoise_net.decoder.dropout.p = 0.0
+    for m in net.modules():
+        if hasattr(m, "drop_prob"):
+            m.drop_prob = 0.0
+    tr = SegTrainer(net, lr=lr, weight_decay=wd, betas=(0.9, 0.999), warmup_iter=2, max_iter=100, warmup_ratio=1e-6, power=1.0)
+    got = [float(tr.step(x.to(DEV), labels.to(DEV))) for _ in range(3)]
+    res.append(result("seg_trainer_loss_trajectory", max(abs(a - b) / abs(b) for a, b in zip(got, ref_losses)), 2e-2, note=f"{got} vs {ref_losses}"))
+    for g in range(3):
+        num = den = 0.0
+        for k, p in net.named_parameters():
+            if k in leaves and gid(k) == g:
+                du, dr = (p.detach().cpu() - sd[k]), (leaves[k].detach() - sd[k])
+                num += float((du - dr).pow(2).sum())
+                den += float(dr.pow(2).sum())
+        res.append(result(f"seg_trainer_update_rel_l2_group{g}", (num / den) ** 0.5, 0.35))
+    cw = net.denoise_net.classifier.weight
+    res.append(result("seg_trainer_classifier_frozen", float((cw.detach().cpu() - sd["denoise_net.classifier.weight"]).abs().max()), 0.0))
+    res.append(result("seg_trainer_lr_groups", max(abs(tr.opt.groups[i]["lr"] - b * (1 - 2 / 100.0)) / b for i, b in enumerate(base)), 1e-6))
+    return res
+
+
+@check
+def fusion_composite_step():
+    """train_fusion rounds >= 2 (train.py:361-380): Fusionloss_grad3 on the fused plane + CE through YCrCb2RGB and the
+    frozen segmentation network.  Checks d(loss)/d(fused) of the CE branch (recompose + Network3._loss with frozen
+    weights: no weight gradients are formed) against the oracle, and one composite FusionTrainer step's loss value."""
+    from segmif_b200.autograd import recompose_rgb
+    from segmif_b200.core.model_fusion import Network3
+    res = []
+    B, H, W = 2, 64, 96
+    seg0 = synth.load_synthetic(Network3("mit_b1", 9, 256, None), 0)
+    ssd = {k: v.clone() for k, v in seg0.state_dict().items()}
+    inp = synth.synth_inputs(B, H, W, seed=5)
+    fused = (inp["ir"] * 0.6 + 0.3 * inp["vis"][:, :1]).clone()
+    ycc = O.rgb2ycrcb(inp["vis"])
+    fr = fused.clone().requires_grad_(True)
+    ce_ref = O.seg_cross_entropy(O.network3_forward(O.recompose_rgb(fr, ycc, clamp=False), ssd, "mit_b1", train_bn=True), inp["labels"])
+    ce_ref.backward()
+    seg = copy.deepcopy(seg0).to(DEV).train()
+    seg.denoise_net.decoder.dropout.p = 0.0
+    for m in seg.modules():
+        if hasattr(m, "drop_prob"):
+            m.drop_prob = 0.0
+    for p in seg.parameters():
+        p.requires_grad_(False)
+    fd = fused.to(DEV).requires_grad_(True)
+    ce = seg._loss(recompose_rgb(fd, inp["vis"].to(DEV), False), inp["labels"].to(DEV), torch.nn.CrossEntropyLoss(ignore_index=255))
+    ce.backward()
+    res.append(result("composite_ce_value", abs(float(ce) - float(ce_ref)) / abs(float(ce_ref)), 2e-2))
+    res.append(result("composite_ce_dfused", rel_err(fd.grad, fr.grad), 0.2))
+    res.append(result("composite_seg_params_no_grad", 0.0 if all(p.grad is None for p in seg.parameters()) else 1.0, 0.0))
+    # one composite trainer step: loss = 0.4/iter_ * Fusionloss_grad3 + 0.8 * CE (train.py:379-380, n_iter <= 10)
+    from segmif_b200.core.loss import Fusionloss_grad3
+    from segmif_b200.ddp import FusionTrainer
+    fus, sd, finp, vis, out1, out2 = _fusion_case(B, H, W, seed=5)
+    with torch.no_grad():
+        f_ref = O.fusion_network3_ac(finp["ir"], vis, out1, out2, sd)
+        l_ref = 0.2 * O.fusionloss_grad3(finp["ir"], vis, f_ref, finp["mask"]) + 0.8 * O.seg_cross_entropy(
+            O.network3_forward(O.recompose_rgb(f_ref, vis, clamp=False), ssd, "mit_b1", train_bn=True), finp["labels"])
+    net = copy.deepcopy(fus).to(DEV).train()
+    tr = FusionTrainer(net, Fusionloss_grad3(), lr=1.5e-4, max_iter=100, seg_net=seg, iter_=2)
+    before = tr.flat.param.clone()
+    l, _ = tr.step(finp["ir"].to(DEV), vis.to(DEV), out1.to(DEV), out2.to(DEV), finp["mask"].to(DEV), vis_rgb=finp["vis"].to(DEV),
+                   labels=finp["labels"].to(DEV))
+    res.append(result("composite_step_loss", abs(float(l) - float(l_ref)) / abs(float(l_ref)), 3e-2, note=f"{float(l):.5f} vs {float(l_ref):.5f}"))
+    res.append(result("composite_step_updates_params", 0.0 if float((tr.flat.param - before).abs().max()) > 0 else 1.0, 0.0))
     return res

@@ -102,3 +102,48 @@ def test_training_forward_refuses_cpu():
     net = Fusion_Network3_ac().train()
     with pytest.raises(RuntimeError, match="no CPU path|CUDA"):
         net(torch.zeros(1, 1, 16, 16), torch.zeros(1, 3, 16, 16), torch.zeros(1, 64, 16, 16), torch.zeros(1, 128, 16, 16))
+
+
+def test_seg_param_groups_are_contiguous_ranges_matching_get_param_groups():
+    """train.py:170-189: WeTr.get_param_groups() -> [encoder weights, encoder norms, decoder (+ classifier)].  The flat
+    buffer must hold each group as one contiguous range (one AdamW launch per group) with exactly those members."""
+    from segmif_b200.core.model_fusion import Network3
+    from segmif_b200.ddp import FlatParams
+    net = Network3("mit_b0", 9, 256, None)
+    ref_groups = net.denoise_net.get_param_groups()
+    ids = [{id(p) for p in g} for g in ref_groups]
+    gid = lambda k: 2 if ".decoder." in k else (1 if "norm" in k.split("encoder.", 1)[-1] else 0)
+    keys_before = list(net.state_dict().keys())
+    flat = FlatParams(net, used=lambda k: not k.endswith("classifier.weight"), group_of=gid)
+    assert flat.skipped == ["denoise_net.classifier.weight"]
+    assert list(net.state_dict().keys()) == keys_before
+    lookup = dict(net.named_parameters())
+    covered = 0
+    for g in (0, 1, 2):
+        lo, hi = flat.group_ranges[g]
+        members = [k for k, (off, n) in flat.offsets.items() if lo <= off < hi]
+        assert all(gid(k) == g for k in members)
+        assert {id(lookup[k]) for k in members} == ids[g] - {id(net.denoise_net.classifier.weight)}
+        covered += hi - lo
+    assert covered == flat.numel                                  # the three ranges tile the buffer
+    r = sorted(flat.group_ranges.values())
+    assert r[0][0] == 0 and r[0][1] == r[1][0] and r[1][1] == r[2][0] and r[2][1] == flat.numel
+
+
+def test_grouped_schedule_matches_reference_seg_optimizer():
+    """PolyWarmupAdamW_seg (utils/optimizer.py:36-66): every group's lr follows its own base lr times the common
+    multiplier, starting from iter_curr."""
+    from segmif_b200.ddp import poly_warmup_lr
+    from segmif_b200.utils.optimizer import PolyWarmupAdamW_seg
+    ps = [torch.nn.Parameter(torch.zeros(3)) for _ in range(3)]
+    opt = PolyWarmupAdamW_seg([{"params": [ps[0]], "lr": 6e-5, "weight_decay": 0.01}, {"params": [ps[1]], "lr": 6e-5, "weight_decay": 0.0},
+                               {"params": [ps[2]], "lr": 6e-4, "weight_decay": 0.01}], lr=6e-5, weight_decay=0.01, betas=(0.9, 0.999),
+                              iter_curr=5, warmup_iter=10, max_iter=40, warmup_ratio=1e-6, power=1.0)
+    lrs = [6e-5, 6e-5, 6e-4]
+    for step in range(5, 50):
+        for p in ps:
+            p.grad = torch.ones(3)
+        opt.step()
+        for i, base in enumerate((6e-5, 6e-5, 6e-4)):
+            lrs[i] = poly_warmup_lr(base, step, 10, 40, 1e-6, 1.0, lrs[i])
+            assert abs(lrs[i] - opt.param_groups[i]["lr"]) < 1e-15, (i, step)

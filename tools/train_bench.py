@@ -1,7 +1,12 @@
-"""Times the data-parallel train_fusion step (train.py:343-386, round 1: Fusionloss3; --loss grad3 for rounds >= 2 without
-the CE term): frozen-encoder forward_fusion (no_grad) -> Fusion_Network3_ac forward -> loss -> hand-written backward ->
-ONE gradient all-reduce -> fused AdamW.  Not the headline bench (bench.py measures BASELINE configs[1]); this is the
-configs[2] workload restricted to the fusion network, per-GPU batch 4 at 480x640.
+"""Times the data-parallel training steps of train.py (BASELINE configs[2]; not the headline bench -- bench.py measures
+configs[1]), per-GPU batch 4 at 480x640:
+  --mode fusion     train_fusion round 1 (train.py:343-386, Fusionloss3; --loss grad3 = rounds >= 2 without the CE term):
+                    frozen-encoder forward_fusion (no_grad) -> Fusion_Network3_ac forward -> loss -> hand-written
+                    backward -> ONE gradient all-reduce -> fused AdamW
+  --mode fusion_ce  train_fusion rounds >= 2 (train.py:361-380): + YCrCb2RGB -> Network3._loss (CE) differentiated
+                    through the frozen segmentation network (train mode: batch-statistics BN, DropPath, Dropout2d)
+  --mode seg        train_seg (train.py:207-226): Network3 forward -> upsample + CE -> backward -> all-reduce of the
+                    24.7 M-parameter flat buffer -> AdamW over three param groups
     python tools/train_bench.py [--batch 4] [--steps 10]            # 1 GPU
     python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/train_bench.py"""
 import argparse
@@ -25,28 +30,44 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--backbone", default="mit_b2")
     ap.add_argument("--loss", default="loss3", choices=["loss3", "grad3", "grad2"])
+    ap.add_argument("--mode", default="fusion", choices=["fusion", "fusion_ce", "seg"])
     a = ap.parse_args()
     from segmif_b200 import _lib, synth
     from segmif_b200.core.loss import Fusionloss3, Fusionloss_grad2, Fusionloss_grad3
     from segmif_b200.core.model_fusion import Fusion_Network3_ac, Network3, RGB2YCrCb
-    from segmif_b200.ddp import FusionTrainer
+    from segmif_b200.ddp import FusionTrainer, SegTrainer
     world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    seg = synth.load_synthetic(Network3(a.backbone, 9, 256, None), 0).eval().to(dev)
-    fus = synth.load_synthetic(Fusion_Network3_ac(), 0).train().to(dev)
-    crit = {"loss3": Fusionloss3, "grad3": Fusionloss_grad3, "grad2": Fusionloss_grad2}[a.loss]()
-    tr = FusionTrainer(fus, crit, lr=3e-4, weight_decay=0.01, betas=(0.9, 0.999), warmup_iter=3e-5, max_iter=6000,
-                       warmup_ratio=1e-6, power=1.0)
+    torch.manual_seed(1234 + rank)                                                   # DropPath / Dropout2d draws
+    seg = synth.load_synthetic(Network3(a.backbone, 9, 256, None), 0).to(dev)
+    seg = seg.train() if a.mode != "fusion" else seg.eval()       # train.py never calls .eval() on it; "fusion" keeps v1's setup
     inp = {k: v.to(dev) for k, v in synth.synth_inputs(a.batch, a.height, a.width, seed=rank).items()}
+    if a.mode == "seg":
+        tr = SegTrainer(seg, lr=6e-5, weight_decay=0.01, betas=(0.9, 0.999), warmup_iter=1500, max_iter=160000,
+                        warmup_ratio=1e-6, power=1.0)
 
-    def step():
-        with torch.no_grad():
-            vis = RGB2YCrCb(inp["vis"])                                              # train.py:356
-            out0, out1 = seg.denoise_net.encoder.forward_fusion(inp["mask"])         # train.py:358-359
-        return tr.step(inp["ir"], vis, out0, out1, inp["mask"])
+        def step():
+            return (tr.step(inp["mask"], inp["labels"]),)
+    else:
+        fus = synth.load_synthetic(Fusion_Network3_ac(), 0).train().to(dev)
+        if a.mode == "fusion_ce":
+            tr = FusionTrainer(fus, Fusionloss_grad3(), lr=1.5e-4, weight_decay=0.01, betas=(0.9, 0.999), warmup_iter=1.5e-5,
+                               max_iter=6000, warmup_ratio=1e-6, power=1.0, seg_net=seg, iter_=2)
+        else:
+            crit = {"loss3": Fusionloss3, "grad3": Fusionloss_grad3, "grad2": Fusionloss_grad2}[a.loss]()
+            tr = FusionTrainer(fus, crit, lr=3e-4, weight_decay=0.01, betas=(0.9, 0.999), warmup_iter=3e-5, max_iter=6000,
+                               warmup_ratio=1e-6, power=1.0)
+
+        def step():
+            with torch.no_grad():
+                vis = RGB2YCrCb(inp["vis"])                                              # train.py:356
+                out0, out1 = seg.denoise_net.encoder.forward_fusion(inp["mask"])         # train.py:358-359
+            if a.mode == "fusion_ce":
+                return tr.step(inp["ir"], vis, out0, out1, inp["mask"], vis_rgb=inp["vis"], labels=inp["labels"])
+            return tr.step(inp["ir"], vis, out0, out1, inp["mask"])
 
     losses = []
     for _ in range(max(a.warmup, 1)):
@@ -74,9 +95,11 @@ def main():
         in_sync = True
     if rank == 0:
         ms = float(ms.item())
-        print(json.dumps({"metric": "train_fusion_pairs_per_sec", "value": a.batch * world * a.steps / (ms * 1e-3), "unit": "pairs/s",
+        print(json.dumps({"metric": {"fusion": "train_fusion_pairs_per_sec", "fusion_ce": "train_fusion_ce_pairs_per_sec",
+                                     "seg": "train_seg_images_per_sec"}[a.mode], "value": a.batch * world * a.steps / (ms * 1e-3), "unit": "pairs/s",
                           "n_gpus": world, "steps": a.steps, "ms_per_step": ms / a.steps, "batch_per_gpu": a.batch,
-                          "height": a.height, "width": a.width, "loss": a.loss, "scaling": "weak",
+                          "height": a.height, "width": a.width, "loss": a.loss if a.mode == "fusion" else "ce", "mode": a.mode, "backbone": a.backbone, "scaling": "weak",
+                          "allreduce_mb": tr.flat.numel * 4 / 2 ** 20,
                           "launches_per_step": (_lib.launch_count - l0) / a.steps, "replicas_in_sync": in_sync,
                           "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30,
                           "loss_first_last": [float(losses[0]), float(losses[-1])]}), flush=True)

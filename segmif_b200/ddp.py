@@ -10,7 +10,6 @@ slot would silently decay them ("unused parameters under DD
 import torch
 import torch.distributed as dist
 
-from . import packing
 
 
 class FlatParams:
@@ -30,9 +29,11 @@ class FlatParams:
         self.param = torch.zeros((self.numel,), dtype=torch.float32, device=dev)
         self.grad = torch.zeros((self.numel,), dtype=torch.float32, device=dev)
         self.offsets = {}
+        self.epoch = [0]                              # bumped by the optimizer; PackCache reads it through the parameter
         off = 0
         with torch.no_grad():
             for k, p in self.named:
+                p._segmif_epoch = self.epoch
                 n = p.numel()
                 self.param[off:off + n].copy_(p.detach().reshape(-1))
                 p.data = self.param[off:off + n].view(p.shape)
@@ -115,62 +116,118 @@ class FusedPolyWarmupAdamW:
             ops.adamw_step(self.flat.param[lo:hi], self.flat.grad[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi],
                            lr=g["lr"], beta1=self.betas[0], beta2=self.betas[1], eps=self.eps,
                            weight_decay=g["weight_decay"], step=self.opt_steps + 1, grad_scale=grad_scale)
-        packing.invalidate_all()
+        self.flat.epoch[0] += 1                       # the kernel wrote through raw pointers: packed copies are stale
         self.global_step += 1
         self.opt_steps += 1
 
 
-class FusionTrainer:
+class _GraphedStep:
+    """Optional CUDA-graph form of a trainer's forward + backward: `capture(*example_inputs)` records zero_grad, the
+    forward, the loss and the whole reverse pass (about 850 kernel launches for train_seg, each a Python -> ctypes ->
+    cudaLaunchKernel round trip in eager mode) into one graph over static input buffers; `step` then copies the batch
+    into those buffers and replays.  The gradient all-reduce and the AdamW launches stay outside the graph (the
+    learning rate and step count are host scalars that change every step).  Run at least one eager step first
+    (lazy per-kernel initialisation is not capturable)."""
+
+    _graph = None
+
+    def _capture(self, body, **static_inputs):
+        self._static = {k: v.clone() for k, v in static_inputs.items() if v is not None}
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            outs = body(**self._static)
+        self._graph, self._graph_outs = graph, outs
+        return self
+
+    def _replay(self, **inputs):
+        for k, v in inputs.items():
+            if v is not None:
+                self._static[k].copy_(v, non_blocking=True)
+        self._graph.replay()
+        return tuple(o.clone() for o in self._graph_outs)
+
+    def _finish(self):
+        world = self.flat.all_reduce(self.group)
+        self.opt.step(grad_scale=1.0 / world)
+
+
+class FusionTrainer(_GraphedStep):
     """One optimisation step of train_fusion (train.py:343-386) for the fusion network, data parallel:
         fused = model2(ir, vis_ycrcb, out0, out1);  loss = criterion(ir, vis, fused, mask);  loss.backward();
         all-reduce;  AdamW.
-    The encoder features out0 / out1 come from the frozen segmentation network (train.py:358-359, no_grad).
+    The encoder features out0 / out1 come from the frozen segmentation network (train.py:358-359, no_grad):
+    `step` takes them as arguments, `step_images` computes them itself from `seg_net` (and can be graph-captured).
 
-    With `seg_net` given, the step is the rounds >= 2 composite (train.py:361-380, iter_ > 1):
+    With `seg_net` given and `with_ce`, the step is the rounds >= 2 composite (train.py:361-380, iter_ > 1):
         loss1 = criterion(...);  loss2 = seg_net._loss(YCrCb2RGB([fused, Cr, Cb]), labels, CE);
         loss = w0 * loss1 * (0.4 / iter_) + w1 * loss2 * 0.8,   (w0, w1) = 2 softmax(ratio of the two previous losses / 1000)
-    The reference reads the loss history on the host with .item() every step; here it is a device-resident [2, 3] ring
-    (no synchronisation), weights all ones for the first 11 steps as in train.py:377-380.  The segmentation network is
-    differentiated through but frozen: its weight gradients (which the reference computes and never uses, SURVEY.md
-    App. B) are skipped."""
+    The reference reads the loss history on the host with .item() every step; here the two previous loss pairs and the
+    step count are device-resident (no synchronisation, capturable), weights all ones for the first 11 steps as in
+    train.py:377-380.  The segmentation network is differentiated through but frozen: its weight gradients (which the
+    reference computes and never uses) are skipped."""
 
     def __init__(self, fusion_net, criterion, lr=3e-4, weight_decay=0.01, betas=(0.9, 0.999), warmup_iter=3e-5,
-                 max_iter=40000, warmup_ratio=1e-6, power=1.0, group=None, seg_net=None, iter_=1, ignore_index=255):
+                 max_iter=40000, warmup_ratio=1e-6, power=1.0, group=None, seg_net=None, iter_=1, ignore_index=255,
+                 with_ce=None):
         self.net, self.criterion, self.group = fusion_net, criterion, group
         self.flat = FlatParams(fusion_net, used=lambda k: not k.startswith("ffm2."))
         self.opt = FusedPolyWarmupAdamW(self.flat, lr, weight_decay, betas, warmup_iter, max_iter, warmup_ratio, power)
         self.seg_net, self.iter_ = seg_net, iter_
-        self.n_iter = 0
-        if seg_net is not None:
+        self.with_ce = (seg_net is not None) if with_ce is None else with_ce
+        if self.with_ce:
             for p in seg_net.parameters():
                 p.requires_grad_(False)
             self.ce = torch.nn.CrossEntropyLoss(ignore_index=ignore_index)
-            self.history = torch.ones((2, 3), dtype=torch.float32, device=self.flat.param.device)
+            dev = self.flat.param.device
+            self.prev1 = torch.ones((2,), dtype=torch.float32, device=dev)        # losses of step n-1
+            self.prev2 = torch.ones((2,), dtype=torch.float32, device=dev)        # losses of step n-2
+            self.count = torch.zeros((), dtype=torch.float32, device=dev)         # n_iter
 
-    def step(self, ir, vis_ycrcb, out0, out1, mask, vis_rgb=None, labels=None):
+    def _forward_backward(self, ir, vis_ycrcb, out0, out1, mask, vis_rgb=None, labels=None):
         self.flat.zero_grad()
         fused = self.net(ir, vis_ycrcb, out0, out1)
         loss = self.criterion(ir, vis_ycrcb, fused, mask)
-        if self.seg_net is not None:
+        if self.with_ce:
             from .autograd import recompose_rgb
             loss2 = self.seg_net._loss(recompose_rgb(fused, vis_rgb, False), labels, self.ce)
-            h = self.history
-            slot = self.n_iter % 3
-            h[0, slot], h[1, slot] = loss.detach(), loss2.detach()
-            if self.n_iter > 10:
-                w_i = h[:, (self.n_iter - 1) % 3] / h[:, (self.n_iter - 2) % 3]
-                bw = 2 * torch.softmax(w_i / 1000.0, dim=-1)
-                loss = bw[0] * loss * (0.4 / self.iter_) + bw[1] * loss2 * 0.8
-            else:
-                loss = (0.4 / self.iter_) * loss + 0.8 * loss2
+            bw = 2 * torch.softmax((self.prev1 / self.prev2) / 1000.0, dim=-1)                  # train.py:373-374
+            bw = torch.where(self.count > 10, bw, torch.ones_like(bw))                          # train.py:370,377-380
+            cur = torch.stack([loss.detach(), loss2.detach()])
+            loss = bw[0] * loss * (0.4 / self.iter_) + bw[1] * loss2 * 0.8
+            self.prev2.copy_(self.prev1)
+            self.prev1.copy_(cur)
+            self.count += 1
         loss.backward()
-        world = self.flat.all_reduce(self.group)
-        self.opt.step(grad_scale=1.0 / world)
-        self.n_iter += 1
         return loss.detach(), fused.detach()
 
+    def _images_body(self, ir, vis_rgb, mask, labels=None):
+        from .core.model_fusion import RGB2YCrCb
+        with torch.no_grad():
+            vis = RGB2YCrCb(vis_rgb)                                                            # train.py:356
+            out0, out1 = self.seg_net.denoise_net.encoder.forward_fusion(mask)                  # train.py:358-359
+        return self._forward_backward(ir, vis, out0, out1, mask, vis_rgb, labels)
 
-class SegTrainer:
+    def step(self, ir, vis_ycrcb, out0, out1, mask, vis_rgb=None, labels=None):
+        out = self._forward_backward(ir, vis_ycrcb, out0, out1, mask, vis_rgb, labels)
+        self._finish()
+        return out
+
+    def capture_images(self, ir, vis_rgb, mask, labels=None):
+        return self._capture(self._images_body, ir=ir, vis_rgb=vis_rgb, mask=mask, labels=labels)
+
+    def step_images(self, ir, vis_rgb, mask, labels=None):
+        """train.py:350-381 from the loader's tensors: RGB->YCrCb, frozen-encoder features, fusion forward, loss(es),
+        backward; then the all-reduce and AdamW."""
+        if self._graph is not None:
+            out = self._replay(ir=ir, vis_rgb=vis_rgb, mask=mask, labels=labels)
+        else:
+            out = self._images_body(ir, vis_rgb, mask, labels)
+        self._finish()
+        return out
+
+
+class SegTrainer(_GraphedStep):
     """One optimisation step of train_seg (train.py:207-226), data parallel:
         _, _, segmap = model(mask);  loss = CE(bilinear(segmap -> label size), labels);  backward;  all-reduce;  AdamW
     with train.py:170-189's three param groups (WeTr.get_param_groups: encoder weights, encoder norms with weight_decay 0,
@@ -187,10 +244,19 @@ class SegTrainer:
                                                 2: dict(lr=lr * 10, weight_decay=weight_decay)}, iter_curr=iter_curr)
         self.ce = torch.nn.CrossEntropyLoss(ignore_index=ignore_index)
 
-    def step(self, mask, labels):
+    def _forward_backward(self, mask, labels):
         self.flat.zero_grad()
         loss = self.net._loss(mask, labels, self.ce)
         loss.backward()
-        world = self.flat.all_reduce(self.group)
-        self.opt.step(grad_scale=1.0 / world)
-        return loss.detach()
+        return (loss.detach(),)
+
+    def capture(self, mask, labels):
+        return self._capture(self._forward_backward, mask=mask, labels=labels)
+
+    def step(self, mask, labels):
+        if self._graph is not None:
+            (loss,) = self._replay(mask=mask, labels=labels)
+        else:
+            (loss,) = self._forward_backward(mask, labels)
+        self._finish()
+        return loss

@@ -7,9 +7,17 @@ _EPOCH = [0]
 
 
 def invalidate_all():
-    """Called by the fused optimizer: its kernel updates parameters through raw pointers, which does not bump
-    torch's per-tensor version counters, so every cached pack is declared stale explicitly."""
+    """Declares every cached pack stale (for code that writes parameters through raw pointers without going through
+    ddp.FlatParams, whose optimizer bumps a per-buffer epoch instead -- see _epoch)."""
     _EPOCH[0] += 1
+
+
+def _epoch(param):
+    """The fused optimizer updates parameters through raw pointers, which does not bump torch's per-tensor version
+    counters; ddp.FlatParams therefore hangs a shared mutable epoch on each parameter it owns and the optimizer bumps
+    it.  Parameters outside any flat buffer (a frozen network next to a trained one) are not invalidated by it."""
+    e = getattr(param, "_segmif_epoch", None)
+    return (_EPOCH[0], e[0] if e is not None else -1)
 
 
 class PackCache:
@@ -30,7 +38,7 @@ class PackCache:
 
     def get(self, param, fn, tag=""):
         key = (id(param), tag)
-        stamp = (param.data_ptr(), param._version, param.device, _EPOCH[0])
+        stamp = (param.data_ptr(), param._version, param.device, _epoch(param))
         hit = self._c.get(key)
         if hit is not None and hit[0] == stamp:
             return hit[1]
@@ -42,7 +50,7 @@ class PackCache:
     def get_multi(self, params, fn, tag):
         """One packed object derived from several parameters."""
         key = ("multi", tag)
-        stamp = tuple((p.data_ptr(), p._version, p.device) for p in params) + (_EPOCH[0],)
+        stamp = tuple((p.data_ptr(), p._version, p.device, _epoch(p)) for p in params)
         hit = self._c.get(key)
         if hit is not None and hit[0] == stamp:
             return hit[1]

@@ -676,6 +676,19 @@ def seg_trainer_steps():
                 num += float((du - dr).pow(2).sum())
                 den += float(dr.pow(2).sum())
         res.append(result(f"seg_trainer_update_rel_l2_group{g}", (num / den) ** 0.5, 0.35))
+    # the same three steps with forward + backward replayed from a CUDA graph (captured after one eager step)
+    net2 = copy.deepcopy(net0).to(DEV).train()
+    net2.denoise_net.decoder.dropout.p = 0.0
+    for m in net2.modules():
+        if hasattr(m, "drop_prob"):
+            m.drop_prob = 0.0
+    tr2 = SegTrainer(net2, lr=lr, weight_decay=wd, betas=(0.9, 0.999), warmup_iter=2, max_iter=100, warmup_ratio=1e-6, power=1.0)
+    xd, ld = x.to(DEV), labels.to(DEV)
+    got2 = [float(tr2.step(xd, ld))]
+    tr2.capture(xd, ld)
+    got2 += [float(tr2.step(xd, ld)) for _ in range(2)]
+    res.append(result("seg_trainer_graph_equals_eager_losses", max(abs(a - b) / abs(b) for a, b in zip(got2, got)), 1e-3, note=f"{got2}"))
+    res.append(result("seg_trainer_graph_equals_eager_params", rel_err(tr2.flat.param, tr.flat.param), 1e-2))
     cw = net.denoise_net.classifier.weight
     res.append(result("seg_trainer_classifier_frozen", float((cw.detach().cpu() - sd["denoise_net.classifier.weight"]).abs().max()), 0.0))
     res.append(result("seg_trainer_lr_groups", max(abs(tr.opt.groups[i]["lr"] - b * (1 - 2 / 100.0)) / b for i, b in enumerate(base)), 1e-6))

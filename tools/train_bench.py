@@ -31,10 +31,11 @@ def main():
     ap.add_argument("--backbone", default="mit_b2")
     ap.add_argument("--loss", default="loss3", choices=["loss3", "grad3", "grad2"])
     ap.add_argument("--mode", default="fusion", choices=["fusion", "fusion_ce", "seg"])
+    ap.add_argument("--graph", type=int, default=1, help="1: forward+backward replayed from one CUDA graph; 0: eager launches")
     a = ap.parse_args()
     from segmif_b200 import _lib, synth
     from segmif_b200.core.loss import Fusionloss3, Fusionloss_grad2, Fusionloss_grad3
-    from segmif_b200.core.model_fusion import Fusion_Network3_ac, Network3, RGB2YCrCb
+    from segmif_b200.core.model_fusion import Fusion_Network3_ac, Network3
     from segmif_b200.ddp import FusionTrainer, SegTrainer
     world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
     torch.cuda.set_device(local)
@@ -51,6 +52,8 @@ def main():
 
         def step():
             return (tr.step(inp["mask"], inp["labels"]),)
+
+        capture = lambda: tr.capture(inp["mask"], inp["labels"])
     else:
         fus = synth.load_synthetic(Fusion_Network3_ac(), 0).train().to(dev)
         if a.mode == "fusion_ce":
@@ -59,17 +62,18 @@ def main():
         else:
             crit = {"loss3": Fusionloss3, "grad3": Fusionloss_grad3, "grad2": Fusionloss_grad2}[a.loss]()
             tr = FusionTrainer(fus, crit, lr=3e-4, weight_decay=0.01, betas=(0.9, 0.999), warmup_iter=3e-5, max_iter=6000,
-                               warmup_ratio=1e-6, power=1.0)
+                               warmup_ratio=1e-6, power=1.0, seg_net=seg, with_ce=False)
+        lab = inp["labels"] if a.mode == "fusion_ce" else None
 
         def step():
-            with torch.no_grad():
-                vis = RGB2YCrCb(inp["vis"])                                              # train.py:356
-                out0, out1 = seg.denoise_net.encoder.forward_fusion(inp["mask"])         # train.py:358-359
-            if a.mode == "fusion_ce":
-                return tr.step(inp["ir"], vis, out0, out1, inp["mask"], vis_rgb=inp["vis"], labels=inp["labels"])
-            return tr.step(inp["ir"], vis, out0, out1, inp["mask"])
+            return tr.step_images(inp["ir"], inp["vis"], inp["mask"], lab)
+
+        capture = lambda: tr.capture_images(inp["ir"], inp["vis"], inp["mask"], lab)
 
     losses = []
+    losses.append(step()[0])                      # eager: lazy per-kernel initialisation happens here
+    if a.graph:
+        capture()
     for _ in range(max(a.warmup, 1)):
         losses.append(step()[0])
     if world > 1:
@@ -98,9 +102,9 @@ def main():
         print(json.dumps({"metric": {"fusion": "train_fusion_pairs_per_sec", "fusion_ce": "train_fusion_ce_pairs_per_sec",
                                      "seg": "train_seg_images_per_sec"}[a.mode], "value": a.batch * world * a.steps / (ms * 1e-3), "unit": "pairs/s",
                           "n_gpus": world, "steps": a.steps, "ms_per_step": ms / a.steps, "batch_per_gpu": a.batch,
-                          "height": a.height, "width": a.width, "loss": a.loss if a.mode == "fusion" else "ce", "mode": a.mode, "backbone": a.backbone, "scaling": "weak",
+                          "height": a.height, "width": a.width, "loss": a.loss if a.mode == "fusion" else "ce", "mode": a.mode, "cuda_graph": bool(a.graph), "backbone": a.backbone, "scaling": "weak",
                           "allreduce_mb": tr.flat.numel * 4 / 2 ** 20,
-                          "launches_per_step": (_lib.launch_count - l0) / a.steps, "replicas_in_sync": in_sync,
+                          "eager_launches_per_step": (_lib.launch_count - l0) / a.steps, "replicas_in_sync": in_sync,
                           "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30,
                           "loss_first_last": [float(losses[0]), float(losses[-1])]}), flush=True)
     if world > 1:

@@ -362,11 +362,13 @@ int segmif_bn_train_bwd(const void* z, const void* y, const void* dy, const floa
 /* y[b,p,c] = x[b,p,c] * scale[b,c]: nn.Dropout2d forward and backward (core/segformer_head.py:57,79), bf16 [B,HW,C]. */
 int segmif_channel_scale(const void* x, const float* scale, void* y, int B, int64_t HW, int C, segmif_stream_t stream);
 /* depthwise 3x3 without activation (flip != 0: transposed taps = the data gradient of DWConv, mix_transformer.py:381-387)
- * and the backward of dwconv + GELU w.r.t. the pre-activation: dz = dy * gelu'(dwconv(x) + b), dw9c / dbias accumulated. */
+ * and the backward of dwconv + GELU w.r.t. the pre-activation: dz = dy * gelu'(dwconv(x) + b), dw9c / dbias accumulated
+ * from per-strip partials in `workspace` (fixed summation order: deterministic).                                      */
 int segmif_dwconv3x3(const void* x, const float* w9c, const float* bias, void* y, int B, int H, int W, int C, int flip,
                      segmif_stream_t stream);
+int64_t segmif_dwconv3x3_gelu_bwd_workspace(int B, int H, int W, int C);      /* number of floats (need not be zeroed) */
 int segmif_dwconv3x3_gelu_bwd(const void* x, const float* w9c, const float* bias, const void* dy, void* dz, int B, int H,
-                              int W, int C, float* dw9c, float* dbias, segmif_stream_t stream);
+                              int W, int C, float* dw9c, float* dbias, float* workspace, segmif_stream_t stream);
 /* adjoint of im2col for the strided convolutions (OverlapPatchEmbed.proj mix_transformer.py:193, Attention.sr :100):
  * dcol bf16 [B*Ho*Wo, ldc], column (c*k + ky)*k + kx  ->  dx [B,H,W,C] pixel-major (fp32 or bf16).                   */
 int segmif_col2im(const void* dcol, int ldc, void* dx, int dx_dtype, int B, int H, int W, int C, int k, int stride, int pad,

@@ -123,14 +123,16 @@ SIGNATURES = {
     "segmif_bn_train_bwd": [P, P, P, P, P, c_int64, c_int, P, P, P, P, P],
     "segmif_channel_scale": [P, P, P, c_int, c_int64, c_int, P],
     "segmif_dwconv3x3": [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P],
-    "segmif_dwconv3x3_gelu_bwd": [P, P, P, P, P, c_int, c_int, c_int, c_int, P, P, P],
+    "segmif_dwconv3x3_gelu_bwd": [P, P, P, P, P, c_int, c_int, c_int, c_int, P, P, P, P],
+    "segmif_dwconv3x3_gelu_bwd_workspace": [c_int, c_int, c_int, c_int],
     "segmif_col2im": [P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P],
     "segmif_channel_affine_nchw": [P, P, P, P, c_int, c_int, c_int64, P],
     "segmif_recompose_rgb_bwd": [P, P, P, c_int, c_int, c_int64, P],
     "segmif_cast": [P, c_int, P, c_int, c_int64, P],
     "segmif_scale_add_rows": [P, P, c_int, P, P, c_int64, c_int64, c_int, P],
 }
-_RESTYPES = {"segmif_last_error": c_char_p, "segmif_loss_workspace_bytes": c_size_t, "segmif_wgrad_workspace_bytes": c_size_t}
+_RESTYPES = {"segmif_last_error": c_char_p, "segmif_loss_workspace_bytes": c_size_t, "segmif_wgrad_workspace_bytes": c_size_t,
+             "segmif_dwconv3x3_gelu_bwd_workspace": c_int64}
 
 _lib = None
 _lock = threading.Lock()

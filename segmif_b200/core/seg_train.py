@@ -62,8 +62,7 @@ def _wgrad(g, *args, **kw):
 def _colsum(dy, N, rows, out, g=None):
     if g is not None and g.frozen:
         return
-    for c0 in range(0, N, 256):
-        ops.colsum(dy, N, c0, rows, min(256, N - c0), out[c0:])
+    ops.colsum(dy, N, 0, rows, N, out)
 
 
 def _lin_bwd(dy, x, weight_param, cache, g, wname, bname, need_dx=True, residual=None):
@@ -239,7 +238,7 @@ def _block_backward(blk, sv, dx, B, N, g, pre):
     dw9c = torch.zeros((9, hid), dtype=F32, device=dev)
     dz = ops.dwconv3x3_gelu_bwd(sv["h1"], ml.dwconv._w(), ml.dwconv.dwconv.bias.detach(), dh2, B, H, W, dw9c,
                                 g[pre + "mlp.dwconv.dwconv.bias"])
-    g[pre + "mlp.dwconv.dwconv.weight"].copy_(dw9c.t().reshape(hid, 1, 3, 3))
+    g[pre + "mlp.dwconv.dwconv.weight"].add_(dw9c.t().reshape(hid, 1, 3, 3))
     dh1 = ops.dwconv3x3(dz, ml.dwconv._w(), None, B, H, W, flip=True)
     dn2 = _lin_bwd(dh1, sv["n2"], ml.fc1.weight, ml._packs, g, pre + "mlp.fc1.weight", pre + "mlp.fc1.bias")
     ops.layernorm_bwd(sv["x2"], dn2, C, 0, blk.norm2.weight.detach(), blk.norm2.eps, dx, C, 0, M, C,
@@ -329,7 +328,7 @@ def head_backward(head, tape, dlogits, B, g, prefix):
               s_co=E, s_tap=1, s_ci=1, co_take=nc)
     db = torch.zeros((32,), dtype=F32, device=dev)
     ops.colsum(dl, 32, 0, M, 32, db)
-    g[prefix + "linear_pred.bias"].copy_(db[:nc])
+    g[prefix + "linear_pred.bias"].add_(db[:nc])
 
     def wt_pred(w):
         w2 = w.detach().reshape(nc, E).float()
@@ -377,12 +376,33 @@ class SegNetFn(torch.autograd.Function):
         dev = dlogits.device
         B = ctx.etape["B"]
         lookup = dict(net3.named_parameters())
-        g = _Grads((n, torch.zeros(lookup[n].shape, dtype=F32, device=dev)) for n in ctx.names)
+        # A parameter whose .grad already exists (ddp.FlatParams pre-allocates them as views of one flat buffer) gets its
+        # gradient accumulated IN PLACE by the kernels (they all add into their output) and None is returned for it:
+        # saves a zero-fill, an AccumulateGrad add and 2x the parameter bytes of traffic per tensor.  The others share
+        # one zero-filled scratch buffer (a single fill instead of one per tensor).
+        g = _Grads()
         g.frozen = not any(ctx.needs_input_grad[4:])
+        direct, pending = {}, []
+        for i, n in enumerate(ctx.names):
+            p = lookup[n]
+            pg = p.grad
+            if ctx.needs_input_grad[4 + i] and pg is not None and pg.dtype == F32 and pg.is_contiguous() and pg.device == dev \
+                    and not torch.is_grad_enabled() and pg.shape == p.shape:
+                g[n] = pg
+                direct[n] = True
+            else:
+                pending.append((n, p))
+        if pending:
+            pad4 = lambda k: (k + 3) & ~3
+            flat = torch.zeros((sum(pad4(p.numel()) for _, p in pending),), dtype=F32, device=dev)
+            off = 0
+            for n, p in pending:
+                g[n] = flat[off:off + p.numel()].view(p.shape)
+                off += pad4(p.numel())
         douts = head_backward(wetr.decoder, ctx.htape, dlogits.float().contiguous(), B, g, "denoise_net.decoder.")
         dimg = encoder_backward(wetr.encoder, ctx.etape, douts, g, "denoise_net.encoder.", ctx.want_x)
         ctx.etape = ctx.htape = None
-        grads = tuple(g[n] if ctx.needs_input_grad[4 + i] else None for i, n in enumerate(ctx.names))
+        grads = tuple(g[n] if (ctx.needs_input_grad[4 + i] and n not in direct) else None for i, n in enumerate(ctx.names))
         return (None, dimg if ctx.want_x else None, None, None) + grads
 
 

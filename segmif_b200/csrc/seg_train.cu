@@ -257,97 +257,144 @@ __global__ void __launch_bounds__(256) channel_scale_kernel(const bf16* __restri
 }
 
 // ------------------------------------------------------------------------------------------------ depthwise conv
+// Strip-walking layout shared by the two kernels below.  A block owns one tile of `tcg` channel PAIRS (<= 64 pairs = 128
+// channels = 256 B per pixel) and a strip of S = 256 / tcg adjacent image columns, and walks down the rows of its row
+// range: thread (pair, column) loads its 3x3 neighbourhood as nine 4-byte loads (a warp reads whole 128-byte lines), so
+// the three rows of the strip (+1 halo column each side) stay in L1 between consecutive rows and every input line comes
+// from L2 about 1.5x instead of 9x.  Two channels per thread keep the backward's 9x2 + 2 weight-gradient accumulators in
+// registers at three resident blocks per SM.
+struct DwStrip {
+  int c, col, row0, row1, b;
+  bool live;
+};
+__device__ __forceinline__ DwStrip dw_strip(int tcg, int S, int strips_x, int rchunks, int H, int W) {
+  DwStrip d;
+  const int pair = threadIdx.x % tcg, slot = threadIdx.x / tcg;
+  d.c = (blockIdx.x * tcg + pair) * 2;
+  int u = blockIdx.y;
+  const int rc = u % rchunks; u /= rchunks;
+  const int sx = u % strips_x;
+  d.b = u / strips_x;
+  d.col = sx * S + slot;
+  const int rows_per = (H + rchunks - 1) / rchunks;
+  d.row0 = rc * rows_per;
+  d.row1 = min(H, d.row0 + rows_per);
+  d.live = slot < S && d.col < W;
+  return d;
+}
+__device__ __forceinline__ float2 ld_bf2(const bf16* p) {
+  const uint32_t u = *reinterpret_cast<const uint32_t*>(p);
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+__device__ __forceinline__ void st_bf2(bf16* p, float a, float b) {
+  *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
+}
+
 // y = dwconv3x3(x) (+ bias), pixel-major bf16, w fp32 [9][C]; flip != 0 uses the transposed taps (data gradient)
 __global__ void __launch_bounds__(256) dwconv3x3_kernel(const bf16* __restrict__ x, const float* __restrict__ w9c,
-                                                        const float* __restrict__ bias, bf16* __restrict__ y, int B, int H,
-                                                        int W, int C, int flip) {
-  const int g = C >> 3;
-  const int64_t n = (int64_t)B * H * W * g;
-  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
-    const int grp = (int)(i % g);
-    const int64_t pix = i / g;
-    const int px = (int)(pix % W), py = (int)((pix / W) % H);
-    const int64_t b = pix / ((int64_t)W * H);
-    float acc[8];
+                                                        const float* __restrict__ bias, bf16* __restrict__ y, int H, int W,
+                                                        int C, int flip, int tcg, int S, int strips_x, int rchunks) {
+  const DwStrip d = dw_strip(tcg, S, strips_x, rchunks, H, W);
+  if (!d.live) return;
+  float2 wr[9];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] = bias ? bias[grp * 8 + e] : 0.f;
+  for (int t = 0; t < 9; ++t) wr[t] = *reinterpret_cast<const float2*>(w9c + (flip ? 8 - t : t) * C + d.c);
+  const float2 bv = bias ? *reinterpret_cast<const float2*>(bias + d.c) : make_float2(0.f, 0.f);
+  const bool hasl = d.col > 0, hasr = d.col + 1 < W;
+  for (int r = d.row0; r < d.row1; ++r) {
+    float2 acc = bv;
 #pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      const int yy = py + t / 3 - 1, xx = px + t % 3 - 1;
-      if ((unsigned)yy >= (unsigned)H || (unsigned)xx >= (unsigned)W) continue;
-      float v[8];
-      load8(x + ((b * H + yy) * W + xx) * C + grp * 8, v);
-      const float* wt = w9c + (flip ? 8 - t : t) * C + grp * 8;
-#pragma unroll
-      for (int e = 0; e < 8; ++e) acc[e] = fmaf(wt[e], v[e], acc[e]);
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yy = r + ky - 1;
+      if ((unsigned)yy >= (unsigned)H) continue;
+      const bf16* row = x + ((size_t)(d.b * H + yy) * W + d.col) * C + d.c;
+      if (hasl) { const float2 v = ld_bf2(row - C); acc.x = fmaf(wr[ky * 3].x, v.x, acc.x); acc.y = fmaf(wr[ky * 3].y, v.y, acc.y); }
+      { const float2 v = ld_bf2(row); acc.x = fmaf(wr[ky * 3 + 1].x, v.x, acc.x); acc.y = fmaf(wr[ky * 3 + 1].y, v.y, acc.y); }
+      if (hasr) { const float2 v = ld_bf2(row + C); acc.x = fmaf(wr[ky * 3 + 2].x, v.x, acc.x); acc.y = fmaf(wr[ky * 3 + 2].y, v.y, acc.y); }
     }
-    store8(y + pix * C + grp * 8, acc);
+    st_bf2(y + ((size_t)(d.b * H + r) * W + d.col) * C + d.c, acc.x, acc.y);
   }
 }
 
-// z = dwconv(x) + b;  dz = dy * gelu'(z);  dw[t][c] += sum dz * x(p + t);  db[c] += sum dz
+// z = dwconv(x) + b;  dz = dy * gelu'(z);  part[blockIdx.y][t][c] = sum dz * x(p + t) (t < 9), [9][c] = sum dz
 __global__ void __launch_bounds__(256) dwconv3x3_gelu_bwd_kernel(const bf16* __restrict__ x, const float* __restrict__ w9c,
                                                                  const float* __restrict__ bias, const bf16* __restrict__ dy,
-                                                                 bf16* __restrict__ dz, int B, int H, int W, int C,
+                                                                 bf16* __restrict__ dz, int H, int W, int C,
+                                                                 float* __restrict__ part, int tcg, int S, int strips_x,
+                                                                 int rchunks) {
+  __shared__ float sacc[10 * 128];
+  const DwStrip d = dw_strip(tcg, S, strips_x, rchunks, H, W);
+  float2 aw[9], ab = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int t = 0; t < 9; ++t) aw[t] = make_float2(0.f, 0.f);
+  if (d.live) {
+    float2 wr[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wr[t] = *reinterpret_cast<const float2*>(w9c + t * C + d.c);
+    const float2 bv = *reinterpret_cast<const float2*>(bias + d.c);
+    const bool hasl = d.col > 0, hasr = d.col + 1 < W;
+    for (int r = d.row0; r < d.row1; ++r) {
+      float2 xv[9];
+      float2 z = bv;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int yy = r + ky - 1;
+        const bool rowok = (unsigned)yy < (unsigned)H;
+        const bf16* row = x + ((size_t)(d.b * H + (rowok ? yy : r)) * W + d.col) * C + d.c;
+        xv[ky * 3] = (rowok && hasl) ? ld_bf2(row - C) : make_float2(0.f, 0.f);
+        xv[ky * 3 + 1] = rowok ? ld_bf2(row) : make_float2(0.f, 0.f);
+        xv[ky * 3 + 2] = (rowok && hasr) ? ld_bf2(row + C) : make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int t = 0; t < 9; ++t) { z.x = fmaf(wr[t].x, xv[t].x, z.x); z.y = fmaf(wr[t].y, xv[t].y, z.y); }
+      const size_t o = ((size_t)(d.b * H + r) * W + d.col) * C + d.c;
+      float2 g = ld_bf2(dy + o);
+      g.x *= 0.5f * (1.0f + erff(z.x * 0.70710678118654752440f)) + z.x * 0.39894228040143267794f * __expf(-0.5f * z.x * z.x);
+      g.y *= 0.5f * (1.0f + erff(z.y * 0.70710678118654752440f)) + z.y * 0.39894228040143267794f * __expf(-0.5f * z.y * z.y);
+      ab.x += g.x; ab.y += g.y;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) { aw[t].x = fmaf(g.x, xv[t].x, aw[t].x); aw[t].y = fmaf(g.y, xv[t].y, aw[t].y); }
+      st_bf2(dz + o, g.x, g.y);
+    }
+  }
+  const int tile_c = tcg * 2;
+  for (int i = threadIdx.x; i < 10 * tile_c; i += 256) sacc[i] = 0.f;
+  __syncthreads();
+  if (d.live) {
+    const int lc = (threadIdx.x % tcg) * 2;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) { atomicAdd(&sacc[t * tile_c + lc], aw[t].x); atomicAdd(&sacc[t * tile_c + lc + 1], aw[t].y); }
+    atomicAdd(&sacc[9 * tile_c + lc], ab.x);
+    atomicAdd(&sacc[9 * tile_c + lc + 1], ab.y);
+  }
+  __syncthreads();
+  float* dst = part + (size_t)blockIdx.y * 10 * C + blockIdx.x * tile_c;
+  for (int i = threadIdx.x; i < 10 * tile_c; i += 256) dst[(i / tile_c) * C + (i % tile_c)] = sacc[i];
+}
+
+// dw9c[i] += sum_u part[u][i] (i < 9C), dbias[c] += sum_u part[u][9C + c]: fixed summation order, no atomics
+__global__ void __launch_bounds__(256) dwconv_part_reduce_kernel(const float* __restrict__ part, int nparts, int C,
                                                                  float* __restrict__ dw9c, float* __restrict__ dbias) {
-  extern __shared__ float sacc[];                 // [10][C]
-  const int g = C >> 3, rpi = 256 / g;
-  const bool active = threadIdx.x < rpi * g;
-  const int grp = threadIdx.x % g, rin = threadIdx.x / g;
-  float aw[9][8], ab[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    ab[e] = 0.f;
-#pragma unroll
-    for (int t = 0; t < 9; ++t) aw[t][e] = 0.f;
-  }
-  const int64_t npix = (int64_t)B * H * W;
-  if (active)
-    for (int64_t pix = (int64_t)blockIdx.x * rpi + rin; pix < npix; pix += (int64_t)gridDim.x * rpi) {
-      const int px = (int)(pix % W), py = (int)((pix / W) % H);
-      const int64_t b = pix / ((int64_t)W * H);
-      float z[8], xv[9][8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) z[e] = bias[grp * 8 + e];
-#pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        const int yy = py + t / 3 - 1, xx = px + t % 3 - 1;
-        if ((unsigned)yy < (unsigned)H && (unsigned)xx < (unsigned)W) {
-          load8(x + ((b * H + yy) * W + xx) * C + grp * 8, xv[t]);
-        } else {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) xv[t][e] = 0.f;
-        }
-        const float* wt = w9c + t * C + grp * 8;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) z[e] = fmaf(wt[e], xv[t][e], z[e]);
-      }
-      float d[8];
-      load8(dy + pix * C + grp * 8, d);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float cdf = 0.5f * (1.0f + erff(z[e] * 0.70710678118654752440f));
-        const float pdf = 0.39894228040143267794f * expf(-0.5f * z[e] * z[e]);
-        d[e] *= cdf + z[e] * pdf;
-        ab[e] += d[e];
-#pragma unroll
-        for (int t = 0; t < 9; ++t) aw[t][e] = fmaf(d[e], xv[t][e], aw[t][e]);
-      }
-      store8(dz + pix * C + grp * 8, d);
-    }
-  for (int i = threadIdx.x; i < 10 * C; i += 256) sacc[i] = 0.f;
-  __syncthreads();
-  if (active) {
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      atomicAdd(&sacc[9 * C + grp * 8 + e], ab[e]);
-#pragma unroll
-      for (int t = 0; t < 9; ++t) atomicAdd(&sacc[t * C + grp * 8 + e], aw[t][e]);
-    }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 9 * C; i += 256) atomicAdd(dw9c + i, sacc[i]);
-  for (int i = threadIdx.x; i < C; i += 256) atomicAdd(dbias + i, sacc[9 * C + i]);
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= 10 * C) return;
+  float s = 0.f;
+  for (int u = 0; u < nparts; ++u) s += part[(size_t)u * 10 * C + i];
+  if (i < 9 * C) dw9c[i] += s; else dbias[i - 9 * C] += s;
+}
+
+struct DwGeom { int tcg, S, strips_x, rchunks, ctiles, units; };
+static DwGeom dw_geom(int B, int H, int W, int C) {
+  DwGeom g;
+  const int pairs = C / 2;
+  g.tcg = 64;
+  while (pairs % g.tcg) g.tcg >>= 1;                      // C % 8 == 0 -> tcg >= 4
+  g.S = 256 / g.tcg;
+  g.strips_x = (W + g.S - 1) / g.S;
+  g.ctiles = pairs / g.tcg;
+  const int base = B * g.strips_x * g.ctiles;
+  g.rchunks = std::max(1, std::min(H / 4, (2 * 148 + base - 1) / base));      // >= two blocks per SM, >= 4 rows per walk
+  g.units = B * g.strips_x * g.rchunks;
+  return g;
 }
 
 // ------------------------------------------------------------------------------------------------ col2im
@@ -492,26 +539,29 @@ extern "C" int segmif_channel_scale(const void* x, const float* scale, void* y, 
 extern "C" int segmif_dwconv3x3(const void* x, const float* w9c, const float* bias, void* y, int B, int H, int W, int C,
                                 int flip, segmif_stream_t stream) {
   SEGMIF_REQUIRE(x && w9c && y && C % 8 == 0 && B > 0 && H > 0 && W > 0, "dwconv3x3: bad arguments");
-  dwconv3x3_kernel<<<grid_n((int64_t)B * H * W * (C >> 3), 512), 256, 0, as_stream(stream)>>>((const bf16*)x, w9c, bias, (bf16*)y, B, H, W, C, flip);
+  const DwGeom g = dw_geom(B, H, W, C);
+  SEGMIF_REQUIRE(g.units <= 65535, "dwconv3x3: %d strips exceed the grid's y extent", g.units);
+  dwconv3x3_kernel<<<dim3(g.ctiles, g.units), 256, 0, as_stream(stream)>>>((const bf16*)x, w9c, bias, (bf16*)y, H, W, C, flip, g.tcg,
+                                                                           g.S, g.strips_x, g.rchunks);
   return check_launch("segmif_dwconv3x3");
 }
 
+extern "C" int64_t segmif_dwconv3x3_gelu_bwd_workspace(int B, int H, int W, int C) {
+  if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || C % 8) return 0;
+  return (int64_t)dw_geom(B, H, W, C).units * 10 * C;
+}
+
 extern "C" int segmif_dwconv3x3_gelu_bwd(const void* x, const float* w9c, const float* bias, const void* dy, void* dz, int B,
-                                         int H, int W, int C, float* dw9c, float* dbias, segmif_stream_t stream) {
-  SEGMIF_REQUIRE(x && w9c && bias && dy && dz && dw9c && dbias, "dwconv3x3_gelu_bwd: null pointer");
-  SEGMIF_REQUIRE(C % 8 == 0 && C > 0 && C <= 2048 && B > 0 && H > 0 && W > 0, "dwconv3x3_gelu_bwd: C=%d must be a multiple of 8, <= 2048", C);
-  const size_t smem = (size_t)10 * C * sizeof(float);
-  static bool cfg = false;
-  if (!cfg) {
-    cfg = true;
-    cudaError_t e = cudaFuncSetAttribute((const void*)dwconv3x3_gelu_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 10 * 2048 * 4);
-    if (e != cudaSuccess) { set_error("dwconv3x3_gelu_bwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return SEGMIF_ERR_CUDA; }
-  }
-  const int g = C >> 3;
-  const int rpi = g <= 256 ? 256 / g : 1;
-  SEGMIF_REQUIRE(g <= 256, "dwconv3x3_gelu_bwd: C=%d too wide for one block row", C);
-  dwconv3x3_gelu_bwd_kernel<<<grid_n((int64_t)B * H * W, rpi * 16), 256, smem, as_stream(stream)>>>((const bf16*)x, w9c, bias, (const bf16*)dy, (bf16*)dz,
-                                                                                                      B, H, W, C, dw9c, dbias);
+                                         int H, int W, int C, float* dw9c, float* dbias, float* workspace,
+                                         segmif_stream_t stream) {
+  SEGMIF_REQUIRE(x && w9c && bias && dy && dz && dw9c && dbias && workspace, "dwconv3x3_gelu_bwd: null pointer");
+  SEGMIF_REQUIRE(C % 8 == 0 && C > 0 && B > 0 && H > 0 && W > 0, "dwconv3x3_gelu_bwd: C=%d must be a multiple of 8", C);
+  const DwGeom g = dw_geom(B, H, W, C);
+  SEGMIF_REQUIRE(g.units <= 65535, "dwconv3x3_gelu_bwd: %d strips exceed the grid's y extent", g.units);
+  cudaStream_t st = as_stream(stream);
+  dwconv3x3_gelu_bwd_kernel<<<dim3(g.ctiles, g.units), 256, 0, st>>>((const bf16*)x, w9c, bias, (const bf16*)dy, (bf16*)dz, H, W, C,
+                                                                     workspace, g.tcg, g.S, g.strips_x, g.rchunks);
+  dwconv_part_reduce_kernel<<<(10 * C + 255) / 256, 256, 0, st>>>(workspace, g.units, C, dw9c, dbias);
   return check_launch("segmif_dwconv3x3_gelu_bwd");
 }
 

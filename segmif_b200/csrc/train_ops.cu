@@ -97,29 +97,33 @@ __global__ void __launch_bounds__(256) prelu_plane_bwd_kernel(const float* __res
   }
 }
 
+// grid = (row chunks, 256-channel tiles): every thread walks its chunk's rows with 16-byte loads, the block folds its
+// row lanes in shared memory and issues one global atomic per channel (<= 128 row chunks -> <= 128 adds per address)
 __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x, int ld, int64_t rows, int C,
                                                      float* __restrict__ out) {
   __shared__ float scol[256];
-  const int g = C >> 3, rpi = 256 / g;
+  const int c0 = blockIdx.y * 256;
+  const int ct = min(256, C - c0);
+  const int g = ct >> 3, rpi = 256 / g;
   const bool active = threadIdx.x < rpi * g;
   const int grp = threadIdx.x % g, rin = threadIdx.x / g;
   float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (active) {
     for (int64_t r = (int64_t)blockIdx.x * rpi + rin; r < rows; r += (int64_t)gridDim.x * rpi) {
       float v[8];
-      load8(x + r * ld + grp * 8, v);
+      load8(x + r * ld + c0 + grp * 8, v);
 #pragma unroll
       for (int i = 0; i < 8; ++i) cs[i] += v[i];
     }
   }
-  for (int i = threadIdx.x; i < C; i += 256) scol[i] = 0.f;
+  for (int i = threadIdx.x; i < ct; i += 256) scol[i] = 0.f;
   __syncthreads();
   if (active) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) atomicAdd(&scol[grp * 8 + i], cs[i]);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < C; i += 256) atomicAdd(out + i, scol[i]);
+  for (int i = threadIdx.x; i < ct; i += 256) atomicAdd(out + c0 + i, scol[i]);
 }
 
 __global__ void __launch_bounds__(256) add_bf16_kernel(const bf16* __restrict__ a, int lda, const bf16* __restrict__ b,
@@ -381,9 +385,11 @@ extern "C" int segmif_prelu_plane_bwd(const float* out, const float* dout, int64
 
 extern "C" int segmif_colsum(const void* x, int ld, int coff, int64_t rows, int C, float* out, segmif_stream_t stream) {
   SEGMIF_REQUIRE(x && out && rows > 0, "colsum: bad arguments");
-  SEGMIF_REQUIRE(C % 8 == 0 && C > 0 && C <= 256 && ld % 8 == 0 && coff % 8 == 0, "colsum: C, pitch and offset must be multiples of 8 (C <= 256)");
-  const int rpi = 256 / (C >> 3);
-  colsum_kernel<<<grid_for(rows, rpi * 8), 256, 0, as_stream(stream)>>>((const bf16*)x + coff, ld, rows, C, out);
+  SEGMIF_REQUIRE(C % 8 == 0 && C > 0 && ld % 8 == 0 && coff % 8 == 0, "colsum: C, pitch and offset must be multiples of 8");
+  const int ctiles = (C + 255) / 256;
+  const int rpi = 256 / (std::min(C, 256) >> 3);
+  const int chunks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(rows, (int64_t)rpi * 4), std::max(1, 296 / ctiles)));
+  colsum_kernel<<<dim3(std::min(chunks, 128), ctiles), 256, 0, as_stream(stream)>>>((const bf16*)x + coff, ld, rows, C, out);
   return check_launch("segmif_colsum");
 }
 

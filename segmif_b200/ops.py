@@ -712,8 +712,10 @@ def dwconv3x3(x, w9c, bias, B, H, W, flip=False):
 def dwconv3x3_gelu_bwd(x, w9c, bias, dy, B, H, W, dw9c, dbias):
     st = _prep(x, w9c, bias, dy, dw9c, dbias)
     dz = torch.empty_like(x)
-    _lib.call("segmif_dwconv3x3_gelu_bwd", _ptr(x), _ptr(w9c), _ptr(bias), _ptr(dy), _ptr(dz), B, H, W, x.shape[-1],
-              _ptr(dw9c), _ptr(dbias), st)
+    C = x.shape[-1]
+    ws = torch.empty((int(_lib.load().segmif_dwconv3x3_gelu_bwd_workspace(B, H, W, C)),), dtype=torch.float32, device=x.device)
+    _lib.call("segmif_dwconv3x3_gelu_bwd", _ptr(x), _ptr(w9c), _ptr(bias), _ptr(dy), _ptr(dz), B, H, W, C,
+              _ptr(dw9c), _ptr(dbias), _ptr(ws), st)
     return dz
 
 

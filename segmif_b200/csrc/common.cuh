@@ -123,4 +123,12 @@ __device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
   *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
 }
 
+// dwconv_tma.cu: TMA-staged depthwise 3x3 kernels (used whenever the channel count is a multiple of 64)
+bool dwconv_tma_ok(int B, int H, int W, int C);
+int dwconv_tma_fwd(const void* x, const float* w9c, const float* bias, void* y, int B, int H, int W, int C, int flip, int gelu,
+                   cudaStream_t st);
+int64_t dwconv_tma_bwd_workspace(int B, int H, int W, int C);
+int dwconv_tma_gelu_bwd(const void* x, const float* w9c, const float* bias, const void* dy, void* dz, int B, int H, int W, int C,
+                        float* dw9c, float* dbias, float* workspace, cudaStream_t st);
+
 }  // namespace segmif

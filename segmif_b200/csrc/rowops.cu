@@ -397,6 +397,7 @@ extern "C" int segmif_dwconv3x3_gelu_fwd(const void* x, const float* w9c, const 
   SEGMIF_REQUIRE(x && w9c && bias && y, "dwconv: null pointer");
   SEGMIF_REQUIRE(C % 8 == 0, "dwconv: C=%d must be a multiple of 8", C);
   if ((int64_t)B * H * W == 0) return SEGMIF_OK;
+  if (dwconv_tma_ok(B, H, W, C)) return dwconv_tma_fwd(x, w9c, bias, y, B, H, W, C, 0, 1, as_stream(stream));
   SEGMIF_REQUIRE((int64_t)B * H * W * C < (1ll << 32) && H <= 65535 && B <= 65535, "dwconv: tensor of %d x %d x %d x %d elements exceeds the 32-bit element index", B, H, W, C);
   dim3 grid((unsigned)ceil_div((int64_t)W * (C / 8), 256), (unsigned)H, (unsigned)B);
   dwconv3x3_gelu_kernel<<<grid, 256, 0, as_stream(stream)>>>((const bf16*)x, w9c, bias, (bf16*)y, H, W, C);

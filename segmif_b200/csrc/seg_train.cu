@@ -290,7 +290,24 @@ __device__ __forceinline__ void st_bf2(bf16* p, float a, float b) {
   *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
 }
 
-// y = dwconv3x3(x) (+ bias), pixel-major bf16, w fp32 [9][C]; flip != 0 uses the transposed taps (data gradient)
+// one image row of the thread's 3-column window (zeros outside the image)
+struct DwRow { float2 l, m, r; };
+__device__ __forceinline__ DwRow dw_load_row(const bf16* __restrict__ x, int b, int yy, int H, int W, int C, int col, int c,
+                                             bool hasl, bool hasr) {
+  DwRow o;
+  o.l = o.m = o.r = make_float2(0.f, 0.f);
+  if ((unsigned)yy < (unsigned)H) {
+    const bf16* row = x + ((size_t)(b * H + yy) * W + col) * C + c;
+    o.m = ld_bf2(row);
+    if (hasl) o.l = ld_bf2(row - C);
+    if (hasr) o.r = ld_bf2(row + C);
+  }
+  return o;
+}
+
+// y = dwconv3x3(x) (+ bias), pixel-major bf16, w fp32 [9][C]; flip != 0 uses the transposed taps (data gradient).
+// The three window rows live in registers and slide down; the row two below is requested before the current row's
+// arithmetic, so its L2 latency overlaps it (the first version reloaded all nine taps per row and was latency-bound).
 __global__ void __launch_bounds__(256) dwconv3x3_kernel(const bf16* __restrict__ x, const float* __restrict__ w9c,
                                                         const float* __restrict__ bias, bf16* __restrict__ y, int H, int W,
                                                         int C, int flip, int tcg, int S, int strips_x, int rchunks) {
@@ -301,23 +318,25 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(const bf16* __restrict__
   for (int t = 0; t < 9; ++t) wr[t] = *reinterpret_cast<const float2*>(w9c + (flip ? 8 - t : t) * C + d.c);
   const float2 bv = bias ? *reinterpret_cast<const float2*>(bias + d.c) : make_float2(0.f, 0.f);
   const bool hasl = d.col > 0, hasr = d.col + 1 < W;
+  DwRow ra = dw_load_row(x, d.b, d.row0 - 1, H, W, C, d.col, d.c, hasl, hasr);
+  DwRow rb = dw_load_row(x, d.b, d.row0, H, W, C, d.col, d.c, hasl, hasr);
+  DwRow rc = dw_load_row(x, d.b, d.row0 + 1, H, W, C, d.col, d.c, hasl, hasr);
   for (int r = d.row0; r < d.row1; ++r) {
+    const DwRow rn = dw_load_row(x, d.b, r + 2, H, W, C, d.col, d.c, hasl, hasr);
     float2 acc = bv;
-#pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-      const int yy = r + ky - 1;
-      if ((unsigned)yy >= (unsigned)H) continue;
-      const bf16* row = x + ((size_t)(d.b * H + yy) * W + d.col) * C + d.c;
-      if (hasl) { const float2 v = ld_bf2(row - C); acc.x = fmaf(wr[ky * 3].x, v.x, acc.x); acc.y = fmaf(wr[ky * 3].y, v.y, acc.y); }
-      { const float2 v = ld_bf2(row); acc.x = fmaf(wr[ky * 3 + 1].x, v.x, acc.x); acc.y = fmaf(wr[ky * 3 + 1].y, v.y, acc.y); }
-      if (hasr) { const float2 v = ld_bf2(row + C); acc.x = fmaf(wr[ky * 3 + 2].x, v.x, acc.x); acc.y = fmaf(wr[ky * 3 + 2].y, v.y, acc.y); }
-    }
+#define SEGMIF_DW_ROW(R, K)                                                                             \
+    acc.x = fmaf(wr[K].x, R.l.x, acc.x); acc.y = fmaf(wr[K].y, R.l.y, acc.y);                          \
+    acc.x = fmaf(wr[K + 1].x, R.m.x, acc.x); acc.y = fmaf(wr[K + 1].y, R.m.y, acc.y);                  \
+    acc.x = fmaf(wr[K + 2].x, R.r.x, acc.x); acc.y = fmaf(wr[K + 2].y, R.r.y, acc.y);
+    SEGMIF_DW_ROW(ra, 0) SEGMIF_DW_ROW(rb, 3) SEGMIF_DW_ROW(rc, 6)
+#undef SEGMIF_DW_ROW
     st_bf2(y + ((size_t)(d.b * H + r) * W + d.col) * C + d.c, acc.x, acc.y);
+    ra = rb; rb = rc; rc = rn;
   }
 }
 
 // z = dwconv(x) + b;  dz = dy * gelu'(z);  part[blockIdx.y][t][c] = sum dz * x(p + t) (t < 9), [9][c] = sum dz
-__global__ void __launch_bounds__(256) dwconv3x3_gelu_bwd_kernel(const bf16* __restrict__ x, const float* __restrict__ w9c,
+__global__ void __launch_bounds__(256, 3) dwconv3x3_gelu_bwd_kernel(const bf16* __restrict__ x, const float* __restrict__ w9c,
                                                                  const float* __restrict__ bias, const bf16* __restrict__ dy,
                                                                  bf16* __restrict__ dz, int H, int W, int C,
                                                                  float* __restrict__ part, int tcg, int S, int strips_x,
@@ -333,28 +352,33 @@ __global__ void __launch_bounds__(256) dwconv3x3_gelu_bwd_kernel(const bf16* __r
     for (int t = 0; t < 9; ++t) wr[t] = *reinterpret_cast<const float2*>(w9c + t * C + d.c);
     const float2 bv = *reinterpret_cast<const float2*>(bias + d.c);
     const bool hasl = d.col > 0, hasr = d.col + 1 < W;
-    for (int r = d.row0; r < d.row1; ++r) {
-      float2 xv[9];
+    DwRow ra = dw_load_row(x, d.b, d.row0 - 1, H, W, C, d.col, d.c, hasl, hasr);
+    DwRow rb = dw_load_row(x, d.b, d.row0, H, W, C, d.col, d.c, hasl, hasr);
+    DwRow rc = dw_load_row(x, d.b, d.row0 + 1, H, W, C, d.col, d.c, hasl, hasr);
+    size_t o = ((size_t)(d.b * H + d.row0) * W + d.col) * C + d.c;
+    const size_t ostep = (size_t)W * C;
+    float2 g = d.row0 < d.row1 ? ld_bf2(dy + o) : make_float2(0.f, 0.f);
+    for (int r = d.row0; r < d.row1; ++r, o += ostep) {
+      const DwRow rn = dw_load_row(x, d.b, r + 2, H, W, C, d.col, d.c, hasl, hasr);
+      const float2 gn = r + 1 < d.row1 ? ld_bf2(dy + o + ostep) : make_float2(0.f, 0.f);
       float2 z = bv;
-#pragma unroll
-      for (int ky = 0; ky < 3; ++ky) {
-        const int yy = r + ky - 1;
-        const bool rowok = (unsigned)yy < (unsigned)H;
-        const bf16* row = x + ((size_t)(d.b * H + (rowok ? yy : r)) * W + d.col) * C + d.c;
-        xv[ky * 3] = (rowok && hasl) ? ld_bf2(row - C) : make_float2(0.f, 0.f);
-        xv[ky * 3 + 1] = rowok ? ld_bf2(row) : make_float2(0.f, 0.f);
-        xv[ky * 3 + 2] = (rowok && hasr) ? ld_bf2(row + C) : make_float2(0.f, 0.f);
-      }
-#pragma unroll
-      for (int t = 0; t < 9; ++t) { z.x = fmaf(wr[t].x, xv[t].x, z.x); z.y = fmaf(wr[t].y, xv[t].y, z.y); }
-      const size_t o = ((size_t)(d.b * H + r) * W + d.col) * C + d.c;
-      float2 g = ld_bf2(dy + o);
+#define SEGMIF_DW_ROW(R, K)                                                                             \
+      z.x = fmaf(wr[K].x, R.l.x, z.x); z.y = fmaf(wr[K].y, R.l.y, z.y);                                \
+      z.x = fmaf(wr[K + 1].x, R.m.x, z.x); z.y = fmaf(wr[K + 1].y, R.m.y, z.y);                        \
+      z.x = fmaf(wr[K + 2].x, R.r.x, z.x); z.y = fmaf(wr[K + 2].y, R.r.y, z.y);
+      SEGMIF_DW_ROW(ra, 0) SEGMIF_DW_ROW(rb, 3) SEGMIF_DW_ROW(rc, 6)
+#undef SEGMIF_DW_ROW
       g.x *= 0.5f * (1.0f + erff(z.x * 0.70710678118654752440f)) + z.x * 0.39894228040143267794f * __expf(-0.5f * z.x * z.x);
       g.y *= 0.5f * (1.0f + erff(z.y * 0.70710678118654752440f)) + z.y * 0.39894228040143267794f * __expf(-0.5f * z.y * z.y);
       ab.x += g.x; ab.y += g.y;
-#pragma unroll
-      for (int t = 0; t < 9; ++t) { aw[t].x = fmaf(g.x, xv[t].x, aw[t].x); aw[t].y = fmaf(g.y, xv[t].y, aw[t].y); }
+#define SEGMIF_DW_ROW(R, K)                                                                             \
+      aw[K].x = fmaf(g.x, R.l.x, aw[K].x); aw[K].y = fmaf(g.y, R.l.y, aw[K].y);                        \
+      aw[K + 1].x = fmaf(g.x, R.m.x, aw[K + 1].x); aw[K + 1].y = fmaf(g.y, R.m.y, aw[K + 1].y);        \
+      aw[K + 2].x = fmaf(g.x, R.r.x, aw[K + 2].x); aw[K + 2].y = fmaf(g.y, R.r.y, aw[K + 2].y);
+      SEGMIF_DW_ROW(ra, 0) SEGMIF_DW_ROW(rb, 3) SEGMIF_DW_ROW(rc, 6)
+#undef SEGMIF_DW_ROW
       st_bf2(dz + o, g.x, g.y);
+      ra = rb; rb = rc; rc = rn; g = gn;
     }
   }
   const int tile_c = tcg * 2;
@@ -392,7 +416,7 @@ static DwGeom dw_geom(int B, int H, int W, int C) {
   g.strips_x = (W + g.S - 1) / g.S;
   g.ctiles = pairs / g.tcg;
   const int base = B * g.strips_x * g.ctiles;
-  g.rchunks = std::max(1, std::min(H / 4, (2 * 148 + base - 1) / base));      // >= two blocks per SM, >= 4 rows per walk
+  g.rchunks = std::max(1, std::min(H / 8, (6 * 148 + base - 1) / base));      // ~six blocks per SM, >= 8 rows per walk
   g.units = B * g.strips_x * g.rchunks;
   return g;
 }
@@ -539,6 +563,7 @@ extern "C" int segmif_channel_scale(const void* x, const float* scale, void* y, 
 extern "C" int segmif_dwconv3x3(const void* x, const float* w9c, const float* bias, void* y, int B, int H, int W, int C,
                                 int flip, segmif_stream_t stream) {
   SEGMIF_REQUIRE(x && w9c && y && C % 8 == 0 && B > 0 && H > 0 && W > 0, "dwconv3x3: bad arguments");
+  if (dwconv_tma_ok(B, H, W, C)) return dwconv_tma_fwd(x, w9c, bias, y, B, H, W, C, flip, 0, as_stream(stream));
   const DwGeom g = dw_geom(B, H, W, C);
   SEGMIF_REQUIRE(g.units <= 65535, "dwconv3x3: %d strips exceed the grid's y extent", g.units);
   dwconv3x3_kernel<<<dim3(g.ctiles, g.units), 256, 0, as_stream(stream)>>>((const bf16*)x, w9c, bias, (bf16*)y, H, W, C, flip, g.tcg,
@@ -548,6 +573,7 @@ extern "C" int segmif_dwconv3x3(const void* x, const float* w9c, const float* bi
 
 extern "C" int64_t segmif_dwconv3x3_gelu_bwd_workspace(int B, int H, int W, int C) {
   if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || C % 8) return 0;
+  if (dwconv_tma_ok(B, H, W, C)) return dwconv_tma_bwd_workspace(B, H, W, C);
   return (int64_t)dw_geom(B, H, W, C).units * 10 * C;
 }
 
@@ -556,6 +582,7 @@ extern "C" int segmif_dwconv3x3_gelu_bwd(const void* x, const float* w9c, const 
                                          segmif_stream_t stream) {
   SEGMIF_REQUIRE(x && w9c && bias && dy && dz && dw9c && dbias && workspace, "dwconv3x3_gelu_bwd: null pointer");
   SEGMIF_REQUIRE(C % 8 == 0 && C > 0 && B > 0 && H > 0 && W > 0, "dwconv3x3_gelu_bwd: C=%d must be a multiple of 8", C);
+  if (dwconv_tma_ok(B, H, W, C)) return dwconv_tma_gelu_bwd(x, w9c, bias, dy, dz, B, H, W, C, dw9c, dbias, workspace, as_stream(stream));
   const DwGeom g = dw_geom(B, H, W, C);
   SEGMIF_REQUIRE(g.units <= 65535, "dwconv3x3_gelu_bwd: %d strips exceed the grid's y extent", g.units);
   cudaStream_t st = as_stream(stream);

@@ -741,3 +741,113 @@ def fusion_composite_step():
     res.append(result("composite_step_loss", abs(float(l) - float(l_ref)) / abs(float(l_ref)), 3e-2, note=f"{float(l):.5f} vs {float(l_ref):.5f}"))
     res.append(result("composite_step_updates_params", 0.0 if float((tr.flat.param - before).abs().max()) > 0 else 1.0, 0.0))
     return res
+
+
+@check
+def dropin_train_loop_bodies():
+    """The reference's own loop bodies, statement for statement, on the mirror modules -- what `python -m
+    segmif_b200.dropin train.py` executes: train_seg (train.py:207-226: model(mask) -> F.interpolate -> CrossEntropyLoss ->
+    backward -> PolyWarmupAdamW_seg over WeTr.get_param_groups()) and train_fusion rounds >= 2 (train.py:350-381:
+    forward_fusion under no_grad, model2(...), Fusionloss_grad3, torch-op YCrCb2RGB, model._loss, .item()-weighted sum,
+    backward, PolyWarmupAdamW).  torch's own ops (interpolate, CE, the colour matrix product, the optimizers) run beside
+    the segmif_b200 autograd nodes.  Losses of the first step are compared with the oracle; two more steps must run and
+    move the parameters."""
+    from segmif_b200.core import Fusionloss_grad3
+    from segmif_b200.core.model_fusion import Fusion_Network3_ac, Network3, RGB2YCrCb
+    from segmif_b200.utils.optimizer import PolyWarmupAdamW, PolyWarmupAdamW_seg
+    res = []
+    B, H, W = 2, 64, 96
+    inp = synth.synth_inputs(B, H, W, seed=7)
+    dev = torch.device(DEV)
+
+    def no_drop(net):
+        net.denoise_net.decoder.dropout.p = 0.0
+        for m in net.modules():
+            if hasattr(m, "drop_prob"):
+                m.drop_prob = 0.0
+        return net
+
+    # ---------------- train_seg
+    seg0 = synth.load_synthetic(Network3("mit_b1", 9, 256, None), 0)
+    ssd = {k: v.clone() for k, v in seg0.state_dict().items()}
+    with torch.no_grad():
+        ref_seg_loss = float(O.seg_cross_entropy(O.network3_forward(inp["mask"], ssd, "mit_b1", train_bn=True), inp["labels"]))
+    criterion_seg = torch.nn.CrossEntropyLoss(ignore_index=255).to(dev)
+    model = no_drop(copy.deepcopy(seg0)).cuda()
+    param_groups = model.denoise_net.get_param_groups()
+    model = model.train()
+    model.to(dev)
+    optimizer = PolyWarmupAdamW_seg(
+        params=[{"params": param_groups[0], "lr": 6e-5, "weight_decay": 0.01}, {"params": param_groups[1], "lr": 6e-5, "weight_decay": 0.0},
+                {"params": param_groups[2], "lr": 6e-4, "weight_decay": 0.01}],
+        lr=6e-5, weight_decay=0.01, betas=[0.9, 0.999], iter_curr=0, warmup_iter=2, max_iter=100, warmup_ratio=1e-6, power=1.0)
+    inputs_mask, labels = inp["mask"].to(dev, non_blocking=True), inp["labels"].to(dev, non_blocking=True)
+    before = model.denoise_net.decoder.linear_pred.weight.detach().clone()
+    losses = []
+    for n_iter in range(3):
+        _, __, segmap = model(inputs_mask)
+        outputs = F.interpolate(segmap, size=labels.shape[1:], mode='bilinear', align_corners=False)
+        seg_loss = criterion_seg(outputs, labels.type(torch.long))
+        optimizer.zero_grad()
+        seg_loss.backward()
+        optimizer.step()
+        losses.append(seg_loss.item())
+    res.append(result("dropin_train_seg_first_loss", abs(losses[0] - ref_seg_loss) / abs(ref_seg_loss), 2e-2, note=f"{losses}"))
+    res.append(result("dropin_train_seg_finite_and_moving", 0.0 if all(map(lambda v: v == v and abs(v) < 1e4, losses))
+                      and float((model.denoise_net.decoder.linear_pred.weight.detach() - before).abs().max()) > 0 else 1.0, 0.0))
+    res.append(result("dropin_train_seg_classifier_grad_none", 0.0 if model.denoise_net.classifier.weight.grad is None else 1.0, 0.0))
+
+    # ---------------- train_fusion, iter_ = 2
+    def YCrCb2RGB(input_im):                                   # train.py:243-264 with .cuda() -> the input's device
+        im_flat = input_im.transpose(1, 3).transpose(1, 2).reshape(-1, 3)
+        mat = torch.tensor([[1.0, 1.0, 1.0], [1.403, -0.714, 0.0], [0.0, -0.344, 1.773]], device=input_im.device)
+        bias = torch.tensor([0.0 / 255, -0.5, -0.5], device=input_im.device)
+        temp = (im_flat + bias).mm(mat)
+        return temp.reshape(list(input_im.size())[0], list(input_im.size())[2], list(input_im.size())[3], 3).transpose(1, 3).transpose(2, 3)
+
+    iter_ = 2
+    fus0 = synth.load_synthetic(Fusion_Network3_ac(), 0)
+    fsd = {k: v.clone() for k, v in fus0.state_dict().items()}
+    with torch.no_grad():
+        vis_ref = O.rgb2ycrcb(inp["vis"])
+        o0, o1 = O.mit_forward_fusion(inp["mask"], O._sub(ssd, "denoise_net.encoder"), "mit_b1")
+        f_ref = O.fusion_network3_ac(inp["ir"][:, 0:1], vis_ref, o0, o1, fsd)
+        l1_ref = float(O.fusionloss_grad3(inp["ir"], vis_ref, f_ref, inp["mask"]))
+        l2_ref = float(O.seg_cross_entropy(O.network3_forward(O.recompose_rgb(f_ref, vis_ref, clamp=False), ssd, "mit_b1", train_bn=True),
+                                           inp["labels"]))
+    model = no_drop(copy.deepcopy(seg0)).cuda()                 # train mode, as train.py leaves it
+    model2 = copy.deepcopy(fus0)
+    model.to(dev)
+    model2.to(dev)
+    optimizer = PolyWarmupAdamW(params=[{"params": model2.parameters(), "lr": 3e-4 / iter_, "weight_decay": 0.01}], lr=(3e-4) / iter_,
+                                weight_decay=0.01, betas=[0.9, 0.999], warmup_iter=(3e-5) / iter_, max_iter=100, warmup_ratio=1e-6, power=1.0)
+    criterion_seg = torch.nn.CrossEntropyLoss(ignore_index=255)
+    w_before = model2.conv2.weight.detach().clone()
+    got = []
+    for n_iter in range(3):
+        inputs_ir = inp["ir"].to(dev, non_blocking=True)
+        inputs_vis = inp["vis"].to(dev, non_blocking=True)
+        inputs_mask = inp["mask"].to(dev, non_blocking=True)
+        labels = inp["labels"].to(dev, non_blocking=True)
+        inputs_ir = inputs_ir[:, 0:1, :, :]
+        inputs_vis = RGB2YCrCb(inputs_vis)
+        with torch.no_grad():
+            out0, out1 = model.denoise_net.encoder.forward_fusion(inputs_mask)
+        fusion = model2(inputs_ir, inputs_vis, out0, out1)
+        optimizer.zero_grad()
+        fusion_loss = Fusionloss_grad3()
+        fused_ycbcr = inputs_vis.clone()
+        fused_ycbcr[:, 0:1, :, :] = fusion
+        fused_rgb = YCrCb2RGB(fused_ycbcr)
+        loss1 = fusion_loss(inputs_ir, inputs_vis, fusion, inputs_mask)
+        loss2 = model._loss(fused_rgb, labels, criterion_seg)
+        seg_loss = (0.4 / iter_) * loss1 + 0.8 * loss2
+        seg_loss.backward()
+        optimizer.step()
+        got.append((loss1.item(), loss2.item()))
+    res.append(result("dropin_train_fusion_loss1", abs(got[0][0] - l1_ref) / abs(l1_ref), 3e-2, note=f"{got[0][0]:.5f} vs {l1_ref:.5f}"))
+    res.append(result("dropin_train_fusion_loss2_ce", abs(got[0][1] - l2_ref) / abs(l2_ref), 3e-2, note=f"{got[0][1]:.5f} vs {l2_ref:.5f}"))
+    res.append(result("dropin_train_fusion_finite_and_moving", 0.0 if all(v == v for pair in got for v in pair)
+                      and float((model2.conv2.weight.detach() - w_before).abs().max()) > 0 else 1.0, 0.0))
+    res.append(result("dropin_train_fusion_ffm2_grad_none", 0.0 if all(p.grad is None for k, p in model2.named_parameters() if k.startswith("ffm2.")) else 1.0, 0.0))
+    return res

@@ -321,6 +321,104 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_kernel(WgradArgs a) {
   }
 }
 
+// ---- linear layers (NT = 1):  dW[co][ci] = sum_p dY[p][co] * X[p][ci]  as a 128 x 128 x (pixels) tile per block ----------
+// The generic kernel above gives each block a 32 x 64 output tile, so for a linear layer it refills 24 KB of shared
+// memory per 16 MMAs and re-reads X once per 32 output channels: it ran at 25-60 TFLOP/s, bound by the fill traffic.
+// Here a block owns 128 output x 128 input channels, eight warps of 64 x 32 each (16 MMAs per six ldmatrix), and walks its
+// contiguous pixel range in 64-pixel steps through a 3-stage cp.async ring.  Both operands are pixel-major, i.e. K-outer
+// in shared memory, so both fragment loads are ldmatrix.trans; the 16-byte chunks of each 256-byte pixel row are XOR-
+// swizzled with the pixel index so that the eight rows of an 8x8 matrix fall into distinct bank groups.
+constexpr int kWlBM = 128, kWlBN = 128, kWlBK = 64, kWlStages = 3;
+
+__global__ void __launch_bounds__(256, 2) wgrad_lin_kernel(WgradArgs a, int64_t pix_per_chunk) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  constexpr int ROW = 256;                                   // bytes per pixel row of either operand tile (128 channels)
+  constexpr int OP_BYTES = kWlBK * ROW;                      // 16 KB
+  constexpr int STAGE = 2 * OP_BYTES;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 2, wn = warp & 3;                   // 2 x 4 warps: 64 co x 32 ci each
+  const int ci0 = blockIdx.y * kWlBN, co0 = blockIdx.z * kWlBM;
+  const int64_t p_begin = (int64_t)blockIdx.x * pix_per_chunk;
+  const int64_t p_end = min(a.P, p_begin + pix_per_chunk);
+  const int nsteps = p_end > p_begin ? (int)((p_end - p_begin + kWlBK - 1) / kWlBK) : 0;
+
+  float acc[4][4][4];
+#pragma unroll
+  for (int m = 0; m < 4; ++m)
+#pragma unroll
+    for (int n = 0; n < 4; ++n)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[m][n][j] = 0.f;
+
+  auto issue = [&](int step) {
+    if (step < nsteps) {
+      uint8_t* sY = smem_raw + (step % kWlStages) * STAGE;
+      uint8_t* sX = sY + OP_BYTES;
+      const int64_t p0 = p_begin + (int64_t)step * kWlBK;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {                          // 64 px x 16 chunks per operand, 256 threads
+        const int i = tid + k * 256;
+        const int p = i >> 4, chunk = i & 15;
+        const int64_t pix = p0 + p;
+        const bool okp = pix < p_end;
+        const bool oky = okp && co0 + chunk * 8 < a.Cout;
+        const bool okx = okp && ci0 + chunk * 8 < a.Cin;
+        const uint32_t off = (uint32_t)(p * ROW + ((chunk ^ (p & 7)) << 4));
+        cp_async16_cg(smem_u32(sY + off), oky ? a.dy + pix * a.ldy + co0 + chunk * 8 : a.dy, oky ? 16 : 0);
+        cp_async16_cg(smem_u32(sX + off), okx ? a.x + pix * a.ldx + ci0 + chunk * 8 : a.x, okx ? 16 : 0);
+      }
+    }
+    cp_async_commit();
+  };
+
+  issue(0);
+  issue(1);
+  for (int step = 0; step < nsteps; ++step) {
+    issue(step + 2);
+    cp_async_wait<2>();
+    __syncthreads();
+    const uint8_t* sY = smem_raw + (step % kWlStages) * STAGE;
+    const uint8_t* sX = sY + OP_BYTES;
+#pragma unroll
+    for (int kk = 0; kk < kWlBK / 16; ++kk) {
+      uint32_t af[4][4], bfr[2][4];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int p = kk * 16 + (lane & 7) + ((lane >> 4) << 3);
+        const int chunk = wm * 8 + m * 2 + ((lane >> 3) & 1);
+        ldmatrix_x4_trans(af[m], smem_u32(sY + p * ROW + ((chunk ^ (p & 7)) << 4)));
+      }
+#pragma unroll
+      for (int n2 = 0; n2 < 2; ++n2) {
+        const int p = kk * 16 + (lane & 15);
+        const int chunk = wn * 4 + n2 * 2 + (lane >> 4);
+        ldmatrix_x4_trans(bfr[n2], smem_u32(sX + p * ROW + ((chunk ^ (p & 7)) << 4)));
+      }
+#pragma unroll
+      for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int n = 0; n < 4; ++n) mma_bf16_16816(acc[m][n], af[m], bfr[n >> 1][(n & 1) * 2], bfr[n >> 1][(n & 1) * 2 + 1]);
+    }
+    __syncthreads();                                          // the stage is refilled two iterations later
+  }
+  cp_async_wait<0>();
+  // partial[chunk][co][ci]
+  const int g = lane >> 2, tq = lane & 3;
+  float* out = a.partials + (int64_t)blockIdx.x * a.Cout * a.Cin;
+#pragma unroll
+  for (int m = 0; m < 4; ++m)
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      const int ci = ci0 + wn * 32 + n * 8 + tq * 2;
+      if (ci >= a.Cin) continue;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int co = co0 + wm * 64 + m * 16 + g + half * 8;
+        if (co < a.Cout) *reinterpret_cast<float2*>(out + (int64_t)co * a.Cin + ci) = make_float2(acc[m][n][half * 2], acc[m][n][half * 2 + 1]);
+      }
+    }
+}
+
 // grad[co*s_co + tap*s_tap + ci*s_ci] += sum_chunk partial[chunk][co][tap][ci]   (fixed order)
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partials, int nchunk, int Cout, int NT,
                                                            int Cin, float* __restrict__ grad, int64_t s_co, int64_t s_tap,
@@ -470,9 +568,21 @@ extern "C" int segmif_wgrad(const void* dy, int ldy, int coffy, const void* x, i
     cudaError_t e = cudaFuncSetAttribute((const void*)wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
     if (e != cudaSuccess) { set_error("wgrad: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return SEGMIF_ERR_CUDA; }
   }
-  dim3 grid(nchunk, (Cin + 63) / 64, Cout / 32);
-  if (taps == 9) wgrad_kernel<9><<<grid, kWgThreads, smem, st>>>(a);
-  else wgrad_kernel<1><<<grid, kWgThreads, smem, st>>>(a);
+  if (taps == 1) {
+    static bool cfgl = false;
+    constexpr int smem_lin = kWlStages * 2 * kWlBK * 256;
+    if (!cfgl) {
+      cfgl = true;
+      cudaError_t e = cudaFuncSetAttribute((const void*)wgrad_lin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_lin);
+      if (e != cudaSuccess) { set_error("wgrad: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return SEGMIF_ERR_CUDA; }
+    }
+    const int64_t ppc = ceil_div(ceil_div(P, (int64_t)nchunk), (int64_t)kWlBK) * kWlBK;      // whole 64-pixel steps per chunk
+    dim3 grid(nchunk, (Cin + kWlBN - 1) / kWlBN, (Cout + kWlBM - 1) / kWlBM);
+    wgrad_lin_kernel<<<grid, 256, smem_lin, st>>>(a, ppc);
+  } else {
+    dim3 grid(nchunk, (Cin + 63) / 64, Cout / 32);
+    wgrad_kernel<9><<<grid, kWgThreads, smem, st>>>(a);
+  }
   int rc = check_launch("segmif_wgrad");
   if (rc) return rc;
   const int64_t n = (int64_t)Cout * taps * Cin;

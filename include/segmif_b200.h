@@ -299,6 +299,7 @@ int segmif_layernorm_bwd(const void* x, int x_dtype, const void* dy, int dy_dtyp
  *   grad[co*s_co + tap*s_tap + ci*s_ci] += sum_p dy[p][coffy+co] * x[p + tap][coffx+ci]      co < co_take, ci < ci_take
  * dy bf16 [P, ldy], x bf16 [B,H,W,ldx]; Cout % 32 == 0, Cin % 8 == 0; workspace: segmif_wgrad_workspace_bytes().   */
 size_t segmif_wgrad_workspace_bytes(int nchunk, int Cout, int taps, int Cin);
+int segmif_wgrad_chunks(int B, int H, int W, int64_t P, int Cin, int Cout, int taps, int dil);   /* nchunk to call segmif_wgrad with */
 int segmif_wgrad(const void* dy, int ldy, int coffy, const void* x, int ldx, int coffx, int B, int H, int W, int64_t P,
                  int Cin, int Cout, int taps, int dil, float* workspace, int nchunk, float* grad, int64_t s_co,
                  int64_t s_tap, int64_t s_ci, int co_take, int ci_take, segmif_stream_t stream);

@@ -131,4 +131,10 @@ int64_t dwconv_tma_bwd_workspace(int B, int H, int W, int C);
 int dwconv_tma_gelu_bwd(const void* x, const float* w9c, const float* bias, const void* dy, void* dz, int B, int H, int W, int C,
                         float* dw9c, float* dbias, float* workspace, cudaStream_t st);
 
+// wgrad_tc.cu: 3x3 weight gradients on tcgen05 (MN-major operands, accumulators resident in TMEM)
+bool wgrad_tc_ok(int B, int H, int W, int Cin, int Cout, int taps, int dil, int ldy, int ldx);
+int wgrad_tc_chunks(int B, int H, int W, int Cin, int Cout);
+int wgrad_tc(const void* dy, int ldy, const void* x, int ldx, int B, int H, int W, int Cin, int Cout, int dil, float* partials,
+             int nchunk, cudaStream_t st);
+
 }  // namespace segmif

@@ -11,6 +11,7 @@
 //   adamw_step     fused AdamW over a flat fp32 parameter / gradient / moment buffer (utils/optimizer.py:16-33)
 // Activations and their gradients are bf16 pixel-major [pixels, ld] slices (ld = channel pitch, coff = offset).
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -539,6 +540,23 @@ extern "C" size_t segmif_wgrad_workspace_bytes(int nchunk, int Cout, int taps, i
   return (size_t)nchunk * Cout * taps * Cin * sizeof(float);
 }
 
+static bool wgrad_use_tc() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SEGMIF_WGRAD_TC"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
+/* number of pixel chunks (= per-block partial buffers) segmif_wgrad should be called with for this problem */
+extern "C" int segmif_wgrad_chunks(int B, int H, int W, int64_t P, int Cin, int Cout, int taps, int dil) {
+  if (taps == 1) {
+    const int64_t tiles = (int64_t)((Cin + kWlBN - 1) / kWlBN) * ((Cout + kWlBM - 1) / kWlBM);
+    return (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(P, (int64_t)kWlBK), (2 * 148) / std::max<int64_t>(1, tiles)));
+  }
+  if (wgrad_use_tc() && wgrad_tc_ok(B, H, W, Cin, Cout, taps, dil, 8, 8)) return wgrad_tc_chunks(B, H, W, Cin, Cout);
+  const int64_t ntiles = (int64_t)B * ((H + kWgTH - 1) / kWgTH) * ((W + kWgTW - 1) / kWgTW);
+  return (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, (2 * 148) / std::max(1, ((Cin + 63) / 64) * (Cout / 32))));
+}
+
 extern "C" int segmif_wgrad(const void* dy, int ldy, int coffy, const void* x, int ldx, int coffx, int B, int H, int W,
                             int64_t P, int Cin, int Cout, int taps, int dil, float* workspace, int nchunk, float* grad,
                             int64_t s_co, int64_t s_tap, int64_t s_ci, int co_take, int ci_take, segmif_stream_t stream) {
@@ -579,6 +597,9 @@ extern "C" int segmif_wgrad(const void* dy, int ldy, int coffy, const void* x, i
     const int64_t ppc = ceil_div(ceil_div(P, (int64_t)nchunk), (int64_t)kWlBK) * kWlBK;      // whole 64-pixel steps per chunk
     dim3 grid(nchunk, (Cin + kWlBN - 1) / kWlBN, (Cout + kWlBM - 1) / kWlBM);
     wgrad_lin_kernel<<<grid, 256, smem_lin, st>>>(a, ppc);
+  } else if (wgrad_use_tc() && wgrad_tc_ok(B, H, W, Cin, Cout, taps, dil, ldy, ldx)) {
+    int rc = wgrad_tc(a.dy, ldy, a.x, ldx, B, H, W, Cin, Cout, dil, workspace, nchunk, st);
+    if (rc) return rc;
   } else {
     dim3 grid(nchunk, (Cin + 63) / 64, Cout / 32);
     wgrad_kernel<9><<<grid, kWgThreads, smem, st>>>(a);

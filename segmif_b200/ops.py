@@ -569,12 +569,9 @@ def wgrad(dy, ldy, coffy, x, ldx, coffx, *, B, H, W, Cin, Cout, taps, dil, grad,
         P = B * H * W if P is None else P
         B, W = 1, 16
         H = (P + 15) // 16
-        tiles = ((Cin + 127) // 128) * ((Cout + 127) // 128)             # wgrad_lin_kernel: 128 x 128 channel tiles
-        nchunk = max(1, min((P + 63) // 64, (2 * _sm_count(dy.device)) // tiles))
     else:
         P = B * H * W
-        ntiles = B * ((H + 7) // 8) * ((W + 15) // 16)
-        nchunk = max(1, min(ntiles, (2 * _sm_count(dy.device)) // (((Cin + 63) // 64) * (Cout // 32))))
+    nchunk = int(_lib.load().segmif_wgrad_chunks(B, H, W, P, Cin, Cout, taps, dil))
     ws = torch.empty((nchunk * Cout * taps * Cin,), dtype=torch.float32, device=dy.device)
     _lib.call("segmif_wgrad", _ptr(dy), ldy, coffy, _ptr(x), ldx, coffx, B, H, W, P, Cin, Cout, taps, dil, _ptr(ws), nchunk,
               _ptr(grad), s_co, s_tap, s_ci, Cout if co_take is None else co_take, Cin if ci_take is None else ci_take, st)

@@ -156,6 +156,18 @@ int segmif_bilinear_nhwc_fwd(const void* src, int src_dtype, int B, int h, int w
 int segmif_upsample_argmax_fwd(const float* logits, int B, int h, int w, int nc, int64_t* labels, int H, int W,
                                segmif_stream_t stream);
 
+/* ---- validation / post-processing on the device ------------------------------------------
+ * segmif_confusion_matrix: conf[t*nc + p] += #{i : truth[i] == t, pred[i] == p}, pairs with a value outside [0, nc) dropped
+ *   -- sklearn.metrics.confusion_matrix(label, prediction, labels=[0..nc-1]) accumulated as `conf_total += conf`
+ *   (test_segmentation.py:173-177); conf is int64 [nc, nc] on the device, rows = ground truth.
+ * segmif_fused_to_uint8: val_performance.py:447-460 -- clamp(rgb, 0, 1) -> uint8(255 x) -> NHWC -> batch-wide min-max
+ *   renormalisation -> uint8(255 y), numpy's truncating casts and double-precision division reproduced exactly.
+ *   rgb fp32 NCHW [B,3,H,W] -> out uint8 [B,H,W,3]; minmax: 2 uint32 of device workspace (receives the min and max). */
+int segmif_confusion_matrix(const int64_t* truth, const int64_t* pred, int64_t n, int num_classes, int64_t* conf,
+                            segmif_stream_t stream);
+int segmif_fused_to_uint8(const float* rgb, unsigned char* out_nhwc, unsigned int* minmax, int B, int64_t HW,
+                          segmif_stream_t stream);
+
 /* ---- layout converters at the module boundary (NCHW fp32 is the reference's interface layout) -------- */
 int segmif_nhwc_to_nchw(const void* src, int src_dtype, int ld_src, int src_coff, float* dst, int B, int HW, int C,
                         segmif_stream_t stream);

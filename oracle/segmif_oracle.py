@@ -402,3 +402,40 @@ def inference_pipeline(ir, vis_rgb, mask, seg_sd, fusion_sd, backbone, ycrcb_inp
     logits = network3_forward(rgb, seg_sd, backbone)
     labels = seg_labels(logits, ir.shape[2:])
     return dict(out0=out0, out1=out1, fused=fused, rgb=rgb, logits=logits, labels=labels)
+
+
+# ----------------------------------------------------------------------------- validation
+
+
+def confusion_matrix(labels, prediction, num_classes=9):
+    """test_segmentation.py:173-176 -- sklearn.metrics.confusion_matrix(y_true, y_pred, labels=[0..nc-1]): rows = truth,
+    columns = prediction; pairs with a value outside `labels` (the ignore index 255) are not counted."""
+    t, p = labels.reshape(-1).long(), prediction.reshape(-1).long()
+    ok = (t >= 0) & (t < num_classes) & (p >= 0) & (p < num_classes)
+    idx = t[ok] * num_classes + p[ok]
+    return torch.bincount(idx, minlength=num_classes * num_classes).reshape(num_classes, num_classes)
+
+
+def compute_results(conf_total):
+    """util/util.py:31-55 (consider_unlabeled = True): precision = TP / column sum, recall = TP / row sum,
+    IoU = TP / (row + column - TP); NaN where the denominator is zero."""
+    import numpy as np
+    conf = np.asarray(conf_total, dtype=np.float64)
+    n = conf.shape[0]
+    prec, rec, iou = np.zeros(n), np.zeros(n), np.zeros(n)
+    for c in range(n):
+        col, row = conf[:, c].sum(), conf[c, :].sum()
+        prec[c] = np.nan if col == 0 else conf[c, c] / col
+        rec[c] = np.nan if row == 0 else conf[c, c] / row
+        iou[c] = np.nan if row + col - conf[c, c] == 0 else conf[c, c] / (row + col - conf[c, c])
+    return prec, rec, iou
+
+
+def fused_to_uint8(rgb):
+    """val_performance.py:447-460 -- clamp to [0,1], np.uint8(255.0 * x), NCHW -> NHWC, (u - min) / (max - min) over the
+    whole batch, np.uint8(255.0 * y); numpy's own dtype rules (uint8 difference, float64 quotient, truncating casts)."""
+    import numpy as np
+    x = rgb.clamp(0.0, 1.0).cpu().numpy()
+    u = np.uint8(255.0 * x).transpose((0, 2, 3, 1))
+    y = (u - np.min(u)) / (np.max(u) - np.min(u))
+    return np.uint8(255.0 * y)

@@ -125,6 +125,8 @@ SIGNATURES = {
     "segmif_dwconv3x3": [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P],
     "segmif_dwconv3x3_gelu_bwd": [P, P, P, P, P, c_int, c_int, c_int, c_int, P, P, P, P],
     "segmif_dwconv3x3_gelu_bwd_workspace": [c_int, c_int, c_int, c_int],
+    "segmif_confusion_matrix": [P, P, c_int64, c_int, P, P],
+    "segmif_fused_to_uint8": [P, P, P, c_int, c_int64, P],
     "segmif_wgrad_chunks": [c_int, c_int, c_int, c_int64, c_int, c_int, c_int, c_int],
     "segmif_col2im": [P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P],
     "segmif_channel_affine_nchw": [P, P, P, P, c_int, c_int, c_int64, P],

@@ -487,8 +487,10 @@ extern "C" int segmif_colsum(const void* x, int ld, int coff, int64_t rows, int 
   SEGMIF_REQUIRE(C % 8 == 0 && C > 0 && ld % 8 == 0 && coff % 8 == 0, "colsum: C, pitch and offset must be multiples of 8");
   const int ctiles = (C + 255) / 256;
   const int rpi = 256 / (std::min(C, 256) >> 3);
-  const int chunks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(rows, (int64_t)rpi * 4), std::max(1, 296 / ctiles)));
-  colsum_kernel<<<dim3(std::min(chunks, 128), ctiles), 256, 0, as_stream(stream)>>>((const bf16*)x + coff, ld, rows, C, out);
+  // ~16 rows per thread, at most 8 blocks per SM: big tensors (the fusion net's full-resolution maps) need the whole GPU,
+  // small ones few atomics per address
+  const int chunks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(rows, (int64_t)rpi * 16), std::max(1, 148 * 8 / ctiles)));
+  colsum_kernel<<<dim3(chunks, ctiles), 256, 0, as_stream(stream)>>>((const bf16*)x + coff, ld, rows, C, out);
   return check_launch("segmif_colsum");
 }
 

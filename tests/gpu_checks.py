@@ -583,3 +583,36 @@ def run_all(verbose=True):
         out.extend(rs)
         torch.cuda.synchronize()
     return out
+
+
+# ----------------------------------------------------------------------------------------- validation on the device
+@check
+def validation_kernels():
+    """SURVEY.md 8(f) row 2, bit-exact integer / byte work: confusion matrix vs the reference-generated fixture and vs
+    the oracle at full size (8 x 480 x 640 labels incl. the ignore index), accumulation, and the uint8 post-processing."""
+    from segmif_b200 import metrics
+    res = []
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "validation.npz"))
+    conf = metrics.confusion_matrix(torch.from_numpy(g["label"]).to(DEV), torch.from_numpy(g["pred"]).to(DEV), 9)
+    res.append(result("confusion_matrix_vs_reference_fixture", float((conf.cpu().numpy() != g["conf"]).sum()), 0.0))
+    p, r, iou = metrics.compute_results(conf)
+    res.append(result("miou_vs_reference_fixture", float(np.nanmax(np.abs(iou - g["iou"]))), 1e-15))
+    inp = synth.synth_inputs(8, 480, 640, seed=3)
+    gen = torch.Generator().manual_seed(5)
+    pred = torch.where(torch.rand(inp["labels"].shape, generator=gen) < 0.6, inp["labels"].clamp(max=8), torch.randint(0, 9, inp["labels"].shape, generator=gen))
+    ref = O.confusion_matrix(inp["labels"], pred)
+    acc = torch.zeros((9, 9), dtype=torch.int64, device=DEV)
+    for _ in range(2):                                             # conf_total += conf
+        metrics.confusion_matrix(inp["labels"].to(DEV), pred.to(DEV), 9, out=acc)
+    res.append(result("confusion_matrix_full_size_accumulated", float((acc.cpu() != 2 * ref).sum()), 0.0))
+    u8 = metrics.fused_to_uint8(torch.from_numpy(g["fusion_image"]).to(DEV))
+    res.append(result("fused_to_uint8_vs_reference_fixture", float((u8.cpu().numpy() != g["fused_uint8"]).sum()), 0.0))
+    big = torch.rand(4, 3, 480, 640, generator=gen) * 1.3 - 0.1
+    res.append(result("fused_to_uint8_full_size", float((metrics.fused_to_uint8(big.to(DEV)).cpu().numpy() != O.fused_to_uint8(big)).sum()), 0.0))
+    # end to end: SegmentationMetrics over the network's own predictions == oracle confusion of the same predictions
+    seg, fus, _ = models()
+    m = metrics.SegmentationMetrics(9, DEV)
+    small = synth.synth_inputs(2, 64, 96, seed=9)
+    pr = m.update(seg, small["mask"].to(DEV), small["labels"].to(DEV))
+    res.append(result("segmentation_metrics_update", float((m.conf_total.cpu() != O.confusion_matrix(small["labels"], pr.cpu())).sum()), 0.0))
+    return res

@@ -99,6 +99,9 @@ typedef struct {
   int act;
   int res_dtype, ld_res, res_coff;
   int dst_dtype, ld_dst, dst_coff;
+  int weight_kn;            /* 0: weight bf16 [N, K] (nn.Linear's own layout: y = x W^T).  1: weight bf16 [K, N] -- the SAME
+                               buffer read as the operand of the data gradient dX = dY W (MN-major tcgen05 B operand), so
+                               the backward needs no transposed copy of the weights; requires N % 64 == 0               */
 } segmif_linear_params;
 int segmif_linear_tc_fwd(const segmif_linear_params* p, segmif_stream_t stream);
 /* ---- K10/K11 on tcgen05: 3x3 stride-1 'same' convolution (dilation 1 or 2), Cout in {32, 64}, bf16 out ----------

@@ -42,6 +42,7 @@ class LinearParams(ctypes.Structure):
         ("act", c_int),
         ("res_dtype", c_int), ("ld_res", c_int), ("res_coff", c_int),
         ("dst_dtype", c_int), ("ld_dst", c_int), ("dst_coff", c_int),
+        ("weight_kn", c_int),
     ]
 
 

@@ -74,7 +74,15 @@ def _lin_bwd(dy, x, weight_param, cache, g, wname, bname, need_dx=True, residual
         _colsum(dy, N, M, g[bname], g)
     if not need_dx:
         return None
-    return ops.linear_tc(dy, _t_pack(cache, weight_param, "lin_t"), None, residual=residual)
+    return _dgrad(dy, cache.linear(weight_param), lambda: _t_pack(cache, weight_param, "lin_t"), K, residual)
+
+
+def _dgrad(dy, fwd_pack, t_pack_fn, n_in, residual=None):
+    """dX = dY W.  The forward pack [out, 1, in] is read as a [K, N] operand (MN-major tcgen05 B descriptor) -- no
+    transposed copy of the weights -- whenever the input width is a multiple of 64; otherwise the transposed pack."""
+    if n_in % 64 == 0:
+        return ops.linear_tc(dy, fwd_pack, None, residual=residual, weight_kn=True)
+    return ops.linear_tc(dy, t_pack_fn(), None, residual=residual)
 
 
 def _im2col_nhwc(x, B, H, W, C, k, s, p):
@@ -261,7 +269,7 @@ def _block_backward(blk, sv, dx, B, N, g, pre):
         _wgrad(g, dred16, C, 0, sv["P_sr"], K, 0, B=1, H=1, W=1, P=Mk, Cin=K, Cout=C, taps=1, dil=1, grad=g[pre + "attn.sr.weight"],
                   s_co=K, s_tap=1, s_ci=1)
         _colsum(dred16, C, Mk, g[pre + "attn.sr.bias"], g)
-        dP = ops.linear_tc(dred16, _flat_t_pack(at._packs, at.sr.weight, K, "sr_flat_t"), None)
+        dP = _dgrad(dred16, _flat_pack(at._packs, at.sr.weight, K, "sr_flat"), lambda: _flat_t_pack(at._packs, at.sr.weight, K, "sr_flat_t"), K)
         extra = _patches_to_map(dP, B, sv["Hk"], sv["Wk"], C, r, H, W)
         extra = extra if extra.is_contiguous() else extra.contiguous()
     else:
@@ -307,7 +315,7 @@ def encoder_backward(enc, tape, douts, g, prefix, want_input_grad):
                   s_co=Cin * k * k, s_tap=1, s_ci=1, ci_take=Cin * k * k)
         _colsum(dy16, C, M, g[pp + "proj.bias"], g)
         if s > 0 or want_input_grad:
-            dP = ops.linear_tc(dy16, _flat_t_pack(pe._packs, pe.proj.weight, Kp, "pe_flat_t"), None)
+            dP = _dgrad(dy16, _flat_pack(pe._packs, pe.proj.weight, Kp, "pe_flat"), lambda: _flat_t_pack(pe._packs, pe.proj.weight, Kp, "pe_flat_t"), Kp)
             if s > 0:
                 carry = ops.col2im(dP, B, st["Hin"], st["Win"], Cin, k, st["s"], st["p"], out_dtype=BF16).view(-1, Cin)
             else:
@@ -342,7 +350,7 @@ def head_backward(head, tape, dlogits, B, g, prefix):
     cat2 = tape["cat"].view(M, 4 * E)
     _wgrad(g, dz, E, 0, cat2, 4 * E, 0, B=1, H=1, W=1, P=M, Cin=4 * E, Cout=E, taps=1, dil=1, grad=g[prefix + "linear_fuse.conv.weight"],
               s_co=4 * E, s_tap=1, s_ci=1)
-    dcat = ops.linear_tc(dz, _t_pack(head._packs, conv.weight, "fuse_t"), None)            # [M, 4E]
+    dcat = _dgrad(dz, head._packs.conv(conv.weight), lambda: _t_pack(head._packs, conv.weight, "fuse_t"), 4 * E)   # [M, 4E]
     t1, t2, t3, t4 = tape["toks"]
     douts = [None] * 4
     for slot, (name, mlp, t, h, w, idx) in enumerate((("linear_c4", head.linear_c4, t4, h4, w4, 3), ("linear_c3", head.linear_c3, t3, h3, w3, 2),

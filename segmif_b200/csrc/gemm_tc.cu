@@ -127,7 +127,9 @@ constexpr int kTcThreads = 192;
 // Persistent: each CTA walks output tiles (m-tile major, n-tile minor) with a stride of gridDim.x.  The 4-stage
 // operand ring runs across tile boundaries and the TMEM accumulator is double buffered, so TMA, MMA and the
 // epilogue of consecutive tiles overlap.
-template <int BN, bool GELU>
+// WKN: the weight is stored [K, N] (N contiguous) and used as an MN-major B operand: per stage 64 contraction rows of
+// 128-byte SW128 lines, one 8 KB box per 64 output columns (LBO apart), 8-row groups 1024 bytes apart (SBO).
+template <int BN, bool GELU, bool WKN>
 __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB,
                                                                 const TcEpilogue e, const int num_k_blocks,
@@ -169,14 +171,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
           tc::mbar_wait(empty + s, ph ^ 1);
           tc::mbar_expect_tx(full + s, A_BYTES + B_BYTES);
           tc::tma_load_2d(sA + s * A_BYTES, &tmA, full + s, kb * 64, m0);
-          tc::tma_load_2d(sB + s * B_BYTES, &tmB, full + s, kb * 64, n0);
+          if (WKN) {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) tc::tma_load_2d(sB + s * B_BYTES + j * 8192, &tmB, full + s, n0 + j * 64, kb * 64);
+          } else {
+            tc::tma_load_2d(sB + s * B_BYTES, &tmB, full + s, kb * 64, n0);
+          }
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    constexpr uint32_t idesc = tc::make_idesc_bf16(128, BN);
+    constexpr uint32_t idesc = tc::make_idesc_bf16(128, BN) | (WKN ? (1u << 16) : 0u);
     constexpr uint64_t HI = (uint64_t)tc::desc_hi_sw128(1024) << 32;
+    constexpr uint64_t HI_B = HI | (WKN ? ((uint64_t)(8192 >> 4) << 16) : 0);         // LBO between 64-column groups
+    constexpr uint64_t B_KSTEP = WKN ? (16 * 128) >> 4 : 2;                           // descriptor advance per K = 16
     const bool leader = tc::elect_one();
     int it = 0, lt = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
@@ -189,11 +198,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         tc::mbar_wait(full + s, (it / kTcStages) & 1);
         tc::tc_fence_after();
         if (leader) {
-          uint64_t a_d = HI | (uint64_t)(smem_u32(sA + s * A_BYTES) >> 4), b_d = HI | (uint64_t)(smem_u32(sB + s * B_BYTES) >> 4);
+          uint64_t a_d = HI | (uint64_t)(smem_u32(sA + s * A_BYTES) >> 4), b_d = HI_B | (uint64_t)(smem_u32(sB + s * B_BYTES) >> 4);
           asm volatile("" : "+l"(a_d), "+l"(b_d));     // opaque bases: k offsets stay immediates of one UIADD3.64 each
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            tc::umma_bf16(acc, a_d + (uint64_t)(k * 2), b_d + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+            tc::umma_bf16(acc, a_d + (uint64_t)(k * 2), b_d + (uint64_t)k * B_KSTEP, idesc, (kb | k) != 0 ? 1u : 0u);
           tc::umma_commit(empty + s);          // frees the smem stage when these MMAs have read it
         }
         __syncwarp();
@@ -232,10 +241,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
   if (warp == 1) tc::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-template <int BN, bool GELU>
+template <int BN, bool GELU, bool WKN = false>
 static int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcEpilogue& e, int K, cudaStream_t st) {
   constexpr size_t smem = (size_t)kTcStages * (128 * 128 + BN * 128) + (2 * kTcStages + 4) * 8 + 16;
-  auto kern = gemm_tc_kernel<BN, GELU>;
+  auto kern = gemm_tc_kernel<BN, GELU, WKN>;
   static bool configured = false;
   if (!configured) {
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -269,6 +278,7 @@ static int linear_tc_impl(const segmif_linear_params* p, cudaStream_t st) {
   SEGMIF_REQUIRE(((uintptr_t)p->src & 15) == 0 && ((uintptr_t)p->weight & 15) == 0 && ((uintptr_t)p->dst & 15) == 0,
                  "linear_tc: pointers must be 16-byte aligned");
   const int BN = (p->N % 128 == 0 || p->N > 192) ? 128 : (p->N % 64 == 0 ? 64 : 32);
+  SEGMIF_REQUIRE(!p->weight_kn || (p->N % 64 == 0 && p->act != SEGMIF_ACT_GELU), "linear_tc: weight_kn needs N %% 64 == 0 and no GELU");
   CUtensorMap tmA, tmB;
   {
     const uint64_t dims[2] = {(uint64_t)p->K, (uint64_t)p->M};
@@ -277,7 +287,13 @@ static int linear_tc_impl(const segmif_linear_params* p, cudaStream_t st) {
     int rc = make_tmap_bf16(&tmA, reinterpret_cast<const bf16*>(p->src) + p->src_coff, 2, dims, strides, box, true, "linear_tc(A)");
     if (rc) return rc;
   }
-  {
+  if (p->weight_kn) {
+    const uint64_t dims[2] = {(uint64_t)p->N, (uint64_t)p->K};
+    const uint64_t strides[1] = {(uint64_t)p->N * 2};
+    const uint32_t box[2] = {64, 64};
+    int rc = make_tmap_bf16(&tmB, p->weight, 2, dims, strides, box, true, "linear_tc(W, [K,N])");
+    if (rc) return rc;
+  } else {
     const uint64_t dims[2] = {(uint64_t)p->K, (uint64_t)p->N};
     const uint64_t strides[1] = {(uint64_t)p->K * 2};
     const uint32_t box[2] = {64, (uint32_t)BN};
@@ -292,6 +308,10 @@ static int linear_tc_impl(const segmif_linear_params* p, cudaStream_t st) {
     if (BN == 128) return launch_gemm_tc<128, true>(tmA, tmB, e, p->K, st);
     if (BN == 64) return launch_gemm_tc<64, true>(tmA, tmB, e, p->K, st);
     return launch_gemm_tc<32, true>(tmA, tmB, e, p->K, st);
+  }
+  if (p->weight_kn) {
+    if (BN == 128) return launch_gemm_tc<128, false, true>(tmA, tmB, e, p->K, st);
+    return launch_gemm_tc<64, false, true>(tmA, tmB, e, p->K, st);
   }
   if (BN == 128) return launch_gemm_tc<128, false>(tmA, tmB, e, p->K, st);
   if (BN == 64) return launch_gemm_tc<64, false>(tmA, tmB, e, p->K, st);

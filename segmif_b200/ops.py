@@ -160,8 +160,9 @@ def linear(x, weight, bias, *, act=ACT_NONE, residual=None, out_dtype=torch.bflo
 
 
 def _linear_params(x, weight, bias, M, N, K, ld_src, src_coff, act, prelu_alpha, residual, ld_res, res_coff, out, ld_dst,
-                   dst_coff):
+                   dst_coff, weight_kn=False):
     p = _lib.LinearParams()
+    p.weight_kn = 1 if weight_kn else 0
     p.src, p.weight = x.data_ptr(), weight.data_ptr()
     p.bias = bias.data_ptr() if bias is not None else None
     p.prelu_alpha = prelu_alpha.data_ptr() if prelu_alpha is not None else None
@@ -176,11 +177,16 @@ def _linear_params(x, weight, bias, M, N, K, ld_src, src_coff, act, prelu_alpha,
 
 
 def linear_tc(x, weight, bias, *, M=None, K=None, ld_src=None, src_coff=0, act=ACT_NONE, prelu_alpha=None, residual=None,
-              ld_res=None, res_coff=0, out=None, out_dtype=torch.bfloat16, ld_dst=None, dst_coff=0):
-    """tcgen05 + TMA linear layer (segmif_linear_tc_fwd).  x bf16 [..., ld_src]; weight packed bf16 [N, 1, K]."""
+              ld_res=None, res_coff=0, out=None, out_dtype=torch.bfloat16, ld_dst=None, dst_coff=0, weight_kn=False):
+    """tcgen05 + TMA linear layer (segmif_linear_tc_fwd).  x bf16 [..., ld_src]; weight packed bf16 [N, 1, K], or with
+    weight_kn the [K, 1, N] buffer -- a forward pack reused as the operand of the data gradient dX = dY W."""
     st = _prep(x, weight, bias, prelu_alpha, residual, out)
-    N = weight.shape[0]
-    K = weight.shape[-1] if K is None else K
+    if weight_kn:
+        N = weight.shape[-1]
+        K = weight.shape[0] if K is None else K
+    else:
+        N = weight.shape[0]
+        K = weight.shape[-1] if K is None else K
     ld_src = x.shape[-1] if ld_src is None else ld_src
     M = x.numel() // ld_src if M is None else M
     if out is None:
@@ -191,7 +197,7 @@ def linear_tc(x, weight, bias, *, M=None, K=None, ld_src=None, src_coff=0, act=A
     if residual is not None and ld_res is None:
         ld_res = residual.shape[-1]
     p = _linear_params(x, weight, bias, M, N, K, ld_src, src_coff, act, prelu_alpha, residual, ld_res, res_coff, out,
-                       ld_dst, dst_coff)
+                       ld_dst, dst_coff, weight_kn)
     _lib.call("segmif_linear_tc_fwd", ctypes.byref(p), st)
     return out
 

@@ -179,6 +179,16 @@ def conv_weight_and_data_gradients():
         ops.wgrad(dy.bfloat16().to(DEV), N, 0, x.bfloat16().to(DEV), K, 0, B=1, H=1, W=1, P=P, Cin=K, Cout=N, taps=1, dil=1,
                   grad=grad, s_co=K, s_tap=1, s_ci=1)
         res.append(result(f"wgrad_linear_{P}x{K}x{N}", rel_err(grad, dy.t() @ x), 1e-3))
+    # data gradient of a linear layer straight from the forward pack: dX = dY W with W [out, in] read as a [K, N] operand
+    for (P, out_f, in_f) in ((1000, 128, 64), (333, 64, 256), (4096, 2048, 512), (77, 320, 1280), (500, 256, 1024)):
+        W_ = rnd(out_f, in_f, seed=out_f, scale=0.1)
+        dy = rnd(P, out_f, seed=in_f + 1)
+        base = rnd(P, in_f, seed=3, bf16=False)
+        pack = W_.bfloat16().reshape(out_f, 1, in_f).contiguous().to(DEV)
+        dx = ops.linear_tc(dy.bfloat16().to(DEV), pack, None, weight_kn=True, out_dtype=torch.float32)
+        res.append(result(f"dgrad_linear_weight_kn_{P}x{out_f}x{in_f}", rel_err(dx, dy @ W_), 1e-3))
+        dx2 = ops.linear_tc(dy.bfloat16().to(DEV), pack, None, weight_kn=True, residual=base.to(DEV), out_dtype=torch.float32)
+        res.append(result(f"dgrad_linear_weight_kn_residual_{out_f}x{in_f}", rel_err(dx2, dy @ W_ + base), 1e-3))
     # slices: dy / x inside wider pitches, co_take / ci_take
     x = rnd(1, 16, 24, 40, seed=5)
     dy = rnd(1, 16, 24, 64, seed=6)

@@ -43,117 +43,227 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__
   }
 }
 
+// ------------------------------------------------------------------------------------------------ streaming stencils
+// SSIM, the Laplacian residuals and Sobel share one layout ("column streaming").  A block of 128 threads owns a strip of
+// 128 image columns and walks down a range of rows; thread = column.  Rows arrive in GROUPS: cp.async copies the next
+// group's rows (+ R halo columns each side, zero fill outside the image) straight into the other half of a
+// double-buffered shared-memory block while the current group is consumed, so a block keeps ~10 KB in flight and
+// synchronises twice per group instead of once per row.  For every row each thread applies the HORIZONTAL taps to its
+// column, and the VERTICAL filter is a scatter into a ring of partial output accumulators held in REGISTERS: input row
+// r adds g[r - o + R] * h(r) to every output row o in [r - R, r + R]; output r - R is then complete and is consumed on the
+// spot.  The group length equals the ring length and the group loop is fully unrolled, so all ring indices are
+// compile-time constants.  Each input pixel is read from HBM once (plus 2R/rows and 2R/128 halo overheads) and nothing but
+// the loss partials is written; the first versions (32x32 tiles with halo in shared memory, one shared load per FMA)
+// were bound by shared-memory bandwidth at 8-9 % of the HBM roofline.
+constexpr int kStripW = 128;
+
+__device__ __forceinline__ void cp_async4(void* smem_dst, const float* gsrc, bool ok) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(ok ? 4 : 0));
+}
+
+struct StreamGeom {
+  int x0, y0, y1;          // first column, output rows [y0, y1)
+  int col;                 // this thread's column
+  bool col_ok;
+};
+__device__ __forceinline__ StreamGeom stream_geom(int H, int W, int rows_per_chunk) {
+  StreamGeom g;
+  g.x0 = blockIdx.x * kStripW;
+  g.y0 = blockIdx.y * rows_per_chunk;
+  g.y1 = min(H, g.y0 + rows_per_chunk);
+  g.col = g.x0 + threadIdx.x;
+  g.col_ok = g.col < W;
+  return g;
+}
+
+// rows [r0, r0 + ROWS) of NIMG planes -> buf[row][image][R + 128 + R]; rows / columns outside the image (or >= r_end) read 0
+template <int NIMG, int R, int ROWS>
+__device__ __forceinline__ void issue_rows(const float* const (&src)[NIMG], float (*buf)[NIMG][kStripW + 2 * R], int r0, int r_end,
+                                           int H, int W, const StreamGeom& g) {
+  const int t = threadIdx.x;
+  const bool has_halo = t < 2 * R;
+  const int hslot = t < R ? t : kStripW + t;                       // left halo slots [0, R), right [R + 128, 2R + 128)
+  const int hcol = t < R ? g.x0 - R + t : g.x0 + kStripW + (t - R);
+  const bool hcol_ok = has_halo && (unsigned)hcol < (unsigned)W;
+#pragma unroll
+  for (int i = 0; i < ROWS; ++i) {
+    const int r = r0 + i;
+    const bool row_ok = (unsigned)r < (unsigned)H && r < r_end;
+    const int64_t o = (int64_t)(row_ok ? r : 0) * W;
+#pragma unroll
+    for (int m = 0; m < NIMG; ++m) {
+      cp_async4(&buf[i][m][R + t], src[m] + o + (g.col_ok ? g.col : 0), row_ok && g.col_ok);
+      if (has_halo) cp_async4(&buf[i][m][hslot], src[m] + o + (hcol_ok ? hcol : 0), row_ok && hcol_ok);
+    }
+  }
+  cp_async_commit();
+}
+
 // ------------------------------------------------------------------------------------------------ SSIM
 struct Gauss11 { float g[11]; };
 
-__global__ void __launch_bounds__(256) ssim_kernel(const float* __restrict__ a, const float* __restrict__ b, int H,
-                                                   int W, Gauss11 win, float* __restrict__ partials) {
-  constexpr int T = 32, R = 5, TW = T + 2 * R;   // 42
-  __shared__ float sa[TW][TW + 1], sb[TW][TW + 1];
-  __shared__ float hz[5][TW][T + 1];
+// packed fp32 pairs (FFMA2 / FMUL2): (mu1, mu2) and (E[x^2], E[y^2]) travel together -- the kernel is issue bound
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
+                     rc = *reinterpret_cast<unsigned long long*>(&c), rd;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  return *reinterpret_cast<float2*>(&rd);
+}
+
+__global__ void __launch_bounds__(128) ssim_kernel(const float* __restrict__ a, const float* __restrict__ b, int H, int W,
+                                                   int rows_per_chunk, Gauss11 win, float* __restrict__ partials) {
+  constexpr int R = 5, N = 11;
+  __shared__ float lines[2][N][2][kStripW + 2 * R];
   __shared__ float sred[8];
-  const int bx = blockIdx.x * T, by = blockIdx.y * T;
-  const int64_t img = blockIdx.z;
-  const float* pa = a + img * H * W;
-  const float* pb = b + img * H * W;
-  for (int i = threadIdx.x; i < TW * TW; i += 256) {
-    const int r = i / TW, c = i % TW;
-    const int y = by + r - R, x = bx + c - R;
-    const bool ok = (unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W;
-    sa[r][c] = ok ? pa[(int64_t)y * W + x] : 0.f;
-    sb[r][c] = ok ? pb[(int64_t)y * W + x] : 0.f;
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < TW * T; i += 256) {
-    const int r = i / T, c = i % T;
-    float m1 = 0.f, m2 = 0.f, s11 = 0.f, s22 = 0.f, s12 = 0.f;
+  const StreamGeom g = stream_geom(H, W, rows_per_chunk);
+  const float* const src[2] = {a + (int64_t)blockIdx.z * H * W, b + (int64_t)blockIdx.z * H * W};
+  const int t = threadIdx.x;
+  float2 am[N], as[N];                                     // ring of (mu1, mu2) and (E[x^2], E[y^2]) partial sums
+  float ax[N];                                             // ... and E[xy]
 #pragma unroll
-    for (int k = 0; k < 11; ++k) {
-      const float x = sa[r][c + k], y = sb[r][c + k], g = win.g[k];
-      m1 = fmaf(g, x, m1); m2 = fmaf(g, y, m2);
-      s11 = fmaf(g, x * x, s11); s22 = fmaf(g, y * y, s22); s12 = fmaf(g, x * y, s12);
-    }
-    hz[0][r][c] = m1; hz[1][r][c] = m2; hz[2][r][c] = s11; hz[3][r][c] = s22; hz[4][r][c] = s12;
-  }
-  __syncthreads();
+  for (int j = 0; j < N; ++j) { am[j] = make_float2(0.f, 0.f); as[j] = make_float2(0.f, 0.f); ax[j] = 0.f; }
   float local = 0.f;
-  for (int i = threadIdx.x; i < T * T; i += 256) {
-    const int r = i / T, c = i % T;
-    if (by + r >= H || bx + c >= W) continue;
-    float m1 = 0.f, m2 = 0.f, s11 = 0.f, s22 = 0.f, s12 = 0.f;
+  const int r_begin = g.y0 - R, r_end = g.y1 + R;         // input rows that touch this chunk's outputs
+  issue_rows<2, R, N>(src, lines[0], r_begin, r_end, H, W, g);
+  int pb = 0;
+  for (int rb = r_begin; rb < r_end; rb += N, pb ^= 1) {
+    issue_rows<2, R, N>(src, lines[pb ^ 1], rb + N, r_end, H, W, g);
+    cp_async_wait<1>();
+    __syncthreads();
 #pragma unroll
-    for (int k = 0; k < 11; ++k) {
-      const float g = win.g[k];
-      m1 = fmaf(g, hz[0][r + k][c], m1); m2 = fmaf(g, hz[1][r + k][c], m2);
-      s11 = fmaf(g, hz[2][r + k][c], s11); s22 = fmaf(g, hz[3][r + k][c], s22); s12 = fmaf(g, hz[4][r + k][c], s12);
+    for (int i = 0; i < N; ++i) {
+      const int r = rb + i;
+      if (r < r_end) {                                    // block-uniform
+        if ((unsigned)r < (unsigned)H) {
+          const float* la = lines[pb][i][0] + t;
+          const float* lb = lines[pb][i][1] + t;
+          float2 hm = make_float2(0.f, 0.f), hs = make_float2(0.f, 0.f);
+          float hx = 0.f;
+#pragma unroll
+          for (int k = 0; k < N; ++k) {
+            const float2 v = make_float2(la[k], lb[k]);
+            const float2 w = make_float2(win.g[k], win.g[k]);
+            hm = ffma2(w, v, hm);
+            hs = ffma2(w, fmul2(v, v), hs);
+            hx = fmaf(win.g[k], v.x * v.y, hx);
+          }
+#pragma unroll
+          for (int j = 0; j < N; ++j) {                   // output row o = r - R + j gets weight g[N - 1 - j]
+            const float2 w = make_float2(win.g[N - 1 - j], win.g[N - 1 - j]);
+            const int sl = (i + j) % N;
+            am[sl] = ffma2(w, hm, am[sl]);
+            as[sl] = ffma2(w, hs, as[sl]);
+            ax[sl] = fmaf(w.x, hx, ax[sl]);
+          }
+        }
+        const int o = r - R;                              // complete now: slot i
+        if (o >= g.y0 && o < g.y1 && g.col_ok) {
+          const float m1 = am[i].x, m2 = am[i].y;
+          const float mu1_sq = m1 * m1, mu2_sq = m2 * m2, mu12 = m1 * m2;
+          const float sg1 = as[i].x - mu1_sq, sg2 = as[i].y - mu2_sq, sg12 = ax[i] - mu12;
+          const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+          local += ((2.f * mu12 + C1) * (2.f * sg12 + C2)) / ((mu1_sq + mu2_sq + C1) * (sg1 + sg2 + C2));
+        }
+        am[i] = make_float2(0.f, 0.f);
+        as[i] = make_float2(0.f, 0.f);
+        ax[i] = 0.f;
+      }
     }
-    const float mu1_sq = m1 * m1, mu2_sq = m2 * m2, mu12 = m1 * m2;
-    const float sg1 = s11 - mu1_sq, sg2 = s22 - mu2_sq, sg12 = s12 - mu12;
-    const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
-    local += ((2.f * mu12 + C1) * (2.f * sg12 + C2)) / ((mu1_sq + mu2_sq + C1) * (sg1 + sg2 + C2));
+    __syncthreads();                                      // this half is refilled by the next iteration's cp.async
   }
+  cp_async_wait<0>();
   const float tot = block_sum_256(local, sred);
   if (threadIdx.x == 0) partials[((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = tot;
 }
 
 // ------------------------------------------------------------------------------------------------ Laplacian
-struct LapKernels { float k3[9], k5[25], k7[49]; };
-
-template <int K>
-__device__ __forceinline__ float lap_residual(const float (*t)[39], int r, int c, const float* ker) {
-  // t has a 3-pixel halo; residual = centre - (G_K * img)
-  constexpr int R = K / 2;
-  float s = 0.f;
-#pragma unroll
-  for (int dy = 0; dy < K; ++dy)
-#pragma unroll
-    for (int dx = 0; dx < K; ++dx) s = fmaf(ker[dy * K + dx], t[r + 3 - R + dy][c + 3 - R + dx], s);
-  return t[r + 3][c + 3] - s;
-}
+// lap_loss.py:39-71: the (k,k) Gaussian exp(-(dx^2+dy^2)/(2 sigma^2)) normalised to sum 1 is the outer product of the
+// normalised 1-D Gaussians, so each blur is a horizontal and a vertical k-tap pass.  residual = img - blur is built in the
+// accumulator ring itself (+centre when the centre row passes, -g_v * h_k for every row).
+struct LapTaps { float g3[3], g5[5], g7[7]; };
 
 // NIMG = 3: LapLoss2 (input, ir, vis -> target = max(res ir, res vis));  NIMG = 2: LapLoss (input, target)
 template <int NIMG>
-__global__ void __launch_bounds__(256) laploss_kernel(const float* __restrict__ inp, const float* __restrict__ p1,
-                                                      const float* __restrict__ p2, int H, int W, LapKernels ker,
-                                                      float* __restrict__ partials) {
-  constexpr int T = 32, R = 3, TW = T + 2 * R;   // 38
-  __shared__ float s0[TW][39], s1[TW][39], s2[NIMG == 3 ? TW : 1][39];
+__global__ void __launch_bounds__(128) laploss_kernel(const float* __restrict__ inp, const float* __restrict__ p1,
+                                                      const float* __restrict__ p2, int H, int W, int rows_per_chunk,
+                                                      LapTaps tp, float* __restrict__ partials) {
+  constexpr int R = 3, N = 7;
+  __shared__ float lines[2][N][NIMG][kStripW + 2 * R];
   __shared__ float sred[8];
-  const int bx = blockIdx.x * T, by = blockIdx.y * T;
+  const StreamGeom g = stream_geom(H, W, rows_per_chunk);
   const int64_t off = (int64_t)blockIdx.z * H * W;
-  for (int i = threadIdx.x; i < TW * TW; i += 256) {
-    const int r = i / TW, c = i % TW;
-    const int y = by + r - R, x = bx + c - R;
-    const bool ok = (unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W;
-    const int64_t o = off + (int64_t)y * W + x;
-    s0[r][c] = ok ? inp[o] : 0.f;
-    s1[r][c] = ok ? p1[o] : 0.f;
-    if (NIMG == 3) s2[r][c] = ok ? p2[o] : 0.f;
-  }
-  __syncthreads();
+  const float* src[NIMG];
+  src[0] = inp + off;
+  src[1] = p1 + off;
+  if (NIMG == 3) src[NIMG - 1] = p2 + off;
+  const int t = threadIdx.x;
+  float acc[N][NIMG][3];                                   // [ring slot][image][scale 3/5/7]
+#pragma unroll
+  for (int j = 0; j < N; ++j)
+#pragma unroll
+    for (int m = 0; m < NIMG; ++m)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) acc[j][m][k] = 0.f;
   float l3 = 0.f, l5 = 0.f, l7 = 0.f;
-  for (int i = threadIdx.x; i < T * T; i += 256) {
-    const int r = i / T, c = i % T;
-    if (by + r >= H || bx + c >= W) continue;
-    {
-      const float a = lap_residual<3>(s0, r, c, ker.k3);
-      float t = lap_residual<3>(s1, r, c, ker.k3);
-      if (NIMG == 3) t = fmaxf(t, lap_residual<3>(s2, r, c, ker.k3));
-      l3 += fabsf(a - t);
+  const int r_begin = g.y0 - R, r_end = g.y1 + R;
+  issue_rows<NIMG, R, N>(src, lines[0], r_begin, r_end, H, W, g);
+  int pb = 0;
+  for (int rb = r_begin; rb < r_end; rb += N, pb ^= 1) {
+    issue_rows<NIMG, R, N>(src, lines[pb ^ 1], rb + N, r_end, H, W, g);
+    cp_async_wait<1>();
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const int r = rb + i;
+      if (r < r_end) {
+        if ((unsigned)r < (unsigned)H) {
+#pragma unroll
+          for (int m = 0; m < NIMG; ++m) {
+            float v[N];
+#pragma unroll
+            for (int k = 0; k < N; ++k) v[k] = lines[pb][i][m][t + k];
+            float h3 = 0.f, h5 = 0.f, h7 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) h3 = fmaf(tp.g3[k], v[2 + k], h3);
+#pragma unroll
+            for (int k = 0; k < 5; ++k) h5 = fmaf(tp.g5[k], v[1 + k], h5);
+#pragma unroll
+            for (int k = 0; k < 7; ++k) h7 = fmaf(tp.g7[k], v[k], h7);
+#pragma unroll
+            for (int j = 0; j < N; ++j) {                 // output row o = r - R + j; d = r - o
+              const int sl = (i + j) % N;
+              const int d = R - j;
+              if (d >= -1 && d <= 1) acc[sl][m][0] = fmaf(-tp.g3[d + 1], h3, acc[sl][m][0]);
+              if (d >= -2 && d <= 2) acc[sl][m][1] = fmaf(-tp.g5[d + 2], h5, acc[sl][m][1]);
+              acc[sl][m][2] = fmaf(-tp.g7[d + 3], h7, acc[sl][m][2]);
+            }
+            const int sc = (i + R) % N;                   // o == r: the centre pixel of the residual
+            acc[sc][m][0] += v[R]; acc[sc][m][1] += v[R]; acc[sc][m][2] += v[R];
+          }
+        }
+        const int o = r - R;
+        if (o >= g.y0 && o < g.y1 && g.col_ok) {
+          float tgt[3];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) tgt[k] = NIMG == 3 ? fmaxf(acc[i][1][k], acc[i][NIMG - 1][k]) : acc[i][1][k];
+          l3 += fabsf(acc[i][0][0] - tgt[0]);
+          l5 += fabsf(acc[i][0][1] - tgt[1]);
+          l7 += fabsf(acc[i][0][2] - tgt[2]);
+        }
+#pragma unroll
+        for (int m = 0; m < NIMG; ++m)
+#pragma unroll
+          for (int k = 0; k < 3; ++k) acc[i][m][k] = 0.f;
+      }
     }
-    {
-      const float a = lap_residual<5>(s0, r, c, ker.k5);
-      float t = lap_residual<5>(s1, r, c, ker.k5);
-      if (NIMG == 3) t = fmaxf(t, lap_residual<5>(s2, r, c, ker.k5));
-      l5 += fabsf(a - t);
-    }
-    {
-      const float a = lap_residual<7>(s0, r, c, ker.k7);
-      float t = lap_residual<7>(s1, r, c, ker.k7);
-      if (NIMG == 3) t = fmaxf(t, lap_residual<7>(s2, r, c, ker.k7));
-      l7 += fabsf(a - t);
-    }
+    __syncthreads();
   }
+  cp_async_wait<0>();
   const int64_t blk = ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
   const float t3 = block_sum_256(l3, sred);
   const float t5 = block_sum_256(l5, sred);
@@ -162,83 +272,132 @@ __global__ void __launch_bounds__(256) laploss_kernel(const float* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------ Entropy
-// A warp walks 32-float wide row segments: P rows x 32 columns hold 32/P patches; lane k is histogram bin k.
+// A warp walks P-row x 32-column segments (32 / P patches; the P lanes [q P, (q+1) P) hold patch q).  core/Entropy.py
+// evaluates all 32 Gaussian kernels (sigma = 0.01, bins 1/31 = 3.2 sigma apart) for every pixel; a bin more than 3 bins
+// away from the pixel's nearest bin is >= 11 sigma off and weighs < exp(-60), below fp32 resolution of the patch sums, so
+// each lane evaluates only the 7 bins around each of its P pixels (7 exp per pixel instead of 32: the first version
+// was MUFU-issue bound) and adds them into its PRIVATE column of a per-warp shared-memory histogram hist[bin][lane] --
+// plain read-modify-write, no atomics (a shared-memory float atomicAdd is a compare-and-swap loop; ncu showed the
+// atomic version stalled on it with 70 M bank conflicts).  Then lane = bin: the P columns of a patch are summed,
+// normalised (one warp sum per patch) and -p log p accumulated per lane.  Rows are 33 floats apart: the scatter hits
+// bank (bin + lane) % 32 (neighbouring pixels fall into neighbouring bins: rarely equal), the gather bank (lane + column).
 struct Bins32 { float b[32]; };
+
+__device__ __forceinline__ float ex2_ftz(float x) {        // one MUFU, no denormal fix-up code (weights < 2^-126 are 0 anyway)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 template <int P>
 __global__ void __launch_bounds__(256) entropy_kernel(const float* __restrict__ img, int B, int H, int W, Bins32 bins,
                                                       float* __restrict__ partials) {
+  constexpr int NP = 32 / P;                               // patches per segment
+  __shared__ float hist[8][32][33];
+  __shared__ float sbin[32];
   __shared__ float sred[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  if (threadIdx.x < 32) sbin[threadIdx.x] = bins.b[threadIdx.x];
+  __syncthreads();
   const int segs_x = (W + 31) / 32;
   const int prow = H / P;
   const int64_t nseg = (int64_t)B * prow * segs_x;
-  const float mybin = bins.b[lane];
   const float inv_sigma = 1.0f / 0.01f;
   const float nhl2e = -0.5f * 1.4426950408889634f;
+  float (*hw)[33] = hist[warp];
   float total = 0.f;
   for (int64_t sidx = (int64_t)blockIdx.x * nwarp + warp; sidx < nseg; sidx += (int64_t)gridDim.x * nwarp) {
     const int sx = (int)(sidx % segs_x);
     const int py = (int)((sidx / segs_x) % prow);
     const int64_t b = sidx / ((int64_t)segs_x * prow);
     const int x = sx * 32 + lane;
-    float v[P];
+    float val[P];
 #pragma unroll
-    for (int dy = 0; dy < P; ++dy) v[dy] = x < W ? img[(b * H + (int64_t)py * P + dy) * W + x] : 0.f;
+    for (int dy = 0; dy < P; ++dy) val[dy] = x < W ? img[(b * H + (int64_t)py * P + dy) * W + x] : 0.f;
 #pragma unroll
-    for (int q = 0; q < 32 / P; ++q) {
-      if (sx * 32 + q * P >= W) break;              // warp-uniform
+    for (int j = 0; j < 32; ++j) hw[j][lane] = 0.f;        // own column
+    if (x < W) {
+#pragma unroll
+      for (int dy = 0; dy < P; ++dy) {
+        const int j0 = min(31, max(0, __float2int_rn(val[dy] * 31.0f)));
+#pragma unroll
+        for (int dj = -3; dj <= 3; ++dj) {
+          const int j = j0 + dj;
+          if ((unsigned)j < 32u) {
+            const float r = (val[dy] - sbin[j]) * inv_sigma;
+            hw[j][lane] += ex2_ftz(nhl2e * (r * r));
+          }
+        }
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+      if (sx * 32 + q * P >= W) break;                     // warp-uniform (W % P == 0)
       float acc = 0.f;
 #pragma unroll
-      for (int dy = 0; dy < P; ++dy)
-#pragma unroll
-        for (int dx = 0; dx < P; ++dx) {
-          const float val = __shfl_sync(0xffffffffu, v[dy], q * P + dx);
-          const float r = (val - mybin) * inv_sigma;
-          acc += exp2f(nhl2e * (r * r));          // exp(-r^2/2) through MUFU.EX2: the loop is MUFU-issue bound
-        }
-      float pdf = acc / (float)(P * P);
+      for (int p = 0; p < P; ++p) acc += hw[lane][q * P + p];
+      float pdf = acc * (1.0f / (float)(P * P));
       const float norm = warp_sum(pdf) + 1e-40f;
-      pdf = pdf / norm + 1e-40f;
-      total -= warp_sum(pdf * logf(pdf));
+      pdf = pdf * __frcp_rn(norm) + 1e-40f;
+      // p log p of an (almost) empty bin: the reference's 1e-40 * log(1e-40) ~ -1e-38; dropped (and __logf would flush
+      // the denormal to -inf)
+      if (pdf > 1e-30f) total -= pdf * __logf(pdf);
     }
+    __syncwarp();
   }
+  total = warp_sum(total);
   if (lane != 0) total = 0.f;
-  const float t = block_sum_256(total, sred);
-  if (threadIdx.x == 0) partials[blockIdx.x] = t;
+  const float tsum = block_sum_256(total, sred);
+  if (threadIdx.x == 0) partials[blockIdx.x] = tsum;
 }
 
 // ------------------------------------------------------------------------------------------------ Sobel + L1
-__device__ __forceinline__ float sobel_at(const float* p, int y, int x, int H, int W) {
-  float n[3][3];
-#pragma unroll
-  for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-    for (int dx = 0; dx < 3; ++dx) {
-      const int yy = y + dy - 1, xx = x + dx - 1;
-      n[dy][dx] = ((unsigned)yy < (unsigned)H && (unsigned)xx < (unsigned)W) ? p[(int64_t)yy * W + xx] : 0.f;
-    }
-  const float gx = -n[0][0] + n[0][2] - 2.f * n[1][0] + 2.f * n[1][2] - n[2][0] + n[2][2];
-  const float gy = n[0][0] + 2.f * n[0][1] + n[0][2] - n[2][0] - 2.f * n[2][1] - n[2][2];
-  return fabsf(gx) + fabsf(gy);
-}
-
-__global__ void __launch_bounds__(256) sobel_l1_kernel(const float* __restrict__ x, const float* __restrict__ y, int B,
-                                                       int H, int W, float* __restrict__ partials) {
+// column streaming with a three-row register window per image: per row d = right - left and s = left + 2 c + right;
+// gx(o) = d(o-1) + 2 d(o) + d(o+1), gy(o) = s(o-1) - s(o+1)   (core/loss.py:634-650, zero padding)
+__global__ void __launch_bounds__(128) sobel_l1_kernel(const float* __restrict__ x, const float* __restrict__ y, int H, int W,
+                                                       int rows_per_chunk, float* __restrict__ partials) {
+  constexpr int R = 1, N = 8;
+  __shared__ float lines[2][N][2][kStripW + 2 * R];
   __shared__ float sred[8];
+  const StreamGeom g = stream_geom(H, W, rows_per_chunk);
+  const float* const src[2] = {x + (int64_t)blockIdx.z * H * W, y + (int64_t)blockIdx.z * H * W};
+  const int t = threadIdx.x;
+  const int r_begin = g.y0 - R, r_end = g.y1 + R;
+  float2 d0 = make_float2(0.f, 0.f), d1 = d0, s0 = d0, s1 = d0;      // rows r-2 (0) and r-1 (1), (x image, y image)
   float l1 = 0.f, lg = 0.f;
-  const int64_t n = (int64_t)B * H * W;
-  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
-    const int px = (int)(i % W), py = (int)((i / W) % H);
-    const int64_t b = i / ((int64_t)W * H);
-    const float* xp = x + b * H * W;
-    const float* yp = y + b * H * W;
-    l1 += fabsf(xp[(int64_t)py * W + px] - yp[(int64_t)py * W + px]);
-    lg += fabsf(sobel_at(xp, py, px, H, W) - sobel_at(yp, py, px, H, W));
+  issue_rows<2, R, N>(src, lines[0], r_begin, r_end, H, W, g);
+  int pb = 0;
+  for (int rb = r_begin; rb < r_end; rb += N, pb ^= 1) {
+    issue_rows<2, R, N>(src, lines[pb ^ 1], rb + N, r_end, H, W, g);
+    cp_async_wait<1>();
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const int r = rb + i;
+      if (r < r_end) {
+        const float* lx = lines[pb][i][0] + t;
+        const float* ly = lines[pb][i][1] + t;
+        const float2 lf = make_float2(lx[0], ly[0]), ce = make_float2(lx[1], ly[1]), rt = make_float2(lx[2], ly[2]);
+        const float2 d2 = make_float2(rt.x - lf.x, rt.y - lf.y);
+        const float2 s2 = make_float2(lf.x + 2.f * ce.x + rt.x, lf.y + 2.f * ce.y + rt.y);
+        if (r >= g.y0 && r < g.y1 && g.col_ok) l1 += fabsf(ce.x - ce.y);
+        const int o = r - R;
+        if (o >= g.y0 && o < g.y1 && g.col_ok) {
+          const float gxx = d0.x + 2.f * d1.x + d2.x, gyx = s0.x - s2.x;
+          const float gxy = d0.y + 2.f * d1.y + d2.y, gyy = s0.y - s2.y;
+          lg += fabsf((fabsf(gxx) + fabsf(gyx)) - (fabsf(gxy) + fabsf(gyy)));
+        }
+        d0 = d1; d1 = d2; s0 = s1; s1 = s2;
+      }
+    }
+    __syncthreads();
   }
+  cp_async_wait<0>();
+  const int64_t blk = ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
   const float a = block_sum_256(l1, sred);
-  const float g = block_sum_256(lg, sred);
-  if (threadIdx.x == 0) { partials[blockIdx.x * 2] = a; partials[blockIdx.x * 2 + 1] = g; }
+  const float gsum = block_sum_256(lg, sred);
+  if (threadIdx.x == 0) { partials[blk * 2] = a; partials[blk * 2 + 1] = gsum; }
 }
 
 __global__ void __launch_bounds__(256) mse_l1_kernel(const float* __restrict__ x, const float* __restrict__ y,
@@ -353,6 +512,21 @@ extern "C" size_t segmif_loss_workspace_bytes(int B, int H, int W) {
   return 256 + blocks * 3 * sizeof(float);
 }
 
+// column-streaming launch geometry: strips of 128 columns x row chunks of <= 128 rows (halo rows re-read: 2R / rows)
+struct StreamGrid { dim3 grid; int rows_per_chunk; int per_image; };
+static StreamGrid stream_grid(int B, int H, int W) {
+  StreamGrid g;
+  const int strips = (W + kStripW - 1) / kStripW;
+  int chunks = (H + 127) / 128;
+  // small images: split rows further so that at least ~2 blocks per SM exist (never below 32 rows per chunk)
+  while ((int64_t)strips * chunks * B < 2 * 148 && (H + chunks) / (chunks + 1) >= 32) ++chunks;
+  g.rows_per_chunk = (H + chunks - 1) / chunks;
+  chunks = (H + g.rows_per_chunk - 1) / g.rows_per_chunk;
+  g.grid = dim3(strips, chunks, B);
+  g.per_image = strips * chunks;
+  return g;
+}
+
 static Gauss11 make_gauss11() {
   // pytorch_ssim/__init__.py:8-10: exp(-(x-5)^2 / (2*1.5^2)) as python floats, stored to fp32, normalised in fp32
   Gauss11 w;
@@ -369,34 +543,28 @@ extern "C" int segmif_ssim_fwd(const float* img1, const float* img2, int B, int 
   SEGMIF_REQUIRE(B > 0 && H > 0 && W > 0, "ssim: empty input");
   SEGMIF_REQUIRE(!per_image || B <= 32, "ssim: per-image mode supports at most 32 images per call");
   static const Gauss11 win = make_gauss11();
-  dim3 grid((W + 31) / 32, (H + 31) / 32, B);
+  const StreamGrid sg = stream_grid(B, H, W);
   cudaStream_t st = as_stream(stream);
-  ssim_kernel<<<grid, 256, 0, st>>>(img1, img2, H, W, win, partial_area(workspace));
+  ssim_kernel<<<sg.grid, 128, 0, st>>>(img1, img2, H, W, sg.rows_per_chunk, win, partial_area(workspace));
   int rc = check_launch("segmif_ssim_fwd");
   if (rc) return rc;
-  const int per = grid.x * grid.y;
+  const int per = sg.per_image;
   if (per_image) return finish(workspace, B, per, 1, 0, 1.0 / ((double)H * W), out, st, "segmif_ssim_fwd");
   return finish(workspace, 1, per * B, 1, 0, 1.0 / ((double)B * H * W), out, st, "segmif_ssim_fwd");
 }
 
-static LapKernels make_lap_kernels() {
-  // lap_loss.py:39-60: fp32 exp of -(dx^2+dy^2)/(2*sigma^2), times 1/(2 pi sigma^2), normalised by its fp32 sum
-  LapKernels k;
+static LapTaps make_lap_taps() {
+  // lap_loss.py:39-60 builds exp(-(dx^2+dy^2)/(2 sigma^2)) / (2 pi sigma^2) on a (k,k) grid and divides by its sum; that is
+  // the outer product of e_i / sum(e) with e_i = exp(-(i - mean)^2 / (2 sigma^2)), sigma = 2 (the constant cancels)
+  LapTaps k;
   const int sizes[3] = {3, 5, 7};
-  float* dst[3] = {k.k3, k.k5, k.k7};
+  float* dst[3] = {k.g3, k.g5, k.g7};
   for (int s = 0; s < 3; ++s) {
     const int n = sizes[s];
-    const float mean = (n - 1) / 2.0f, var = 4.0f;
-    float sum = 0.f;
-    for (int y = 0; y < n; ++y)
-      for (int x = 0; x < n; ++x) {
-        const float d2 = (x - mean) * (x - mean) + (y - mean) * (y - mean);
-        const float e = expf(-d2 / (2.f * var));
-        const float v = (float)(1.0 / (2.0 * 3.14159265358979323846 * 4.0)) * e;
-        dst[s][y * n + x] = v;
-        sum += v;
-      }
-    for (int i = 0; i < n * n; ++i) dst[s][i] /= sum;
+    const double mean = (n - 1) / 2.0;
+    double e[7], sum = 0.0;
+    for (int i = 0; i < n; ++i) { e[i] = exp(-(i - mean) * (i - mean) / 8.0); sum += e[i]; }
+    for (int i = 0; i < n; ++i) dst[s][i] = (float)(e[i] / sum);
   }
   return k;
 }
@@ -405,26 +573,26 @@ extern "C" int segmif_laploss2_fwd(const float* inp, const float* ir, const floa
                                    float* workspace, float* out, segmif_stream_t stream) {
   SEGMIF_REQUIRE(inp && ir && vis && workspace && out, "laploss2: null pointer");
   SEGMIF_REQUIRE(B > 0 && H > 0 && W > 0, "laploss2: empty input");
-  static const LapKernels ker = make_lap_kernels();
-  dim3 grid((W + 31) / 32, (H + 31) / 32, B);
+  static const LapTaps ker = make_lap_taps();
+  const StreamGrid sg = stream_grid(B, H, W);
   cudaStream_t st = as_stream(stream);
-  laploss_kernel<3><<<grid, 256, 0, st>>>(inp, ir, vis, H, W, ker, partial_area(workspace));
+  laploss_kernel<3><<<sg.grid, 128, 0, st>>>(inp, ir, vis, H, W, sg.rows_per_chunk, ker, partial_area(workspace));
   int rc = check_launch("segmif_laploss2_fwd");
   if (rc) return rc;
-  return finish(workspace, 1, grid.x * grid.y * B, 3, 1, 1.0 / ((double)B * H * W), out, st, "segmif_laploss2_fwd");
+  return finish(workspace, 1, sg.per_image * B, 3, 1, 1.0 / ((double)B * H * W), out, st, "segmif_laploss2_fwd");
 }
 
 extern "C" int segmif_laploss_fwd(const float* inp, const float* target, int B, int H, int W, float* workspace,
                                   float* out, segmif_stream_t stream) {
   SEGMIF_REQUIRE(inp && target && workspace && out, "laploss: null pointer");
   SEGMIF_REQUIRE(B > 0 && H > 0 && W > 0, "laploss: empty input");
-  static const LapKernels ker = make_lap_kernels();
-  dim3 grid((W + 31) / 32, (H + 31) / 32, B);
+  static const LapTaps ker = make_lap_taps();
+  const StreamGrid sg = stream_grid(B, H, W);
   cudaStream_t st = as_stream(stream);
-  laploss_kernel<2><<<grid, 256, 0, st>>>(inp, target, nullptr, H, W, ker, partial_area(workspace));
+  laploss_kernel<2><<<sg.grid, 128, 0, st>>>(inp, target, nullptr, H, W, sg.rows_per_chunk, ker, partial_area(workspace));
   int rc = check_launch("segmif_laploss_fwd");
   if (rc) return rc;
-  return finish(workspace, 1, grid.x * grid.y * B, 3, 1, 1.0 / ((double)B * H * W), out, st, "segmif_laploss_fwd");
+  return finish(workspace, 1, sg.per_image * B, 3, 1, 1.0 / ((double)B * H * W), out, st, "segmif_laploss_fwd");
 }
 
 extern "C" int segmif_entropy_fwd(const float* img, int B, int H, int W, int patch, float* workspace, float* out,
@@ -454,12 +622,12 @@ extern "C" int segmif_sobel_l1_fwd(const float* x, const float* y, int B, int H,
   SEGMIF_REQUIRE(x && y && workspace && out, "sobel_l1: null pointer");
   SEGMIF_REQUIRE(B > 0 && H > 0 && W > 0, "sobel_l1: empty input");
   const int64_t n = (int64_t)B * H * W;
-  const int nblocks = (int)std::min<int64_t>(ceil_div(n, 256), 148 * 8);
+  const StreamGrid sg = stream_grid(B, H, W);
   cudaStream_t st = as_stream(stream);
-  sobel_l1_kernel<<<nblocks, 256, 0, st>>>(x, y, B, H, W, partial_area(workspace));
+  sobel_l1_kernel<<<sg.grid, 128, 0, st>>>(x, y, H, W, sg.rows_per_chunk, partial_area(workspace));
   int rc = check_launch("segmif_sobel_l1_fwd");
   if (rc) return rc;
-  return finish(workspace, 1, nblocks, 2, 3, 1.0 / (double)n, out, st, "segmif_sobel_l1_fwd");
+  return finish(workspace, 1, sg.per_image * B, 2, 3, 1.0 / (double)n, out, st, "segmif_sobel_l1_fwd");
 }
 
 extern "C" int segmif_mse_l1_fwd(const float* x, const float* y, int64_t n, float* workspace, float* out,

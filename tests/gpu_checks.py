@@ -391,7 +391,7 @@ def losses():
     fused = (0.6 * ir + 0.4 * vis).clamp(0, 1)
     rs.append(result("ssim_random", rel_err(ops.ssim(fused.to(DEV), mask.to(DEV)), O.ssim(fused, mask)), SSIM_TOL))
     rs.append(result("laploss2_random", rel_err(ops.laploss2(fused.to(DEV), ir.to(DEV), vis.to(DEV)), O.lap_loss2(fused, ir, vis)), 1e-5))
-    big = synth.synth_inputs(2, 64, 96, seed=6)["ir"]
+    big = synth.synth_inputs(2, 64, 112, seed=6)["ir"]              # 112 = 3.5 warps wide: a partly filled segment
     rs.append(result("entropy4_random", rel_err(ops.entropy(big.to(DEV), 4), O.entropy(big, 4)), 1e-5))
     rs.append(result("entropy16_random", rel_err(ops.entropy(big.to(DEV), 16), O.entropy(big, 16)), 1e-5))
     l1, lg = ops.sobel_l1(mask.to(DEV), fused.to(DEV))

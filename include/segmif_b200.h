@@ -102,6 +102,9 @@ typedef struct {
   int weight_kn;            /* 0: weight bf16 [N, K] (nn.Linear's own layout: y = x W^T).  1: weight bf16 [K, N] -- the SAME
                                buffer read as the operand of the data gradient dX = dY W (MN-major tcgen05 B operand), so
                                the backward needs no transposed copy of the weights; requires N % 64 == 0               */
+  const float* row_scale;   /* optional fp32 [ceil(M / rows_per_scale)]: dst = act(.) * row_scale[row / rows_per_scale] + residual
+                               -- timm DropPath in train mode (core/mix_transformer.py:129,152-153) fused into proj / fc2   */
+  int rows_per_scale;
 } segmif_linear_params;
 int segmif_linear_tc_fwd(const segmif_linear_params* p, segmif_stream_t stream);
 /* ---- K10/K11 on tcgen05: 3x3 stride-1 'same' convolution (dilation 1 or 2), Cout in {32, 64}, bf16 out ----------
@@ -396,6 +399,8 @@ int segmif_channel_affine_nchw(const float* x, const float* scale, const float* 
 int segmif_recompose_rgb_bwd(const float* rgb, const float* drgb, float* dfused, int clamp01, int B, int64_t HW,
                              segmif_stream_t stream);
 int segmif_cast(const void* x, int x_dtype, void* y, int y_dtype, int64_t n, segmif_stream_t stream);
+int segmif_scale_cast_rows(const float* x, const float* scale, void* y, int64_t rows, int64_t rows_per_sample, int C,
+                           segmif_stream_t stream);   /* y = bf16(scale[row / rows_per_sample] * x): DropPath branch gradient */
 int segmif_scale_add_rows(const float* x, const void* y, int y_dtype, const float* scale, float* out, int64_t rows,
                           int64_t rows_per_sample, int C, segmif_stream_t stream);
 

@@ -43,6 +43,7 @@ class LinearParams(ctypes.Structure):
         ("res_dtype", c_int), ("ld_res", c_int), ("res_coff", c_int),
         ("dst_dtype", c_int), ("ld_dst", c_int), ("dst_coff", c_int),
         ("weight_kn", c_int),
+        ("row_scale", c_void_p), ("rows_per_scale", c_int),
     ]
 
 
@@ -133,6 +134,7 @@ SIGNATURES = {
     "segmif_channel_affine_nchw": [P, P, P, P, c_int, c_int, c_int64, P],
     "segmif_recompose_rgb_bwd": [P, P, P, c_int, c_int, c_int64, P],
     "segmif_cast": [P, c_int, P, c_int, c_int64, P],
+    "segmif_scale_cast_rows": [P, P, P, c_int64, c_int64, c_int, P],
     "segmif_scale_add_rows": [P, P, c_int, P, P, c_int64, c_int64, c_int, P],
 }
 _RESTYPES = {"segmif_last_error": c_char_p, "segmif_loss_workspace_bytes": c_size_t, "segmif_wgrad_workspace_bytes": c_size_t,

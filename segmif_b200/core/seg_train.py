@@ -134,19 +134,14 @@ def _block_forward(blk, x, B, N, H, W, dp_scales):
     kv = ops.linear(src, at._packs.linear(at.kv.weight), at._b(at.kv))
     att, lse = ops.sr_attention_train(q, kv, B, heads, N, Nk, D, at.scale)
     s1, s2 = dp_scales
-    if s1 is None:
-        x2 = ops.linear(att, at._packs.linear(at.proj.weight), at.proj.bias.detach(), residual=x, out_dtype=F32)
-    else:
-        y = ops.linear(att, at._packs.linear(at.proj.weight), at.proj.bias.detach(), out_dtype=F32)
-        x2 = ops.scale_add_rows(x, y, s1, N)
+    # x2 = x + s1 * proj(att): the DropPath factor rides in the GEMM epilogue (row_scale), like the residual add
+    x2 = ops.linear_tc(att, at._packs.linear(at.proj.weight), at.proj.bias.detach(), residual=x, out_dtype=F32,
+                       row_scale=s1, rows_per_scale=N)
     n2 = ops.layernorm(x2, blk.norm2.weight.detach(), blk.norm2.bias.detach(), blk.norm2.eps)
     h1 = ops.linear(n2, ml._packs.linear(ml.fc1.weight), ml.fc1.bias.detach())
     h2 = ml.dwconv.forward_gelu(h1.view(B, N, -1), H, W).view(B * N, -1)
-    if s2 is None:
-        x3 = ops.linear(h2, ml._packs.linear(ml.fc2.weight), ml.fc2.bias.detach(), residual=x2, out_dtype=F32)
-    else:
-        y = ops.linear(h2, ml._packs.linear(ml.fc2.weight), ml.fc2.bias.detach(), out_dtype=F32)
-        x3 = ops.scale_add_rows(x2, y, s2, N)
+    x3 = ops.linear_tc(h2, ml._packs.linear(ml.fc2.weight), ml.fc2.bias.detach(), residual=x2, out_dtype=F32,
+                       row_scale=s2, rows_per_scale=N)
     sv.update(n1=n1, q=q, src=src, kv=kv, att=att, lse=lse, Nk=Nk, x2=x2, n2=n2, h1=h1, h2=h2, s1=s1, s2=s2)
     return x3, sv
 
@@ -237,7 +232,7 @@ def _block_backward(blk, sv, dx, B, N, g, pre):
     def branch_grad(scale):
         if scale is None:
             return ops.cast(dx, BF16)
-        return ops.cast(ops.scale_add_rows(torch.zeros_like(dx), dx, scale, N), BF16)
+        return ops.scale_cast_rows(dx, scale, N)
 
     # ---- Mix-FFN branch: x3 = x2 + s2 * fc2(gelu(dwconv(fc1(LN2(x2)))))
     dy = branch_grad(sv["s2"])

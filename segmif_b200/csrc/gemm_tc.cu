@@ -51,6 +51,8 @@ struct TcEpilogue {
   const void* res;
   void* dst;
   int M, N, act, res_dtype, ld_res, res_coff, dst_dtype, ld_dst, dst_coff;
+  const float* row_scale;      // optional: act(.) is multiplied by row_scale[row / rows_per_scale] before the residual add
+  int rows_per_scale;          // (timm DropPath in train mode: one 0 or 1/keep factor per sample)
 };
 
 // one output row (this thread) x 32 columns starting at n.  `slope`: act(v) = v >= 0 ? v : slope*v covers none (1),
@@ -74,7 +76,8 @@ __device__ __forceinline__ void load_res_row32(const TcEpilogue& e, ResRow32& r,
 }
 
 template <bool GELU>
-__device__ __forceinline__ void epilogue_row32(const TcEpilogue& e, float (&v)[32], const ResRow32& rr, int64_t m, int n, float slope) {
+__device__ __forceinline__ void epilogue_row32(const TcEpilogue& e, float (&v)[32], const ResRow32& rr, int64_t m, int n, float slope,
+                                               float rscale) {
   if (e.bias) {
     const float4* bp = reinterpret_cast<const float4*>(e.bias + n);
 #pragma unroll
@@ -89,6 +92,10 @@ __device__ __forceinline__ void epilogue_row32(const TcEpilogue& e, float (&v)[3
   } else {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = v[j] >= 0.f ? v[j] : slope * v[j];
+  }
+  if (e.row_scale) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= rscale;
   }
   if (e.res) {
     if (e.res_dtype == SEGMIF_F32) {
@@ -219,6 +226,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
       const int m0 = (tile / n_tiles) * 128, n0 = (tile % n_tiles) * BN;
       const int64_t m = (int64_t)m0 + quad * 32 + lane;
       const bool has_res = e.res != nullptr && m < e.M;
+      const float rscale = (e.row_scale != nullptr && m < e.M) ? e.row_scale[m / e.rows_per_scale] : 1.f;
       ResRow32 cur, nxt;
       if (has_res && n0 < e.N) load_res_row32(e, cur, m, n0);          // in flight while the MMAs of this tile finish
       tc::mbar_wait(tmem_full + buf, (lt >> 1) & 1);
@@ -228,7 +236,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         if (has_res && c + 32 < BN && (n0 + c + 32) < e.N) load_res_row32(e, nxt, m, n0 + c + 32);
         float v[32];
         tc::tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN + c), v);   // warp-collective
-        if (m < e.M && (n0 + c) < e.N) epilogue_row32<GELU>(e, v, cur, m, n0 + c, slope);
+        if (m < e.M && (n0 + c) < e.N) epilogue_row32<GELU>(e, v, cur, m, n0 + c, slope, rscale);
         cur = nxt;
       }
       tc::tc_fence_before();
@@ -304,6 +312,8 @@ static int linear_tc_impl(const segmif_linear_params* p, cudaStream_t st) {
   e.bias = p->bias; e.alpha = p->prelu_alpha; e.res = p->residual; e.dst = p->dst;
   e.M = p->M; e.N = p->N; e.act = p->act; e.res_dtype = p->res_dtype; e.ld_res = p->ld_res; e.res_coff = p->res_coff;
   e.dst_dtype = p->dst_dtype; e.ld_dst = p->ld_dst; e.dst_coff = p->dst_coff;
+  e.row_scale = p->row_scale; e.rows_per_scale = p->rows_per_scale > 0 ? p->rows_per_scale : 1;
+  SEGMIF_REQUIRE(!p->row_scale || p->rows_per_scale > 0, "linear_tc: row_scale needs rows_per_scale > 0");
   if (p->act == SEGMIF_ACT_GELU) {
     if (BN == 128) return launch_gemm_tc<128, true>(tmA, tmB, e, p->K, st);
     if (BN == 64) return launch_gemm_tc<64, true>(tmA, tmB, e, p->K, st);

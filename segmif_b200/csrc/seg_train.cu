@@ -494,6 +494,19 @@ __global__ void __launch_bounds__(256) scale_add_rows_kernel(const float* __rest
   }
 }
 
+// y[r, c] = bf16(scale[r / rows_per_sample] * x[r, c]): the branch gradient of a DropPath residual, cast for the GEMMs
+__global__ void __launch_bounds__(256) scale_cast_rows_kernel(const float* __restrict__ x, const float* __restrict__ scale,
+                                                              bf16* __restrict__ y, int64_t rows_per_sample, int C, int64_t n4) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    const float s = scale[(i * 4 / C) / rows_per_sample];
+    uint2 o;
+    o.x = pack_bf16x2(v.x * s, v.y * s);
+    o.y = pack_bf16x2(v.z * s, v.w * s);
+    reinterpret_cast<uint2*>(y)[i] = o;
+  }
+}
+
 }  // namespace segmif
 
 using namespace segmif;
@@ -629,6 +642,14 @@ extern "C" int segmif_cast(const void* x, int x_dtype, void* y, int y_dtype, int
   else if (x_dtype == SEGMIF_BF16 && y_dtype == SEGMIF_F32) cast_kernel<bf16, float><<<grid, 256, 0, st>>>((const bf16*)x, (float*)y, n);
   else { set_error("cast: unsupported dtype pair (%d -> %d)", x_dtype, y_dtype); return SEGMIF_ERR_INVALID; }
   return check_launch("segmif_cast");
+}
+
+extern "C" int segmif_scale_cast_rows(const float* x, const float* scale, void* y, int64_t rows, int64_t rows_per_sample, int C,
+                                      segmif_stream_t stream) {
+  SEGMIF_REQUIRE(x && scale && y && rows > 0 && rows_per_sample > 0 && C > 0 && C % 4 == 0, "scale_cast_rows: bad arguments");
+  const int64_t n4 = rows * C / 4;
+  scale_cast_rows_kernel<<<grid_n(n4, 1024), 256, 0, as_stream(stream)>>>(x, scale, (bf16*)y, rows_per_sample, C, n4);
+  return check_launch("segmif_scale_cast_rows");
 }
 
 extern "C" int segmif_scale_add_rows(const float* x, const void* y, int y_dtype, const float* scale, float* out,

@@ -160,9 +160,11 @@ def linear(x, weight, bias, *, act=ACT_NONE, residual=None, out_dtype=torch.bflo
 
 
 def _linear_params(x, weight, bias, M, N, K, ld_src, src_coff, act, prelu_alpha, residual, ld_res, res_coff, out, ld_dst,
-                   dst_coff, weight_kn=False):
+                   dst_coff, weight_kn=False, row_scale=None, rows_per_scale=0):
     p = _lib.LinearParams()
     p.weight_kn = 1 if weight_kn else 0
+    p.row_scale = row_scale.data_ptr() if row_scale is not None else None
+    p.rows_per_scale = int(rows_per_scale)
     p.src, p.weight = x.data_ptr(), weight.data_ptr()
     p.bias = bias.data_ptr() if bias is not None else None
     p.prelu_alpha = prelu_alpha.data_ptr() if prelu_alpha is not None else None
@@ -177,10 +179,11 @@ def _linear_params(x, weight, bias, M, N, K, ld_src, src_coff, act, prelu_alpha,
 
 
 def linear_tc(x, weight, bias, *, M=None, K=None, ld_src=None, src_coff=0, act=ACT_NONE, prelu_alpha=None, residual=None,
-              ld_res=None, res_coff=0, out=None, out_dtype=torch.bfloat16, ld_dst=None, dst_coff=0, weight_kn=False):
+              ld_res=None, res_coff=0, out=None, out_dtype=torch.bfloat16, ld_dst=None, dst_coff=0, weight_kn=False,
+              row_scale=None, rows_per_scale=0):
     """tcgen05 + TMA linear layer (segmif_linear_tc_fwd).  x bf16 [..., ld_src]; weight packed bf16 [N, 1, K], or with
     weight_kn the [K, 1, N] buffer -- a forward pack reused as the operand of the data gradient dX = dY W."""
-    st = _prep(x, weight, bias, prelu_alpha, residual, out)
+    st = _prep(x, weight, bias, prelu_alpha, residual, out, row_scale)
     if weight_kn:
         N = weight.shape[-1]
         K = weight.shape[0] if K is None else K
@@ -197,7 +200,7 @@ def linear_tc(x, weight, bias, *, M=None, K=None, ld_src=None, src_coff=0, act=A
     if residual is not None and ld_res is None:
         ld_res = residual.shape[-1]
     p = _linear_params(x, weight, bias, M, N, K, ld_src, src_coff, act, prelu_alpha, residual, ld_res, res_coff, out,
-                       ld_dst, dst_coff, weight_kn)
+                       ld_dst, dst_coff, weight_kn, row_scale, rows_per_scale)
     _lib.call("segmif_linear_tc_fwd", ctypes.byref(p), st)
     return out
 
@@ -753,6 +756,15 @@ def cast(x, dtype):
     st = _prep(x)
     y = torch.empty(x.shape, dtype=dtype, device=x.device)
     _lib.call("segmif_cast", _ptr(x), _dt(x), _ptr(y), _dt(y), x.numel(), st)
+    return y
+
+
+def scale_cast_rows(x, scale, rows_per_sample):
+    """bf16(scale[row // rows_per_sample] * x) for fp32 x [rows, C]."""
+    st = _prep(x, scale)
+    C = x.shape[-1]
+    y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    _lib.call("segmif_scale_cast_rows", _ptr(x), _ptr(scale), _ptr(y), x.numel() // C, rows_per_sample, C, st)
     return y
 
 

@@ -468,6 +468,14 @@ def encoder_training_kernels():
     s2 = torch.tensor([0.0, 1.0 / 0.9, 1.0])
     out = ops.scale_add_rows(xf.to(DEV), yb.bfloat16().to(DEV), s2.to(DEV), 100)
     res.append(result("scale_add_rows", rel_err(out, xf + s2.repeat_interleave(100)[:, None] * yb), 1e-6))
+    sc16 = ops.scale_cast_rows(xf.to(DEV), s2.to(DEV), 100)
+    res.append(result("scale_cast_rows", rel_err(sc16.float(), (s2.repeat_interleave(100)[:, None] * xf).bfloat16().float()), 0.0))
+    # DropPath factor in the GEMM epilogue: y = (x W^T + b) * s[row // rps] + residual
+    Wl, bl = rnd(128, 64, seed=21, scale=0.2), 0.1 * rnd(128, seed=22, bf16=False)
+    xin, resid = rnd(300, 64, seed=23), rnd(300, 128, seed=24, bf16=False)
+    yl = ops.linear_tc(xin.bfloat16().to(DEV), Wl.bfloat16().reshape(128, 1, 64).contiguous().to(DEV), bl.to(DEV), residual=resid.to(DEV),
+                       out_dtype=torch.float32, row_scale=s2.to(DEV), rows_per_scale=100)
+    res.append(result("linear_row_scale_residual", rel_err(yl, (xin @ Wl.t() + bl) * s2.repeat_interleave(100)[:, None] + resid), 1e-3))
     # LayerNorm backward accumulating into the residual-stream gradient
     x = rnd(100, 128, seed=12, bf16=False)
     dy = rnd(100, 128, seed=13)

@@ -420,10 +420,46 @@ __global__ void __launch_bounds__(256, 2) wgrad_lin_kernel(WgradArgs a, int64_t 
     }
 }
 
-// grad[co*s_co + tap*s_tap + ci*s_ci] += sum_chunk partial[chunk][co][tap][ci]   (fixed order)
+// grad[co*s_co + tap*s_tap + ci*s_ci] += sum_chunk partial[chunk][co][tap][ci]   (fixed order: deterministic)
+// A block reduces 32 consecutive outputs; its 8 warps split the chunks (warp w takes chunks w, w+8, ... with four
+// independent accumulators), then the 8 warp sums are added in warp order.  (One thread per output walking all chunks
+// serially was latency-bound: a 64x64 layer has 4096 outputs but ~300 chunks.)
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partials, int nchunk, int Cout, int NT,
                                                            int Cin, float* __restrict__ grad, int64_t s_co, int64_t s_tap,
                                                            int64_t s_ci, int co_take, int ci_take) {
+  __shared__ float ssum[8][32];
+  const int64_t n = (int64_t)Cout * NT * Cin;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t base = (int64_t)blockIdx.x * 32; base < n; base += (int64_t)gridDim.x * 32) {
+    const int64_t i = base + lane;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if (i < n) {
+      int c = warp;
+      for (; c + 24 < nchunk; c += 32) {
+        a0 += partials[(int64_t)c * n + i];
+        a1 += partials[(int64_t)(c + 8) * n + i];
+        a2 += partials[(int64_t)(c + 16) * n + i];
+        a3 += partials[(int64_t)(c + 24) * n + i];
+      }
+      for (; c < nchunk; c += 8) a0 += partials[(int64_t)c * n + i];
+    }
+    ssum[warp][lane] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (warp == 0 && i < n) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += ssum[w][lane];
+      const int ci = (int)(i % Cin), tp = (int)((i / Cin) % NT), co = (int)(i / ((int64_t)Cin * NT));
+      if (co < co_take && ci < ci_take) grad[co * s_co + tp * s_tap + ci * s_ci] += t;
+    }
+    __syncthreads();
+  }
+}
+
+// few chunks (wide layers: many outputs, each a short sum): one thread per output, coalesced, two accumulators
+__global__ void __launch_bounds__(256) wgrad_reduce_flat_kernel(const float* __restrict__ partials, int nchunk, int Cout, int NT,
+                                                                int Cin, float* __restrict__ grad, int64_t s_co, int64_t s_tap,
+                                                                int64_t s_ci, int co_take, int ci_take) {
   const int64_t n = (int64_t)Cout * NT * Cin;
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
     const int ci = (int)(i % Cin), t = (int)((i / Cin) % NT), co = (int)(i / ((int64_t)Cin * NT));
@@ -609,7 +645,10 @@ extern "C" int segmif_wgrad(const void* dy, int ldy, int coffy, const void* x, i
   int rc = check_launch("segmif_wgrad");
   if (rc) return rc;
   const int64_t n = (int64_t)Cout * taps * Cin;
-  wgrad_reduce_kernel<<<grid_for(n, 256), 256, 0, st>>>(workspace, nchunk, Cout, taps, Cin, grad, s_co, s_tap, s_ci, co_take, ci_take);
+  if (nchunk >= 32)
+    wgrad_reduce_kernel<<<grid_for(n, 32), 256, 0, st>>>(workspace, nchunk, Cout, taps, Cin, grad, s_co, s_tap, s_ci, co_take, ci_take);
+  else
+    wgrad_reduce_flat_kernel<<<grid_for(n, 256), 256, 0, st>>>(workspace, nchunk, Cout, taps, Cin, grad, s_co, s_tap, s_ci, co_take, ci_take);
   return check_launch("segmif_wgrad(reduce)");
 }
 

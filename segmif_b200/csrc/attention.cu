@@ -177,6 +177,8 @@ static int sr_attention_impl(const void* q, int ldq, const void* k, const void* 
   SEGMIF_REQUIRE(ldq % 8 == 0 && ldkv % 8 == 0 && ldo % 2 == 0, "sr_attention: pitches must be multiples of 8");
   SEGMIF_REQUIRE(Nk > 0, "sr_attention: Nk must be positive");
   if (B * heads == 0 || N == 0) return SEGMIF_OK;
+  if (sr_attention_tc_ok(B, heads, N, Nk, D, ldq, ldkv, ldo, q, k, v, out))
+    return sr_attention_tc(q, ldq, k, v, ldkv, out, ldo, B, heads, N, Nk, scale, lse, as_stream(stream));
   dim3 grid((unsigned)ceil_div(N, 64), (unsigned)(B * heads));
   const float sl2 = scale * 1.4426950408889634f;
   if (D == 64)

@@ -131,6 +131,12 @@ int64_t dwconv_tma_bwd_workspace(int B, int H, int W, int C);
 int dwconv_tma_gelu_bwd(const void* x, const float* w9c, const float* bias, const void* dy, void* dz, int B, int H, int W, int C,
                         float* dw9c, float* dbias, float* workspace, cudaStream_t st);
 
+// attention_tc.cu: spatial-reduction attention on tcgen05 (head dim 64, Nk <= 320)
+bool sr_attention_tc_ok(int B, int heads, int N, int Nk, int D, int ldq, int ldkv, int ldo, const void* q, const void* k, const void* v,
+                        const void* out);
+int sr_attention_tc(const void* q, int ldq, const void* k, const void* v, int ldkv, void* out, int ldo, int B, int heads, int N, int Nk,
+                    float scale, float* lse, cudaStream_t st);
+
 // wgrad_tc.cu: 3x3 weight gradients on tcgen05 (MN-major operands, accumulators resident in TMEM)
 bool wgrad_tc_ok(int B, int H, int W, int Cin, int Cout, int taps, int dil, int ldy, int ldx);
 int wgrad_tc_chunks(int B, int H, int W, int Cin, int Cout);

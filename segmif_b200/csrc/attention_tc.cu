@@ -228,7 +228,9 @@ int encode3(CUtensorMap* out, const void* base, int C, int rows, int ld, int B, 
 bool sr_attention_tc_ok(int B, int heads, int N, int Nk, int D, int ldq, int ldkv, int ldo, const void* q, const void* k, const void* v,
                         const void* out) {
   static int enabled = -1;
-  if (enabled < 0) { const char* e = getenv("SEGMIF_ATTN_TC"); enabled = (e && e[0] == '0') ? 0 : 1; }
+  // opt-in (SEGMIF_ATTN_TC=1) until it beats the mma.sync kernel in the whole step: its softmax runs on four warps per SM
+  // while the tensor pipe idles, and at cfg 2 the first measurement was 15.6 vs 15.2 ms/step
+  if (enabled < 0) { const char* e = getenv("SEGMIF_ATTN_TC"); enabled = (e && e[0] == '1') ? 1 : 0; }
   if (!enabled) return false;
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   return D == 64 && Nk >= 1 && Nk <= MAXKB * 64 && N >= 1 && ldq % 8 == 0 && ldkv % 8 == 0 && ldo % 8 == 0 && al16(q) && al16(k) &&
@@ -253,7 +255,8 @@ int sr_attention_tc(const void* q, int ldq, const void* k, const void* v, int ld
     cfg = true;
   }
   const int bhn = B * heads;
-  const int gx = std::max(1, std::min(a.q_tiles, (148 + bhn - 1) / bhn));
+  // one CTA per SM (193 KB of shared memory, all of TMEM): never more CTAs than SMs, or the tail CTAs run as a second wave
+  const int gx = std::max(1, std::min(a.q_tiles, 148 / bhn));
   sr_attention_tc_kernel<<<dim3(gx, bhn), kThreads, smem, st>>>(tmQ, tmK, tmV, a);
   return check_launch("segmif_sr_attention_fwd (tcgen05)");
 }

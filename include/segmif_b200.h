@@ -356,6 +356,10 @@ int segmif_adamw_step(float* param, const float* grad, float* exp_avg, float* ex
  * sr_attention_train_fwd  = segmif_sr_attention_fwd that also stores the per-row log-sum-exp (exp2 domain) [B*heads, N].
  * sr_attention_bwd        core/mix_transformer.py:107-111 backward: dq bf16 (same layout as q); dK / dV ADDED into the
  *                         fp32 accumulator dkv [B, Nk, lddkv] (dK at column h*D, dV at v_off + h*D); D = 64.          */
+/* The same contraction on tcgen05 (attention_tc.cu: S = QK^T in TMEM, per-row two-pass softmax, O = PV with V as an MN-major
+ * operand) for head dim 64 and Nk <= 320; segmif_sr_attention_fwd / _train_fwd use it when SEGMIF_ATTN_TC=1. lse may be NULL. */
+int segmif_sr_attention_tc_fwd(const void* q, int ldq, const void* k, const void* v, int ldkv, void* out, int ldo, int B,
+                               int heads, int N, int Nk, int D, float scale, float* lse, segmif_stream_t stream);
 int segmif_sr_attention_train_fwd(const void* q, int ldq, const void* k, const void* v, int ldkv, void* out, int ldo,
                                   int B, int heads, int N, int Nk, int D, float scale, float* lse, segmif_stream_t stream);
 int segmif_sr_attention_bwd(const void* q, int ldq, const void* k, const void* v, int ldkv, const void* out,

@@ -194,6 +194,15 @@ extern "C" int segmif_sr_attention_fwd(const void* q, int ldq, const void* k, co
   return sr_attention_impl(q, ldq, k, v, ldkv, out, ldo, B, heads, N, Nk, D, scale, nullptr, stream);
 }
 
+/* the tcgen05 kernel explicitly (head dim 64, Nk <= 320); lse may be NULL */
+extern "C" int segmif_sr_attention_tc_fwd(const void* q, int ldq, const void* k, const void* v, int ldkv, void* out, int ldo,
+                                          int B, int heads, int N, int Nk, int D, float scale, float* lse, segmif_stream_t stream) {
+  SEGMIF_REQUIRE(q && k && v && out, "sr_attention_tc: null pointer");
+  SEGMIF_REQUIRE(sr_attention_tc_supported(B, heads, N, Nk, D, ldq, ldkv, ldo, q, k, v, out),
+                 "sr_attention_tc: needs head dim 64, 1 <= Nk <= 320, 16-byte aligned pointers and pitches that are multiples of 8");
+  return sr_attention_tc(q, ldq, k, v, ldkv, out, ldo, B, heads, N, Nk, scale, lse, as_stream(stream));
+}
+
 extern "C" int segmif_sr_attention_train_fwd(const void* q, int ldq, const void* k, const void* v, int ldkv, void* out,
                                              int ldo, int B, int heads, int N, int Nk, int D, float scale, float* lse,
                                              segmif_stream_t stream) {

@@ -225,6 +225,13 @@ int encode3(CUtensorMap* out, const void* base, int C, int rows, int ld, int B, 
 
 }  // namespace
 
+bool sr_attention_tc_supported(int B, int heads, int N, int Nk, int D, int ldq, int ldkv, int ldo, const void* q, const void* k,
+                               const void* v, const void* out) {
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  return D == 64 && Nk >= 1 && Nk <= MAXKB * 64 && N >= 1 && ldq % 8 == 0 && ldkv % 8 == 0 && ldo % 8 == 0 && al16(q) && al16(k) &&
+         al16(v) && al16(out) && B * heads <= 65535 && B * heads >= 1;
+}
+
 bool sr_attention_tc_ok(int B, int heads, int N, int Nk, int D, int ldq, int ldkv, int ldo, const void* q, const void* k, const void* v,
                         const void* out) {
   static int enabled = -1;
@@ -232,9 +239,7 @@ bool sr_attention_tc_ok(int B, int heads, int N, int Nk, int D, int ldq, int ldk
   // while the tensor pipe idles, and at cfg 2 the first measurement was 15.6 vs 15.2 ms/step
   if (enabled < 0) { const char* e = getenv("SEGMIF_ATTN_TC"); enabled = (e && e[0] == '1') ? 1 : 0; }
   if (!enabled) return false;
-  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-  return D == 64 && Nk >= 1 && Nk <= MAXKB * 64 && N >= 1 && ldq % 8 == 0 && ldkv % 8 == 0 && ldo % 8 == 0 && al16(q) && al16(k) &&
-         al16(v) && al16(out) && B * heads <= 65535;
+  return sr_attention_tc_supported(B, heads, N, Nk, D, ldq, ldkv, ldo, q, k, v, out);
 }
 
 int sr_attention_tc(const void* q, int ldq, const void* k, const void* v, int ldkv, void* out, int ldo, int B, int heads, int N, int Nk,

@@ -132,6 +132,8 @@ int dwconv_tma_gelu_bwd(const void* x, const float* w9c, const float* bias, cons
                         float* dw9c, float* dbias, float* workspace, cudaStream_t st);
 
 // attention_tc.cu: spatial-reduction attention on tcgen05 (head dim 64, Nk <= 320)
+bool sr_attention_tc_supported(int B, int heads, int N, int Nk, int D, int ldq, int ldkv, int ldo, const void* q, const void* k,
+                               const void* v, const void* out);
 bool sr_attention_tc_ok(int B, int heads, int N, int Nk, int D, int ldq, int ldkv, int ldo, const void* q, const void* k, const void* v,
                         const void* out);
 int sr_attention_tc(const void* q, int ldq, const void* k, const void* v, int ldkv, void* out, int ldo, int B, int heads, int N, int Nk,

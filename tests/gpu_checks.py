@@ -268,6 +268,12 @@ def attention():
                                heads, N, Nk, D, D ** -0.5)
         # P is rounded to bf16 before the PV product and the output is bf16: bound = a few bf16 ulps
         rs.append(result(name, rel_err(got.float(), ref), 1.2e-2))
+        if D == 64 and Nk <= 320:                # the tcgen05 kernel explicitly (the default path is selected by SEGMIF_ATTN_TC)
+            got_tc, lse = ops.sr_attention_tc(q.bfloat16().reshape(B * N, C).to(DEV), kv.bfloat16().reshape(B * Nk, 2 * C).to(DEV), B,
+                                              heads, N, Nk, D, D ** -0.5, want_lse=True)
+            rs.append(result(name + "_tcgen05", rel_err(got_tc.float(), ref), 1.2e-2))
+            lse_ref = torch.logsumexp((qh @ kh.transpose(-2, -1)) * D ** -0.5, -1) * 1.4426950408889634      # exp2 domain
+            rs.append(result(name + "_tcgen05_lse", rel_err(lse.reshape(B, heads, N), lse_ref), 1e-3))
     return rs
 
 

@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(128) sr_attention_kernel(const bf16* __restric
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
       const float m_new = fmaxf(m_run[r], mx[r]);
-      corr[r] = exp2f(m_run[r] - m_new);       // m_run = -inf on the first tile -> 0
+      corr[r] = ex2_approx(m_run[r] - m_new);       // m_run = -inf on the first tile -> 0
       m_run[r] = m_new;
       l_run[r] *= corr[r];
     }
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(128) sr_attention_kernel(const bf16* __restric
     for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float p = exp2f(s[nt][j] - m_run[j >> 1]);
+        const float p = ex2_approx(s[nt][j] - m_run[j >> 1]);
         s[nt][j] = p;
         rs[j >> 1] += p;
       }

@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(kAbThreads) sr_attention_bwd_kernel(
         for (int e = 0; e < 2; ++e) {
           const int j = half * 2 + e;
           const bool live = rlive && (kbase + nt * 8 + e) < Nk;
-          const float p = live ? exp2f(s[nt][j] * scale_log2e - lrow[half]) : 0.f;
+          const float p = live ? ex2_approx(s[nt][j] * scale_log2e - lrow[half]) : 0.f;
           p2[e] = p;
           d2[e] = p * (dp[nt][j] - delta[half]) * scale;
           s[nt][j] = d2[e];                       // keep dS (fp32) for dQ

@@ -83,6 +83,13 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// 2^x through one MUFU.EX2 with flush-to-zero: exp2f() wraps the same instruction in denormal range fix-ups (3-4 extra
+// instructions per call) that softmax weights in (0, 1] never need; -inf -> +0
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
 __device__ __forceinline__ float apply_act(float v, int act, float alpha) {

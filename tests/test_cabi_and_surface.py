@@ -107,3 +107,41 @@ def test_optimizer_schedule_matches_reference_formula():
     assert abs(lrs[0] - 1e-3 * 1e-6) < 1e-12
     assert abs(lrs[5] - 1e-3 * (1 - (1 - 5 / 10) * (1 - 1e-6))) < 1e-12
     assert abs(lrs[20] - 1e-3 * (1 - 20 / 100)) < 1e-12
+
+
+def test_host_only_sizing_entry_points():
+    """Workspace / chunk sizing functions are pure host code: callable without a GPU, and their answers must be
+    consistent with what the kernels index (partials[chunk][Cout][taps][Cin], per-block depthwise partials)."""
+    from segmif_b200 import _lib
+    lib = _lib.load()
+    # wgrad: at least one chunk, never more chunks than 128-pixel tiles (3x3) / 64-pixel steps (linear)
+    for (B, H, W, Cin, Cout, taps, dil) in ((4, 480, 640, 64, 32, 9, 2), (1, 17, 23, 8, 64, 9, 1), (4, 480, 640, 224, 32, 9, 2),
+                                            (1, 8, 16, 192, 32, 9, 2)):
+        n = lib.segmif_wgrad_chunks(B, H, W, B * H * W, Cin, Cout, taps, dil)
+        tiles = B * ((H + 7) // 8) * ((W + 15) // 16)
+        assert 1 <= n <= tiles
+        assert lib.segmif_wgrad_workspace_bytes(n, Cout, taps, Cin) == n * Cout * taps * Cin * 4
+    for (P, K, N) in ((76800, 64, 64), (50, 64, 64), (1200, 512, 2048), (4800, 1280, 320)):
+        n = lib.segmif_wgrad_chunks(1, (P + 15) // 16, 16, P, K, N, 1, 1)
+        assert 1 <= n <= (P + 63) // 64
+    # depthwise backward: one partial row of 10*C floats per block
+    for (B, H, W, C) in ((4, 120, 160, 256), (1, 7, 9, 2048), (1, 9, 11, 40), (8, 15, 20, 2048)):
+        ws = lib.segmif_dwconv3x3_gelu_bwd_workspace(B, H, W, C)
+        assert ws > 0 and ws % (10 * C) == 0
+    assert lib.segmif_dwconv3x3_gelu_bwd_workspace(1, 8, 8, 12) == 0          # C % 8 != 0: rejected
+    assert lib.segmif_loss_workspace_bytes(2, 64, 96) >= 256 + 4096 * 3 * 4
+
+
+def test_argument_validation_fails_before_any_launch():
+    """Bad arguments are refused with a message by the entry points themselves (checked before the first CUDA call)."""
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import ctypes
+    from segmif_b200 import _lib
+    lib = _lib.load()
+    buf = (ctypes.c_float * 64)()
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    assert lib.segmif_confusion_matrix(p, p, 10, 100, p, None) != 0 and "num_classes" in _lib.last_error()
+    assert lib.segmif_colsum(p, 12, 0, 10, 12, p, None) != 0 and "multiples of 8" in _lib.last_error()
+    assert lib.segmif_sr_attention_tc_fwd(p, 64, p, p, 128, p, 64, 1, 1, 10, 400, 64, 0.125, None, None) != 0 \
+        and "Nk <= 320" in _lib.last_error()

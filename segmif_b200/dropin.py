@@ -6,7 +6,8 @@ or, from Python, before importing the script:
     import segmif_b200.dropin as d; d.install()
 
 Nothing in the scripts has to change; dataset / checkpoint paths inside them are of course still
-the reference's own.  omegaconf is not required by this package; if a script imports it, it must be installed."""
+the reference's own.  The scripts read configs/voc*.yaml through `OmegaConf.load`; when omegaconf is not installed a
+minimal stand-in (segmif_b200/utils/omegaconf_shim.py: load + attribute access) is registered under that name."""
 import importlib
 import runpy
 import sys
@@ -39,6 +40,11 @@ def install(force=False):
                 sys.modules[parent] = pmod
             if not hasattr(sys.modules[parent], child):
                 setattr(sys.modules[parent], child, mod)
+    if "omegaconf" not in sys.modules:
+        try:
+            importlib.import_module("omegaconf")
+        except ImportError:
+            sys.modules["omegaconf"] = importlib.import_module("segmif_b200.utils.omegaconf_shim")
     return sorted(_ALIASES)
 
 

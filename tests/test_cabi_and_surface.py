@@ -145,3 +145,29 @@ def test_argument_validation_fails_before_any_launch():
     assert lib.segmif_colsum(p, 12, 0, 10, 12, p, None) != 0 and "multiples of 8" in _lib.last_error()
     assert lib.segmif_sr_attention_tc_fwd(p, 64, p, p, 128, p, 64, 1, 1, 10, 400, 64, 0.125, None, None) != 0 \
         and "Nk <= 320" in _lib.last_error()
+
+
+def test_configs_load_through_the_dropin_omegaconf():
+    """configs/voc*.yaml (the reference's schema) load through `OmegaConf.load` exactly as train.py:25 / test_fusion.py:44
+    do, with or without the real omegaconf: attribute access, list values, and the exponent-only floats ('1e-6') that
+    OmegaConf reads as numbers."""
+    import glob
+    import sys
+    import segmif_b200.dropin as d
+    had = sys.modules.get("omegaconf")
+    try:
+        d.install()
+        from omegaconf import OmegaConf
+        paths = sorted(glob.glob(os.path.join(ROOT, "configs", "voc*.yaml")))
+        assert paths
+        for path in paths:
+            cfg = OmegaConf.load(path)
+            assert cfg.exp.backbone.startswith("mit_b")
+            assert isinstance(cfg.dataset.num_classes, int) and cfg.dataset.ignore_index == 255
+            assert len(cfg.optimizer.betas) == 2 and abs(cfg.optimizer.betas[0] - 0.9) < 1e-12
+            assert isinstance(cfg.optimizer.learning_rate, float) and 0 < cfg.optimizer.learning_rate < 1e-2
+            assert isinstance(cfg.scheduler.warmup_ratio, float) and cfg.scheduler.warmup_ratio in (1e-6, 1e-4)
+            assert cfg.train.samples_per_gpu // 2 >= 1 and cfg.train.max_iters > 0            # train.py:138,197
+    finally:
+        if had is None:
+            sys.modules.pop("omegaconf", None)

@@ -51,7 +51,9 @@ def install(force=False):
 if __name__ == "__main__":
     if len(sys.argv) < 2:
         raise SystemExit(__doc__)
+    import os
     install()
     script = sys.argv[1]
     sys.argv = sys.argv[1:]
+    sys.path.insert(0, os.path.dirname(os.path.abspath(script)))     # `python script.py` semantics: sibling modules importable
     runpy.run_path(script, run_name="__main__")

@@ -171,3 +171,30 @@ def test_configs_load_through_the_dropin_omegaconf():
     finally:
         if had is None:
             sys.modules.pop("omegaconf", None)
+
+
+def test_dropin_runs_a_script_with_the_reference_import_lines(tmp_path):
+    """`python -m segmif_b200.dropin script.py` with the import statements of the reference's entry scripts
+    (train.py:18,25,111-112, test_fusion.py:9,16,30,44): sibling modules of the script resolve (python script.py semantics),
+    `core.*` / `pytorch_ssim` / `lap_loss` / `utils.optimizer` / `omegaconf` resolve to the mirror, the config loads."""
+    import subprocess
+    import sys
+    (tmp_path / "TaskFusion_dataset2.py").write_text("class Fusion_dataset:\n    pass\n")
+    (tmp_path / "configs").mkdir()
+    (tmp_path / "configs" / "voc.yaml").write_text(open(os.path.join(ROOT, "configs", "voc.yaml")).read())
+    (tmp_path / "entry.py").write_text(
+        "from core.model_fusion import Mean, Network3, Fusion_Network3_ac\n"
+        "from core import Total_fusion_loss, Total_fusion_loss2, RGB2YCrCb, Fusionloss, Fusionloss_add, Fusionloss2, Fusionloss3, Fusionloss4, Fusionloss_grad3\n"
+        "from core.model_fusion import RGB2YCrCb as R2, YCrCb2RGB\n"
+        "from TaskFusion_dataset2 import Fusion_dataset\n"
+        "from utils.optimizer import PolyWarmupAdamW, PolyWarmupAdamW_seg\n"
+        "import pytorch_ssim, lap_loss\n"
+        "from omegaconf import OmegaConf\n"
+        "cfg = OmegaConf.load('configs/voc.yaml')\n"
+        "m = Network3(cfg.exp.backbone, cfg.dataset.num_classes, 256, None)\n"
+        "print('DROPIN_OK', cfg.exp.backbone, sum(p.numel() for p in m.parameters()))\n")
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, "-m", "segmif_b200.dropin", "entry.py"], cwd=str(tmp_path), env=env, capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "DROPIN_OK mit_b3 44604" in r.stdout.replace(",", ""), r.stdout        # 44.605 M parameters (SURVEY.md App. C)

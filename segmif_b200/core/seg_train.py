@@ -379,18 +379,20 @@ class SegNetFn(torch.autograd.Function):
         dev = dlogits.device
         B = ctx.etape["B"]
         lookup = dict(net3.named_parameters())
-        # A parameter whose .grad already exists (ddp.FlatParams pre-allocates them as views of one flat buffer) gets its
-        # gradient accumulated IN PLACE by the kernels (they all add into their output) and None is returned for it:
-        # saves a zero-fill, an AccumulateGrad add and 2x the parameter bytes of traffic per tensor.  The others share
-        # one zero-filled scratch buffer (a single fill instead of one per tensor).
+        # A parameter owned by ddp.FlatParams (which pre-allocates its .grad as a view of one flat buffer and marks it with
+        # _segmif_epoch) gets its gradient accumulated IN PLACE by the kernels (they all add into their output) and None
+        # is returned for it: saves a zero-fill, an AccumulateGrad add and 2x the parameter bytes of traffic per tensor.
+        # Everything else goes through autograd's own accumulation (so hooks, e.g. of torch's DistributedDataParallel,
+        # still fire) out of one zero-filled scratch buffer (a single fill instead of one per tensor).
         g = _Grads()
         g.frozen = not any(ctx.needs_input_grad[4:])
         direct, pending = {}, []
         for i, n in enumerate(ctx.names):
             p = lookup[n]
             pg = p.grad
-            if ctx.needs_input_grad[4 + i] and pg is not None and pg.dtype == F32 and pg.is_contiguous() and pg.device == dev \
-                    and not torch.is_grad_enabled() and pg.shape == p.shape:
+            if ctx.needs_input_grad[4 + i] and getattr(p, "_segmif_epoch", None) is not None and pg is not None \
+                    and pg.dtype == F32 and pg.is_contiguous() and pg.device == dev and not torch.is_grad_enabled() \
+                    and pg.shape == p.shape:
                 g[n] = pg
                 direct[n] = True
             else:

@@ -203,6 +203,8 @@ class FusionTrainer(_GraphedStep):
 
     def _images_body(self, ir, vis_rgb, mask, labels=None):
         from .core.model_fusion import RGB2YCrCb
+        if self.seg_net is None:
+            raise ValueError("FusionTrainer.step_images needs seg_net (the frozen Network3 whose encoder provides out0 / out1)")
         with torch.no_grad():
             vis = RGB2YCrCb(vis_rgb)                                                            # train.py:356
             out0, out1 = self.seg_net.denoise_net.encoder.forward_fusion(mask)                  # train.py:358-359

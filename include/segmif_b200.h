@@ -11,7 +11,9 @@
  *  - plain pointers + sizes only; all pointers are DEVICE pointers unless stated otherwise;
  *    no allocation, no synchronisation and no global state inside (outputs and workspaces are
  *    caller allocated); every launch goes to the stream passed in (a cudaStream_t cast to void*),
- *    which must be the stream the caller orders its other work on.
+ *    which must be the stream the caller orders its other work on.  (The only process-wide state: one-time
+ *    cudaFuncSetAttribute opt-ins to large dynamic shared memory, and the read-once diagnostic switches
+ *    SEGMIF_WGRAD_TC / SEGMIF_ATTN_TC listed in INTEGRATION.md section 6.)
  *  - return value: 0 on success, negative SEGMIF_ERR_* otherwise; segmif_last_error() returns a
  *    thread-local message for the last failure.
  *  - "tokens"/NHWC: activations are pixel-major [B, H, W, C] (equivalently [B, N, C] tokens, the

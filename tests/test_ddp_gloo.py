@@ -147,3 +147,42 @@ def test_grouped_schedule_matches_reference_seg_optimizer():
         for i, base in enumerate((6e-5, 6e-5, 6e-4)):
             lrs[i] = poly_warmup_lr(base, step, 10, 40, 1e-6, 1.0, lrs[i])
             assert abs(lrs[i] - opt.param_groups[i]["lr"]) < 1e-15, (i, step)
+
+
+def test_fused_optimizer_host_logic_with_a_stub_kernel(monkeypatch):
+    """FusedPolyWarmupAdamW's host side (per-group schedule, contiguous ranges, bias-correction step count, pack-epoch
+    bump) with the CUDA kernel replaced by a recorder -- the kernel itself is checked on the GPU."""
+    from segmif_b200 import ops
+    from segmif_b200.core.model_fusion import Network3
+    from segmif_b200.ddp import FlatParams, FusedPolyWarmupAdamW, poly_warmup_lr
+    calls = []
+    monkeypatch.setattr(ops, "adamw_step", lambda param, grad, m, v, **kw: calls.append((param.data_ptr(), param.numel(), kw)))
+    net = Network3("mit_b0", 9, 256, None)
+    gid = lambda k: 2 if ".decoder." in k else (1 if "norm" in k.split("encoder.", 1)[-1] else 0)
+    flat = FlatParams(net, used=lambda k: not k.endswith("classifier.weight"), group_of=gid)
+    opt = FusedPolyWarmupAdamW(flat, 6e-5, 0.01, (0.9, 0.999), warmup_iter=4, max_iter=50, warmup_ratio=1e-6, power=1.0,
+                               groups={0: dict(lr=6e-5, weight_decay=0.01), 1: dict(lr=6e-5, weight_decay=0.0),
+                                       2: dict(lr=6e-4, weight_decay=0.01)}, iter_curr=3)
+    epoch0 = flat.epoch[0]
+    lrs = [6e-5, 6e-5, 6e-4]
+    for it in range(3):
+        calls.clear()
+        opt.step(grad_scale=0.5)
+        assert len(calls) == 3                                              # one launch per param group
+        covered = 0
+        for gi, (ptr, n, kw) in enumerate(calls):
+            lo, hi = flat.group_ranges[gi]
+            assert ptr == flat.param.data_ptr() + 4 * lo and n == hi - lo
+            lrs[gi] = poly_warmup_lr((6e-5, 6e-5, 6e-4)[gi], 3 + it, 4, 50, 1e-6, 1.0, lrs[gi])
+            assert abs(kw["lr"] - lrs[gi]) < 1e-18
+            assert kw["weight_decay"] == (0.01, 0.0, 0.01)[gi] and kw["grad_scale"] == 0.5
+            assert kw["step"] == it + 1                                     # AdamW's own step count starts at 1 (not iter_curr)
+            covered += n
+        assert covered == flat.numel
+    assert flat.epoch[0] == epoch0 + 3 and opt.global_step == 6
+    # a parameter owned by the flat buffer reports a new pack epoch after every optimizer step
+    from segmif_b200.packing import _epoch
+    p0 = flat.named[0][1]
+    e = _epoch(p0)
+    opt.step()
+    assert _epoch(p0) != e

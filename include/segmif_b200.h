@@ -410,6 +410,76 @@ int segmif_scale_cast_rows(const float* x, const float* scale, void* y, int64_t 
 int segmif_scale_add_rows(const float* x, const void* y, int y_dtype, const float* scale, float* out, int64_t rows,
                           int64_t rows_per_sample, int C, segmif_stream_t stream);
 
+/* ============================================================================================================
+ * Strict-precision (fp32-parity) mode.  The reference computes everything in fp32; north_star asks
+ * for <= 1e-3 relative end to end and bit-exact argmax labels (test_segmentation.py:169-175).  In this mode activations
+ * stay fp32 in HBM; an operand of a tensor-core contraction is its 3-way bf16 split  a = a0 + a1 + a2  stored as three
+ * planes, and the contraction evaluates the six partial products of order <= 2^-16 with kind::f16 tcgen05 MMAs into a
+ * main and a correction TMEM accumulator (csrc/gemm_split_tc.cu).  The same call sites as above are replaced:
+ *   segmif_split_gemm_fwd      nn.Linear / 1x1 conv (row mode: the call sites listed at segmif_linear_tc_fwd) and the
+ *                              3x3 / dilated 3x3 nn.Conv2d of core/model_fusion.py:135-151, :1063-1064 (patch mode,
+ *                              ntaps = 9; tap_dx / tap_dy = (kx - 1) * dil, (ky - 1) * dil; zero padding by TMA);
+ *                              im2col rows from segmif_im2col_split3 serve core/mix_transformer.py:193 (patch_embed2-4)
+ *                              and :100 (Attention.sr).
+ *   dst[m, n] = residual[m, n] + act(bias[n] + sum_{tap, k} A[pix(m, tap), k] * W[n, tap, k])
+ * ============================================================================================================ */
+typedef struct {
+  const void* a_planes;      /* bf16; plane p starts a_plane_stride ELEMENTS after plane p-1; pixel-major, pitch ld_a     */
+  int64_t a_plane_stride;
+  const void* w_planes;      /* bf16 [N][ntaps][3][Kp], Kp = 64 * ceil(K / 64), zero padded (segmif_split3 builds it)     */
+  const float* bias;         /* fp32 [N] or NULL                                                                          */
+  const float* prelu_alpha;  /* device scalar (PReLU only)                                                                */
+  const float* residual;     /* fp32 [M, ld_res] or NULL, added after the activation                                      */
+  float* dst;                /* fp32 [M, ld_dst] or NULL                                                                  */
+  void* dst_planes;          /* bf16 split of the same result, three planes dst_plane_stride apart, or NULL               */
+  int64_t dst_plane_stride;
+  int M, N, K, ld_a, a_coff;
+  int act;                   /* SEGMIF_ACT_NONE | RELU | PRELU                                                            */
+  int ld_res, res_coff, ld_dst, dst_coff, ld_dp, dp_coff;
+  int nterms;                /* 6: fp32-grade product, 3: two planes (2^-16), 1: plain bf16                               */
+  int B, H, W;               /* patch mode (ntaps > 0): A is [B, H, W, ld_a] and M = B*H*W; row mode: ignored             */
+  int ntaps;                 /* 0 = row mode                                                                              */
+  int tap_dx[9], tap_dy[9];
+} segmif_split_gemm_params;
+int segmif_split_gemm_fwd(const segmif_split_gemm_params* p, segmif_stream_t stream);
+/* x fp32 slice [rows, C] (pitch ld_x, offset coff_x) -> optional ReLU -> y fp32 slice (may alias x, may be NULL) and / or
+ * three bf16 planes (planes + p * plane_stride)[r * ld_p + coff_p + c].  Also packs weights: rows = N * ntaps, ld_p = 3 * Kp,
+ * plane_stride = Kp over a zero-initialised buffer.                                                                      */
+int segmif_split3(const float* x, int ld_x, int coff_x, int64_t rows, int C, int relu, float* y, int ld_y, int coff_y,
+                  void* planes, int ld_p, int coff_p, int64_t plane_stride, segmif_stream_t stream);
+/* im2col of fp32 pixel-major x [B, H, W, ld_x] (C channels at coff_x) for a k x k / stride / pad convolution, written
+ * directly as split planes [3][B*Ho*Wo][k*k*C], column (ky*k + kx)*C + c (core/mix_transformer.py:100,193).              */
+int segmif_im2col_split3(const float* x, int ld_x, int coff_x, int B, int H, int W, int C, int k, int stride, int pad,
+                         void* planes, int64_t plane_stride, segmif_stream_t stream);
+/* core/mix_transformer.py:107-111 on fp32 q [B,N,ldq], k / v [B,Nk,ldkv] -> out fp32 [B,N,ldo]; D in {32, 64}.          */
+int segmif_sr_attention_f32_fwd(const float* q, int ldq, const float* k, const float* v, int ldkv, float* out, int ldo,
+                                int B, int heads, int N, int Nk, int D, float scale, segmif_stream_t stream);
+/* core/mix_transformer.py:381-387 (+ :49 when gelu != 0) on fp32 tokens [B,H,W,C]; w fp32 [9][C].                         */
+int segmif_dwconv3x3_f32_fwd(const float* x, const float* w9c, const float* bias, float* y, int B, int H, int W, int C,
+                             int gelu, segmif_stream_t stream);
+/* K13 pass 1 in strict mode: partials double [B, nchunk, 64, 64] of P^T P over the pixels of each image, P = the fp32
+ * 64-channel slice p[.., coff..coff+64) (optionally ReLU'd); pass 2: segmif_ffm_ctx_f64_fwd takes partials
+ * [3][B][nchunk][64][64] and produces ctx fp32 [B,3,8,8,8] and the folded matrices fp32 [B,4,64,64] (fp64 inside).       */
+int segmif_gram64_f64(const float* p, int ld, int coff, int B, int64_t HW, int relu, double* partials, int nchunk,
+                      segmif_stream_t stream);
+int segmif_ffm_ctx_f64_fwd(const double* partials, int nchunk, const float* wkv, const float* wend, float* folded,
+                           float* ctx_out, int B, segmif_stream_t stream);
+/* conv1_ir / conv1_vis / conv22 (core/model_fusion.py:1051-1056,1065) with fp32 pixel-major activations.                 */
+int segmif_conv3x3_in1_f32_fwd(const float* plane, int64_t bstride, const float* w, const float* bias,
+                               const float* prelu_alpha, float* dst, int ld_dst, int dst_coff, int B, int H, int W,
+                               int Cout, segmif_stream_t stream);
+int segmif_conv3x3_out1_f32_fwd(const float* src, int ld_src, const float* w, const float* bias, const float* prelu_alpha,
+                                float* dst, int B, int H, int W, int Cin, segmif_stream_t stream);
+
+/* ---- map-valued loss pieces (core/loss.py:634-650 Sobelxy.forward and the composites that use its MAP: Fusionloss :423-439,
+ * Fusionloss4 / Fusionloss_add :545-580, new_loss_sobel :389-399, IQALoss :605-633).  fp32 planes [B,1,H,W].
+ * sobel_map: out = |Gx| + |Gy| (zero padding); sobel_map_bwd: dx (+)= d/dx of sum(dout * sobel_map(x)), sign(0) = 0.
+ * ew2: mode 0: a*x + b*y;  1: max(x, y);  2: |a + b*x| (y may be NULL);  3: x*y;  4: b * sign(a + b*x) * y.        */
+int segmif_sobel_map_fwd(const float* x, float* out, int B, int H, int W, segmif_stream_t stream);
+int segmif_sobel_map_bwd(const float* x, const float* dout, float* dx, int B, int H, int W, int accumulate,
+                         segmif_stream_t stream);
+int segmif_ew2(const float* x, const float* y, float a, float b, int mode, float* out, int64_t n, segmif_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -387,6 +387,55 @@ def fusionloss_grad2(ir, vis, fused, mask):
     return F.l1_loss(m, fused) + 0.1 * lap_loss2(fused, vis[:, :1], ir[:, :1]) + 1.1 * (1 - ssim(fused, m))
 
 
+def fusionloss(ir, vis, fused):
+    """core/loss.py:423-439 -- L1(max(vis_y, ir), fused) + 8 * L1(max(sobel(vis_y), sobel(ir)), sobel(fused))."""
+    y, i = vis[:, :1], ir[:, :1]
+    return F.l1_loss(torch.max(y, i), fused) + 8 * F.l1_loss(torch.max(sobelxy(y), sobelxy(i)), sobelxy(fused))
+
+
+def fusionloss4(ir, vis, fused, mask):
+    """core/loss.py:545-559 -- L1((vis_y + ir) / 2, fused) + 4 * L1(sobel((vis_y + ir) / 2), sobel(fused))."""
+    syn = (vis[:, :1] + ir[:, :1]) / 2
+    return F.l1_loss(syn, fused) + 4 * F.l1_loss(sobelxy(syn), sobelxy(fused))
+
+
+def fusionloss_add(ir, vis, fused):
+    """core/loss.py:561-577 -- 1.5 * L1(0.4 vis_y + 0.6 ir, fused) + 5 * L1(max(sobel(vis_y), sobel(ir)), sobel(fused))."""
+    y, i = vis[:, :1], ir[:, :1]
+    return 1.5 * F.l1_loss(y * 0.4 + i * 0.6, fused) + 5 * F.l1_loss(torch.max(sobelxy(y), sobelxy(i)), sobelxy(fused))
+
+
+def new_loss_sobel(ir, vis, mask_ir, fused):
+    """core/loss.py:386-399, INCLUDING the rebinding of mask_ir / mask_vis to the scalar MSE terms (:394-395) that
+    then scale the Sobel maps (:396-397)."""
+    mask_vis = torch.abs(1 - mask_ir)
+    a = F.mse_loss(mask_ir * fused, mask_ir * ir)
+    v = F.mse_loss(mask_vis * fused, mask_vis * vis)
+    a2 = F.mse_loss(a * sobelxy(fused), a * sobelxy(ir))
+    v2 = F.mse_loss(v * sobelxy(fused), v * sobelxy(vis))
+    return (v + v2) * 1.0 + (a + a2) * 0.85
+
+
+def total_fusion_loss(ir, vis, mask, fused):
+    """core/loss.py:578-588."""
+    y, i = vis[:, :1], ir[:, :1]
+    return fusionloss(i, y, fused) * 1.2 + new_loss_sobel(i, y, mask, fused) * 0.85
+
+
+def total_fusion_loss2(ir, vis, mask, fused):
+    """core/loss.py:591-599."""
+    return new_loss_sobel(ir[:, :1], vis[:, :1], mask, fused)
+
+
+def iqa_loss(lr, vis, mask):
+    """core/loss.py:610-633 -- the entropy / std softmax weights (:616-626) are computed and never used."""
+    lr, vis, mask = lr[:, 0:1], vis[:, 0:1], mask[:, 0:1]
+    inv = torch.abs(1 - mask)
+    mse = 0.5 * F.mse_loss(lr, mask) + 0.5 * F.mse_loss(vis, inv)
+    grad = 0.5 * F.mse_loss(sobelxy(lr), sobelxy(mask)) + 0.5 * F.mse_loss(sobelxy(vis), sobelxy(inv))
+    return mse + grad
+
+
 # ----------------------------------------------------------------------------- whole pipeline
 
 

@@ -58,6 +58,22 @@ class DrdbPushParams(ctypes.Structure):
                 ("slab_offset", c_int), ("slab_width", c_int), ("n_out", c_int), ("groups", DrdbPushGroup * 4)]
 
 
+class SplitGemmParams(ctypes.Structure):
+    """Mirror of segmif_split_gemm_params."""
+    _fields_ = [
+        ("a_planes", c_void_p), ("a_plane_stride", c_int64), ("w_planes", c_void_p), ("bias", c_void_p),
+        ("prelu_alpha", c_void_p), ("residual", c_void_p), ("dst", c_void_p), ("dst_planes", c_void_p),
+        ("dst_plane_stride", c_int64),
+        ("M", c_int), ("N", c_int), ("K", c_int), ("ld_a", c_int), ("a_coff", c_int),
+        ("act", c_int),
+        ("ld_res", c_int), ("res_coff", c_int), ("ld_dst", c_int), ("dst_coff", c_int), ("ld_dp", c_int), ("dp_coff", c_int),
+        ("nterms", c_int),
+        ("B", c_int), ("H", c_int), ("W", c_int),
+        ("ntaps", c_int),
+        ("tap_dx", c_int * 9), ("tap_dy", c_int * 9),
+    ]
+
+
 P = c_void_p
 # name -> argtypes; every function returns int except where noted in _RESTYPES
 SIGNATURES = {
@@ -137,6 +153,18 @@ SIGNATURES = {
     "segmif_cast": [P, c_int, P, c_int, c_int64, P],
     "segmif_scale_cast_rows": [P, P, P, c_int64, c_int64, c_int, P],
     "segmif_scale_add_rows": [P, P, c_int, P, P, c_int64, c_int64, c_int, P],
+    "segmif_sobel_map_fwd": [P, P, c_int, c_int, c_int, P],
+    "segmif_sobel_map_bwd": [P, P, P, c_int, c_int, c_int, c_int, P],
+    "segmif_ew2": [P, P, c_float, c_float, c_int, P, c_int64, P],
+    "segmif_split_gemm_fwd": [ctypes.POINTER(SplitGemmParams), P],
+    "segmif_split3": [P, c_int, c_int, c_int64, c_int, c_int, P, c_int, c_int, P, c_int, c_int, c_int64, P],
+    "segmif_im2col_split3": [P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int64, P],
+    "segmif_sr_attention_f32_fwd": [P, c_int, P, P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P],
+    "segmif_dwconv3x3_f32_fwd": [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P],
+    "segmif_gram64_f64": [P, c_int, c_int, c_int, c_int64, c_int, P, c_int, P],
+    "segmif_ffm_ctx_f64_fwd": [P, c_int, P, P, P, P, c_int, P],
+    "segmif_conv3x3_in1_f32_fwd": [P, c_int64, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P],
+    "segmif_conv3x3_out1_f32_fwd": [P, c_int, P, P, P, P, c_int, c_int, c_int, c_int, P],
 }
 _RESTYPES = {"segmif_last_error": c_char_p, "segmif_loss_workspace_bytes": c_size_t, "segmif_wgrad_workspace_bytes": c_size_t,
              "segmif_dwconv3x3_gelu_bwd_workspace": c_int64}

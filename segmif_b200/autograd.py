@@ -135,3 +135,63 @@ def mse_l1(x, y):
 
 def sobel_l1(x, y):
     return SobelL1Fn.apply(x, y)
+
+
+class SobelMapFn(torch.autograd.Function):
+    """core/loss.py:647-650 Sobelxy.forward as a map, with its backward (sign maps re-derived from x)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = x.float().contiguous()
+        ctx.save_for_backward(x)
+        return ops.sobel_map(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return ops.sobel_map_bwd(x, g.float().contiguous())
+
+
+class MulDataFn(torch.autograd.Function):
+    """x * data (gradient to x only): the mask products of new_loss_sobel (core/loss.py:394-397)."""
+
+    @staticmethod
+    def forward(ctx, x, data):
+        data = data.float().contiguous()
+        ctx.save_for_backward(data)
+        return ops.ew2(x, data, ops.EW_MUL)
+
+    @staticmethod
+    def backward(ctx, g):
+        _no_second(ctx, 1)
+        (data,) = ctx.saved_tensors
+        return ops.ew2(g, data, ops.EW_MUL), None
+
+
+class AbsAffineFn(torch.autograd.Function):
+    """|a + b*x| (torch.abs(1 - mask), core/loss.py:392,615)."""
+
+    @staticmethod
+    def forward(ctx, x, a, b):
+        x = x.float().contiguous()
+        ctx.save_for_backward(x)
+        ctx.ab = (a, b)
+        return ops.ew2(x, None, ops.EW_ABS_AFFINE, a, b)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        a, b = ctx.ab
+        return ops.ew2(x, g, ops.EW_ABS_AFFINE_BWD, a, b), None, None
+
+
+def sobel_map(x):
+    return SobelMapFn.apply(x)
+
+
+def mul_data(x, data):
+    return MulDataFn.apply(x, data)
+
+
+def abs_affine(x, a, b):
+    return AbsAffineFn.apply(x, a, b)

@@ -8,7 +8,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops  # noqa: F401
-from ..autograd import mse_l1, sobel_l1
+from ..autograd import abs_affine, mse_l1, mul_data, sobel_l1, sobel_map
 from ..lap_loss import LapLoss, LapLoss2
 from ..pytorch_ssim import ssim
 from .Entropy import Entropy
@@ -20,15 +20,18 @@ def _y(t):
 
 
 class Sobelxy(nn.Module):
-    """core/loss.py:634-650: |Gx| + |Gy| with zero padding.  Exposed for API parity; the composites below use
-    the fused Sobel+L1 reduction instead of materialising gradient maps."""
+    """core/loss.py:634-650: |Gx| + |Gy| with zero padding, as a map (one kernel; backward registered).  The live
+    composites (Fusionloss3) use the fused Sobel+L1 reduction instead of materialising gradient maps."""
 
     def __init__(self):
         super().__init__()
+        kernelx = torch.tensor([[-1., 0., 1.], [-2., 0., 2.], [-1., 0., 1.]]).view(1, 1, 3, 3)
+        kernely = torch.tensor([[1., 2., 1.], [0., 0., 0.], [-1., -2., -1.]]).view(1, 1, 3, 3)
+        # plain attributes, as in the reference (nn.Parameter(...).cuda() returns a non-registered tensor there: no state_dict keys)
+        self.weightx, self.weighty = kernelx, kernely
 
     def forward(self, x):
-        raise NotImplementedError("segmif_b200: Sobelxy is only available fused with its L1 reduction "
-                                  "(ops.sobel_l1); the reference never uses the gradient map on its own")
+        return sobel_map(x)
 
 
 class Fusionloss3(nn.Module):
@@ -90,22 +93,121 @@ class Fusionloss_grad3(nn.Module):
         return mse_l1(g, m)[0] + 1.1 * (1 - ssim(g, m))
 
 
-def _unbuilt(name, where):
-    class _U(nn.Module):
-        def __init__(self, *a, **k):
-            super().__init__()
+class Fusionloss(nn.Module):
+    """core/loss.py:423-439: L1(max(vis_y, ir), fused) + 8 * L1(max(sobel(vis_y), sobel(ir)), sobel(fused))."""
 
-        def forward(self, *a, **k):
-            raise NotImplementedError(f"segmif_b200: {name} ({where}) is imported by train.py but never called "
-                                      "there; it is not part of the accelerated path yet")
-    _U.__name__ = _U.__qualname__ = name
-    return _U
+    def __init__(self):
+        super().__init__()
+        self.sobelconv = Sobelxy()
+
+    def forward(self, image_ir, image_vis, generate_img):
+        y, ir = _y(image_vis), _y(image_ir)
+        loss_in = mse_l1(generate_img, ops.ew2(y, ir, ops.EW_MAX))[1]
+        joint = ops.ew2(ops.sobel_map(y), ops.sobel_map(ir), ops.EW_MAX)
+        loss_grad = mse_l1(self.sobelconv(generate_img), joint)[1]
+        return loss_in + 8 * loss_grad
 
 
-# imported by name at train.py:111-112 but never instantiated on the live path
-Total_fusion_loss = _unbuilt("Total_fusion_loss", "core/loss.py:519")
-Total_fusion_loss2 = _unbuilt("Total_fusion_loss2", "core/loss.py:547")
-Fusionloss = _unbuilt("Fusionloss", "core/loss.py:423")
-Fusionloss_add = _unbuilt("Fusionloss_add", "core/loss.py")
-Fusionloss4 = _unbuilt("Fusionloss4", "core/loss.py")
-IQALoss = _unbuilt("IQALoss", "core/loss.py:605")
+class Fusionloss4(nn.Module):
+    """core/loss.py:545-559: L1((vis_y + ir) / 2, fused) + 4 * L1(sobel((vis_y + ir) / 2), sobel(fused))."""
+
+    def __init__(self):
+        super().__init__()
+        self.sobelconv = Sobelxy()
+
+    def forward(self, image_ir, image_vis, generate_img, mask):
+        syn = ops.ew2(_y(image_vis), _y(image_ir), ops.EW_LINCOMB, 0.5, 0.5)
+        l1, lgrad = sobel_l1(generate_img, syn)
+        return l1 + 4 * lgrad
+
+
+class Fusionloss_add(nn.Module):
+    """core/loss.py:561-577: 1.5 * L1(0.4 vis_y + 0.6 ir, fused) + 5 * L1(max(sobel(vis_y), sobel(ir)), sobel(fused))."""
+
+    def __init__(self):
+        super().__init__()
+        self.sobelconv = Sobelxy()
+
+    def forward(self, image_ir, image_vis, generate_img):
+        y, ir = _y(image_vis), _y(image_ir)
+        loss_in = mse_l1(generate_img, ops.ew2(y, ir, ops.EW_LINCOMB, 0.4, 0.6))[1]
+        joint = ops.ew2(ops.sobel_map(y), ops.sobel_map(ir), ops.EW_MAX)
+        loss_grad = mse_l1(self.sobelconv(generate_img), joint)[1]
+        return loss_in * 1.5 + 5 * loss_grad
+
+
+class new_loss_sobel(nn.Module):
+    """core/loss.py:386-399.  The reference REBINDS `mask_ir` / `mask_vis` to the two scalar MSE terms before they
+    multiply the Sobel maps (:394-397), so the gradient terms are a^2 * MSE(sobel(fused), sobel(ir)) and
+    v^2 * MSE(sobel(fused), sobel(vis)) with a, v the (differentiable) intensity terms; reproduced as written."""
+
+    def __init__(self):
+        super().__init__()
+        self.sobel = Sobelxy()
+
+    def forward(self, ir, vis, mask_ir, fused_img):
+        ir, vis, m = _y(ir), _y(vis), _y(mask_ir)
+        mv = ops.ew2(m, None, ops.EW_ABS_AFFINE, 1.0, -1.0)                       # torch.abs(1 - mask_ir)
+        a = mse_l1(mul_data(fused_img, m), ops.ew2(m, ir, ops.EW_MUL))[0]
+        v = mse_l1(mul_data(fused_img, mv), ops.ew2(mv, vis, ops.EW_MUL))[0]
+        sf = self.sobel(fused_img)
+        a2 = a * a * mse_l1(sf, ops.sobel_map(ir))[0]                              # MSE(a * S(f), a * S(ir)), a scalar
+        v2 = v * v * mse_l1(sf, ops.sobel_map(vis))[0]
+        return (v + v2) * 1.0 + (a + a2) * 0.85
+
+
+class Total_fusion_loss(nn.Module):
+    """core/loss.py:578-588 (note the argument order: mask BEFORE generate_img)."""
+
+    def __init__(self):
+        super().__init__()
+        self.nls = new_loss_sobel()
+        self.fl = Fusionloss()
+
+    def forward(self, image_ir, image_vis, mask, generate_img):
+        return self.fl(image_ir, image_vis, generate_img) * 1.2 + self.nls(image_ir, image_vis, mask, generate_img) * 0.85
+
+
+class Total_fusion_loss2(nn.Module):
+    """core/loss.py:591-599."""
+
+    def __init__(self):
+        super().__init__()
+        self.nls = new_loss_sobel()
+
+    def forward(self, image_ir, image_vis, mask, generate_img):
+        return self.nls(image_ir, image_vis, mask, generate_img)
+
+
+class Total_fusion_loss3(nn.Module):
+    """core/loss.py:600-608."""
+
+    def __init__(self):
+        super().__init__()
+        self.fl = Fusionloss()
+
+    def forward(self, image_ir, image_vis, mask, generate_img):
+        return self.fl(image_ir, image_vis, generate_img) * 3
+
+
+class IQALoss(nn.Module):
+    """core/loss.py:605-633: 0.5 MSE(lr, mask) + 0.5 MSE(vis, |1 - mask|) + the same two terms on Sobel maps.
+    The entropy / std softmax weights the reference computes (:616-626) never enter the result; the two entropies are
+    still evaluated (the only caller of core/Entropy.py) and kept in `last_entropy` as device scalars -- without the
+    reference's host round trip (`torch.tensor([e1, e2])`).  Gradients flow to `mask`."""
+
+    def __init__(self):
+        super().__init__()
+        self.entropy_ = Entropy(4)
+        self.sobel = Sobelxy()
+        self.last_entropy = None
+
+    def forward(self, lr, vis, mask):
+        lr, vis = _y(lr), _y(vis)
+        m = mask[:, 0:1].float().contiguous()
+        inv = abs_affine(m, 1.0, -1.0)                                             # torch.abs(1 - mask)
+        with torch.no_grad():
+            self.last_entropy = (self.entropy_(m.detach()), self.entropy_(inv.detach()))
+        mse_loss = 0.5 * mse_l1(m, lr)[0] + 0.5 * mse_l1(inv, vis)[0]
+        grad_loss = 0.5 * mse_l1(self.sobel(m), ops.sobel_map(lr))[0] + 0.5 * mse_l1(self.sobel(inv), ops.sobel_map(vis))[0]
+        return mse_loss + grad_loss

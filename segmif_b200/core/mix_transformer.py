@@ -18,6 +18,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
+from .. import strict as _strict
 from ..packing import PackCache
 from ..ops import ACT_NONE
 
@@ -189,6 +190,8 @@ class Block(nn.Module):
                                       "Network3.forward/_loss (core/seg_train.py) or under torch.no_grad()")
         x = x.contiguous() if x.dtype == torch.float32 else x.float().contiguous()
         B, N, C = x.shape
+        if _strict.is_strict() and not self.training:
+            return _strict.block(self, x, H, W)
         s1, s2 = self._droppath_scale(B, x.device), self._droppath_scale(B, x.device)
         n1 = ops.layernorm(x, self.norm1.weight.detach(), self.norm1.bias.detach(), self.norm1.eps)
         if s1 is None:
@@ -296,7 +299,9 @@ class MixVisionTransformer(nn.Module):
 
     # ---- the stage pipeline, pixel-major throughout -----------------------------------------------------
     def forward_stages(self, x, in_scale=None, in_shift=None, n_stages=4):
-        """Returns per stage (tokens bf16 [B, N, C] after the stage LayerNorm, H, W)."""
+        """Returns per stage (tokens bf16 [B, N, C] after the stage LayerNorm, H, W); fp32 tokens in strict precision."""
+        if _strict.is_strict() and not self.training:
+            return _strict.encoder_stages(self, x, in_scale, in_shift, n_stages)
         B = x.shape[0]
         outs = []
         tok_bf16, H, W = None, None, None
@@ -330,6 +335,8 @@ class MixVisionTransformer(nn.Module):
         Returned tensors are logically NCHW [B,C,H,W] (the reference's interface) but are bf16 views of
         pixel-major storage (channels_last strides), which Fusion_Network3_ac consumes without a copy.
         Stages 3-4, which the reference computes and discards here, are skipped."""
+        if _strict.is_strict() and not self.training:
+            return _strict.forward_fusion(self, x)
         B, _, H, W = x.shape
         outs = []
         for tok, h, w in self.forward_stages(x, n_stages=2):

@@ -13,6 +13,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
+from .. import strict as _strict
 from ..ops import ACT_PRELU, ACT_RELU
 from ..packing import PackCache
 from . import mix_transformer
@@ -87,6 +88,8 @@ class WeTr(nn.Module):
 
     def forward_pixel_major(self, x, in_scale=None, in_shift=None):
         """fp32 logits [B, H/4, W/4, nc], pixel-major (what the fused upsample+argmax / CE kernels consume)."""
+        if _strict.is_strict() and not self.training:
+            return _strict.wetr_logits(self, x, in_scale, in_shift)
         stages = self.encoder.forward_stages(x, in_scale, in_shift)
         return self.decoder.forward_tokens(stages)
 
@@ -266,6 +269,12 @@ class DRDB(nn.Module):
     def forward(self, x):
         _no_autograd(self, x)
         B, C, H, W = x.shape
+        if _strict.is_strict() and self.in_ch == 64 and self.growth == 32:
+            rows = _strict.nchw_to_rows_f32(x)
+            g = _strict.Planes(B * H * W, self.total, x.device)
+            _strict.split(rows, planes=g)
+            y, _ = _strict.drdb(self, g, rows, B, H, W, want_planes=False)
+            return ops.nhwc_to_nchw(y, B, H * W, C).view(B, C, H, W)
         buf = torch.empty((B, H, W, self.total), dtype=torch.bfloat16, device=x.device)
         ops.nchw_to_nhwc(x.float().contiguous(), out=buf.view(B, H * W, self.total), ld_dst=self.total)
         part = torch.empty((B, H, W, 128), dtype=torch.bfloat16, device=x.device)
@@ -404,6 +413,10 @@ class FeatureFusionModule(nn.Module):
     def forward(self, x1, x2, segfeature):
         _no_autograd(self, x1, x2, segfeature)
         B, C, H, W = x1.shape
+        if _strict.is_strict():
+            r1, r2, r3 = (_strict.nchw_to_rows_f32(t) for t in (x1, x2, segfeature))
+            o1, o2, _ = _strict.ffm_full(self, r1, _strict.split(r1), r2, _strict.split(r2), r3, None, B, H, W)
+            return tuple(ops.nhwc_to_nchw(o, B, H * W, C).view(B, C, H, W) for o in (o1, o2))
         t1, t2, t3 = _pixel_major_bf16(x1), _pixel_major_bf16(x2), _pixel_major_bf16(segfeature)
         o1 = torch.empty((B, H * W, C), dtype=torch.bfloat16, device=x1.device)
         o2 = torch.empty_like(o1)
@@ -440,6 +453,9 @@ class Fusion_Network3_ac(nn.Module):
             from .fusion_train import forward_with_grad
             return forward_with_grad(self, ir, vis, out1, out2)
         _no_autograd(self, ir, vis, out1, out2)
+        if _strict.is_strict():
+            return _strict.fusion_network(self, ir, vis, ("full", _strict.nchw_to_rows_f32(out1)),
+                                          ("full", _strict.nchw_to_rows_f32(out2)))
         return self._run(ir, vis, ("full", _pixel_major_bf16(out1)), ("full", _pixel_major_bf16(out2)))
 
     def forward_lowres(self, ir, vis, stage1, stage2):
@@ -448,6 +464,9 @@ class Fusion_Network3_ac(nn.Module):
         The 1x1 convs, channel_proj3 and the bilinear resize commute (all linear), so the full-resolution feature
         maps are never written; see csrc/ffm.cu."""
         _no_autograd(self, ir, vis)
+        if _strict.is_strict():
+            f32 = lambda st: ("lowres", st[0].float(), st[1], st[2])
+            return _strict.fusion_network(self, ir, vis, f32(stage1), f32(stage2))
         return self._run(ir, vis, ("lowres",) + tuple(stage1), ("lowres",) + tuple(stage2))
 
     def _ffm(self, x1, x2, seg, out1, ldo1, coffo1, out2, ldo2, coffo2, B, H, W, pre_conv):

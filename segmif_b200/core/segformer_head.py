@@ -9,6 +9,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
+from .. import strict as _strict
 from ..ops import ACT_NONE, ACT_RELU
 from ..packing import PackCache
 
@@ -81,6 +82,8 @@ class SegFormerHead(nn.Module):
         if self.training:
             raise NotImplementedError("segmif_b200: train-mode decode head (batch-stat BN, Dropout2d, autograd) is not "
                                       "built yet; call .eval()")
+        if _strict.is_strict():
+            return _strict.head_logits(self, [(t.float(), h, w) for t, h, w in stages])
         (t1, h1, w1), (t2, h2, w2), (t3, h3, w3), (t4, h4, w4) = stages
         B, E = t1.shape[0], self.embedding_dim
         cat = torch.empty((B, h1, w1, 4 * E), dtype=torch.bfloat16, device=t1.device)
@@ -100,7 +103,7 @@ class SegFormerHead(nn.Module):
         B = c1.shape[0]
         stages = []
         for c in x:
-            tok = ops.nchw_to_nhwc(c.float().contiguous(), out_dtype=torch.bfloat16)
+            tok = ops.nchw_to_nhwc(c.float().contiguous(), out_dtype=torch.float32 if _strict.is_strict() else torch.bfloat16)
             stages.append((tok, c.shape[2], c.shape[3]))
         logits = self.forward_tokens(stages)
         h1, w1 = c1.shape[2], c1.shape[3]

@@ -447,6 +447,37 @@ def mse_l1(x, y):
     return out[0], out[1]
 
 
+def sobel_map(x):
+    """core/loss.py:647-650: |sobel_x(x)| + |sobel_y(x)| as a map."""
+    x = _plane(x)
+    st = _prep(x)
+    B, _, H, W = x.shape
+    out = torch.empty_like(x)
+    _lib.call("segmif_sobel_map_fwd", _ptr(x), _ptr(out), B, H, W, st)
+    return out
+
+
+def sobel_map_bwd(x, dout):
+    x, dout = _plane(x), _plane(dout)
+    st = _prep(x, dout)
+    B, _, H, W = x.shape
+    dx = torch.empty_like(x)
+    _lib.call("segmif_sobel_map_bwd", _ptr(x), _ptr(dout), _ptr(dx), B, H, W, 0, st)
+    return dx
+
+
+EW_LINCOMB, EW_MAX, EW_ABS_AFFINE, EW_MUL, EW_ABS_AFFINE_BWD = 0, 1, 2, 3, 4
+
+
+def ew2(x, y, mode, a=0.0, b=0.0):
+    x = x.float().contiguous()
+    y = y.float().contiguous() if y is not None else None
+    st = _prep(x, y)
+    out = torch.empty_like(x)
+    _lib.call("segmif_ew2", _ptr(x), _ptr(y), float(a), float(b), int(mode), _ptr(out), x.numel(), st)
+    return out
+
+
 def upsample_ce(logits_nhwc, B, h, w, nc, labels, ignore_index=255, return_count=False):
     st = _prep(logits_nhwc, labels)
     H, W = labels.shape[1], labels.shape[2]

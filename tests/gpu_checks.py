@@ -436,6 +436,38 @@ def loss_modules():
     return rs
 
 
+@check
+def loss_modules_extra():
+    """core/loss.py composites off the live path, product classes on the GPU against the fixture generated by the
+    unmodified reference (values, and gradients w.r.t. the fused image / mask from the reference's autograd)."""
+    from conftest import GOLDEN
+    from segmif_b200.core import loss as CL
+    g = np.load(os.path.join(GOLDEN, "losses_extra.npz"))
+    inp = synth.synth_inputs(2, 48, 80, seed=3)
+    ir, vis, mask = inp["ir"], inp["vis"], inp["mask"][:, :1].contiguous()
+    fused = (0.6 * ir + 0.4 * vis[:, :1]).clamp(0, 1)
+    d = lambda t: t.to(DEV)
+    cases = {
+        "fusionloss": lambda f: CL.Fusionloss()(d(ir), d(vis), f),
+        "fusionloss4": lambda f: CL.Fusionloss4()(d(ir), d(vis), f, d(mask)),
+        "fusionloss_add": lambda f: CL.Fusionloss_add()(d(ir), d(vis), f),
+        "total_fusion_loss": lambda f: CL.Total_fusion_loss()(d(ir), d(vis), d(mask), f),
+        "total_fusion_loss2": lambda f: CL.Total_fusion_loss2()(d(ir), d(vis), d(mask), f),
+        "iqa_loss": lambda f: CL.IQALoss()(d(ir), d(vis), f),
+    }
+    rs = []
+    for name, fn in cases.items():
+        f = d(fused).clone().requires_grad_(True)
+        val = fn(f)
+        (grad,) = torch.autograd.grad(val, f)
+        rs.append(result(f"mod_{name}", rel_err(val.detach(), torch.tensor(g[name])), 1e-5))
+        gerr = float((grad[:, :, ::3, ::5].cpu() - torch.from_numpy(g[name + "_grad_s"])).abs().max()) / float(g[name + "_grad_max"])
+        rs.append(result(f"mod_{name}_grad", gerr, 1e-4))
+    sm = CL.Sobelxy()(d(fused))
+    rs.append(result("mod_Sobelxy_map", rel_err(sm[:, :, ::2, ::2], torch.from_numpy(g["sobel_map_s"])), 1e-6))
+    return rs
+
+
 # ----------------------------------------------------------------------------------------- modules vs oracle / golden
 def _golden():
     from conftest import GOLDEN
@@ -557,6 +589,12 @@ def pipeline_golden():
     lab = out["labels"].cpu().numpy().astype(np.int16)
     agree = float((lab == g["labels"]).mean())
     rs.append(result("pipe_label_agreement", 1.0 - agree, 0.03, note=f"{agree * 100:.2f}% of pixels equal the reference's labels (bf16 path)"))
+    # the path bench.py times (forward_lowres: the two full-resolution encoder maps are never written)
+    with torch.no_grad():
+        fused_lr, labels_lr = pipe(inp["ir"].to(DEV), inp["vis"].to(DEV), inp["mask"].to(DEV))
+    rs.append(result("pipe_lowres_fused_vs_reference", rel_err(fused_lr, torch.from_numpy(g["fused"])), 5e-2))
+    agree = float((labels_lr.cpu().numpy().astype(np.int16) == g["labels"]).mean())
+    rs.append(result("pipe_lowres_label_agreement", 1.0 - agree, 0.03, note=f"{agree * 100:.2f}% (bf16 path; bit-exact labels are the strict mode's contract, gpu_checks_strict.py)"))
     return rs
 
 

@@ -9,6 +9,7 @@ pytestmark = pytest.mark.gpu
 def _checks():
     import gpu_checks
     import gpu_checks_train  # noqa: F401  (registers the training-side checks in the same list)
+    import gpu_checks_strict  # noqa: F401  (strict-precision mode)
     return gpu_checks.CHECKS
 
 

@@ -293,7 +293,8 @@ int segmif_entropy_bwd(const float* img, int B, int H, int W, int patch, const f
 
 /* ---- activation backward from the layer OUTPUT y (F.relu core/model_fusion.py:135-156; the shared nn.PReLU
  * :1038,1051-1065, slope must be > 0):  dz = dy * f'(y);  dbias[c] += sum_p dz[p][c];  dalpha += sum dy * z [z<=0].
- * dbias / dalpha may be NULL.  C % 8 == 0, C <= 256.                                                             */
+ * dbias / dalpha may be NULL.  C % 8 == 0, C <= 256.  A PReLU slope <= 0 makes sign(y) ambiguous: the kernels then write
+ * NaN gradients (loud) instead of wrong ones; ddp.FusionTrainer additionally checks the slope on the host every 50 steps. */
 int segmif_act_bwd(const void* y, int ldy, int coffy, const void* dy, int lddy, int coffdy, void* dz, int lddz,
                    int coffdz, int64_t rows, int C, int act, const float* prelu_alpha, float* dbias, float* dalpha,
                    segmif_stream_t stream);
@@ -384,6 +385,12 @@ int segmif_bn_train_fwd(const void* z, int64_t rows, int C, const float* gamma, 
                         segmif_stream_t stream);
 int segmif_bn_train_bwd(const void* z, const void* y, const void* dy, const float* stats, const float* gamma, int64_t rows,
                         int C, double* workspace, void* dz, float* dgamma, float* dbeta, segmif_stream_t stream);
+/* The same layer in EVAL mode with gradients (train.py:232-236: val_segformer() leaves the model in eval() and training
+ * continues with running statistics, no dropout): stats = {running_mean, rsqrt(running_var + eps)}; dz = gamma * rstd * dy 1[y>0]. */
+int segmif_bn_eval_fwd(const void* z, int64_t rows, int C, const float* gamma, const float* beta, float eps,
+                       const float* running_mean, const float* running_var, float* stats, void* y, segmif_stream_t stream);
+int segmif_bn_eval_bwd(const void* z, const void* y, const void* dy, const float* stats, const float* gamma, int64_t rows,
+                       int C, double* workspace, void* dz, float* dgamma, float* dbeta, segmif_stream_t stream);
 /* y[b,p,c] = x[b,p,c] * scale[b,c]: nn.Dropout2d forward and backward (core/segformer_head.py:57,79), bf16 [B,HW,C]. */
 int segmif_channel_scale(const void* x, const float* scale, void* y, int B, int64_t HW, int C, segmif_stream_t stream);
 /* depthwise 3x3 without activation (flip != 0: transposed taps = the data gradient of DWConv, mix_transformer.py:381-387)

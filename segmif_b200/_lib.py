@@ -140,6 +140,8 @@ SIGNATURES = {
     "segmif_bilinear_nhwc_bwd": [P, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, c_int, P],
     "segmif_bn_train_fwd": [P, c_int64, c_int, P, P, c_float, c_float, P, P, P, P, P, P],
     "segmif_bn_train_bwd": [P, P, P, P, P, c_int64, c_int, P, P, P, P, P],
+    "segmif_bn_eval_fwd": [P, c_int64, c_int, P, P, c_float, P, P, P, P, P],
+    "segmif_bn_eval_bwd": [P, P, P, P, P, c_int64, c_int, P, P, P, P, P],
     "segmif_channel_scale": [P, P, P, c_int, c_int64, c_int, P],
     "segmif_dwconv3x3": [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P],
     "segmif_dwconv3x3_gelu_bwd": [P, P, P, P, P, c_int, c_int, c_int, c_int, P, P, P, P],

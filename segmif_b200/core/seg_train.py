@@ -210,8 +210,11 @@ def head_forward(head, stages, B, masks):
             pdrop = head.dropout.p
             scale = (torch.rand((B, E), device=dev) >= pdrop).float() / (1.0 - pdrop)
     else:
-        raise NotImplementedError("segmif_b200: the training tape needs the decode head in train mode (batch-statistics "
-                                  "BatchNorm, core/segformer_head.py:50-55); call model.train()")
+        # The reference's train_seg calls val_segformer() every 1000 iterations, which leaves the model in eval() and never
+        # restores train() (train.py:232-236): from then on it trains with running-statistics BatchNorm, no Dropout2d and no
+        # DropPath.  Same here: BN uses the running statistics (constants for the backward), scale = None.
+        y, stats = ops.bn_eval_fwd(z, bn.weight.detach(), bn.bias.detach(), bn.eps, bn.running_mean, bn.running_var)
+        scale = None
     yd = ops.channel_scale(y, scale, B, h1 * w1, E) if scale is not None else y
     logits = ops.linear(yd, head._packs.conv(head.linear_pred.weight), head.linear_pred.bias.detach(), act=ACT_NONE, out_dtype=F32)
     tape = dict(cat=cat, z=z, y=y, yd=yd, stats=stats, scale=scale, dims=((h1, w1), (h2, w2), (h3, w3), (h4, w4)),
@@ -341,7 +344,7 @@ def head_backward(head, tape, dlogits, B, g, prefix):
     dy = ops.channel_scale(dyd, tape["scale"], B, h1 * w1, E) if tape["scale"] is not None else dyd
     bn, conv = head.linear_fuse.bn, head.linear_fuse.conv
     dz = ops.bn_train_bwd(tape["z"], tape["y"], dy, tape["stats"], bn.weight.detach(), g[prefix + "linear_fuse.bn.weight"],
-                          g[prefix + "linear_fuse.bn.bias"])
+                          g[prefix + "linear_fuse.bn.bias"], eval_mode=not tape["train_bn"])
     cat2 = tape["cat"].view(M, 4 * E)
     _wgrad(g, dz, E, 0, cat2, 4 * E, 0, B=1, H=1, W=1, P=M, Cin=4 * E, Cout=E, taps=1, dil=1, grad=g[prefix + "linear_fuse.conv.weight"],
               s_co=4 * E, s_tap=1, s_ci=1)

@@ -215,10 +215,11 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_apply_kernel(const bf16* __re
                                                                 const bf16* __restrict__ dy, const float* __restrict__ stats,
                                                                 const float* __restrict__ gamma, const double* __restrict__ sums,
                                                                 bf16* __restrict__ dz, int64_t rows, int C,
-                                                                float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                                                float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                                float corr) {
   const int g = C >> 3;
   const int64_t n = rows * g;
-  const float inv_rows = 1.f / (float)rows;
+  const float inv_rows = corr / (float)rows;      // corr = 0: eval-mode BatchNorm (running statistics are constants)
   if (blockIdx.x == 0)
     for (int c = threadIdx.x; c < C; c += 256) {
       if (dgamma) dgamma[c] += (float)sums[C + c];
@@ -561,8 +562,42 @@ extern "C" int segmif_bn_train_bwd(const void* z, const void* y, const void* dy,
   const int rpi = 256 / (C >> 3);
   bn_relu_bwd_reduce_kernel<<<grid_n(rows, rpi * 8), 256, 0, st>>>((const bf16*)z, (const bf16*)y, (const bf16*)dy, stats, rows, C, workspace);
   bn_relu_bwd_apply_kernel<<<grid_n(rows * (C >> 3), 1024), 256, 0, st>>>((const bf16*)z, (const bf16*)y, (const bf16*)dy, stats, gamma, workspace,
-                                                                            (bf16*)dz, rows, C, dgamma, dbeta);
+                                                                            (bf16*)dz, rows, C, dgamma, dbeta, 1.f);
   return check_launch("segmif_bn_train_bwd");
+}
+
+// eval-mode BatchNorm2d + ReLU with gradients (the reference keeps training after val_segformer() left the model in
+// eval(), train.py:232-236: running statistics, no batch coupling): stats = {running_mean, rsqrt(running_var + eps)}
+__global__ void bn_eval_stats_kernel(const float* __restrict__ running_mean, const float* __restrict__ running_var, float eps,
+                                     int C, float* __restrict__ stats) {
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
+    stats[c] = running_mean[c];
+    stats[C + c] = (float)(1.0 / sqrt((double)running_var[c] + (double)eps));
+  }
+}
+
+extern "C" int segmif_bn_eval_fwd(const void* z, int64_t rows, int C, const float* gamma, const float* beta, float eps,
+                                  const float* running_mean, const float* running_var, float* stats, void* y,
+                                  segmif_stream_t stream) {
+  SEGMIF_REQUIRE(z && gamma && beta && running_mean && running_var && stats && y && rows > 0, "bn_eval_fwd: bad arguments");
+  SEGMIF_REQUIRE(C % 8 == 0 && C > 0 && C <= 512, "bn_eval_fwd: C=%d must be a multiple of 8, <= 512", C);
+  cudaStream_t st = as_stream(stream);
+  bn_eval_stats_kernel<<<1, 256, 0, st>>>(running_mean, running_var, eps, C, stats);
+  bn_relu_apply_kernel<<<grid_n(rows * (C >> 3), 1024), 256, 0, st>>>((const bf16*)z, stats, gamma, beta, (bf16*)y, rows, C);
+  return check_launch("segmif_bn_eval_fwd");
+}
+
+extern "C" int segmif_bn_eval_bwd(const void* z, const void* y, const void* dy, const float* stats, const float* gamma,
+                                  int64_t rows, int C, double* workspace, void* dz, float* dgamma, float* dbeta,
+                                  segmif_stream_t stream) {
+  SEGMIF_REQUIRE(z && y && dy && stats && gamma && workspace && dz && rows > 0, "bn_eval_bwd: bad arguments");
+  SEGMIF_REQUIRE(C % 8 == 0 && C > 0 && C <= 512, "bn_eval_bwd: C=%d must be a multiple of 8, <= 512", C);
+  cudaStream_t st = as_stream(stream);
+  const int rpi = 256 / (C >> 3);
+  bn_relu_bwd_reduce_kernel<<<grid_n(rows, rpi * 8), 256, 0, st>>>((const bf16*)z, (const bf16*)y, (const bf16*)dy, stats, rows, C, workspace);
+  bn_relu_bwd_apply_kernel<<<grid_n(rows * (C >> 3), 1024), 256, 0, st>>>((const bf16*)z, (const bf16*)y, (const bf16*)dy, stats, gamma, workspace,
+                                                                            (bf16*)dz, rows, C, dgamma, dbeta, 0.f);
+  return check_launch("segmif_bn_eval_bwd");
 }
 
 extern "C" int segmif_channel_scale(const void* x, const float* scale, void* y, int B, int64_t HW, int C,

@@ -31,6 +31,9 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const bf16* __restrict__ y
   const int grp = threadIdx.x % g, rin = threadIdx.x / g;
   const float alpha = act == SEGMIF_ACT_PRELU ? *alpha_p : 0.f;
   const float inv_alpha = act == SEGMIF_ACT_PRELU ? 1.f / alpha : 0.f;
+  // The pre-activation is recovered from the stored OUTPUT (sign(y) == sign(z), z = y / alpha on the negative side), which
+  // only holds for a slope > 0.  A trained slope that reaches <= 0 must not silently give wrong gradients: poison them.
+  const float poison = (act == SEGMIF_ACT_PRELU && !(alpha > 0.f)) ? __int_as_float(0x7fc00000) : 0.f;
   float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   float da = 0.f;
   if (active) {
@@ -41,7 +44,7 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const bf16* __restrict__ y
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const bool pos = vy[i] > 0.f;
-        o[i] = pos ? vd[i] : alpha * vd[i];
+        o[i] = (pos ? vd[i] : alpha * vd[i]) + poison;
         if (!pos) da = fmaf(vd[i], vy[i] * inv_alpha, da);     // z = y / alpha on the negative side
         cs[i] += o[i];
       }
@@ -77,11 +80,12 @@ __global__ void __launch_bounds__(256) prelu_plane_bwd_kernel(const float* __res
                                                               float* __restrict__ dalpha) {
   __shared__ float sred[2][8];
   const float alpha = *alpha_p, inv_alpha = 1.f / alpha;
+  const float poison = !(alpha > 0.f) ? __int_as_float(0x7fc00000) : 0.f;     // see act_bwd_kernel: slope must stay > 0
   float sb = 0.f, sa = 0.f;
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
     const float o = out[i], d = dout[i];
     const bool pos = o > 0.f;
-    const float v = pos ? d : alpha * d;
+    const float v = (pos ? d : alpha * d) + poison;
     if (!pos) sa = fmaf(d, o * inv_alpha, sa);
     sb += v;
     dz[i * ld] = __float2bfloat16_rn(v);

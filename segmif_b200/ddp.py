@@ -48,6 +48,21 @@ class FlatParams:
                 lo, hi = self.group_ranges.get(group_of(k), (o, o))
                 self.group_ranges[group_of(k)] = (min(lo, o), max(hi, o + pad4(n)))
 
+    def broadcast(self, module=None, group=None, src=0):
+        """Makes every replica start from rank `src`'s parameters (and `module`'s buffers, e.g. BatchNorm running
+        statistics): random initialisation or construction order may differ between ranks, and replicas that start apart
+        diverge silently because only gradients are exchanged afterwards."""
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+            return False
+        dist.broadcast(self.param, src=src, group=group)
+        if module is not None:
+            owned = {p.data_ptr() for _, p in self.named}
+            for t in list(module.parameters()) + list(module.buffers()):
+                if t.data_ptr() not in owned and t.numel() > 0:
+                    dist.broadcast(t.data, src=src, group=group)
+        self.epoch[0] += 1                            # packed copies of the old values are stale
+        return True
+
     def zero_grad(self):
         self.grad.zero_()
         for k, p in self.named:                       # autograd may have replaced a view; re-attach if so
@@ -132,11 +147,19 @@ class _GraphedStep:
     _graph = None
 
     def _capture(self, body, **static_inputs):
+        from . import packing
         self._static = {k: v.clone() for k, v in static_inputs.items() if v is not None}
         torch.cuda.synchronize()
+        # Every packed (bf16) weight copy must be REBUILT INSIDE the graph, otherwise replays keep reading the copies of
+        # capture time while AdamW updates the fp32 masters: declare all of them stale before capturing, and again afterwards
+        # so that eager code never aliases tensors living in the graph's private memory pool.
+        packing.invalidate_all()
+        self.flat.epoch[0] += 1
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             outs = body(**self._static)
+        packing.invalidate_all()
+        self.flat.epoch[0] += 1
         self._graph, self._graph_outs = graph, outs
         return self
 
@@ -150,6 +173,10 @@ class _GraphedStep:
     def _finish(self):
         world = self.flat.all_reduce(self.group)
         self.opt.step(grad_scale=1.0 / world)
+        self._post_step()
+
+    def _post_step(self):
+        pass
 
 
 class FusionTrainer(_GraphedStep):
@@ -175,7 +202,15 @@ class FusionTrainer(_GraphedStep):
         self.opt = FusedPolyWarmupAdamW(self.flat, lr, weight_decay, betas, warmup_iter, max_iter, warmup_ratio, power)
         self.seg_net, self.iter_ = seg_net, iter_
         self.with_ce = (seg_net is not None) if with_ce is None else with_ce
+        self.flat.broadcast(fusion_net, group)
+        if seg_net is not None and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            for t in list(seg_net.parameters()) + list(seg_net.buffers()):      # the frozen network must agree across ranks too
+                if t.numel() > 0:
+                    dist.broadcast(t.data, src=0, group=group)
         if self.with_ce:
+            # train.py never steps the segmentation network in train_fusion; its weight gradients are skipped while these
+            # flags are off.  `release_seg_net()` restores them (a later SegTrainer on the same network needs them).
+            self._seg_requires_grad = [(p, p.requires_grad) for p in seg_net.parameters()]
             for p in seg_net.parameters():
                 p.requires_grad_(False)
             self.ce = torch.nn.CrossEntropyLoss(ignore_index=ignore_index)
@@ -183,6 +218,14 @@ class FusionTrainer(_GraphedStep):
             self.prev1 = torch.ones((2,), dtype=torch.float32, device=dev)        # losses of step n-1
             self.prev2 = torch.ones((2,), dtype=torch.float32, device=dev)        # losses of step n-2
             self.count = torch.zeros((), dtype=torch.float32, device=dev)         # n_iter
+
+    def _post_step(self):
+        # The activation backward recovers pre-activations from stored outputs, which needs the shared PReLU slope > 0
+        # (csrc/train_ops.cu).  AdamW + weight decay can in principle drive it to <= 0; the kernels then emit NaN gradients,
+        # and this periodic host check (one 4-byte read every 50 steps) names the cause instead of a bare NaN loss.
+        if self.opt.opt_steps % 50 == 0 and not float(self.net.relu.weight.detach().reshape(-1)[0]) > 0.0:
+            raise RuntimeError("segmif_b200: Fusion_Network3_ac.relu (the shared PReLU slope) reached %g <= 0; the hand-written "
+                               "activation backward is only valid for a positive slope" % float(self.net.relu.weight.detach().reshape(-1)[0]))
 
     def _forward_backward(self, ir, vis_ycrcb, out0, out1, mask, vis_rgb=None, labels=None):
         self.flat.zero_grad()
@@ -200,6 +243,12 @@ class FusionTrainer(_GraphedStep):
             self.count += 1
         loss.backward()
         return loss.detach(), fused.detach()
+
+    def release_seg_net(self):
+        """Restores the requires_grad flags this trainer cleared on the frozen segmentation network."""
+        for p, flag in getattr(self, "_seg_requires_grad", []):
+            p.requires_grad_(flag)
+        self._seg_requires_grad = []
 
     def _images_body(self, ir, vis_rgb, mask, labels=None):
         from .core.model_fusion import RGB2YCrCb
@@ -244,6 +293,7 @@ class SegTrainer(_GraphedStep):
         self.opt = FusedPolyWarmupAdamW(self.flat, lr, weight_decay, betas, warmup_iter, max_iter, warmup_ratio, power,
                                         groups={0: dict(lr=lr, weight_decay=weight_decay), 1: dict(lr=lr, weight_decay=0.0),
                                                 2: dict(lr=lr * 10, weight_decay=weight_decay)}, iter_curr=iter_curr)
+        self.flat.broadcast(seg_net, group)
         self.ce = torch.nn.CrossEntropyLoss(ignore_index=ignore_index)
 
     def _forward_backward(self, mask, labels):

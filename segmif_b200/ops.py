@@ -733,15 +733,29 @@ def bn_train_fwd(z, gamma, beta, eps, momentum, running_mean, running_var):
     y = torch.empty_like(z)
     _lib.call("segmif_bn_train_fwd", _ptr(z), rows, C, _ptr(gamma), _ptr(beta), float(eps), float(momentum),
               _ptr(running_mean), _ptr(running_var), _ptr(ws), _ptr(stats), _ptr(y), st)
+    for buf in (running_mean, running_var):        # the kernel wrote through raw pointers: bump torch's version counters so
+        if buf is not None:                        # version-stamped caches (SegFormerHead._fuse_pack) see the update
+            torch.autograd.graph.increment_version(buf)
     return y, stats
 
 
-def bn_train_bwd(z, y, dy, stats, gamma, dgamma, dbeta):
+def bn_eval_fwd(z, gamma, beta, eps, running_mean, running_var):
+    """Eval-mode BatchNorm + ReLU that keeps what its backward needs; returns (y bf16, stats = running mean, rstd)."""
+    st = _prep(z, gamma, beta, running_mean, running_var)
+    rows, C = z.shape
+    stats = torch.empty((2, C), dtype=torch.float32, device=z.device)
+    y = torch.empty_like(z)
+    _lib.call("segmif_bn_eval_fwd", _ptr(z), rows, C, _ptr(gamma), _ptr(beta), float(eps), _ptr(running_mean),
+              _ptr(running_var), _ptr(stats), _ptr(y), st)
+    return y, stats
+
+
+def bn_train_bwd(z, y, dy, stats, gamma, dgamma, dbeta, eval_mode=False):
     st = _prep(z, y, dy, stats, gamma, dgamma, dbeta)
     rows, C = z.shape
     ws = torch.zeros((2 * C,), dtype=torch.float64, device=z.device)
     dz = torch.empty_like(z)
-    _lib.call("segmif_bn_train_bwd", _ptr(z), _ptr(y), _ptr(dy), _ptr(stats), _ptr(gamma), rows, C, _ptr(ws), _ptr(dz),
+    _lib.call("segmif_bn_eval_bwd" if eval_mode else "segmif_bn_train_bwd", _ptr(z), _ptr(y), _ptr(dy), _ptr(stats), _ptr(gamma), rows, C, _ptr(ws), _ptr(dz),
               _ptr(dgamma), _ptr(dbeta), st)
     return dz
 

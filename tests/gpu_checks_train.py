@@ -869,3 +869,38 @@ def dropin_train_loop_bodies():
                       and float((model2.conv2.weight.detach() - w_before).abs().max()) > 0 else 1.0, 0.0))
     res.append(result("dropin_train_fusion_ffm2_grad_none", 0.0 if all(p.grad is None for k, p in model2.named_parameters() if k.startswith("ffm2.")) else 1.0, 0.0))
     return res
+
+
+@check
+def seg_training_after_eval():
+    """train.py:232-236: val_segformer() leaves the model in eval() and train_seg keeps training -- running-statistics
+    BatchNorm, no Dropout2d, no DropPath.  Network3._loss in that state: every parameter gradient against autograd over
+    the oracle with train_bn=False (bound as in seg_network_backward), and the running statistics must not move."""
+    from segmif_b200.core.seg_train import CeFn, logits_with_grad
+    res = []
+    net0, sd, names, x, drop, labels, cot, dps = _seg_case()
+    leaves = {k: sd[k].clone().requires_grad_(True) for k in names}
+    full = dict(sd)
+    full.update(leaves)
+    lg_ref = O.network3_forward(x, full, "mit_b1", train_bn=False)
+    O.seg_cross_entropy(lg_ref, labels).backward()
+    gmax = max(float(leaves[n].grad.abs().max()) for n in names)
+    net = copy.deepcopy(net0).to(DEV).eval()
+    rm0 = net.denoise_net.decoder.linear_fuse.bn.running_mean.clone()
+    loss = net._loss(x.to(DEV), labels.to(DEV), torch.nn.CrossEntropyLoss(ignore_index=255))
+    loss.backward()
+    res.append(result("seg_eval_train_loss", rel_err(loss.detach(), O.seg_cross_entropy(lg_ref, labels).detach()), 2e-2))
+    got = dict(net.named_parameters())
+    worst, worst_name = 0.0, ""
+    for k in names:
+        if got[k].grad is None:
+            res.append(result(f"seg_eval_grad_missing_{k}", float("nan"), 0.0))
+            continue
+        e = _floored_err(got[k].grad, leaves[k].grad, 1e-2 * gmax)
+        if e > worst:
+            worst, worst_name = e, k
+    res.append(result("seg_eval_train_grad_worst", worst, 0.2, note=worst_name))
+    for k in ("denoise_net.decoder.linear_fuse.bn.weight", "denoise_net.decoder.linear_fuse.bn.bias", "denoise_net.decoder.linear_fuse.conv.weight"):
+        res.append(result(f"seg_eval_train_grad_{k.split('decoder.')[1]}", _floored_err(got[k].grad, leaves[k].grad, 1e-2 * gmax), 0.1))
+    res.append(result("seg_eval_running_stats_untouched", float((net.denoise_net.decoder.linear_fuse.bn.running_mean - rm0).abs().max()), 0.0))
+    return res

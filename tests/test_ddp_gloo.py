@@ -186,3 +186,42 @@ def test_fused_optimizer_host_logic_with_a_stub_kernel(monkeypatch):
     e = _epoch(p0)
     opt.step()
     assert _epoch(p0) != e
+
+
+class _ToyBn(torch.nn.Module):
+    def __init__(self, seed):
+        super().__init__()
+        torch.manual_seed(seed)
+        self.a = torch.nn.Linear(4, 3)
+        self.bn = torch.nn.BatchNorm1d(3)
+        with torch.no_grad():
+            self.bn.running_mean.normal_()
+
+
+def _broadcast_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from segmif_b200.ddp import FlatParams
+    m = _ToyBn(seed=10 + rank)                              # replicas constructed with DIFFERENT seeds
+    flat = FlatParams(m)
+    e0 = flat.epoch[0]
+    assert flat.broadcast(m) is True
+    assert flat.epoch[0] == e0 + 1                          # cached weight packs of the old values are declared stale
+    mine = torch.cat([flat.param, m.bn.running_mean])
+    gathered = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine)
+    assert all(torch.equal(gathered[0], t) for t in gathered)          # parameters AND buffers equal rank 0's
+    ref = _ToyBn(seed=10)
+    assert torch.equal(m.a.weight.detach(), ref.a.weight.detach()) and torch.equal(m.bn.running_mean, ref.bn.running_mean)
+    if rank == 0:
+        torch.save(dict(ok=True), out)
+    dist.destroy_process_group()
+
+
+def test_replicas_start_from_rank0_world2(tmp_path):
+    """only gradients are exchanged per step, so replicas must be made identical once at construction."""
+    out = str(tmp_path / "b0.pt")
+    port = 29500 + ((os.getpid() + 137) % 500)
+    mp.spawn(_broadcast_worker, args=(2, port, out), nprocs=2, join=True)
+    assert torch.load(out)["ok"]

@@ -1,7 +1,9 @@
 """Benchmark of the SegMiF hot path: IR+visible 480x640 image pairs per second (BASELINE.json metric).
 
     python bench.py --gpus N --steps K --warmup W            # our CUDA path (default N=1)
-    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU cores
+    python bench.py --impl reference --steps K --warmup W    # the UNMODIFIED reference on the host CPU cores (oracle/_ref)
+    python bench.py --workload train_seg|train_fusion_ce     # BASELINE configs[2]: the data-parallel training steps, with
+                                                             # the gradient all-reduce and AdamW inside the timed region
 
 A step is one pass of the inference pipeline (forward_fusion -> Fusion_Network3_ac -> colour recompose ->
 Network3 -> upsample -> argmax) over one batch of synthetic pairs; workload = BASELINE.json
@@ -41,6 +43,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying the captured CUDA graph")
     ap.add_argument("--profile", action="store_true", help="for ncu: 1 warm-up + K steps, no e2e / CPU legs (not a bench value)")
+    ap.add_argument("--workload", default="infer", choices=["infer", "train_seg", "train_fusion_ce"])
+    ap.add_argument("--train-batch", type=int, default=4, help="pairs per GPU per training step (configs[2]: global 32 on 8 GPUs)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary blocks (strict mode, training steps, cfg 1/4/5)")
     return ap.parse_args()
 
 
@@ -48,7 +53,8 @@ def workload_config(a, n_gpus):
     return {"workload": f"configs[1]: {a.backbone} SegMiF fusion+seg inference forward, batch {a.batch}/GPU, "
                         f"{a.height}x{a.width} synthetic IR+visible pairs",
             "backbone": a.backbone, "batch_per_gpu": a.batch, "global_batch": a.batch * n_gpus,
-            "height": a.height, "width": a.width, "parallelism": f"replicas x{n_gpus} (pairs sharded, no collective)",
+            "height": a.height, "width": a.width, "parallelism": f"replicas x{n_gpus} (pairs sharded, no collective; the training steps "
+                                                                 "with their NCCL all-reduce are timed in `secondary` at the same world size)",
             "l2": "per-step working set (>2 GB of activations) exceeds the 126 MB L2; no explicit flush"}
 
 
@@ -63,15 +69,43 @@ def _cpu_setup(a):
     return synth.synth_state_dict(shapes(seg), 0), synth.synth_state_dict(shapes(fus), 0)
 
 
+_REF = {}
+
+
+def _reference_models(a, sds):
+    """The UNMODIFIED reference modules (vendored byte for byte into oracle/_ref by oracle/build_ref.py, or mounted at
+    /root/reference) with the same synthetic weights; None when neither is present (then the oracle port is timed)."""
+    if "models" not in _REF:
+        _REF["models"] = None
+        try:
+            from oracle import ref_shim
+            if ref_shim.available():
+                ns = ref_shim.load_reference()
+                seg, fus = ref_shim.build_reference_models(ns, a.backbone)
+                _REF["models"] = (ns, seg, fus)
+        except Exception as e:  # noqa: BLE001 -- the port below is always available
+            _REF["error"] = repr(e)
+    return _REF["models"]
+
+
 def _cpu_pass(a, sds, pairs, height, width):
     import torch
     from oracle import segmif_oracle as O
     from segmif_b200 import synth
     inp = synth.synth_inputs(pairs, height, width, seed=0)
+    ref = _reference_models(a, sds)
     with torch.no_grad():
         t0 = time.perf_counter()
-        O.inference_pipeline(inp["ir"], inp["vis"], inp["mask"], sds[0], sds[1], a.backbone)
+        if ref is not None:
+            from oracle import ref_shim
+            ref_shim.reference_inference_pipeline(ref[0], ref[1], ref[2], inp["ir"], inp["vis"], inp["mask"])
+        else:
+            O.inference_pipeline(inp["ir"], inp["vis"], inp["mask"], sds[0], sds[1], a.backbone)
         return time.perf_counter() - t0
+
+
+def cpu_kind(a):
+    return "reference" if _REF.get("models") is not None else "port"
 
 
 def _pick_threads(a, sds):
@@ -110,8 +144,10 @@ def cpu_pipeline_time(a, repeats=1, warm=1, budget_s=150.0):
         if i >= max(warm - 1, 0):
             times.append(dt)
     sec = sorted(times)[len(times) // 2]
+    what = ("the unmodified reference modules (oracle/_ref: core/mix_transformer.py, segformer_head.py, model_fusion.py) on torch CPU fp32"
+            if cpu_kind(a) == "reference" else "oracle port on torch CPU fp32 (oracle/_ref absent)")
     sample = (f"{'1 pair' if frac == 1.0 else '%gx%g crop = %g pair' % (h, w, frac)} {h}x{w} per step ({a.backbone}), "
-              f"oracle port on torch CPU fp32, {threads} of {os.cpu_count()} host threads (fastest of a calibration sweep), "
+              f"{what}, {threads} of {os.cpu_count()} host threads (fastest of a calibration sweep), "
               f"{len(times)} timed step(s), median {sec:.1f} s/step")
     return frac / sec, threads, sec, sample
 
@@ -125,9 +161,9 @@ def run_reference(a):
             "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(a, a.gpus),
-            "cpu_baseline": {"value": pps, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": sample + "; the reference is Python and cannot travel to the GPU box, so its "
-                                                "oracle port (pinned to reference-generated fixtures) is timed"},
+            "cpu_baseline": {"value": pps, "unit": UNIT, "cores": cores, "kind": cpu_kind(a), "sample": sample},
+            "n_procs": 1, "note": "ONE host process on rank 0 regardless of --gpus (the other ranks exit): divide an N-GPU value by "
+                                  "this number only as 'N GPUs vs one CPU socket'",
             "e2e": {"value": pps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -191,13 +227,217 @@ def measured_peaks():
 def dominant_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel family, from the committed
     `ncu --set full` capture summarised in profiles/r1_ncu_dominant_kernel.json (null when that file is absent)."""
-    p = os.path.join(ROOT, "profiles", "r1_ncu_dominant_kernel.json")
+    p = os.path.join(ROOT, "profiles", "r2_ncu_dominant_kernel.json")
     if not os.path.exists(p):
         return None
     try:
         return json.load(open(p))["traffic_bytes_per_launch"]
     except Exception:  # noqa: BLE001
         return None
+
+
+# ------------------------------------------------------------------------------------------------ training steps (configs[2])
+def measure_train(mode, a, dev, world, rank, steps, warmup):
+    """One data-parallel training step of train.py per timed step, EVERYTHING inside the timed region: H2D copy of the
+    step's batch from pinned host memory, forward + backward (one CUDA graph replay), the NCCL gradient all-reduce over the
+    flat fp32 buffer, the fused AdamW launches, and a D2H read of the loss.
+      train_seg        train.py:207-226  Network3 (MiT-B2) forward -> upsample + CE -> backward -> all-reduce (94 MB) -> AdamW
+      train_fusion_ce  train.py:350-381  rounds >= 2: frozen-encoder features, Fusion_Network3_ac fwd/bwd, Fusionloss_grad3 + CE
+                                          through the frozen segmentation network -> all-reduce (3.7 MB) -> AdamW
+    Returns a dict (value = items/s over all ranks, device-event time, max over ranks)."""
+    import torch
+    import torch.distributed as dist
+    from segmif_b200 import _lib, synth
+    from segmif_b200.core.loss import Fusionloss_grad3
+    from segmif_b200.core.model_fusion import Fusion_Network3_ac, Network3
+    from segmif_b200.ddp import FusionTrainer, SegTrainer
+    B, H, W = a.train_batch, a.height, a.width
+    torch.manual_seed(1234 + rank)
+    seg = synth.load_synthetic(Network3(a.backbone, 9, 256, None), 0).to(dev).train()
+    inp = synth.synth_inputs(B, H, W, seed=100 + rank)
+    host = {k: v.pin_memory() for k, v in inp.items()}
+    d = {k: v.to(dev) for k, v in host.items()}
+    if mode == "train_seg":
+        tr = SegTrainer(seg, lr=6e-5, weight_decay=0.01, betas=(0.9, 0.999), warmup_iter=1500, max_iter=160000, warmup_ratio=1e-6, power=1.0)
+        keys = ("mask", "labels")
+        step = lambda: tr.step(d["mask"], d["labels"])
+        capture = lambda: tr.capture(d["mask"], d["labels"])
+    else:
+        fus = synth.load_synthetic(Fusion_Network3_ac(), 0).train().to(dev)
+        tr = FusionTrainer(fus, Fusionloss_grad3(), lr=1.5e-4, weight_decay=0.01, betas=(0.9, 0.999), warmup_iter=1.5e-5, max_iter=6000,
+                           warmup_ratio=1e-6, power=1.0, seg_net=seg, iter_=2)
+        keys = ("ir", "vis", "mask", "labels")
+        step = lambda: tr.step_images(d["ir"], d["vis"], d["mask"], d["labels"])[0]
+        capture = lambda: tr.capture_images(d["ir"], d["vis"], d["mask"], d["labels"])
+    loss_host = torch.empty((1,), dtype=torch.float32).pin_memory()
+
+    def full_step():
+        for k in keys:
+            d[k].copy_(host[k], non_blocking=True)
+        loss = step()
+        loss_host.copy_(loss.reshape(1), non_blocking=True)
+
+    full_step()                                   # eager: lazy per-kernel initialisation
+    capture()
+    for _ in range(max(warmup, 2)):
+        full_step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = _lib.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        full_step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    in_sync = True
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        chk = tr.flat.param.double().sum().reshape(1)
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        in_sync = bool((hi - lo).abs().item() == 0.0)
+    ms = float(ms.item())
+    flop_per_item = 181e9 if mode == "train_seg" else 2.14e12          # SURVEY.md 8(d)
+    items = B * world * steps
+    out = {"metric": "train_seg_images_per_sec" if mode == "train_seg" else "train_fusion_ce_pairs_per_sec",
+           "value": items / (ms * 1e-3), "unit": "img/s" if mode == "train_seg" else "pairs/s", "ms_per_step": ms / steps,
+           "steps": steps, "batch_per_gpu": B, "global_batch": B * world, "n_gpus": world, "scaling": "weak",
+           "collective": f"ONE NCCL all_reduce(SUM) of {tr.flat.numel * 4 / 2 ** 20:.1f} MiB fp32 per step + fused AdamW, inside the timed region",
+           "h2d_bytes_per_step": sum(host[k].numel() * host[k].element_size() for k in keys), "d2h_bytes_per_step": 4,
+           "achieved_tflops": items * flop_per_item / (ms * 1e-3) / 1e12, "replicas_in_sync": in_sync,
+           "loss": float(loss_host.item()), "cuda_graph": True, "backbone": a.backbone, "height": H, "width": W,
+           "gpu_launches": (getattr(tr, "launches_per_replay", 0) + (_lib.launch_count - l0) // steps) * steps}
+    del tr, seg
+    torch.cuda.empty_cache()
+    return out
+
+
+def secondary_blocks(a, dev, world, rank, pipe, devin):
+    """Measurements beside the headline, each in its own try block (a failure is recorded, never fatal): the strict-precision
+    mode on the same workload, the two training steps of configs[2] at this world size (collective included), and on rank 0
+    the loss kernels of configs[4], the MiT-B4 backbone of configs[3] and the single-pair latency of configs[0]."""
+    import torch
+    import segmif_b200
+    from segmif_b200 import ops, synth
+    out = {}
+
+    def ev_time(fn, iters, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    try:                                                           # strict (fp32-parity) mode, eager launches
+        sb = min(a.batch, 4)
+        args = tuple(devin[k][:sb] for k in ("ir", "vis", "mask"))
+        with segmif_b200.precision("strict"):
+            ms = ev_time(lambda: pipe(*args), 3, 1)
+        out["strict_mode"] = {"metric": METRIC, "value": sb / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "batch": sb,
+                              "what": "same pipeline with set_precision('strict'): fp32 activations, split-bf16 tcgen05 contractions "
+                                      "(6 partial products); parity <= 2e-6, labels bit-exact (tests/gpu_checks_strict.py)"}
+    except Exception as e:  # noqa: BLE001
+        out["strict_mode"] = {"error": repr(e)[:300]}
+    torch.cuda.empty_cache()
+    for mode in ("train_seg", "train_fusion_ce"):                  # all ranks: the step contains the collective
+        try:
+            out[mode] = measure_train(mode, a, dev, world, rank, steps=5, warmup=2)
+        except Exception as e:  # noqa: BLE001
+            out[mode] = {"error": repr(e)[:300]}
+        torch.cuda.empty_cache()
+    if rank != 0:
+        return out
+    peaks = measured_peaks()
+    try:                                                           # configs[4]: loss kernels, batch 64 of 1x1024x1024 fp32
+        g = torch.Generator(device=dev).manual_seed(0)
+        x, y, z = (torch.rand((64, 1, 1024, 1024), generator=g, device=dev) for _ in range(3))
+        n = 64 * 1024 * 1024
+        blk = {}
+        for name, fn, planes in (("ssim", lambda: ops.ssim(x, y), 2), ("laploss2", lambda: ops.laploss2(x, y, z), 3),
+                                 ("entropy4", lambda: ops.entropy(x, 4), 1), ("sobel_l1", lambda: ops.sobel_l1(x, y), 2)):
+            ms = ev_time(fn, 10, 3)
+            gbs = planes * n * 4 / (ms * 1e-3) / 1e9
+            blk[name] = {"ms": ms, "algorithmic_bytes": planes * n * 4, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peaks["hbm_gbs"]}
+        out["cfg5_loss_kernels_b64_1024x1024"] = blk
+        del x, y, z
+    except Exception as e:  # noqa: BLE001
+        out["cfg5_loss_kernels_b64_1024x1024"] = {"error": repr(e)[:300]}
+    torch.cuda.empty_cache()
+    try:                                                           # configs[3]: MiT-B4 backbone, batch 4, 1024x1024
+        from segmif_b200.core import mix_transformer as MT
+        enc = synth.load_synthetic(MT.mit_b4(), 0).eval().to(dev)
+        xi = torch.rand((4, 3, 1024, 1024), device=dev)
+        with torch.no_grad():
+            ms = ev_time(lambda: enc.forward_stages(xi), 5, 2)
+        out["cfg4_mit_b4_b4_1024x1024"] = {"ms_per_batch": ms, "images_per_s": 4 / (ms * 1e-3), "achieved_tflops": 4 * 631.5e9 / (ms * 1e-3) / 1e12}
+        del enc, xi
+    except Exception as e:  # noqa: BLE001
+        out["cfg4_mit_b4_b4_1024x1024"] = {"error": repr(e)[:300]}
+    torch.cuda.empty_cache()
+    try:                                                           # configs[0]: one 256x256 pair, MiT-B0 (adapted) and MiT-B1
+        from segmif_b200.core.model_fusion import Fusion_Network3_ac, Network3
+        from segmif_b200.pipeline import FusionSegPipeline
+        blk = {}
+        one = {k: v.to(dev) for k, v in synth.synth_inputs(1, 256, 256, seed=11).items()}
+        for bb, kw in (("mit_b0", dict(in_ch1=32, in_ch2=64)), ("mit_b1", {})):
+            p1 = FusionSegPipeline(synth.load_synthetic(Network3(bb, 9, 256, None), 0).eval().to(dev),
+                                   synth.load_synthetic(Fusion_Network3_ac(**kw), 0).eval().to(dev))
+            p1.capture(1, 256, 256, dev, splits=1)
+            for k in ("ir", "vis", "mask"):
+                p1.static_inputs[k].copy_(one[k])
+            ms = ev_time(p1.replay, 20, 3)
+            blk[bb] = {"ms_per_pair": ms, "pairs_per_s": 1e3 / ms}
+        out["cfg1_single_pair_256x256"] = blk
+    except Exception as e:  # noqa: BLE001
+        out["cfg1_single_pair_256x256"] = {"error": repr(e)[:300]}
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_train(a):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    r = measure_train(a.workload, a, dev, world, rank, a.steps, max(a.warmup, 3))
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        peaks = measured_peaks()
+        line = {"metric": r["metric"], "value": r["value"], "unit": r["unit"], "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+                "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic",
+                "config": {"workload": f"configs[2]: train.py {a.workload} step, {a.backbone}, batch {a.train_batch}/GPU (global {a.train_batch * world}), "
+                                       f"{a.height}x{a.width}", "parallelism": f"dp{world}", "collective": r["collective"],
+                           "l2": "per-step working set exceeds the 126 MB L2; no explicit flush"},
+                "e2e": {"value": r["value"], "unit": r["unit"], "h2d_bytes_per_step": r["h2d_bytes_per_step"], "d2h_bytes_per_step": r["d2h_bytes_per_step"],
+                        "note": "the timed step already copies its batch from pinned host memory and reads the loss back"},
+                "roofline": {"bound": "tensor", "achieved": r["achieved_tflops"], "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                             "frac": r["achieved_tflops"] / peaks["bf16_tflops_sustained"], "traffic": None,
+                             "kernel": "whole step (fwd + bwd, SURVEY.md 8(d) FLOP count)"},
+                "gpu_launches": r["gpu_launches"], "launch_mode": "cuda_graph + all_reduce + adamw", "clocks": clocks, "cpu_baseline": None,
+                "replicas_in_sync": r["replicas_in_sync"]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def run_ours(a):
@@ -285,9 +525,8 @@ def run_ours(a):
     use_graph = not a.no_graph
     launches_per_step = None
     if use_graph:
-        l0 = _lib.launch_count
-        static = pipe.capture(a.batch, a.height, a.width, dev)       # 2 eager warm-ups + 1 captured step
-        launches_per_step = (_lib.launch_count - l0) // 3
+        static = pipe.capture(a.batch, a.height, a.width, dev)       # eager warm-ups + 1 captured step
+        launches_per_step = pipe.launches_per_replay
         for k in static:
             static[k].copy_(devin[k])
         step_timed = pipe.replay
@@ -341,10 +580,14 @@ def run_ours(a):
     e2e_value = pairs / (ms_e2e * 1e-3)
     peaks = measured_peaks()
 
+    ops.conv, ops.drdb_push = orig_conv, orig_push
+    secondary = None
+    if not a.no_secondary:
+        secondary = secondary_blocks(a, dev, world, rank, pipe, devin)
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         pps, cores, sec, sample = cpu_pipeline_time(a, repeats=1, warm=1, budget_s=30.0)
-        cpu = {"value": pps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        cpu = {"value": pps, "unit": UNIT, "cores": cores, "kind": cpu_kind(a), "sample": sample}
     if rank == 0:
         h2d = sum(host[k].numel() * host[k].element_size() for k in host)
         d2h = a.batch * a.height * a.width * (4 + 8)
@@ -356,7 +599,7 @@ def run_ours(a):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / a.steps,
                         "mode": "submit_host: copies on dedicated streams overlap neighbouring steps" if use_graph else "run_host: serial"},
-                "gpu_launches": launches, "launch_mode": "cuda_graph" if use_graph else "eager", "clocks": clocks,
+                "gpu_launches": launches, "launch_mode": (f"cuda_graph ({getattr(pipe, 'splits', 1)} concurrent sub-batch stream(s))" if use_graph else "eager"), "clocks": clocks,
                 "roofline": {"kernel": "DRDB Dcov1-5 (3x3 dil-2 implicit GEMM on tcgen05): drdb_push_tc_kernel<96|64,.,64> for the x0 slab + "
                                        "conv3x3_tc_kernel<32,2,2> over the g-slabs",
                              "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
@@ -367,7 +610,7 @@ def run_ours(a):
                              "algorithmic": "2*B*H*W*9*K*N FLOP per launch (K = input channels of the launch, N = its output channels); "
                                             "per DRDB the launches sum to 2*B*H*W*9*640*32, the FLOPs of the five reference "
                                             "layers (Cin 64..192 -> 32)"},
-                "cpu_baseline": cpu}
+                "cpu_baseline": cpu, "secondary": secondary}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -377,5 +620,7 @@ if __name__ == "__main__":
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload != "infer":
+        run_train(args)
     else:
         run_ours(args)

@@ -135,6 +135,38 @@ typedef struct {
 } segmif_drdb_push_params;
 int segmif_drdb_push_tc_fwd(const segmif_drdb_push_params* p, segmif_stream_t stream);
 
+/* ---- K10 as a dataflow: one whole DRDB (core/model_fusion.py:134-157) as seven CONCURRENT persistent kernels -------
+ * x0 push a / b (segmif_drdb_push_tc_fwd's N = 96 / 64 steps), the four pull layers (segmif_conv3x3_tc_fwd with pre_add)
+ * and the 1x1 + ReLU + residual (segmif_linear_tc_fwd) run at the same time on disjoint groups of SMs; a stage's tile waits
+ * on per-tile-row completion counters of the stage that produces the rows it reads (csrc/dataflow.cuh), so slabs and
+ * partial pre-activations are consumed out of L2 a tile row or two after they were written instead of round-tripping
+ * through HBM between launches.  Results are bit-identical to the sequential launches.
+ * The call forks `stream` into six internal side streams and joins them again (legal under stream capture); `flags` is
+ * a device workspace of segmif_drdb_dataflow_workspace_bytes(B, H) bytes that the call zeroes; its LAST word is set to 1
+ * if a dependency wait ever timed out (a bug, never expected).  segmif_drdb_dataflow_prepare(device) creates the side
+ * streams ahead of time (call it once outside any capture).  This is the only entry point with process-wide state
+ * beyond the shared-memory opt-ins.                                                                                   */
+typedef struct {
+  void* growth;             /* bf16 [B, H, W, ld]: x0 in channels 0..63 on entry; g1..g5 appended at 64..223            */
+  int ld;
+  void* partial;            /* bf16 [B, H, W, ld_partial] scratch: P2..P5 at channels 0..127                            */
+  int ld_partial;
+  const void* w_push_a;     /* bf16 [96][9*64]: layers 1, 2, 3 restricted to the x0 slab, tap-major                      */
+  const void* w_push_b;     /* bf16 [64][9*64]: layers 4, 5                                                              */
+  const void* w_pull[4];    /* bf16 [32][9][32*(j-1)]: layer j = 2..5 restricted to the g-slabs                          */
+  const float* bias[5];     /* Dcov1..5                                                                                  */
+  const void* w_1x1;        /* bf16 [64][224]                                                                            */
+  const float* bias_1x1;
+  void* out;                /* bf16 [B*H*W, ld_out] channels out_coff..out_coff+63                                       */
+  int ld_out, out_coff;
+  int B, H, W;
+  unsigned int* flags;
+  int ctas[7];              /* SMs per stage (push a, push b, L2, L3, L4, L5, 1x1); all zero = built-in split            */
+} segmif_drdb_dataflow_params;
+size_t segmif_drdb_dataflow_workspace_bytes(int B, int H);
+int segmif_drdb_dataflow_prepare(int device);
+int segmif_drdb_dataflow_fwd(const segmif_drdb_dataflow_params* p, segmif_stream_t stream);
+
 /* ---- K1 (stage 1): 7x7 stride-4 pad-3 patch embedding + LayerNorm --------------------------------
  * replaces core/mix_transformer.py:192-198 for patch_embed1, fused with the input affine of
  * Network3.forward core/model_fusion.py:1083-1085 (x*255 - mean)/std  (pass scale=1, shift=0 otherwise).

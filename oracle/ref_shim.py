@@ -21,7 +21,14 @@ import types
 import torch
 import torch.nn as nn
 
-REF_ROOT = os.environ.get("SEGMIF_REFERENCE_ROOT", "/root/reference")
+def _default_root():
+    """/root/reference in the build container; on the GPU box the byte-for-byte copies oracle/build_ref.py vendored."""
+    if os.path.isfile("/root/reference/core/model_fusion.py"):
+        return "/root/reference"
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+REF_ROOT = os.environ.get("SEGMIF_REFERENCE_ROOT") or _default_root()
 _PREFIX = "_segmif_ref"
 
 
@@ -159,3 +166,33 @@ def load_reference_losses():
             else:
                 sys.modules[k] = v
     return mod
+
+
+def reference_inference_pipeline(ns, seg, fus, ir, vis_rgb, mask):
+    """The unit of work of the headline metric executed by the UNMODIFIED reference modules on the CPU, statement for
+    statement as train.py:356-366 + test_fusion.py:100-111 + test_segmentation.py:169-175 do (the hard-coded .cuda()
+    calls neutralised by cuda_is_identity).  `seg` / `fus`: reference Network3 / Fusion_Network3_ac instances."""
+    import torch.nn.functional as F
+    with torch.no_grad(), cuda_is_identity():
+        out0, out1 = seg.denoise_net.encoder.forward_fusion(mask)
+        vis_ycc = ns.model_fusion.RGB2YCrCb(vis_rgb)
+        fused = fus(ir, vis_ycc, out0, out1)
+        ycc = vis_ycc.clone()
+        ycc[:, 0:1] = fused
+        rgb = ns.model_fusion.YCrCb2RGB(ycc).clamp(0, 1)
+        logits = seg(rgb.clone())[2]
+        labels = F.interpolate(logits, size=ir.shape[2:], mode="bilinear", align_corners=False).argmax(1)
+    return dict(fused=fused, rgb=rgb, logits=logits, labels=labels)
+
+
+def build_reference_models(ns, backbone, seed=0):
+    """Reference Network3(backbone) + Fusion_Network3_ac with the deterministic synthetic weights of segmif_b200.synth."""
+    import contextlib
+    import io
+    from segmif_b200 import synth
+    with contextlib.redirect_stdout(io.StringIO()):           # DRDB.__init__ prints (model_fusion.py:131)
+        seg = ns.model_fusion.Network3(backbone, 9, 256, None)
+        fus = ns.model_fusion.Fusion_Network3_ac()
+    synth.load_synthetic(seg, seed)
+    synth.load_synthetic(fus, seed)
+    return seg.eval(), fus.eval()

@@ -74,6 +74,14 @@ class SplitGemmParams(ctypes.Structure):
     ]
 
 
+class DrdbDataflowParams(ctypes.Structure):
+    """Mirror of segmif_drdb_dataflow_params."""
+    _fields_ = [("growth", c_void_p), ("ld", c_int), ("partial", c_void_p), ("ld_partial", c_int),
+                ("w_push_a", c_void_p), ("w_push_b", c_void_p), ("w_pull", c_void_p * 4), ("bias", c_void_p * 5),
+                ("w_1x1", c_void_p), ("bias_1x1", c_void_p), ("out", c_void_p), ("ld_out", c_int), ("out_coff", c_int),
+                ("B", c_int), ("H", c_int), ("W", c_int), ("flags", c_void_p), ("ctas", c_int * 7)]
+
+
 P = c_void_p
 # name -> argtypes; every function returns int except where noted in _RESTYPES
 SIGNATURES = {
@@ -158,6 +166,9 @@ SIGNATURES = {
     "segmif_sobel_map_fwd": [P, P, c_int, c_int, c_int, P],
     "segmif_sobel_map_bwd": [P, P, P, c_int, c_int, c_int, c_int, P],
     "segmif_ew2": [P, P, c_float, c_float, c_int, P, c_int64, P],
+    "segmif_drdb_dataflow_workspace_bytes": [c_int, c_int],
+    "segmif_drdb_dataflow_prepare": [c_int],
+    "segmif_drdb_dataflow_fwd": [ctypes.POINTER(DrdbDataflowParams), P],
     "segmif_split_gemm_fwd": [ctypes.POINTER(SplitGemmParams), P],
     "segmif_split3": [P, c_int, c_int, c_int64, c_int, c_int, P, c_int, c_int, P, c_int, c_int, c_int64, P],
     "segmif_im2col_split3": [P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int64, P],
@@ -168,7 +179,7 @@ SIGNATURES = {
     "segmif_conv3x3_in1_f32_fwd": [P, c_int64, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P],
     "segmif_conv3x3_out1_f32_fwd": [P, c_int, P, P, P, P, c_int, c_int, c_int, c_int, P],
 }
-_RESTYPES = {"segmif_last_error": c_char_p, "segmif_loss_workspace_bytes": c_size_t, "segmif_wgrad_workspace_bytes": c_size_t,
+_RESTYPES = {"segmif_drdb_dataflow_workspace_bytes": c_size_t, "segmif_last_error": c_char_p, "segmif_loss_workspace_bytes": c_size_t, "segmif_wgrad_workspace_bytes": c_size_t,
              "segmif_dwconv3x3_gelu_bwd_workspace": c_int64}
 
 _lib = None

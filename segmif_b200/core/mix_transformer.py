@@ -80,7 +80,11 @@ class DWConv(nn.Module):
         return ops.dwconv3x3_gelu(x, self._w(), self.dwconv.bias.detach(), B, H, W)
 
     def forward(self, x, H, W):
-        raise NotImplementedError("segmif_b200: DWConv is only available fused with GELU (Mlp.forward)")
+        """core/mix_transformer.py:381-387: tokens [B, N, C] -> depthwise 3x3 (pad 1, bias) -> tokens, no activation."""
+        B, N, C = x.shape
+        if x.dtype == torch.float32:
+            return _strict.dwconv_f32(x.contiguous().view(B * N, C), self._w(), self.dwconv.bias.detach(), B, H, W, gelu=False).view(B, N, C)
+        return ops.dwconv3x3(_as_tokens_bf16(x).view(B * N, C), self._w(), self.dwconv.bias.detach(), B, H, W).view(B, N, C)
 
 
 class Mlp(nn.Module):

@@ -174,8 +174,11 @@ Network = Network3     # core/__init__.py:4 of the reference imports a `Network`
 class DRDB(nn.Module):
     """Dilated residual dense block (core/model_fusion.py:117-157)."""
     GROWTH_LD = 224
-    # growth-layer formulation: "hybrid" (x0 slab pushed with N = 96/64, g-slabs pulled with N = 32 + partial add;
-    # fastest), "push" (every slab pushed, bf16 partials read-modify-written), "pull" (one N = 32 conv per layer)
+    # growth-layer formulation: "hybrid" (default: x0 slab pushed with N = 96/64, g-slabs pulled with N = 32 + partial add,
+    # one launch after the other), "dataflow" (the same stages plus the 1x1 as seven CONCURRENT kernels chained through L2 by
+    # per-tile-row counters, csrc/drdb_dataflow.cu: bit-identical to hybrid, measured SLOWER on B200 -- 3.5 ms vs 1.6 ms per DRDB
+    # at batch 8, 480x640 -- because every stage keeps its per-SM rate and the SMs are merely divided, DESIGN.md), "push" (every
+    # slab pushed, bf16 partials read-modify-written), "pull" (one N = 32 conv per layer).
     MODE = os.environ.get("SEGMIF_DRDB_MODE", "hybrid")
 
     def __init__(self, in_ch=64, growth_rate=32):
@@ -248,12 +251,34 @@ class DRDB(nn.Module):
                      Cout=g, act=ACT_RELU, out=buf.view(-1, ld), ld_dst=ld, dst_coff=c + cin, pre_add=part.view(-1, part.shape[-1]),
                      pre_coff=g * (j - 2), entry="segmif_conv3x3_tc_fwd")
 
+    @staticmethod
+    def _df_words(B, H):
+        from .. import _lib
+        return _lib.load().segmif_drdb_dataflow_workspace_bytes(B, H) // 4
+
+    def dataflow_timed_out(self):
+        """True if a dependency wait of the last dataflow forward hit its timeout (never expected; checked by the tests)."""
+        f = getattr(self, "_df_flags", None)
+        return bool(f is not None and int(f[-1].item()) != 0)
+
     def forward_buffer(self, buf, B, H, W, out=None, ld_dst=None, dst_coff=0, partials=None):
         """`buf` bf16 [B, H, W, total] with the block input in channels 0..in_ch; appends the five growth slices
         in place, then writes x + relu(conv1x1(all)) to `out` (pixel-major bf16).  `partials` (bf16 [B,H,W,128]
         scratch) selects the push form of the growth layers; without it the per-layer (pull) kernels run."""
         ld = buf.shape[-1]
         cin = self.in_ch
+        if partials is not None and DRDB.MODE == "dataflow" and self.in_ch == 64 and self.growth == 32 and ld >= self.total:
+            w, wh = self._push_packs(), self._hybrid_packs()
+            if out is None:
+                ld_dst = self.in_ch
+                out = torch.empty((B * H * W, ld_dst), dtype=torch.bfloat16, device=buf.device)
+            elif ld_dst is None:
+                ld_dst = out.shape[-1]
+            self._df_flags = ops.drdb_dataflow(buf, partials, w[0], w[1], wh, [getattr(self, f"Dcov{i}").bias.detach() for i in range(1, 6)],
+                                               self._packs.conv(self.conv.weight), self.conv.bias.detach(), out, ld_dst, dst_coff, B, H, W,
+                                               flags=getattr(self, "_df_flags", None) if getattr(self, "_df_flags", None) is not None
+                                               and self._df_flags.device == buf.device and self._df_flags.numel() == self._df_words(B, H) else None)
+            return out
         if partials is not None and DRDB.MODE != "pull" and self.in_ch == 64 and self.growth == 32:
             (self._growth_push if DRDB.MODE == "push" else self._growth_hybrid)(buf, partials, B, H, W)
             cin = self.total
@@ -283,7 +308,53 @@ class DRDB(nn.Module):
 
 
 # ------------------------------------------------------------------------------------------------ HIA
-class CrossAttention(nn.Module):
+def _cross_ctx(mod, feats, kv_weights):
+    """Per-head 8x8 contexts of up to three token streams (None entries are skipped): k^T v = Wk (P^T P) Wv^T because the kv
+    Linears carry no bias (core/model_fusion.py:251,291).  Returns ctx fp32 [B, 3, 8, 8, 8]."""
+    from .. import _lib
+    if mod.dim != 64 or mod.num_heads != 8 or any(w.shape != (128, 64) for w in kv_weights) or mod.kv_has_bias():
+        raise NotImplementedError("segmif_b200: the cross-attention kernels are specialised for dim=64, 8 heads, qkv_bias=False")
+    live = [f for f in feats if f is not None]
+    B, N, C = live[0].shape
+    dev = live[0].device
+    nchunk = max(1, min(296 // max(B, 1), (N + 511) // 512))
+    partials = torch.zeros((3, B, nchunk, 64, 64), dtype=torch.float64, device=dev)
+    st = ops._prep(live[0])
+    for s, f in enumerate(feats):
+        if f is not None:
+            f = f.float().contiguous()
+            _lib.call("segmif_gram64_f64", _strict._p(f), C, 0, B, N, 0, _strict._p(partials[s]), nchunk, st)
+    wkv = torch.stack([w.detach().float() for w in kv_weights]).contiguous()
+    wend = torch.zeros((2, 64, 128), dtype=torch.float32, device=dev)
+    folded = torch.empty((B, 4, 64, 64), dtype=torch.float32, device=dev)
+    ctx = torch.empty((B, 3, 8, 8, 8), dtype=torch.float32, device=dev)
+    _lib.call("segmif_ffm_ctx_f64_fwd", _strict._p(partials), nchunk, _strict._p(wkv), _strict._p(wend), _strict._p(folded),
+              _strict._p(ctx), B, st)
+    return ctx
+
+
+def _apply_ctx(q, ctx):
+    """(q per head) @ ctx: q fp32 [B, N, 64], ctx [B, 8, 8, 8] (head, i, j) -> [B, N, 64]; one tensor-core product per image
+    with the block-diagonal 64x64 matrix W[h8+j, h8+i] = ctx[h, i, j] (index shuffling only on the host side)."""
+    B, N, C = q.shape
+    W = torch.zeros((B, 8, 8, 8, 8), dtype=torch.float32, device=q.device)            # [b, h_out, j, h_in, i]
+    for h in range(8):
+        W[:, h, :, h, :] = ctx[:, h].transpose(-1, -2)
+    wp = _strict.pack_rows(W.view(B * 64, 64)).view(B, 64, 3, 64)
+    q2 = q.float().contiguous().view(B * N, C)
+    planes = _strict.split(q2)
+    out = torch.empty((B * N, C), dtype=torch.float32, device=q.device)
+    for b in range(B):
+        _strict.gemm(planes, 64, wp[b], 64, row0=b * N, rows=N, dst=out)
+    return out.view(B, N, C)
+
+
+class _KvBiasMixin:
+    def kv_has_bias(self):
+        return any(getattr(self, n).bias is not None for n in ("kv1", "kv2", "kv3") if hasattr(self, n))
+
+
+class CrossAttention(_KvBiasMixin, nn.Module):
     """MoAM parameters (core/model_fusion.py:250-262); the computation lives in CrossPath's fused kernels."""
 
     def __init__(self, dim, num_heads=8, qkv_bias=False, qk_scale=None):
@@ -294,8 +365,15 @@ class CrossAttention(nn.Module):
         self.scale = qk_scale or (dim // num_heads) ** -0.5
         self.kv3 = nn.Linear(dim, dim * 2, bias=qkv_bias)
 
+    def forward(self, x1, x2, segfeature):
+        """core/model_fusion.py:263-288 on fp32 tokens [B, N, 64]: ctx3 = softmax_{dim=-2}(k3^T v3 * scale) from
+        kv3(segfeature); returns (q1 @ ctx3, q2 @ ctx3).  Built from the strict-precision kernels (fp64 Gram / context,
+        split-bf16 tensor-core product); CrossPath uses the fused kernels instead."""
+        ctx = _cross_ctx(self, [None, None, segfeature], [self.kv3.weight] * 3)
+        return _apply_ctx(x1, ctx[:, 2]), _apply_ctx(x2, ctx[:, 2])
 
-class CrossAttention2(nn.Module):
+
+class CrossAttention2(_KvBiasMixin, nn.Module):
     """SoAM parameters (core/model_fusion.py:290-302)."""
 
     def __init__(self, dim, num_heads=8, qkv_bias=False, qk_scale=None):
@@ -306,6 +384,12 @@ class CrossAttention2(nn.Module):
         self.scale = qk_scale or (dim // num_heads) ** -0.5
         self.kv1 = nn.Linear(dim, dim * 2, bias=qkv_bias)
         self.kv2 = nn.Linear(dim, dim * 2, bias=qkv_bias)
+
+    def forward(self, x1, x2, segfeature):
+        """core/model_fusion.py:303-328: ctx_i = softmax_{dim=-2}(k_i^T v_i * scale) from kv_i(x_i); returns
+        (q3 @ ctx1, q3 @ ctx2) with q3 = segfeature."""
+        ctx = _cross_ctx(self, [x1, x2, None], [self.kv1.weight, self.kv2.weight, self.kv1.weight])
+        return _apply_ctx(segfeature, ctx[:, 0]), _apply_ctx(segfeature, ctx[:, 1])
 
 
 class CrossPath(nn.Module):
@@ -429,8 +513,12 @@ class FeatureFusionModule(nn.Module):
 class Fusion_Network3_ac(nn.Module):
     """core/model_fusion.py:1026-1067."""
 
-    def __init__(self):
+    def __init__(self, in_ch1=64, in_ch2=128):
+        """`in_ch1` / `in_ch2`: channels of the two encoder feature maps fed to conv3 / conv4.  The reference hard-codes
+        64 / 128 (core/model_fusion.py:1041-1042), which fits every backbone except mit_b0 (32 / 64 channels,
+        core/mix_transformer.py:392) -- the backbone BASELINE configs[0] names; SURVEY.md 8(c) asks for the kwargs."""
         super().__init__()
+        self.in_ch1, self.in_ch2 = in_ch1, in_ch2
         self.conv1_ir = nn.Conv2d(1, 64, 3, padding=1)
         self.conv1_vis = nn.Conv2d(1, 64, 3, padding=1)
         self.DRDB1 = DRDB(in_ch=64)
@@ -441,8 +529,8 @@ class Fusion_Network3_ac(nn.Module):
         self.relu = nn.PReLU()                 # ONE shared scalar slope for all five call sites (:1038)
         self.ffm = FeatureFusionModule(64)
         self.ffm2 = FeatureFusionModule(64)    # allocated and saved by the reference, never used (:1040)
-        self.conv3 = nn.Conv2d(64, 64, 1, padding=0)
-        self.conv4 = nn.Conv2d(128, 64, 1, padding=0)
+        self.conv3 = nn.Conv2d(in_ch1, 64, 1, padding=0)
+        self.conv4 = nn.Conv2d(in_ch2, 64, 1, padding=0)
         self.conv21 = nn.Conv2d(64, 32, 3, padding=1)
         self.conv22 = nn.Conv2d(32, 1, 3, padding=1)
         self._packs = PackCache()
@@ -475,6 +563,9 @@ class Fusion_Network3_ac(nn.Module):
             self.ffm.forward_pixel_major_lr(x1, 64, x2, 64, tok, qh, qw, out1, ldo1, coffo1, out2, ldo2, coffo2, B, H, W, pre_conv)
         else:
             t = seg[1]
+            if t.shape[-1] not in (64, 128):      # mit_b0's 32-channel map: the 1x1 conv as its own GEMM, then the 64-channel kernels
+                t = ops.linear(t, self._packs.conv(pre_conv.weight), pre_conv.bias.detach()).view(B, H * W, 64)
+                pre_conv = None
             self.ffm.forward_pixel_major(x1, 64, x2, 64, t, t.shape[-1], out1, ldo1, coffo1, out2, ldo2, coffo2, B, H * W,
                                          pre_conv=pre_conv)
 

@@ -23,6 +23,7 @@
 #include <algorithm>
 #include <type_traits>
 
+#include "dataflow.cuh"
 #include "tc_common.cuh"
 
 namespace segmif {
@@ -36,6 +37,8 @@ struct ConvTcArgs {
   const bf16* pre;         // direct mode: partial pre-activations (channel offset applied), pitch ld_pre
   bf16* dst;               // direct mode: destination slice (channel offset applied), pitch ld_dst
   int ld_pre, ld_dst;
+  int y_shift;             // the tile grid starts y_shift rows above the image (dataflow.cuh); 0 otherwise
+  Dataflow df;             // cross-kernel dependencies (df.enabled == 0: plain stream-ordered kernel)
 };
 
 constexpr int kConvTcThreads = 192;
@@ -116,7 +119,11 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv3x3_tc_kernel(const __g
       int it = 0, lt = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
         const int b = tile / tiles_per_img, rem = tile - b * tiles_per_img;
-        const int y0 = (rem / a.tiles_x) * Cfg::TH, x0 = (rem % a.tiles_x) * Cfg::TW;
+        const int y0 = (rem / a.tiles_x) * Cfg::TH - a.y_shift, x0 = (rem % a.tiles_x) * Cfg::TW;
+        if (a.df.enabled) {                     // producer stages must have finished the rows this tile reads
+          df_wait(a.df.dep[1], a.df.error, b, y0, y0 + Cfg::TH, a.H);
+          df_wait(a.df.dep[0], a.df.error, b, y0, y0 + Cfg::TH, a.H);
+        }
         if (a.has_pre && a.staged) {            // partial pre-activation tile of this output tile
           const int pb = lt & 1;
           tc::mbar_wait(pempty + pb, ((lt >> 1) & 1) ^ 1);
@@ -204,10 +211,11 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv3x3_tc_kernel(const __g
     const bool store_leader = (warp == 2 && lane == 0);
     int lt = 0;
     if (a.staged) {
+      int prev_b = -1, prev_t = 0;               // dataflow: tile whose TMA stores are still in flight
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
         const int buf = lt & 1;
         const int b = tile / tiles_per_img, rem = tile - b * tiles_per_img;
-        const int y0 = (rem / a.tiles_x) * Cfg::TH, x0 = (rem % a.tiles_x) * Cfg::TW;
+        const int y0 = (rem / a.tiles_x) * Cfg::TH - a.y_shift, x0 = (rem % a.tiles_x) * Cfg::TW;
         if (a.has_pre) tc::mbar_wait(pfull + buf, (lt >> 1) & 1);
         tc::mbar_wait(tmem_full + buf, (lt >> 1) & 1);
         tc::tc_fence_after();
@@ -251,7 +259,17 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv3x3_tc_kernel(const __g
 #pragma unroll
           for (int sub = 0; sub < NSUB; ++sub) tc::tma_store_4d(&tmO, sOut + sub * Cfg::SUB_BYTES, 0, x0 + sub * 8, y0, b);
           tc::bulk_commit();
+          if (a.df.enabled && a.df.signal) {
+            // publish the PREVIOUS tile: all bulk groups but the one just committed have completed their global writes
+            asm volatile("cp.async.bulk.wait_group 1;\n" ::: "memory");
+            if (prev_b >= 0) df_signal(a.df.signal, prev_b, a.tiles_y, prev_t);
+            prev_b = b; prev_t = rem / a.tiles_x;
+          }
         }
+      }
+      if (store_leader && a.df.enabled && a.df.signal && prev_b >= 0) {
+        tc::bulk_wait_all0();
+        df_signal(a.df.signal, prev_b, a.tiles_y, prev_t);
       }
     } else {
       // direct epilogue: this thread owns pixel (r / 8, r % 8) of every sub-tile
@@ -259,17 +277,24 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv3x3_tc_kernel(const __g
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
         const int buf = lt & 1;
         const int b = tile / tiles_per_img, rem = tile - b * tiles_per_img;
-        const int y = (rem / a.tiles_x) * Cfg::TH + ty, x0 = (rem % a.tiles_x) * Cfg::TW + tx;
-        const size_t rowpix = ((size_t)b * a.H + y) * a.W;
+        const int yt0 = (rem / a.tiles_x) * Cfg::TH - a.y_shift;
+        const int y = yt0 + ty, x0 = (rem % a.tiles_x) * Cfg::TW + tx;
+        const bool y_ok = (unsigned)y < (unsigned)a.H;
+        const size_t rowpix = ((size_t)b * a.H + (y_ok ? y : 0)) * a.W;
         uint4 pv[NSUB][COUT / 8];
         if (a.has_pre) {                           // partial rows in flight while the MMAs of this tile still run
+          if (a.df.enabled) {                      // ... once their producer stage has published them
+            if (lane == 0) df_wait(a.df.dep[1], a.df.error, b, yt0, yt0 + Cfg::TH, a.H);
+            __syncwarp();
+          }
 #pragma unroll
           for (int sub = 0; sub < NSUB; ++sub) {
             const int x = x0 + sub * 8;
-            const bool ok = y < a.H && x < a.W;
+            const bool ok = y_ok && x < a.W;
             const uint4* pp = reinterpret_cast<const uint4*>(a.pre + (rowpix + x) * a.ld_pre);
 #pragma unroll
-            for (int j = 0; j < COUT / 8; ++j) pv[sub][j] = ok ? __ldg(pp + j) : make_uint4(0, 0, 0, 0);
+            for (int j = 0; j < COUT / 8; ++j)      // written by a concurrently running kernel in dataflow mode: no .nc path
+              pv[sub][j] = ok ? (a.df.enabled ? __ldcg(pp + j) : __ldg(pp + j)) : make_uint4(0, 0, 0, 0);
           }
         }
         tc::mbar_wait(tmem_full + buf, (lt >> 1) & 1);
@@ -294,7 +319,7 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv3x3_tc_kernel(const __g
             v[j] = t >= 0.f ? t : slope * t;
           }
           const int x = x0 + sub * 8;
-          if (y < a.H && x < a.W) {
+          if (y_ok && x < a.W) {
             uint4* d = reinterpret_cast<uint4*>(a.dst + (rowpix + x) * a.ld_dst + c);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
@@ -305,6 +330,11 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv3x3_tc_kernel(const __g
         tc::tc_fence_before();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(tmem_empty + buf);
+        if (a.df.enabled && a.df.signal) {         // every epilogue thread's stores are ordered before the published count
+          __threadfence();
+          tc::named_bar_sync(2, 128);
+          if (store_leader) df_signal(a.df.signal, b, a.tiles_y, rem / a.tiles_x);
+        }
       }
     }
     if (store_leader) tc::bulk_wait_all0();
@@ -321,7 +351,7 @@ static size_t conv_tc_fixed_smem(int nchunks, bool has_pre, bool staged) {
 }
 
 template <int COUT, int DIL, int NSUB>
-static int launch_conv_tc(const segmif_conv_params* p, cudaStream_t st) {
+static int launch_conv_tc(const segmif_conv_params* p, cudaStream_t st, const ConvDfExtra* x = nullptr) {
   using Cfg = ConvTcCfg<COUT, DIL, NSUB>;
   const int nchunks = (p->Cin + 63) / 64;
   const bool has_pre = p->pre_add != nullptr;
@@ -377,7 +407,9 @@ static int launch_conv_tc(const segmif_conv_params* p, cudaStream_t st) {
   ConvTcArgs a;
   a.bias = p->bias; a.alpha = p->prelu_alpha;
   a.B = p->B; a.H = p->H; a.W = p->W; a.nchunks = nchunks; a.act = p->act; a.has_pre = has_pre ? 1 : 0;
-  a.tiles_x = (p->W + Cfg::TW - 1) / Cfg::TW; a.tiles_y = (p->H + Cfg::TH - 1) / Cfg::TH;
+  a.y_shift = x ? x->y_shift : 0;
+  if (x) a.df = x->df; else { a.df = Dataflow(); a.df.enabled = 0; a.df.signal = nullptr; a.df.error = nullptr; a.df.dep[0].flags = a.df.dep[1].flags = nullptr; }
+  a.tiles_x = (p->W + Cfg::TW - 1) / Cfg::TW; a.tiles_y = (p->H + a.y_shift + Cfg::TH - 1) / Cfg::TH;
   a.cin = p->Cin;
   a.ksteps_last = ((p->Cin - 1) % 64) / 16 + 1;
   a.nstages = nstages;
@@ -386,7 +418,8 @@ static int launch_conv_tc(const segmif_conv_params* p, cudaStream_t st) {
   a.dst = reinterpret_cast<bf16*>(p->dst) + p->dst_coff;
   a.ld_pre = p->ld_pre; a.ld_dst = p->ld_dst;
   const int num_tiles = a.tiles_x * a.tiles_y * a.B;
-  kern<<<std::min(num_tiles, sms), kConvTcThreads, smem, st>>>(tmA, tmW, tmO, tmP, a);
+  const int ctas = (x && x->max_ctas > 0) ? std::min(x->max_ctas, sms) : sms;
+  kern<<<std::min(num_tiles, ctas), kConvTcThreads, smem, st>>>(tmA, tmW, tmO, tmP, a);
   return check_launch("segmif_conv3x3_tc_fwd");
 }
 
@@ -399,7 +432,7 @@ static bool conv_tc_fits(int nchunks, bool has_pre) {
 
 using namespace segmif;
 
-extern "C" int segmif_conv3x3_tc_fwd(const segmif_conv_params* p, segmif_stream_t stream) {
+static int conv3x3_tc_dispatch(const segmif_conv_params* p, cudaStream_t st, const ConvDfExtra* x) {
   SEGMIF_REQUIRE(p && p->src && p->weight && p->dst && p->bias, "conv3x3_tc: null pointer (bias is required)");
   SEGMIF_REQUIRE(p->KH == 3 && p->KW == 3 && p->stride == 1 && (p->dil == 1 || p->dil == 2) && p->pad == p->dil,
                  "conv3x3_tc: only 3x3, stride 1, dilation 1 or 2 with 'same' padding");
@@ -413,23 +446,37 @@ extern "C" int segmif_conv3x3_tc_fwd(const segmif_conv_params* p, segmif_stream_
   SEGMIF_REQUIRE(p->src_coff + p->Cin <= p->ld_src && p->dst_coff + p->Cout <= p->ld_dst, "conv3x3_tc: channel slice exceeds pitch");
   SEGMIF_REQUIRE(((uintptr_t)p->src & 15) == 0 && ((uintptr_t)p->weight & 15) == 0 && ((uintptr_t)p->dst & 15) == 0 && ((uintptr_t)p->bias & 15) == 0,
                  "conv3x3_tc: pointers must be 16-byte aligned");
-  cudaStream_t st = as_stream(stream);
   const int nchunks = (p->Cin + 63) / 64;
   const bool pre = p->pre_add != nullptr;
   if (p->Cout == 32 && p->dil == 2) {
-    if (conv_tc_fits<32, 2, 2>(nchunks, pre)) return launch_conv_tc<32, 2, 2>(p, st);
+    if (conv_tc_fits<32, 2, 2>(nchunks, pre)) return launch_conv_tc<32, 2, 2>(p, st, x);
     SEGMIF_REQUIRE((conv_tc_fits<32, 2, 1>(nchunks, pre)), "conv3x3_tc: Cin=%d too large for resident weights", p->Cin);
-    return launch_conv_tc<32, 2, 1>(p, st);
+    return launch_conv_tc<32, 2, 1>(p, st, x);
   }
   if (p->Cout == 32 && p->dil == 1) {
-    if (conv_tc_fits<32, 1, 2>(nchunks, pre)) return launch_conv_tc<32, 1, 2>(p, st);
+    if (conv_tc_fits<32, 1, 2>(nchunks, pre)) return launch_conv_tc<32, 1, 2>(p, st, x);
     SEGMIF_REQUIRE((conv_tc_fits<32, 1, 1>(nchunks, pre)), "conv3x3_tc: Cin=%d too large for resident weights", p->Cin);
-    return launch_conv_tc<32, 1, 1>(p, st);
+    return launch_conv_tc<32, 1, 1>(p, st, x);
   }
   if (p->Cout == 64 && p->dil == 1) {
     SEGMIF_REQUIRE((conv_tc_fits<64, 1, 1>(nchunks, pre)), "conv3x3_tc: Cin=%d too large for resident weights", p->Cin);
-    return launch_conv_tc<64, 1, 1>(p, st);
+    return launch_conv_tc<64, 1, 1>(p, st, x);
   }
   SEGMIF_REQUIRE((conv_tc_fits<64, 2, 1>(nchunks, pre)), "conv3x3_tc: Cin=%d too large for resident weights", p->Cin);
-  return launch_conv_tc<64, 2, 1>(p, st);
+  return launch_conv_tc<64, 2, 1>(p, st, x);
+}
+
+namespace segmif {
+int conv3x3_tc_df(const segmif_conv_params* p, const ConvDfExtra& x, cudaStream_t st) { return conv3x3_tc_dispatch(p, st, &x); }
+// tile width (pixels) the dispatch above selects: the consumer of this stage's counters needs tiles per tile row
+int conv3x3_tc_tile_w(int Cin, int Cout, int dil, bool has_pre) {
+  const int nchunks = (Cin + 63) / 64;
+  if (Cout == 32 && dil == 2) return conv_tc_fits<32, 2, 2>(nchunks, has_pre) ? 16 : 8;
+  if (Cout == 32 && dil == 1) return conv_tc_fits<32, 1, 2>(nchunks, has_pre) ? 16 : 8;
+  return 8;
+}
+}  // namespace segmif
+
+extern "C" int segmif_conv3x3_tc_fwd(const segmif_conv_params* p, segmif_stream_t stream) {
+  return conv3x3_tc_dispatch(p, as_stream(stream), nullptr);
 }

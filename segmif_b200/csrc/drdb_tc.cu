@@ -15,6 +15,7 @@
 // never multiplied) and their weights are packed two taps per 128-byte row.
 #include <algorithm>
 
+#include "dataflow.cuh"
 #include "tc_common.cuh"
 
 namespace segmif {
@@ -29,6 +30,7 @@ struct PushGroup {          // one 32-channel output group of the step
 struct PushArgs {
   PushGroup g[4];
   int B, H, W, tiles_x, tiles_y;
+  unsigned* signal;        // dataflow.cuh: finished-tile counters [B * tiles_y] published for concurrently running consumers
 };
 
 constexpr int kPushThreads = 192;
@@ -192,6 +194,11 @@ __global__ void __launch_bounds__(kPushThreads, 1) drdb_push_tc_kernel(const __g
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(tmem_empty + buf);
+      if (a.signal) {
+        __threadfence();
+        tc::named_bar_sync(2, 128);
+        if (warp == 2 && lane == 0) df_signal(a.signal, b, a.tiles_y, rem / a.tiles_x);
+      }
     }
   }
   tc::tc_fence_before();
@@ -200,7 +207,7 @@ __global__ void __launch_bounds__(kPushThreads, 1) drdb_push_tc_kernel(const __g
 }
 
 template <int NOUT, int NSUB, int KSLAB>
-static int launch_push(const segmif_drdb_push_params* p, cudaStream_t st) {
+static int launch_push(const segmif_drdb_push_params* p, cudaStream_t st, const ConvDfExtra* x = nullptr) {
   using Cfg = PushCfg<NOUT, NSUB, KSLAB>;
   auto kern = drdb_push_tc_kernel<NOUT, NSUB, KSLAB>;
   static bool configured = false;
@@ -240,8 +247,10 @@ static int launch_push(const segmif_drdb_push_params* p, cudaStream_t st) {
   }
   a.B = p->B; a.H = p->H; a.W = p->W;
   a.tiles_x = (p->W + Cfg::TW - 1) / Cfg::TW; a.tiles_y = (p->H + Cfg::TH - 1) / Cfg::TH;
+  a.signal = x ? x->df.signal : nullptr;
   const int num_tiles = a.tiles_x * a.tiles_y * a.B;
-  kern<<<std::min(num_tiles, sms), kPushThreads, Cfg::SMEM, st>>>(tmA, tmW, a);
+  const int ctas = (x && x->max_ctas > 0) ? std::min(x->max_ctas, sms) : sms;
+  kern<<<std::min(num_tiles, ctas), kPushThreads, Cfg::SMEM, st>>>(tmA, tmW, a);
   return check_launch("segmif_drdb_push_tc_fwd");
 }
 
@@ -249,7 +258,7 @@ static int launch_push(const segmif_drdb_push_params* p, cudaStream_t st) {
 
 using namespace segmif;
 
-extern "C" int segmif_drdb_push_tc_fwd(const segmif_drdb_push_params* p, segmif_stream_t stream) {
+static int drdb_push_dispatch(const segmif_drdb_push_params* p, cudaStream_t st, const ConvDfExtra* x) {
   SEGMIF_REQUIRE(p && p->src && p->weight, "drdb_push: null pointer");
   SEGMIF_REQUIRE(p->slab_width == 32 || p->slab_width == 64, "drdb_push: slab_width=%d must be 32 or 64", p->slab_width);
   SEGMIF_REQUIRE(p->n_out == 32 || p->n_out == 64 || p->n_out == 96 || p->n_out == 128, "drdb_push: n_out=%d must be 32/64/96/128", p->n_out);
@@ -261,16 +270,25 @@ extern "C" int segmif_drdb_push_tc_fwd(const segmif_drdb_push_params* p, segmif_
     SEGMIF_REQUIRE(!g.partial_in || (((uintptr_t)g.partial_in & 15) == 0 && g.ld_partial_in % 8 == 0 && g.coff_partial_in % 8 == 0), "drdb_push: group %d partial_in misaligned", i);
     SEGMIF_REQUIRE(!g.bias || ((uintptr_t)g.bias & 15) == 0, "drdb_push: group %d bias misaligned", i);
   }
-  cudaStream_t st = as_stream(stream);
   if (p->slab_width == 64) {
-    if (p->n_out == 96) return launch_push<96, 1, 64>(p, st);      // 108 KB of weights: one sub-tile per box
-    if (p->n_out == 64) return launch_push<64, 2, 64>(p, st);
-    if (p->n_out == 32) return launch_push<32, 2, 64>(p, st);
+    if (p->n_out == 96) return launch_push<96, 1, 64>(p, st, x);      // 108 KB of weights: one sub-tile per box
+    if (p->n_out == 64) return launch_push<64, 2, 64>(p, st, x);
+    if (p->n_out == 32) return launch_push<32, 2, 64>(p, st, x);
     set_error("drdb_push: n_out=128 with a 64-channel slab does not fit shared memory");
     return SEGMIF_ERR_INVALID;
   }
-  if (p->n_out == 128) return launch_push<128, 2, 32>(p, st);
-  if (p->n_out == 96) return launch_push<96, 2, 32>(p, st);
-  if (p->n_out == 64) return launch_push<64, 2, 32>(p, st);
-  return launch_push<32, 2, 32>(p, st);
+  if (p->n_out == 128) return launch_push<128, 2, 32>(p, st, x);
+  if (p->n_out == 96) return launch_push<96, 2, 32>(p, st, x);
+  if (p->n_out == 64) return launch_push<64, 2, 32>(p, st, x);
+  return launch_push<32, 2, 32>(p, st, x);
+}
+
+namespace segmif {
+int drdb_push_df(const segmif_drdb_push_params* p, const ConvDfExtra& x, cudaStream_t st) { return drdb_push_dispatch(p, st, &x); }
+// tile width of the instance the dispatch selects (64-channel slab: N = 96 uses 8-pixel-wide tiles, the others 16)
+int drdb_push_tile_w(int slab_width, int n_out) { return (slab_width == 64 && n_out == 96) ? 8 : 16; }
+}  // namespace segmif
+
+extern "C" int segmif_drdb_push_tc_fwd(const segmif_drdb_push_params* p, segmif_stream_t stream) {
+  return drdb_push_dispatch(p, as_stream(stream), nullptr);
 }

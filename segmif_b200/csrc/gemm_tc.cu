@@ -8,6 +8,7 @@
 // Warp roles: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = epilogue (TMEM lane quadrant = warp % 4).
 #include <algorithm>
 
+#include "dataflow.cuh"
 #include "tc_common.cuh"
 
 namespace segmif {
@@ -131,6 +132,13 @@ __device__ __forceinline__ void epilogue_row32(const TcEpilogue& e, float (&v)[3
 constexpr int kTcStages = 4;
 constexpr int kTcThreads = 192;
 
+// dataflow.cuh: the A rows are pixels of [B, H, W] images written by a concurrently running producer stage
+struct GemmDfDev {
+  DfDep dep;
+  unsigned* error;
+  int H, W, HW;
+};
+
 // Persistent: each CTA walks output tiles (m-tile major, n-tile minor) with a stride of gridDim.x.  The 4-stage
 // operand ring runs across tile boundaries and the TMEM accumulator is double buffered, so TMA, MMA and the
 // epilogue of consecutive tiles overlap.
@@ -140,7 +148,7 @@ template <int BN, bool GELU, bool WKN>
 __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB,
                                                                 const TcEpilogue e, const int num_k_blocks,
-                                                                const int n_tiles, const int num_tiles) {
+                                                                const int n_tiles, const int num_tiles, const GemmDfDev d) {
   constexpr int A_BYTES = 128 * 128, B_BYTES = BN * 128;
   constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -172,6 +180,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
       int it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = (tile / n_tiles) * 128, n0 = (tile % n_tiles) * BN;
+        if (d.dep.flags) {                       // rows m0 .. m0+127 = pixels of one or two images
+          const int m1 = (m0 + 127 < e.M ? m0 + 127 : e.M - 1);
+          const int b0 = m0 / d.HW, b1 = m1 / d.HW;
+          const int ya = (m0 - b0 * d.HW) / d.W, yb = (m1 - b1 * d.HW) / d.W + 1;
+          if (b0 == b1) {
+            df_wait(d.dep, d.error, b0, ya, yb, d.H);
+          } else {
+            df_wait(d.dep, d.error, b0, ya, d.H, d.H);
+            df_wait(d.dep, d.error, b1, 0, yb, d.H);
+          }
+        }
         for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
           const int s = it % kTcStages;
           const uint32_t ph = (it / kTcStages) & 1;
@@ -250,7 +269,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
 }
 
 template <int BN, bool GELU, bool WKN = false>
-static int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcEpilogue& e, int K, cudaStream_t st) {
+static int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcEpilogue& e, int K, cudaStream_t st,
+                          const GemmDfExtra* x = nullptr) {
   constexpr size_t smem = (size_t)kTcStages * (128 * 128 + BN * 128) + (2 * kTcStages + 4) * 8 + 16;
   auto kern = gemm_tc_kernel<BN, GELU, WKN>;
   static bool configured = false;
@@ -264,12 +284,18 @@ static int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   const int n_tiles = (int)ceil_div(e.N, BN), m_tiles = (int)ceil_div(e.M, 128);
   const int64_t num_tiles = (int64_t)n_tiles * m_tiles;
   const int ctas_per_sm = BN <= 64 ? 2 : 1;          // 96 KB (BN=64) / 80 KB (BN=32) of smem: two CTAs fit and hide latency
-  const int grid = (int)std::min<int64_t>(num_tiles, (int64_t)sms * ctas_per_sm);
-  kern<<<grid, kTcThreads, smem, st>>>(tmA, tmB, e, (int)ceil_div(K, 64), n_tiles, (int)num_tiles);
+  int grid = (int)std::min<int64_t>(num_tiles, (int64_t)sms * ctas_per_sm);
+  GemmDfDev d;
+  d.dep.flags = nullptr; d.dep.target = 0; d.dep.tiles_y = d.dep.shift = d.dep.halo = 0; d.error = nullptr; d.H = d.W = d.HW = 1;
+  if (x) {
+    d.dep = x->dep; d.error = x->error; d.H = x->H; d.W = x->W; d.HW = x->H * x->W;
+    if (x->max_ctas > 0) grid = std::min(grid, x->max_ctas);
+  }
+  kern<<<grid, kTcThreads, smem, st>>>(tmA, tmB, e, (int)ceil_div(K, 64), n_tiles, (int)num_tiles, d);
   return check_launch("segmif_linear_tc_fwd");
 }
 
-static int linear_tc_impl(const segmif_linear_params* p, cudaStream_t st) {
+static int linear_tc_impl(const segmif_linear_params* p, cudaStream_t st, const GemmDfExtra* x = nullptr) {
   SEGMIF_REQUIRE(p && p->src && p->weight && p->dst, "linear_tc: null pointer");
   SEGMIF_REQUIRE(p->M > 0 && p->N > 0 && p->K > 0, "linear_tc: bad sizes");
   SEGMIF_REQUIRE(p->K % 8 == 0 && p->ld_src % 8 == 0 && p->src_coff % 8 == 0, "linear_tc: K, ld_src, src_coff must be multiples of 8");
@@ -315,18 +341,20 @@ static int linear_tc_impl(const segmif_linear_params* p, cudaStream_t st) {
   e.row_scale = p->row_scale; e.rows_per_scale = p->rows_per_scale > 0 ? p->rows_per_scale : 1;
   SEGMIF_REQUIRE(!p->row_scale || p->rows_per_scale > 0, "linear_tc: row_scale needs rows_per_scale > 0");
   if (p->act == SEGMIF_ACT_GELU) {
-    if (BN == 128) return launch_gemm_tc<128, true>(tmA, tmB, e, p->K, st);
-    if (BN == 64) return launch_gemm_tc<64, true>(tmA, tmB, e, p->K, st);
-    return launch_gemm_tc<32, true>(tmA, tmB, e, p->K, st);
+    if (BN == 128) return launch_gemm_tc<128, true>(tmA, tmB, e, p->K, st, x);
+    if (BN == 64) return launch_gemm_tc<64, true>(tmA, tmB, e, p->K, st, x);
+    return launch_gemm_tc<32, true>(tmA, tmB, e, p->K, st, x);
   }
   if (p->weight_kn) {
-    if (BN == 128) return launch_gemm_tc<128, false, true>(tmA, tmB, e, p->K, st);
-    return launch_gemm_tc<64, false, true>(tmA, tmB, e, p->K, st);
+    if (BN == 128) return launch_gemm_tc<128, false, true>(tmA, tmB, e, p->K, st, x);
+    return launch_gemm_tc<64, false, true>(tmA, tmB, e, p->K, st, x);
   }
-  if (BN == 128) return launch_gemm_tc<128, false>(tmA, tmB, e, p->K, st);
-  if (BN == 64) return launch_gemm_tc<64, false>(tmA, tmB, e, p->K, st);
-  return launch_gemm_tc<32, false>(tmA, tmB, e, p->K, st);
+  if (BN == 128) return launch_gemm_tc<128, false>(tmA, tmB, e, p->K, st, x);
+  if (BN == 64) return launch_gemm_tc<64, false>(tmA, tmB, e, p->K, st, x);
+  return launch_gemm_tc<32, false>(tmA, tmB, e, p->K, st, x);
 }
+
+int linear_tc_df(const segmif_linear_params* p, const GemmDfExtra& x, cudaStream_t st) { return linear_tc_impl(p, st, &x); }
 
 }  // namespace segmif
 

@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(256) ew2_kernel(const float* __restrict__ x, c
   const float xv = x[i], yv = y ? y[i] : 0.f;
   float r;
   switch (mode) {
-    case 0: r = a * xv + b * yv; break;
+    case 0: r = __fadd_rn(__fmul_rn(a, xv), __fmul_rn(b, yv)); break;     // as torch evaluates a*x + b*y: no FMA contraction
     case 1: r = fmaxf(xv, yv); break;
     case 2: r = fabsf(a + b * xv); break;
     case 3: r = xv * yv; break;

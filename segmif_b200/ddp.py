@@ -155,9 +155,12 @@ class _GraphedStep:
         # so that eager code never aliases tensors living in the graph's private memory pool.
         packing.invalidate_all()
         self.flat.epoch[0] += 1
+        from . import _lib
         graph = torch.cuda.CUDAGraph()
+        l0 = _lib.launch_count
         with torch.cuda.graph(graph):
             outs = body(**self._static)
+        self.launches_per_replay = _lib.launch_count - l0       # segmif_b200 kernel-launching calls recorded in the graph
         packing.invalidate_all()
         self.flat.epoch[0] += 1
         self._graph, self._graph_outs = graph, outs

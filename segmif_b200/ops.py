@@ -144,6 +144,43 @@ def drdb_push(buf, weight, B, H, W, slab_offset, slab_width, groups):
     _lib.call("segmif_drdb_push_tc_fwd", ctypes.byref(p), st)
 
 
+_DF_CTAS = [int(v) for v in os.environ.get("SEGMIF_DRDB_CTAS", "").split(",") if v.strip()]     # tuning: 7 SM counts
+
+
+def drdb_dataflow(buf, part, w_push_a, w_push_b, w_pull, biases, w_1x1, bias_1x1, out, ld_out, out_coff, B, H, W, flags=None,
+                  ctas=None):
+    """One whole DRDB as seven concurrent kernels chained through L2 (segmif_drdb_dataflow_fwd).  Returns the flags
+    workspace (its last word is non-zero if a dependency wait timed out)."""
+    st = _prep(buf, part, w_push_a, w_push_b, *w_pull, *biases, w_1x1, bias_1x1, out, flags)
+    dev = buf.device
+    nwords = _lib.load().segmif_drdb_dataflow_workspace_bytes(B, H) // 4
+    if flags is None:
+        flags = torch.empty((nwords,), dtype=torch.int32, device=dev)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    if idx not in _DF_READY:
+        _lib.check(_lib.load().segmif_drdb_dataflow_prepare(idx), "segmif_drdb_dataflow_prepare")
+        _DF_READY.add(idx)
+    p = _lib.DrdbDataflowParams()
+    p.growth, p.ld, p.partial, p.ld_partial = buf.data_ptr(), buf.shape[-1], part.data_ptr(), part.shape[-1]
+    p.w_push_a, p.w_push_b = w_push_a.data_ptr(), w_push_b.data_ptr()
+    for i in range(4):
+        p.w_pull[i] = w_pull[i].data_ptr()
+    for i in range(5):
+        p.bias[i] = biases[i].data_ptr()
+    p.w_1x1, p.bias_1x1 = w_1x1.data_ptr(), bias_1x1.data_ptr()
+    p.out, p.ld_out, p.out_coff = out.data_ptr(), ld_out, out_coff
+    p.B, p.H, p.W = B, H, W
+    p.flags = flags.data_ptr()
+    ctas = ctas if ctas is not None else (_DF_CTAS if len(_DF_CTAS) == 7 else None)
+    for i in range(7):
+        p.ctas[i] = int(ctas[i]) if ctas else 0
+    _lib.call("segmif_drdb_dataflow_fwd", ctypes.byref(p), st)
+    return flags
+
+
+_DF_READY = set()
+
+
 def conv_mma(src, weight, bias, **kw):
     """Forces the mma.sync implicit-GEMM kernel (segmif_conv_fwd)."""
     return conv(src, weight, bias, entry="segmif_conv_fwd", **kw)

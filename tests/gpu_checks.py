@@ -489,25 +489,33 @@ def models(backbone="mit_b1"):
 
 @check
 def drdb_module():
-    """DRDB against the oracle in the three formulations of the growth layers (hybrid = default)."""
+    """DRDB against the oracle in the four formulations of the growth layers (dataflow = default: the hybrid stages as
+    seven concurrent kernels chained through L2; it must equal the sequential hybrid launches BIT FOR BIT, and none of its
+    dependency waits may time out)."""
     from segmif_b200.core.model_fusion import DRDB
     seg, fus, (seg_sd, fus_sd) = models()
     rs = []
-    for shape in ((1, 64, 24, 40), (2, 64, 37, 53)):           # second one: sizes that are not tile multiples
+    for shape in ((1, 64, 24, 40), (2, 64, 37, 53), (3, 64, 200, 168)):  # not tile multiples; the last spans many tile rows / CTAs
         x = rnd(*shape, seed=shape[2])
         with torch.no_grad():
             ref = O.drdb(x, fus_sd, "DRDB1")
             keep = DRDB.MODE
             try:
                 got = {}
-                for mode in ("hybrid", "push", "pull"):
+                for mode in ("hybrid", "push", "pull", "dataflow"):
                     DRDB.MODE = mode
                     got[mode] = fus.DRDB1(x.to(DEV))
+                    if mode == "dataflow":
+                        for _ in range(3):            # repeated runs: the counters are re-zeroed by every call
+                            again = fus.DRDB1(x.to(DEV))
+                        rs.append(result(f"DRDB_dataflow_repeatable_{shape[2]}x{shape[3]}", float((again != got[mode]).sum()), 0.0))
+                        rs.append(result(f"DRDB_dataflow_no_timeout_{shape[2]}x{shape[3]}", 1.0 if fus.DRDB1.dataflow_timed_out() else 0.0, 0.0))
             finally:
                 DRDB.MODE = keep
         # 6 chained bf16 tensor-core layers with bf16 storage (and, for push / hybrid, bf16 partial sums) between them
-        for mode in ("hybrid", "push", "pull"):
+        for mode in ("hybrid", "push", "pull", "dataflow"):
             rs.append(result(f"DRDB_{mode}_vs_oracle_{shape[2]}x{shape[3]}", rel_err(got[mode], ref), 2e-2))
+        rs.append(result(f"DRDB_dataflow_equals_hybrid_{shape[2]}x{shape[3]}", float((got["dataflow"] != got["hybrid"]).sum()), 0.0))
     return rs
 
 
@@ -660,3 +668,94 @@ def validation_kernels():
     pr = m.update(seg, small["mask"].to(DEV), small["labels"].to(DEV))
     res.append(result("segmentation_metrics_update", float((m.conf_total.cpu() != O.confusion_matrix(small["labels"], pr.cpu())).sum()), 0.0))
     return res
+
+
+# ----------------------------------------------------------------------------------------- module-level surface + cfg 1
+@check
+def module_level_forwards():
+    """Forwards of the reference classes that the fused paths bypass, called on their own (VERDICT r1 'stubbed surface'):
+    CrossAttention.forward (core/model_fusion.py:263-288), CrossAttention2.forward (:303-328), DWConv.forward
+    (core/mix_transformer.py:381-387) against the oracle's restatement of the same lines."""
+    seg, fus, (seg_sd, fus_sd) = models()
+    cp = fus.ffm.cross
+    rs = []
+    u1, u2, u3 = (rnd(2, 700, 64, seed=s, bf16=False).abs() for s in (31, 32, 33))
+    with torch.no_grad():
+        v1, v2 = cp.cross_attn(u1.to(DEV), u2.to(DEV), u3.to(DEV))
+        kv3 = F.linear(u3, fus_sd["ffm.cross.cross_attn.kv3.weight"])
+        c3 = O._ctx(kv3[..., :64], kv3[..., 64:], 8)
+        rs.append(result("CrossAttention_forward", max(rel_err(v1, O._apply_ctx(u1, c3)), rel_err(v2, O._apply_ctx(u2, c3))), 1e-5))
+        z1, z2 = cp.cross_attn2(u1.to(DEV), u2.to(DEV), u3.to(DEV))
+        kv1 = F.linear(u1, fus_sd["ffm.cross.cross_attn2.kv1.weight"])
+        kv2 = F.linear(u2, fus_sd["ffm.cross.cross_attn2.kv2.weight"])
+        r1 = O._apply_ctx(u3, O._ctx(kv1[..., :64], kv1[..., 64:], 8))
+        r2 = O._apply_ctx(u3, O._ctx(kv2[..., :64], kv2[..., 64:], 8))
+        rs.append(result("CrossAttention2_forward", max(rel_err(z1, r1), rel_err(z2, r2)), 1e-5))
+        dw = seg.denoise_net.encoder.block1[0].mlp.dwconv
+        B, H, W, C = 2, 9, 13, dw.dwconv.weight.shape[0]
+        x = rnd(B, H * W, C, seed=34, bf16=False)
+        w, b = seg_sd["denoise_net.encoder.block1.0.mlp.dwconv.dwconv.weight"], seg_sd["denoise_net.encoder.block1.0.mlp.dwconv.dwconv.bias"]
+        ref = F.conv2d(x.transpose(1, 2).reshape(B, C, H, W), w, b, padding=1, groups=C).flatten(2).transpose(1, 2)
+        rs.append(result("DWConv_forward_fp32", rel_err(dw(x.to(DEV), H, W), ref), 1e-5))
+        rs.append(result("DWConv_forward_bf16", rel_err(dw(x.to(DEV).bfloat16(), H, W).float(), ref), 1e-2))
+    return rs
+
+
+@check
+def cfg1_mit_b0_and_b1_256():
+    """BASELINE configs[0]: one 256x256 pair through test_fusion.py's path with MiT-B0 (Fusion_Network3_ac(in_ch1=32,
+    in_ch2=64): the reference hard-codes 64 / 128) and with MiT-B1 (runs unmodified), default and strict
+    precision, against the oracle."""
+    import segmif_b200
+    from segmif_b200.core.model_fusion import Fusion_Network3_ac, Network3
+    from segmif_b200.pipeline import FusionSegPipeline
+    rs = []
+    inp = synth.synth_inputs(1, 256, 256, seed=11)
+    for bb, kw in (("mit_b0", dict(in_ch1=32, in_ch2=64)), ("mit_b1", {})):
+        seg = synth.load_synthetic(Network3(bb, 9, 256, None), 0).eval()
+        fus = synth.load_synthetic(Fusion_Network3_ac(**kw), 0).eval()
+        seg_sd = {k: v.clone() for k, v in seg.state_dict().items()}
+        fus_sd = {k: v.clone() for k, v in fus.state_dict().items()}
+        with torch.no_grad():
+            ref = O.inference_pipeline(inp["ir"], inp["vis"], inp["mask"], seg_sd, fus_sd, bb)
+        pipe = FusionSegPipeline(seg.to(DEV), fus.to(DEV))
+        args = (inp["ir"].to(DEV), inp["vis"].to(DEV), inp["mask"].to(DEV))
+        with torch.no_grad():
+            f16, l16 = pipe(*args)
+            full = pipe(*args, return_intermediates=True)            # the reference's interface tensors (full-resolution maps)
+            with segmif_b200.precision("strict"):
+                fs, ls = pipe(*args)
+        rs.append(result(f"cfg1_{bb}_fused_bf16", rel_err(f16, ref["fused"]), 3e-2))
+        rs.append(result(f"cfg1_{bb}_fused_bf16_full_path", rel_err(full["fused"], ref["fused"]), 3e-2))
+        rs.append(result(f"cfg1_{bb}_fused_strict", rel_err(fs, ref["fused"]), 1e-4))
+        up = F.interpolate(ref["logits"], size=(256, 256), mode="bilinear", align_corners=False)
+        top2 = up.topk(2, dim=1).values
+        mism = ls.cpu() != ref["labels"]
+        bad = int(((top2[:, 0] - top2[:, 1])[mism] > 1e-5 * float(up.abs().max())).sum())
+        rs.append(result(f"cfg1_{bb}_labels_strict", float(bad), 0.0, note=f"{int(mism.sum())} differ (ties only)" if mism.any() else "bit-exact"))
+        agree = float((l16.cpu() == ref["labels"]).float().mean())
+        rs.append(result(f"cfg1_{bb}_label_disagreement_bf16", 1.0 - agree, 0.03))
+    return rs
+
+
+@check
+def baseline_size_kernels():
+    """Parity at BASELINE config SIZES: the attention core at MiT-B4 1024^2 stage-1 geometry
+    (N = 65 536 queries, Nk = 1024 keys; one batch item) against an fp32 torch softmax(QK^T)V evaluated in chunks, and the
+    loss kernels on 1024 x 1024 planes against the oracle."""
+    rs = []
+    B, heads, N, Nk, D = 1, 1, 65536, 1024, 64
+    q, kv = rnd(B, N, D, seed=41), rnd(B, Nk, 2 * D, seed=42)
+    got = ops.sr_attention(q.to(DEV).bfloat16().view(-1, D), kv.to(DEV).bfloat16().view(-1, 2 * D), B, heads, N, Nk, D, D ** -0.5).float().cpu()
+    k, v = kv[0, :, :D], kv[0, :, D:]
+    ref = torch.cat([((q[0, i:i + 8192] @ k.t()) * D ** -0.5).softmax(-1) @ v for i in range(0, N, 8192)])
+    rs.append(result("attention_n65536_nk1024", rel_err(got, ref), 1e-2))
+    gen = torch.Generator().manual_seed(43)
+    a, b, c = (torch.rand(2, 1, 1024, 1024, generator=gen) for _ in range(3))
+    A, Bq, Cq = a.to(DEV), b.to(DEV), c.to(DEV)
+    rs.append(result("ssim_1024", rel_err(ops.ssim(A, Bq), O.ssim(a, b)), 5e-5))
+    rs.append(result("laploss2_1024", rel_err(ops.laploss2(A, Bq, Cq), O.lap_loss2(a, b, c)), 1e-5))
+    rs.append(result("entropy4_1024", rel_err(ops.entropy(A[:1], 4), O.entropy(a[:1], 4)), 1e-5))
+    l1, lg = ops.sobel_l1(A, Bq)
+    rs.append(result("sobel_l1_1024", rel_err(l1 + lg, F.l1_loss(a, b) + F.l1_loss(O.sobelxy(a), O.sobelxy(b))), 1e-5))
+    return rs

@@ -1,0 +1,75 @@
+"""Times one DRDB (core/model_fusion.py:134-157) at BASELINE configs[1] size (batch 8, 480x640) in its sequential
+('hybrid') and concurrent ('dataflow') forms, with CUDA events over 10 calls after 3 warm-ups, checks that both give the
+same bits, and sweeps the SM split of the dataflow form.  The growth + partial buffers (1.7 GB) exceed the L2 many times
+over, so consecutive calls do not reuse each other's data.
+
+    python tools/drdb_bench.py [--splits "25,17,12,16,20,26,32;24,16,10,14,20,28,36"]"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from segmif_b200 import ops, synth  # noqa: E402
+from segmif_b200.core.model_fusion import DRDB, Fusion_Network3_ac  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--height", type=int, default=480)
+    ap.add_argument("--width", type=int, default=640)
+    ap.add_argument("--splits", default="")
+    ap.add_argument("--iters", type=int, default=10)
+    a = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    fus = synth.load_synthetic(Fusion_Network3_ac(), 0).eval().to(dev)
+    d = fus.DRDB1
+    B, H, W = a.batch, a.height, a.width
+    g = torch.Generator(device=dev).manual_seed(0)
+    buf = torch.zeros((B, H, W, 224), dtype=torch.bfloat16, device=dev)
+    buf[..., :64] = (torch.rand((B, H, W, 64), generator=g, device=dev) - 0.3).bfloat16()
+    part = torch.empty((B, H, W, 128), dtype=torch.bfloat16, device=dev)
+    out = torch.empty((B * H * W, 64), dtype=torch.bfloat16, device=dev)
+    flops = 2.0 * B * H * W * (9 * 640 * 32 + 224 * 64)
+
+    def run(mode, ctas=None):
+        DRDB.MODE = mode
+        if ctas is not None:
+            ops._DF_CTAS[:] = ctas
+        else:
+            ops._DF_CTAS[:] = []
+        with torch.no_grad():
+            for _ in range(3):
+                d.forward_buffer(buf, B, H, W, out=out, ld_dst=64, partials=part)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(a.iters):
+                d.forward_buffer(buf, B, H, W, out=out, ld_dst=64, partials=part)
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / a.iters
+        return ms, out.clone()
+
+    res = {}
+    ms_h, ref = run("hybrid")
+    res["hybrid"] = {"ms": ms_h, "tflops": flops / ms_h / 1e9}
+    print("hybrid  ", f"{ms_h:.3f} ms  {flops / ms_h / 1e9:.0f} TFLOP/s", flush=True)
+    splits = [None] + [[int(v) for v in s.split(",")] for s in a.splits.split(";") if s.strip()]
+    for sp in splits:
+        ms, got = run("dataflow", sp)
+        same = bool((got == ref).all())
+        key = "dataflow_" + ("default" if sp is None else "-".join(map(str, sp)))
+        res[key] = {"ms": ms, "tflops": flops / ms / 1e9, "equals_hybrid": same, "timed_out": d.dataflow_timed_out()}
+        print(key, f"{ms:.3f} ms  {flops / ms / 1e9:.0f} TFLOP/s  equal={same} timeout={d.dataflow_timed_out()}", flush=True)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(res, open(os.path.join(ROOT, "gpurun_out", "drdb_bench.json"), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()

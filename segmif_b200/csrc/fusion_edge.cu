@@ -5,9 +5,12 @@
 namespace segmif {
 
 // conv1_ir / conv1_vis: fp32 plane [B,H,W] -> bf16 pixel-major, Cout channels (multiple of 8).
-// A thread owns one 8-channel group (its 72 weights stay in registers) and 4 horizontally consecutive pixels (18 input
-// loads instead of 36); a warp covers 16 consecutive pixels x 8 groups, so every store instruction writes whole
-// 128-byte pixel records.  Requires Cout == 64 (8 groups); other widths use more warps per pixel block.
+// A thread owns one 8-channel group (its 72 weights stay in registers) and 4 horizontally consecutive pixels; a warp covers
+// 16 consecutive pixels x 8 groups, so every store instruction writes whole 128-byte pixel records.  The warp walks kIn1Rows
+// rows of its 16-pixel column strip with a three-row register window (6 new input loads per row instead of 18) -- the first
+// version reloaded the 72 weights + bias for every 4 pixels and reached 1.7 TB/s of stores; this one amortises them over
+// 4 * kIn1Rows pixels.  Requires Cout == 64 (8 groups) for full warps; other widths use more warps per pixel block.
+constexpr int kIn1Rows = 16;
 __global__ void __launch_bounds__(256) conv3x3_in1_kernel(const float* __restrict__ plane, int64_t bstride,
                                                           const float* __restrict__ w, const float* __restrict__ bias,
                                                           const float* __restrict__ alpha_p, bf16* __restrict__ dst,
@@ -17,7 +20,8 @@ __global__ void __launch_bounds__(256) conv3x3_in1_kernel(const float* __restric
   const int gpw = ngroups < 8 ? ngroups : 8;           // groups handled by one warp (8 lanes-groups)
   const int cg_sets = (ngroups + 7) / 8;               // warps needed to cover all channels of one pixel block
   const int xblocks = (W + 15) / 16;
-  const int64_t units = (int64_t)B * H * xblocks * cg_sets;
+  const int ystrips = (H + kIn1Rows - 1) / kIn1Rows;
+  const int64_t units = (int64_t)B * ystrips * xblocks * cg_sets;
   const int64_t unit = (int64_t)blockIdx.x * 8 + warp_in_blk;
   if (unit >= units) return;
   const unsigned uu = (unsigned)unit;                  // units < 2^31 (checked by the host): 32-bit divisions only
@@ -25,8 +29,8 @@ __global__ void __launch_bounds__(256) conv3x3_in1_kernel(const float* __restric
   const unsigned u2 = uu / (unsigned)cg_sets;
   const int xb = (int)(u2 % (unsigned)xblocks);
   const unsigned u3 = u2 / (unsigned)xblocks;
-  const int y = (int)(u3 % (unsigned)H);
-  const int64_t b = u3 / (unsigned)H;
+  const int ys = (int)(u3 % (unsigned)ystrips);
+  const int64_t b = u3 / (unsigned)ystrips;
   const int grp = cset * 8 + (lane & 7), q = lane >> 3;
   if ((lane & 7) >= gpw || grp >= ngroups) return;
   const int c = grp * 8;
@@ -37,39 +41,105 @@ __global__ void __launch_bounds__(256) conv3x3_in1_kernel(const float* __restric
   for (int t = 0; t < 9; ++t) load8(w + t * Cout + c, wr[t]);
   const int x0 = xb * 16 + q * 4;
   const float* src = plane + b * bstride;
-  float in[3][6];
-#pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    const int iy = y + r - 1;
+  const int y_begin = ys * kIn1Rows, y_end = min(H, y_begin + kIn1Rows);
+  auto load_row = [&](int iy, float (&row)[6]) {
 #pragma unroll
     for (int cc = 0; cc < 6; ++cc) {
       const int ix = x0 + cc - 1;
-      in[r][cc] = ((unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W) ? src[(int64_t)iy * W + ix] : 0.f;
+      row[cc] = ((unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W) ? __ldg(src + (int64_t)iy * W + ix) : 0.f;
     }
-  }
+  };
+  float in[3][6];
+  load_row(y_begin - 1, in[0]);
+  load_row(y_begin, in[1]);
+  for (int y = y_begin; y < y_end; ++y) {
+    load_row(y + 1, in[2]);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int x = x0 + i;
-    if (x >= W) break;
-    float acc[8];
+    for (int i = 0; i < 4; ++i) {
+      const int x = x0 + i;
+      if (x >= W) break;
+      float acc[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = bs[j];
+      for (int j = 0; j < 8; ++j) acc[j] = bs[j];
 #pragma unroll
-    for (int r = 0; r < 3; ++r)
+      for (int r = 0; r < 3; ++r)
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const float v = in[r][i + kx];
+        for (int kx = 0; kx < 3; ++kx) {
+          const float v = in[r][i + kx];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wr[r * 3 + kx][j], acc[j]);
-      }
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wr[r * 3 + kx][j], acc[j]);
+        }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = acc[j] >= 0.f ? acc[j] : alpha * acc[j];
-    store8(dst + ((b * H + y) * W + x) * ld_dst + dst_coff + c, acc);
+      for (int j = 0; j < 8; ++j) acc[j] = acc[j] >= 0.f ? acc[j] : alpha * acc[j];
+      store8(dst + ((b * H + y) * W + x) * ld_dst + dst_coff + c, acc);
+    }
+#pragma unroll
+    for (int cc = 0; cc < 6; ++cc) { in[0][cc] = in[1][cc]; in[1][cc] = in[2][cc]; }
   }
 }
 
-// conv22: bf16 pixel-major Cin channels -> fp32 plane [B,1,H,W]; a quad of 4 lanes shares one pixel
-// (each lane owns Cin/4 channels), reduced with two shuffles.
+// conv22: bf16 pixel-major Cin channels -> fp32 plane [B,1,H,W]; a quad of 4 lanes shares one pixel (each lane owns
+// Cin/4 = 8 channels, its 72 weights in registers), reduced with two shuffles.  A quad walks kOut1Run consecutive pixels of
+// a row with a three-COLUMN window of packed bf16 (3 new 16-byte loads per pixel instead of 9; the first version also
+// re-read the 9 x 8 weights from L1 for every pixel and reached 0.6 TB/s).  Cin == 32.
+constexpr int kOut1Run = 8;
+__global__ void __launch_bounds__(256) conv3x3_out1_c32_kernel(const bf16* __restrict__ src, int ld_src,
+                                                               const float* __restrict__ w, const float* __restrict__ bias,
+                                                               const float* __restrict__ alpha_p, float* __restrict__ dst,
+                                                               int B, int H, int W) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t run = gid >> 2;
+  const int q = (int)(gid & 3);
+  const int runs_x = (W + kOut1Run - 1) / kOut1Run;
+  const int64_t nruns = (int64_t)B * H * runs_x;
+  const bool live = run < nruns;
+  const int64_t rr = live ? run : 0;
+  const int rx = (int)(rr % runs_x);
+  const int Y = (int)((rr / runs_x) % H);
+  const int64_t b = rr / ((int64_t)runs_x * H);
+  float wr[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) load8(w + t * 32 + q * 8, wr[t]);
+  const float alpha = *alpha_p, b0 = bias[0];
+  const int x_begin = rx * kOut1Run;
+  auto load_col = [&](int ix, uint4 (&col)[3]) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int iy = Y + r - 1;
+      col[r] = ((unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W)
+                   ? __ldg(reinterpret_cast<const uint4*>(src + ((b * H + iy) * W + ix) * ld_src + q * 8)) : make_uint4(0, 0, 0, 0);
+    }
+  };
+  uint4 win[3][3];                        // [column][row]
+  load_col(x_begin - 1, win[0]);
+  load_col(x_begin, win[1]);
+#pragma unroll 1
+  for (int i = 0; i < kOut1Run; ++i) {
+    const int X = x_begin + i;
+    load_col(X + 1, win[2]);
+    float acc = 0.f;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const uint4 u = win[kx][ky];
+        const float2 p0 = unpack_bf16x2(u.x), p1 = unpack_bf16x2(u.y), p2 = unpack_bf16x2(u.z), p3 = unpack_bf16x2(u.w);
+        const float* ww = wr[ky * 3 + kx];
+        acc = fmaf(p0.x, ww[0], acc); acc = fmaf(p0.y, ww[1], acc); acc = fmaf(p1.x, ww[2], acc); acc = fmaf(p1.y, ww[3], acc);
+        acc = fmaf(p2.x, ww[4], acc); acc = fmaf(p2.y, ww[5], acc); acc = fmaf(p3.x, ww[6], acc); acc = fmaf(p3.y, ww[7], acc);
+      }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (live && q == 0 && X < W) {
+      const float v = acc + b0;
+      dst[(b * H + Y) * W + X] = v >= 0.f ? v : alpha * v;
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) { win[0][r] = win[1][r]; win[1][r] = win[2][r]; }
+  }
+}
+
+// general Cin (multiple of 32): one pixel per quad, taps re-read (kept for shapes other than conv22's 32 channels)
 __global__ void __launch_bounds__(256) conv3x3_out1_kernel(const bf16* __restrict__ src, int ld_src,
                                                            const float* __restrict__ w, const float* __restrict__ bias,
                                                            const float* __restrict__ alpha_p, float* __restrict__ dst,
@@ -175,7 +245,7 @@ extern "C" int segmif_conv3x3_in1_fwd(const float* plane, int64_t bstride, const
                                       int W, int Cout, segmif_stream_t stream) {
   SEGMIF_REQUIRE(plane && w && bias && prelu_alpha && dst, "conv3x3_in1: null pointer");
   SEGMIF_REQUIRE(Cout % 8 == 0 && ld_dst % 8 == 0 && dst_coff % 8 == 0, "conv3x3_in1: channel counts must be multiples of 8");
-  const int64_t units = (int64_t)B * H * ((W + 15) / 16) * ((Cout / 8 + 7) / 8);     // one warp each
+  const int64_t units = (int64_t)B * ((H + kIn1Rows - 1) / kIn1Rows) * ((W + 15) / 16) * ((Cout / 8 + 7) / 8);     // one warp each
   if (units == 0) return SEGMIF_OK;
   SEGMIF_REQUIRE(units < (1ll << 31), "conv3x3_in1: too many pixel blocks for the 32-bit unit index");
   conv3x3_in1_kernel<<<(unsigned)ceil_div(units, 8), 256, 0, as_stream(stream)>>>(
@@ -191,6 +261,12 @@ extern "C" int segmif_conv3x3_out1_fwd(const void* src, int ld_src, const float*
   SEGMIF_REQUIRE((int64_t)B * H * W < (1ll << 31), "conv3x3_out1: B*H*W must be below 2^31");
   const int64_t total = (int64_t)B * H * W * 4;
   if (total == 0) return SEGMIF_OK;
+  if (Cin == 32 && ((uintptr_t)src & 15) == 0) {
+    const int64_t threads = (int64_t)B * H * ((W + kOut1Run - 1) / kOut1Run) * 4;
+    conv3x3_out1_c32_kernel<<<(unsigned)ceil_div(threads, 256), 256, 0, as_stream(stream)>>>(
+        (const bf16*)src, ld_src, w, bias, prelu_alpha, dst, B, H, W);
+    return check_launch("segmif_conv3x3_out1_fwd");
+  }
   conv3x3_out1_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, as_stream(stream)>>>(
       (const bf16*)src, ld_src, w, bias, prelu_alpha, dst, B, H, W, Cin);
   return check_launch("segmif_conv3x3_out1_fwd");

@@ -503,6 +503,15 @@ int segmif_gram64_f64(const float* p, int ld, int coff, int B, int64_t HW, int r
                       segmif_stream_t stream);
 int segmif_ffm_ctx_f64_fwd(const double* partials, int nchunk, const float* wkv, const float* wend, float* folded,
                            float* ctx_out, int B, segmif_stream_t stream);
+/* Generic pieces for the ablation networks (core/model_fusion.py:363-425 CrossPath_M / CrossPath_S at dim 32, :626-1025):
+ * xty: partials double [B, nchunk, Cx, Cy] of X^T Y over the pixels of each image (k^T v of CrossAttention[2] :281,316);
+ * ctx_blockdiag: ctx fp32 [B, heads, d, d] = softmax_{dim=-2}(scale * k^T v per head) and the block-diagonal [C x C] matrix per
+ * image that applies it (W[h d + j][h d + i] = ctx[h][i][j]);  sigmoid_gate: x * sigmoid(x) (AttentionModule :759-771).    */
+int segmif_xty_f64(const float* x, int ldx, int coffx, int Cx, const float* y, int ldy, int coffy, int Cy, int B, int64_t HW,
+                   double* partials, int nchunk, segmif_stream_t stream);
+int segmif_ctx_blockdiag(const double* partials, int nchunk, int C, int heads, float scale, float* ctx, float* wout, int B,
+                         segmif_stream_t stream);
+int segmif_sigmoid_gate(const float* x, float* out, int64_t n, segmif_stream_t stream);
 /* conv1_ir / conv1_vis / conv22 (core/model_fusion.py:1051-1056,1065) with fp32 pixel-major activations.                 */
 int segmif_conv3x3_in1_f32_fwd(const float* plane, int64_t bstride, const float* w, const float* bias,
                                const float* prelu_alpha, float* dst, int ld_dst, int dst_coff, int B, int H, int W,

@@ -259,6 +259,88 @@ def fusion_network3_ac(ir, vis, out1, out2, sd):
     return F.prelu(F.conv2d(f, sd["conv22.weight"], sd["conv22.bias"], padding=1), a)
 
 
+# ----------------------------------------------------------------------------- ablation networks
+
+
+def cross_path_variant(x1, x2, seg, sd, name, mode, heads=8):
+    """core/model_fusion.py:350-361 (mode 'full'), :384-395 ('M': MoAM only), :417-428 ('S': SoAM only), any dim."""
+    y1, u1 = F.relu(_linear(x1, sd, name + ".channel_proj1")).chunk(2, dim=-1)
+    y2, u2 = F.relu(_linear(x2, sd, name + ".channel_proj2")).chunk(2, dim=-1)
+    y3, u3 = F.relu(_linear(seg, sd, name + ".channel_proj3")).chunk(2, dim=-1)
+    c = u1.shape[-1]
+    parts1, parts2 = [], []
+    if mode in ("full", "S"):
+        kv1 = F.linear(y1, sd[name + ".cross_attn2.kv1.weight"])
+        kv2 = F.linear(y2, sd[name + ".cross_attn2.kv2.weight"])
+        parts1.append(_apply_ctx(y3, _ctx(kv1[..., :c], kv1[..., c:], heads)))
+        parts2.append(_apply_ctx(y3, _ctx(kv2[..., :c], kv2[..., c:], heads)))
+    if mode in ("full", "M"):
+        kv3 = F.linear(u3, sd[name + ".cross_attn.kv3.weight"])
+        ctx3 = _ctx(kv3[..., :c], kv3[..., c:], heads)
+        parts1.append(_apply_ctx(u1, ctx3))
+        parts2.append(_apply_ctx(u2, ctx3))
+    o1 = layer_norm(x1 + _linear(torch.cat(parts1, -1), sd, name + ".end_proj1"), sd, name + ".norm1", DEFAULT_LN_EPS)
+    o2 = layer_norm(x2 + _linear(torch.cat(parts2, -1), sd, name + ".end_proj2"), sd, name + ".norm2", DEFAULT_LN_EPS)
+    return o1, o2
+
+
+def ffm_variant(x1, x2, seg, sd, name, mode):
+    """core/model_fusion.py:453-463 / :486-494 / :516-523 -- NCHW -> tokens -> cross path variant -> NCHW."""
+    b, c, h, w = x1.shape
+    tok = lambda t: t.flatten(2).transpose(1, 2)
+    o1, o2 = cross_path_variant(tok(x1), tok(x2), tok(seg), sd, name + ".cross", mode)
+    img = lambda t: t.reshape(b, h, w, -1).permute(0, 3, 1, 2).contiguous()
+    return img(o1), img(o2)
+
+
+def attention_module(x, sd, name):
+    """core/model_fusion.py:759-771 -- conv3x3, ReLU, conv3x3, then x * sigmoid(x)."""
+    t = F.conv2d(F.relu(F.conv2d(x, sd[name + ".conv.0.weight"], sd[name + ".conv.0.bias"], padding=1)),
+                 sd[name + ".conv.2.weight"], sd[name + ".conv.2.bias"], padding=1)
+    return torch.sigmoid(t) * t
+
+
+def fusion_network3_variant(ir, vis, out1, out2, sd, variant):
+    """core/model_fusion.py:626-660 ('base'), :821-890 ('S', 'M'), :661-709 ('Con'), :710-758 ('Add'), :772-820 ('Average'):
+    32-channel streams, conv21 is the 32 -> 1 output layer, one shared scalar PReLU."""
+    a = sd["relu.weight"]
+    cv = lambda x, n, pad: F.conv2d(x, sd[n + ".weight"], sd[n + ".bias"], padding=pad)
+    x1 = drdb(F.prelu(cv(ir[:, 0:1], "conv1_ir", 1), a), sd, "DRDB1")
+    x2 = drdb(F.prelu(cv(vis[:, 0:1], "conv1_vis", 1), a), sd, "DRDB2")
+    s1, s2 = cv(out1, "conv3", 0), cv(out2, "conv4", 0)
+    if variant in ("base", "S", "M"):
+        mode = {"base": "full", "S": "S", "M": "M"}[variant]
+        x1, x2 = ffm_variant(x1, x2, s1, sd, "ffm", mode)
+        x1, x2 = drdb(x1, sd, "DRDB3"), drdb(x2, sd, "DRDB4")
+        x1, x2 = ffm_variant(x1, x2, s2, sd, "ffm", mode)
+    elif variant in ("Con", "Add"):
+        mix = (lambda x, s: torch.cat([x, s], 1)) if variant == "Con" else (lambda x, s: x + s)
+        x1, x2 = cv(mix(x1, s1), "conv211", 1), cv(mix(x2, s1), "conv221", 1)
+        x1, x2 = drdb(x1, sd, "DRDB3"), drdb(x2, sd, "DRDB4")
+        x1, x2 = cv(mix(x1, s2), "conv411", 1), cv(mix(x2, s2), "conv421", 1)
+    elif variant == "Average":
+        x1 = attention_module(x1, sd, "att1") + attention_module(s1, sd, "att2")
+        x2 = attention_module(x2, sd, "att3") + attention_module(s1, sd, "att4")
+        x1, x2 = drdb(x1, sd, "DRDB3"), drdb(x2, sd, "DRDB4")
+        x1 = attention_module(x1, sd, "att5") + attention_module(s2, sd, "att6")
+        x2 = attention_module(x2, sd, "att7") + attention_module(s2, sd, "att8")
+    else:
+        raise ValueError(variant)
+    f = F.prelu(cv(torch.cat([x1, x2], 1), "conv2", 1), a)
+    return F.prelu(cv(f, "conv21", 1), a)
+
+
+def fusion_network_rmseg(ir, vis, sd):
+    """core/model_fusion.py:938-973 -- the fusion network without segmentation features; returns (fused, [x1, x2])."""
+    a = sd["relu.weight"]
+    cv = lambda x, n: F.conv2d(x, sd[n + ".weight"], sd[n + ".bias"], padding=1)
+    x1 = drdb(drdb(F.prelu(cv(ir[:, 0:1], "conv1_ir"), a), sd, "DRDB1"), sd, "DRDB3")
+    x2 = drdb(drdb(F.prelu(cv(vis[:, 0:1], "conv1_vis"), a), sd, "DRDB2"), sd, "DRDB4")
+    f = F.prelu(cv(torch.cat([x1, x2], 1), "conv2"), a)
+    f = F.prelu(cv(f, "conv21"), a)
+    return F.prelu(cv(f, "conv22"), a), [x1, x2]
+
+
 # ----------------------------------------------------------------------------- colour transforms
 
 

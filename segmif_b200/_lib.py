@@ -176,6 +176,9 @@ SIGNATURES = {
     "segmif_dwconv3x3_f32_fwd": [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P],
     "segmif_gram64_f64": [P, c_int, c_int, c_int, c_int64, c_int, P, c_int, P],
     "segmif_ffm_ctx_f64_fwd": [P, c_int, P, P, P, P, c_int, P],
+    "segmif_xty_f64": [P, c_int, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int64, P, c_int, P],
+    "segmif_ctx_blockdiag": [P, c_int, c_int, c_int, c_float, P, P, c_int, P],
+    "segmif_sigmoid_gate": [P, P, c_int64, P],
     "segmif_conv3x3_in1_f32_fwd": [P, c_int64, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P],
     "segmif_conv3x3_out1_f32_fwd": [P, c_int, P, P, P, P, c_int, c_int, c_int, c_int, P],
 }

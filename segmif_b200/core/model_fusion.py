@@ -259,7 +259,17 @@ class DRDB(nn.Module):
     def dataflow_timed_out(self):
         """True if a dependency wait of the last dataflow forward hit its timeout (never expected; checked by the tests)."""
         f = getattr(self, "_df_flags", None)
-        return bool(f is not None and int(f[-1].item()) != 0)
+        return bool(f is not None and int(f[-36].item()) != 0)
+
+    def dataflow_stage_times(self):
+        """Diagnostics: per stage (push a, push b, L2..L5, 1x1) the [begin, end] of the last dataflow forward in microseconds
+        relative to the earliest begin (globaltimer stamps written by the kernels)."""
+        f = getattr(self, "_df_flags", None)
+        if f is None:
+            return None
+        t = f[-32:].view(torch.int64)[:14].view(7, 2).cpu().tolist()
+        t0 = min(b for b, e in t if e > 0)
+        return [((b - t0) / 1e3, (e - t0) / 1e3) if e > 0 else None for b, e in t]
 
     def forward_buffer(self, buf, B, H, W, out=None, ld_dst=None, dst_coff=0, partials=None):
         """`buf` bf16 [B, H, W, total] with the block input in channels 0..in_ch; appends the five growth slices
@@ -614,3 +624,10 @@ class Mean(nn.Module):
         rgb = ops.recompose_rgb(mask[:, 0:1].float().contiguous(), vis.float().contiguous(), clamp=True)
         lo, hi = torch.aminmax(rgb)
         return (rgb - lo) / (hi - lo)
+
+
+# the paper's ablation networks (core/model_fusion.py:363-425, :465-523, :626-1025) live in ablation.py; imported last because
+# they build on the classes above
+from .ablation import (AttentionModule, CrossPath_M, CrossPath_S, FeatureFusionModule_MoAM, FeatureFusionModule_SoAM,  # noqa: E402,F401
+                       Fusion_Network3, Fusion_Network3_Add, Fusion_Network3_Average, Fusion_Network3_Con, Fusion_Network3_M,
+                       Fusion_Network3_S, Fusion_Network_rmseg, Fusion_Network_rmseg_att)

@@ -20,6 +20,7 @@ from .. import ops
 from ..ops import ACT_NONE
 
 BF16, F32 = torch.bfloat16, torch.float32
+STAGE_DONE_HOOK = None      # set by ddp.SegTrainer: called with the 0-based stage index when the reverse pass has finished a stage
 
 
 # ------------------------------------------------------------------------------------------------ helpers
@@ -320,6 +321,8 @@ def encoder_backward(enc, tape, douts, g, prefix, want_input_grad):
                 d_nhwc = ops.col2im(dP, B, st["Hin"], st["Win"], 3, k, st["s"], st["p"], out_dtype=F32)
                 dxn = ops.nhwc_to_nchw(d_nhwc, B, st["Hin"] * st["Win"], 3).view(B, 3, st["Hin"], st["Win"])
                 dimg = ops.channel_affine_nchw(dxn, tape["in_scale"], None) if tape["in_scale"] is not None else dxn
+        if STAGE_DONE_HOOK is not None:
+            STAGE_DONE_HOOK(s)
     return dimg
 
 

@@ -108,6 +108,7 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv3x3_tc_kernel(const __g
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0 && a.df.enabled) df_mark_begin(a.df.timing);
 
   if (warp == 0) {
     if (tc::elect_one()) {
@@ -117,12 +118,13 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv3x3_tc_kernel(const __g
         for (int t = 0; t < 9; ++t)
           tc::tma_load_2d(sW + (c * 9 + t) * Cfg::W_TILE_BYTES, &tmW, wfull, t * a.cin + c * 64, 0);
       int it = 0, lt = 0;
+      DfSeen seen0 = {-1, -1, 0}, seen1 = {-1, -1, 0};
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
         const int b = tile / tiles_per_img, rem = tile - b * tiles_per_img;
         const int y0 = (rem / a.tiles_x) * Cfg::TH - a.y_shift, x0 = (rem % a.tiles_x) * Cfg::TW;
         if (a.df.enabled) {                     // producer stages must have finished the rows this tile reads
-          df_wait(a.df.dep[1], a.df.error, b, y0, y0 + Cfg::TH, a.H);
-          df_wait(a.df.dep[0], a.df.error, b, y0, y0 + Cfg::TH, a.H);
+          df_wait(a.df.dep[1], a.df.error, b, y0, y0 + Cfg::TH, a.H, seen1);
+          df_wait(a.df.dep[0], a.df.error, b, y0, y0 + Cfg::TH, a.H, seen0);
         }
         if (a.has_pre && a.staged) {            // partial pre-activation tile of this output tile
           const int pb = lt & 1;
@@ -274,6 +276,8 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv3x3_tc_kernel(const __g
     } else {
       // direct epilogue: this thread owns pixel (r / 8, r % 8) of every sub-tile
       const int ty = r >> 3, tx = r & 7;
+      DfSeen seen_e = {-1, -1, 0};
+      int prev_b = -1, prev_t = 0;                 // dataflow: the tile whose stores are not yet published
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
         const int buf = lt & 1;
         const int b = tile / tiles_per_img, rem = tile - b * tiles_per_img;
@@ -284,7 +288,7 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv3x3_tc_kernel(const __g
         uint4 pv[NSUB][COUT / 8];
         if (a.has_pre) {                           // partial rows in flight while the MMAs of this tile still run
           if (a.df.enabled) {                      // ... once their producer stage has published them
-            if (lane == 0) df_wait(a.df.dep[1], a.df.error, b, yt0, yt0 + Cfg::TH, a.H);
+            if (lane == 0) df_wait(a.df.dep[1], a.df.error, b, yt0, yt0 + Cfg::TH, a.H, seen_e);
             __syncwarp();
           }
 #pragma unroll
@@ -299,6 +303,12 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv3x3_tc_kernel(const __g
         }
         tc::mbar_wait(tmem_full + buf, (lt >> 1) & 1);
         tc::tc_fence_after();
+        if (a.df.enabled && a.df.signal && prev_b >= 0) {
+          // publish the PREVIOUS tile now: its stores were issued a whole tile ago, so the fence no longer waits on them
+          __threadfence();
+          tc::named_bar_sync(2, 128);
+          if (store_leader) df_signal(a.df.signal, prev_b, a.tiles_y, prev_t);
+        }
 #pragma unroll
         for (int sc = 0; sc < NSUB * (COUT / 32); ++sc) {
           const int sub = sc / (COUT / 32), c = (sc % (COUT / 32)) * 32;
@@ -330,11 +340,12 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv3x3_tc_kernel(const __g
         tc::tc_fence_before();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(tmem_empty + buf);
-        if (a.df.enabled && a.df.signal) {         // every epilogue thread's stores are ordered before the published count
-          __threadfence();
-          tc::named_bar_sync(2, 128);
-          if (store_leader) df_signal(a.df.signal, b, a.tiles_y, rem / a.tiles_x);
-        }
+        prev_b = b; prev_t = rem / a.tiles_x;
+      }
+      if (a.df.enabled && a.df.signal && prev_b >= 0) {   // every epilogue thread's stores are ordered before the published count
+        __threadfence();
+        tc::named_bar_sync(2, 128);
+        if (store_leader) df_signal(a.df.signal, prev_b, a.tiles_y, prev_t);
       }
     }
     if (store_leader) tc::bulk_wait_all0();
@@ -342,6 +353,7 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv3x3_tc_kernel(const __g
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 1) tc::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (threadIdx.x == 0 && a.df.enabled) df_mark_end(a.df.timing);
 }
 
 template <int COUT, int DIL, int NSUB>
@@ -408,7 +420,7 @@ static int launch_conv_tc(const segmif_conv_params* p, cudaStream_t st, const Co
   a.bias = p->bias; a.alpha = p->prelu_alpha;
   a.B = p->B; a.H = p->H; a.W = p->W; a.nchunks = nchunks; a.act = p->act; a.has_pre = has_pre ? 1 : 0;
   a.y_shift = x ? x->y_shift : 0;
-  if (x) a.df = x->df; else { a.df = Dataflow(); a.df.enabled = 0; a.df.signal = nullptr; a.df.error = nullptr; a.df.dep[0].flags = a.df.dep[1].flags = nullptr; }
+  if (x) a.df = x->df; else { a.df = Dataflow(); a.df.enabled = 0; a.df.signal = nullptr; a.df.error = nullptr; a.df.timing = nullptr; a.df.dep[0].flags = a.df.dep[1].flags = nullptr; }
   a.tiles_x = (p->W + Cfg::TW - 1) / Cfg::TW; a.tiles_y = (p->H + a.y_shift + Cfg::TH - 1) / Cfg::TH;
   a.cin = p->Cin;
   a.ksteps_last = ((p->Cin - 1) % 64) / 16 + 1;

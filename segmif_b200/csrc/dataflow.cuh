@@ -28,6 +28,7 @@ struct Dataflow {
   unsigned* signal;        // this stage's counters [B * tiles_y] (nullptr: do not publish)
   unsigned* error;
   int enabled;
+  unsigned long long* timing;   // 2 words (diagnostics) or nullptr
 };
 
 __device__ __forceinline__ unsigned df_load_acquire(const unsigned* p) {
@@ -37,15 +38,24 @@ __device__ __forceinline__ unsigned df_load_acquire(const unsigned* p) {
 }
 __device__ __forceinline__ void df_fence_proxy_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
+// What a polling thread already knows: producer tile rows t_lo .. t_done of image b have been seen complete.  A CTA walks
+// its tiles in row order, so consecutive tiles mostly need rows that were verified for the previous tile: without this
+// memo every tile paid two or three dependent L2 round trips (ld.acquire) in the TMA-producer warp, directly on the path
+// that keeps the halo-tile ring full.
+struct DfSeen { int b, t_done, t_lo; };
+
 // waits until the producer rows covering image rows [ya - halo, yb + halo) of image b are complete
-static __device__ __noinline__ void df_wait(const DfDep& e, unsigned* error, int b, int ya, int yb, int H) {
+static __device__ __noinline__ void df_wait(const DfDep& e, unsigned* error, int b, int ya, int yb, int H, DfSeen& seen) {
   if (e.flags == nullptr) return;
   ya = ya - e.halo < 0 ? 0 : ya - e.halo;
   yb = yb + e.halo > H ? H : yb + e.halo;
   if (ya >= yb) return;
-  const int t0 = (ya + e.shift) >> 4;
+  int t0 = (ya + e.shift) >> 4;
   int t1 = (yb - 1 + e.shift) >> 4;
   if (t1 > e.tiles_y - 1) t1 = e.tiles_y - 1;
+  if (seen.b != b || t0 > seen.t_done + 1 || t0 < seen.t_lo) { seen.b = b; seen.t_lo = t0; seen.t_done = t0 - 1; }   // new interval
+  if (t0 <= seen.t_done) t0 = seen.t_done + 1;
+  if (t0 > t1) return;
   for (int t = t0; t <= t1; ++t) {
     const unsigned* f = e.flags + (size_t)b * e.tiles_y + t;
     if (df_load_acquire(f) >= e.target) continue;
@@ -60,6 +70,7 @@ static __device__ __noinline__ void df_wait(const DfDep& e, unsigned* error, int
       }
     }
   }
+  seen.t_done = t1;
   df_fence_proxy_all();
 }
 
@@ -69,6 +80,15 @@ __device__ __forceinline__ void df_signal(unsigned* counters, int b, int tiles_y
   __threadfence();
   asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counters + (size_t)b * tiles_y + t) : "memory");
 }
+
+// optional per-stage timing (diagnostics): t[0] = min over CTAs of the start time, t[1] = max of the end time (globaltimer, ns)
+__device__ __forceinline__ unsigned long long df_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void df_mark_begin(unsigned long long* t) { if (t) atomicMin(t, df_now()); }
+__device__ __forceinline__ void df_mark_end(unsigned long long* t) { if (t) atomicMax(t + 1, df_now()); }
 
 // ---- stage launchers with dataflow arguments (defined next to their kernels) -----------------------------------------
 struct ConvDfExtra {
@@ -83,6 +103,7 @@ int drdb_push_tile_w(int slab_width, int n_out);
 struct GemmDfExtra {
   DfDep dep;           // producer of the A rows (tile rows of an image of H x W pixels)
   unsigned* error;
+  unsigned long long* timing;
   int H, W;
   int max_ctas;
 };

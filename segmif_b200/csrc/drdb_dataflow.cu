@@ -48,7 +48,7 @@ using namespace segmif;
 
 extern "C" size_t segmif_drdb_dataflow_workspace_bytes(int B, int H) {
   const size_t ty = (size_t)(H + 8 + 15) / 16;
-  return (6 * (size_t)B * ty + 4) * sizeof(unsigned);
+  return (6 * (size_t)B * ty + 4 + 32) * sizeof(unsigned);     // counters, error word (+3 pad), 7 x {begin, end} timestamps (diagnostics)
 }
 
 extern "C" int segmif_drdb_dataflow_prepare(int device) {
@@ -81,10 +81,11 @@ extern "C" int segmif_drdb_dataflow_fwd(const segmif_drdb_dataflow_params* p, se
     ctas[6] *= 2;
   } else {
     for (int i = 0; i < 7; ++i) ctas[i] = p->ctas[i];
+    if (ctas[6] < 0) { total -= ctas[6]; ctas[6] = 0; }
     // the six conv stages need a whole SM per CTA; two CTAs of the 1x1 GEMM (96 KB of shared memory, 128 TMEM columns) share one
     const int sm_need = total - ctas[6] + (ctas[6] + 1) / 2;
     SEGMIF_REQUIRE(sm_need <= sms, "drdb_dataflow: the stages need %d SMs, the device has %d (all stages must be co-resident)", sm_need, sms);
-    for (int i = 0; i < 7; ++i) SEGMIF_REQUIRE(ctas[i] > 0, "drdb_dataflow: stage %d has no CTAs", i);
+    for (int i = 0; i < 6; ++i) SEGMIF_REQUIRE(ctas[i] > 0, "drdb_dataflow: stage %d has no CTAs", i);
   }
   const int B = p->B, H = p->H, W = p->W;
   const size_t ty_max = (size_t)(H + 8 + 15) / 16;
@@ -92,8 +93,11 @@ extern "C" int segmif_drdb_dataflow_fwd(const segmif_drdb_dataflow_params* p, se
   int tiles_y[6];
   for (int s = 0; s < 6; ++s) { flags[s] = p->flags + (size_t)s * B * ty_max; tiles_y[s] = (H + kShift[s] + 15) / 16; }
   unsigned* error = p->flags + 6 * (size_t)B * ty_max;
+  unsigned long long* timing = reinterpret_cast<unsigned long long*>(error + 4);     // [7][2]; begin words start at ~0 (atomicMin)
   cudaError_t ce = cudaMemsetAsync(p->flags, 0, segmif_drdb_dataflow_workspace_bytes(B, H), st);
+  if (ce == cudaSuccess) ce = cudaMemsetAsync(timing, 0xff, 16 * sizeof(unsigned long long), st);
   if (ce != cudaSuccess) { set_error("drdb_dataflow: cudaMemsetAsync: %s", cudaGetErrorString(ce)); return SEGMIF_ERR_CUDA; }
+  for (int s = 0; s < 7; ++s) cudaMemsetAsync(timing + 2 * s + 1, 0, sizeof(unsigned long long), st);
   // fork
   cudaEventRecord(ds->fork, st);
   for (int i = 0; i < 6; ++i) cudaStreamWaitEvent(ds->side[i], ds->fork, 0);
@@ -127,7 +131,7 @@ extern "C" int segmif_drdb_dataflow_fwd(const segmif_drdb_dataflow_params* p, se
       for (int i = 0; i < 2; ++i) { q.groups[i].dst = p->partial; q.groups[i].ld_dst = p->ld_partial; q.groups[i].coff_dst = 64 + 32 * i; }
     }
     ConvDfExtra x;
-    x.df.enabled = 1; x.df.dep[0] = none; x.df.dep[1] = none; x.df.signal = flags[s]; x.df.error = error;
+    x.df.enabled = 1; x.df.dep[0] = none; x.df.dep[1] = none; x.df.signal = flags[s]; x.df.error = error; x.df.timing = timing + 2 * s;
     x.y_shift = 0; x.max_ctas = ctas[s];
     rc = drdb_push_df(&q, x, stage_stream(s));
   }
@@ -141,27 +145,36 @@ extern "C" int segmif_drdb_dataflow_fwd(const segmif_drdb_dataflow_params* p, se
     q.dst_dtype = SEGMIF_BF16; q.ld_dst = p->ld; q.dst_coff = 64 + 32 * (j - 1);
     q.pre_add = p->partial; q.ld_pre = p->ld_partial; q.pre_coff = 32 * (j - 2);
     ConvDfExtra x;
-    x.df.enabled = 1; x.df.signal = flags[j]; x.df.error = error;
+    x.df.enabled = 1; x.df.signal = flags[j]; x.df.error = error; x.df.timing = timing + 2 * j;
     x.df.dep[0] = dep(j == 2 ? 0 : j - 1, 2);                    // the slabs: previous layer (transitively all earlier ones)
     x.df.dep[1] = j == 2 ? none : dep(j <= 3 ? 0 : 1, 0);         // P_j: push a wrote P2, P3; push b wrote P4, P5
     x.y_shift = kShift[j]; x.max_ctas = ctas[j];
     rc = conv3x3_tc_df(&q, x, stage_stream(j));
   }
-  // ---- stage 6: out = x0 + relu(conv1x1(all 224 channels))
-  if (rc == SEGMIF_OK) {
+  // ---- stage 6: out = x0 + relu(conv1x1(all 224 channels)); ctas[6] < 0: run it AFTER the join, stream ordered, whole GPU
+  const bool seq_1x1 = p->ctas[6] < 0;
+  if (rc == SEGMIF_OK && !seq_1x1) {
     segmif_linear_params q;
     q.src = p->growth; q.weight = p->w_1x1; q.bias = p->bias_1x1; q.prelu_alpha = nullptr; q.residual = p->growth; q.dst = p->out;
     q.M = B * H * W; q.N = 64; q.K = 224; q.ld_src = p->ld; q.src_coff = 0; q.act = SEGMIF_ACT_RELU;
     q.res_dtype = SEGMIF_BF16; q.ld_res = p->ld; q.res_coff = 0; q.dst_dtype = SEGMIF_BF16; q.ld_dst = p->ld_out; q.dst_coff = p->out_coff;
     q.weight_kn = 0; q.row_scale = nullptr; q.rows_per_scale = 0;
     GemmDfExtra x;
-    x.dep = dep(5, 0); x.error = error; x.H = H; x.W = W; x.max_ctas = ctas[6];
+    x.dep = dep(5, 0); x.error = error; x.timing = timing + 12; x.H = H; x.W = W; x.max_ctas = ctas[6];
     rc = linear_tc_df(&q, x, stage_stream(6));
   }
   // join (always, so that a capture in progress is left in a consistent state even after a failed launch)
   for (int i = 0; i < 6; ++i) {
     cudaEventRecord(ds->join[i], ds->side[i]);
     cudaStreamWaitEvent(st, ds->join[i], 0);
+  }
+  if (rc == SEGMIF_OK && seq_1x1) {
+    segmif_linear_params q;
+    q.src = p->growth; q.weight = p->w_1x1; q.bias = p->bias_1x1; q.prelu_alpha = nullptr; q.residual = p->growth; q.dst = p->out;
+    q.M = B * H * W; q.N = 64; q.K = 224; q.ld_src = p->ld; q.src_coff = 0; q.act = SEGMIF_ACT_RELU;
+    q.res_dtype = SEGMIF_BF16; q.ld_res = p->ld; q.res_coff = 0; q.dst_dtype = SEGMIF_BF16; q.ld_dst = p->ld_out; q.dst_coff = p->out_coff;
+    q.weight_kn = 0; q.row_scale = nullptr; q.rows_per_scale = 0;
+    rc = segmif_linear_tc_fwd(&q, stream);
   }
   return rc;
 }

@@ -31,6 +31,7 @@ struct PushArgs {
   PushGroup g[4];
   int B, H, W, tiles_x, tiles_y;
   unsigned* signal;        // dataflow.cuh: finished-tile counters [B * tiles_y] published for concurrently running consumers
+  unsigned long long* timing;
 };
 
 constexpr int kPushThreads = 192;
@@ -90,6 +91,7 @@ __global__ void __launch_bounds__(kPushThreads, 1) drdb_push_tc_kernel(const __g
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) df_mark_begin(a.timing);
 
   if (warp == 0) {
     if (tc::elect_one()) {
@@ -146,6 +148,7 @@ __global__ void __launch_bounds__(kPushThreads, 1) drdb_push_tc_kernel(const __g
     const int quad = warp & 3;
     const int r = quad * 32 + lane, ty = r >> 3, tx = r & 7;
     int lt = 0;
+    int prev_b = -1, prev_t = 0;                   // dataflow: the tile whose stores are not yet published
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
       const int buf = lt & 1;
       const int b = tile / tiles_per_img, rem = tile - b * tiles_per_img;
@@ -153,6 +156,11 @@ __global__ void __launch_bounds__(kPushThreads, 1) drdb_push_tc_kernel(const __g
       const int x0 = (rem % a.tiles_x) * Cfg::TW + tx;
       tc::mbar_wait(tmem_full + buf, (lt >> 1) & 1);
       tc::tc_fence_after();
+      if (a.signal && prev_b >= 0) {               // publish the previous tile: its stores were issued a whole tile ago
+        __threadfence();
+        tc::named_bar_sync(2, 128);
+        if (warp == 2 && lane == 0) df_signal(a.signal, prev_b, a.tiles_y, prev_t);
+      }
 #pragma unroll 1
       for (int sg = 0; sg < NSUB * (NOUT / 32); ++sg) {
         const int sub = sg / (NOUT / 32), gi = sg % (NOUT / 32);
@@ -194,16 +202,18 @@ __global__ void __launch_bounds__(kPushThreads, 1) drdb_push_tc_kernel(const __g
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(tmem_empty + buf);
-      if (a.signal) {
-        __threadfence();
-        tc::named_bar_sync(2, 128);
-        if (warp == 2 && lane == 0) df_signal(a.signal, b, a.tiles_y, rem / a.tiles_x);
-      }
+      prev_b = b; prev_t = rem / a.tiles_x;
+    }
+    if (a.signal && prev_b >= 0) {
+      __threadfence();
+      tc::named_bar_sync(2, 128);
+      if (warp == 2 && lane == 0) df_signal(a.signal, prev_b, a.tiles_y, prev_t);
     }
   }
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 1) tc::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (threadIdx.x == 0) df_mark_end(a.timing);
 }
 
 template <int NOUT, int NSUB, int KSLAB>
@@ -248,6 +258,7 @@ static int launch_push(const segmif_drdb_push_params* p, cudaStream_t st, const 
   a.B = p->B; a.H = p->H; a.W = p->W;
   a.tiles_x = (p->W + Cfg::TW - 1) / Cfg::TW; a.tiles_y = (p->H + Cfg::TH - 1) / Cfg::TH;
   a.signal = x ? x->df.signal : nullptr;
+  a.timing = x ? x->df.timing : nullptr;
   const int num_tiles = a.tiles_x * a.tiles_y * a.B;
   const int ctas = (x && x->max_ctas > 0) ? std::min(x->max_ctas, sms) : sms;
   kern<<<std::min(num_tiles, ctas), kPushThreads, Cfg::SMEM, st>>>(tmA, tmW, a);

@@ -136,6 +136,7 @@ constexpr int kTcThreads = 192;
 struct GemmDfDev {
   DfDep dep;
   unsigned* error;
+  unsigned long long* timing;
   int H, W, HW;
 };
 
@@ -174,10 +175,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) df_mark_begin(d.timing);
 
   if (warp == 0) {
     if (tc::elect_one()) {
       int it = 0;
+      DfSeen seen = {-1, -1, 0};
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = (tile / n_tiles) * 128, n0 = (tile % n_tiles) * BN;
         if (d.dep.flags) {                       // rows m0 .. m0+127 = pixels of one or two images
@@ -185,10 +188,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
           const int b0 = m0 / d.HW, b1 = m1 / d.HW;
           const int ya = (m0 - b0 * d.HW) / d.W, yb = (m1 - b1 * d.HW) / d.W + 1;
           if (b0 == b1) {
-            df_wait(d.dep, d.error, b0, ya, yb, d.H);
+            df_wait(d.dep, d.error, b0, ya, yb, d.H, seen);
           } else {
-            df_wait(d.dep, d.error, b0, ya, d.H, d.H);
-            df_wait(d.dep, d.error, b1, 0, yb, d.H);
+            df_wait(d.dep, d.error, b0, ya, d.H, d.H, seen);
+            df_wait(d.dep, d.error, b1, 0, yb, d.H, seen);
           }
         }
         for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
@@ -266,6 +269,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 1) tc::tmem_dealloc(tmem_base, TMEM_COLS);
+  if (threadIdx.x == 0) df_mark_end(d.timing);
 }
 
 template <int BN, bool GELU, bool WKN = false>
@@ -286,9 +290,9 @@ static int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   const int ctas_per_sm = BN <= 64 ? 2 : 1;          // 96 KB (BN=64) / 80 KB (BN=32) of smem: two CTAs fit and hide latency
   int grid = (int)std::min<int64_t>(num_tiles, (int64_t)sms * ctas_per_sm);
   GemmDfDev d;
-  d.dep.flags = nullptr; d.dep.target = 0; d.dep.tiles_y = d.dep.shift = d.dep.halo = 0; d.error = nullptr; d.H = d.W = d.HW = 1;
+  d.dep.flags = nullptr; d.dep.target = 0; d.dep.tiles_y = d.dep.shift = d.dep.halo = 0; d.error = nullptr; d.timing = nullptr; d.H = d.W = d.HW = 1;
   if (x) {
-    d.dep = x->dep; d.error = x->error; d.H = x->H; d.W = x->W; d.HW = x->H * x->W;
+    d.dep = x->dep; d.error = x->error; d.timing = x->timing; d.H = x->H; d.W = x->W; d.HW = x->H * x->W;
     if (x->max_ctas > 0) grid = std::min(grid, x->max_ctas);
   }
   kern<<<grid, kTcThreads, smem, st>>>(tmA, tmB, e, (int)ceil_div(K, 64), n_tiles, (int)num_tiles, d);

@@ -287,6 +287,88 @@ __global__ void __launch_bounds__(256) ffm_fold_f32_kernel(const float* __restri
   }
 }
 
+// ---- generic cross product  X^T Y  over the pixels of each image (Cx, Cy <= 64, multiples of 4), fp64 accumulation ------
+// The ablation networks' attention modules (core/model_fusion.py:363-425, dim 32, head_dim 4) need k^T v for k, v of any
+// width; partials double [B, nchunk, Cx, Cy].  One thread per output element group: thread t owns row i = t / (Cy/4),
+// columns 4 (t % (Cy/4)) .. +3.
+__global__ void __launch_bounds__(256) xty_f64_kernel(const float* __restrict__ x, int ldx, int coffx, int Cx,
+                                                      const float* __restrict__ y, int ldy, int coffy, int Cy, int64_t HW,
+                                                      double* __restrict__ partials, int nchunk) {
+  __shared__ __align__(16) float sx[32][64];
+  __shared__ __align__(16) float sy[32][64];
+  const int chunk = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const int cy4 = Cy >> 2;
+  const bool active = tid < Cx * cy4;
+  const int i = active ? tid / cy4 : 0, j4 = active ? (tid % cy4) * 4 : 0;
+  const int64_t per = (HW + nchunk - 1) / nchunk;
+  const int64_t p0 = chunk * per, p1 = p0 + per < HW ? p0 + per : HW;
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int64_t base = p0; base < p1; base += 32) {
+    __syncthreads();
+    for (int idx = tid; idx < 32 * 16; idx += 256) {
+      const int r = idx >> 4, c4 = (idx & 15) * 4;
+      const bool row_ok = base + r < p1;
+      float4 vx = make_float4(0.f, 0.f, 0.f, 0.f), vy = vx;
+      if (row_ok && c4 < Cx) vx = *reinterpret_cast<const float4*>(x + ((int64_t)b * HW + base + r) * ldx + coffx + c4);
+      if (row_ok && c4 < Cy) vy = *reinterpret_cast<const float4*>(y + ((int64_t)b * HW + base + r) * ldy + coffy + c4);
+      *reinterpret_cast<float4*>(&sx[r][c4]) = vx;
+      *reinterpret_cast<float4*>(&sy[r][c4]) = vy;
+    }
+    __syncthreads();
+    float f[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) {
+      const float a = sx[r][i];
+      const float4 c = *reinterpret_cast<const float4*>(&sy[r][j4]);
+      f[0] = fmaf(a, c.x, f[0]); f[1] = fmaf(a, c.y, f[1]); f[2] = fmaf(a, c.z, f[2]); f[3] = fmaf(a, c.w, f[3]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[k] += (double)f[k];
+  }
+  if (active) {
+    double* o = partials + (((int64_t)b * nchunk + chunk) * Cx + i) * Cy + j4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o[k] = acc[k];
+  }
+}
+
+// ctx[b][h][i][j] = softmax over i of (scale * sum_chunks partial[b][.][h d + i][h d + j]);  also the block-diagonal weight
+// wout[b][h d + j][h d + i] = ctx[b][h][i][j] that turns "q @ ctx per head" into one [C x C] product per image.
+__global__ void __launch_bounds__(256) ctx_blockdiag_kernel(const double* __restrict__ partials, int nchunk, int C, int heads,
+                                                            float scale, float* __restrict__ ctx, float* __restrict__ wout) {
+  __shared__ double lg[64 * 8];           // heads * d * d <= 64 * 8 (C <= 64, d <= 8)
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int d = C / heads, per_head = d * d, n = heads * per_head;
+  for (int idx = tid; idx < n; idx += 256) {
+    const int h = idx / per_head, i = (idx % per_head) / d, j = idx % d;
+    double a = 0.0;
+    for (int c = 0; c < nchunk; ++c) a += partials[(((int64_t)b * nchunk + c) * C + h * d + i) * C + h * d + j];
+    lg[idx] = (double)((float)a) * (double)scale;       // the reference forms k^T v in fp32, then multiplies by the fp32 scale
+  }
+  for (int idx = tid; idx < C * C; idx += 256) wout[(int64_t)b * C * C + idx] = 0.f;
+  __syncthreads();
+  if (tid < heads * d) {                                // one (head, column j): softmax over i (dim = -2)
+    const int h = tid / d, j = tid % d;
+    double m = -INFINITY;
+    for (int i = 0; i < d; ++i) m = fmax(m, lg[h * per_head + i * d + j]);
+    double s = 0.0;
+    for (int i = 0; i < d; ++i) s += exp(lg[h * per_head + i * d + j] - m);
+    for (int i = 0; i < d; ++i) {
+      const float p = (float)(exp(lg[h * per_head + i * d + j] - m) / s);
+      ctx[(int64_t)b * n + h * per_head + i * d + j] = p;
+      wout[(int64_t)b * C * C + (h * d + j) * C + h * d + i] = p;
+    }
+  }
+}
+
+// out = x * sigmoid(x)  (AttentionModule, core/model_fusion.py:759-771: `out = sigmoid(x1); return out * x1`)
+__global__ void __launch_bounds__(256) sigmoid_gate_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = x[i];
+  out[i] = v * (1.0f / (1.0f + expf(-v)));
+}
+
 // ---- edge layers of the fusion network with fp32 activations ---------------------------------------------------------
 // conv1_ir / conv1_vis: fp32 plane -> fp32 pixel-major [.., Cout]; one thread per (pixel, 4 channels)
 __global__ void __launch_bounds__(256) conv3x3_in1_f32_kernel(const float* __restrict__ plane, int64_t bstride,
@@ -469,4 +551,30 @@ extern "C" int segmif_conv3x3_out1_f32_fwd(const float* src, int ld_src, const f
   if (total == 0) return SEGMIF_OK;
   conv3x3_out1_f32_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, as_stream(stream)>>>(src, ld_src, w, bias, prelu_alpha, dst, B, H, W, Cin);
   return check_launch("segmif_conv3x3_out1_f32_fwd");
+}
+
+extern "C" int segmif_xty_f64(const float* x, int ldx, int coffx, int Cx, const float* y, int ldy, int coffy, int Cy, int B,
+                              int64_t HW, double* partials, int nchunk, segmif_stream_t stream) {
+  SEGMIF_REQUIRE(x && y && partials && nchunk > 0 && B > 0, "xty: bad arguments");
+  SEGMIF_REQUIRE(Cx > 0 && Cy > 0 && Cx <= 64 && Cy <= 64 && Cx % 4 == 0 && Cy % 4 == 0 && Cx * (Cy / 4) <= 256,
+                 "xty: Cx, Cy must be multiples of 4 with Cx * Cy <= 1024 (got %d x %d)", Cx, Cy);
+  SEGMIF_REQUIRE(ldx % 4 == 0 && coffx % 4 == 0 && ldy % 4 == 0 && coffy % 4 == 0 && (((uintptr_t)x | (uintptr_t)y) & 15) == 0,
+                 "xty: slices must be 16-byte aligned");
+  xty_f64_kernel<<<dim3(nchunk, B), 256, 0, as_stream(stream)>>>(x, ldx, coffx, Cx, y, ldy, coffy, Cy, HW, partials, nchunk);
+  return check_launch("segmif_xty_f64");
+}
+
+extern "C" int segmif_ctx_blockdiag(const double* partials, int nchunk, int C, int heads, float scale, float* ctx, float* wout,
+                                    int B, segmif_stream_t stream) {
+  SEGMIF_REQUIRE(partials && ctx && wout && nchunk > 0 && B > 0, "ctx_blockdiag: bad arguments");
+  SEGMIF_REQUIRE(C > 0 && C <= 64 && heads > 0 && C % heads == 0 && C / heads <= 8, "ctx_blockdiag: C <= 64, head dim <= 8");
+  ctx_blockdiag_kernel<<<B, 256, 0, as_stream(stream)>>>(partials, nchunk, C, heads, scale, ctx, wout);
+  return check_launch("segmif_ctx_blockdiag");
+}
+
+extern "C" int segmif_sigmoid_gate(const float* x, float* out, int64_t n, segmif_stream_t stream) {
+  SEGMIF_REQUIRE(x && out, "sigmoid_gate: null pointer");
+  if (n == 0) return SEGMIF_OK;
+  sigmoid_gate_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, as_stream(stream)>>>(x, out, n);
+  return check_launch("segmif_sigmoid_gate");
 }

@@ -7,6 +7,8 @@ is the additive wrapper its `--local_rank` flag was meant for.
 Parameters that never receive a gradient on the live path (Fusion_Network3_ac.ffm2.*, WeTr.classifier) are kept OUT of
 the flat buffer: torch.optim.AdamW skips parameters whose grad is None (no weight decay either), and a zero-filled
 slot would silently decay them ("unused parameters under DDP")."""
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -16,13 +18,19 @@ class FlatParams:
     """Re-homes the selected parameters of `module` as views of one flat fp32 buffer and gives them gradient views
     of a second flat buffer, so the all-reduce and the optimizer each touch a single contiguous tensor."""
 
-    def __init__(self, module, used=lambda name: True, group_of=None):
+    def __init__(self, module, used=lambda name: True, group_of=None, early_of=None):
+        """`group_of(name)`: optimizer param group id (groups become contiguous ranges).  `early_of(name)`: True for parameters
+        whose gradient is complete EARLY in the backward pass; inside every group they are placed first, so that the early
+        part of each group is one contiguous range that can be all-reduced while the rest of the backward still runs
+        (`early_ranges` / `late_ranges`)."""
         self.named = [(k, p) for k, p in module.named_parameters() if p.requires_grad and used(k)]
         self.skipped = [k for k, p in module.named_parameters() if p.requires_grad and not used(k)]
         if not self.named:
             raise ValueError("FlatParams: no parameters selected")
-        if group_of is not None:                      # optimizer param groups become contiguous ranges of the buffer
-            self.named.sort(key=lambda kp: group_of(kp[0]))
+        if group_of is not None or early_of is not None:      # optimizer param groups become contiguous ranges of the buffer
+            gkey = group_of if group_of is not None else (lambda k: 0)
+            ekey = (lambda k: 0 if early_of(k) else 1) if early_of is not None else (lambda k: 0)
+            self.named.sort(key=lambda kp: (gkey(kp[0]), ekey(kp[0])))
         dev = self.named[0][1].device
         pad4 = lambda n: (n + 3) & ~3              # every view starts 16-byte aligned (the kernels read biases / gains as float4)
         self.numel = sum(pad4(p.numel()) for _, p in self.named)
@@ -47,6 +55,17 @@ class FlatParams:
                 o, n = self.offsets[k]
                 lo, hi = self.group_ranges.get(group_of(k), (o, o))
                 self.group_ranges[group_of(k)] = (min(lo, o), max(hi, o + pad4(n)))
+        # contiguous [lo, hi) ranges of the early / late parameters (at most one of each per group)
+        self.early_ranges, self.late_ranges = [], [(0, self.numel)]
+        if early_of is not None:
+            spans = {}
+            for k, p in self.named:
+                o, n = self.offsets[k]
+                key = ((group_of(k) if group_of is not None else 0), bool(early_of(k)))
+                lo, hi = spans.get(key, (o, o))
+                spans[key] = (min(lo, o), max(hi, o + pad4(n)))
+            self.early_ranges = sorted(v for (g, e), v in spans.items() if e)
+            self.late_ranges = sorted(v for (g, e), v in spans.items() if not e)
 
     def broadcast(self, module=None, group=None, src=0):
         """Makes every replica start from rank `src`'s parameters (and `module`'s buffers, e.g. BatchNorm running
@@ -70,10 +89,16 @@ class FlatParams:
             if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + off * 4:
                 p.grad = self.grad[off:off + n].view(p.shape)
 
-    def all_reduce(self, group=None):
-        """The step's single collective: SUM over ranks (the mean's 1/world is applied by the optimizer kernel)."""
+    def all_reduce(self, group=None, ranges=None):
+        """The step's collective: SUM over ranks (the mean's 1/world is applied by the optimizer kernel).  ranges=None: the
+        whole flat buffer in ONE call; otherwise only the given [lo, hi) ranges (the overlapped two-bucket schedule)."""
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=group)
+            if ranges is None:
+                dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=group)
+            else:
+                for lo, hi in ranges:
+                    if hi > lo:
+                        dist.all_reduce(self.grad[lo:hi], op=dist.ReduceOp.SUM, group=group)
             return dist.get_world_size(group)
         return 1
 
@@ -292,18 +317,57 @@ class SegTrainer(_GraphedStep):
                  warmup_ratio=1e-6, power=1.0, iter_curr=0, ignore_index=255, group=None):
         self.net, self.group = seg_net, group
         gid = lambda k: 2 if ".decoder." in k else (1 if "norm" in k.split("encoder.", 1)[-1] else 0)
-        self.flat = FlatParams(seg_net, used=lambda k: not k.endswith("classifier.weight"), group_of=gid)
+        # gradients of the decode head and of encoder stages 3-4 (93 % of the 94 MB) are complete when the reverse pass
+        # leaves stage 3; they are all-reduced on a side stream while stages 2 and 1 (most of the backward's TIME: they hold
+        # 94 % of the tokens) are still being differentiated.  SEGMIF_OVERLAP_ALLREDUCE=0 restores the single call.
+        early = lambda k: ".decoder." in k or any(t in k for t in ("patch_embed3.", "patch_embed4.", "block3.", "block4.", "norm3.", "norm4."))
+        self.overlap = os.environ.get("SEGMIF_OVERLAP_ALLREDUCE", "1") != "0"
+        self.flat = FlatParams(seg_net, used=lambda k: not k.endswith("classifier.weight"), group_of=gid,
+                               early_of=early if self.overlap else None)
+        self._side = None
         self.opt = FusedPolyWarmupAdamW(self.flat, lr, weight_decay, betas, warmup_iter, max_iter, warmup_ratio, power,
                                         groups={0: dict(lr=lr, weight_decay=weight_decay), 1: dict(lr=lr, weight_decay=0.0),
                                                 2: dict(lr=lr * 10, weight_decay=weight_decay)}, iter_curr=iter_curr)
         self.flat.broadcast(seg_net, group)
         self.ce = torch.nn.CrossEntropyLoss(ignore_index=ignore_index)
 
+    def _world(self):
+        return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+
+    def _early_hook(self, stage):
+        """Called by the reverse pass (core/seg_train.py) when encoder stage `stage` (0-based) is done: after stage index 2
+        every gradient of `early_ranges` is final."""
+        if stage != 2 or self._world() == 1 or not self.flat.early_ranges:
+            return
+        cur = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            self.flat.all_reduce(self.group, ranges=self.flat.early_ranges)
+        self._early_pending = True
+
     def _forward_backward(self, mask, labels):
+        from .core import seg_train
         self.flat.zero_grad()
         loss = self.net._loss(mask, labels, self.ce)
-        loss.backward()
+        self._early_pending = False
+        seg_train.STAGE_DONE_HOOK = self._early_hook if self.overlap else None
+        try:
+            loss.backward()
+        finally:
+            seg_train.STAGE_DONE_HOOK = None
+        if self._early_pending:                    # join (inside the captured graph when capturing)
+            torch.cuda.current_stream().wait_stream(self._side)
         return (loss.detach(),)
+
+    def _finish(self):
+        if self.overlap and self.flat.early_ranges and self._world() > 1:
+            world = self.flat.all_reduce(self.group, ranges=self.flat.late_ranges)       # stages 1-2: ~7 % of the bytes
+        else:
+            world = self.flat.all_reduce(self.group)
+        self.opt.step(grad_scale=1.0 / world)
+        self._post_step()
 
     def capture(self, mask, labels):
         return self._capture(self._forward_backward, mask=mask, labels=labels)

@@ -268,3 +268,44 @@ def strict_pipeline_480x640_mit_b2():
     rs.append(result("bf16_480_fused", rel_err(fb, ref["fused"]), 3e-2))
     rs.append(result("bf16_480_label_disagreement", 1.0 - agree, 0.02, note=f"{agree * 100:.3f}% equal (bf16 operands; strict mode is the parity path)"))
     return rs
+
+
+@check
+def ablation_networks():
+    """the paper's ablation networks (core/model_fusion.py:363-425, :626-1025) as compositions of the
+    strict-precision kernels, against the fixture generated by the UNMODIFIED reference (oracle/make_golden_ablation.py;
+    the oracle restatements are pinned to the same fixture on the CPU)."""
+    import os
+    from conftest import GOLDEN
+    from segmif_b200.core import model_fusion as MF
+    g = np.load(os.path.join(GOLDEN, "ablation.npz"))
+    inp = synth.synth_inputs(1, 32, 48, seed=21)
+    gen = torch.Generator().manual_seed(77)
+    out1 = torch.randn(1, 64, 32, 48, generator=gen) * 0.5
+    out2 = torch.randn(1, 128, 32, 48, generator=gen) * 0.5
+    d = lambda t: t.to(DEV)
+    rs = []
+    with torch.no_grad():
+        for name in ("Fusion_Network3", "Fusion_Network3_S", "Fusion_Network3_M", "Fusion_Network3_Con", "Fusion_Network3_Add",
+                     "Fusion_Network3_Average"):
+            net = synth.load_synthetic(getattr(MF, name)(), 3).eval().to(DEV)
+            got = net(d(inp["ir"]), d(inp["vis"]), d(out1), d(out2))
+            rs.append(result(f"ablation_{name}", rel_err(got, torch.from_numpy(g[name])), 1e-4))
+        net = synth.load_synthetic(MF.Fusion_Network_rmseg(), 3).eval().to(DEV)
+        rs.append(result("ablation_Fusion_Network_rmseg", rel_err(net(d(inp["ir"]), d(inp["vis"])), torch.from_numpy(g["Fusion_Network_rmseg"])), 1e-4))
+        net = synth.load_synthetic(MF.Fusion_Network_rmseg_att(), 3).eval().to(DEV)
+        o, feats = net(d(inp["ir"]), d(inp["vis"]))
+        rs.append(result("ablation_Fusion_Network_rmseg_att", rel_err(o, torch.from_numpy(g["Fusion_Network_rmseg"])), 1e-4,
+                         note=f"features {tuple(feats[0].shape)}"))
+        gen = torch.Generator().manual_seed(5)
+        t1, t2, t3 = (torch.randn(2, 150, 32, generator=gen) for _ in range(3))
+        for name in ("CrossPath_M", "CrossPath_S"):
+            cp = synth.load_synthetic(getattr(MF, name)(32), 3).eval()
+            cp.load_state_dict({k: v * (10.0 if ".kv" in k else 1.0) for k, v in cp.state_dict().items()})
+            cp = cp.to(DEV)
+            r1, r2 = cp(d(t1), d(t2), d(t3))
+            rs.append(result(f"ablation_{name}", max(rel_err(r1, torch.from_numpy(g[name + "_1"])), rel_err(r2, torch.from_numpy(g[name + "_2"]))), 1e-4))
+        am = synth.load_synthetic(MF.AttentionModule(), 3).eval().to(DEV)
+        x = torch.randn(1, 32, 20, 28, generator=gen)
+        rs.append(result("ablation_AttentionModule", rel_err(am(d(x)), torch.from_numpy(g["AttentionModule"])), 1e-4))
+    return rs

@@ -57,6 +57,26 @@ def main():
         return ms, out.clone()
 
     res = {}
+
+    def ev(fn):
+        with torch.no_grad():
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(a.iters):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / a.iters
+    DRDB.MODE = "hybrid"
+    ms_g = ev(lambda: d._growth_hybrid(buf, part, B, H, W))
+    gf = 2.0 * B * H * W * 9 * 640 * 32
+    print("growth only (hybrid)", f"{ms_g:.3f} ms  {gf / ms_g / 1e9:.0f} TFLOP/s", flush=True)
+    ms_p = ev(lambda: d._growth_push(buf, part, B, H, W))
+    print("growth only (push-all)", f"{ms_p:.3f} ms  {gf / ms_p / 1e9:.0f} TFLOP/s", flush=True)
+    res["growth_hybrid_ms"], res["growth_push_ms"] = ms_g, ms_p
     ms_h, ref = run("hybrid")
     res["hybrid"] = {"ms": ms_h, "tflops": flops / ms_h / 1e9}
     print("hybrid  ", f"{ms_h:.3f} ms  {flops / ms_h / 1e9:.0f} TFLOP/s", flush=True)
@@ -67,6 +87,7 @@ def main():
         key = "dataflow_" + ("default" if sp is None else "-".join(map(str, sp)))
         res[key] = {"ms": ms, "tflops": flops / ms / 1e9, "equals_hybrid": same, "timed_out": d.dataflow_timed_out()}
         print(key, f"{ms:.3f} ms  {flops / ms / 1e9:.0f} TFLOP/s  equal={same} timeout={d.dataflow_timed_out()}", flush=True)
+        print("   stage [begin, end] us:", " ".join("-" if t is None else f"[{t[0]:.0f},{t[1]:.0f}]" for t in d.dataflow_stage_times()), flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(res, open(os.path.join(ROOT, "gpurun_out", "drdb_bench.json"), "w"), indent=1)
 

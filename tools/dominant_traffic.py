@@ -1,6 +1,7 @@
-"""Writes profiles/r1_ncu_dominant_kernel.json (read by bench.py's roofline.traffic) from an ncu_summary.py CSV of the
-DRDB dilated-conv launches: dram__bytes_read.sum + dram__bytes_write.sum, averaged per launch.
-usage: python tools/dominant_traffic.py profiles/r1_ncu_conv3x3_tc_v10_summary.csv"""
+"""Writes profiles/r2_ncu_dominant_kernel.json (read by bench.py's roofline.traffic) from an ncu_summary.py CSV of the
+DRDB dilated-conv launches: dram__bytes_read.sum + dram__bytes_write.sum, averaged per launch of the dominant family
+(conv3x3_tc_kernel<32, 2, .> pulls and drdb_push_tc_kernel).
+usage: python tools/dominant_traffic.py profiles/r2_ncu_drdb_summary.csv"""
 import csv
 import json
 import os
@@ -15,13 +16,15 @@ def nbytes(cell):
 
 
 def main(path):
-    rows = list(csv.DictReader(open(path)))
+    rows = [r for r in csv.DictReader(open(path)) if "conv3x3_tc_kernel<32, 2" in r["kernel"] or "drdb_push_tc_kernel" in r["kernel"]]
     per = [nbytes(r["dram_rd"]) + nbytes(r["dram_wr"]) for r in rows]
     out = {"source": os.path.basename(path), "kernel": rows[0]["kernel"], "launches": len(per),
            "traffic_bytes_per_launch": sum(per) / len(per), "per_launch": per,
-           "note": "ncu --set full --clock-control none, one DRDB (layers 2-5, g-slab pull launches, B=8 480x640); "
-                   "algorithmic bytes per launch = (Cin_g + 32 partial + 32 out) * 2 B * 2 457 600 px = 472 / 629 / 786 / 944 MB"}
-    dst = os.path.join(os.path.dirname(os.path.abspath(path)), "r1_ncu_dominant_kernel.json")
+           "kernels": [r["kernel"] for r in rows],
+           "note": "ncu --set full --clock-control none at HEAD of round 2 (bench.py --profile --no-graph, B=8 480x640): two pull launches "
+                   "(layers 4, 5: algorithmic (Cin_g + 32 partial + 32 out) * 2 B * 2 457 600 px = 786 / 944 MB) and the two x0 push "
+                   "launches (algorithmic 64 in + 96 | 64 out channels: 787 / 629 MB)"}
+    dst = os.path.join(os.path.dirname(os.path.abspath(path)), "r2_ncu_dominant_kernel.json")
     json.dump(out, open(dst, "w"), indent=1)
     print(dst, out["traffic_bytes_per_launch"])
 

@@ -395,6 +395,12 @@ int segmif_adamw_step(float* param, const float* grad, float* exp_avg, float* ex
  * operand) for head dim 64 and Nk <= 320; segmif_sr_attention_fwd / _train_fwd use it when SEGMIF_ATTN_TC=1. lse may be NULL. */
 int segmif_sr_attention_tc_fwd(const void* q, int ldq, const void* k, const void* v, int ldkv, void* out, int ldo, int B,
                                int heads, int N, int Nk, int D, float scale, float* lse, segmif_stream_t stream);
+/* Flash-style tcgen05 kernel for ANY Nk (attention_fa_tc.cu: 128-key blocks through a TMA ring, two score buffers in TMEM so
+ * S_{j+1} = Q K_{j+1}^T runs under the softmax of S_j, online softmax with lazy rescaling of the TMEM accumulator, O += P V with V
+ * as an MN-major operand) -- the default of segmif_sr_attention_fwd / _train_fwd for head dim 64 (SEGMIF_ATTN=mma selects the
+ * mma.sync kernel); BASELINE configs[3] (MiT-B4 at 1024^2: Nk = 1024).                                                      */
+int segmif_sr_attention_fa_fwd(const void* q, int ldq, const void* k, const void* v, int ldkv, void* out, int ldo, int B,
+                               int heads, int N, int Nk, int D, float scale, float* lse, segmif_stream_t stream);
 int segmif_sr_attention_train_fwd(const void* q, int ldq, const void* k, const void* v, int ldkv, void* out, int ldo,
                                   int B, int heads, int N, int Nk, int D, float scale, float* lse, segmif_stream_t stream);
 int segmif_sr_attention_bwd(const void* q, int ldq, const void* k, const void* v, int ldkv, const void* out,

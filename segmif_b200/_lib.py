@@ -142,6 +142,7 @@ SIGNATURES = {
     "segmif_adamw_step": [P, P, P, P, c_int64, c_float, c_float, c_float, c_float, c_float, c_int, c_float, P],
     "segmif_sr_attention_train_fwd": [P, c_int, P, P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P, P],
     "segmif_sr_attention_tc_fwd": [P, c_int, P, P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P, P],
+    "segmif_sr_attention_fa_fwd": [P, c_int, P, P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P, P],
     "segmif_sr_attention_bwd": [P, c_int, P, P, c_int, P, P, c_int, P, P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int,
                                 c_int, c_float, P],
     "segmif_upsample_ce_bwd": [P, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, P, P, P, P],

@@ -2,6 +2,8 @@
 // materialising the [N, Nk] score matrix (the reference writes 184 MB of scores per layer at cfg 2).
 // Flash-style: 64 queries per CTA (4 warps x 16 rows), K/V streamed in 64-key tiles through a
 // double-buffered cp.async ring, S and O accumulators in registers, online softmax in the exp2 domain.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace segmif {
@@ -177,8 +179,17 @@ static int sr_attention_impl(const void* q, int ldq, const void* k, const void* 
   SEGMIF_REQUIRE(ldq % 8 == 0 && ldkv % 8 == 0 && ldo % 2 == 0, "sr_attention: pitches must be multiples of 8");
   SEGMIF_REQUIRE(Nk > 0, "sr_attention: Nk must be positive");
   if (B * heads == 0 || N == 0) return SEGMIF_OK;
+  // kernel selection (read once): SEGMIF_ATTN = fa (default: flash-style tcgen05 kernel, head dim 64, any Nk) | mma (the mma.sync
+  // flash kernel, also used for head dim 32) | SEGMIF_ATTN_TC=1 (the first tcgen05 kernel: whole score row in TMEM, Nk <= 320)
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("SEGMIF_ATTN");
+    mode = (e && e[0] == 'm') ? 1 : 0;
+  }
   if (sr_attention_tc_ok(B, heads, N, Nk, D, ldq, ldkv, ldo, q, k, v, out))
     return sr_attention_tc(q, ldq, k, v, ldkv, out, ldo, B, heads, N, Nk, scale, lse, as_stream(stream));
+  if (mode == 0 && ldo % 8 == 0 && sr_attention_fa_tc_supported(B, heads, N, Nk, D, ldq, ldkv, ldo, q, k, v, out))
+    return sr_attention_fa_tc(q, ldq, k, v, ldkv, out, ldo, B, heads, N, Nk, scale, lse, as_stream(stream));
   dim3 grid((unsigned)ceil_div(N, 64), (unsigned)(B * heads));
   const float sl2 = scale * 1.4426950408889634f;
   if (D == 64)
@@ -192,6 +203,15 @@ extern "C" int segmif_sr_attention_fwd(const void* q, int ldq, const void* k, co
                                        int ldo, int B, int heads, int N, int Nk, int D, float scale,
                                        segmif_stream_t stream) {
   return sr_attention_impl(q, ldq, k, v, ldkv, out, ldo, B, heads, N, Nk, D, scale, nullptr, stream);
+}
+
+/* the flash-style tcgen05 kernel explicitly (head dim 64, any Nk); lse may be NULL */
+extern "C" int segmif_sr_attention_fa_fwd(const void* q, int ldq, const void* k, const void* v, int ldkv, void* out, int ldo,
+                                          int B, int heads, int N, int Nk, int D, float scale, float* lse, segmif_stream_t stream) {
+  SEGMIF_REQUIRE(q && k && v && out, "sr_attention_fa: null pointer");
+  SEGMIF_REQUIRE(sr_attention_fa_tc_supported(B, heads, N, Nk, D, ldq, ldkv, ldo, q, k, v, out),
+                 "sr_attention_fa: needs head dim 64, 16-byte aligned pointers and pitches that are multiples of 8");
+  return sr_attention_fa_tc(q, ldq, k, v, ldkv, out, ldo, B, heads, N, Nk, scale, lse, as_stream(stream));
 }
 
 /* the tcgen05 kernel explicitly (head dim 64, Nk <= 320); lse may be NULL */

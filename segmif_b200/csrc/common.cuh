@@ -146,6 +146,12 @@ bool sr_attention_tc_ok(int B, int heads, int N, int Nk, int D, int ldq, int ldk
 int sr_attention_tc(const void* q, int ldq, const void* k, const void* v, int ldkv, void* out, int ldo, int B, int heads, int N, int Nk,
                     float scale, float* lse, cudaStream_t st);
 
+// attention_fa_tc.cu: flash-style spatial-reduction attention on tcgen05 (head dim 64, any Nk)
+bool sr_attention_fa_tc_supported(int B, int heads, int N, int Nk, int D, int ldq, int ldkv, int ldo, const void* q, const void* k,
+                                  const void* v, const void* out);
+int sr_attention_fa_tc(const void* q, int ldq, const void* k, const void* v, int ldkv, void* out, int ldo, int B, int heads, int N,
+                       int Nk, float scale, float* lse, cudaStream_t st);
+
 // wgrad_tc.cu: 3x3 weight gradients on tcgen05 (MN-major operands, accumulators resident in TMEM)
 bool wgrad_tc_ok(int B, int H, int W, int Cin, int Cout, int taps, int dil, int ldy, int ldx);
 int wgrad_tc_chunks(int B, int H, int W, int Cin, int Cout);

@@ -731,6 +731,18 @@ def sr_attention_tc(q, kv, B, heads, N, Nk, D, scale, want_lse=False):
     return (out, lse) if want_lse else out
 
 
+def sr_attention_fa(q, kv, B, heads, N, Nk, D, scale, want_lse=False):
+    """The flash-style tcgen05 attention kernel explicitly (head dim 64, any Nk); same arguments as sr_attention."""
+    st = _prep(q, kv)
+    C = heads * D
+    out = torch.empty((B * N, C), dtype=torch.bfloat16, device=q.device)
+    lse = torch.empty((B * heads, N), dtype=torch.float32, device=q.device) if want_lse else None
+    kptr = kv.data_ptr()
+    _lib.call("segmif_sr_attention_fa_fwd", _ptr(q), C, ctypes.c_void_p(kptr), ctypes.c_void_p(kptr + 2 * C), 2 * C,
+              _ptr(out), C, B, heads, N, Nk, D, float(scale), _ptr(lse), st)
+    return (out, lse) if want_lse else out
+
+
 def sr_attention_bwd(q, kv, out, dout, lse, B, heads, N, Nk, D, scale):
     """Returns (dq bf16 [B*N, C], dkv fp32 [B*Nk, 2C])."""
     st = _prep(q, kv, out, dout, lse)

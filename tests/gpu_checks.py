@@ -761,3 +761,36 @@ def baseline_size_kernels():
     l1, lg = ops.sobel_l1(A, Bq)
     rs.append(result("sobel_l1_1024", rel_err(l1 + lg, F.l1_loss(a, b) + F.l1_loss(O.sobelxy(a), O.sobelxy(b))), 1e-5))
     return rs
+
+
+@check
+def attention_flash_tcgen05():
+    """The flash-style tcgen05 attention kernel (attention_fa_tc.cu, the default for head dim 64) called explicitly: block
+    counts 1 .. 8, ragged key / query counts, several heads, the log-sum-exp output, and two adversarial cases for the lazy
+    rescaling of the TMEM accumulator: keys ordered by INCREASING score (every block raises the row maximum, by much more
+    than the 2^8 threshold) and large-magnitude scores."""
+    rs = []
+    cases = [("fa_h1_N384_Nk300", 2, 1, 384, 300, 1.0, False), ("fa_h2_N100_Nk37", 1, 2, 100, 37, 1.0, False),
+             ("fa_h5_N130_Nk128", 2, 5, 130, 128, 1.0, False), ("fa_h8_N6_Nk6", 1, 8, 6, 6, 1.0, False),
+             ("fa_Nk1024", 1, 1, 300, 1024, 1.0, False), ("fa_Nk1000_h2", 2, 2, 257, 1000, 1.0, False),
+             ("fa_rising_scores_Nk640", 1, 2, 200, 640, 4.0, True), ("fa_big_scores_Nk513", 1, 1, 129, 513, 8.0, False), ("fa_odd_tiles_N700", 1, 2, 700, 300, 1.0, False),
+             ("fa_many_pairs_per_cta", 8, 8, 1900, 300, 1.0, False), ("fa_many_pairs_Nk1024", 4, 8, 1100, 1024, 2.0, False)]
+    for name, B, heads, N, Nk, qscale, rising in cases:
+        D, C = 64, heads * 64
+        q = rnd(B, N, C, seed=11) * qscale
+        kv = rnd(B, Nk, 2 * C, seed=12)
+        if rising:                                             # key j's score grows with j for every query: k_j = (j / Nk) * 3 * mean direction
+            ramp = torch.linspace(0.2, 3.0, Nk).view(1, Nk, 1)
+            kv[..., :C] = (kv[..., :C].abs() * ramp * torch.sign(q.mean(1, keepdim=True))).bfloat16().float()
+        k, v = kv[..., :C], kv[..., C:]
+        qh = q.reshape(B, N, heads, D).permute(0, 2, 1, 3)
+        kh = k.reshape(B, Nk, heads, D).permute(0, 2, 1, 3)
+        vh = v.reshape(B, Nk, heads, D).permute(0, 2, 1, 3)
+        sc = (qh @ kh.transpose(-2, -1)) * D ** -0.5
+        ref = (sc.softmax(-1) @ vh).transpose(1, 2).reshape(B * N, C)
+        got, lse = ops.sr_attention_fa(q.bfloat16().reshape(B * N, C).to(DEV), kv.bfloat16().reshape(B * Nk, 2 * C).to(DEV), B, heads, N,
+                                       Nk, D, D ** -0.5, want_lse=True)
+        rs.append(result(name, rel_err(got.float(), ref), 1.2e-2, note=f"score range {float(sc.min()):.0f}..{float(sc.max()):.0f}"))
+        lse_ref = torch.logsumexp(sc, -1) * 1.4426950408889634                                           # exp2 domain
+        rs.append(result(name + "_lse", rel_err(lse.reshape(B, heads, N), lse_ref), 1e-3))
+    return rs

@@ -11,6 +11,10 @@
 #include "dataflow.cuh"
 #include "tc_common.cuh"
 
+#ifndef SEGMIF_TC_STAGES_SMALL
+#define SEGMIF_TC_STAGES_SMALL 3
+#endif
+
 namespace segmif {
 
 EncodeTiledFn get_encode_tiled() {
@@ -129,7 +133,10 @@ __device__ __forceinline__ void epilogue_row32(const TcEpilogue& e, float (&v)[3
   }
 }
 
-constexpr int kTcStages = 4;
+constexpr int kTcStagesDefault = 4;
+// BN <= 64: 3 stages (72 KB / 60 KB of shared memory) so that THREE CTAs share an SM -- the N <= 64 launches are HBM bound (the DRDB 1x1:
+// 1.4 GB per launch) and their row-per-thread epilogue waits on residual loads; a third CTA per SM keeps more loads in flight.
+template <int BN> struct TcStages { static constexpr int value = BN <= 64 ? (SEGMIF_TC_STAGES_SMALL) : 4; };
 constexpr int kTcThreads = 192;
 
 // dataflow.cuh: the A rows are pixels of [B, H, W] images written by a concurrently running producer stage
@@ -151,6 +158,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
                                                                 const TcEpilogue e, const int num_k_blocks,
                                                                 const int n_tiles, const int num_tiles, const GemmDfDev d) {
   constexpr int A_BYTES = 128 * 128, B_BYTES = BN * 128;
+  constexpr int kTcStages = TcStages<BN>::value;
   constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
@@ -275,6 +283,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
 template <int BN, bool GELU, bool WKN = false>
 static int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcEpilogue& e, int K, cudaStream_t st,
                           const GemmDfExtra* x = nullptr) {
+  constexpr int kTcStages = TcStages<BN>::value;
   constexpr size_t smem = (size_t)kTcStages * (128 * 128 + BN * 128) + (2 * kTcStages + 4) * 8 + 16;
   auto kern = gemm_tc_kernel<BN, GELU, WKN>;
   static bool configured = false;
@@ -287,7 +296,7 @@ static int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
   const int n_tiles = (int)ceil_div(e.N, BN), m_tiles = (int)ceil_div(e.M, 128);
   const int64_t num_tiles = (int64_t)n_tiles * m_tiles;
-  const int ctas_per_sm = BN <= 64 ? 2 : 1;          // 96 KB (BN=64) / 80 KB (BN=32) of smem: two CTAs fit and hide latency
+  const int ctas_per_sm = BN <= 64 ? (kTcStages <= 3 ? 3 : 2) : 1;          // 72 KB (BN=64) / 60 KB (BN=32) of smem with 3 stages: three CTAs fit
   int grid = (int)std::min<int64_t>(num_tiles, (int64_t)sms * ctas_per_sm);
   GemmDfDev d;
   d.dep.flags = nullptr; d.dep.target = 0; d.dep.tiles_y = d.dep.shift = d.dep.halo = 0; d.error = nullptr; d.timing = nullptr; d.H = d.W = d.HW = 1;

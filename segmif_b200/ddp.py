@@ -319,9 +319,11 @@ class SegTrainer(_GraphedStep):
         gid = lambda k: 2 if ".decoder." in k else (1 if "norm" in k.split("encoder.", 1)[-1] else 0)
         # gradients of the decode head and of encoder stages 3-4 (93 % of the 94 MB) are complete when the reverse pass
         # leaves stage 3; they are all-reduced on a side stream while stages 2 and 1 (most of the backward's TIME: they hold
-        # 94 % of the tokens) are still being differentiated.  SEGMIF_OVERLAP_ALLREDUCE=0 restores the single call.
+        # 94 % of the tokens) are still being differentiated.  Opt-in (SEGMIF_OVERLAP_ALLREDUCE=1): measured on B200 x2 and x8
+        # (profiles/r2_train_seg_n8_*_v1.json: 12.33 ms overlapped vs 12.24 ms single) the NCCL channels' CTAs take SMs from
+        # the stage-2/1 backward kernels for as long as they hide the 0.3 ms reduction, so the single call stays the default.
         early = lambda k: ".decoder." in k or any(t in k for t in ("patch_embed3.", "patch_embed4.", "block3.", "block4.", "norm3.", "norm4."))
-        self.overlap = os.environ.get("SEGMIF_OVERLAP_ALLREDUCE", "1") != "0"
+        self.overlap = os.environ.get("SEGMIF_OVERLAP_ALLREDUCE", "0") == "1"
         self.flat = FlatParams(seg_net, used=lambda k: not k.endswith("classifier.weight"), group_of=gid,
                                early_of=early if self.overlap else None)
         self._side = None

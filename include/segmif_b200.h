@@ -534,6 +534,59 @@ int segmif_sobel_map_bwd(const float* x, const float* dout, float* dx, int B, in
                          segmif_stream_t stream);
 int segmif_ew2(const float* x, const float* y, float a, float b, int mode, float* out, int64_t n, segmif_stream_t stream);
 
+/* ---- training data path on the device -------------------------------------------------------------
+ * Replaces, per batch, what the reference's DataLoader workers do per sample on the host: datasets/voc_fusion3.py:169-209
+ * (`VOC12SegDataset.__transforms`) = imutils.random_scaling2 (:34-49 -> _img_rescaling2 :69-91: Pillow BILINEAR on uint8 for
+ * the three images, NEAREST for the label), random_fliplr2 (:121-129), PhotoMetricDistortion on the visible image (:295-380:
+ * convert, mmcv.bgr2hsv / hsv2bgr = OpenCV), random_crop2 (:199-249: mean_rgb / ignore_index canvas at a random offset, up to
+ * ten candidate windows), `/ 255.0` and HWC -> CHW.  Results are bit-identical to the reference's (tests/golden/datapath.npz).
+ * The host keeps only the random draws and the accept / reject decision; it describes each sample with this struct
+ * (one array in device memory for the kernels, the same array in host memory for argument checks and grid sizing).         */
+#define SEGMIF_DP_MAX_OPS 6
+#define SEGMIF_DP_OP_CONVERT 0      /* convert(img, alpha, beta): uint8(clip(float32(img) * alpha + beta, 0, 255))  :308-312 */
+#define SEGMIF_DP_OP_SATURATION 1   /* hsv[..., 1] = convert(hsv[..., 1], alpha)                                    :332-341 */
+#define SEGMIF_DP_OP_HUE 2          /* hsv[..., 0] = (int(hsv[..., 0]) + delta) % 180                                :343-351 */
+typedef struct {
+  const unsigned char* ir;     /* decoded planes in device memory: infrared [H,W], visible [H,W,3], mask [H,W], label [H,W] */
+  const unsigned char* vis;
+  const unsigned char* mask;
+  const unsigned char* label;
+  int32_t H, W;                /* decoded size */
+  int32_t nh, nw;              /* size after random_scaling2: int(ratio * h), int(ratio * w); == H, W when rescaling is off */
+  int32_t resized;             /* 1: the images went through the uint8 resize and are float32 from there on (:75-82)         */
+  int32_t flip;                /* random_fliplr2 fired */
+  int32_t pad_h, pad_w;        /* H_pad, W_pad of random_crop2 */
+  int32_t PH, PW;              /* canvas: max(crop, nh), max(crop, nw) */
+  int32_t cand_hs[10], cand_ws[10]; /* the ten candidate windows (H_start, W_start) */
+  int32_t hs, ws;              /* the window that was kept (image stage) */
+  int32_t n_ops;               /* PhotoMetricDistortion program, in execution order */
+  int32_t op_kind[SEGMIF_DP_MAX_OPS];
+  int32_t op_u8[SEGMIF_DP_MAX_OPS];   /* the image is uint8 when this op runs (after any convert, or never resized) */
+  int32_t op_delta[SEGMIF_DP_MAX_OPS];
+  float op_alpha[SEGMIF_DP_MAX_OPS];
+  float op_beta[SEGMIF_DP_MAX_OPS];
+  int32_t ks_x, ks_y;          /* Pillow ksize per axis: ceil(max(in/out, 1)) * 2 + 1 */
+  int32_t roi_x0, roi_x1, roi_y0, roi_y1; /* part of the resized image the kept window touches (unflipped coordinates) */
+  int32_t src_y0, src_y1;      /* source rows the vertical pass needs for roi_y0..roi_y1 */
+  int64_t tab_off;             /* int32 elements into table_arena: 2 nw + nw ks_x + 2 nh + nh ks_y + nw + nh per resized sample */
+  int64_t tmp_off;             /* bytes into tmp_arena:     5 (src_y1 - src_y0) (roi_x1 - roi_x0) */
+  int64_t rs_off;              /* bytes into resized_arena: 5 (roi_y1 - roi_y0) (roi_x1 - roi_x0) */
+  int64_t lab_off;             /* bytes into label_arena:   PH PW */
+} segmif_dp_sample;
+/* label stage: coefficient / index tables, the label canvas, and for each candidate window stats[n][10][3] = {number of
+ * non-ignored values present, count of the most frequent one, non-ignored pixels} (np.unique at :222-225).                  */
+int segmif_dp_label_stage(const segmif_dp_sample* samples_dev, const segmif_dp_sample* samples_host, int n, int crop,
+                          int ignore_index, int32_t* table_arena, unsigned char* label_arena, int32_t* stats,
+                          segmif_stream_t stream);
+/* image stage: both resize passes over the needed region, then flip + distortion + canvas + crop + /255 + CHW.
+ * mean_rgb: 3 floats in HOST memory.  Outputs fp32 [n,3,crop,crop] x3, label fp32 [n,crop,crop] (+ int64 copy if given).   */
+int segmif_dp_image_stage(const segmif_dp_sample* samples_dev, const segmif_dp_sample* samples_host, int n, int crop,
+                          const float* mean_rgb, const int32_t* table_arena, unsigned char* tmp_arena,
+                          unsigned char* resized_arena, const unsigned char* label_arena, float* out_ir, float* out_vis,
+                          float* out_mask, float* out_label, int64_t* out_label_i64, segmif_stream_t stream);
+/* aug=False branch (:193-205 on uint8 arrays): HWC uint8 (C = 1 is replicated to three channels) -> CHW float64 / 255.0.   */
+int segmif_dp_u8_to_chw_f64(const unsigned char* src, int H, int W, int C, double* dst, segmif_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

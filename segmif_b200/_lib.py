@@ -82,6 +82,22 @@ class DrdbDataflowParams(ctypes.Structure):
                 ("B", c_int), ("H", c_int), ("W", c_int), ("flags", c_void_p), ("ctas", c_int * 7)]
 
 
+DP_MAX_OPS = 6
+
+
+class DpSample(ctypes.Structure):
+    """Mirror of segmif_dp_sample (training data path, include/segmif_b200.h)."""
+    _fields_ = [("ir", c_void_p), ("vis", c_void_p), ("mask", c_void_p), ("label", c_void_p),
+                ("H", c_int), ("W", c_int), ("nh", c_int), ("nw", c_int), ("resized", c_int), ("flip", c_int),
+                ("pad_h", c_int), ("pad_w", c_int), ("PH", c_int), ("PW", c_int),
+                ("cand_hs", c_int * 10), ("cand_ws", c_int * 10), ("hs", c_int), ("ws", c_int), ("n_ops", c_int),
+                ("op_kind", c_int * DP_MAX_OPS), ("op_u8", c_int * DP_MAX_OPS), ("op_delta", c_int * DP_MAX_OPS),
+                ("op_alpha", c_float * DP_MAX_OPS), ("op_beta", c_float * DP_MAX_OPS),
+                ("ks_x", c_int), ("ks_y", c_int), ("roi_x0", c_int), ("roi_x1", c_int), ("roi_y0", c_int), ("roi_y1", c_int),
+                ("src_y0", c_int), ("src_y1", c_int),
+                ("tab_off", c_int64), ("tmp_off", c_int64), ("rs_off", c_int64), ("lab_off", c_int64)]
+
+
 P = c_void_p
 # name -> argtypes; every function returns int except where noted in _RESTYPES
 SIGNATURES = {
@@ -156,6 +172,9 @@ SIGNATURES = {
     "segmif_dwconv3x3_gelu_bwd": [P, P, P, P, P, c_int, c_int, c_int, c_int, P, P, P, P],
     "segmif_dwconv3x3_gelu_bwd_workspace": [c_int, c_int, c_int, c_int],
     "segmif_confusion_matrix": [P, P, c_int64, c_int, P, P],
+    "segmif_dp_label_stage": [P, P, c_int, c_int, c_int, P, P, P, P],
+    "segmif_dp_image_stage": [P, P, c_int, c_int, P, P, P, P, P, P, P, P, P, P, P],
+    "segmif_dp_u8_to_chw_f64": [P, c_int, c_int, c_int, P, P],
     "segmif_fused_to_uint8": [P, P, P, c_int, c_int64, P],
     "segmif_wgrad_chunks": [c_int, c_int, c_int, c_int64, c_int, c_int, c_int, c_int],
     "segmif_col2im": [P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P],

@@ -10,6 +10,7 @@ def _checks():
     import gpu_checks
     import gpu_checks_train  # noqa: F401  (registers the training-side checks in the same list)
     import gpu_checks_strict  # noqa: F401  (strict-precision mode)
+    import gpu_checks_data  # noqa: F401  (device data path)
     return gpu_checks.CHECKS
 
 

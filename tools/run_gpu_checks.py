@@ -10,6 +10,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import gpu_checks  # noqa: E402
 import gpu_checks_train  # noqa: E402,F401
 import gpu_checks_strict  # noqa: E402,F401
+import gpu_checks_data  # noqa: E402,F401
 
 if __name__ == "__main__":
     only = sys.argv[1:]

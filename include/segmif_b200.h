@@ -569,15 +569,17 @@ typedef struct {
   int32_t roi_x0, roi_x1, roi_y0, roi_y1; /* part of the resized image the kept window touches (unflipped coordinates) */
   int32_t src_y0, src_y1;      /* source rows the vertical pass needs for roi_y0..roi_y1 */
   int64_t tab_off;             /* int32 elements into table_arena: 2 nw + nw ks_x + 2 nh + nh ks_y + nw + nh per resized sample */
-  int64_t tmp_off;             /* bytes into tmp_arena:     5 (src_y1 - src_y0) (roi_x1 - roi_x0) */
-  int64_t rs_off;              /* bytes into resized_arena: 5 (roi_y1 - roi_y0) (roi_x1 - roi_x0) */
-  int64_t lab_off;             /* bytes into label_arena:   PH PW */
+  /* uint8 intermediates use a row pitch p16(w) = (w + 15) & ~15; offsets are multiples of 16 and the arenas 16-byte aligned */
+  int64_t tmp_off;             /* bytes into tmp_arena:     5 (src_y1 - src_y0) p16(roi_x1 - roi_x0) */
+  int64_t rs_off;              /* bytes into resized_arena: 5 (roi_y1 - roi_y0) p16(roi_x1 - roi_x0) */
+  int64_t lab_off;             /* bytes into label_arena:   PH p16(PW) */
 } segmif_dp_sample;
 /* label stage: coefficient / index tables, the label canvas, and for each candidate window stats[n][10][3] = {number of
- * non-ignored values present, count of the most frequent one, non-ignored pixels} (np.unique at :222-225).                  */
+ * non-ignored values present, count of the most frequent one, non-ignored pixels} (np.unique at :222-225).
+ * hist_ws: n * 10 * 256 int32 of device workspace.                                                                         */
 int segmif_dp_label_stage(const segmif_dp_sample* samples_dev, const segmif_dp_sample* samples_host, int n, int crop,
-                          int ignore_index, int32_t* table_arena, unsigned char* label_arena, int32_t* stats,
-                          segmif_stream_t stream);
+                          int ignore_index, int32_t* table_arena, unsigned char* label_arena, int32_t* hist_ws,
+                          int32_t* stats, segmif_stream_t stream);
 /* image stage: both resize passes over the needed region, then flip + distortion + canvas + crop + /255 + CHW.
  * mean_rgb: 3 floats in HOST memory.  Outputs fp32 [n,3,crop,crop] x3, label fp32 [n,crop,crop] (+ int64 copy if given).   */
 int segmif_dp_image_stage(const segmif_dp_sample* samples_dev, const segmif_dp_sample* samples_host, int n, int crop,

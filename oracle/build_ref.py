@@ -18,7 +18,7 @@ DST = os.path.join(HERE, "_ref")
 SRC = os.environ.get("SEGMIF_REFERENCE_SRC", "/root/reference")
 # the modules on the path SURVEY.md 8(a) names (+ the config surface); nothing else of the reference is needed
 FILES = ["core/mix_transformer.py", "core/segformer_head.py", "core/model_fusion.py", "core/Entropy.py", "core/loss.py",
-         "pytorch_ssim/__init__.py", "lap_loss.py"]
+         "pytorch_ssim/__init__.py", "lap_loss.py", "datasets/imutils.py", "datasets/voc_fusion3.py"]
 
 
 def build(src=SRC, dst=DST):

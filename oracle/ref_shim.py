@@ -196,3 +196,37 @@ def build_reference_models(ns, backbone, seed=0):
     synth.load_synthetic(seg, seed)
     synth.load_synthetic(fus, seed)
     return seg.eval(), fus.eval()
+
+
+def load_reference_datapath():
+    """The reference's data path (datasets/imutils.py + datasets/voc_fusion3.py), unmodified, as a callable
+    `transforms(image, image_vis, image_mask, label, crop_size, rescale_range) -> (image, image_vis, image_mask, label)` that runs
+    `VOC12SegDataset.__transforms` (voc_fusion3.py:169-209) with the global `random` / `np.random` generators.  mmcv is not in
+    this image: its two colour helpers are `cv2.cvtColor(img, cv2.COLOR_BGR2HSV / HSV2BGR)` (mmcv/image/colorspace.py) and are
+    attached to the stand-in module; imageio (PNG reading only) is stubbed.  Needs Pillow and OpenCV."""
+    import cv2
+    _install_stubs()
+    mm = sys.modules["mmcv"]
+    mm.bgr2hsv = lambda img: cv2.cvtColor(img, cv2.COLOR_BGR2HSV)
+    mm.hsv2bgr = lambda img: cv2.cvtColor(img, cv2.COLOR_HSV2BGR)
+    sys.modules.setdefault("imageio", types.ModuleType("imageio"))
+    try:
+        import torchvision  # noqa: F401  (imutils.py:6)
+    except ImportError:
+        sys.modules.setdefault("torchvision", types.ModuleType("torchvision"))
+    pkg_name = f"{_PREFIX}.datasets"
+    if pkg_name not in sys.modules:
+        pkg = types.ModuleType(pkg_name)
+        pkg.__path__ = [os.path.join(REF_ROOT, "datasets")]
+        sys.modules[pkg_name] = pkg
+    imutils = _load("datasets.imutils", os.path.join("datasets", "imutils.py"), package=pkg_name)
+    sys.modules[pkg_name].imutils = imutils
+    voc = _load("datasets.voc_fusion3", os.path.join("datasets", "voc_fusion3.py"), package=pkg_name)
+
+    def transforms(image, image_vis, image_mask, label, crop_size=512, rescale_range=(0.5, 2.0)):
+        ds = object.__new__(voc.VOC12SegDataset)
+        ds.aug, ds.ignore_index, ds.resize_range, ds.rescale_range, ds.crop_size, ds.img_fliplr = True, 255, [512, 640], rescale_range, crop_size, True
+        ds.color_jittor = imutils.PhotoMetricDistortion()
+        return ds._VOC12SegDataset__transforms(image, image_vis, image_mask, label)
+
+    return transforms

@@ -172,7 +172,7 @@ SIGNATURES = {
     "segmif_dwconv3x3_gelu_bwd": [P, P, P, P, P, c_int, c_int, c_int, c_int, P, P, P, P],
     "segmif_dwconv3x3_gelu_bwd_workspace": [c_int, c_int, c_int, c_int],
     "segmif_confusion_matrix": [P, P, c_int64, c_int, P, P],
-    "segmif_dp_label_stage": [P, P, c_int, c_int, c_int, P, P, P, P],
+    "segmif_dp_label_stage": [P, P, c_int, c_int, c_int, P, P, P, P, P],
     "segmif_dp_image_stage": [P, P, c_int, c_int, P, P, P, P, P, P, P, P, P, P, P],
     "segmif_dp_u8_to_chw_f64": [P, c_int, c_int, c_int, P, P],
     "segmif_fused_to_uint8": [P, P, P, c_int, c_int64, P],

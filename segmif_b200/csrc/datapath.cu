@@ -19,6 +19,17 @@ namespace segmif {
 
 constexpr int kPrecisionBits = 32 - 8 - 2;   // Resample.c PRECISION_BITS
 
+// The 352-byte descriptor is staged once per block in shared memory: a per-thread copy would live in local memory (the op arrays
+// are indexed dynamically) and cost more traffic than the pixels.
+__device__ __forceinline__ const segmif_dp_sample& stage_sample(const segmif_dp_sample* __restrict__ samples, int idx, segmif_dp_sample* sh) {
+  static_assert(sizeof(segmif_dp_sample) % 4 == 0, "descriptor is copied as 32-bit words");
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(samples + idx);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(sh);
+  for (int i = threadIdx.x; i < (int)(sizeof(segmif_dp_sample) / 4); i += blockDim.x) dst[i] = src[i];
+  __syncthreads();
+  return *sh;
+}
+
 __device__ __forceinline__ const int32_t* tab(const int32_t* arena, const segmif_dp_sample& s, int which) {
   // [xmin_x nw][xcnt_x nw][k_x nw*ks_x][xmin_y nh][xcnt_y nh][k_y nh*ks_y][near_x nw][near_y nh]
   const int32_t* p = arena + s.tab_off;
@@ -42,7 +53,8 @@ __device__ __forceinline__ const int32_t* tab(const int32_t* arena, const segmif
 // grid (ceil(max(nh, nw) / 128), 2, n): axis 0 = x (W -> nw), 1 = y (H -> nh).  Thread (axis, xx) writes one coefficient row;
 // thread 0 of block 0 of each axis walks the NEAREST index table sequentially (the reference accumulates `xo += a0`).
 __global__ void __launch_bounds__(128) resize_tables_kernel(const segmif_dp_sample* __restrict__ samples, int32_t* __restrict__ arena) {
-  const segmif_dp_sample s = samples[blockIdx.z];
+  __shared__ segmif_dp_sample sh_sample;
+  const segmif_dp_sample& s = stage_sample(samples, blockIdx.z, &sh_sample);
   if (!s.resized) return;
   const int axis = blockIdx.y;
   const int in_size = axis == 0 ? s.W : s.H, out_size = axis == 0 ? s.nw : s.nh, ks = axis == 0 ? s.ks_x : s.ks_y;
@@ -99,99 +111,155 @@ __device__ __forceinline__ uint8_t clip8(int v) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------- resize
+// Row pitch of every uint8 intermediate (label canvas, horizontal-pass output, resized region): the width rounded up to 16, so
+// that a thread can move four neighbouring pixels with one aligned 32-bit access.
+__host__ __device__ __forceinline__ int pitch16(int w) { return (w + 15) & ~15; }
+
 // Horizontal pass over the source rows the vertical pass will need [src_y0, src_y1) and the output columns [roi_x0, roi_x1):
-// tmp is PLANAR uint8 [5][rows][roi_w] (ir, vis c0, vis c1, vis c2, mask).  grid (ceil(roi_w/128), rows, n).
+// tmp is PLANAR uint8 [5][rows][pitch] (ir, vis c0, vis c1, vis c2, mask).  Four output columns per thread.
+// grid (ceil(pitch/4/128), rows, n).
 __global__ void __launch_bounds__(128) resize_h_kernel(const segmif_dp_sample* __restrict__ samples, const int32_t* __restrict__ arena,
                                                        uint8_t* __restrict__ tmp_arena) {
-  const segmif_dp_sample s = samples[blockIdx.z];
+  __shared__ segmif_dp_sample sh_sample;
+  const segmif_dp_sample& s = stage_sample(samples, blockIdx.z, &sh_sample);
   if (!s.resized) return;
-  const int rows = s.src_y1 - s.src_y0, roi_w = s.roi_x1 - s.roi_x0;
-  const int r = blockIdx.y, xo = blockIdx.x * 128 + threadIdx.x;
-  if (r >= rows || xo >= roi_w) return;
-  const int xx = s.roi_x0 + xo, y = s.src_y0 + r;
-  const int lo = tab(arena, s, 0)[xx], n = tab(arena, s, 1)[xx];
-  const int32_t* k = tab(arena, s, 2) + (int64_t)xx * s.ks_x;
-  const uint8_t* ir = s.ir + (int64_t)y * s.W + lo;
-  const uint8_t* vis = s.vis + ((int64_t)y * s.W + lo) * 3;
-  const uint8_t* mk = s.mask + (int64_t)y * s.W + lo;
-  int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0, a3 = a0, a4 = a0;
-  for (int j = 0; j < n; ++j) {
-    const int kj = k[j];
-    a0 += kj * ir[j];
-    a1 += kj * vis[3 * j];
-    a2 += kj * vis[3 * j + 1];
-    a3 += kj * vis[3 * j + 2];
-    a4 += kj * mk[j];
+  const int rows = s.src_y1 - s.src_y0, roi_w = s.roi_x1 - s.roi_x0, pitch = pitch16(roi_w);
+  const int r = blockIdx.y, x4 = (blockIdx.x * 128 + threadIdx.x) * 4;
+  if (r >= rows || x4 >= roi_w) return;
+  const int y = s.src_y0 + r;
+  const int32_t* xmin_t = tab(arena, s, 0);
+  const int32_t* xcnt_t = tab(arena, s, 1);
+  const int32_t* k_t = tab(arena, s, 2);
+  uint32_t pk[5] = {0u, 0u, 0u, 0u, 0u};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (x4 + q >= roi_w) break;
+    const int xx = s.roi_x0 + x4 + q;
+    const int lo = xmin_t[xx], n = xcnt_t[xx];
+    const int32_t* k = k_t + (int64_t)xx * s.ks_x;
+    const uint8_t* ir = s.ir + (int64_t)y * s.W + lo;
+    const uint8_t* vis = s.vis + ((int64_t)y * s.W + lo) * 3;
+    const uint8_t* mk = s.mask + (int64_t)y * s.W + lo;
+    int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0, a3 = a0, a4 = a0;
+    for (int j = 0; j < n; ++j) {
+      const int kj = k[j];
+      a0 += kj * ir[j];
+      a1 += kj * vis[3 * j];
+      a2 += kj * vis[3 * j + 1];
+      a3 += kj * vis[3 * j + 2];
+      a4 += kj * mk[j];
+    }
+    pk[0] |= (uint32_t)clip8(a0) << (8 * q);
+    pk[1] |= (uint32_t)clip8(a1) << (8 * q);
+    pk[2] |= (uint32_t)clip8(a2) << (8 * q);
+    pk[3] |= (uint32_t)clip8(a3) << (8 * q);
+    pk[4] |= (uint32_t)clip8(a4) << (8 * q);
   }
-  uint8_t* t = tmp_arena + s.tmp_off + (int64_t)r * roi_w + xo;
-  const int64_t plane = (int64_t)rows * roi_w;
-  t[0] = clip8(a0);
-  t[plane] = clip8(a1);
-  t[2 * plane] = clip8(a2);
-  t[3 * plane] = clip8(a3);
-  t[4 * plane] = clip8(a4);
+  uint8_t* t = tmp_arena + s.tmp_off + (int64_t)r * pitch + x4;
+  const int64_t plane = (int64_t)rows * pitch;
+#pragma unroll
+  for (int c = 0; c < 5; ++c) *reinterpret_cast<uint32_t*>(t + c * plane) = pk[c];
 }
 
-// Vertical pass: resized ROI, planar uint8 [5][roi_h][roi_w].  grid (ceil(roi_w/128), roi_h, n).
+// Vertical pass: resized region, planar uint8 [5][roi_h][pitch], four columns per thread.  grid (ceil(pitch/4/128), roi_h, n).
 __global__ void __launch_bounds__(128) resize_v_kernel(const segmif_dp_sample* __restrict__ samples, const int32_t* __restrict__ arena,
                                                        const uint8_t* __restrict__ tmp_arena, uint8_t* __restrict__ rs_arena) {
-  const segmif_dp_sample s = samples[blockIdx.z];
+  __shared__ segmif_dp_sample sh_sample;
+  const segmif_dp_sample& s = stage_sample(samples, blockIdx.z, &sh_sample);
   if (!s.resized) return;
-  const int rows = s.src_y1 - s.src_y0, roi_w = s.roi_x1 - s.roi_x0, roi_h = s.roi_y1 - s.roi_y0;
-  const int yo = blockIdx.y, xo = blockIdx.x * 128 + threadIdx.x;
-  if (yo >= roi_h || xo >= roi_w) return;
+  const int rows = s.src_y1 - s.src_y0, roi_w = s.roi_x1 - s.roi_x0, roi_h = s.roi_y1 - s.roi_y0, pitch = pitch16(roi_w);
+  const int yo = blockIdx.y, x4 = (blockIdx.x * 128 + threadIdx.x) * 4;
+  if (yo >= roi_h || x4 >= roi_w) return;
   const int yy = s.roi_y0 + yo;
   const int lo = tab(arena, s, 3)[yy], n = tab(arena, s, 4)[yy];
   const int32_t* k = tab(arena, s, 5) + (int64_t)yy * s.ks_y;
-  const int64_t tplane = (int64_t)rows * roi_w, oplane = (int64_t)roi_h * roi_w;
-  const uint8_t* t = tmp_arena + s.tmp_off + (int64_t)(lo - s.src_y0) * roi_w + xo;
-  uint8_t* o = rs_arena + s.rs_off + (int64_t)yo * roi_w + xo;
+  const int64_t tplane = (int64_t)rows * pitch, oplane = (int64_t)roi_h * pitch;
+  const uint8_t* t = tmp_arena + s.tmp_off + (int64_t)(lo - s.src_y0) * pitch + x4;
+  uint8_t* o = rs_arena + s.rs_off + (int64_t)yo * pitch + x4;
 #pragma unroll
   for (int c = 0; c < 5; ++c) {
-    int acc = 1 << (kPrecisionBits - 1);
-    for (int j = 0; j < n; ++j) acc += k[j] * t[c * tplane + (int64_t)j * roi_w];
-    o[c * oplane] = clip8(acc);
+    int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0, a3 = a0;
+    for (int j = 0; j < n; ++j) {
+      const uint32_t v = *reinterpret_cast<const uint32_t*>(t + c * tplane + (int64_t)j * pitch);
+      const int kj = k[j];
+      a0 += kj * (int)(v & 255u);
+      a1 += kj * (int)((v >> 8) & 255u);
+      a2 += kj * (int)((v >> 16) & 255u);
+      a3 += kj * (int)(v >> 24);
+    }
+    *reinterpret_cast<uint32_t*>(o + c * oplane) =
+        (uint32_t)clip8(a0) | ((uint32_t)clip8(a1) << 8) | ((uint32_t)clip8(a2) << 16) | ((uint32_t)clip8(a3) << 24);
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------------- labels
-// pad_label of random_crop2 as uint8 [PH][PW] (the reference holds it as float32; the values are the same integers).
-__global__ void __launch_bounds__(256) label_pad_kernel(const segmif_dp_sample* __restrict__ samples, const int32_t* __restrict__ arena,
+// pad_label of random_crop2 as uint8 [PH][pitch16(PW)] (the reference holds it as float32; the values are the same integers).
+// Four pixels per thread, one 32-bit store.  grid (ceil(max pitch / 4 / 128), max PH, n).
+__global__ void __launch_bounds__(128) label_pad_kernel(const segmif_dp_sample* __restrict__ samples, const int32_t* __restrict__ arena,
                                                         uint8_t* __restrict__ lab_arena, int ignore_index) {
-  const segmif_dp_sample s = samples[blockIdx.z];
-  const int64_t n = (int64_t)s.PH * s.PW;
+  __shared__ segmif_dp_sample sh_sample;
+  const segmif_dp_sample& s = stage_sample(samples, blockIdx.z, &sh_sample);
+  const int pitch = pitch16(s.PW);
+  const int y = blockIdx.y, x4 = (blockIdx.x * 128 + threadIdx.x) * 4;
+  if (y >= s.PH || x4 >= pitch) return;
+  const int ys = y - s.pad_h;
+  const bool row_in = ys >= 0 && ys < s.nh;
+  const uint8_t* src_row = row_in ? s.label + (int64_t)(s.resized ? tab(arena, s, 7)[ys] : ys) * s.W : nullptr;
   const int32_t* near_x = tab(arena, s, 6);
-  const int32_t* near_y = tab(arena, s, 7);
-  uint8_t* dst = lab_arena + s.lab_off;
-  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
-    const int y = (int)(i / s.PW), x = (int)(i - (int64_t)y * s.PW);
-    const int ys = y - s.pad_h, xs = x - s.pad_w;
-    uint8_t v = (uint8_t)ignore_index;
-    if (ys >= 0 && ys < s.nh && xs >= 0 && xs < s.nw) {
+  uint32_t pk = 0u;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int xs = x4 + q - s.pad_w;
+    uint32_t v = (uint32_t)ignore_index;
+    if (row_in && xs >= 0 && xs < s.nw) {
       const int xr = s.flip ? s.nw - 1 - xs : xs;
-      const int sy = s.resized ? near_y[ys] : ys, sx = s.resized ? near_x[xr] : xr;
-      v = s.label[(int64_t)sy * s.W + sx];
+      v = src_row[s.resized ? near_x[xr] : xr];
     }
-    dst[i] = v;
+    pk |= v << (8 * q);
   }
+  *reinterpret_cast<uint32_t*>(lab_arena + s.lab_off + (int64_t)y * pitch + x4) = pk;
 }
 
-// One block per (candidate, sample): 256-bin histogram of the window, then {#values != ignore, max count, sum of counts}.
-__global__ void __launch_bounds__(256) window_stats_kernel(const segmif_dp_sample* __restrict__ samples, const uint8_t* __restrict__ lab_arena,
-                                                           int crop, int ignore_index, int32_t* __restrict__ stats) {
-  const segmif_dp_sample s = samples[blockIdx.y];
+// Histogram of each candidate window: grid (10 candidates, kHistSlices row slices, n).  Labels are piecewise constant, so each
+// thread walks 32 consecutive pixels and issues one shared-memory atomic per RUN of equal values; non-empty bins are then added
+// to hist_ws [n][10][256] (zeroed by the entry point).
+constexpr int kHistSlices = 8;
+__global__ void __launch_bounds__(256) window_hist_kernel(const segmif_dp_sample* __restrict__ samples, const uint8_t* __restrict__ lab_arena,
+                                                          int crop, unsigned int* __restrict__ hist_ws) {
+  __shared__ segmif_dp_sample sh_sample;
+  const segmif_dp_sample& s = stage_sample(samples, blockIdx.z, &sh_sample);
   const int cand = blockIdx.x;
   __shared__ unsigned int hist[256];
   hist[threadIdx.x] = 0u;
   __syncthreads();
-  const uint8_t* lab = lab_arena + s.lab_off + (int64_t)s.cand_hs[cand] * s.PW + s.cand_ws[cand];
-  const int n = crop * crop;
-  for (int i = threadIdx.x; i < n; i += 256) {
-    const int y = i / crop, x = i - y * crop;
-    atomicAdd(&hist[lab[(int64_t)y * s.PW + x]], 1u);
+  const int pitch = pitch16(s.PW);
+  const int rps = (crop + kHistSlices - 1) / kHistSlices, r0 = blockIdx.y * rps, r1 = min(crop, r0 + rps);
+  const int segs = (crop + 31) / 32, total = max(r1 - r0, 0) * segs;
+  const uint8_t* lab = lab_arena + s.lab_off + (int64_t)s.cand_hs[cand] * pitch + s.cand_ws[cand];
+  for (int t = threadIdx.x; t < total; t += 256) {
+    const int row = r0 + t / segs, x0 = (t % segs) * 32, x1 = min(crop, x0 + 32);
+    const uint8_t* p = lab + (int64_t)row * pitch;
+    unsigned cur = p[x0], cnt = 1;
+    for (int x = x0 + 1; x < x1; ++x) {
+      const unsigned v = p[x];
+      if (v == cur) {
+        ++cnt;
+      } else {
+        atomicAdd(&hist[cur], cnt);
+        cur = v;
+        cnt = 1;
+      }
+    }
+    atomicAdd(&hist[cur], cnt);
   }
   __syncthreads();
-  unsigned int c = threadIdx.x == (unsigned)ignore_index ? 0u : hist[threadIdx.x];
+  if (hist[threadIdx.x]) atomicAdd(hist_ws + ((int64_t)blockIdx.z * 10 + cand) * 256 + threadIdx.x, hist[threadIdx.x]);
+}
+
+// One block per (candidate, sample): {#values != ignore present, count of the most frequent one, non-ignored pixels}.
+__global__ void __launch_bounds__(256) window_stats_kernel(const unsigned int* __restrict__ hist_ws, int ignore_index, int32_t* __restrict__ stats) {
+  const int cand = blockIdx.x;
+  unsigned int c = threadIdx.x == (unsigned)ignore_index ? 0u : hist_ws[((int64_t)blockIdx.y * 10 + cand) * 256 + threadIdx.x];
   unsigned int nz = c ? 1u : 0u, mx = c, sm = c;
   for (int o = 16; o; o >>= 1) {
     nz += __shfl_xor_sync(0xffffffffu, nz, o);
@@ -232,13 +300,14 @@ __device__ __forceinline__ int hsv_div_table(int num, double den) {   // cvRound
   return (int)rint(__ddiv_rn((double)(num << 12), den));
 }
 
-__device__ __forceinline__ void bgr2hsv_u8(int b, int g, int r, int& h, int& s, int& v) {
+// div_tab: [0,256) sdiv, [256,512) hdiv (OpenCV builds the same tables once; here once per block that needs them)
+__device__ __forceinline__ void bgr2hsv_u8(int b, int g, int r, const int* __restrict__ div_tab, int& h, int& s, int& v) {
   v = max(max(b, g), r);
   const int vmin = min(min(b, g), r);
   const int diff = v - vmin;
   const int vr = v == r ? -1 : 0, vg = v == g ? -1 : 0;
-  const int sdiv = v ? hsv_div_table(255, (double)v) : 0;
-  const int hdiv = diff ? hsv_div_table(180, 6.0 * diff) : 0;
+  const int sdiv = div_tab[v];
+  const int hdiv = div_tab[256 + diff];
   s = (diff * sdiv + (1 << 11)) >> 12;
   h = (vr & (g - b)) + (~vr & ((vg & (b - r + 2 * diff)) + ((~vg) & (r - g + 4 * diff))));
   h = (h * hdiv + (1 << 11)) >> 12;
@@ -303,7 +372,7 @@ __device__ __forceinline__ int py_mod180(int v) {
 
 // PhotoMetricDistortion on one pixel.  The dtype of the image (uint8 or float32) at each op is resolved by the host
 // (op_u8[i]); values of a uint8 image are held as exact small integers in the float registers.
-__device__ __forceinline__ Px photometric(Px p, const segmif_dp_sample& s, bool tail8, bool tail32) {
+__device__ __forceinline__ Px photometric(Px p, const segmif_dp_sample& s, const int* __restrict__ div_tab, bool tail8, bool tail32) {
   for (int i = 0; i < s.n_ops; ++i) {
     const int kind = s.op_kind[i];
     if (kind == SEGMIF_DP_OP_CONVERT) {
@@ -312,7 +381,7 @@ __device__ __forceinline__ Px photometric(Px p, const segmif_dp_sample& s, bool 
       p.r = convert_u8(p.r, s.op_alpha[i], s.op_beta[i]);
     } else if (s.op_u8[i]) {
       int h, sa, v, b, g, r;
-      bgr2hsv_u8((int)p.b, (int)p.g, (int)p.r, h, sa, v);
+      bgr2hsv_u8((int)p.b, (int)p.g, (int)p.r, div_tab, h, sa, v);
       if (kind == SEGMIF_DP_OP_SATURATION) sa = (int)convert_u8((float)sa, s.op_alpha[i], 0.f);
       else h = py_mod180(h + s.op_delta[i]);
       hsv2bgr_u8(h, sa, v, tail32, b, g, r);
@@ -335,7 +404,18 @@ __global__ void __launch_bounds__(256) finish_kernel(const segmif_dp_sample* __r
                                                      const uint8_t* __restrict__ lab_arena, int crop, float mean0, float mean1, float mean2,
                                                      float* __restrict__ out_ir, float* __restrict__ out_vis, float* __restrict__ out_mask,
                                                      float* __restrict__ out_label, int64_t* __restrict__ label_i64) {
-  const segmif_dp_sample s = samples[blockIdx.z];
+  __shared__ segmif_dp_sample sh_sample;
+  const segmif_dp_sample& s = stage_sample(samples, blockIdx.z, &sh_sample);
+  __shared__ int div_tab[512];
+  bool need_tab = false;
+  for (int k = 0; k < s.n_ops; ++k) need_tab |= s.op_kind[k] != SEGMIF_DP_OP_CONVERT && s.op_u8[k];
+  if (need_tab) {                                               // uniform per block
+    for (int k = threadIdx.x; k < 512; k += 256) {
+      const int d = k & 255;
+      div_tab[k] = d == 0 ? 0 : (k < 256 ? hsv_div_table(255, (double)d) : hsv_div_table(180, 6.0 * d));
+    }
+    __syncthreads();
+  }
   const int i = blockIdx.x * 256 + threadIdx.x;
   const int n = crop * crop;
   if (i >= n) return;
@@ -343,7 +423,7 @@ __global__ void __launch_bounds__(256) finish_kernel(const segmif_dp_sample* __r
   const int yp = s.hs + y, xp = s.ws + x;                       // canvas coordinates
   const int ys = yp - s.pad_h, xs = xp - s.pad_w;               // coordinates in the (flipped) image PhotoMetricDistortion saw
   const int64_t o = (int64_t)blockIdx.z * 3 * n + i;
-  const uint8_t lab = lab_arena[s.lab_off + (int64_t)yp * s.PW + xp];
+  const uint8_t lab = lab_arena[s.lab_off + (int64_t)yp * pitch16(s.PW) + xp];
   out_label[(int64_t)blockIdx.z * n + i] = (float)lab;
   if (label_i64) label_i64[(int64_t)blockIdx.z * n + i] = (int64_t)lab;
   float ir, mk;
@@ -351,9 +431,9 @@ __global__ void __launch_bounds__(256) finish_kernel(const segmif_dp_sample* __r
   if (ys >= 0 && ys < s.nh && xs >= 0 && xs < s.nw) {
     const int xr = s.flip ? s.nw - 1 - xs : xs;
     if (s.resized) {
-      const int roi_w = s.roi_x1 - s.roi_x0, roi_h = s.roi_y1 - s.roi_y0;
-      const int64_t plane = (int64_t)roi_h * roi_w;
-      const uint8_t* q = rs_arena + s.rs_off + (int64_t)(ys - s.roi_y0) * roi_w + (xr - s.roi_x0);
+      const int pitch = pitch16(s.roi_x1 - s.roi_x0), roi_h = s.roi_y1 - s.roi_y0;
+      const int64_t plane = (int64_t)roi_h * pitch;
+      const uint8_t* q = rs_arena + s.rs_off + (int64_t)(ys - s.roi_y0) * pitch + (xr - s.roi_x0);
       ir = (float)q[0];
       p = Px{(float)q[plane], (float)q[2 * plane], (float)q[3 * plane]};
       mk = (float)q[4 * plane];
@@ -363,7 +443,7 @@ __global__ void __launch_bounds__(256) finish_kernel(const segmif_dp_sample* __r
       p = Px{(float)s.vis[3 * q], (float)s.vis[3 * q + 1], (float)s.vis[3 * q + 2]};
       mk = (float)s.mask[q];
     }
-    p = photometric(p, s, xs >= (s.nw / 8) * 8, xs >= (s.nw / 32) * 32);
+    p = photometric(p, s, div_tab, xs >= (s.nw / 8) * 8, xs >= (s.nw / 32) * 32);
     out_ir[o] = __fdiv_rn(ir, 255.f);
     out_ir[o + n] = __fdiv_rn(ir, 255.f);
     out_ir[o + 2 * n] = __fdiv_rn(ir, 255.f);
@@ -403,9 +483,9 @@ static int max_of(const segmif_dp_sample* host, int n, int (*f)(const segmif_dp_
 }
 
 extern "C" int segmif_dp_label_stage(const segmif_dp_sample* samples_dev, const segmif_dp_sample* samples_host, int n, int crop,
-                                     int ignore_index, int32_t* table_arena, uint8_t* label_arena, int32_t* stats,
+                                     int ignore_index, int32_t* table_arena, uint8_t* label_arena, int32_t* hist_ws, int32_t* stats,
                                      segmif_stream_t stream) {
-  SEGMIF_REQUIRE(samples_dev && samples_host && table_arena && label_arena && stats && n > 0 && crop > 0, "dp_label_stage: bad arguments");
+  SEGMIF_REQUIRE(samples_dev && samples_host && table_arena && label_arena && hist_ws && stats && n > 0 && crop > 0, "dp_label_stage: bad arguments");
   SEGMIF_REQUIRE(ignore_index >= 0 && ignore_index <= 255, "dp_label_stage: ignore_index=%d must fit the uint8 label", ignore_index);
   for (int i = 0; i < n; ++i) {
     const segmif_dp_sample& s = samples_host[i];
@@ -418,9 +498,15 @@ extern "C" int segmif_dp_label_stage(const segmif_dp_sample* samples_dev, const 
   cudaStream_t st = as_stream(stream);
   const int mo = max_of(samples_host, n, [](const segmif_dp_sample& s) { return s.resized ? std::max(s.nh, s.nw) : 0; });
   if (mo > 0) resize_tables_kernel<<<dim3(ceil_div(mo, 128), 2, n), 128, 0, st>>>(samples_dev, table_arena);
-  const int mp = max_of(samples_host, n, [](const segmif_dp_sample& s) { return (int)std::min<int64_t>(ceil_div((int64_t)s.PH * s.PW, (int64_t)256 * 4), 148 * 2); });
-  label_pad_kernel<<<dim3(mp, 1, n), 256, 0, st>>>(samples_dev, table_arena, label_arena, ignore_index);
-  window_stats_kernel<<<dim3(10, n), 256, 0, st>>>(samples_dev, label_arena, crop, ignore_index, stats);
+  const int mph = max_of(samples_host, n, [](const segmif_dp_sample& s) { return (int)s.PH; });
+  const int mpw = max_of(samples_host, n, [](const segmif_dp_sample& s) { return (int)s.PW; });
+  label_pad_kernel<<<dim3(ceil_div(pitch16(mpw) / 4, 128), mph, n), 128, 0, st>>>(samples_dev, table_arena, label_arena, ignore_index);
+  {
+    cudaError_t e = cudaMemsetAsync(hist_ws, 0, (size_t)n * 10 * 256 * sizeof(int32_t), st);
+    if (e != cudaSuccess) { set_error("dp_label_stage: cudaMemsetAsync failed: %s", cudaGetErrorString(e)); return SEGMIF_ERR_CUDA; }
+  }
+  window_hist_kernel<<<dim3(10, kHistSlices, n), 256, 0, st>>>(samples_dev, label_arena, crop, reinterpret_cast<unsigned int*>(hist_ws));
+  window_stats_kernel<<<dim3(10, n), 256, 0, st>>>(reinterpret_cast<const unsigned int*>(hist_ws), ignore_index, stats);
   return check_launch("segmif_dp_label_stage");
 }
 
@@ -446,8 +532,8 @@ extern "C" int segmif_dp_image_stage(const segmif_dp_sample* samples_dev, const 
   }
   cudaStream_t st = as_stream(stream);
   if (rows > 0) {
-    resize_h_kernel<<<dim3(ceil_div(roi_w, 128), rows, n), 128, 0, st>>>(samples_dev, table_arena, tmp_arena);
-    resize_v_kernel<<<dim3(ceil_div(roi_w, 128), roi_h, n), 128, 0, st>>>(samples_dev, table_arena, tmp_arena, resized_arena);
+    resize_h_kernel<<<dim3(ceil_div(pitch16(roi_w) / 4, 128), rows, n), 128, 0, st>>>(samples_dev, table_arena, tmp_arena);
+    resize_v_kernel<<<dim3(ceil_div(pitch16(roi_w) / 4, 128), roi_h, n), 128, 0, st>>>(samples_dev, table_arena, tmp_arena, resized_arena);
   }
   finish_kernel<<<dim3(ceil_div(crop * crop, 256), 1, n), 256, 0, st>>>(samples_dev, resized_arena, label_arena, crop, mean_rgb[0], mean_rgb[1],
                                                                      mean_rgb[2], out_ir, out_vis, out_mask, out_label, out_label_i64);

@@ -91,6 +91,10 @@ def _ksize(in_size, out_size):
     return int(math.ceil(max(in_size / out_size, 1.0))) * 2 + 1          # Pillow precompute_coeffs
 
 
+def _p16(w):
+    return (w + 15) & ~15          # row pitch of the uint8 intermediates (datapath.cu pitch16)
+
+
 def _src_rows(in_size, out_size, y0, y1):
     """Source rows [lo, hi) that output rows [y0, y1) of the bilinear pass read (same double arithmetic as the kernel)."""
     scale = in_size / out_size
@@ -150,12 +154,11 @@ class DeviceTransforms:
         s.PH, s.PW = max(c, s.nh), max(c, s.nw)                                       # :202-203
         s.pad_h = int(rng.np.randint(s.PH - s.nh + 1))                                # :211-212
         s.pad_w = int(rng.np.randint(s.PW - s.nw + 1))
-        states = []
+        state = rng.py.getstate()                                                     # rewound in _decide
         for i in range(10):                                                           # :223-228
             s.cand_hs[i] = rng.py.randrange(0, s.PH - c + 1, 1)
             s.cand_ws[i] = rng.py.randrange(0, s.PW - c + 1, 1)
-            states.append(rng.py.getstate() if i < 9 else None)
-        return states
+        return state
 
     def _decide(self, s, stats, states, rng):
         """:229-233: the first candidate holding a non-ignored class whose largest class covers < 75 % of the non-ignored
@@ -166,10 +169,13 @@ class DeviceTransforms:
             if n_val > 0 and 4 * mx < 3 * sm:
                 pick = i
                 break
-        if pick < 9:
-            rng.py.setstate(states[pick])
-        s.hs, s.ws = s.cand_hs[pick], s.cand_ws[pick]
         c = self.crop_size
+        if pick < 9:                               # leave `random` where the reference would: after pick + 1 candidate draws
+            rng.py.setstate(states)
+            for _ in range(pick + 1):
+                rng.py.randrange(0, s.PH - c + 1, 1)
+                rng.py.randrange(0, s.PW - c + 1, 1)
+        s.hs, s.ws = s.cand_hs[pick], s.cand_ws[pick]
         if s.resized:
             ys0, ys1 = max(s.hs, s.pad_h) - s.pad_h, min(s.hs + c, s.pad_h + s.nh) - s.pad_h
             xs0, xs1 = max(s.ws, s.pad_w) - s.pad_w, min(s.ws + c, s.pad_w + s.nw) - s.pad_w
@@ -202,6 +208,7 @@ class DeviceTransforms:
         host_t = torch.frombuffer(host, dtype=torch.uint8)
         dev_t = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         stats = torch.empty((n, 10, 3), dtype=torch.int32, device=dev)
+        hist_ws = torch.empty((n, 10, 256), dtype=torch.int32, device=dev)
         # label stage: arenas grow with the draws, so in shared-rng mode they are sized per sample
         tab_parts, lab_parts = [], []
         groups = [[k] for k in range(n)] if shared else [list(range(n))]
@@ -214,7 +221,7 @@ class DeviceTransforms:
                 s.tab_off, s.lab_off = tab_elems, lab_bytes
                 if s.resized:
                     tab_elems += 3 * s.nw + s.nw * s.ks_x + 3 * s.nh + s.nh * s.ks_y
-                lab_bytes += s.PH * s.PW
+                lab_bytes += s.PH * _p16(s.PW)
             tab = torch.empty(max(tab_elems, 1), dtype=torch.int32, device=dev)
             lab = torch.empty(lab_bytes, dtype=torch.uint8, device=dev)
             tab_parts.append(tab)
@@ -223,7 +230,7 @@ class DeviceTransforms:
             off = g0 * ctypes.sizeof(_lib.DpSample)
             dev_t[off:off + gn * ctypes.sizeof(_lib.DpSample)].copy_(host_t[off:off + gn * ctypes.sizeof(_lib.DpSample)], non_blocking=False)
             _lib.call("segmif_dp_label_stage", dev_t.data_ptr() + off, ctypes.addressof(host) + off, gn, c, self.ignore_index,
-                      tab.data_ptr(), lab.data_ptr(), stats[g0:g0 + gn].data_ptr(), stream)
+                      tab.data_ptr(), lab.data_ptr(), hist_ws[g0:g0 + gn].data_ptr(), stats[g0:g0 + gn].data_ptr(), stream)
             st = stats[g0:g0 + gn].cpu().numpy()                       # the one device->host read of the stage
             for j, k in enumerate(group):
                 self._decide(host[k], st[j], states[k], rngs[k])
@@ -240,8 +247,8 @@ class DeviceTransforms:
             s = host[k]
             if s.resized:
                 s.tmp_off, s.rs_off = tmp_bytes, rs_bytes
-                tmp_bytes += 5 * (s.src_y1 - s.src_y0) * (s.roi_x1 - s.roi_x0)
-                rs_bytes += 5 * (s.roi_y1 - s.roi_y0) * (s.roi_x1 - s.roi_x0)
+                tmp_bytes += 5 * (s.src_y1 - s.src_y0) * _p16(s.roi_x1 - s.roi_x0)
+                rs_bytes += 5 * (s.roi_y1 - s.roi_y0) * _p16(s.roi_x1 - s.roi_x0)
         tmp = torch.empty(max(tmp_bytes, 1), dtype=torch.uint8, device=dev)
         rs = torch.empty(max(rs_bytes, 1), dtype=torch.uint8, device=dev)
         dev_t.copy_(host_t, non_blocking=False)

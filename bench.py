@@ -426,6 +426,13 @@ def secondary_blocks(a, dev, world, rank, pipe, devin):
     except Exception as e:  # noqa: BLE001
         out["cfg1_single_pair_256x256"] = {"error": repr(e)[:300]}
     torch.cuda.empty_cache()
+    try:                                                           # device data path, dataset defaults
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import datapath_bench
+        out["datapath_480x640_crop512_b32"] = datapath_bench.measure(batch=32, iters=10, warm=2, cpu_samples=4)
+    except Exception as e:  # noqa: BLE001
+        out["datapath_480x640_crop512_b32"] = {"error": repr(e)[:300]}
+    torch.cuda.empty_cache()
     return out
 
 

@@ -336,6 +336,14 @@ int segmif_prelu_plane_bwd(const float* out, const float* dout, int64_t n, const
                            int coffdz, float* dbias, float* dalpha, segmif_stream_t stream);
 /* out[c] += sum_p x[p][coff + c] (bias gradients); out = a + b on bf16 slices (DRDB residual, :156). */
 int segmif_colsum(const void* x, int ld, int coff, int64_t rows, int C, float* out, segmif_stream_t stream);
+/* Linear layer backward, parameter side (nn.Linear inside core/mix_transformer.py, core/segformer_head.py, core/model_fusion.py):
+ * grad[co*s_co + ci*s_ci] += sum_t dy[t][co] x[t][ci] and, when dbias != NULL, dbias[co] += sum_t dy[t][co], from one pass over
+ * dy and x on tcgen05 (both operands MN-major).  workspace: nchunk * Cout * Cin floats, nchunk = segmif_wgrad_lin_chunks(...).
+ * Only co < co_take, ci < ci_take are written (padded operands); dbias always receives all Cout sums.                        */
+int segmif_wgrad_lin_chunks(int64_t P, int Cin, int Cout);
+int segmif_wgrad_lin(const void* dy, int ldy, int coffy, const void* x, int ldx, int coffx, int64_t P, int Cin, int Cout,
+                     float* workspace, int nchunk, float* grad, int64_t s_co, int64_t s_ci, int co_take, int ci_take,
+                     float* dbias, segmif_stream_t stream);
 int segmif_add_bf16(const void* a, int lda, int coffa, const void* b, int ldb, int coffb, void* out, int ldo, int coffo,
                     int64_t rows, int C, segmif_stream_t stream);
 

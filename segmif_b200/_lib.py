@@ -145,6 +145,8 @@ SIGNATURES = {
     "segmif_act_bwd": [P, c_int, c_int, P, c_int, c_int, P, c_int, c_int, c_int64, c_int, c_int, P, P, P, P],
     "segmif_prelu_plane_bwd": [P, P, c_int64, P, P, c_int, c_int, P, P, P],
     "segmif_colsum": [P, c_int, c_int, c_int64, c_int, P, P],
+    "segmif_wgrad_lin_chunks": [c_int64, c_int, c_int],
+    "segmif_wgrad_lin": [P, c_int, c_int, P, c_int, c_int, c_int64, c_int, c_int, P, c_int, P, c_int64, c_int64, c_int, c_int, P, P],
     "segmif_add_bf16": [P, c_int, c_int, P, c_int, c_int, P, c_int, c_int, c_int64, c_int, P],
     "segmif_layernorm_bwd": [P, c_int, P, c_int, c_int, c_int, P, c_float, P, c_int, c_int, c_int, c_int64, c_int, P, P, P, c_int, P],
     "segmif_wgrad_workspace_bytes": [c_int, c_int, c_int, c_int],

@@ -139,8 +139,7 @@ def _drdb_backward(m, buf, r, dout, ld_do, coff_do, g, prefix, B, H, W):
     buf2 = buf.view(N, G)
     dz = torch.empty((N, 64), dtype=torch.bfloat16, device=dev)
     ops.act_bwd(r, 64, 0, dout, ld_do, coff_do, dz, 64, 0, N, 64, ACT_RELU, dbias=g[prefix + "conv.bias"])
-    ops.wgrad(dz, 64, 0, buf2, G, 0, B=B, H=H, W=W, Cin=G, Cout=64, taps=1, dil=1, grad=g[prefix + "conv.weight"],
-              s_co=G, s_tap=1, s_ci=1)
+    ops.wgrad_lin(dz, 64, 0, buf2, G, 0, P=N, Cin=G, Cout=64, grad=g[prefix + "conv.weight"], s_co=G)
     dbuf = torch.empty((N, G), dtype=torch.bfloat16, device=dev)
     wt = pk["wt1x1"]                                                                   # [224, 1, 64]
     ops.linear_tc(dz, wt[:64], None, residual=dout, ld_res=ld_do, res_coff=coff_do, out=dbuf, ld_dst=G, dst_coff=0)
@@ -172,9 +171,8 @@ def _ffm_backward(net, pk, bp, x1, x2, s3, fw, do1, ld1, coff1, do2, ld2, coff2,
     dP = ops.ffm_bwd_apply(x1, 64, 0, x2, 64, 0, s3, 64, 0, dr[0], dr[1], bp["wfull"], bp["bfull"], mats, B, HW)
     outs = []
     for i, (dp, x, res) in enumerate(((dP[0], x1, dr[0]), (dP[1], x2, dr[1]), (dP[2], s3, None)), 1):
-        ops.wgrad(dp, 128, 0, x, 64, 0, B=1, H=1, W=1, P=N, Cin=64, Cout=128, taps=1, dil=1,
-                  grad=g[f"{cp}channel_proj{i}.weight"], s_co=64, s_tap=1, s_ci=1)
-        ops.colsum(dp, 128, 0, N, 128, g[f"{cp}channel_proj{i}.bias"])
+        ops.wgrad_lin(dp, 128, 0, x, 64, 0, P=N, Cin=64, Cout=128, grad=g[f"{cp}channel_proj{i}.weight"], s_co=64,
+                      dbias=g[f"{cp}channel_proj{i}.bias"])
         outs.append(ops.linear_tc(dp, bp["wt"][i - 1], None, residual=res))
     return outs
 
@@ -217,16 +215,12 @@ def train_backward(net, sv, dfused):
     x1, x2, x3, x4 = sv["x"]
     # second application of ffm (inputs x3, x4, conv4(out2))
     dx3, dx4, ds3b = _ffm_backward(net, pk, bp, x3, x4, sv["s3"][1], sv["ffm"][1], dcat, 128, 0, dcat, 128, 64, g, B, HW)
-    ops.wgrad(ds3b, 64, 0, sv["seg_in"][1], 128, 0, B=1, H=1, W=1, P=N, Cin=128, Cout=64, taps=1, dil=1,
-              grad=g["conv4.weight"], s_co=128, s_tap=1, s_ci=1)
-    ops.colsum(ds3b, 64, 0, N, 64, g["conv4.bias"])
+    ops.wgrad_lin(ds3b, 64, 0, sv["seg_in"][1], 128, 0, P=N, Cin=128, Cout=64, grad=g["conv4.weight"], s_co=128, dbias=g["conv4.bias"])
     db3 = _drdb_backward(net.DRDB3, sv["bufs"][2], sv["r"][2], dx3, 64, 0, g, "DRDB3.", B, H, W)
     db4 = _drdb_backward(net.DRDB4, sv["bufs"][3], sv["r"][3], dx4, 64, 0, g, "DRDB4.", B, H, W)
     # first application of ffm (inputs x1, x2, conv3(out1)); its outputs were the inputs of DRDB3 / DRDB4
     dx1, dx2, ds3a = _ffm_backward(net, pk, bp, x1, x2, sv["s3"][0], sv["ffm"][0], db3, G, 0, db4, G, 0, g, B, HW)
-    ops.wgrad(ds3a, 64, 0, sv["seg_in"][0], 64, 0, B=1, H=1, W=1, P=N, Cin=64, Cout=64, taps=1, dil=1,
-              grad=g["conv3.weight"], s_co=64, s_tap=1, s_ci=1)
-    ops.colsum(ds3a, 64, 0, N, 64, g["conv3.bias"])
+    ops.wgrad_lin(ds3a, 64, 0, sv["seg_in"][0], 64, 0, P=N, Cin=64, Cout=64, grad=g["conv3.weight"], s_co=64, dbias=g["conv3.bias"])
     del db3, db4
     db1 = _drdb_backward(net.DRDB1, sv["bufs"][0], sv["r"][0], dx1, 64, 0, g, "DRDB1.", B, H, W)
     db2 = _drdb_backward(net.DRDB2, sv["bufs"][1], sv["r"][1], dx2, 64, 0, g, "DRDB2.", B, H, W)

@@ -70,9 +70,8 @@ def _lin_bwd(dy, x, weight_param, cache, g, wname, bname, need_dx=True, residual
     """dy bf16 [M, N], x bf16 [M, K] -> weight / bias gradients accumulated; returns dx bf16 [M, K] (+ residual)."""
     M, N = dy.shape
     K = x.shape[1]
-    _wgrad(g, dy, N, 0, x, K, 0, B=1, H=1, W=1, P=M, Cin=K, Cout=N, taps=1, dil=1, grad=g[wname], s_co=K, s_tap=1, s_ci=1)
-    if bname is not None:
-        _colsum(dy, N, M, g[bname], g)
+    if not g.frozen:               # weight and bias gradient from one pass over dy and x (tcgen05, csrc/wgrad_lin_tc.cu)
+        ops.wgrad_lin(dy, N, 0, x, K, 0, P=M, Cin=K, Cout=N, grad=g[wname], s_co=K, s_ci=1, dbias=g[bname] if bname is not None else None)
     if not need_dx:
         return None
     return _dgrad(dy, cache.linear(weight_param), lambda: _t_pack(cache, weight_param, "lin_t"), K, residual)
@@ -265,9 +264,9 @@ def _block_backward(blk, sv, dx, B, N, g, pre):
                           dgamma=g[pre + "attn.norm.weight"], dbeta=g[pre + "attn.norm.bias"])
         dred16 = ops.cast(dred, BF16)
         K = C * r * r
-        _wgrad(g, dred16, C, 0, sv["P_sr"], K, 0, B=1, H=1, W=1, P=Mk, Cin=K, Cout=C, taps=1, dil=1, grad=g[pre + "attn.sr.weight"],
-                  s_co=K, s_tap=1, s_ci=1)
-        _colsum(dred16, C, Mk, g[pre + "attn.sr.bias"], g)
+        if not g.frozen:
+            ops.wgrad_lin(dred16, C, 0, sv["P_sr"], K, 0, P=Mk, Cin=K, Cout=C, grad=g[pre + "attn.sr.weight"], s_co=K,
+                          dbias=g[pre + "attn.sr.bias"])
         dP = _dgrad(dred16, _flat_pack(at._packs, at.sr.weight, K, "sr_flat"), lambda: _flat_t_pack(at._packs, at.sr.weight, K, "sr_flat_t"), K)
         extra = _patches_to_map(dP, B, sv["Hk"], sv["Wk"], C, r, H, W)
         extra = extra if extra.is_contiguous() else extra.contiguous()
@@ -310,9 +309,9 @@ def encoder_backward(enc, tape, douts, g, prefix, want_input_grad):
                           dgamma=g[pp + "norm.weight"], dbeta=g[pp + "norm.bias"])
         dy16 = ops.cast(dy, BF16)
         Kp, k, Cin = st["Kp"], st["k"], st["Cin"]
-        _wgrad(g, dy16, C, 0, st["P"], Kp, 0, B=1, H=1, W=1, P=M, Cin=Kp, Cout=C, taps=1, dil=1, grad=g[pp + "proj.weight"],
-                  s_co=Cin * k * k, s_tap=1, s_ci=1, ci_take=Cin * k * k)
-        _colsum(dy16, C, M, g[pp + "proj.bias"], g)
+        if not g.frozen:
+            ops.wgrad_lin(dy16, C, 0, st["P"], Kp, 0, P=M, Cin=Kp, Cout=C, grad=g[pp + "proj.weight"], s_co=Cin * k * k,
+                          ci_take=Cin * k * k, dbias=g[pp + "proj.bias"])
         if s > 0 or want_input_grad:
             dP = _dgrad(dy16, _flat_pack(pe._packs, pe.proj.weight, Kp, "pe_flat"), lambda: _flat_t_pack(pe._packs, pe.proj.weight, Kp, "pe_flat_t"), Kp)
             if s > 0:
@@ -333,10 +332,11 @@ def head_backward(head, tape, dlogits, B, g, prefix):
     M = B * h1 * w1
     dl = torch.zeros((M, 32), dtype=BF16, device=dev)                       # class gradients padded to 32 channels
     dl[:, :nc] = dlogits.reshape(M, nc)
-    _wgrad(g, dl, 32, 0, tape["yd"], E, 0, B=1, H=1, W=1, P=M, Cin=E, Cout=32, taps=1, dil=1, grad=g[prefix + "linear_pred.weight"],
-              s_co=E, s_tap=1, s_ci=1, co_take=nc)
     db = torch.zeros((32,), dtype=F32, device=dev)
-    ops.colsum(dl, 32, 0, M, 32, db)
+    if g.frozen:
+        ops.colsum(dl, 32, 0, M, 32, db)
+    else:
+        ops.wgrad_lin(dl, 32, 0, tape["yd"], E, 0, P=M, Cin=E, Cout=32, grad=g[prefix + "linear_pred.weight"], s_co=E, co_take=nc, dbias=db)
     g[prefix + "linear_pred.bias"].add_(db[:nc])
 
     def wt_pred(w):
@@ -349,8 +349,8 @@ def head_backward(head, tape, dlogits, B, g, prefix):
     dz = ops.bn_train_bwd(tape["z"], tape["y"], dy, tape["stats"], bn.weight.detach(), g[prefix + "linear_fuse.bn.weight"],
                           g[prefix + "linear_fuse.bn.bias"], eval_mode=not tape["train_bn"])
     cat2 = tape["cat"].view(M, 4 * E)
-    _wgrad(g, dz, E, 0, cat2, 4 * E, 0, B=1, H=1, W=1, P=M, Cin=4 * E, Cout=E, taps=1, dil=1, grad=g[prefix + "linear_fuse.conv.weight"],
-              s_co=4 * E, s_tap=1, s_ci=1)
+    if not g.frozen:
+        ops.wgrad_lin(dz, E, 0, cat2, 4 * E, 0, P=M, Cin=4 * E, Cout=E, grad=g[prefix + "linear_fuse.conv.weight"], s_co=4 * E)
     dcat = _dgrad(dz, head._packs.conv(conv.weight), lambda: _t_pack(head._packs, conv.weight, "fuse_t"), 4 * E)   # [M, 4E]
     t1, t2, t3, t4 = tape["toks"]
     douts = [None] * 4

@@ -153,6 +153,10 @@ int sr_attention_fa_tc(const void* q, int ldq, const void* k, const void* v, int
                        int Nk, float scale, float* lse, cudaStream_t st);
 
 // wgrad_tc.cu: 3x3 weight gradients on tcgen05 (MN-major operands, accumulators resident in TMEM)
+bool wgrad_lin_tc_ok(int64_t P, int Cin, int Cout, int ldy, int ldx);
+void wgrad_lin_tc_plan(int64_t P, int Cin, int Cout, int* nchunk, int64_t* tok_per_chunk, int* bn);
+int wgrad_lin_tc(const void* dy, int ldy, const void* x, int ldx, int64_t P, int Cin, int Cout, float* partials, int nchunk,
+                 int64_t tok_per_chunk, int bn, float* dbias, cudaStream_t st);
 bool wgrad_tc_ok(int B, int H, int W, int Cin, int Cout, int taps, int dil, int ldy, int ldx);
 int wgrad_tc_chunks(int B, int H, int W, int Cin, int Cout);
 int wgrad_tc(const void* dy, int ldy, const void* x, int ldx, int B, int H, int W, int Cin, int Cout, int dil, float* partials,

@@ -656,6 +656,52 @@ extern "C" int segmif_wgrad(const void* dy, int ldy, int coffy, const void* x, i
   return check_launch("segmif_wgrad(reduce)");
 }
 
+/* Linear layer: weight gradient (+= into grad[co*s_co + ci*s_ci]) and, when dbias is given, the bias gradient (+= column sums
+ * of dY) from ONE pass over dY and X on tcgen05 (wgrad_lin_tc.cu).  nchunk / workspace as reported by
+ * segmif_wgrad_lin_chunks.  SEGMIF_WGRAD_LIN_TC=0 (or shapes TMA cannot address) selects the mma.sync kernel + colsum. */
+static bool wgrad_lin_use_tc() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SEGMIF_WGRAD_LIN_TC"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
+extern "C" int segmif_wgrad_lin_chunks(int64_t P, int Cin, int Cout) {
+  if (wgrad_lin_use_tc() && wgrad_lin_tc_ok(P, Cin, Cout, 8, 8)) {
+    int nchunk, bn;
+    int64_t per;
+    wgrad_lin_tc_plan(P, Cin, Cout, &nchunk, &per, &bn);
+    return nchunk;
+  }
+  return segmif_wgrad_chunks(1, (int)((P + 15) / 16), 16, P, Cin, Cout, 1, 1);
+}
+
+extern "C" int segmif_wgrad_lin(const void* dy, int ldy, int coffy, const void* x, int ldx, int coffx, int64_t P, int Cin, int Cout,
+                                float* workspace, int nchunk, float* grad, int64_t s_co, int64_t s_ci, int co_take, int ci_take,
+                                float* dbias, segmif_stream_t stream) {
+  SEGMIF_REQUIRE(dy && x && workspace && grad && P > 0 && nchunk > 0, "wgrad_lin: bad arguments");
+  SEGMIF_REQUIRE(co_take > 0 && co_take <= Cout && ci_take > 0 && ci_take <= Cin, "wgrad_lin: co_take / ci_take out of range");
+  SEGMIF_REQUIRE(ldy % 8 == 0 && ldx % 8 == 0 && coffy % 8 == 0 && coffx % 8 == 0, "wgrad_lin: pitches/offsets must be multiples of 8");
+  cudaStream_t st = as_stream(stream);
+  if (!(wgrad_lin_use_tc() && wgrad_lin_tc_ok(P, Cin, Cout, ldy, ldx))) {
+    int rc = segmif_wgrad(dy, ldy, coffy, x, ldx, coffx, 1, (int)((P + 15) / 16), 16, P, Cin, Cout, 1, 1, workspace, nchunk, grad, s_co,
+                          1, s_ci, co_take, ci_take, stream);
+    if (rc || !dbias) return rc;
+    return segmif_colsum(dy, ldy, coffy, P, Cout, dbias, stream);
+  }
+  int want, bn;
+  int64_t per;
+  wgrad_lin_tc_plan(P, Cin, Cout, &want, &per, &bn);
+  SEGMIF_REQUIRE(nchunk == want, "wgrad_lin: nchunk=%d, segmif_wgrad_lin_chunks says %d", nchunk, want);
+  int rc = wgrad_lin_tc((const bf16*)dy + coffy, ldy, (const bf16*)x + coffx, ldx, P, Cin, Cout, workspace, nchunk, per, bn, dbias, st);
+  if (rc) return rc;
+  const int64_t n = (int64_t)Cout * Cin;
+  if (nchunk >= 32)
+    wgrad_reduce_kernel<<<grid_for(n, 32), 256, 0, st>>>(workspace, nchunk, Cout, 1, Cin, grad, s_co, 1, s_ci, co_take, ci_take);
+  else
+    wgrad_reduce_flat_kernel<<<grid_for(n, 256), 256, 0, st>>>(workspace, nchunk, Cout, 1, Cin, grad, s_co, 1, s_ci, co_take, ci_take);
+  return check_launch("segmif_wgrad_lin(reduce)");
+}
+
 extern "C" int segmif_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                                  float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
                                  segmif_stream_t stream) {

@@ -655,6 +655,17 @@ def wgrad(dy, ldy, coffy, x, ldx, coffx, *, B, H, W, Cin, Cout, taps, dil, grad,
     return grad
 
 
+def wgrad_lin(dy, ldy, coffy, x, ldx, coffx, *, P, Cin, Cout, grad, s_co, s_ci=1, dbias=None, co_take=None, ci_take=None):
+    """Linear layer: grad[co*s_co + ci*s_ci] += sum_t dy[t][co] x[t][ci] and (dbias given) dbias[co] += sum_t dy[t][co] in
+    one pass on tcgen05 (csrc/wgrad_lin_tc.cu)."""
+    st = _prep(dy, x, grad) if dbias is None else _prep(dy, x, grad, dbias)
+    nchunk = int(_lib.load().segmif_wgrad_lin_chunks(P, Cin, Cout))
+    ws = torch.empty((nchunk * Cout * Cin,), dtype=torch.float32, device=dy.device)
+    _lib.call("segmif_wgrad_lin", _ptr(dy), ldy, coffy, _ptr(x), ldx, coffx, P, Cin, Cout, _ptr(ws), nchunk, _ptr(grad), s_co, s_ci,
+              Cout if co_take is None else co_take, Cin if ci_take is None else ci_take, _ptr(dbias) if dbias is not None else None, st)
+    return grad
+
+
 def ffm_train_fwd(x1, ld1, coff1, x2, ld2, coff2, x3, ld3, packs, out1, ldo1, coffo1, out2, ldo2, coffo2, B, HW):
     """Training forward of the HIA module (C3 = 64): returns the tensors the backward needs."""
     st = _prep(x1, x2, x3, out1, out2)

@@ -904,3 +904,41 @@ def seg_training_after_eval():
         res.append(result(f"seg_eval_train_grad_{k.split('decoder.')[1]}", _floored_err(got[k].grad, leaves[k].grad, 1e-2 * gmax), 0.1))
     res.append(result("seg_eval_running_stats_untouched", float((net.denoise_net.decoder.linear_fuse.bn.running_mean - rm0).abs().max()), 0.0))
     return res
+
+
+@check
+def wgrad_lin_tcgen05():
+    """Linear weight + bias gradient in one pass (csrc/wgrad_lin_tc.cu: both operands MN-major on tcgen05, ones-MMA for the
+    column sums) against an fp64 contraction of the SAME bf16 operands.  fp32 accumulation over P tokens: <= 2e-5 of max |dW|
+    (measured ~1e-6); every MiT-B2 layer shape class, token counts that are not multiples of the 64-token stage, padded
+    operands (co_take / ci_take), channel slices of wider buffers, accumulation into a non-zero gradient."""
+    res = []
+    cases = [  # name, P, Cin, Cout, ldx, coffx, ldy, coffy, co_take, ci_take, bias
+        ("s1_q_64x64", 5000, 64, 64, 64, 0, 64, 0, None, None, True),
+        ("s1_fc1_64x256", 4100, 64, 256, 64, 0, 256, 0, None, None, True),
+        ("s1_fc2_256x64", 4100, 256, 64, 256, 0, 64, 0, None, None, True),
+        ("s3_fc1_320x1280", 1234, 320, 1280, 320, 0, 1280, 0, None, None, True),
+        ("s4_fc2_2048x512", 300, 2048, 512, 2048, 0, 512, 0, None, None, True),
+        ("pred_pad32_take9", 3001, 256, 32, 256, 0, 32, 0, 9, None, True),
+        ("patch_embed_kpad", 2000, 152, 64, 152, 0, 64, 0, None, 147, True),
+        ("drdb_1x1_slice", 2500, 224, 64, 224, 0, 96, 32, None, None, False),
+        ("x_slice_of_wider", 1500, 64, 128, 192, 64, 128, 0, None, None, True),
+        ("tiny_P_63", 63, 128, 320, 128, 0, 320, 0, None, None, True),
+        ("single_chunk_P_64", 64, 512, 512, 512, 0, 512, 0, None, None, True),
+    ]
+    for name, P, Cin, Cout, ldx, coffx, ldy, coffy, co_take, ci_take, bias in cases:
+        x = rnd(P, ldx, seed=11).to(torch.bfloat16)
+        dy = (rnd(P, ldy, seed=12) * 0.05 + 0.01).to(torch.bfloat16)
+        ct, it = co_take or Cout, ci_take or Cin
+        g0 = rnd(ct, it, seed=13, bf16=False)
+        b0 = rnd(Cout, seed=14, bf16=False)
+        xs, ys = x[:, coffx:coffx + Cin].double(), dy[:, coffy:coffy + Cout].double()
+        ref_w = g0.double() + (ys.t() @ xs)[:ct, :it]
+        ref_b = b0.double() + ys.sum(0)
+        grad, dbias = g0.clone().to(DEV), b0.clone().to(DEV)
+        ops.wgrad_lin(dy.to(DEV), ldy, coffy, x.to(DEV), ldx, coffx, P=P, Cin=Cin, Cout=Cout, grad=grad, s_co=it, co_take=co_take,
+                      ci_take=ci_take, dbias=dbias if bias else None)
+        res.append(result(f"wgrad_lin_{name}", rel_err(grad, ref_w), 2e-5))
+        if bias:
+            res.append(result(f"wgrad_lin_{name}_bias", rel_err(dbias, ref_b), 2e-5))
+    return res

@@ -55,6 +55,44 @@ class _Grads(dict):
     frozen = False
 
 
+class SideWgrad:
+    """Weight-gradient launches are off the critical path of the reverse pass (nothing reads them before the all-reduce), and
+    most of them are small (19-114 blocks): with this object installed in WGRAD_SIDE they are queued on a second stream -- a
+    parallel branch of the step's CUDA graph -- and fill the SMs the dgrad chain leaves idle.  The operands are kept referenced
+    until `join`, so the caching allocator cannot hand their memory to a later kernel of the main stream."""
+
+    def __init__(self, device=None):
+        self.stream = torch.cuda.Stream(device=device)
+        self.keep, self.used = [], False
+
+    def run(self, fn, *operands):
+        self.stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.stream):
+            fn()
+        self.keep.append(operands)
+        self.used = True
+
+    def join(self):
+        if self.used:
+            torch.cuda.current_stream().wait_stream(self.stream)
+        self.keep.clear()
+        self.used = False
+
+
+WGRAD_SIDE = None           # set by ddp.SegTrainer around loss.backward()
+
+
+def _wgrad_lin(g, dy, x, **kw):
+    """Parameter-side backward of a linear layer (ops.wgrad_lin) unless the parameters are frozen."""
+    if g.frozen:
+        return
+    fn = lambda: ops.wgrad_lin(dy, kw.pop("ldy"), 0, x, kw.pop("ldx"), 0, **kw)
+    if WGRAD_SIDE is not None:
+        WGRAD_SIDE.run(fn, dy, x)
+    else:
+        fn()
+
+
 def _wgrad(g, *args, **kw):
     if not g.frozen:
         ops.wgrad(*args, **kw)
@@ -70,8 +108,8 @@ def _lin_bwd(dy, x, weight_param, cache, g, wname, bname, need_dx=True, residual
     """dy bf16 [M, N], x bf16 [M, K] -> weight / bias gradients accumulated; returns dx bf16 [M, K] (+ residual)."""
     M, N = dy.shape
     K = x.shape[1]
-    if not g.frozen:               # weight and bias gradient from one pass over dy and x (tcgen05, csrc/wgrad_lin_tc.cu)
-        ops.wgrad_lin(dy, N, 0, x, K, 0, P=M, Cin=K, Cout=N, grad=g[wname], s_co=K, s_ci=1, dbias=g[bname] if bname is not None else None)
+    # weight and bias gradient from one pass over dy and x (tcgen05, csrc/wgrad_lin_tc.cu)
+    _wgrad_lin(g, dy, x, ldy=N, ldx=K, P=M, Cin=K, Cout=N, grad=g[wname], s_co=K, dbias=g[bname] if bname is not None else None)
     if not need_dx:
         return None
     return _dgrad(dy, cache.linear(weight_param), lambda: _t_pack(cache, weight_param, "lin_t"), K, residual)
@@ -264,9 +302,8 @@ def _block_backward(blk, sv, dx, B, N, g, pre):
                           dgamma=g[pre + "attn.norm.weight"], dbeta=g[pre + "attn.norm.bias"])
         dred16 = ops.cast(dred, BF16)
         K = C * r * r
-        if not g.frozen:
-            ops.wgrad_lin(dred16, C, 0, sv["P_sr"], K, 0, P=Mk, Cin=K, Cout=C, grad=g[pre + "attn.sr.weight"], s_co=K,
-                          dbias=g[pre + "attn.sr.bias"])
+        _wgrad_lin(g, dred16, sv["P_sr"], ldy=C, ldx=K, P=Mk, Cin=K, Cout=C, grad=g[pre + "attn.sr.weight"], s_co=K,
+                   dbias=g[pre + "attn.sr.bias"])
         dP = _dgrad(dred16, _flat_pack(at._packs, at.sr.weight, K, "sr_flat"), lambda: _flat_t_pack(at._packs, at.sr.weight, K, "sr_flat_t"), K)
         extra = _patches_to_map(dP, B, sv["Hk"], sv["Wk"], C, r, H, W)
         extra = extra if extra.is_contiguous() else extra.contiguous()
@@ -309,9 +346,8 @@ def encoder_backward(enc, tape, douts, g, prefix, want_input_grad):
                           dgamma=g[pp + "norm.weight"], dbeta=g[pp + "norm.bias"])
         dy16 = ops.cast(dy, BF16)
         Kp, k, Cin = st["Kp"], st["k"], st["Cin"]
-        if not g.frozen:
-            ops.wgrad_lin(dy16, C, 0, st["P"], Kp, 0, P=M, Cin=Kp, Cout=C, grad=g[pp + "proj.weight"], s_co=Cin * k * k,
-                          ci_take=Cin * k * k, dbias=g[pp + "proj.bias"])
+        _wgrad_lin(g, dy16, st["P"], ldy=C, ldx=Kp, P=M, Cin=Kp, Cout=C, grad=g[pp + "proj.weight"], s_co=Cin * k * k,
+                   ci_take=Cin * k * k, dbias=g[pp + "proj.bias"])
         if s > 0 or want_input_grad:
             dP = _dgrad(dy16, _flat_pack(pe._packs, pe.proj.weight, Kp, "pe_flat"), lambda: _flat_t_pack(pe._packs, pe.proj.weight, Kp, "pe_flat_t"), Kp)
             if s > 0:
@@ -349,8 +385,7 @@ def head_backward(head, tape, dlogits, B, g, prefix):
     dz = ops.bn_train_bwd(tape["z"], tape["y"], dy, tape["stats"], bn.weight.detach(), g[prefix + "linear_fuse.bn.weight"],
                           g[prefix + "linear_fuse.bn.bias"], eval_mode=not tape["train_bn"])
     cat2 = tape["cat"].view(M, 4 * E)
-    if not g.frozen:
-        ops.wgrad_lin(dz, E, 0, cat2, 4 * E, 0, P=M, Cin=4 * E, Cout=E, grad=g[prefix + "linear_fuse.conv.weight"], s_co=4 * E)
+    _wgrad_lin(g, dz, cat2, ldy=E, ldx=4 * E, P=M, Cin=4 * E, Cout=E, grad=g[prefix + "linear_fuse.conv.weight"], s_co=4 * E)
     dcat = _dgrad(dz, head._packs.conv(conv.weight), lambda: _t_pack(head._packs, conv.weight, "fuse_t"), 4 * E)   # [M, 4E]
     t1, t2, t3, t4 = tape["toks"]
     douts = [None] * 4

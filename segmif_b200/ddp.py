@@ -327,6 +327,8 @@ class SegTrainer(_GraphedStep):
         self.flat = FlatParams(seg_net, used=lambda k: not k.endswith("classifier.weight"), group_of=gid,
                                early_of=early if self.overlap else None)
         self._side = None
+        # small weight-gradient kernels on a parallel branch of the step graph (core/seg_train.py SideWgrad); 0 = in line
+        self._wgrad_side = None if os.environ.get("SEGMIF_WGRAD_SIDE_STREAM", "1") == "0" else "lazy"
         self.opt = FusedPolyWarmupAdamW(self.flat, lr, weight_decay, betas, warmup_iter, max_iter, warmup_ratio, power,
                                         groups={0: dict(lr=lr, weight_decay=weight_decay), 1: dict(lr=lr, weight_decay=0.0),
                                                 2: dict(lr=lr * 10, weight_decay=weight_decay)}, iter_curr=iter_curr)
@@ -345,6 +347,8 @@ class SegTrainer(_GraphedStep):
         if self._side is None:
             self._side = torch.cuda.Stream()
         self._side.wait_stream(cur)
+        if self._wgrad_side is not None and self._wgrad_side != "lazy":
+            self._side.wait_stream(self._wgrad_side.stream)       # weight gradients of the early ranges queued on their own stream
         with torch.cuda.stream(self._side):
             self.flat.all_reduce(self.group, ranges=self.flat.early_ranges)
         self._early_pending = True
@@ -355,10 +359,16 @@ class SegTrainer(_GraphedStep):
         loss = self.net._loss(mask, labels, self.ce)
         self._early_pending = False
         seg_train.STAGE_DONE_HOOK = self._early_hook if self.overlap else None
+        if self._wgrad_side == "lazy":
+            self._wgrad_side = seg_train.SideWgrad(mask.device) if mask.is_cuda else None
+        seg_train.WGRAD_SIDE = self._wgrad_side
         try:
             loss.backward()
         finally:
             seg_train.STAGE_DONE_HOOK = None
+            seg_train.WGRAD_SIDE = None
+            if self._wgrad_side is not None:
+                self._wgrad_side.join()
         if self._early_pending:                    # join (inside the captured graph when capturing)
             torch.cuda.current_stream().wait_stream(self._side)
         return (loss.detach(),)

@@ -1,5 +1,5 @@
 # per-kernel durations of one batch of the device data path (ncu launch list; cold-cache, serialised)
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/dp_launches.csv python tools/_dp_once.py 2>&1 | tail -1
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/dp_launches.csv python tools/dp_once.py 2>&1 | tail -1
 python - <<PY
 import csv, collections
 rows = [r for r in csv.reader(open("gpurun_out/dp_launches.csv")) if len(r) > 10]

@@ -131,6 +131,19 @@ def _conv_dgrad(dy, cin_dy, wd, B, H, W, dil, out, ld_out, coff_out, accumulate)
     return out
 
 
+WGRAD_SIDE = None           # a core.seg_train.SideWgrad installed by ddp.FusionTrainer around loss.backward()
+
+
+def _side(fn, *operands):
+    """Weight-gradient launches are off the critical path of the reverse pass: with WGRAD_SIDE installed they go to a second
+    stream (a parallel branch of the step's CUDA graph) and overlap the HBM-bound activation / data-gradient kernels; their
+    operands stay referenced until the join, and no operand may be overwritten later in the pass (fresh buffers below)."""
+    if WGRAD_SIDE is not None:
+        WGRAD_SIDE.run(fn, *operands)
+    else:
+        fn()
+
+
 def _drdb_backward(m, buf, r, dout, ld_do, coff_do, g, prefix, B, H, W):
     """dout: gradient of the block output [N, .] (slice ld_do / coff_do).  Returns dbuf [N, 224] whose first 64
     channels are the gradient of the block input."""
@@ -139,17 +152,17 @@ def _drdb_backward(m, buf, r, dout, ld_do, coff_do, g, prefix, B, H, W):
     buf2 = buf.view(N, G)
     dz = torch.empty((N, 64), dtype=torch.bfloat16, device=dev)
     ops.act_bwd(r, 64, 0, dout, ld_do, coff_do, dz, 64, 0, N, 64, ACT_RELU, dbias=g[prefix + "conv.bias"])
-    ops.wgrad_lin(dz, 64, 0, buf2, G, 0, P=N, Cin=G, Cout=64, grad=g[prefix + "conv.weight"], s_co=G)
+    _side(lambda: ops.wgrad_lin(dz, 64, 0, buf2, G, 0, P=N, Cin=G, Cout=64, grad=g[prefix + "conv.weight"], s_co=G), dz, buf2)
     dbuf = torch.empty((N, G), dtype=torch.bfloat16, device=dev)
     wt = pk["wt1x1"]                                                                   # [224, 1, 64]
     ops.linear_tc(dz, wt[:64], None, residual=dout, ld_res=ld_do, res_coff=coff_do, out=dbuf, ld_dst=G, dst_coff=0)
     ops.linear_tc(dz, wt[64:], None, out=dbuf, ld_dst=G, dst_coff=64)
-    dg = torch.empty((N, 32), dtype=torch.bfloat16, device=dev)
     for j in range(5, 0, -1):
         cin = 64 + 32 * (j - 1)
+        dg = torch.empty((N, 32), dtype=torch.bfloat16, device=dev)      # fresh per layer: the weight gradient may still be reading the last one
         ops.act_bwd(buf2, G, cin, dbuf, G, cin, dg, 32, 0, N, 32, ACT_RELU, dbias=g[f"{prefix}Dcov{j}.bias"])
-        ops.wgrad(dg, 32, 0, buf2, G, 0, B=B, H=H, W=W, Cin=cin, Cout=32, taps=9, dil=2,
-                  grad=g[f"{prefix}Dcov{j}.weight"], s_co=cin * 9, s_tap=1, s_ci=9)
+        _side(lambda: ops.wgrad(dg, 32, 0, buf2, G, 0, B=B, H=H, W=W, Cin=cin, Cout=32, taps=9, dil=2,
+                                grad=g[f"{prefix}Dcov{j}.weight"], s_co=cin * 9, s_tap=1, s_ci=9), dg, buf2)
         _conv_dgrad(dg, 32, pk["wd"][j - 1], B, H, W, 2, dbuf, G, 0, accumulate=True)
     return dbuf
 
@@ -171,8 +184,8 @@ def _ffm_backward(net, pk, bp, x1, x2, s3, fw, do1, ld1, coff1, do2, ld2, coff2,
     dP = ops.ffm_bwd_apply(x1, 64, 0, x2, 64, 0, s3, 64, 0, dr[0], dr[1], bp["wfull"], bp["bfull"], mats, B, HW)
     outs = []
     for i, (dp, x, res) in enumerate(((dP[0], x1, dr[0]), (dP[1], x2, dr[1]), (dP[2], s3, None)), 1):
-        ops.wgrad_lin(dp, 128, 0, x, 64, 0, P=N, Cin=64, Cout=128, grad=g[f"{cp}channel_proj{i}.weight"], s_co=64,
-                      dbias=g[f"{cp}channel_proj{i}.bias"])
+        _side(lambda: ops.wgrad_lin(dp, 128, 0, x, 64, 0, P=N, Cin=64, Cout=128, grad=g[f"{cp}channel_proj{i}.weight"], s_co=64,
+                                    dbias=g[f"{cp}channel_proj{i}.bias"]), dp, x)
         outs.append(ops.linear_tc(dp, bp["wt"][i - 1], None, residual=res))
     return outs
 
@@ -192,21 +205,21 @@ def train_backward(net, sv, dfused):
     # conv22 (32 -> 1): the single gradient plane is padded to a 32-channel pixel-major tensor (channel 0 live)
     dz22 = torch.zeros((N, 32), dtype=torch.bfloat16, device=dev)
     ops.prelu_plane_bwd(sv["fused"], dfused, alpha, dz22, 32, 0, dbias=g["conv22.bias"], dalpha=dalpha)
-    ops.wgrad(dz22, 32, 0, sv["o21"], 32, 0, B=B, H=H, W=W, Cin=32, Cout=32, taps=9, dil=1, grad=g["conv22.weight"],
-              s_co=288, s_tap=1, s_ci=9, co_take=1)
+    _side(lambda: ops.wgrad(dz22, 32, 0, sv["o21"], 32, 0, B=B, H=H, W=W, Cin=32, Cout=32, taps=9, dil=1, grad=g["conv22.weight"],
+                            s_co=288, s_tap=1, s_ci=9, co_take=1), dz22, sv["o21"])
     wd22 = net._packs.get(net.conv22.weight, lambda w: _dgrad_pack(w, 32), "dgrad")
     do21 = torch.empty((N, 32), dtype=torch.bfloat16, device=dev)
     _conv_dgrad(dz22, 32, wd22, B, H, W, 1, do21, 32, 0, accumulate=False)
     # conv21 (64 -> 32)
     ops.act_bwd(sv["o21"], 32, 0, do21, 32, 0, do21, 32, 0, N, 32, ACT_PRELU, alpha=alpha, dbias=g["conv21.bias"], dalpha=dalpha)
-    ops.wgrad(do21, 32, 0, sv["o2"], 64, 0, B=B, H=H, W=W, Cin=64, Cout=32, taps=9, dil=1, grad=g["conv21.weight"],
-              s_co=576, s_tap=1, s_ci=9)
+    _side(lambda: ops.wgrad(do21, 32, 0, sv["o2"], 64, 0, B=B, H=H, W=W, Cin=64, Cout=32, taps=9, dil=1, grad=g["conv21.weight"],
+                            s_co=576, s_tap=1, s_ci=9), do21, sv["o2"])
     do2 = torch.empty((N, 64), dtype=torch.bfloat16, device=dev)
     _conv_dgrad(do21, 32, net._packs.get(net.conv21.weight, _dgrad_pack, "dgrad"), B, H, W, 1, do2, 64, 0, accumulate=False)
     # conv2 (128 -> 64)
     ops.act_bwd(sv["o2"], 64, 0, do2, 64, 0, do2, 64, 0, N, 64, ACT_PRELU, alpha=alpha, dbias=g["conv2.bias"], dalpha=dalpha)
-    ops.wgrad(do2, 64, 0, sv["cat"], 128, 0, B=B, H=H, W=W, Cin=128, Cout=64, taps=9, dil=1, grad=g["conv2.weight"],
-              s_co=1152, s_tap=1, s_ci=9)
+    _side(lambda: ops.wgrad(do2, 64, 0, sv["cat"], 128, 0, B=B, H=H, W=W, Cin=128, Cout=64, taps=9, dil=1, grad=g["conv2.weight"],
+                            s_co=1152, s_tap=1, s_ci=9), do2, sv["cat"])
     dcat = torch.empty((N, 128), dtype=torch.bfloat16, device=dev)
     _conv_dgrad(do2, 64, net._packs.get(net.conv2.weight, _dgrad_pack, "dgrad"), B, H, W, 1, dcat, 128, 0, accumulate=False)
 
@@ -215,12 +228,14 @@ def train_backward(net, sv, dfused):
     x1, x2, x3, x4 = sv["x"]
     # second application of ffm (inputs x3, x4, conv4(out2))
     dx3, dx4, ds3b = _ffm_backward(net, pk, bp, x3, x4, sv["s3"][1], sv["ffm"][1], dcat, 128, 0, dcat, 128, 64, g, B, HW)
-    ops.wgrad_lin(ds3b, 64, 0, sv["seg_in"][1], 128, 0, P=N, Cin=128, Cout=64, grad=g["conv4.weight"], s_co=128, dbias=g["conv4.bias"])
+    _side(lambda: ops.wgrad_lin(ds3b, 64, 0, sv["seg_in"][1], 128, 0, P=N, Cin=128, Cout=64, grad=g["conv4.weight"], s_co=128,
+                                dbias=g["conv4.bias"]), ds3b, sv["seg_in"][1])
     db3 = _drdb_backward(net.DRDB3, sv["bufs"][2], sv["r"][2], dx3, 64, 0, g, "DRDB3.", B, H, W)
     db4 = _drdb_backward(net.DRDB4, sv["bufs"][3], sv["r"][3], dx4, 64, 0, g, "DRDB4.", B, H, W)
     # first application of ffm (inputs x1, x2, conv3(out1)); its outputs were the inputs of DRDB3 / DRDB4
     dx1, dx2, ds3a = _ffm_backward(net, pk, bp, x1, x2, sv["s3"][0], sv["ffm"][0], db3, G, 0, db4, G, 0, g, B, HW)
-    ops.wgrad_lin(ds3a, 64, 0, sv["seg_in"][0], 64, 0, P=N, Cin=64, Cout=64, grad=g["conv3.weight"], s_co=64, dbias=g["conv3.bias"])
+    _side(lambda: ops.wgrad_lin(ds3a, 64, 0, sv["seg_in"][0], 64, 0, P=N, Cin=64, Cout=64, grad=g["conv3.weight"], s_co=64,
+                                dbias=g["conv3.bias"]), ds3a, sv["seg_in"][0])
     del db3, db4
     db1 = _drdb_backward(net.DRDB1, sv["bufs"][0], sv["r"][0], dx1, 64, 0, g, "DRDB1.", B, H, W)
     db2 = _drdb_backward(net.DRDB2, sv["bufs"][1], sv["r"][1], dx2, 64, 0, g, "DRDB2.", B, H, W)
@@ -230,8 +245,8 @@ def train_backward(net, sv, dfused):
         ops.act_bwd(buf.view(N, G), G, 0, db, G, 0, dz1, 64, 0, N, 64, ACT_PRELU, alpha=alpha, dbias=g[name + ".bias"], dalpha=dalpha)
         x8 = torch.zeros((B, HW, 8), dtype=torch.bfloat16, device=dev)
         ops.nchw_to_nhwc(plane, out=x8, ld_dst=8, dst_coff=0)
-        ops.wgrad(dz1, 64, 0, x8, 8, 0, B=B, H=H, W=W, Cin=8, Cout=64, taps=9, dil=1, grad=g[name + ".weight"],
-                  s_co=9, s_tap=1, s_ci=9, ci_take=1)
+        _side(lambda: ops.wgrad(dz1, 64, 0, x8, 8, 0, B=B, H=H, W=W, Cin=8, Cout=64, taps=9, dil=1, grad=g[name + ".weight"],
+                                s_co=9, s_tap=1, s_ci=9, ci_take=1), dz1, x8)
     # scatter the stacked kv / end_proj gradients to their parameters
     ca = "ffm.cross."
     g[ca + "cross_attn2.kv1.weight"] = g["_dwkv"][0]
@@ -239,6 +254,8 @@ def train_backward(net, sv, dfused):
     g[ca + "cross_attn.kv3.weight"] = g["_dwkv"][2]
     g[ca + "end_proj1.weight"] = g["_dwend"][0]
     g[ca + "end_proj2.weight"] = g["_dwend"][1]
+    if WGRAD_SIDE is not None:          # autograd accumulates the returned tensors on this stream as soon as we return
+        WGRAD_SIDE.join()
     return g
 
 

@@ -448,6 +448,8 @@ class SegNetFn(torch.autograd.Function):
         douts = head_backward(wetr.decoder, ctx.htape, dlogits.float().contiguous(), B, g, "denoise_net.decoder.")
         dimg = encoder_backward(wetr.encoder, ctx.etape, douts, g, "denoise_net.encoder.", ctx.want_x)
         ctx.etape = ctx.htape = None
+        if WGRAD_SIDE is not None and pending:      # tensors handed back to autograd are consumed on this stream right away
+            WGRAD_SIDE.join()
         grads = tuple(g[n] if (ctx.needs_input_grad[4 + i] and n not in direct) else None for i, n in enumerate(ctx.names))
         return (None, dimg if ctx.want_x else None, None, None) + grads
 

@@ -32,6 +32,8 @@ def main():
     ap.add_argument("--loss", default="loss3", choices=["loss3", "grad3", "grad2"])
     ap.add_argument("--mode", default="fusion", choices=["fusion", "fusion_ce", "seg"])
     ap.add_argument("--graph", type=int, default=1, help="1: forward+backward replayed from one CUDA graph; 0: eager launches")
+    ap.add_argument("--profile", type=int, default=0, help="N > 0: after the timed steps, run N more under torch.profiler (CUPTI) and "
+                    "write the per-kernel totals of those steps to gpurun_out/train_profile_<mode>.json")
     a = ap.parse_args()
     from segmif_b200 import _lib, synth
     from segmif_b200.core.loss import Fusionloss3, Fusionloss_grad2, Fusionloss_grad3
@@ -107,6 +109,23 @@ def main():
                           "eager_launches_per_step": (_lib.launch_count - l0) / a.steps, "replicas_in_sync": in_sync,
                           "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30,
                           "loss_first_last": [float(losses[0]), float(losses[-1])]}), flush=True)
+    if a.profile and rank == 0:
+        from torch.profiler import ProfilerActivity, profile
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(a.profile):
+                step()
+            torch.cuda.synchronize()
+        rows = sorted(((e.key, e.count, getattr(e, "device_time_total", None) or getattr(e, "cuda_time_total", 0.0)) for e in prof.key_averages()),
+                      key=lambda r: -r[2])
+        tot = sum(r[2] for r in rows)
+        out = {"mode": a.mode, "steps": a.profile, "kernel_time_ms_per_step": tot / 1e3 / a.profile,
+               "kernels": [{"name": k[:110], "launches_per_step": c / a.profile, "ms_per_step": t / 1e3 / a.profile, "share": t / tot} for k, c, t in rows[:45]]}
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        json.dump(out, open(os.path.join(ROOT, "gpurun_out", f"train_profile_{a.mode}.json"), "w"), indent=1)
+        print(f"kernel time per step {out['kernel_time_ms_per_step']:.3f} ms (sum over streams)")
+        for k in out["kernels"][:32]:
+            print(f"  {k['name'][:84]:84s} n={k['launches_per_step']:6.1f} {k['ms_per_step']:7.3f} ms {100 * k['share']:5.1f}%")
     if world > 1:
         dist.destroy_process_group()
 

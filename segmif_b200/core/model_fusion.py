@@ -178,7 +178,9 @@ class DRDB(nn.Module):
     # one launch after the other), "dataflow" (the same stages plus the 1x1 as seven CONCURRENT kernels chained through L2 by
     # per-tile-row counters, csrc/drdb_dataflow.cu: bit-identical to hybrid, measured SLOWER on B200 -- 3.5 ms vs 1.6 ms per DRDB
     # at batch 8, 480x640 -- because every stage keeps its per-SM rate and the SMs are merely divided), "push" (every
-    # slab pushed, bf16 partials read-modify-written), "pull" (one N = 32 conv per layer).
+    # slab pushed, bf16 partials read-modify-written), "pair" (g-slabs read with N = 64 for two consumer layers at a time + two
+    # single-slab pulls: 12 instead of 20 slab-k-steps per tap, but 512 B/px more partial traffic -- measured 1.72 ms against
+    # 1.26 ms for the hybrid growth layers, tools/drdb_bench.py), "pull" (one N = 32 conv per layer).
     MODE = os.environ.get("SEGMIF_DRDB_MODE", "hybrid")
 
     def __init__(self, in_ch=64, growth_rate=32):
@@ -251,6 +253,48 @@ class DRDB(nn.Module):
                      Cout=g, act=ACT_RELU, out=buf.view(-1, ld), ld_dst=ld, dst_coff=c + cin, pre_add=part.view(-1, part.shape[-1]),
                      pre_coff=g * (j - 2), entry="segmif_conv3x3_tc_fwd")
 
+    def _pair_packs(self):
+        """Weights of the "pair" formulation: slab pushes with N = 64 (two consumer layers at a time) + two N = 32 pulls."""
+        convs = [getattr(self, f"Dcov{i}") for i in range(1, 6)]
+
+        def build(*ws):
+            c, g = self.in_ch, self.growth
+
+            def slab(layers, c0, c1):
+                w = torch.cat([ws[j - 1].detach().float()[:, c0:c1] for j in layers], 0)
+                w = w.permute(0, 2, 3, 1).reshape(w.shape[0], 9, c1 - c0)
+                if c1 - c0 == 32:
+                    w = torch.cat([w, torch.zeros_like(w[:, :1])], 1)
+                return w.reshape(w.shape[0], -1).to(torch.bfloat16).contiguous()
+
+            def pull(j, c0, c1):
+                w = ws[j - 1].detach().float()[:, c0:c1]
+                return w.permute(0, 2, 3, 1).reshape(w.shape[0], 9, c1 - c0).to(torch.bfloat16).contiguous()
+            return [slab((2, 3), c, c + g), slab((4, 5), c, c + 2 * g), slab((4, 5), c + 2 * g, c + 3 * g),
+                    pull(3, c + g, c + 2 * g), pull(5, c + 3 * g, c + 4 * g)]
+        return self._packs.get_multi([cv.weight for cv in convs], build, "pair")
+
+    def _growth_pair(self, buf, part, B, H, W):
+        """x0 pushed as in the hybrid form; then every g-slab is read with N = 64 where two layers consume it:
+        g1 -> (finish g2, add into P3); L3 pulls g2 only; g1g2 -> (add into P4, P5); g3 -> (finish g4, add into P5); L5 pulls g4
+        only.  12 slab-k-steps per tap on the shared-memory-bound N <= 64 path instead of 20, for 512 B/px more partial traffic."""
+        w, pw = self._push_packs(), self._pair_packs()
+        b = [getattr(self, f"Dcov{i}").bias.detach() for i in range(1, 6)]
+        c, g, ld = self.in_ch, self.growth, buf.shape[-1]
+        Pn = lambda off: dict(bias=None, partial_in=None, dst=part, coff_dst=off, relu=False)
+        Pa = lambda off: dict(bias=None, partial_in=part, coff_partial_in=off, dst=part, coff_dst=off, relu=False)
+        Fin = lambda bias, poff, coff: dict(bias=bias, partial_in=part, coff_partial_in=poff, dst=buf, coff_dst=coff, relu=True)
+        pull = lambda wj, bj, soff, doff, poff: ops.conv(buf, wj, bj, B=B, H=H, W=W, Cin=g, ld_src=ld, src_coff=soff, KH=3, KW=3, pad=2,
+                                                         dil=2, Cout=g, act=ACT_RELU, out=buf.view(-1, ld), ld_dst=ld, dst_coff=doff,
+                                                         pre_add=part.view(-1, part.shape[-1]), pre_coff=poff, entry="segmif_conv3x3_tc_fwd")
+        ops.drdb_push(buf, w[0], B, H, W, 0, c, [dict(bias=b[0], partial_in=None, dst=buf, coff_dst=c, relu=True), Pn(0), Pn(g)])
+        ops.drdb_push(buf, w[1], B, H, W, 0, c, [Pn(2 * g), Pn(3 * g)])
+        ops.drdb_push(buf, pw[0], B, H, W, c, g, [Fin(b[1], 0, c + g), Pa(g)])                     # g1 -> g2, P3
+        ops.drdb_push(buf, pw[1], B, H, W, c, 2 * g, [Pa(2 * g), Pa(3 * g)])                       # g1 g2 -> P4, P5
+        pull(pw[3], b[2], c + g, c + 2 * g, g)                                                    # L3 over g2 -> g3
+        ops.drdb_push(buf, pw[2], B, H, W, c + 2 * g, g, [Fin(b[3], 2 * g, c + 3 * g), Pa(3 * g)])  # g3 -> g4, P5
+        pull(pw[4], b[4], c + 3 * g, c + 4 * g, 3 * g)                                            # L5 over g4 -> g5
+
     @staticmethod
     def _df_words(B, H):
         from .. import _lib
@@ -290,7 +334,7 @@ class DRDB(nn.Module):
                                                and self._df_flags.device == buf.device and self._df_flags.numel() == self._df_words(B, H) else None)
             return out
         if partials is not None and DRDB.MODE != "pull" and self.in_ch == 64 and self.growth == 32:
-            (self._growth_push if DRDB.MODE == "push" else self._growth_hybrid)(buf, partials, B, H, W)
+            {"push": self._growth_push, "pair": self._growth_pair}.get(DRDB.MODE, self._growth_hybrid)(buf, partials, B, H, W)
             cin = self.total
         for i in range(1, 6) if cin == self.in_ch else ():
             cv = getattr(self, f"Dcov{i}")

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--width", type=int, default=640)
     ap.add_argument("--splits", default="")
     ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--dataflow", type=int, default=0, help="1: also time the concurrent (dataflow) form")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     fus = synth.load_synthetic(Fusion_Network3_ac(), 0).eval().to(dev)
@@ -77,10 +78,20 @@ def main():
     ms_p = ev(lambda: d._growth_push(buf, part, B, H, W))
     print("growth only (push-all)", f"{ms_p:.3f} ms  {gf / ms_p / 1e9:.0f} TFLOP/s", flush=True)
     res["growth_hybrid_ms"], res["growth_push_ms"] = ms_g, ms_p
+    ms_q = ev(lambda: d._growth_pair(buf, part, B, H, W))
+    print("growth only (pair)", f"{ms_q:.3f} ms  {gf / ms_q / 1e9:.0f} TFLOP/s", flush=True)
+    res["growth_pair_ms"] = ms_q
+    with torch.no_grad():
+        d._growth_hybrid(buf, part, B, H, W)
+        ref_g = buf[..., 64:].float().clone()
+        d._growth_pair(buf, part, B, H, W)
+        err = float((buf[..., 64:].float() - ref_g).abs().max() / ref_g.abs().max())
+    print("pair vs hybrid growth slabs: max rel err", f"{err:.3e}", flush=True)
+    res["pair_vs_hybrid_rel_err"] = err
     ms_h, ref = run("hybrid")
     res["hybrid"] = {"ms": ms_h, "tflops": flops / ms_h / 1e9}
     print("hybrid  ", f"{ms_h:.3f} ms  {flops / ms_h / 1e9:.0f} TFLOP/s", flush=True)
-    splits = [None] + [[int(v) for v in s.split(",")] for s in a.splits.split(";") if s.strip()]
+    splits = ([None] if a.dataflow else []) + [[int(v) for v in s.split(",")] for s in a.splits.split(";") if s.strip()]
     for sp in splits:
         ms, got = run("dataflow", sp)
         same = bool((got == ref).all())

@@ -76,3 +76,24 @@ def analytic_images(batch=2, height=64, width=96, phases=(0.0, 0.9, 2.1)):
         img = np.stack([0.5 + 0.5 * np.sin(0.13 * x + 0.07 * y * (b + 1) + phi) for b in range(batch)])
         out.append(torch.from_numpy(img[:, None].astype(np.float32)))
     return out
+
+
+def synth_decoded_sample(seed, h, w, n_class=9, ignore_frac=0.03):
+    """One decoded training sample as the reference's dataset class holds it after imread (datasets/voc_fusion3.py:36-55):
+    uint8 infrared [h, w], visible [h, w, 3], mask [h, w], label [h, w] (numpy).  The label is made of rectangles, so crop
+    windows dominated by one class (the retry branch of random_crop2) and windows of ignore_index both occur; half of the
+    visible image is quantised / grey so every HSV sector and the s == 0 path are hit."""
+    rs = np.random.RandomState(seed)
+    ir = rs.randint(0, 256, size=(h, w)).astype(np.uint8)
+    vis = rs.randint(0, 256, size=(h, w, 3)).astype(np.uint8)
+    vis[: h // 2] = (vis[: h // 2] // 64) * 64
+    vis[:, : w // 4, 1] = vis[:, : w // 4, 0]
+    vis[:, : w // 8, 2] = vis[:, : w // 8, 0]
+    mask = (rs.rand(h, w) > 0.7).astype(np.uint8) * 255
+    label = np.zeros((h, w), np.uint8)
+    for _ in range(6):
+        y0, x0 = rs.randint(0, h), rs.randint(0, w)
+        y1, x1 = min(h, y0 + rs.randint(4, h)), min(w, x0 + rs.randint(4, w))
+        label[y0:y1, x0:x1] = rs.randint(0, n_class)
+    label[rs.rand(h, w) < ignore_frac] = 255
+    return ir, vis, mask, label

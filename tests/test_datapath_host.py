@@ -76,6 +76,13 @@ def test_distortion_program_matches_oracle_dtype_state_machine():
             assert len(ops) <= _lib.DP_MAX_OPS
 
 
+def test_product_and_oracle_synthesise_the_same_samples():
+    from segmif_b200 import synth
+    for seed, h, w in ((0, 48, 64), (7, 60, 80), (1003, 480, 640)):
+        for a, b in zip(synth.synth_decoded_sample(seed, h, w), do.synth_sample(seed, h, w)):
+            assert a.dtype == b.dtype and np.array_equal(a, b)
+
+
 def test_descriptor_layout_matches_header():
     """ctypes mirror vs include/segmif_b200.h (compiled with the host compiler)."""
     import os

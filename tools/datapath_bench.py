@@ -17,11 +17,10 @@ sys.path.insert(0, ROOT)
 
 
 def measure(batch=32, crop=512, h=480, w=640, iters=20, warm=3, cpu_samples=6, shared_rng=False):
-    from oracle import data_oracle as do                      # synthetic decoded samples (test infrastructure; inputs only)
-    from segmif_b200 import _lib
+    from segmif_b200 import _lib, synth
     from segmif_b200.datasets import DeviceTransforms, Rng
     dev = torch.device("cuda", 0)
-    host_samples = [do.synth_sample(1000 + k, h, w) for k in range(batch)]
+    host_samples = [synth.synth_decoded_sample(1000 + k, h, w) for k in range(batch)]
     samples = [tuple(torch.from_numpy(a).to(dev) for a in s) for s in host_samples]
     tf = DeviceTransforms(crop_size=crop)
     rngs = Rng.seeded(1) if shared_rng else [Rng.seeded(k) for k in range(batch)]
@@ -45,6 +44,7 @@ def measure(batch=32, crop=512, h=480, w=640, iters=20, warm=3, cpu_samples=6, s
            "entry_point_calls_per_batch": (_lib.launch_count - l0) // iters,
            "algorithmic_bytes_per_sample": bytes_per_sample, "achieved_GBps_wall": batch * bytes_per_sample / wall / 1e9}
     if cpu_samples:
+        from oracle import data_oracle as do                  # cpu_baseline leg only: the reference / its restatement as the thing timed
         try:
             from oracle import ref_shim
             ref = ref_shim.load_reference_datapath()

@@ -1,9 +1,9 @@
 import sys, torch
 sys.path.insert(0, '/root/repo')
-from oracle import data_oracle as do
+from segmif_b200 import synth
 from segmif_b200.datasets import DeviceTransforms, Rng
 dev = torch.device("cuda", 0)
-hs = [do.synth_sample(1000 + k, 480, 640) for k in range(32)]
+hs = [synth.synth_decoded_sample(1000 + k, 480, 640) for k in range(32)]
 samples = [tuple(torch.from_numpy(a).to(dev) for a in s) for s in hs]
 tf = DeviceTransforms(crop_size=512)
 rngs = [Rng.seeded(k) for k in range(32)]

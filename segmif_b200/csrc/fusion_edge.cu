@@ -11,7 +11,16 @@ namespace segmif {
 // version reloaded the 72 weights + bias for every 4 pixels and reached 1.7 TB/s of stores; this one amortises them over
 // 4 * kIn1Rows pixels.  Requires Cout == 64 (8 groups) for full warps; other widths use more warps per pixel block.
 constexpr int kIn1Rows = 16;
-__global__ void __launch_bounds__(256) conv3x3_in1_kernel(const float* __restrict__ plane, int64_t bstride,
+// packed fp32 pairs (FFMA2): two output channels per issue slot; same roundings as scalar fmaf
+__device__ __forceinline__ float2 in1_fma2(float2 a, float2 b, float2 c) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
+                     rc = *reinterpret_cast<unsigned long long*>(&c), rd;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  return *reinterpret_cast<float2*>(&rd);
+}
+// Round 2: 146 registers gave ONE 256-thread block per SM (12 % occupancy, issue-active 48 %: profiles/r2_ncu_misc_summary.csv);
+// capped at 128 for two blocks per SM, and the 72 FMAs per pixel and channel group issued as 36 FFMA2.
+__global__ void __launch_bounds__(256, 2) conv3x3_in1_kernel(const float* __restrict__ plane, int64_t bstride,
                                                           const float* __restrict__ w, const float* __restrict__ bias,
                                                           const float* __restrict__ alpha_p, bf16* __restrict__ dst,
                                                           int ld_dst, int dst_coff, int B, int H, int W, int Cout) {
@@ -35,10 +44,19 @@ __global__ void __launch_bounds__(256) conv3x3_in1_kernel(const float* __restric
   if ((lane & 7) >= gpw || grp >= ngroups) return;
   const int c = grp * 8;
   const float alpha = *alpha_p;
-  float wr[9][8], bs[8];
-  load8(bias + c, bs);
+  float2 wr[9][4], bs[4];
+  {
+    float t8[8];
+    load8(bias + c, t8);
 #pragma unroll
-  for (int t = 0; t < 9; ++t) load8(w + t * Cout + c, wr[t]);
+    for (int j = 0; j < 4; ++j) bs[j] = make_float2(t8[2 * j], t8[2 * j + 1]);
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      load8(w + t * Cout + c, t8);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) wr[t][j] = make_float2(t8[2 * j], t8[2 * j + 1]);
+    }
+  }
   const int x0 = xb * 16 + q * 4;
   const float* src = plane + b * bstride;
   const int y_begin = ys * kIn1Rows, y_end = min(H, y_begin + kIn1Rows);
@@ -58,19 +76,23 @@ __global__ void __launch_bounds__(256) conv3x3_in1_kernel(const float* __restric
     for (int i = 0; i < 4; ++i) {
       const int x = x0 + i;
       if (x >= W) break;
-      float acc[8];
+      float2 a2[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = bs[j];
+      for (int j = 0; j < 4; ++j) a2[j] = bs[j];
 #pragma unroll
       for (int r = 0; r < 3; ++r)
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
-          const float v = in[r][i + kx];
+          const float2 v = make_float2(in[r][i + kx], in[r][i + kx]);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wr[r * 3 + kx][j], acc[j]);
+          for (int j = 0; j < 4; ++j) a2[j] = in1_fma2(v, wr[r * 3 + kx][j], a2[j]);
         }
+      float acc[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = acc[j] >= 0.f ? acc[j] : alpha * acc[j];
+      for (int j = 0; j < 4; ++j) {
+        acc[2 * j] = a2[j].x >= 0.f ? a2[j].x : alpha * a2[j].x;
+        acc[2 * j + 1] = a2[j].y >= 0.f ? a2[j].y : alpha * a2[j].y;
+      }
       store8(dst + ((b * H + y) * W + x) * ld_dst + dst_coff + c, acc);
     }
 #pragma unroll

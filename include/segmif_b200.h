@@ -555,7 +555,7 @@ int segmif_ew2(const float* x, const float* y, float a, float b, int mode, float
 #define SEGMIF_DP_OP_SATURATION 1   /* hsv[..., 1] = convert(hsv[..., 1], alpha)                                    :332-341 */
 #define SEGMIF_DP_OP_HUE 2          /* hsv[..., 0] = (int(hsv[..., 0]) + delta) % 180                                :343-351 */
 typedef struct {
-  const unsigned char* ir;     /* decoded planes in device memory: infrared [H,W], visible [H,W,3], mask [H,W], label [H,W] */
+  const unsigned char* ir;     /* decoded planes in device memory: infrared [H,W], visible [H,W,3], mask [H,W] or [H,W,3], label [H,W] */
   const unsigned char* vis;
   const unsigned char* mask;
   const unsigned char* label;
@@ -574,12 +574,13 @@ typedef struct {
   float op_alpha[SEGMIF_DP_MAX_OPS];
   float op_beta[SEGMIF_DP_MAX_OPS];
   int32_t ks_x, ks_y;          /* Pillow ksize per axis: ceil(max(in/out, 1)) * 2 + 1 */
+  int32_t mask_c, reserved;    /* mask channels: 1 = plane replicated to three (voc_fusion3.py:46-48), 3 = image (voc_fusion2.py:46) */
   int32_t roi_x0, roi_x1, roi_y0, roi_y1; /* part of the resized image the kept window touches (unflipped coordinates) */
   int32_t src_y0, src_y1;      /* source rows the vertical pass needs for roi_y0..roi_y1 */
   int64_t tab_off;             /* int32 elements into table_arena: 2 nw + nw ks_x + 2 nh + nh ks_y + nw + nh per resized sample */
   /* uint8 intermediates use a row pitch p16(w) = (w + 15) & ~15; offsets are multiples of 16 and the arenas 16-byte aligned */
-  int64_t tmp_off;             /* bytes into tmp_arena:     5 (src_y1 - src_y0) p16(roi_x1 - roi_x0) */
-  int64_t rs_off;              /* bytes into resized_arena: 5 (roi_y1 - roi_y0) p16(roi_x1 - roi_x0) */
+  int64_t tmp_off;             /* bytes into tmp_arena:     (4 + mask_c) (src_y1 - src_y0) p16(roi_x1 - roi_x0) */
+  int64_t rs_off;              /* bytes into resized_arena: (4 + mask_c) (roi_y1 - roi_y0) p16(roi_x1 - roi_x0) */
   int64_t lab_off;             /* bytes into label_arena:   PH p16(PW) */
 } segmif_dp_sample;
 /* label stage: coefficient / index tables, the label canvas, and for each candidate window stats[n][10][3] = {number of

@@ -308,7 +308,7 @@ def transforms(image, image_vis, image_mask, label, rng, aug=True, rescale_range
 
 
 # --------------------------------------------------------------------------------------------------- seeded synthetic samples
-def synth_sample(seed, h, w, n_class=9, ignore_frac=0.03):
+def synth_sample(seed, h, w, n_class=9, ignore_frac=0.03, mask_channels=1):
     """One decoded training sample as the dataset class holds it after imread (voc_fusion3.py:36-55): uint8 infrared H x W,
     visible H x W x 3, mask H x W, label H x W.  The label is made of rectangles so that crop windows dominated by one class
     (the retry branch of random_crop2) and windows of ignore_index both occur."""
@@ -326,9 +326,12 @@ def synth_sample(seed, h, w, n_class=9, ignore_frac=0.03):
         y1, x1 = min(h, y0 + rs.randint(4, h)), min(w, x0 + rs.randint(4, w))
         label[y0:y1, x0:x1] = rs.randint(0, n_class)
     label[rs.rand(h, w) < ignore_frac] = 255
+    if mask_channels == 3:          # the fused RGB image train_seg reads back as its "mask" (voc_fusion2.py:44-48); own stream
+        mask = np.random.RandomState(seed + 7919).randint(0, 256, size=(h, w, 3)).astype(np.uint8)
     return ir, vis, mask, label
 
 
 def dataset_views(ir, vis, mask):
-    """voc_fusion3.py:39-48: single-channel planes replicated to three channels."""
-    return np.repeat(ir[:, :, None], 3, 2), vis, np.repeat(mask[:, :, None], 3, 2)
+    """voc_fusion3.py:39-48: single-channel planes replicated to three channels; voc_fusion2.py:44-48 keeps a three-channel
+    mask image as it is."""
+    return np.repeat(ir[:, :, None], 3, 2), vis, (np.repeat(mask[:, :, None], 3, 2) if mask.ndim == 2 else mask)

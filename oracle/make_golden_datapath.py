@@ -20,11 +20,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 REF = os.environ.get("SEGMIF_REFERENCE", "/root/reference")
 
+MASK3 = {16, 17, 18, 19}       # cases whose mask is an H x W x 3 image (train_seg's dataset, voc_fusion2.py:44-48)
 CASES = [  # (seed, h, w, crop, rescale_range)
     (0, 48, 64, 40, (0.5, 2.0)), (1, 48, 64, 40, (0.5, 2.0)), (2, 48, 64, 40, (0.5, 2.0)), (3, 48, 64, 40, (0.5, 2.0)),
     (4, 60, 80, 64, (0.5, 2.0)), (5, 60, 80, 64, (0.5, 2.0)), (6, 60, 80, 32, (0.5, 2.0)), (7, 60, 80, 32, (0.5, 2.0)),
     (8, 37, 53, 48, (0.5, 2.0)), (9, 37, 53, 48, (0.5, 2.0)), (10, 96, 72, 56, (0.75, 1.25)), (11, 96, 72, 56, (0.75, 1.25)),
     (12, 48, 64, 40, None), (13, 48, 64, 40, None), (14, 48, 64, 40, None), (15, 48, 64, 40, None),
+    (16, 48, 64, 40, (0.5, 2.0)), (17, 60, 80, 64, (0.5, 2.0)), (18, 37, 53, 48, (0.5, 2.0)), (19, 48, 64, 40, None),
 ]
 
 
@@ -45,9 +47,9 @@ def main():
     from PIL import Image
     from oracle import data_oracle as do
     imutils, voc = load_reference()
-    out = {"cases": np.array([(s, h, w, c, -1 if r is None else r[0], -1 if r is None else r[1]) for s, h, w, c, r in CASES], np.float64)}
+    out = {"cases": np.array([(s, h, w, c, -1 if r is None else r[0], -1 if r is None else r[1], 3 if s in MASK3 else 1) for s, h, w, c, r in CASES], np.float64)}
     for seed, h, w, crop, rr in CASES:
-        ir, vis, mask, label = do.synth_sample(seed, h, w)
+        ir, vis, mask, label = do.synth_sample(seed, h, w, mask_channels=3 if seed in MASK3 else 1)
         image, image_vis, image_mask = do.dataset_views(ir, vis, mask)
         ds = object.__new__(voc.VOC12SegDataset)
         ds.aug, ds.ignore_index, ds.resize_range, ds.rescale_range, ds.crop_size, ds.img_fliplr = True, 255, [512, 640], rr, crop, True

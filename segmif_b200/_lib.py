@@ -93,7 +93,7 @@ class DpSample(ctypes.Structure):
                 ("cand_hs", c_int * 10), ("cand_ws", c_int * 10), ("hs", c_int), ("ws", c_int), ("n_ops", c_int),
                 ("op_kind", c_int * DP_MAX_OPS), ("op_u8", c_int * DP_MAX_OPS), ("op_delta", c_int * DP_MAX_OPS),
                 ("op_alpha", c_float * DP_MAX_OPS), ("op_beta", c_float * DP_MAX_OPS),
-                ("ks_x", c_int), ("ks_y", c_int), ("roi_x0", c_int), ("roi_x1", c_int), ("roi_y0", c_int), ("roi_y1", c_int),
+                ("ks_x", c_int), ("ks_y", c_int), ("mask_c", c_int), ("reserved", c_int), ("roi_x0", c_int), ("roi_x1", c_int), ("roi_y0", c_int), ("roi_y1", c_int),
                 ("src_y0", c_int), ("src_y1", c_int),
                 ("tab_off", c_int64), ("tmp_off", c_int64), ("rs_off", c_int64), ("lab_off", c_int64)]
 

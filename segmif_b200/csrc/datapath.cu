@@ -116,7 +116,7 @@ __device__ __forceinline__ uint8_t clip8(int v) {
 __host__ __device__ __forceinline__ int pitch16(int w) { return (w + 15) & ~15; }
 
 // Horizontal pass over the source rows the vertical pass will need [src_y0, src_y1) and the output columns [roi_x0, roi_x1):
-// tmp is PLANAR uint8 [5][rows][pitch] (ir, vis c0, vis c1, vis c2, mask).  Four output columns per thread.
+// tmp is PLANAR uint8 [4 + mask_c][rows][pitch] (ir, vis c0, vis c1, vis c2, mask c0 [, c1, c2]).  Four output columns per thread.
 // grid (ceil(pitch/4/128), rows, n).
 __global__ void __launch_bounds__(128) resize_h_kernel(const segmif_dp_sample* __restrict__ samples, const int32_t* __restrict__ arena,
                                                        uint8_t* __restrict__ tmp_arena) {
@@ -130,7 +130,8 @@ __global__ void __launch_bounds__(128) resize_h_kernel(const segmif_dp_sample* _
   const int32_t* xmin_t = tab(arena, s, 0);
   const int32_t* xcnt_t = tab(arena, s, 1);
   const int32_t* k_t = tab(arena, s, 2);
-  uint32_t pk[5] = {0u, 0u, 0u, 0u, 0u};
+  const int mc = s.mask_c;                 // 1: plane (voc_fusion3.py), 3: H x W x 3 image (voc_fusion2.py)
+  uint32_t pk[7] = {0u, 0u, 0u, 0u, 0u, 0u, 0u};
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     if (x4 + q >= roi_w) break;
@@ -139,29 +140,36 @@ __global__ void __launch_bounds__(128) resize_h_kernel(const segmif_dp_sample* _
     const int32_t* k = k_t + (int64_t)xx * s.ks_x;
     const uint8_t* ir = s.ir + (int64_t)y * s.W + lo;
     const uint8_t* vis = s.vis + ((int64_t)y * s.W + lo) * 3;
-    const uint8_t* mk = s.mask + (int64_t)y * s.W + lo;
-    int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0, a3 = a0, a4 = a0;
+    const uint8_t* mk = s.mask + ((int64_t)y * s.W + lo) * mc;
+    int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0, a3 = a0, a4 = a0, a5 = a0, a6 = a0;
     for (int j = 0; j < n; ++j) {
       const int kj = k[j];
       a0 += kj * ir[j];
       a1 += kj * vis[3 * j];
       a2 += kj * vis[3 * j + 1];
       a3 += kj * vis[3 * j + 2];
-      a4 += kj * mk[j];
+      a4 += kj * mk[mc * j];
+      if (mc == 3) {
+        a5 += kj * mk[3 * j + 1];
+        a6 += kj * mk[3 * j + 2];
+      }
     }
     pk[0] |= (uint32_t)clip8(a0) << (8 * q);
     pk[1] |= (uint32_t)clip8(a1) << (8 * q);
     pk[2] |= (uint32_t)clip8(a2) << (8 * q);
     pk[3] |= (uint32_t)clip8(a3) << (8 * q);
     pk[4] |= (uint32_t)clip8(a4) << (8 * q);
+    pk[5] |= (uint32_t)clip8(a5) << (8 * q);
+    pk[6] |= (uint32_t)clip8(a6) << (8 * q);
   }
   uint8_t* t = tmp_arena + s.tmp_off + (int64_t)r * pitch + x4;
   const int64_t plane = (int64_t)rows * pitch;
 #pragma unroll
-  for (int c = 0; c < 5; ++c) *reinterpret_cast<uint32_t*>(t + c * plane) = pk[c];
+  for (int c = 0; c < 7; ++c)
+    if (c < 4 + mc) *reinterpret_cast<uint32_t*>(t + c * plane) = pk[c];
 }
 
-// Vertical pass: resized region, planar uint8 [5][roi_h][pitch], four columns per thread.  grid (ceil(pitch/4/128), roi_h, n).
+// Vertical pass: resized region, planar uint8 [4 + mask_c][roi_h][pitch], four columns per thread.  grid (ceil(pitch/4/128), roi_h, n).
 __global__ void __launch_bounds__(128) resize_v_kernel(const segmif_dp_sample* __restrict__ samples, const int32_t* __restrict__ arena,
                                                        const uint8_t* __restrict__ tmp_arena, uint8_t* __restrict__ rs_arena) {
   __shared__ segmif_dp_sample sh_sample;
@@ -177,7 +185,8 @@ __global__ void __launch_bounds__(128) resize_v_kernel(const segmif_dp_sample* _
   const uint8_t* t = tmp_arena + s.tmp_off + (int64_t)(lo - s.src_y0) * pitch + x4;
   uint8_t* o = rs_arena + s.rs_off + (int64_t)yo * pitch + x4;
 #pragma unroll
-  for (int c = 0; c < 5; ++c) {
+  for (int c = 0; c < 7; ++c) {
+    if (c >= 4 + s.mask_c) break;
     int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0, a3 = a0;
     for (int j = 0; j < n; ++j) {
       const uint32_t v = *reinterpret_cast<const uint32_t*>(t + c * tplane + (int64_t)j * pitch);
@@ -426,7 +435,7 @@ __global__ void __launch_bounds__(256) finish_kernel(const segmif_dp_sample* __r
   const uint8_t lab = lab_arena[s.lab_off + (int64_t)yp * pitch16(s.PW) + xp];
   out_label[(int64_t)blockIdx.z * n + i] = (float)lab;
   if (label_i64) label_i64[(int64_t)blockIdx.z * n + i] = (int64_t)lab;
-  float ir, mk;
+  float ir, mk[3];
   Px p;
   if (ys >= 0 && ys < s.nh && xs >= 0 && xs < s.nw) {
     const int xr = s.flip ? s.nw - 1 - xs : xs;
@@ -436,20 +445,24 @@ __global__ void __launch_bounds__(256) finish_kernel(const segmif_dp_sample* __r
       const uint8_t* q = rs_arena + s.rs_off + (int64_t)(ys - s.roi_y0) * pitch + (xr - s.roi_x0);
       ir = (float)q[0];
       p = Px{(float)q[plane], (float)q[2 * plane], (float)q[3 * plane]};
-      mk = (float)q[4 * plane];
+      mk[0] = (float)q[4 * plane];
+      mk[1] = s.mask_c == 3 ? (float)q[5 * plane] : mk[0];
+      mk[2] = s.mask_c == 3 ? (float)q[6 * plane] : mk[0];
     } else {
       const int64_t q = (int64_t)ys * s.W + xr;
       ir = (float)s.ir[q];
       p = Px{(float)s.vis[3 * q], (float)s.vis[3 * q + 1], (float)s.vis[3 * q + 2]};
-      mk = (float)s.mask[q];
+      mk[0] = (float)s.mask[q * s.mask_c];
+      mk[1] = s.mask_c == 3 ? (float)s.mask[q * 3 + 1] : mk[0];
+      mk[2] = s.mask_c == 3 ? (float)s.mask[q * 3 + 2] : mk[0];
     }
     p = photometric(p, s, div_tab, xs >= (s.nw / 8) * 8, xs >= (s.nw / 32) * 32);
     out_ir[o] = __fdiv_rn(ir, 255.f);
     out_ir[o + n] = __fdiv_rn(ir, 255.f);
     out_ir[o + 2 * n] = __fdiv_rn(ir, 255.f);
-    out_mask[o] = __fdiv_rn(mk, 255.f);
-    out_mask[o + n] = __fdiv_rn(mk, 255.f);
-    out_mask[o + 2 * n] = __fdiv_rn(mk, 255.f);
+    out_mask[o] = __fdiv_rn(mk[0], 255.f);
+    out_mask[o + n] = __fdiv_rn(mk[1], 255.f);
+    out_mask[o + 2 * n] = __fdiv_rn(mk[2], 255.f);
   } else {
     p = Px{mean0, mean1, mean2};
     const float m0 = __fdiv_rn(mean0, 255.f), m1 = __fdiv_rn(mean1, 255.f), m2 = __fdiv_rn(mean2, 255.f);
@@ -521,6 +534,7 @@ extern "C" int segmif_dp_image_stage(const segmif_dp_sample* samples_dev, const 
     const segmif_dp_sample& s = samples_host[i];
     SEGMIF_REQUIRE(s.hs >= 0 && s.hs + crop <= s.PH && s.ws >= 0 && s.ws + crop <= s.PW, "dp_image_stage: sample %d window outside the canvas", i);
     SEGMIF_REQUIRE(s.n_ops >= 0 && s.n_ops <= SEGMIF_DP_MAX_OPS, "dp_image_stage: sample %d has %d ops", i, s.n_ops);
+    SEGMIF_REQUIRE(s.mask_c == 1 || s.mask_c == 3, "dp_image_stage: sample %d mask_c=%d must be 1 or 3", i, s.mask_c);
     if (!s.resized) continue;
     SEGMIF_REQUIRE(tmp_arena && resized_arena, "dp_image_stage: resize workspaces missing");
     SEGMIF_REQUIRE(0 <= s.roi_x0 && s.roi_x0 < s.roi_x1 && s.roi_x1 <= s.nw && 0 <= s.roi_y0 && s.roi_y0 < s.roi_y1 && s.roi_y1 <= s.nh &&

@@ -114,9 +114,10 @@ class DeviceTransforms:
 
     __call__(samples, rng) -> image [n,3,c,c], image_vis [n,3,c,c], image_mask [n,3,c,c] (fp32, CHW, / 255.0) and label
     [n,c,c] (fp32 like the reference's pad_label; `label_int64=True` adds the int64 tensor the loss consumes).
-      samples: list of (ir uint8 [H,W], vis uint8 [H,W,3], mask uint8 [H,W], label uint8 [H,W]) CUDA tensors -- the single-
-               channel planes are NOT replicated to three channels on the way in (voc_fusion3.py:40-48 does; the result is the
-               same three identical planes, except over the canvas where each channel takes its mean_rgb value).
+      samples: list of (ir uint8 [H,W], vis uint8 [H,W,3], mask uint8 [H,W] or [H,W,3], label uint8 [H,W]) CUDA tensors -- the
+               single-channel planes are NOT replicated to three channels on the way in (voc_fusion3.py:40-48 does; the result
+               is the same three identical planes, except over the canvas where each channel takes its mean_rgb value).  A
+               three-channel mask is the fused RGB image train_seg reads back (voc_fusion2.py:44-48).
       rng:     one Rng shared by all samples (the reference's worker semantics: sample k+1 continues where sample k stopped;
                costs one device->host read of 30 integers per sample) or a list with one Rng per sample (one read per batch).
     """
@@ -137,6 +138,7 @@ class DeviceTransforms:
         h, w = label.shape
         s.ir, s.vis, s.mask, s.label = ir.data_ptr(), vis.data_ptr(), mask.data_ptr(), label.data_ptr()
         s.H, s.W = h, w
+        s.mask_c = 1 if mask.dim() == 2 else 3
         if self.rescale_range:
             ratio = rng.py.uniform(self.rescale_range[0], self.rescale_range[1])      # imutils.py:40
             s.nw, s.nh, s.resized = int(ratio * w), int(ratio * h), 1                 # :73
@@ -191,7 +193,7 @@ class DeviceTransforms:
         for ir, vis, mask, label in samples:
             _check_plane(label, 2, "label")
             h, w = label.shape
-            for t, nd, what in ((ir, 2, "infrared"), (vis, 3, "visible"), (mask, 2, "mask")):
+            for t, nd, what in ((ir, 2, "infrared"), (vis, 3, "visible"), (mask, mask.dim() if isinstance(mask, torch.Tensor) and mask.dim() == 3 else 2, "mask")):
                 _check_plane(t, nd, what)
                 if tuple(t.shape[:2]) != (h, w) or (nd == 3 and t.shape[2] != 3):
                     raise ValueError(f"segmif_b200.datasets: {what} has shape {tuple(t.shape)}, label is {(h, w)}")
@@ -247,8 +249,8 @@ class DeviceTransforms:
             s = host[k]
             if s.resized:
                 s.tmp_off, s.rs_off = tmp_bytes, rs_bytes
-                tmp_bytes += 5 * (s.src_y1 - s.src_y0) * _p16(s.roi_x1 - s.roi_x0)
-                rs_bytes += 5 * (s.roi_y1 - s.roi_y0) * _p16(s.roi_x1 - s.roi_x0)
+                tmp_bytes += (4 + s.mask_c) * (s.src_y1 - s.src_y0) * _p16(s.roi_x1 - s.roi_x0)
+                rs_bytes += (4 + s.mask_c) * (s.roi_y1 - s.roi_y0) * _p16(s.roi_x1 - s.roi_x0)
         tmp = torch.empty(max(tmp_bytes, 1), dtype=torch.uint8, device=dev)
         rs = torch.empty(max(rs_bytes, 1), dtype=torch.uint8, device=dev)
         dev_t.copy_(host_t, non_blocking=False)

@@ -25,11 +25,13 @@ def _imread(path):
 
 
 class VOC12Dataset:
+    MASK_DIR = "Mask2"             # voc_fusion3.py:27; datasets/voc_fusion2.py overrides it with "Mask" (voc_fusion2.py:27)
+
     def __init__(self, root_dir=None, name_list_dir=None, split="train", stage="train", device="cuda"):
         self.root_dir, self.stage, self.device = root_dir, stage, torch.device(device)
         self.img_dir = os.path.join(root_dir, "Infrared")
         self.img_dir_vis = os.path.join(root_dir, "Visible")
-        self.img_dir_mask = os.path.join(root_dir, "Mask2")
+        self.img_dir_mask = os.path.join(root_dir, self.MASK_DIR)
         self.label_dir = os.path.join(root_dir, "Label")
         self.name_list_dir = os.path.join(name_list_dir, split + ".txt")
         self.name_list = np.atleast_1d(load_img_name_list(self.name_list_dir))
@@ -40,7 +42,7 @@ class VOC12Dataset:
     def decode(self, idx):
         """voc_fusion3.py:34-60 without the three-fold replication of the single-channel planes: uint8 tensors on the device."""
         name = str(self.name_list[idx])
-        up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(self.device, non_blocking=True)
+        up = lambda a: torch.from_numpy(np.array(a, copy=True)).to(self.device, non_blocking=True)
         ir = _imread(os.path.join(self.img_dir, name + ".png"))
         vis = _imread(os.path.join(self.img_dir_vis, name + ".png"))
         mask = _imread(os.path.join(self.img_dir_mask, name + ".png"))

@@ -78,7 +78,7 @@ def analytic_images(batch=2, height=64, width=96, phases=(0.0, 0.9, 2.1)):
     return out
 
 
-def synth_decoded_sample(seed, h, w, n_class=9, ignore_frac=0.03):
+def synth_decoded_sample(seed, h, w, n_class=9, ignore_frac=0.03, mask_channels=1):
     """One decoded training sample as the reference's dataset class holds it after imread (datasets/voc_fusion3.py:36-55):
     uint8 infrared [h, w], visible [h, w, 3], mask [h, w], label [h, w] (numpy).  The label is made of rectangles, so crop
     windows dominated by one class (the retry branch of random_crop2) and windows of ignore_index both occur; half of the
@@ -96,4 +96,6 @@ def synth_decoded_sample(seed, h, w, n_class=9, ignore_frac=0.03):
         y1, x1 = min(h, y0 + rs.randint(4, h)), min(w, x0 + rs.randint(4, w))
         label[y0:y1, x0:x1] = rs.randint(0, n_class)
     label[rs.rand(h, w) < ignore_frac] = 255
+    if mask_channels == 3:          # the fused RGB image train_seg reads back as its "mask" (voc_fusion2.py:44-48); own stream
+        mask = np.random.RandomState(seed + 7919).randint(0, 256, size=(h, w, 3)).astype(np.uint8)
     return ir, vis, mask, label

@@ -79,8 +79,9 @@ def test_distortion_program_matches_oracle_dtype_state_machine():
 def test_product_and_oracle_synthesise_the_same_samples():
     from segmif_b200 import synth
     for seed, h, w in ((0, 48, 64), (7, 60, 80), (1003, 480, 640)):
-        for a, b in zip(synth.synth_decoded_sample(seed, h, w), do.synth_sample(seed, h, w)):
-            assert a.dtype == b.dtype and np.array_equal(a, b)
+        for mc in (1, 3):
+            for a, b in zip(synth.synth_decoded_sample(seed, h, w, mask_channels=mc), do.synth_sample(seed, h, w, mask_channels=mc)):
+                assert a.dtype == b.dtype and np.array_equal(a, b)
 
 
 def test_descriptor_layout_matches_header():

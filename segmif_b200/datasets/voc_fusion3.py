@@ -39,15 +39,19 @@ class VOC12Dataset:
     def __len__(self):
         return len(self.name_list)
 
-    def decode(self, idx):
-        """voc_fusion3.py:34-60 without the three-fold replication of the single-channel planes: uint8 tensors on the device."""
+    def decode_host(self, idx):
+        """voc_fusion3.py:34-60 without the three-fold replication of the single-channel planes: (name, ir, vis, mask, label)
+        as uint8 numpy arrays.  Thread-safe (DeviceLoader decodes a batch ahead in a thread pool)."""
         name = str(self.name_list[idx])
-        up = lambda a: torch.from_numpy(np.array(a, copy=True)).to(self.device, non_blocking=True)
-        ir = _imread(os.path.join(self.img_dir, name + ".png"))
-        vis = _imread(os.path.join(self.img_dir_vis, name + ".png"))
-        mask = _imread(os.path.join(self.img_dir_mask, name + ".png"))
-        label = _imread(os.path.join(self.label_dir, name + ".png"))
-        return name, up(ir), up(vis), up(mask), up(label)
+        rd = lambda d: np.array(_imread(os.path.join(d, name + ".png")), copy=True)
+        return name, rd(self.img_dir), rd(self.img_dir_vis), rd(self.img_dir_mask), rd(self.label_dir)
+
+    def upload(self, decoded):
+        """numpy planes of decode_host -> uint8 tensors on the device (on the CALLER's current stream)."""
+        return (decoded[0],) + tuple(torch.from_numpy(a).to(self.device, non_blocking=True) if isinstance(a, np.ndarray) else a for a in decoded[1:])
+
+    def decode(self, idx):
+        return self.upload(self.decode_host(idx))
 
 
 class VOC12SegDataset(VOC12Dataset):
@@ -65,9 +69,15 @@ class VOC12SegDataset(VOC12Dataset):
         """Decoded samples -> one device call.  Returns (names, image, image_vis, image_mask, label[, label_int64])."""
         if not self.aug:
             raise ValueError("segmif_b200.datasets: batch() needs aug=True (a common crop size); use __getitem__ for validation")
-        dec = [self.decode(i) for i in indices]
-        out = self.transforms([d[1:] for d in dec], rng if rng is not None else self.rng, label_int64=label_int64)
-        return ([d[0] for d in dec],) + tuple(out)
+        return self.transform_decoded([self.decode(i) for i in indices], rng, label_int64)
+
+    def transform_decoded(self, decoded, rng=None, label_int64=False):
+        """`decoded`: list of `decode()` results -> (names, image, image_vis, image_mask, label[, label_int64])."""
+        if not self.aug:
+            raise ValueError("segmif_b200.datasets: batching needs aug=True (a common crop size); use __getitem__ for validation")
+        decoded = [self.upload(d) for d in decoded]
+        out = self.transforms([d[1:] for d in decoded], rng if rng is not None else self.rng, label_int64=label_int64)
+        return ([d[0] for d in decoded],) + tuple(out)
 
     def __getitem__(self, idx):
         name, ir, vis, mask, label = self.decode(idx)

@@ -100,3 +100,21 @@ def test_descriptor_layout_matches_header():
         got = [int(x) for x in subprocess.check_output([os.path.join(d, "t")]).split()]
     S = _lib.DpSample
     assert got == [ctypes.sizeof(S), S.cand_hs.offset, S.op_alpha.offset, S.ks_x.offset, S.tab_off.offset]
+
+
+def test_device_loader_batching_order():
+    """DeviceLoader's index batching (sequential like train.py's loaders, drop_last, seeded shuffle) without touching a GPU."""
+    from segmif_b200.datasets import DeviceLoader
+
+    class Fake:
+        def __len__(self):
+            return 7
+    ld = DeviceLoader(Fake(), batch_size=3, drop_last=True)
+    assert len(ld) == 2 and list(ld._batches()) == [[0, 1, 2], [3, 4, 5]]
+    ld = DeviceLoader(Fake(), batch_size=3, drop_last=False)
+    assert len(ld) == 3 and list(ld._batches())[-1] == [6]
+    g = torch.Generator().manual_seed(3)
+    a = list(DeviceLoader(Fake(), batch_size=2, shuffle=True, generator=g)._batches())
+    g = torch.Generator().manual_seed(3)
+    assert a == list(DeviceLoader(Fake(), batch_size=2, shuffle=True, generator=g)._batches())
+    assert sorted(i for b in a for i in b) != [] and len({i for b in a for i in b}) == 6

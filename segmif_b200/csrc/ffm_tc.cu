@@ -55,8 +55,8 @@ __global__ void __launch_bounds__(kFfmTcThreads, 1) ffm_apply_tc_kernel(const __
   uint8_t* sW = smem;                              // [2][64][128 B]      Wu1, Wu2
   uint8_t* sM = sW + 2 * 8192;                     // [4][64][128 B]      Mz1, Mv1, Mz2, Mv2 of this image
   uint8_t* sX = sM + 4 * 8192;                     // [2 stages][2 streams][128][128 B]
-  uint8_t* sY = sX + 4 * kTileBytes;               // y3 tile
-  uint8_t* sU = sY + kTileBytes;                   // [2 streams] u tiles
+  uint8_t* sY = sX + 4 * kTileBytes;               // [2] y3 tiles: tile i+1's is interpolated while the MMAs of tile i run
+  uint8_t* sU = sY + 2 * kTileBytes;               // [2 streams] u tiles
   uint8_t* sO = sU + 2 * kTileBytes;               // [2 streams] output staging
   uint64_t* wfull = reinterpret_cast<uint64_t*>(sO + 2 * kTileBytes);
   uint64_t* xfull = wfull + 1;                     // [2]
@@ -82,7 +82,11 @@ __global__ void __launch_bounds__(kFfmTcThreads, 1) ffm_apply_tc_kernel(const __
     tc::mbar_init(tile_done, 8);
     tc::fence_barrier_init();
   }
-  if (warp == 1) tc::tmem_alloc(tmem_slot, 256);
+  // TMEM columns: [0,128) stage-1 accumulators of even tiles, [128,256) stage-2 accumulators, [256,384) stage-1 of odd tiles.
+  // Round 2: the stage-1 MMAs of tile i+1 are issued right behind the stage-2 MMAs of tile i (own accumulator buffer), and the
+  // epilogue warps interpolate y3 of tile i+1 while they wait for stage 2 of tile i -- per tile the chain was
+  // y3 | MMA1 -> epi 1 -> MMA2 -> epi 2 with the tensor pipe idle during both epilogues and the warps idle during both MMAs.
+  if (warp == 1) tc::tmem_alloc(tmem_slot, 512);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -111,31 +115,37 @@ __global__ void __launch_bounds__(kFfmTcThreads, 1) ffm_apply_tc_kernel(const __
     tc::mbar_wait(wfull, 0);
     uint64_t w_d = HI | (smem_u32(sW) >> 4), m_d = HI | (smem_u32(sM) >> 4), y_d = HI | (smem_u32(sY) >> 4), u_d = HI | (smem_u32(sU) >> 4);
     asm volatile("" : "+l"(w_d), "+l"(m_d), "+l"(y_d), "+l"(u_d));   // opaque bases: offsets stay immediates of one UIADD3.64
-    int it = 0;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+    auto stage1 = [&](int it) {                                     // U_s = X_s Wu_s^T of tile `it` into its accumulator buffer
       const int s = it & 1;
-      if (it > 0) tc::mbar_wait(tile_done, (it - 1) & 1);          // TMEM of the previous tile has been drained
       tc::mbar_wait(xfull + s, (it >> 1) & 1);
       tc::tc_fence_after();
       if (leader) {
         uint64_t x_d = HI | (smem_u32(sX + s * 2 * kTileBytes) >> 4);
         asm volatile("" : "+l"(x_d));
+        const uint32_t acc1 = tmem_base + (uint32_t)(s * 256);
 #pragma unroll
         for (int st = 0; st < 2; ++st)
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            tc::umma_bf16(tmem_base + st * 64, x_d + (uint64_t)(st * (kTileBytes >> 4) + k * 2), w_d + (uint64_t)(st * 512 + k * 2), idesc, k > 0 ? 1u : 0u);
+            tc::umma_bf16(acc1 + st * 64, x_d + (uint64_t)(st * (kTileBytes >> 4) + k * 2), w_d + (uint64_t)(st * 512 + k * 2), idesc, k > 0 ? 1u : 0u);
         tc::umma_commit(g1_full);
       }
       __syncwarp();
-      tc::mbar_wait(a2_ready, it & 1);
+    };
+    int it = 0;
+    if ((int)blockIdx.x < ntiles) stage1(0);
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      const int s = it & 1;
+      tc::mbar_wait(a2_ready, it & 1);                             // u tiles (and, transitively, this tile's y3) written
+      if (it > 0) tc::mbar_wait(tile_done, (it - 1) & 1);          // stage-2 accumulators of the previous tile have been drained
       tc::tc_fence_after();
       if (leader) {
+        const uint64_t y_ds = y_d + (uint64_t)(s * (kTileBytes >> 4));
 #pragma unroll
         for (int st = 0; st < 2; ++st) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)            // y3 Mz_s^T
-            tc::umma_bf16(tmem_base + 128 + st * 64, y_d + (uint64_t)(k * 2), m_d + (uint64_t)((2 * st) * 512 + k * 2), idesc, k > 0 ? 1u : 0u);
+            tc::umma_bf16(tmem_base + 128 + st * 64, y_ds + (uint64_t)(k * 2), m_d + (uint64_t)((2 * st) * 512 + k * 2), idesc, k > 0 ? 1u : 0u);
 #pragma unroll
           for (int k = 0; k < 4; ++k)            // + u_s Mv_s^T
             tc::umma_bf16(tmem_base + 128 + st * 64, u_d + (uint64_t)(st * (kTileBytes >> 4) + k * 2), m_d + (uint64_t)((2 * st + 1) * 512 + k * 2), idesc, 1u);
@@ -143,6 +153,7 @@ __global__ void __launch_bounds__(kFfmTcThreads, 1) ffm_apply_tc_kernel(const __
         tc::umma_commit(g2_full);
       }
       __syncwarp();
+      if (t + (int)gridDim.x < ntiles) stage1(it + 1);             // next tile's projection runs behind this tile's stage 2
     }
   } else {
     const int ew = warp - 2;                       // 0..7
@@ -155,11 +166,11 @@ __global__ void __launch_bounds__(kFfmTcThreads, 1) ffm_apply_tc_kernel(const __
     const CUtensorMap* tmO = st == 0 ? &tmO1 : &tmO2;
     uint8_t* sUs = sU + st * kTileBytes;
     uint8_t* sOs = sO + st * kTileBytes;
-    int it = 0;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-      const int s = it & 1;
+    // ---- y3 = relu(bilerp(Q[..., 0:64])) of tile `t` -> sY[buf].  Safe without a barrier: the last reader of sY[buf] was stage 2
+    // of the tile two iterations back, whose completion (g2_full) these warps have already waited for.
+    auto write_y3 = [&](int t, int buf) {
       const int64_t p0 = (int64_t)t * 128;
-      // ---- y3 = relu(bilerp(Q[..., 0:64])) -> sY (safe: stage 2 of the previous tile finished before its epilogue 2 ran)
+      uint8_t* sYb = sY + buf * kTileBytes;
       {
         const int pixel = et >> 1, half = et & 1;
         const int64_t p = p0 + pixel;
@@ -189,15 +200,21 @@ __global__ void __launch_bounds__(kFfmTcThreads, 1) ffm_apply_tc_kernel(const __
           for (int c = 0; c < 4; ++c) outv[c] = make_uint4(0, 0, 0, 0);
         }
 #pragma unroll
-        for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(sY + sw128_off(pixel, half * 4 + c)) = outv[c];
+        for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(sYb + sw128_off(pixel, half * 4 + c)) = outv[c];
       }
+    };
+    int it = 0;
+    if ((int)blockIdx.x < ntiles) write_y3(blockIdx.x, 0);
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      const int s = it & 1;
+      const int64_t p0 = (int64_t)t * 128;
       // ---- epilogue 1: u_s = relu(U_s + bu_s) -> sU_s
       tc::mbar_wait(g1_full, it & 1);
       tc::tc_fence_after();
 #pragma unroll
       for (int hc = 0; hc < 2; ++hc) {
         float v[32];
-        tc::tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(st * 64 + hc * 32), v);
+        tc::tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(s * 256 + st * 64 + hc * 32), v);
         const float4* bp = reinterpret_cast<const float4*>(a.bproj + st * 64 + hc * 32);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -215,6 +232,7 @@ __global__ void __launch_bounds__(kFfmTcThreads, 1) ffm_apply_tc_kernel(const __
       tc::fence_proxy_async();                     // sY / sU writes -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(a2_ready);
+      if (t + (int)gridDim.x < ntiles) write_y3(t + (int)gridDim.x, s ^ 1);      // overlaps stage 2 of this tile
       // ---- epilogue 2: + b_end + residual, LayerNorm over the 64 channels of this thread's pixel, TMA store
       tc::mbar_wait(g2_full, it & 1);
       tc::tc_fence_after();
@@ -272,7 +290,7 @@ __global__ void __launch_bounds__(kFfmTcThreads, 1) ffm_apply_tc_kernel(const __
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 1) tc::tmem_dealloc(tmem_base, 256);
+  if (warp == 1) tc::tmem_dealloc(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------------ pass 1 (Gram)
@@ -545,7 +563,7 @@ extern "C" int segmif_ffm_apply_lr_fwd(const void* x1, int ld1, int coff1, const
   FfmTcArgs a;
   a.q = reinterpret_cast<const bf16*>(q3); a.bproj = bproj; a.bend = bend; a.ln_g = ln_gamma; a.ln_b = ln_beta;
   a.eps = eps; a.sy = (float)qh / (float)H; a.sx = (float)qw / (float)W; a.qh = qh; a.qw = qw; a.H = H; a.W = W; a.HW = HW;
-  const size_t smem = 2 * 8192 + 4 * 8192 + 4 * kTileBytes + 3 * kTileBytes + 2 * kTileBytes + 10 * 8 + 16;
+  const size_t smem = 2 * 8192 + 4 * 8192 + 4 * kTileBytes + 4 * kTileBytes + 2 * kTileBytes + 10 * 8 + 16;
   static bool configured = false;
   static int sms = 148;
   if (!configured) {

@@ -165,8 +165,10 @@ __global__ void __launch_bounds__(kFaThreads, 1) sr_attention_fa_tc_kernel(const
             const int st = (kit + j) % kKvStages;
             const uint32_t vbase = smem_u32(sKV + st * KV_STAGE + K_BLOCK);
             const uint32_t pbase = smem_u32(sP + x * P_TILE);
+            const int ksteps = (j + 1) * 128 <= a.Nk ? 8 : (a.Nk - j * 128 + 15) >> 4;   // last block: valid keys only
 #pragma unroll
             for (int k = 0; k < 8; ++k) {                   // 16 keys per step: P columns (k / 4) block, (k % 4) * 32 B; V rows 16 k
+              if (k >= ksteps) break;
               const uint64_t pd = fa_kmajor_desc(pbase + (uint32_t)((k >> 2) * (128 * 128))) + (uint64_t)((k & 3) * 2);
               const uint64_t vd = fa_mnmajor_desc(vbase + (uint32_t)(k * 16 * 128));
               tc::umma_bf16(tmem_base + 256 + (uint32_t)(x * 64), pd, vd, idesc_o, (j | k) != 0 ? 1u : 0u);
@@ -199,12 +201,15 @@ __global__ void __launch_bounds__(kFaThreads, 1) sr_attention_fa_tc_kernel(const
         const int gidx = pl * nkb + j;
         const int kbase = j * 128;
         const bool full = kbase + 128 <= a.Nk;             // block-uniform: only the last block masks keys
+        // a partly filled last block is processed in 32-column steps up to the last valid key only (Nk = 300: 64 of 128
+        // columns); the PV MMAs of that block stop at the same place, so the untouched P columns are never read
+        const int cmax = full ? 128 : min(128, (a.Nk - kbase + 31) & ~31);
         tc::mbar_wait(s_full + x, gidx & 1);
         tc::tc_fence_after();
         // ---- block maximum (log2 domain)
         float bm = -INFINITY;
 #pragma unroll 1
-        for (int c = 0; c < 128; c += 32) {
+        for (int c = 0; c < cmax; c += 32) {
           float v[32];
           tc::tmem_ld32(ts + (uint32_t)c, v);
           if (full) {
@@ -241,7 +246,7 @@ __global__ void __launch_bounds__(kFaThreads, 1) sr_attention_fa_tc_kernel(const
         }
         // ---- P_j = exp2(s - m_ref) -> bf16 -> shared memory (K-major SW128, two 64-key blocks), running sum
 #pragma unroll 1
-        for (int c = 0; c < 128; c += 32) {
+        for (int c = 0; c < cmax; c += 32) {
           float v[32];
           tc::tmem_ld32(ts + (uint32_t)c, v);
           if (full) {

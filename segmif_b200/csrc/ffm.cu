@@ -116,9 +116,13 @@ __global__ void __launch_bounds__(kFfmThreads) ffm_gram_kernel(const bf16* __res
 //     head, column softmax (dim=-2)  ->  ctx[b][s][8][8][8] fp32
 __global__ void __launch_bounds__(256) ffm_ctx_kernel(const float* __restrict__ partials, int nchunk,
                                                       const float* __restrict__ wkv, float* __restrict__ ctx_out) {
-  __shared__ float G[4096];
-  __shared__ float T[4096];
-  __shared__ float lg[512];
+  // Round 2: Wk / Wv are staged in shared memory (the T = Wk G loop read one global weight per FMA: 70 us for this 24-block
+  // launch, two launches per step); summation orders unchanged, results bit-identical.
+  extern __shared__ __align__(16) float ctx_smem[];
+  float* G = ctx_smem;                 // [64][64]
+  float* T = G + 4096;                 // [64][64]
+  float* Wsh = T + 4096;               // [64][65]: Wk, then Wv (row pitch 65: the logits loop reads eight rows per warp)
+  float* lg = Wsh + 64 * 65;           // [512]
   const int s = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
   const float* pb = partials + ((int64_t)b * nchunk * 3 + s) * 4096;
   for (int idx = tid; idx < 4096; idx += 256) {
@@ -136,20 +140,24 @@ __global__ void __launch_bounds__(256) ffm_ctx_kernel(const float* __restrict__ 
   __syncthreads();
   const float* Wk = wkv + (int64_t)s * 128 * 64;
   const float* Wv = Wk + 64 * 64;
+  for (int idx = tid; idx < 4096; idx += 256) Wsh[(idx >> 6) * 65 + (idx & 63)] = Wk[idx];
+  __syncthreads();
   for (int idx = tid; idx < 4096; idx += 256) {       // T = Wk G_s
     const int r = idx >> 6, c = idx & 63;
     float a = 0.f;
 #pragma unroll 8
-    for (int k = 0; k < 64; ++k) a = fmaf(Wk[r * 64 + k], G[k * 64 + c], a);
+    for (int k = 0; k < 64; ++k) a = fmaf(Wsh[r * 65 + k], G[k * 64 + c], a);
     T[idx] = a;
   }
+  __syncthreads();
+  for (int idx = tid; idx < 4096; idx += 256) Wsh[(idx >> 6) * 65 + (idx & 63)] = Wv[idx];
   __syncthreads();
   const float scale = 0.35355339059327379f;           // 8^-1/2 (head_dim 8)
   for (int idx = tid; idx < 512; idx += 256) {        // logits[h][i][j] = scale * T[h8+i,:] . Wv[h8+j,:]
     const int h = idx >> 6, i = (idx >> 3) & 7, j = idx & 7;
     float a = 0.f;
 #pragma unroll 8
-    for (int c = 0; c < 64; ++c) a = fmaf(T[(h * 8 + i) * 64 + c], Wv[(h * 8 + j) * 64 + c], a);
+    for (int c = 0; c < 64; ++c) a = fmaf(T[(h * 8 + i) * 64 + c], Wsh[(h * 8 + j) * 65 + c], a);
     lg[idx] = a * scale;
   }
   __syncthreads();
@@ -360,7 +368,14 @@ extern "C" int segmif_ffm_ctx_fwd(const float* partials, int nchunk, const float
   SEGMIF_REQUIRE(partials && wkv && wend && folded && ctx_out, "ffm_ctx: null pointer (ctx_out [B,3,8,8,8] is required)");
   SEGMIF_REQUIRE(nchunk > 0 && B > 0, "ffm_ctx: bad sizes");
   cudaStream_t st = as_stream(stream);
-  ffm_ctx_kernel<<<dim3(3, B), 256, 0, st>>>(partials, nchunk, wkv, ctx_out);
+  constexpr int ctx_smem = (2 * 4096 + 64 * 65 + 512) * (int)sizeof(float);
+  static bool ctx_cfg = false;
+  if (!ctx_cfg) {
+    cudaError_t e = cudaFuncSetAttribute(ffm_ctx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx_smem);
+    if (e != cudaSuccess) { set_error("ffm_ctx: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SEGMIF_ERR_CUDA; }
+    ctx_cfg = true;
+  }
+  ffm_ctx_kernel<<<dim3(3, B), 256, ctx_smem, st>>>(partials, nchunk, wkv, ctx_out);
   int rc = check_launch("segmif_ffm_ctx_fwd");
   if (rc) return rc;
   ffm_fold_kernel<<<dim3(4, B), 256, 0, st>>>(ctx_out, wend, (bf16*)folded);

@@ -125,17 +125,30 @@ __global__ void __launch_bounds__(256) ffm_ctx_kernel(const float* __restrict__ 
   float* lg = Wsh + 64 * 65;           // [512]
   const int s = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
   const float* pb = partials + ((int64_t)b * nchunk * 3 + s) * 4096;
-  for (int idx = tid; idx < 4096; idx += 256) {
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  {
+    // Only 24 blocks run this kernel, so the reduction is latency bound: all 16 outputs of a thread advance together (64 loads
+    // in flight per thread instead of 4).  Per output the summation order is the one of round 1: four interleaved partial sums
+    // over the chunks, then (a0 + a1) + (a2 + a3).
+    float acc[16][4];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.f;
     int c = 0;
-    for (; c + 4 <= nchunk; c += 4) {        // four independent loads in flight, fixed summation order
-      a0 += pb[(int64_t)(c + 0) * 3 * 4096 + idx];
-      a1 += pb[(int64_t)(c + 1) * 3 * 4096 + idx];
-      a2 += pb[(int64_t)(c + 2) * 3 * 4096 + idx];
-      a3 += pb[(int64_t)(c + 3) * 3 * 4096 + idx];
+    for (; c + 4 <= nchunk; c += 4) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const float* q = pb + (int64_t)c * 3 * 4096 + tid + 256 * k;
+        acc[k][0] += q[0];
+        acc[k][1] += q[(int64_t)1 * 3 * 4096];
+        acc[k][2] += q[(int64_t)2 * 3 * 4096];
+        acc[k][3] += q[(int64_t)3 * 3 * 4096];
+      }
     }
-    for (; c < nchunk; ++c) a0 += pb[(int64_t)c * 3 * 4096 + idx];
-    G[idx] = (a0 + a1) + (a2 + a3);
+    for (; c < nchunk; ++c) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) acc[k][0] += pb[(int64_t)c * 3 * 4096 + tid + 256 * k];
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) G[tid + 256 * k] = (acc[k][0] + acc[k][1]) + (acc[k][2] + acc[k][3]);
   }
   __syncthreads();
   const float* Wk = wkv + (int64_t)s * 128 * 64;

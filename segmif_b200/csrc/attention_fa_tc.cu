@@ -38,6 +38,7 @@ struct FaArgs {
   bf16* out;
   float* lse;
   int ldo, heads, N, Nk, nkb, q_pairs;
+  int trim;            // 1: a partly filled last key block is processed up to its last valid key only (SEGMIF_FA_TRIM=0 disables)
   float scale_log2e;
 };
 
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(kFaThreads, 1) sr_attention_fa_tc_kernel(const
             const int st = (kit + j) % kKvStages;
             const uint32_t vbase = smem_u32(sKV + st * KV_STAGE + K_BLOCK);
             const uint32_t pbase = smem_u32(sP + x * P_TILE);
-            const int ksteps = (j + 1) * 128 <= a.Nk ? 8 : (a.Nk - j * 128 + 15) >> 4;   // last block: valid keys only
+            const int ksteps = ((j + 1) * 128 <= a.Nk || !a.trim) ? 8 : (a.Nk - j * 128 + 15) >> 4;   // last block: valid keys only
 #pragma unroll
             for (int k = 0; k < 8; ++k) {                   // 16 keys per step: P columns (k / 4) block, (k % 4) * 32 B; V rows 16 k
               if (k >= ksteps) break;
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(kFaThreads, 1) sr_attention_fa_tc_kernel(const
         const bool full = kbase + 128 <= a.Nk;             // block-uniform: only the last block masks keys
         // a partly filled last block is processed in 32-column steps up to the last valid key only (Nk = 300: 64 of 128
         // columns); the PV MMAs of that block stop at the same place, so the untouched P columns are never read
-        const int cmax = full ? 128 : min(128, (a.Nk - kbase + 31) & ~31);
+        const int cmax = (full || !a.trim) ? 128 : min(128, (a.Nk - kbase + 31) & ~31);
         tc::mbar_wait(s_full + x, gidx & 1);
         tc::tc_fence_after();
         // ---- block maximum (log2 domain)
@@ -342,6 +343,8 @@ int sr_attention_fa_tc(const void* q, int ldq, const void* k, const void* v, int
   FaArgs a;
   a.out = (bf16*)out; a.lse = lse; a.ldo = ldo; a.heads = heads; a.N = N; a.Nk = Nk;
   a.nkb = (Nk + 127) / 128; a.q_pairs = (N + 255) / 256; a.scale_log2e = scale * 1.4426950408889634f;
+  static const int trim = []() { const char* e = getenv("SEGMIF_FA_TRIM"); return (e && e[0] == '0') ? 0 : 1; }();
+  a.trim = trim;
   const size_t smem = (size_t)kKvStages * KV_STAGE + 2 * P_TILE + 2 * Q_TILE + 1024;
   static bool cfg = false;
   if (!cfg) {
